@@ -1,0 +1,96 @@
+"""``UNetSCN`` -- the 3D backbone of MM2D3D, on this package's ``scn`` modules.
+
+Drop-in for ``3d_net/scn_unet.py:90-126`` of the reference: same constructor arguments
+(``config.yaml:22-28``), same attributes (``in_channels``, ``out_channels``), same
+``forward([coords, feats]) -> [N, m]`` and the same module tree, so parameter names and shapes
+match a SparseConvNet checkpoint:
+
+    layer1 InputLayer(3, full_scale, mode=4)      layer4 BatchNormReLU(m)
+    layer2 SubmanifoldConvolution(in, m, 3)       layer5 OutputLayer
+    layer3 U-Net: per level  [BN-ReLU -> SMC]*reps, then (unless deepest)
+           ConcatTable{Identity | BN-ReLU -> Conv 2/2 -> deeper level -> BN-ReLU -> Deconv 2/2}
+           -> JoinTable -> [BN-ReLU -> SMC]*reps with the first one taking 2p planes
+
+The topology is described once as data (``level_plan``) and then materialised with whatever
+``scn``-shaped backend is passed in; tests pass the CPU oracle's module set to get the
+reference network, the default is the CUDA implementation in ``mm2d3d_b200.scn``.
+"""
+from __future__ import annotations
+
+import torch.nn as nn
+
+DIMENSION = 3
+
+
+def level_plan(planes, reps):
+    """Yield, shallow to deep, ``(p, p_next | None)`` with the (in, out) plane pairs of the
+    pre- and post-join blocks of each level (``scn_unet.py:55-84``)."""
+    plan = []
+    for lvl, p in enumerate(planes):
+        deeper = planes[lvl + 1] if lvl + 1 < len(planes) else None
+        pre = [(p, p)] * reps
+        post = [(2 * p if r == 0 else p, p) for r in range(reps)] if deeper is not None else []
+        plan.append({"planes": p, "deeper": deeper, "pre": pre, "post": post})
+    return plan
+
+
+def _append_block(scn, seq, a, b, residual, leakiness):
+    """One VGG (``scn_unet.py:48-53``) or pre-activation ResNet (``:36-47``) block."""
+    body = scn.Sequential()
+    body.add(scn.BatchNormLeakyReLU(a, leakiness=leakiness))
+    body.add(scn.SubmanifoldConvolution(DIMENSION, a, b, 3, False))
+    if not residual:
+        seq.add(body)
+        return
+    body.add(scn.BatchNormLeakyReLU(b, leakiness=leakiness))
+    body.add(scn.SubmanifoldConvolution(DIMENSION, b, b, 3, False))
+    shortcut = scn.Identity() if a == b else scn.NetworkInNetwork(a, b, False)
+    seq.add(scn.ConcatTable().add(shortcut).add(body))
+    seq.add(scn.AddTable())
+
+
+def build_unet(scn, reps, planes, residual_blocks=False, downsample=(2, 2), leakiness=0):
+    """Materialise the U-Net bottom-up (deepest level first) so no recursion is needed."""
+    plan = level_plan(list(planes), reps)
+    inner = None
+    for lvl in reversed(plan):
+        seq = scn.Sequential()
+        for a, b in lvl["pre"]:
+            _append_block(scn, seq, a, b, residual_blocks, leakiness)
+        if lvl["deeper"] is not None:
+            p, q = lvl["planes"], lvl["deeper"]
+            branch = scn.Sequential()
+            branch.add(scn.BatchNormLeakyReLU(p, leakiness=leakiness))
+            branch.add(scn.Convolution(DIMENSION, p, q, downsample[0], downsample[1], False))
+            branch.add(inner)
+            branch.add(scn.BatchNormLeakyReLU(q, leakiness=leakiness))
+            branch.add(scn.Deconvolution(DIMENSION, q, p, downsample[0], downsample[1], False))
+            seq.add(scn.ConcatTable().add(scn.Identity()).add(branch))
+            seq.add(scn.JoinTable())
+            for a, b in lvl["post"]:
+                _append_block(scn, seq, a, b, residual_blocks, leakiness)
+        inner = seq
+    return inner
+
+
+class UNetSCN(nn.Module):
+    def __init__(self, in_channels=1, m=16, block_reps=1, residual_blocks=False,
+                 full_scale=4096, num_planes=7, backend=None):
+        super().__init__()
+        if backend is None:
+            from . import scn as backend  # CUDA implementation; raises if the library is missing
+        scn = backend
+        self.in_channels = in_channels
+        self.out_channels = m
+        self.full_scale = full_scale
+        planes = [(i + 1) * m for i in range(num_planes)]
+        self.layer1 = scn.InputLayer(DIMENSION, full_scale, mode=4)
+        self.layer2 = scn.SubmanifoldConvolution(DIMENSION, in_channels, m, 3, False)
+        self.layer3 = build_unet(scn, block_reps, planes, residual_blocks)
+        self.layer4 = scn.BatchNormReLU(m)
+        self.layer5 = scn.OutputLayer(DIMENSION)
+
+    def forward(self, x):
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4, self.layer5):
+            x = layer(x)
+        return x
