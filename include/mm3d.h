@@ -1,0 +1,162 @@
+/*
+ * mm3d.h -- C ABI of libmm3d.so, the B200 (sm_100a) implementation of MM2D3D's 3D-branch
+ * hot path.  This is the drop-in boundary: it sits where SparseConvNet's pybind module
+ * `sparseconvnet.SCN` sits under the reference's `import sparseconvnet as scn`
+ * (/root/reference/experiments_USA_SING/rgbd_rgbxyz_sigmoid_for_rgb/3d_net/scn_unet.py:1,
+ * constructors at :38-52,:56-81,:113-117) and where the advanced-indexing lift sits in
+ * 2d_net/model.py:131-137,:166-173.  SparseConvNet (facebookresearch/SparseConvNet@dcf6a7ff,
+ * environment.yml:37) is not vendored, so the "replaces" notes below name its pybind entry
+ * points as listed in SURVEY.md section 8(b).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named *_host;
+ *   - the caller owns every buffer (PyTorch tensors in the shipped host code); scratch comes
+ *     from the caller through (ws, ws_bytes) with a *_workspace_bytes() query per op;
+ *   - every call is stream-ordered on `stream` (a cudaStream_t) and never synchronises the host;
+ *   - returns MM3D_OK or an error code; mm3d_last_error() gives the thread-local message;
+ *   - features are row-major float32 [rows, channels]; weights are SparseConvNet's
+ *     [K, C_in, C_out] (its parameter tensor [K, 1, C_in, C_out] with groups == 1);
+ *   - rule tables are offset-major int32 `tbl[k * tbl_stride + out_row]` = input row or -1.
+ */
+#ifndef MM3D_H_
+#define MM3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MM3D_ABI_VERSION 1
+
+#define MM3D_OK 0
+#define MM3D_ERR_INVALID 1     /* bad argument */
+#define MM3D_ERR_CUDA 2        /* a CUDA runtime call or launch failed */
+#define MM3D_ERR_WORKSPACE 3   /* workspace too small */
+#define MM3D_ERR_UNSUPPORTED 4 /* shape / mode not implemented by this build */
+
+/* arithmetic modes of the convolution kernels */
+#define MM3D_MODE_FP32 0 /* SIMT FP32 FMA -- the parity mode (1e-4) */
+#define MM3D_MODE_TF32 1 /* tcgen05 kind::tf32, FP32 accumulate in TMEM (1e-2) */
+#define MM3D_MODE_BF16 2 /* tcgen05 kind::f16 with BF16 operands, FP32 accumulate (1e-2) */
+
+/* flags of mm3d_conv_fwd */
+#define MM3D_CONV_TRANSPOSE_W 1 /* use W[k]^T: weight is [K, c_out, c_in] as stored by the forward layer (dgrad) */
+#define MM3D_CONV_MIRROR_K 2    /* use W[K-1-k] for table column k (submanifold dgrad) */
+
+typedef void* mm3d_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define MM3D_API __attribute__((visibility("default")))
+#else
+#define MM3D_API
+#endif
+
+MM3D_API int mm3d_abi_version(void);
+MM3D_API const char* mm3d_last_error(void);
+/* 1 if the running device is compute capability 10.x (tcgen05 paths usable), 0 otherwise, <0 on error */
+MM3D_API int mm3d_device_supports_tc(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Structure: replaces SparseConvNet's CPU-only Metadata<3> (InputLayer rules,
+ * SubmanifoldConvolution_SgsToRules, Convolution_InputSgsToRulesAndOutputSgs).
+ *
+ * Keys are b<<48 | x<<32 | y<<16 | z.  Rows are numbered by first occurrence,
+ * computed with an open-addressing hash + atomicMin + prefix scan, so ids are deterministic.
+ * Row counts are data dependent: they are written to DEVICE ints; sizes passed from the host
+ * are capacities (upper bounds).  status_dev is OR-ed with MM3D_STATUS_* bits.
+ * ---------------------------------------------------------------------------------------- */
+#define MM3D_STATUS_BAD_COORD 1 /* a coordinate outside [0, spatial_size) or batch outside [0, 32768) */
+
+/* number of hash slots needed for up to n keys (power of two, load <= 0.5) */
+MM3D_API int64_t mm3d_hash_capacity(int64_t n);
+/* scratch bytes of mm3d_voxelize / mm3d_coarsen for up to n items */
+MM3D_API size_t mm3d_unique_workspace_bytes(int64_t n);
+
+/* InputLayer structure (replaces the rule-building half of SCN InputLayer_updateOutput):
+ * coords int64 [n_points,4] = (x,y,z,batch).  Outputs: p2v[n_points] voxel row of each point,
+ * vox_keys[<=n_points] key of each voxel row, npts[<=n_points] points per voxel,
+ * *n_vox_dev the voxel count; (hash_keys, hash_vals)[hash_cap] the level-0 grid. */
+MM3D_API int mm3d_voxelize(const int64_t* coords, int64_t n_points, int spatial_size,
+                  uint64_t* hash_keys, int32_t* hash_vals, int64_t hash_cap,
+                  int32_t* p2v, uint64_t* vox_keys, int32_t* npts, int32_t* n_vox_dev,
+                  int32_t* status_dev, void* ws, size_t ws_bytes, mm3d_stream_t stream);
+
+/* Stride-2/size-2 structure (replaces Convolution_InputSgsToRulesAndOutputSgs): from the fine
+ * rows (fine_keys[*n_fine_dev], capacity n_fine_cap) build the coarse grid, parent[fine row],
+ * off[fine row] in 0..7 and the offset-major child table child_tbl[8][tbl_stride]. */
+MM3D_API int mm3d_coarsen(const uint64_t* fine_keys, const int32_t* n_fine_dev, int64_t n_fine_cap,
+                 uint64_t* hash_keys, int32_t* hash_vals, int64_t hash_cap,
+                 int32_t* parent, uint8_t* off, uint64_t* coarse_keys,
+                 int32_t* child_tbl, int64_t tbl_stride, int32_t* n_coarse_dev,
+                 void* ws, size_t ws_bytes, mm3d_stream_t stream);
+
+/* 3^3 submanifold rules (replaces SubmanifoldConvolution_SgsToRules): offset-major table
+ * nbr_tbl[27][tbl_stride]; column k = ((dx+1)*3+(dy+1))*3+(dz+1). */
+MM3D_API int mm3d_build_nbr27(const uint64_t* keys, const int32_t* n_dev, int64_t n_cap, int spatial_size,
+                     const uint64_t* hash_keys, const int32_t* hash_vals, int64_t hash_cap,
+                     int32_t* nbr_tbl, int64_t tbl_stride, mm3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * I/O layers (replace SCN InputLayer_updateOutput/updateGradInput, OutputLayer_*).
+ * mode 4 = mean of a voxel's points, 3 = sum.
+ * ---------------------------------------------------------------------------------------- */
+MM3D_API int mm3d_input_fwd(const float* feats, const int32_t* p2v, const int32_t* npts, int64_t n_points,
+                   int64_t n_vox, int c, int mode, float* out_vox, mm3d_stream_t stream);
+MM3D_API int mm3d_input_bwd(const float* d_vox, const int32_t* p2v, const int32_t* npts, int64_t n_points,
+                   int c, int mode, float* d_feats, mm3d_stream_t stream);
+MM3D_API int mm3d_output_fwd(const float* vox, const int32_t* p2v, int64_t n_points, int c, float* out,
+                    mm3d_stream_t stream);
+MM3D_API int mm3d_output_bwd(const float* d_out, const int32_t* p2v, int64_t n_points, int64_t n_vox, int c,
+                    float* d_vox, mm3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Rule-table convolution (replaces SubmanifoldConvolution_/Convolution_/Deconvolution_
+ * updateOutput and _backward):
+ *     out[j,:] = sum_k  in[tbl(j,k), :] . Wsel(k)            j < n_out
+ * tbl(j,k) = tbl[k*tbl_stride + j] for a dense table, or, when onehot_off != NULL,
+ * (onehot_off[j] == k ? tbl[j] : -1) with tbl = parent[] (the deconvolution's table).
+ * Wsel(k) = W[k] ([c_in, c_out]), or with flags: W[k]^T and/or W[K-1-k].
+ * The three layer types and their gradients are all instances.
+ * ---------------------------------------------------------------------------------------- */
+MM3D_API size_t mm3d_conv_workspace_bytes(int64_t n_in, int64_t n_out, int c_in, int c_out, int K, int mode);
+MM3D_API int mm3d_conv_fwd(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
+                  const float* weight, int K, const int32_t* tbl, int64_t tbl_stride,
+                  const uint8_t* onehot_off, int flags, int mode,
+                  void* ws, size_t ws_bytes, mm3d_stream_t stream);
+/* d_weight[k] (+)= sum_j in[tbl(j,k)]^T . d_out[j]   ([K, c_in, c_out]); accumulate=0 overwrites */
+MM3D_API int mm3d_conv_wgrad(const float* in, int64_t n_in, int c_in, const float* d_out, int64_t n_out,
+                    int c_out, float* d_weight, int K, const int32_t* tbl, int64_t tbl_stride,
+                    const uint8_t* onehot_off, int accumulate, int mode,
+                    void* ws, size_t ws_bytes, mm3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BatchNorm + (leaky) ReLU over active rows (replaces BatchNormalization_updateOutput/_backward).
+ * momentum is SparseConvNet's (weight of the old running value, 0.9).  ws: 2*c doubles.
+ * ---------------------------------------------------------------------------------------- */
+MM3D_API size_t mm3d_bnrelu_workspace_bytes(int c);
+MM3D_API int mm3d_bnrelu_fwd(const float* x, float* y, int64_t n, int c, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                    float eps, float momentum, float leakiness, int training,
+                    void* ws, size_t ws_bytes, mm3d_stream_t stream);
+MM3D_API int mm3d_bnrelu_bwd(const float* x, const float* dy, float* dx, int64_t n, int c, const float* gamma,
+                    const float* beta, const float* save_mean, const float* save_invstd,
+                    float* d_gamma, float* d_beta, float leakiness, int training,
+                    void* ws, size_t ws_bytes, mm3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 2D->3D lift (replaces the per-sample advanced indexing of 2d_net/model.py:131-137):
+ * out[n,:] = fmap[b(n), :, idx[n,0], idx[n,1]], fmap NCHW; sample_offsets int64 [B+1] gives the
+ * row range of each sample in the concatenated idx; dtype 0=f32 1=f16 2=bf16 (map and out).
+ * Backward scatter-adds into d_fmap (caller zero-fills), duplicates accumulate.
+ * ---------------------------------------------------------------------------------------- */
+MM3D_API int mm3d_lift2d_fwd(const void* fmap, int dtype, int B, int C, int H, int W, const int64_t* idx,
+                    const int64_t* sample_offsets, int64_t n, void* out, mm3d_stream_t stream);
+MM3D_API int mm3d_lift2d_bwd(const void* d_out, int dtype, int B, int C, int H, int W, const int64_t* idx,
+                    const int64_t* sample_offsets, int64_t n, void* d_fmap, mm3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MM3D_H_ */

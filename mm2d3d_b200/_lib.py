@@ -1,0 +1,82 @@
+"""ctypes binding of ``libmm3d.so`` (the C ABI declared in ``include/mm3d.h``).
+
+There is no CPU fallback: if the library has not been built (``python -m mm2d3d_b200.build``)
+importing this module raises, and every op raises on a non-zero return code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmm3d.so")
+
+ABI_VERSION = 1
+
+MODE_FP32, MODE_TF32, MODE_BF16 = 0, 1, 2
+MODES = {"fp32": MODE_FP32, "tf32": MODE_TF32, "bf16": MODE_BF16}
+CONV_TRANSPOSE_W, CONV_MIRROR_K = 1, 2
+STATUS_BAD_COORD = 1
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -m mm2d3d_b200.build` "
+        "(nvcc, sm_100a). mm2d3d_b200 has no CPU fallback."
+    )
+
+lib = C.CDLL(LIB_PATH)
+
+_p, _i, _i64, _sz, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
+
+# name: (restype, argtypes) -- mirrors include/mm3d.h one to one
+SIGNATURES = {
+    "mm3d_abi_version": (_i, []),
+    "mm3d_last_error": (C.c_char_p, []),
+    "mm3d_device_supports_tc": (_i, []),
+    "mm3d_hash_capacity": (_i64, [_i64]),
+    "mm3d_unique_workspace_bytes": (_sz, [_i64]),
+    "mm3d_voxelize": (_i, [_p, _i64, _i, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mm3d_coarsen": (_i, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _sz, _p]),
+    "mm3d_build_nbr27": (_i, [_p, _p, _i64, _i, _p, _p, _i64, _p, _i64, _p]),
+    "mm3d_input_fwd": (_i, [_p, _p, _p, _i64, _i64, _i, _i, _p, _p]),
+    "mm3d_input_bwd": (_i, [_p, _p, _p, _i64, _i, _i, _p, _p]),
+    "mm3d_output_fwd": (_i, [_p, _p, _i64, _i, _p, _p]),
+    "mm3d_output_bwd": (_i, [_p, _p, _i64, _i64, _i, _p, _p]),
+    "mm3d_conv_workspace_bytes": (_sz, [_i64, _i64, _i, _i, _i, _i]),
+    "mm3d_conv_fwd": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i, _p, _i64, _p, _i, _i, _p, _sz, _p]),
+    "mm3d_conv_wgrad": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i, _p, _i64, _p, _i, _i, _p, _sz, _p]),
+    "mm3d_bnrelu_workspace_bytes": (_sz, [_i]),
+    "mm3d_bnrelu_fwd": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i, _p, _sz, _p]),
+    "mm3d_bnrelu_bwd": (_i, [_p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _f, _i, _p, _sz, _p]),
+    "mm3d_lift2d_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i64, _p, _p]),
+    "mm3d_lift2d_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i64, _p, _p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here = library / header mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+if lib.mm3d_abi_version() != ABI_VERSION:
+    raise ImportError(f"libmm3d ABI {lib.mm3d_abi_version()} != expected {ABI_VERSION}; rebuild the library")
+
+
+class Mm3dError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib.mm3d_last_error().decode("utf-8", "replace")
+        raise Mm3dError(f"{what or 'libmm3d'} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

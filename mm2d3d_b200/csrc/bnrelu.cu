@@ -1,0 +1,272 @@
+// BatchNorm + (leaky) ReLU over the active rows of a sparse tensor (replaces
+// SparseConvNet's BatchNormalization_f_train / _f_test / _b, which launch <= 16 thread blocks).
+//
+// HBM-bound: forward = read x (stats) + read x + write y; backward = 2 x (read x, dy) + write dx.
+// Layout: a CTA's 256 threads tile (rows_pass x CV) where CV = C / VEC channel vectors, so a
+// warp reads consecutive float4s of consecutive rows (fully coalesced) and every thread keeps
+// one fixed channel vector; per-thread FP32 partials are combined in FP64 (shared, then global
+// atomics into 2*C doubles), which makes var = E[x^2] - mean^2 safe.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <int VEC> struct Vec;
+template <> struct Vec<4> { using T = float4; };
+template <> struct Vec<1> { using T = float; };
+
+template <int VEC> __device__ __forceinline__ void vload(const float* p, float (&v)[VEC]);
+template <> __device__ __forceinline__ void vload<4>(const float* p, float (&v)[4]) {
+  float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void vload<1>(const float* p, float (&v)[1]) { v[0] = __ldg(p); }
+template <int VEC> __device__ __forceinline__ void vstore(float* p, const float (&v)[VEC]);
+template <> __device__ __forceinline__ void vstore<4>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void vstore<1>(float* p, const float (&v)[1]) { *p = v[0]; }
+
+// dynamic shared: 2*C doubles (accumulators) -- also reused as 2*C floats of scale/shift
+extern __shared__ double s_acc[];
+
+// ---- forward statistics: sums[0..C) = sum x, sums[C..2C) = sum x^2
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_bn_stats(const float* __restrict__ x, int64_t n, int c, double* __restrict__ sums) {
+  const int cv = c / VEC;
+  const int rows_pass = kThreads / cv;
+  const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
+  for (int i = threadIdx.x; i < 2 * c; i += kThreads) s_acc[i] = 0.0;
+  __syncthreads();
+  if (r < rows_pass) {
+    float s[VEC], q[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) s[j] = q[j] = 0.f;
+    for (int64_t row = (int64_t)blockIdx.x * rows_pass + r; row < n; row += (int64_t)gridDim.x * rows_pass) {
+      float t[VEC];
+      vload<VEC>(x + row * c + v * VEC, t);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { s[j] += t[j]; q[j] = fmaf(t[j], t[j], q[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      atomicAdd(&s_acc[v * VEC + j], (double)s[j]);
+      atomicAdd(&s_acc[c + v * VEC + j], (double)q[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * c; i += kThreads) atomicAdd(sums + i, s_acc[i]);
+}
+
+// ---- forward apply (+ finalise: save_mean / save_invstd / running stats by block 0)
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_bn_apply(const float* __restrict__ x, float* __restrict__ y, int64_t n, int c,
+           const float* __restrict__ gamma, const float* __restrict__ beta,
+           float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+           const double* __restrict__ sums, float eps, float momentum, float leak, int training) {
+  float* s_mean = reinterpret_cast<float*>(s_acc);
+  float* s_scale = s_mean + c;
+  for (int i = threadIdx.x; i < c; i += kThreads) {
+    float mean, invstd;
+    if (training) {
+      const double m = sums[i] / (double)n;
+      double var = sums[c + i] / (double)n - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      invstd = (float)(1.0 / sqrt(var + (double)eps));
+      if (blockIdx.x == 0) {
+        save_mean[i] = mean;
+        save_invstd[i] = invstd;
+        const double unbiased = var * ((double)n / (double)(n > 1 ? n - 1 : 1));
+        running_mean[i] = momentum * running_mean[i] + (1.f - momentum) * mean;
+        running_var[i] = momentum * running_var[i] + (1.f - momentum) * (float)unbiased;
+      }
+    } else {
+      mean = running_mean[i];
+      invstd = rsqrtf(running_var[i] + eps);
+      if (blockIdx.x == 0 && save_mean) { save_mean[i] = mean; save_invstd[i] = invstd; }
+    }
+    s_mean[i] = mean;
+    s_scale[i] = invstd * gamma[i];
+  }
+  __syncthreads();
+  const int cv = c / VEC;
+  const int rows_pass = kThreads / cv;
+  const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
+  if (r >= rows_pass) return;
+  float mean[VEC], scale[VEC], bet[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    mean[j] = s_mean[v * VEC + j];
+    scale[j] = s_scale[v * VEC + j];
+    bet[j] = __ldg(beta + v * VEC + j);
+  }
+  for (int64_t row = (int64_t)blockIdx.x * rows_pass + r; row < n; row += (int64_t)gridDim.x * rows_pass) {
+    float t[VEC];
+    vload<VEC>(x + row * c + v * VEC, t);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float o = fmaf(t[j] - mean[j], scale[j], bet[j]);
+      t[j] = o > 0.f ? o : o * leak;
+    }
+    vstore<VEC>(y + row * c + v * VEC, t);
+  }
+}
+
+// ---- backward reductions: sums[0..C) = sum d, sums[C..2C) = sum d * xhat, d = dy * relu'(y)
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_bn_bwd_stats(const float* __restrict__ x, const float* __restrict__ dy, int64_t n, int c,
+               const float* __restrict__ gamma, const float* __restrict__ beta,
+               const float* __restrict__ save_mean, const float* __restrict__ save_invstd, float leak,
+               double* __restrict__ sums) {
+  const int cv = c / VEC;
+  const int rows_pass = kThreads / cv;
+  const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
+  for (int i = threadIdx.x; i < 2 * c; i += kThreads) s_acc[i] = 0.0;
+  __syncthreads();
+  if (r < rows_pass) {
+    float mean[VEC], invstd[VEC], scale[VEC], bet[VEC], s[VEC], q[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      mean[j] = __ldg(save_mean + v * VEC + j);
+      invstd[j] = __ldg(save_invstd + v * VEC + j);
+      scale[j] = invstd[j] * __ldg(gamma + v * VEC + j);
+      bet[j] = __ldg(beta + v * VEC + j);
+      s[j] = q[j] = 0.f;
+    }
+    for (int64_t row = (int64_t)blockIdx.x * rows_pass + r; row < n; row += (int64_t)gridDim.x * rows_pass) {
+      float t[VEC], g[VEC];
+      vload<VEC>(x + row * c + v * VEC, t);
+      vload<VEC>(dy + row * c + v * VEC, g);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float xc = t[j] - mean[j];
+        const float o = fmaf(xc, scale[j], bet[j]);
+        const float d = o > 0.f ? g[j] : g[j] * leak;
+        s[j] += d;
+        q[j] = fmaf(d, xc * invstd[j], q[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      atomicAdd(&s_acc[v * VEC + j], (double)s[j]);
+      atomicAdd(&s_acc[c + v * VEC + j], (double)q[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * c; i += kThreads) atomicAdd(sums + i, s_acc[i]);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int64_t n, int c,
+               const float* __restrict__ gamma, const float* __restrict__ beta,
+               const float* __restrict__ save_mean, const float* __restrict__ save_invstd, float leak,
+               const double* __restrict__ sums, float* d_gamma, float* d_beta, int training) {
+  const int cv = c / VEC;
+  const int rows_pass = kThreads / cv;
+  const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < c; i += kThreads) {
+      d_beta[i] = (float)sums[i];
+      d_gamma[i] = (float)sums[c + i];
+    }
+  if (r >= rows_pass) return;
+  float mean[VEC], invstd[VEC], scale[VEC], bet[VEC], md[VEC], mdx[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int ch = v * VEC + j;
+    mean[j] = __ldg(save_mean + ch);
+    invstd[j] = __ldg(save_invstd + ch);
+    scale[j] = invstd[j] * __ldg(gamma + ch);
+    bet[j] = __ldg(beta + ch);
+    md[j] = training ? (float)(sums[ch] / (double)n) : 0.f;
+    mdx[j] = training ? (float)(sums[c + ch] / (double)n) : 0.f;
+  }
+  for (int64_t row = (int64_t)blockIdx.x * rows_pass + r; row < n; row += (int64_t)gridDim.x * rows_pass) {
+    float t[VEC], g[VEC];
+    vload<VEC>(x + row * c + v * VEC, t);
+    vload<VEC>(dy + row * c + v * VEC, g);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float xc = t[j] - mean[j];
+      const float o = fmaf(xc, scale[j], bet[j]);
+      const float d = o > 0.f ? g[j] : g[j] * leak;
+      g[j] = scale[j] * (d - md[j] - xc * invstd[j] * mdx[j]);
+    }
+    vstore<VEC>(dx + row * c + v * VEC, g);
+  }
+}
+
+int bn_grid(int64_t n, int cv) {
+  const int rows_pass = kThreads / cv;
+  int64_t g = mm3d_cdiv(n, (int64_t)rows_pass * 4);  // >= 4 rows per thread when there is enough work
+  if (g < 1) g = 1;
+  const int64_t cap = (int64_t)MM3D_NUM_SMS * 8;
+  return (int)(g < cap ? g : cap);
+}
+
+}  // namespace
+
+extern "C" size_t mm3d_bnrelu_workspace_bytes(int c) { return mm3d_align(sizeof(double) * 2 * (size_t)c); }
+
+#define BN_DISPATCH(KERNEL, ...)                                                        \
+  do {                                                                                  \
+    if (vec4) KERNEL<4><<<grid, kThreads, smem, stream>>>(__VA_ARGS__);                 \
+    else      KERNEL<1><<<grid, kThreads, smem, stream>>>(__VA_ARGS__);                 \
+  } while (0)
+
+extern "C" int mm3d_bnrelu_fwd(const float* x, float* y, int64_t n, int c, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                               float eps, float momentum, float leakiness, int training,
+                               void* ws, size_t ws_bytes, mm3d_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MM3D_REQUIRE(c > 0 && n >= 0, MM3D_ERR_INVALID, "bad sizes");
+  const bool vec4 = (c % 4 == 0) && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
+  const int cv = vec4 ? c / 4 : c;
+  MM3D_REQUIRE(cv <= kThreads, MM3D_ERR_UNSUPPORTED, "BatchNorm with %d channels not supported", c);
+  MM3D_REQUIRE(ws_bytes >= mm3d_bnrelu_workspace_bytes(c) && ws, MM3D_ERR_WORKSPACE, "bnrelu workspace too small");
+  if (n == 0) return MM3D_OK;
+  double* sums = (double*)ws;
+  const int grid = bn_grid(n, cv);
+  const size_t smem = sizeof(double) * 2 * c;
+  if (training) {
+    MM3D_REQUIRE(save_mean && save_invstd && running_mean && running_var, MM3D_ERR_INVALID, "training needs stat buffers");
+    MM3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c, stream));
+    BN_DISPATCH(k_bn_stats, x, n, c, sums);
+  }
+  BN_DISPATCH(k_bn_apply, x, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, sums, eps,
+              momentum, leakiness, training);
+  MM3D_CHECK_LAUNCH("mm3d_bnrelu_fwd");
+  return MM3D_OK;
+}
+
+extern "C" int mm3d_bnrelu_bwd(const float* x, const float* dy, float* dx, int64_t n, int c, const float* gamma,
+                               const float* beta, const float* save_mean, const float* save_invstd,
+                               float* d_gamma, float* d_beta, float leakiness, int training,
+                               void* ws, size_t ws_bytes, mm3d_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MM3D_REQUIRE(c > 0 && n >= 0, MM3D_ERR_INVALID, "bad sizes");
+  const bool vec4 = (c % 4 == 0) && ((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0);
+  const int cv = vec4 ? c / 4 : c;
+  MM3D_REQUIRE(cv <= kThreads, MM3D_ERR_UNSUPPORTED, "BatchNorm with %d channels not supported", c);
+  MM3D_REQUIRE(ws_bytes >= mm3d_bnrelu_workspace_bytes(c) && ws, MM3D_ERR_WORKSPACE, "bnrelu workspace too small");
+  double* sums = (double*)ws;
+  MM3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c, stream));
+  if (n == 0) {
+    MM3D_CUDA(cudaMemsetAsync(d_gamma, 0, sizeof(float) * c, stream));
+    MM3D_CUDA(cudaMemsetAsync(d_beta, 0, sizeof(float) * c, stream));
+    return MM3D_OK;
+  }
+  const int grid = bn_grid(n, cv);
+  const size_t smem = sizeof(double) * 2 * c;
+  BN_DISPATCH(k_bn_bwd_stats, x, dy, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums);
+  BN_DISPATCH(k_bn_bwd_apply, x, dy, dx, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums, d_gamma,
+              d_beta, training);
+  MM3D_CHECK_LAUNCH("mm3d_bnrelu_bwd");
+  return MM3D_OK;
+}

@@ -1,0 +1,77 @@
+// C-ABI glue: error state, version, mode dispatch of the convolution entry points.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mm3d_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* mm3d_last_error(void) { return g_err; }
+extern "C" int mm3d_abi_version(void) { return MM3D_ABI_VERSION; }
+
+extern "C" int mm3d_device_supports_tc(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return -1;
+  return major == 10 ? 1 : 0;
+}
+
+// conv_simt.cu
+size_t mm3d_conv_simt_workspace_bytes(int c_in, int c_out, int K);
+int mm3d_conv_fwd_simt(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
+                       const float* weight, int K, const int32_t* tbl, int64_t tbl_stride,
+                       const uint8_t* onehot_off, int flags, void* ws, size_t ws_bytes, cudaStream_t stream);
+int mm3d_conv_wgrad_simt(const float* in, int64_t n_in, int c_in, const float* d_out, int64_t n_out, int c_out,
+                         float* d_weight, int K, const int32_t* tbl, int64_t tbl_stride,
+                         const uint8_t* onehot_off, int accumulate, cudaStream_t stream);
+
+extern "C" size_t mm3d_conv_workspace_bytes(int64_t n_in, int64_t n_out, int c_in, int c_out, int K, int mode) {
+  (void)n_in; (void)n_out; (void)mode;
+  return mm3d_conv_simt_workspace_bytes(c_in, c_out, K);
+}
+
+static int check_conv_args(const void* in, const void* out, const void* w, const int32_t* tbl, int64_t n_in,
+                           int64_t n_out, int c_in, int c_out, int K, int64_t tbl_stride, const uint8_t* onehot) {
+  MM3D_REQUIRE(n_in >= 0 && n_out >= 0 && c_in > 0 && c_out > 0 && K > 0, MM3D_ERR_INVALID, "bad conv sizes");
+  MM3D_REQUIRE(n_out == 0 || (in && out && w && tbl), MM3D_ERR_INVALID, "null conv pointer");
+  MM3D_REQUIRE(onehot || tbl_stride >= n_out, MM3D_ERR_INVALID, "tbl_stride %lld < n_out %lld",
+               (long long)tbl_stride, (long long)n_out);
+  return MM3D_OK;
+}
+
+extern "C" int mm3d_conv_fwd(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
+                             const float* weight, int K, const int32_t* tbl, int64_t tbl_stride,
+                             const uint8_t* onehot_off, int flags, int mode,
+                             void* ws, size_t ws_bytes, mm3d_stream_t stream) {
+  int rc = check_conv_args(in, out, weight, tbl, n_in, n_out, c_in, c_out, K, tbl_stride, onehot_off);
+  if (rc) return rc;
+  switch (mode) {
+    case MM3D_MODE_FP32:
+      return mm3d_conv_fwd_simt(in, n_in, c_in, out, n_out, c_out, weight, K, tbl, tbl_stride, onehot_off, flags,
+                                ws, ws_bytes, (cudaStream_t)stream);
+    default:
+      MM3D_REQUIRE(false, MM3D_ERR_UNSUPPORTED, "conv mode %d not implemented in this build", mode);
+  }
+}
+
+extern "C" int mm3d_conv_wgrad(const float* in, int64_t n_in, int c_in, const float* d_out, int64_t n_out,
+                               int c_out, float* d_weight, int K, const int32_t* tbl, int64_t tbl_stride,
+                               const uint8_t* onehot_off, int accumulate, int mode,
+                               void* ws, size_t ws_bytes, mm3d_stream_t stream) {
+  (void)ws; (void)ws_bytes;
+  int rc = check_conv_args(in, d_out, d_weight, tbl, n_in, n_out, c_in, c_out, K, tbl_stride, onehot_off);
+  if (rc) return rc;
+  switch (mode) {
+    case MM3D_MODE_FP32:
+      return mm3d_conv_wgrad_simt(in, n_in, c_in, d_out, n_out, c_out, d_weight, K, tbl, tbl_stride, onehot_off,
+                                  accumulate, (cudaStream_t)stream);
+    default:
+      MM3D_REQUIRE(false, MM3D_ERR_UNSUPPORTED, "wgrad mode %d not implemented in this build", mode);
+  }
+}

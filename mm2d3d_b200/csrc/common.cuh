@@ -1,0 +1,82 @@
+// Shared helpers of libmm3d: error reporting, key packing, hashing, launch geometry.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mm3d.h"
+
+#define MM3D_NUM_SMS 148  // B200: 2 dies x 74 SMs; persistent / grid-stride kernels size to this
+
+void mm3d_set_error(const char* fmt, ...);
+
+#define MM3D_REQUIRE(cond, code, ...)     \
+  do {                                    \
+    if (!(cond)) {                        \
+      mm3d_set_error(__VA_ARGS__);        \
+      return (code);                      \
+    }                                     \
+  } while (0)
+
+#define MM3D_CHECK_LAUNCH(name)                                                      \
+  do {                                                                               \
+    cudaError_t e__ = cudaGetLastError();                                            \
+    if (e__ != cudaSuccess) {                                                        \
+      mm3d_set_error("%s: launch failed: %s", (name), cudaGetErrorString(e__));      \
+      return MM3D_ERR_CUDA;                                                          \
+    }                                                                                \
+  } while (0)
+
+#define MM3D_CUDA(call)                                                              \
+  do {                                                                               \
+    cudaError_t e__ = (call);                                                        \
+    if (e__ != cudaSuccess) {                                                        \
+      mm3d_set_error("%s failed: %s", #call, cudaGetErrorString(e__));               \
+      return MM3D_ERR_CUDA;                                                          \
+    }                                                                                \
+  } while (0)
+
+static inline int64_t mm3d_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t mm3d_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// grid for a grid-stride kernel over n items: enough CTAs to cover n once, capped at a few
+// waves of the 148 SMs so tiny levels do not launch thousands of empty CTAs.
+static inline int mm3d_grid(int64_t n, int block, int ctas_per_sm = 8) {
+  int64_t g = mm3d_cdiv(n > 0 ? n : 1, block);
+  int64_t cap = (int64_t)MM3D_NUM_SMS * ctas_per_sm;
+  return (int)(g < cap ? g : cap);
+}
+
+#define MM3D_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+__host__ __device__ __forceinline__ uint64_t mm3d_pack_key(uint64_t x, uint64_t y, uint64_t z, uint64_t b) {
+  return (b << 48) | (x << 32) | (y << 16) | z;
+}
+__host__ __device__ __forceinline__ int mm3d_key_x(uint64_t k) { return (int)((k >> 32) & 0xFFFF); }
+__host__ __device__ __forceinline__ int mm3d_key_y(uint64_t k) { return (int)((k >> 16) & 0xFFFF); }
+__host__ __device__ __forceinline__ int mm3d_key_z(uint64_t k) { return (int)(k & 0xFFFF); }
+__host__ __device__ __forceinline__ uint64_t mm3d_key_b(uint64_t k) { return k >> 48; }
+
+// murmur3 finaliser: spreads the structured (mostly low-entropy) voxel keys over the table
+__device__ __forceinline__ uint32_t mm3d_hash(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ULL;
+  k ^= k >> 33;
+  return (uint32_t)k;
+}
+
+// read-only lookup in an open-addressing table (linear probing); -1 when absent
+__device__ __forceinline__ int mm3d_hash_find(const uint64_t* __restrict__ keys,
+                                              const int32_t* __restrict__ vals, uint32_t mask,
+                                              uint64_t key) {
+  uint32_t s = mm3d_hash(key) & mask;
+  while (true) {
+    uint64_t k = __ldg(keys + s);
+    if (k == key) return __ldg(vals + s);
+    if (k == MM3D_KEY_EMPTY) return -1;
+    s = (s + 1) & mask;
+  }
+}

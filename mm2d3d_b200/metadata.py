@@ -1,0 +1,210 @@
+"""Per-forward sparse structure on the GPU -- the counterpart of SparseConvNet's ``Metadata``.
+
+One ``Metadata`` is created by ``InputLayer`` and shared by every layer of that forward
+(SURVEY.md A.1, a12).  It owns, per spatial size ("level"): the voxel keys in row order, the
+voxel hash, the 3^3 neighbour table and the stride-2 tables (parent / offset / child).  All of
+it is built by ``libmm3d`` kernels on the current stream; the only host synchronisation is one
+read of the per-level row counts after a build (SparseConvNet builds all of this on the CPU and
+re-uploads rule lists at every layer call).
+
+Buffers are carved from one ``uint8`` tensor per build and handed to the C ABI as raw pointers;
+tensor views are only materialised for inspection (tests, debugging).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+_ALIGN = 256
+
+
+def _al(x):
+    return (x + _ALIGN - 1) // _ALIGN * _ALIGN
+
+
+class Level:
+    """Structure of one spatial size.  ``cap`` = row capacity the buffers were sized for,
+    ``n`` = actual row count (host int, known after the build's sync)."""
+
+    __slots__ = ("spatial", "cap", "n", "buf", "base", "o_keys", "o_hkeys", "o_hvals", "hcap",
+                 "o_nbr", "o_parent", "o_off", "o_child", "has_nbr", "has_down", "count_slot")
+
+    def ptr(self, off):
+        return self.base + off
+
+
+class Metadata:
+    MAX_LEVELS = 16
+
+    def __init__(self, coords: torch.Tensor, spatial_size: int, prebuild_levels: int = 1):
+        if coords.dim() != 2 or coords.shape[1] != 4:
+            raise ValueError("coords must be [N, 4] = (x, y, z, batch)")
+        if not coords.is_cuda:
+            coords = coords.cuda(non_blocking=True)
+        coords = coords.to(torch.int64).contiguous()
+        self.device = coords.device
+        self.n_points = int(coords.shape[0])
+        self.spatial_size0 = int(spatial_size)
+        self.levels: dict[int, Level] = {}
+        self._order: list[Level] = []
+        n = self.n_points
+        L = max(1, min(int(prebuild_levels), self.MAX_LEVELS))
+        # spatial sizes halve while they stay even and > 1
+        sizes = [self.spatial_size0]
+        while len(sizes) < L and sizes[-1] % 2 == 0 and sizes[-1] > 1:
+            sizes.append(sizes[-1] // 2)
+        L = len(sizes)
+
+        with torch.cuda.device(self.device):
+            stream = _lib.stream_ptr()
+            self._counts = torch.zeros(self.MAX_LEVELS + 1, dtype=torch.int32, device=self.device)
+            ws_bytes = lib.mm3d_unique_workspace_bytes(n)
+            head = _al(4 * n) * 2 + _al(ws_bytes)
+            per_level, lay = self._level_layout(n)
+            self._buf = torch.empty(head + per_level * L, dtype=torch.uint8, device=self.device)
+            base = self._buf.data_ptr()
+            self._o_p2v, self._o_npts, o_ws = 0, _al(4 * n), 2 * _al(4 * n)
+            self._ws = (base + o_ws, ws_bytes)
+            for i, s in enumerate(sizes):
+                lv = self._make_level(s, n, self._buf, head + per_level * i, lay, count_slot=i)
+                self.levels[s] = lv
+                self._order.append(lv)
+            l0 = self._order[0]
+            cp = self._counts.data_ptr()
+            check(lib.mm3d_voxelize(coords.data_ptr(), n, self.spatial_size0, l0.ptr(l0.o_hkeys), l0.ptr(l0.o_hvals),
+                                    l0.hcap, base + self._o_p2v, l0.ptr(l0.o_keys), base + self._o_npts,
+                                    cp, cp + 4 * self.MAX_LEVELS, self._ws[0], self._ws[1], stream), "mm3d_voxelize")
+            self._build_nbr(l0, stream)
+            for i in range(1, L):
+                self._build_down(self._order[i - 1], self._order[i], stream)
+                self._build_nbr(self._order[i], stream)
+            self._sync_counts()
+
+    # ------------------------------------------------------------------ construction helpers
+    @staticmethod
+    def _level_layout(cap):
+        hcap = lib.mm3d_hash_capacity(cap)
+        o = {}
+        off = 0
+        for name, nbytes in (("keys", 8 * cap), ("hkeys", 8 * hcap), ("hvals", 4 * hcap), ("nbr", 108 * cap),
+                             ("parent", 4 * cap), ("off", cap), ("child", 32 * cap)):
+            o[name] = off
+            off += _al(nbytes)
+        o["hcap"] = hcap
+        return off, o
+
+    @staticmethod
+    def _make_level(spatial, cap, buf, base_off, lay, count_slot):
+        lv = Level()
+        lv.spatial, lv.cap, lv.n = spatial, cap, None
+        lv.buf, lv.base = buf, buf.data_ptr() + base_off
+        lv.o_keys, lv.o_hkeys, lv.o_hvals, lv.hcap = lay["keys"], lay["hkeys"], lay["hvals"], lay["hcap"]
+        lv.o_nbr, lv.o_parent, lv.o_off, lv.o_child = lay["nbr"], lay["parent"], lay["off"], lay["child"]
+        lv.has_nbr = lv.has_down = False
+        lv.count_slot = count_slot
+        return lv
+
+    def _count_ptr(self, lv):
+        return self._counts.data_ptr() + 4 * lv.count_slot
+
+    def _build_nbr(self, lv, stream):
+        check(lib.mm3d_build_nbr27(lv.ptr(lv.o_keys), self._count_ptr(lv), lv.cap, lv.spatial, lv.ptr(lv.o_hkeys),
+                                   lv.ptr(lv.o_hvals), lv.hcap, lv.ptr(lv.o_nbr), lv.cap, stream), "mm3d_build_nbr27")
+        lv.has_nbr = True
+
+    def _build_down(self, fine, coarse, stream):
+        # parent/off/child of the 2/2 convolution live with the FINE level; keys/hash with the coarse one
+        check(lib.mm3d_coarsen(fine.ptr(fine.o_keys), self._count_ptr(fine), fine.cap, coarse.ptr(coarse.o_hkeys),
+                               coarse.ptr(coarse.o_hvals), coarse.hcap, fine.ptr(fine.o_parent), fine.ptr(fine.o_off),
+                               coarse.ptr(coarse.o_keys), fine.ptr(fine.o_child), fine.cap, self._count_ptr(coarse),
+                               self._ws[0], self._ws[1], stream), "mm3d_coarsen")
+        fine.has_down = True
+
+    def _sync_counts(self):
+        host = self._counts.cpu()  # the one host synchronisation of a build
+        if int(host[self.MAX_LEVELS]) & _lib.STATUS_BAD_COORD:
+            raise ValueError("InputLayer: coordinates must lie in [0, spatial_size) and batch index in [0, 32768)")
+        for lv in self._order:
+            if lv.n is None:
+                lv.n = int(host[lv.count_slot])
+
+    # ------------------------------------------------------------------ lookups used by the layers
+    def level(self, spatial_size: int) -> Level:
+        return self.levels[int(spatial_size)]
+
+    def nbr(self, spatial_size: int) -> Level:
+        lv = self.levels[int(spatial_size)]
+        if not lv.has_nbr:
+            with torch.cuda.device(self.device):
+                self._build_nbr(lv, _lib.stream_ptr())
+        return lv
+
+    def down(self, spatial_size: int):
+        """(fine level, coarse level) of the 2/2 convolution from ``spatial_size``; built lazily
+        (one extra host sync) when it was not part of the pre-built pyramid."""
+        s = int(spatial_size)
+        fine = self.levels[s]
+        if not fine.has_down:
+            if s % 2 or s < 2:
+                raise ValueError(f"cannot apply a 2/2 convolution at spatial size {s}")
+            if len(self._order) >= self.MAX_LEVELS:
+                raise ValueError("too many levels")
+            with torch.cuda.device(self.device):
+                cap = fine.n
+                per_level, lay = self._level_layout(cap)
+                buf = torch.empty(per_level, dtype=torch.uint8, device=self.device)
+                coarse = self._make_level(s // 2, cap, buf, 0, lay, count_slot=len(self._order))
+                self.levels[s // 2] = coarse
+                self._order.append(coarse)
+                self._build_down(fine, coarse, _lib.stream_ptr())
+                self._sync_counts()
+        return fine, self.levels[s // 2]
+
+    # ------------------------------------------------------------------ inspection (tests)
+    @property
+    def p2v_ptr(self):
+        return self._buf.data_ptr() + self._o_p2v
+
+    @property
+    def npts_ptr(self):
+        return self._buf.data_ptr() + self._o_npts
+
+    @property
+    def n_voxels(self):
+        return self._order[0].n
+
+    def _view(self, buf, byte_off, dtype, numel):
+        esz = torch.empty(0, dtype=dtype).element_size()
+        start = (byte_off) // 1
+        return buf[start:start + numel * esz].view(dtype)
+
+    def p2v(self) -> torch.Tensor:
+        return self._view(self._buf, self._o_p2v, torch.int32, self.n_points)
+
+    def npts(self) -> torch.Tensor:
+        return self._view(self._buf, self._o_npts, torch.int32, self.n_voxels)
+
+    def _lv_view(self, lv, off, dtype, numel):
+        return self._view(lv.buf, lv.base - lv.buf.data_ptr() + off, dtype, numel)
+
+    def coords_at(self, spatial_size) -> torch.Tensor:
+        """int64 [n, 4] (x, y, z, batch) of the level's rows, decoded from the keys."""
+        lv = self.levels[int(spatial_size)]
+        k = self._lv_view(lv, lv.o_keys, torch.int64, lv.n)
+        return torch.stack([(k >> 32) & 0xFFFF, (k >> 16) & 0xFFFF, k & 0xFFFF, k >> 48], 1)
+
+    def nbr_table(self, spatial_size) -> torch.Tensor:
+        """int32 [n, 27] (row-major copy of the offset-major device table)."""
+        lv = self.nbr(spatial_size)
+        t = self._lv_view(lv, lv.o_nbr, torch.int32, 27 * lv.cap).view(27, lv.cap)
+        return t[:, :lv.n].t().contiguous()
+
+    def down_tables(self, spatial_size):
+        """(parent int32 [n_fine], off uint8 [n_fine], child int32 [n_coarse, 8])."""
+        fine, coarse = self.down(spatial_size)
+        parent = self._lv_view(fine, fine.o_parent, torch.int32, fine.n)
+        off = self._lv_view(fine, fine.o_off, torch.uint8, fine.n)
+        child = self._lv_view(fine, fine.o_child, torch.int32, 8 * fine.cap).view(8, fine.cap)
+        return parent, off, child[:, :coarse.n].t().contiguous()

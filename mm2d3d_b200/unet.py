@@ -85,6 +85,9 @@ class UNetSCN(nn.Module):
         self.full_scale = full_scale
         planes = [(i + 1) * m for i in range(num_planes)]
         self.layer1 = scn.InputLayer(DIMENSION, full_scale, mode=4)
+        if hasattr(self.layer1, "prebuild_levels"):
+            # build the whole num_planes-level pyramid in the InputLayer pass: one host sync per forward
+            self.layer1.prebuild_levels = num_planes
         self.layer2 = scn.SubmanifoldConvolution(DIMENSION, in_channels, m, 3, False)
         self.layer3 = build_unet(scn, block_reps, planes, residual_blocks)
         self.layer4 = scn.BatchNormReLU(m)

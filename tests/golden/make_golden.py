@@ -1,0 +1,125 @@
+"""Generates the committed golden fixtures.  Run in the BUILD container (needs /root/reference for
+the lift fixture):  ``python tests/golden/make_golden.py``.
+
+* ``lift_ref.npz``    -- produced by the REFERENCE ITSELF: its ``L2G_classifier_2D``
+  (``2d_net/model.py:145-180``) is imported and run on CPU; we record the map it lifts from
+  (``seg_logit_avg_2d``), the per-sample pixel indices and what it returns (``seg_logit_avg``),
+  plus the gradient torch autograd gives for the map.  This pins the lift oracle and kernel.
+* ``unet_small.npz``  -- produced by the CPU ORACLE (SparseConvNet is not available; see
+  oracle/__init__.py): a small UNetSCN (m=4, 4 planes, full_scale 64) forward + backward with
+  seeded weights on a seeded 2-sample cloud: inputs, parameters, output, all gradients.
+* ``structure_small.npz`` -- oracle voxel ids / level coords / rule tables for a seeded cloud.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import scn_cpu  # noqa: E402
+from oracle import scn_oracle as O  # noqa: E402
+from mm2d3d_b200.unet import UNetSCN  # noqa: E402
+
+REF_2D = "/root/reference/experiments_USA_SING/rgbd_rgbxyz_sigmoid_for_rgb/2d_net/model.py"
+
+
+def lift_from_reference():
+    # import only the class definitions of the reference file (its package-relative import of
+    # .backbones is not needed for L2G_classifier_2D)
+    src = open(REF_2D).read().replace("from .backbones import Backbone", "Backbone = None")
+    mod = type(sys)("ref_2d_model")
+    exec(compile(src, REF_2D, "exec"), mod.__dict__)
+    torch.manual_seed(7)
+    rng = np.random.default_rng(7)
+    B, C_in, H, W, classes = 3, 8, 23, 40, 6
+    head = mod.L2G_classifier_2D(C_in, classes).double()
+    feat = torch.randn(B, C_in, H, W, dtype=torch.float64)
+    counts = [57, 0, 131]
+    img_indices = []
+    for i, n in enumerate(counts):
+        r = rng.integers(0, H, n)
+        c = rng.integers(0, W, n)
+        if i == 2:  # duplicate-heavy sample
+            r, c = r % 4, c % 4
+        img_indices.append(np.stack([r, c], 1).astype(np.int64))
+    preds = head(feat, img_indices)
+    fmap = preds["seg_logit_avg_2d"].detach().clone().requires_grad_(True)
+    # re-run the reference's lift lines on the recorded map to get the autograd gradient
+    lifted = []
+    for i in range(B):
+        lifted.append(fmap.permute(0, 2, 3, 1)[i][img_indices[i][:, 0], img_indices[i][:, 1]])
+    lifted = torch.cat(lifted, 0)
+    assert torch.equal(lifted.detach(), preds["seg_logit_avg"].detach())
+    g = torch.randn_like(lifted)
+    (d_fmap,) = torch.autograd.grad(lifted, fmap, g)
+    np.savez_compressed(
+        os.path.join(HERE, "lift_ref.npz"), fmap=fmap.detach().numpy(), lifted=preds["seg_logit_avg"].detach().numpy(),
+        idx=np.concatenate(img_indices, 0), counts=np.asarray(counts), grad_out=g.numpy(), grad_fmap=d_fmap.numpy())
+
+
+def small_cloud(seed, n=220, b=2, span=28, origin=5):
+    rng = np.random.default_rng(seed)
+    # surface-like: points near two planes so that 3^3 neighbourhoods are populated
+    pts = []
+    for s in range(b):
+        u = rng.integers(0, span, (n, 2))
+        z = (u[:, 0] // 3 + rng.integers(0, 2, n)) % span
+        c = np.stack([u[:, 0], u[:, 1], z], 1) + origin
+        pts.append(np.concatenate([c, np.full((n, 1), s)], 1))
+    coords = np.concatenate(pts, 0).astype(np.int64)
+    feats = rng.random((coords.shape[0], 3), dtype=np.float32)
+    return coords, feats
+
+
+def unet_small():
+    torch.manual_seed(11)
+    coords, feats = small_cloud(11)
+    net = UNetSCN(in_channels=3, m=4, num_planes=4, full_scale=64, backend=scn_cpu).double()
+    # non-trivial BN affine parameters
+    for name, p in net.named_parameters():
+        if p.dim() == 1:
+            with torch.no_grad():
+                p.add_(0.1 * torch.randn_like(p))
+    x = torch.from_numpy(feats).double().requires_grad_(True)
+    out = net([torch.from_numpy(coords), x])
+    g = torch.randn_like(out)
+    params = dict(net.named_parameters())
+    grads = torch.autograd.grad(out, [x] + list(params.values()), g)
+    blob = {"coords": coords, "feats": feats, "out": out.detach().numpy(), "grad_out": g.numpy(),
+            "grad_feats": grads[0].numpy()}
+    for (name, p), gr in zip(params.items(), grads[1:]):
+        blob["param:" + name] = p.detach().numpy()
+        blob["grad:" + name] = gr.numpy()
+    for name, b in net.named_buffers():
+        blob["buffer_after:" + name] = b.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "unet_small.npz"), **blob)
+
+
+def structure_small():
+    coords, _ = small_cloud(23, n=400, b=3, span=40, origin=100)
+    meta = O.Metadata(coords, 4096)
+    blob = {"coords": coords, "p2v": meta.p2v, "npts": meta.npts}
+    s = 4096
+    for lvl in range(4):
+        blob[f"coords_l{lvl}"] = meta.coords_at(s)
+        blob[f"nbr_l{lvl}"] = meta.nbr(s)
+        if lvl < 3:
+            parent, off, nc = meta.down(s)
+            blob[f"parent_l{lvl}"], blob[f"off_l{lvl}"] = parent, off
+            blob[f"child_l{lvl}"] = O.child_table(parent, off, nc)
+        s //= 2
+    np.savez_compressed(os.path.join(HERE, "structure_small.npz"), **blob)
+
+
+if __name__ == "__main__":
+    lift_from_reference()
+    unet_small()
+    structure_small()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

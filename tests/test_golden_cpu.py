@@ -1,0 +1,53 @@
+"""CPU checks of the oracle against the committed golden fixtures (tests/golden)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import lift_oracle, scn_cpu
+from oracle import scn_oracle as O
+from mm2d3d_b200.unet import UNetSCN
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_lift_oracle_matches_reference_fixture():
+    """lift_ref.npz was produced by the reference's own L2G_classifier_2D (make_golden.py)."""
+    z = np.load(os.path.join(G, "lift_ref.npz"))
+    fmap = torch.from_numpy(z["fmap"]).requires_grad_(True)
+    offs = np.concatenate([[0], np.cumsum(z["counts"])])
+    idx = [z["idx"][offs[i]:offs[i + 1]] for i in range(len(z["counts"]))]
+    out = lift_oracle.lift2d(fmap, idx)
+    assert torch.equal(out.detach(), torch.from_numpy(z["lifted"]))
+    (g,) = torch.autograd.grad(out, fmap, torch.from_numpy(z["grad_out"]))
+    assert torch.allclose(g, torch.from_numpy(z["grad_fmap"]), atol=1e-12)
+
+
+def test_structure_fixture():
+    z = np.load(os.path.join(G, "structure_small.npz"))
+    meta = O.Metadata(z["coords"], 4096)
+    assert np.array_equal(meta.p2v, z["p2v"]) and np.array_equal(meta.npts, z["npts"])
+    # literal loop restatement agrees with the fixture too
+    ids, _ = O.first_occurrence_ids_loop(O.pack_keys(z["coords"]))
+    assert np.array_equal(ids, z["p2v"])
+    s = 4096
+    for lvl in range(4):
+        assert np.array_equal(meta.coords_at(s), z[f"coords_l{lvl}"])
+        assert np.array_equal(meta.nbr(s), z[f"nbr_l{lvl}"])
+        if lvl < 3:
+            parent, off, nc = meta.down(s)
+            assert np.array_equal(parent, z[f"parent_l{lvl}"]) and np.array_equal(off, z[f"off_l{lvl}"])
+            assert np.array_equal(O.child_table(parent, off, nc), z[f"child_l{lvl}"])
+        s //= 2
+
+
+def test_unet_small_fixture_reproduces():
+    z = np.load(os.path.join(G, "unet_small.npz"))
+    net = UNetSCN(in_channels=3, m=4, num_planes=4, full_scale=64, backend=scn_cpu).double()
+    sd = {k[len("param:"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param:")}
+    net.load_state_dict(sd, strict=False)
+    x = torch.from_numpy(z["feats"]).double().requires_grad_(True)
+    out = net([torch.from_numpy(z["coords"]), x])
+    assert torch.allclose(out, torch.from_numpy(z["out"]), atol=1e-12)
+    (gx,) = torch.autograd.grad(out, x, torch.from_numpy(z["grad_out"]))
+    assert torch.allclose(gx, torch.from_numpy(z["grad_feats"]), atol=1e-12)

@@ -1,0 +1,359 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): voxel ids / level coordinates / rule tables BIT-EXACT;
+FP32-mode activations and gradients within 1e-4 relative error (max-abs error over max-abs
+reference, per tensor); TF32 / BF16 tensor-core modes within 1e-2.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lift_oracle, scn_cpu
+from oracle import scn_oracle as O
+from mm2d3d_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+TOL = {"fp32": 1e-4, "tf32": 1e-2, "bf16": 1e-2}
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    denom = b.abs().max().item()
+    return (a - b).abs().max().item() / (denom if denom > 0 else 1.0)
+
+
+def _scn():
+    import mm2d3d_b200.scn as scn
+    return scn
+
+
+def _meta(coords, spatial, levels):
+    from mm2d3d_b200.metadata import Metadata
+    return Metadata(torch.from_numpy(coords).to(DEV), spatial, levels)
+
+
+def _cloud(seed, n=400, b=3, span=40, origin=100):
+    rng = np.random.default_rng(seed)
+    pts = []
+    for s in range(b):
+        u = rng.integers(0, span, (n, 2))
+        z = (u[:, 0] // 3 + rng.integers(0, 2, n)) % span
+        pts.append(np.concatenate([np.stack([u[:, 0], u[:, 1], z], 1) + origin, np.full((n, 1), s)], 1))
+    return np.concatenate(pts, 0).astype(np.int64)
+
+
+# ------------------------------------------------------------------------------ structure
+def _check_structure(coords, spatial, levels):
+    ref = O.Metadata(coords, spatial)
+    meta = _meta(coords, spatial, levels)
+    assert np.array_equal(meta.p2v().cpu().numpy(), ref.p2v)
+    assert np.array_equal(meta.npts().cpu().numpy(), ref.npts)
+    s = spatial
+    for lvl in range(levels):
+        assert np.array_equal(meta.coords_at(s).cpu().numpy(), ref.coords_at(s)), f"coords level {lvl}"
+        assert np.array_equal(meta.nbr_table(s).cpu().numpy(), ref.nbr(s)), f"nbr level {lvl}"
+        if lvl + 1 < levels:
+            parent, off, child = meta.down_tables(s)
+            rp, ro, nc = ref.down(s)
+            assert np.array_equal(parent.cpu().numpy(), rp)
+            assert np.array_equal(off.cpu().numpy(), ro)
+            assert np.array_equal(child.cpu().numpy(), O.child_table(rp, ro, nc))
+        s //= 2
+    return meta, ref
+
+
+def test_structure_a10_known_answer():
+    locs = np.array([(1, 1, 1, 0), (2, 1, 1, 0), (1, 1, 1, 0), (5, 5, 5, 0), (1, 1, 1, 1), (4, 5, 5, 0)], dtype=np.int64)
+    meta, _ = _check_structure(locs, 4096, 2)
+    assert meta.p2v().tolist() == [0, 1, 0, 2, 3, 4]
+    assert meta.coords_at(2048).tolist() == [[0, 0, 0, 0], [1, 0, 0, 0], [2, 2, 2, 0], [0, 0, 0, 1]]
+
+
+def test_structure_golden_fixture():
+    z = np.load(os.path.join(G, "structure_small.npz"))
+    meta = _meta(z["coords"], 4096, 4)
+    assert np.array_equal(meta.p2v().cpu().numpy(), z["p2v"])
+    s = 4096
+    for lvl in range(4):
+        assert np.array_equal(meta.coords_at(s).cpu().numpy(), z[f"coords_l{lvl}"])
+        assert np.array_equal(meta.nbr_table(s).cpu().numpy(), z[f"nbr_l{lvl}"])
+        if lvl < 3:
+            parent, off, child = meta.down_tables(s)
+            assert np.array_equal(parent.cpu().numpy(), z[f"parent_l{lvl}"])
+            assert np.array_equal(child.cpu().numpy(), z[f"child_l{lvl}"])
+        s //= 2
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_structure_random_clouds(seed):
+    _check_structure(_cloud(seed), 4096, 5)
+
+
+def test_structure_edge_cases():
+    # empty input
+    meta = _meta(np.zeros((0, 4), np.int64), 16, 3)
+    assert meta.n_voxels == 0 and meta.level(8).n == 0
+    # single point; all points identical; borders of the grid (no wrap-around neighbours)
+    _check_structure(np.array([[3, 3, 3, 0]], dtype=np.int64), 16, 3)
+    _check_structure(np.array([[7, 7, 7, 2]] * 50, dtype=np.int64), 16, 4)
+    _check_structure(np.array([[0, 0, 0, 0], [15, 15, 15, 0], [0, 0, 15, 0], [15, 0, 0, 1]], dtype=np.int64), 16, 4)
+    # lazily built level (not part of the pre-built pyramid)
+    coords = _cloud(4)
+    ref = O.Metadata(coords, 4096)
+    meta = _meta(coords, 4096, 1)
+    parent, off, child = meta.down_tables(4096)
+    rp, ro, nc = ref.down(4096)
+    assert np.array_equal(parent.cpu().numpy(), rp) and np.array_equal(child.cpu().numpy(), O.child_table(rp, ro, nc))
+    assert np.array_equal(meta.nbr_table(2048).cpu().numpy(), ref.nbr(2048))
+    # out-of-range coordinates raise
+    with pytest.raises(ValueError):
+        _meta(np.array([[16, 0, 0, 0]], dtype=np.int64), 16, 1)
+    with pytest.raises(ValueError):
+        _meta(np.array([[0, -1, 0, 0]], dtype=np.int64), 16, 1)
+
+
+def test_structure_nuscenes_scan_all_levels():
+    """One full synthetic nuScenes-shaped scan (~34k points), all 7 levels, bit-exact."""
+    locs, _ = synth.make_batch("nuscenes", batch=2, seed0=0)
+    _check_structure(locs, 4096, 7)
+
+
+def test_structure_full_batch_properties():
+    """Batch-8 (BASELINE config 2) -- size-independent invariants instead of the CPU oracle."""
+    locs, _ = synth.make_batch("nuscenes", batch=8, seed0=0)
+    meta = _meta(locs, 4096, 7)
+    p2v = meta.p2v().long()
+    assert int(meta.npts().sum()) == locs.shape[0]
+    assert int(p2v.max()) + 1 == meta.n_voxels
+    # first-occurrence numbering: the running maximum of p2v grows by at most one per point
+    cm = torch.cummax(p2v, 0).values
+    assert int((cm[1:] - cm[:-1]).max()) <= 1 and int(p2v[0]) == 0
+    # every point's voxel coordinate equals the point's coordinate
+    vc = meta.coords_at(4096)
+    assert torch.equal(vc[p2v], torch.from_numpy(locs).to(DEV))
+    s, prev = 4096, None
+    for lvl in range(7):
+        lv = meta.level(s)
+        if prev is not None:
+            assert lv.n <= prev
+        prev = lv.n
+        t = meta.nbr_table(s).long()
+        n = t.shape[0]
+        assert torch.equal(t[:, 13], torch.arange(n, device=DEV))
+        # symmetry: nbr[j][k] == i  <=>  nbr[i][26-k] == j
+        for k in (0, 4, 10, 12):
+            j = torch.nonzero(t[:, k] >= 0).squeeze(1)
+            assert torch.equal(t[t[j, k], 26 - k], j)
+        if lvl < 6:
+            parent, off, child = meta.down_tables(s)
+            f = torch.arange(n, device=DEV)
+            assert torch.equal(child[parent.long(), off.long()].long(), f)
+            assert torch.equal(meta.coords_at(s // 2)[parent.long()][:, :3], meta.coords_at(s)[:, :3] >> 1)
+        s //= 2
+
+
+# ------------------------------------------------------------------------------ single ops
+def test_io_layers():
+    from mm2d3d_b200 import functional as F
+    coords = _cloud(7, n=500, b=2, span=12)
+    ref = O.Metadata(coords, 4096)
+    meta = _meta(coords, 4096, 1)
+    torch.manual_seed(0)
+    for c, mode in ((3, 4), (1, 4), (16, 3)):
+        feats = torch.randn(coords.shape[0], c)
+        x_ref = feats.clone().requires_grad_(True)
+        x = feats.to(DEV).requires_grad_(True)
+        v_ref = O.input_layer(ref, x_ref, mode)
+        v = F.InputLayerFn.apply(x, meta, mode)
+        assert rel_err(v, v_ref) < 1e-6
+        o_ref = O.output_layer(ref, v_ref)
+        o = F.OutputLayerFn.apply(v, meta)
+        assert rel_err(o, o_ref) < 1e-6
+        g = torch.randn_like(o_ref)
+        (gx_ref,) = torch.autograd.grad(o_ref, x_ref, g)
+        (gx,) = torch.autograd.grad(o, x, g.to(DEV))
+        assert rel_err(gx, gx_ref) < 1e-5
+
+
+CONV_SHAPES = [(3, 16), (16, 16), (32, 16), (48, 48), (64, 96), (112, 112), (192, 96), (20, 7)]
+
+
+@pytest.mark.parametrize("mode", ["fp32"])
+@pytest.mark.parametrize("kind", ["smc", "down", "up"])
+def test_conv_fwd_bwd(kind, mode):
+    from mm2d3d_b200 import functional as F
+    coords = _cloud(11, n=700, b=2, span=24)
+    ref = O.Metadata(coords, 4096)
+    meta = _meta(coords, 4096, 2)
+    torch.manual_seed(1)
+    for c_in, c_out in CONV_SHAPES:
+        K = 27 if kind == "smc" else 8
+        if kind == "up":
+            n_in = ref.down(4096)[2]
+            spatial_in = 2048
+        else:
+            n_in = ref.npts.shape[0]
+            spatial_in = 4096
+        xr = torch.randn(n_in, c_in, requires_grad=True)
+        wr = (torch.randn(K, 1, c_in, c_out) / (c_in ** 0.5)).requires_grad_(True)
+        if kind == "smc":
+            yr = O.submanifold_conv(ref, 4096, xr, wr)
+        elif kind == "down":
+            yr = O.conv_down(ref, 4096, xr, wr)
+        else:
+            yr = O.deconv_up(ref, 4096, xr, wr)
+        x = xr.detach().to(DEV).requires_grad_(True)
+        w = wr.detach().to(DEV).requires_grad_(True)
+        y = F.TableConvFn.apply(x, w, meta, kind, spatial_in, mode)
+        assert y.shape == yr.shape
+        tol = TOL[mode]
+        assert rel_err(y, yr) < tol, (kind, c_in, c_out, "fwd", rel_err(y, yr))
+        g = torch.randn_like(yr)
+        gxr, gwr = torch.autograd.grad(yr, (xr, wr), g)
+        gx, gw = torch.autograd.grad(y, (x, w), g.to(DEV))
+        assert rel_err(gx, gxr) < tol, (kind, c_in, c_out, "dgrad", rel_err(gx, gxr))
+        assert rel_err(gw, gwr) < tol, (kind, c_in, c_out, "wgrad", rel_err(gw, gwr))
+
+
+@pytest.mark.parametrize("c", [16, 48, 112, 192, 6])
+def test_bnrelu(c):
+    from mm2d3d_b200 import functional as F
+    torch.manual_seed(2)
+    for n, leak, training in ((1000, 0.0, True), (37, 0.333, True), (500, 0.0, False), (1, 0.0, True)):
+        xr = (torch.randn(n, c) * 2 + 0.5).requires_grad_(True)
+        gr = (1 + 0.2 * torch.randn(c)).requires_grad_(True)
+        br = (0.1 * torch.randn(c)).requires_grad_(True)
+        rm_r, rv_r = torch.randn(c) * 0.1, torch.rand(c) + 0.5
+        rm, rv = rm_r.clone().to(DEV), rv_r.clone().to(DEV)
+        yr = O.batchnorm_relu(xr, gr, br, rm_r, rv_r, 1e-4, 0.9, training, leak)
+        x = xr.detach().to(DEV).requires_grad_(True)
+        g_ = gr.detach().to(DEV).requires_grad_(True)
+        b_ = br.detach().to(DEV).requires_grad_(True)
+        y = F.BatchNormReLUFn.apply(x, g_, b_, rm, rv, 1e-4, 0.9, leak, training)
+        assert rel_err(y, yr) < 1e-4
+        if n > 1:
+            assert rel_err(rm, rm_r) < 1e-5 and rel_err(rv, rv_r) < 1e-5
+        go = torch.randn_like(yr)
+        ref_grads = torch.autograd.grad(yr, (xr, gr, br), go)
+        grads = torch.autograd.grad(y, (x, g_, b_), go.to(DEV))
+        if n > 1:
+            for a, b in zip(grads, ref_grads):
+                assert rel_err(a, b) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_lift2d_reference_fixture(dtype):
+    """lift_ref.npz comes from the reference's own L2G_classifier_2D (tests/golden/make_golden.py)."""
+    from mm2d3d_b200.lift import LiftIndices, lift2d
+    z = np.load(os.path.join(G, "lift_ref.npz"))
+    offs = np.concatenate([[0], np.cumsum(z["counts"])])
+    idx = [z["idx"][offs[i]:offs[i + 1]] for i in range(len(z["counts"]))]
+    fmap = torch.from_numpy(z["fmap"]).to(DEV, dtype).requires_grad_(True)
+    out = lift2d(fmap, idx)
+    want = torch.from_numpy(z["lifted"]).to(dtype)
+    assert torch.equal(out.detach().cpu(), want)  # a gather is exact in every dtype
+    (g,) = torch.autograd.grad(out, fmap, torch.from_numpy(z["grad_out"]).to(DEV, dtype))
+    tol = 1e-6 if dtype == torch.float32 else 2e-2
+    assert rel_err(g, torch.from_numpy(z["grad_fmap"])) < tol
+    # pre-uploaded indices give the same result
+    li = LiftIndices(idx, DEV)
+    assert torch.equal(lift2d(fmap, li), out)
+
+
+def test_lift2d_benchmark_shape():
+    from mm2d3d_b200.lift import lift2d
+    torch.manual_seed(3)
+    fmap = torch.randn(8, 6, 225, 400)
+    idx = synth.make_img_indices([3000] * 8, seed=1)
+    idx[3] = synth.make_img_indices([3000], seed=2, window=50)[0]  # duplicate-heavy sample
+    a = fmap.clone().requires_grad_(True)
+    b = fmap.clone().to(DEV).requires_grad_(True)
+    ra = lift_oracle.lift2d(a, idx)
+    rb = lift2d(b, idx)
+    assert torch.equal(rb.detach().cpu(), ra.detach())
+    g = torch.randn_like(ra)
+    (ga,) = torch.autograd.grad(ra, a, g)
+    (gb,) = torch.autograd.grad(rb, b, g.to(DEV))
+    assert rel_err(gb, ga) < 1e-6
+
+
+# ------------------------------------------------------------------------------ whole network
+def _run_pair(net_ref, net, coords, feats, tol):
+    xr = feats.clone().requires_grad_(True)
+    x = feats.clone().to(DEV).requires_grad_(True)
+    out_r = net_ref([coords, xr])
+    out = net([coords.to(DEV), x])
+    assert out.shape == out_r.shape
+    assert rel_err(out, out_r) < tol, ("forward", rel_err(out, out_r))
+    g = torch.randn_like(out_r)
+    pr = dict(net_ref.named_parameters())
+    p = dict(net.named_parameters())
+    gr = torch.autograd.grad(out_r, [xr] + list(pr.values()), g)
+    gg = torch.autograd.grad(out, [x] + [p[k] for k in pr], g.to(DEV))
+    worst = 0.0
+    for name, a, b in zip(["feats"] + list(pr), gg, gr):
+        e = rel_err(a, b)
+        worst = max(worst, e)
+        assert e < tol * 5, (name, e)  # gradients pass through up to 60 layers: 5x the per-op bar
+    for (k, a), (_, b) in zip(net.named_buffers(), net_ref.named_buffers()):
+        assert rel_err(a, b) < 1e-4, k
+    return worst
+
+
+def test_unet_small_golden_fixture():
+    from mm2d3d_b200.unet import UNetSCN
+    z = np.load(os.path.join(G, "unet_small.npz"))
+    net = UNetSCN(in_channels=3, m=4, num_planes=4, full_scale=64).to(DEV)
+    sd = {k[len("param:"):]: torch.from_numpy(z[k]).float() for k in z.files if k.startswith("param:")}
+    net.load_state_dict(sd, strict=False)
+    x = torch.from_numpy(z["feats"]).to(DEV).requires_grad_(True)
+    out = net([torch.from_numpy(z["coords"]).to(DEV), x])
+    assert rel_err(out, torch.from_numpy(z["out"])) < 1e-4
+    params = dict(net.named_parameters())
+    grads = torch.autograd.grad(out, [x] + list(params.values()), torch.from_numpy(z["grad_out"]).float().to(DEV))
+    assert rel_err(grads[0], torch.from_numpy(z["grad_feats"])) < 5e-4
+    for (name, _), g in zip(params.items(), grads[1:]):
+        assert rel_err(g, torch.from_numpy(z["grad:" + name])) < 5e-4, name
+    for name, b in net.named_buffers():
+        assert rel_err(b, torch.from_numpy(z["buffer_after:" + name])) < 1e-4, name
+
+
+def test_unetscn_full_config_one_scan():
+    """BASELINE config 1: UNetSCN(m=16, 7 planes, full_scale 4096) on one nuScenes-shaped scan."""
+    from mm2d3d_b200.unet import UNetSCN
+    torch.manual_seed(5)
+    locs, feats = synth.make_batch("nuscenes", batch=1, seed0=3)
+    net_ref = UNetSCN(in_channels=3, backend=scn_cpu)
+    net = UNetSCN(in_channels=3).to(DEV)
+    net.load_state_dict(net_ref.state_dict())
+    worst = _run_pair(net_ref, net, torch.from_numpy(locs), torch.from_numpy(feats), TOL["fp32"])
+    print("worst gradient rel err", worst)
+
+
+def test_module_surface_matches_reference_usage():
+    """The call pattern of 3d_net/scn_unet.py:129-143 (its only 'test'): b=2, n=100 random coords."""
+    from mm2d3d_b200.unet import UNetSCN
+    b, n = 2, 100
+    coords = torch.randint(4096, [b, n, 3])
+    batch_idxs = torch.arange(b).reshape(b, 1, 1).repeat(1, n, 1)
+    coords = torch.cat([coords, batch_idxs], 2).reshape(-1, 4)
+    feats = torch.rand(b * n, 3)
+    net = UNetSCN(3).cuda()
+    out = net([coords, feats.cuda()])  # coords stay on the CPU as in the reference
+    assert out.shape == (200, 16) and out.is_cuda
+    # eval mode uses running statistics and does not touch them
+    net.eval()
+    before = net.layer4.running_mean.clone()
+    net([coords, feats.cuda()])
+    assert torch.equal(before, net.layer4.running_mean)
+    # autocast does not change the 3D branch (FP32 inside)
+    net.train()
+    with torch.autocast("cuda", dtype=torch.float16):
+        out16 = net([coords, feats.cuda()])
+    assert out16.dtype == torch.float32
