@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: UNetSCN forward+backward on synthetic nuScenes-shaped scans.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fp32|tf32|bf16] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch (default 8 scans per GPU, BASELINE.json
+configs[1]): structure build (voxel hash, 7-level pyramid, rule tables), UNetSCN forward, backward
+to the point features and all parameters, and -- for N > 1 -- the flat-gradient all-reduce.
+Prints ONE JSON line (rank 0).  ``--impl reference`` times the CPU restatement of the reference's
+SparseConvNet path (oracle/, the dependency itself is not installable here) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "UNetSCN fwd+bwd scans/sec"
+UNIT = "scans/s"
+NET_KW = dict(in_channels=3, m=16, block_reps=1, residual_blocks=False, full_scale=4096, num_planes=7)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("MM3D_BENCH_MODE", "fp32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--shape", default="nuscenes", choices=["nuscenes", "semantickitti"])
+    ap.add_argument("--batch", type=int, default=8, help="scans per GPU per step")
+    ap.add_argument("--rotate", type=int, default=4, help="distinct resident input batches cycled through")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-pass", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            p = json.load(open(path))
+            return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops", 0)), "source": "measured"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_scans_per_s(iters, warmup, shape):
+    """The reference's CPU path restated (oracle/): SparseConvNet's CPU algorithm -- hash-map rule
+    books + per-offset index_select -> matmul -> index_add_ -- incl. structure build, 1 scan/step."""
+    import torch
+
+    from mm2d3d_b200 import synth
+    from mm2d3d_b200.unet import UNetSCN
+    from oracle import scn_cpu
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    net = UNetSCN(backend=scn_cpu, **NET_KW)
+    locs, feats = synth.make_batch(shape, batch=1, seed0=0)
+    locs_t, feats_t = torch.from_numpy(locs), torch.from_numpy(feats)
+    g = torch.randn(locs.shape[0], NET_KW["m"])
+    times = []
+    for i in range(warmup + iters):
+        t0 = time.perf_counter()
+        x = feats_t.clone().requires_grad_(True)
+        out = net([locs_t, x])
+        out.backward(g)
+        dt = time.perf_counter() - t0
+        for p in net.parameters():
+            p.grad = None
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"value": len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(times)} x (1 {shape}-shaped scan, {locs.shape[0]} points, fwd+bwd incl. rulebook build), "
+                      f"{warmup} warm-up, torch {torch.__version__} CPU ops, {cores} threads",
+            "ms_per_scan": 1e3 * total / len(times)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_reference_scans_per_s(max(args.steps, 1), max(min(args.warmup, 3), 1), args.shape)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_scan"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"UNetSCN(m=16, 7 planes, full_scale=4096) fwd+bwd, {args.shape}-shaped scans; "
+                               f"CPU sample: 1 scan per step", "reference": "oracle port of SparseConvNet CPU path "
+                   "(sparseconvnet@dcf6a7ff is not vendored/installable: no source, no network)"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ kernel pass
+def kernel_pass(net, locs_d, feats_d, mode, pk):
+    """Time every sparse-convolution launch of one forward+backward individually (CUDA events on
+    the launching stream, L2 flushed before each timed launch) through the C ABI, and report the
+    roofline of the slowest one plus the time split by op family."""
+    import torch
+
+    from mm2d3d_b200 import _lib
+    from mm2d3d_b200 import functional as F
+    from mm2d3d_b200.scn import _ConvBase
+
+    lib = _lib.lib
+    dev = feats_d.device
+    records = []
+
+    def hook(mod, inp, out):
+        x = inp[0]
+        records.append((mod, x.features.detach(), x.metadata, int(x.spatial_size[0])))
+
+    hooks = [m.register_forward_hook(hook) for m in net.modules() if isinstance(m, _ConvBase)]
+    names = {m: n for n, m in net.named_modules()}
+    with torch.no_grad():
+        net([locs_d, feats_d])
+    for h in hooks:
+        h.remove()
+
+    flush = torch.empty(384 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    m = _lib.MODES[mode]
+
+    def timed(fn, reps=3):
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sum(ts) / len(ts)
+
+    rows = []
+    for mod, x, meta, spatial in records:
+        w = mod.weight.detach()
+        K, c_in, c_out = w.shape[0], w.shape[2], w.shape[3]
+        fwd_t, bwd_t, bwd_flags = F.conv_tables(meta, mod.kind, spatial)
+        out = torch.empty(fwd_t.n_out, c_out, device=dev)
+        dout = torch.randn(fwd_t.n_out, c_out, device=dev)
+        dx = torch.empty(bwd_t.n_out, c_in, device=dev)
+        dw = torch.empty_like(w)
+        ws = F.scratch(max(lib.mm3d_conv_workspace_bytes(fwd_t.n_in, fwd_t.n_out, c_in, c_out, K, m),
+                           lib.mm3d_conv_workspace_bytes(bwd_t.n_in, bwd_t.n_out, c_out, c_in, K, m)), dev)
+        sp = _lib.stream_ptr()
+        # pairs of the rule table (for flops)
+        if fwd_t.onehot is None:
+            lv = meta.level(spatial)
+            cap = fwd_t.stride
+            if mod.kind == "smc":
+                t = meta._lv_view(lv, lv.o_nbr, torch.int32, 27 * cap).view(27, cap)[:, :fwd_t.n_out]
+            else:
+                t = meta._lv_view(lv, lv.o_child, torch.int32, 8 * cap).view(8, cap)[:, :fwd_t.n_out]
+            pairs = int((t >= 0).sum())
+        else:
+            pairs = fwd_t.n_out
+
+        def f_fwd():
+            _lib.check(lib.mm3d_conv_fwd(x.data_ptr(), fwd_t.n_in, c_in, out.data_ptr(), fwd_t.n_out, c_out,
+                                         w.data_ptr(), K, fwd_t.tbl, fwd_t.stride, fwd_t.onehot, 0, m,
+                                         ws.data_ptr(), ws.numel(), sp))
+
+        def f_dgrad():
+            _lib.check(lib.mm3d_conv_fwd(dout.data_ptr(), bwd_t.n_in, c_out, dx.data_ptr(), bwd_t.n_out, c_in,
+                                         w.data_ptr(), K, bwd_t.tbl, bwd_t.stride, bwd_t.onehot, bwd_flags, m,
+                                         ws.data_ptr(), ws.numel(), sp))
+
+        def f_wgrad():
+            _lib.check(lib.mm3d_conv_wgrad(x.data_ptr(), fwd_t.n_in, c_in, dout.data_ptr(), fwd_t.n_out, c_out,
+                                           dw.data_ptr(), K, fwd_t.tbl, fwd_t.stride, fwd_t.onehot, 0, m,
+                                           ws.data_ptr(), ws.numel(), sp))
+
+        tbl_bytes = 4 * K * fwd_t.n_out if fwd_t.onehot is None else 5 * fwd_t.n_out
+        alg_bytes = 4 * (fwd_t.n_in * c_in + fwd_t.n_out * c_out) + 4 * K * c_in * c_out + tbl_bytes
+        flops = 2 * pairs * c_in * c_out
+        for direction, fn in (("fwd", f_fwd), ("dgrad", f_dgrad), ("wgrad", f_wgrad)):
+            fn()  # warm
+            ms = timed(fn)
+            rows.append({"layer": names[mod], "kind": mod.kind, "dir": direction, "c_in": c_in, "c_out": c_out,
+                         "n_in": fwd_t.n_in, "n_out": fwd_t.n_out, "pairs": pairs, "ms": ms,
+                         "alg_bytes": alg_bytes, "flops": flops})
+    top = max(rows, key=lambda r: r["ms"])
+    ach = top["alg_bytes"] / (top["ms"] * 1e-3) / 1e9
+    split = {}
+    for r in rows:
+        split[r["kind"] + "_" + r["dir"]] = split.get(r["kind"] + "_" + r["dir"], 0.0) + r["ms"]
+    roofline = {
+        "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+        "traffic": None, "peak_source": pk["source"],
+        "kernel": f"conv {top['kind']} {top['dir']} {top['c_in']}->{top['c_out']} @ {top['layer']} "
+                  f"({top['n_out']} rows, {top['pairs']} pairs), mode {mode}",
+        "launch_ms": top["ms"], "alg_bytes_per_launch": top["alg_bytes"],
+        "achieved_tflops": top["flops"] / (top["ms"] * 1e-3) / 1e12,
+        "conv_ms_by_family": {k: round(v, 4) for k, v in sorted(split.items())},
+        "conv_total_ms": round(sum(r["ms"] for r in rows), 4),
+        "conv_total_gflop": round(sum(r["flops"] for r in rows) / 1e9, 3),
+    }
+    return roofline, rows
+
+
+# ------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from mm2d3d_b200 import _lib, synth
+    from mm2d3d_b200 import scn as scn_mod
+    from mm2d3d_b200.dp import FlatGradAllReduce
+    from mm2d3d_b200.unet import UNetSCN
+
+    scn_mod.set_conv_mode(args.mode)
+    torch.manual_seed(0)
+    net = UNetSCN(**NET_KW).to(dev)
+    flat = FlatGradAllReduce(net)
+    flat.broadcast_parameters()
+
+    # resident inputs: `rotate` distinct batches per rank (different scans on every rank)
+    host, resident = [], []
+    for r in range(args.rotate):
+        locs, feats = synth.make_batch(args.shape, batch=args.batch, seed0=(rank * args.rotate + r) * args.batch)
+        gout = np.random.default_rng(77 + r).standard_normal((locs.shape[0], NET_KW["m"]), dtype=np.float32)
+        host.append((torch.from_numpy(locs).pin_memory(), torch.from_numpy(feats).pin_memory()))
+        resident.append((torch.from_numpy(locs).to(dev), torch.from_numpy(feats).to(dev), torch.from_numpy(gout).to(dev)))
+    n_points = [int(h[0].shape[0]) for h in host]
+
+    def step(i):
+        locs_d, feats_d, gout = resident[i % args.rotate]
+        flat.zero_()
+        x = feats_d.detach().requires_grad_(True)  # d(feats) is on the path (3d_net/model.py:46-48)
+        out = net([locs_d, x])
+        out.backward(gout)
+        flat.all_reduce_mean()
+        return out
+
+    def step_e2e(i):
+        locs_h, feats_h = host[i % args.rotate]
+        gout = resident[i % args.rotate][2]
+        locs_d = locs_h.to(dev, non_blocking=True)
+        feats_d = feats_h.to(dev, non_blocking=True)
+        flat.zero_()
+        x = feats_d.requires_grad_(True)
+        out = net([locs_d, x])
+        out.backward(gout)
+        flat.all_reduce_mean()
+        return float((out.detach() * gout).sum().item())  # the step's scalar result, read back to the host
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.lib.mm3d_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.lib.mm3d_kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end: pinned host inputs -> device -> fwd+bwd (-> all-reduce) -> scalar back to the host
+    for i in range(min(args.warmup, 3)):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        pk = peaks()
+        roofline, cpu = None, None
+        if not args.no_kernel_pass:
+            roofline, rows = kernel_pass(net, resident[0][0], resident[0][1], args.mode, pk)
+            roofline["share_of_step"] = roofline["conv_total_ms"] / (ms / args.steps)
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", f"kernel_pass_{args.mode}.json"), "w") as f:
+                json.dump(rows, f, indent=0)
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_reference_scans_per_s(5, 1, args.shape)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        scans = world * args.batch * args.steps
+        avg_pts = sum(n_points) / len(n_points)
+        line = {
+            "impl": "ours", "metric": METRIC, "value": scans / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.mode], "data": "synthetic",
+            "config": {
+                "workload": f"UNetSCN(m=16, 7 planes, full_scale=4096) fwd+bwd, batch {args.batch} "
+                            f"{args.shape}-shaped scans per GPU (BASELINE configs[1])",
+                "scans_per_gpu": args.batch, "points_per_batch": avg_pts, "conv_mode": args.mode,
+                "parallelism": f"dp{world} by scan, flat-gradient all-reduce ({flat.nbytes} B)" if world > 1 else "single GPU",
+                "l2": f"{args.rotate} rotating resident input batches; one step touches >1 GB of activations/tables, "
+                      "far above the 126 MB L2, so no step starts with its data cached",
+                "step": "structure build + forward + backward (d_feats and all parameter grads)"
+                        + (" + gradient all-reduce" if world > 1 else ""),
+            },
+            "clocks": clocks,
+            "e2e": {"value": scans / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(avg_pts * (32 + 4 * NET_KW["in_channels"])), "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+        }
+        if roofline is not None:
+            line["roofline"] = roofline
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,8 @@ MM3D_API int mm3d_abi_version(void);
 MM3D_API const char* mm3d_last_error(void);
 /* 1 if the running device is compute capability 10.x (tcgen05 paths usable), 0 otherwise, <0 on error */
 MM3D_API int mm3d_device_supports_tc(void);
+/* number of CUDA kernels this library has launched in this process (for the benchmark's gpu_launches) */
+MM3D_API long long mm3d_kernel_launches(void);
 
 /* ------------------------------------------------------------------------------------------
  * Structure: replaces SparseConvNet's CPU-only Metadata<3> (InputLayer rules,

@@ -241,6 +241,7 @@ extern "C" int mm3d_bnrelu_fwd(const float* x, float* y, int64_t n, int c, const
   }
   BN_DISPATCH(k_bn_apply, x, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, sums, eps,
               momentum, leakiness, training);
+  mm3d_count_launches(training ? 2 : 1);
   MM3D_CHECK_LAUNCH("mm3d_bnrelu_fwd");
   return MM3D_OK;
 }
@@ -267,6 +268,7 @@ extern "C" int mm3d_bnrelu_bwd(const float* x, const float* dy, float* dx, int64
   BN_DISPATCH(k_bn_bwd_stats, x, dy, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums);
   BN_DISPATCH(k_bn_bwd_apply, x, dy, dx, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums, d_gamma,
               d_beta, training);
+  mm3d_count_launches(2);
   MM3D_CHECK_LAUNCH("mm3d_bnrelu_bwd");
   return MM3D_OK;
 }

@@ -12,6 +12,11 @@ void mm3d_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void mm3d_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long mm3d_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
 extern "C" const char* mm3d_last_error(void) { return g_err; }
 extern "C" int mm3d_abi_version(void) { return MM3D_ABI_VERSION; }
 

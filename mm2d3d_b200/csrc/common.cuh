@@ -10,6 +10,7 @@
 #define MM3D_NUM_SMS 148  // B200: 2 dies x 74 SMs; persistent / grid-stride kernels size to this
 
 void mm3d_set_error(const char* fmt, ...);
+void mm3d_count_launches(int n);  // bookkeeping for mm3d_kernel_launches()
 
 #define MM3D_REQUIRE(cond, code, ...)     \
   do {                                    \

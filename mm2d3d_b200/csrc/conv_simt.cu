@@ -271,6 +271,7 @@ int mm3d_conv_fwd_simt(const float* in, int64_t n_in, int c_in, float* out, int6
     default: MM3D_REQUIRE(false, MM3D_ERR_UNSUPPORTED, "SIMT conv: c_out %d", c_out);
   }
 #undef FWD_CASE
+  mm3d_count_launches(W == weight ? 1 : 2);
   MM3D_CHECK_LAUNCH("mm3d_conv_fwd_simt");
   return MM3D_OK;
 }
@@ -304,6 +305,7 @@ int mm3d_conv_wgrad_simt(const float* in, int64_t n_in, int c_in, const float* d
   }
 #undef WG_TI
   MM3D_REQUIRE(miss == 0, MM3D_ERR_UNSUPPORTED, "SIMT wgrad: no kernel for channels (%d,%d)", c_in, c_out);
+  mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_conv_wgrad_simt");
   return MM3D_OK;
 }

@@ -304,6 +304,7 @@ extern "C" int mm3d_voxelize(const int64_t* coords, int64_t n_points, int spatia
                                                      hash_keys, hash_vals, vox_keys);
     k_ids_level0<<<mm3d_grid(n_points, 256), 256, 0, stream>>>(w.item_slot, hash_vals, w.n_items, p2v, npts);
   }
+  mm3d_count_launches(n_points > 0 ? 7 : 2);
   MM3D_CHECK_LAUNCH("mm3d_voxelize");
   return MM3D_OK;
 }
@@ -334,6 +335,7 @@ extern "C" int mm3d_coarsen(const uint64_t* fine_keys, const int32_t* n_fine_dev
     k_ids_coarsen<<<mm3d_grid(n_fine_cap, 256), 256, 0, stream>>>(w.item_slot, hash_vals, w.n_items, fine_keys,
                                                                  parent, off, child_tbl, tbl_stride);
   }
+  mm3d_count_launches(n_fine_cap > 0 ? 7 : 2);
   MM3D_CHECK_LAUNCH("mm3d_coarsen");
   return MM3D_OK;
 }
@@ -347,6 +349,7 @@ extern "C" int mm3d_build_nbr27(const uint64_t* keys, const int32_t* n_dev, int6
   if (n_cap > 0)
     k_nbr27<<<mm3d_grid(27 * n_cap, 256), 256, 0, stream>>>(keys, n_dev, spatial_size, hash_keys, hash_vals,
                                                            hash_vals + (hash_cap - 1), nbr_tbl, tbl_stride);
+  mm3d_count_launches(n_cap > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_build_nbr27");
   return MM3D_OK;
 }

@@ -133,6 +133,7 @@ extern "C" int mm3d_input_fwd(const float* feats, const int32_t* p2v, const int3
   if (n_vox > 0) MM3D_CUDA(cudaMemsetAsync(out_vox, 0, sizeof(float) * (size_t)n_vox * c, stream));
   if (n_points > 0)
     k_input_fwd<<<mm3d_grid(n_points * c, 256), 256, 0, stream>>>(feats, p2v, npts, n_points, c, mode, out_vox);
+  mm3d_count_launches(n_points > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_input_fwd");
   return MM3D_OK;
 }
@@ -143,6 +144,7 @@ extern "C" int mm3d_input_bwd(const float* d_vox, const int32_t* p2v, const int3
   MM3D_REQUIRE(mode == 3 || mode == 4, MM3D_ERR_UNSUPPORTED, "InputLayer mode %d not implemented", mode);
   if (n_points > 0)
     k_input_bwd<<<mm3d_grid(n_points * c, 256), 256, 0, stream>>>(d_vox, p2v, npts, n_points, c, mode, d_feats);
+  mm3d_count_launches(n_points > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_input_bwd");
   return MM3D_OK;
 }
@@ -157,6 +159,7 @@ extern "C" int mm3d_output_fwd(const float* vox, const int32_t* p2v, int64_t n_p
     else
       k_output_fwd<1><<<mm3d_grid(n_points * c, 256), 256, 0, stream>>>(vox, p2v, n_points, c, out);
   }
+  mm3d_count_launches(n_points > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_output_fwd");
   return MM3D_OK;
 }
@@ -167,6 +170,7 @@ extern "C" int mm3d_output_bwd(const float* d_out, const int32_t* p2v, int64_t n
   if (n_vox > 0) MM3D_CUDA(cudaMemsetAsync(d_vox, 0, sizeof(float) * (size_t)n_vox * c, stream));
   if (n_points > 0)
     k_output_bwd<<<mm3d_grid(n_points * c, 256), 256, 0, stream>>>(d_out, p2v, n_points, c, d_vox);
+  mm3d_count_launches(n_points > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_output_bwd");
   return MM3D_OK;
 }
@@ -183,6 +187,7 @@ extern "C" int mm3d_lift2d_fwd(const void* fmap, int dtype, int B, int C, int H,
     case 2: k_lift_fwd<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)fmap, B, C, H, W, idx, sample_offsets, n, (__nv_bfloat16*)out); break;
     default: MM3D_REQUIRE(false, MM3D_ERR_UNSUPPORTED, "lift dtype %d (0=f32,1=f16,2=bf16)", dtype);
   }
+  mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_lift2d_fwd");
   return MM3D_OK;
 }
@@ -199,6 +204,7 @@ extern "C" int mm3d_lift2d_bwd(const void* d_out, int dtype, int B, int C, int H
     case 2: k_lift_bwd<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)d_out, B, C, H, W, idx, sample_offsets, n, (__nv_bfloat16*)d_fmap); break;
     default: MM3D_REQUIRE(false, MM3D_ERR_UNSUPPORTED, "lift dtype %d (0=f32,1=f16,2=bf16)", dtype);
   }
+  mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_lift2d_bwd");
   return MM3D_OK;
 }

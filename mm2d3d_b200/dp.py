@@ -1,0 +1,63 @@
+"""Scan-sharded data parallelism: one process per GPU, each rank runs the whole hot path on its
+own scans (samples never interact in hashing, rulebooks, convolutions or the I/O layers; BN
+statistics stay per rank exactly like the reference's DDP without SyncBN, ``run.py:262-268``).
+The only exchange step is the gradient mean.
+
+Instead of DDP's 25 MB buckets and per-forward buffer broadcasts, all parameter gradients live in
+ONE flat float32 buffer (10.76 MB for UNetSCN): ``p.grad`` of every parameter is a view into it, so
+backward accumulates straight into the buffer and a single ``all_reduce`` over NCCL (NVLink 5 /
+NVSwitch) averages everything.  At this size the collective is latency-bound, so it is not split.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class FlatGradAllReduce:
+    def __init__(self, module: torch.nn.Module, process_group=None):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        self.group = process_group
+        if not self.params:
+            raise ValueError("module has no trainable parameters")
+        dev, dtype = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=dtype, device=dev)
+        off = 0
+        for p in self.params:
+            if p.device != dev or p.dtype != dtype:
+                raise ValueError("all parameters must share device and dtype")
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * self.flat.element_size()
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def broadcast_parameters(self, src: int = 0):
+        """One-time parameter sync at start-up (what DDP does when it wraps a module)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            for p in self.params:
+                dist.broadcast(p.data, src, group=self.group)
+
+    def all_reduce_mean(self, async_op: bool = False):
+        """Average the flat gradient over the ranks (no-op for a single process)."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        world = dist.get_world_size(self.group)
+        if world == 1:
+            return None
+        self.flat.div_(world)
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+
+
+def shard_scans(n_scans: int, rank: int, world: int):
+    """Indices of the scans rank ``rank`` owns when a global batch is split evenly
+    (``batch_size // gpus`` per process, ``run.py:52-54``)."""
+    if n_scans % world:
+        raise ValueError(f"global batch {n_scans} is not divisible by world size {world}")
+    per = n_scans // world
+    return list(range(rank * per, (rank + 1) * per))

@@ -285,7 +285,8 @@ def test_lift2d_benchmark_shape():
 
 # ------------------------------------------------------------------------------ whole network
 def _run_pair(net_ref, net, coords, feats, tol):
-    xr = feats.clone().requires_grad_(True)
+    """net_ref runs the oracle in FLOAT64, so the error measured is the CUDA path's own FP32 error."""
+    xr = feats.clone().double().requires_grad_(True)
     x = feats.clone().to(DEV).requires_grad_(True)
     out_r = net_ref([coords, xr])
     out = net([coords.to(DEV), x])
@@ -295,7 +296,7 @@ def _run_pair(net_ref, net, coords, feats, tol):
     pr = dict(net_ref.named_parameters())
     p = dict(net.named_parameters())
     gr = torch.autograd.grad(out_r, [xr] + list(pr.values()), g)
-    gg = torch.autograd.grad(out, [x] + [p[k] for k in pr], g.to(DEV))
+    gg = torch.autograd.grad(out, [x] + [p[k] for k in pr], g.float().to(DEV))
     worst = 0.0
     for name, a, b in zip(["feats"] + list(pr), gg, gr):
         e = rel_err(a, b)
@@ -332,6 +333,7 @@ def test_unetscn_full_config_one_scan():
     net_ref = UNetSCN(in_channels=3, backend=scn_cpu)
     net = UNetSCN(in_channels=3).to(DEV)
     net.load_state_dict(net_ref.state_dict())
+    net_ref = net_ref.double()
     worst = _run_pair(net_ref, net, torch.from_numpy(locs), torch.from_numpy(feats), TOL["fp32"])
     print("worst gradient rel err", worst)
 
