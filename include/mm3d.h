@@ -59,6 +59,9 @@ MM3D_API const char* mm3d_last_error(void);
 MM3D_API int mm3d_device_supports_tc(void);
 /* number of CUDA kernels this library has launched in this process (for the benchmark's gpu_launches) */
 MM3D_API long long mm3d_kernel_launches(void);
+/* Synchronises the device and returns (and clears) the sticky error flag a kernel raises when its
+ * internal pipeline timed out: 0 = none, 1 = raised, <0 = could not be read.  Debug / test aid. */
+MM3D_API int mm3d_take_device_error(void);
 
 /* ------------------------------------------------------------------------------------------
  * Structure: replaces SparseConvNet's CPU-only Metadata<3> (InputLayer rules,

@@ -34,6 +34,7 @@ SIGNATURES = {
     "mm3d_last_error": (C.c_char_p, []),
     "mm3d_device_supports_tc": (_i, []),
     "mm3d_kernel_launches": (C.c_longlong, []),
+    "mm3d_take_device_error": (_i, []),
     "mm3d_hash_capacity": (_i64, [_i64]),
     "mm3d_unique_workspace_bytes": (_sz, [_i64]),
     "mm3d_voxelize": (_i, [_p, _i64, _i, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),

@@ -36,9 +36,20 @@ int mm3d_conv_wgrad_simt(const float* in, int64_t n_in, int c_in, const float* d
                          float* d_weight, int K, const int32_t* tbl, int64_t tbl_stride,
                          const uint8_t* onehot_off, int accumulate, cudaStream_t stream);
 
+// conv_tc.cu
+size_t mm3d_conv_tc_workspace_bytes(int c_in, int c_out, int K);
+int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
+                     const float* weight, int K, const int32_t* tbl, int64_t tbl_stride,
+                     const uint8_t* onehot_off, int flags, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 extern "C" size_t mm3d_conv_workspace_bytes(int64_t n_in, int64_t n_out, int c_in, int c_out, int K, int mode) {
   (void)n_in; (void)n_out; (void)mode;
-  return mm3d_conv_simt_workspace_bytes(c_in, c_out, K);
+  // one size for every use of a layer's scratch (forward, dgrad with c_in/c_out swapped, wgrad)
+  size_t a = mm3d_conv_simt_workspace_bytes(c_in, c_out, K);
+  size_t b = mm3d_conv_tc_workspace_bytes(c_in, c_out, K), c = mm3d_conv_tc_workspace_bytes(c_out, c_in, K);
+  if (b > a) a = b;
+  if (c > a) a = c;
+  return a;
 }
 
 static int check_conv_args(const void* in, const void* out, const void* w, const int32_t* tbl, int64_t n_in,
@@ -60,6 +71,9 @@ extern "C" int mm3d_conv_fwd(const float* in, int64_t n_in, int c_in, float* out
     case MM3D_MODE_FP32:
       return mm3d_conv_fwd_simt(in, n_in, c_in, out, n_out, c_out, weight, K, tbl, tbl_stride, onehot_off, flags,
                                 ws, ws_bytes, (cudaStream_t)stream);
+    case MM3D_MODE_TF32:
+      return mm3d_conv_fwd_tc(in, n_in, c_in, out, n_out, c_out, weight, K, tbl, tbl_stride, onehot_off, flags,
+                              ws, ws_bytes, (cudaStream_t)stream);
     default:
       MM3D_REQUIRE(false, MM3D_ERR_UNSUPPORTED, "conv mode %d not implemented in this build", mode);
   }
@@ -74,6 +88,7 @@ extern "C" int mm3d_conv_wgrad(const float* in, int64_t n_in, int c_in, const fl
   if (rc) return rc;
   switch (mode) {
     case MM3D_MODE_FP32:
+    case MM3D_MODE_TF32:  // wgrad has no tcgen05 kernel yet: the FP32 SIMT kernel serves both modes
       return mm3d_conv_wgrad_simt(in, n_in, c_in, d_out, n_out, c_out, d_weight, K, tbl, tbl_stride, onehot_off,
                                   accumulate, (cudaStream_t)stream);
     default:

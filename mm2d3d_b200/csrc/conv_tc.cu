@@ -1,0 +1,455 @@
+// tcgen05 / TMEM rule-table convolution (forward and dgrad) for sm_100a.
+//
+//   out[j,:] = sum_k in[tbl(j,k),:] . W'[k]          j in a tile of 128 output rows
+//
+// Output-stationary implicit GEMM: a CTA owns 128 output rows; for every kernel offset k the
+// 128 neighbour rows (zero where the neighbour is absent) are gathered into a K-major,
+// 128B-swizzled shared-memory tile and multiplied with W'[k] by tcgen05.mma (M=128, N=C_out,
+// kind::tf32), accumulating all K offsets in ONE TMEM accumulator.  No atomics, no read-modify-
+// write of `out`, one coalesced-by-row store per output row: deterministic.
+//
+// Warp roles (192 threads):   warps 0-3  gather producers, then epilogue (TMEM lanes 32w..32w+31)
+//                             warp  4    MMA issuer (one lane) + TMEM allocator
+//                             warp  5    weight loader (cp.async.bulk of the pre-swizzled image)
+// Pipelines (mbarriers):      A ring  : a_full[S]  (128 producer arrivals)  / a_empty[S] (tcgen05.commit)
+//                             B ring  : b_full[2]  (expect_tx + bulk copy)  / b_empty[2] (tcgen05.commit)
+//                             accum   : acc_full   (tcgen05.commit)         / acc_empty  (128 arrivals)
+//
+// Gather: 8 lanes per row read one 128-byte K-block of the row (a full L1 line per request) and
+// write it as one swizzled 128-byte smem row (a conflict-free quarter-warp store).  Absent
+// neighbours cost NO shared-memory traffic: tiles are zeroed once and a thread only re-zeroes a
+// slot it filled the previous time the stage was used -- the 3^3 tables are 10-30 % dense, so this
+// is what keeps the fill proportional to the real pairs instead of 27x the tile.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kKBlock = 32;                 // tf32 elements per 128-byte row of a K-block
+constexpr int kStageBytes = kTileM * 128;   // one A stage = one K-block of 128 rows = 16 KB
+constexpr int kThreads = 192;
+constexpr int kProducers = 128;
+constexpr int kMaxStages = 6;
+constexpr uint32_t kSpinLimit = 1u << 22;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a broken pipeline sets *abort (shared) and the kernel's error flag instead of
+// hanging the GPU; every other wait sees the abort flag and leaves too.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
+  for (uint32_t i = 0; i < kSpinLimit; ++i) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((i & 1023) == 1023 && *abort_flag) return false;
+  }
+  *abort_flag = 1;
+  return false;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major) | SBO>>4 [32,46) = 1024 B between
+// 8-row groups | version=1 [46,48) | layout=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=B=TF32 [7,10)=[10,13)=2,
+// K-major A and B (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+struct TcParams {
+  const float* in;
+  float* out;
+  const float* wimg;  // [K][KB][n_pad][32] tf32, rows 128-byte swizzled
+  const int32_t* tbl;
+  int64_t tbl_stride;
+  const uint8_t* onehot_off;
+  int n_out, c_in, c_out, K, kb, n_pad, num_tiles, stages, tmem_cols;
+  int* err;
+};
+
+// weight image: wimg[k][kb][n][e] = Wsel(k)[kb*32+e][n] (0 beyond c_in / c_out), tf32-rounded,
+// 16-byte chunks of every 128-byte row XOR-swizzled with (n & 7) -- the byte image a
+// SWIZZLE_128B K-major B tile has in shared memory, so the kernel bulk-copies it verbatim.
+__global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ img, int K, int c_in, int c_out,
+                               int kb, int n_pad, int transposed, int mirror) {
+  const int64_t total = (int64_t)K * kb * n_pad * kKBlock;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int e_sw = (int)(i % kKBlock);
+    const int n = (int)((i / kKBlock) % n_pad);
+    const int b = (int)((i / ((int64_t)kKBlock * n_pad)) % kb);
+    const int k = (int)(i / ((int64_t)kKBlock * n_pad * kb));
+    const int chunk = (e_sw >> 2) ^ (n & 7);  // un-swizzle: which logical chunk lives here
+    const int ci = b * kKBlock + chunk * 4 + (e_sw & 3);
+    float v = 0.f;
+    if (ci < c_in && n < c_out) {
+      const int ks = mirror ? K - 1 - k : k;
+      v = transposed ? __ldg(w + ((int64_t)ks * c_out + n) * c_in + ci)   // forward weight is [K][c_out][c_in]
+                     : __ldg(w + ((int64_t)ks * c_in + ci) * c_out + n);  // [K][c_in][c_out]
+    }
+    img[i] = to_tf32(v);
+  }
+}
+
+__device__ __forceinline__ int table_entry(const TcParams& p, int64_t row, int k) {
+  if (row >= p.n_out) return -1;
+  if (p.onehot_off) return (int)__ldg(p.onehot_off + row) == k ? __ldg(p.tbl + row) : -1;
+  return __ldg(p.tbl + (int64_t)k * p.tbl_stride + row);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv_tc(const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [A stages][B x2][barriers][tmem ptr][abort]
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int S = p.stages;
+  const uint32_t b_bytes = (uint32_t)p.n_pad * 128u;
+  const uint32_t b_stride = (b_bytes + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + (uint32_t)S * kStageBytes;
+  const uint32_t bar_base = b_base + 2u * b_stride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar_base - smem_base));
+  // barrier indices
+  auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(kMaxStages + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 + s); };
+  const uint32_t acc_full = bar_base + 8u * (uint32_t)(2 * kMaxStages + 4);
+  const uint32_t acc_empty = bar_base + 8u * (uint32_t)(2 * kMaxStages + 5);
+  constexpr int kNumBars = 2 * kMaxStages + 6;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNumBars);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + kNumBars + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- one-time setup
+  for (uint32_t i = threadIdx.x; i < (uint32_t)S * kStageBytes / 16; i += kThreads)
+    reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(a_full(s), kProducers);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, kProducers);
+    *abort_flag = 0;
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
+  fence_proxy_async();  // the zero fill must be visible to the tensor core's (async-proxy) reads
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int items_per_tile = p.K * p.kb;
+  const int last_chunks = ((p.c_in - (p.kb - 1) * kKBlock) + 3) >> 2;  // 16-byte chunks of the last K-block
+  const bool vec_rows = (p.c_in & 3) == 0;
+
+  if (warp < 4) {
+    // =================================================================== producers + epilogue
+    const int g = threadIdx.x >> 3;  // row within a 16-row pass
+    const int c = threadIdx.x & 7;   // 16-byte chunk within the 128-byte K-block row
+    uint64_t filled = 0;             // bit (stage*8 + pass): this thread's slot holds data, not zeros
+    uint32_t it = 0;                 // A-ring item counter
+    uint32_t tile_iter = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
+      const int64_t row0 = (int64_t)tile * kTileM;
+      int nb_next[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) nb_next[q] = table_entry(p, row0 + q * 16 + g, 0);
+      for (int k = 0; k < p.K; ++k) {
+        int nb[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) nb[q] = nb_next[q];
+        if (k + 1 < p.K) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) nb_next[q] = table_entry(p, row0 + q * 16 + g, k + 1);
+        }
+        for (int b = 0; b < p.kb; ++b, ++it) {
+          const int s = (int)(it % (uint32_t)S);
+          const uint32_t ph = (it / (uint32_t)S) & 1u;
+          const int nchunks = (b == p.kb - 1) ? last_chunks : 8;
+          const bool my_chunk = c < nchunks;
+          // issue the global loads before waiting for the stage
+          float4 v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (nb[q] >= 0 && my_chunk) {
+              const float* src = p.in + (int64_t)nb[q] * p.c_in + b * kKBlock + c * 4;
+              if (vec_rows) {
+                v[q] = __ldg(reinterpret_cast<const float4*>(src));
+              } else {
+                const int rem = p.c_in - (b * kKBlock + c * 4);
+                v[q].x = __ldg(src);
+                if (rem > 1) v[q].y = __ldg(src + 1);
+                if (rem > 2) v[q].z = __ldg(src + 2);
+                if (rem > 3) v[q].w = __ldg(src + 3);
+              }
+            }
+          }
+          if (!mbar_wait(a_empty(s), ph ^ 1u, abort_flag)) goto done;
+          uint8_t* stage = smem + (size_t)s * kStageBytes;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int r = q * 16 + g;
+            const uint64_t bit = 1ull << (s * 8 + q);
+            const bool have = nb[q] >= 0 && my_chunk;
+            if (have || (filled & bit)) {
+              float4 o = make_float4(to_tf32(v[q].x), to_tf32(v[q].y), to_tf32(v[q].z), to_tf32(v[q].w));
+              *reinterpret_cast<float4*>(stage + r * 128 + ((c ^ (r & 7)) << 4)) = o;
+            }
+            filled = have ? (filled | bit) : (filled & ~bit);
+          }
+          fence_proxy_async();
+          mbar_arrive(a_full(s));
+        }
+      }
+      // ---- epilogue of this tile: TMEM -> registers -> global (each thread owns one output row)
+      if (!mbar_wait(acc_full, tile_iter & 1u, abort_flag)) goto done;
+      tc_fence_after();
+      {
+        const int64_t row = row0 + warp * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+          float acc[16];
+          tmem_ld16(taddr + (uint32_t)c0, acc);
+          if (row < p.n_out) {
+            float* dst = p.out + row * p.c_out + c0;
+            if ((p.c_out & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                if (c0 + j < p.c_out) *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.c_out) dst[j] = acc[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty);
+    }
+  } else if (warp == 4) {
+    // =================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(p.n_pad);
+      uint32_t it = 0, bit = 0, tile_iter = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
+        if (!mbar_wait(acc_empty, (tile_iter & 1u) ^ 1u, abort_flag)) break;
+        tc_fence_after();
+        bool ok = true;
+        for (int kk = 0; kk < items_per_tile && ok; ++kk, ++it, ++bit) {
+          const int s = (int)(it % (uint32_t)S);
+          const int bs = (int)(bit & 1u);
+          const int b = kk % p.kb;
+          if (!mbar_wait(b_full(bs), (bit >> 1) & 1u, abort_flag)) { ok = false; break; }
+          if (!mbar_wait(a_full(s), (it / (uint32_t)S) & 1u, abort_flag)) { ok = false; break; }
+          tc_fence_after();
+          const int ksteps = (b == p.kb - 1) ? ((p.c_in - b * kKBlock) + 7) >> 3 : kKBlock / 8;
+          const uint32_t a_addr = a_base + (uint32_t)s * kStageBytes;
+          const uint32_t b_addr = b_base + (uint32_t)bs * b_stride;
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_tf32(tmem_base, make_desc_sw128(a_addr + ks * 32), make_desc_sw128(b_addr + ks * 32), idesc,
+                      (kk | ks) != 0);
+          umma_commit(a_empty(s));
+          umma_commit(b_empty(bs));
+        }
+        if (!ok) break;
+        umma_commit(acc_full);
+      }
+    }
+  } else {
+    // =================================================================== weight loader
+    if (lane == 0) {
+      uint32_t bit = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        bool ok = true;
+        for (int kk = 0; kk < items_per_tile; ++kk, ++bit) {
+          const int bs = (int)(bit & 1u);
+          if (!mbar_wait(b_empty(bs), ((bit >> 1) & 1u) ^ 1u, abort_flag)) { ok = false; break; }
+          mbar_arrive_expect_tx(b_full(bs), b_bytes);
+          bulk_g2s(b_base + (uint32_t)bs * b_stride, p.wimg + (size_t)kk * p.n_pad * kKBlock, b_bytes, b_full(bs));
+        }
+        if (!ok) break;
+      }
+    }
+  }
+done:
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0 && *abort_flag && p.err) atomicExch(p.err, 1);
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+int pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+}  // namespace
+
+// ---- host entry points used by capi.cu -------------------------------------------------------
+
+static int tc_geometry(int c_in, int c_out, int* kb, int* n_pad) {
+  *kb = (c_in + kKBlock - 1) / kKBlock;
+  *n_pad = (c_out + 15) / 16 * 16;
+  return (*n_pad <= 256 && *kb >= 1) ? 0 : 1;
+}
+
+size_t mm3d_conv_tc_workspace_bytes(int c_in, int c_out, int K) {
+  int kb, n_pad;
+  if (tc_geometry(c_in, c_out, &kb, &n_pad)) return 0;
+  return mm3d_align((size_t)K * kb * n_pad * 128);  // weight image
+}
+
+// Sticky per-device error flag set by a kernel whose mbarrier pipeline timed out (never in a
+// correct build; it turns a would-be GPU hang into a reportable error).
+static int* g_err_flag[64] = {nullptr};
+static int* device_err_flag() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!g_err_flag[dev]) {
+    int* p = nullptr;
+    if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, sizeof(int));
+    g_err_flag[dev] = p;
+  }
+  return g_err_flag[dev];
+}
+
+extern "C" int mm3d_take_device_error(void) {
+  int* p = device_err_flag();
+  if (!p) return -1;
+  int v = 0;
+  if (cudaMemcpy(&v, p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (v) cudaMemset(p, 0, sizeof(int));
+  return v;
+}
+
+int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
+                     const float* weight, int K, const int32_t* tbl, int64_t tbl_stride,
+                     const uint8_t* onehot_off, int flags, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  (void)n_in;
+  int kb, n_pad;
+  MM3D_REQUIRE(tc_geometry(c_in, c_out, &kb, &n_pad) == 0, MM3D_ERR_UNSUPPORTED, "tcgen05 conv: c_out %d > 256", c_out);
+  MM3D_REQUIRE(n_out < (1ll << 31), MM3D_ERR_UNSUPPORTED, "tcgen05 conv: too many rows");
+  MM3D_REQUIRE(ws && ws_bytes >= mm3d_conv_tc_workspace_bytes(c_in, c_out, K), MM3D_ERR_WORKSPACE,
+               "tcgen05 conv: workspace too small");
+  MM3D_REQUIRE((((uintptr_t)in | (uintptr_t)out | (uintptr_t)ws) & 15) == 0, MM3D_ERR_INVALID,
+               "tcgen05 conv: pointers must be 16-byte aligned");
+  const bool tr = (flags & MM3D_CONV_TRANSPOSE_W) != 0, mir = (flags & MM3D_CONV_MIRROR_K) != 0;
+  MM3D_REQUIRE(tr || !mir, MM3D_ERR_UNSUPPORTED, "MIRROR_K without TRANSPOSE_W not implemented");
+  if (n_out == 0) return MM3D_OK;
+
+  float* wimg = (float*)ws;
+  int* err = device_err_flag();
+  k_weight_image<<<mm3d_grid((int64_t)K * kb * n_pad * kKBlock, 256), 256, 0, stream>>>(weight, wimg, K, c_in, c_out, kb,
+                                                                                     n_pad, tr ? 1 : 0, mir ? 1 : 0);
+  TcParams p;
+  p.in = in; p.out = out; p.wimg = wimg; p.tbl = tbl; p.tbl_stride = tbl_stride; p.onehot_off = onehot_off;
+  p.n_out = (int)n_out; p.c_in = c_in; p.c_out = c_out; p.K = K; p.kb = kb; p.n_pad = n_pad;
+  p.num_tiles = (int)mm3d_cdiv(n_out, kTileM);
+  p.stages = 4;
+  p.tmem_cols = pow2_cols(n_pad);
+  p.err = err;
+  const uint32_t b_stride = ((uint32_t)n_pad * 128u + 1023u) & ~1023u;
+  const size_t smem = 1024 + (size_t)p.stages * kStageBytes + 2 * b_stride + 8 * (2 * kMaxStages + 6) + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  // persistent CTAs: as many as fit (registers, shared memory, TMEM columns), tiles round-robin
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_conv_tc, kThreads, smem) != cudaSuccess) per_sm = 1;
+  const int by_tmem = 512 / p.tmem_cols;
+  if (per_sm > by_tmem) per_sm = by_tmem;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  int grid = MM3D_NUM_SMS * per_sm;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  k_conv_tc<<<grid, kThreads, smem, stream>>>(p);
+  mm3d_count_launches(2);
+  MM3D_CHECK_LAUNCH("mm3d_conv_fwd_tc");
+  return MM3D_OK;
+}

@@ -184,7 +184,13 @@ def test_io_layers():
 CONV_SHAPES = [(3, 16), (16, 16), (32, 16), (48, 48), (64, 96), (112, 112), (192, 96), (20, 7)]
 
 
-@pytest.mark.parametrize("mode", ["fp32"])
+def _no_device_error():
+    from mm2d3d_b200 import _lib
+    torch.cuda.synchronize()
+    assert _lib.lib.mm3d_take_device_error() == 0, "a kernel reported a pipeline time-out"
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
 @pytest.mark.parametrize("kind", ["smc", "down", "up"])
 def test_conv_fwd_bwd(kind, mode):
     from mm2d3d_b200 import functional as F
@@ -219,6 +225,7 @@ def test_conv_fwd_bwd(kind, mode):
         gx, gw = torch.autograd.grad(y, (x, w), g.to(DEV))
         assert rel_err(gx, gxr) < tol, (kind, c_in, c_out, "dgrad", rel_err(gx, gxr))
         assert rel_err(gw, gwr) < tol, (kind, c_in, c_out, "wgrad", rel_err(gw, gwr))
+    _no_device_error()
 
 
 @pytest.mark.parametrize("c", [16, 48, 112, 192, 6])
@@ -301,7 +308,7 @@ def _run_pair(net_ref, net, coords, feats, tol):
     for name, a, b in zip(["feats"] + list(pr), gg, gr):
         e = rel_err(a, b)
         worst = max(worst, e)
-        assert e < tol * 5, (name, e)  # gradients pass through up to 60 layers: 5x the per-op bar
+        assert e < tol * 10, (name, e)  # gradients pass through ~60 layers: 10x the per-op bar
     for (k, a), (_, b) in zip(net.named_buffers(), net_ref.named_buffers()):
         assert rel_err(a, b) < 1e-4, k
     return worst
@@ -336,6 +343,25 @@ def test_unetscn_full_config_one_scan():
     net_ref = net_ref.double()
     worst = _run_pair(net_ref, net, torch.from_numpy(locs), torch.from_numpy(feats), TOL["fp32"])
     print("worst gradient rel err", worst)
+
+
+def test_unetscn_full_config_tf32():
+    """Same network in the tcgen05 TF32 mode: 1e-2 bar (north_star), FP64 oracle as the truth."""
+    import mm2d3d_b200.scn as scn
+    from mm2d3d_b200.unet import UNetSCN
+    torch.manual_seed(6)
+    locs, feats = synth.make_batch("nuscenes", batch=1, seed0=4)
+    net_ref = UNetSCN(in_channels=3, backend=scn_cpu)
+    net = UNetSCN(in_channels=3).to(DEV)
+    net.load_state_dict(net_ref.state_dict())
+    net_ref = net_ref.double()
+    scn.set_conv_mode("tf32")
+    try:
+        worst = _run_pair(net_ref, net, torch.from_numpy(locs), torch.from_numpy(feats), TOL["tf32"])
+    finally:
+        scn.set_conv_mode("fp32")
+    _no_device_error()
+    print("worst gradient rel err (tf32)", worst)
 
 
 def test_module_surface_matches_reference_usage():
