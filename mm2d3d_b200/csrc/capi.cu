@@ -38,6 +38,7 @@ int mm3d_conv_wgrad_simt(const float* in, int64_t n_in, int c_in, const float* d
 
 // conv_tc.cu
 size_t mm3d_conv_tc_workspace_bytes(int c_in, int c_out, int K);
+int mm3d_conv_tc_supported(int c_in, int c_out, int K);
 int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
                      const float* weight, int K, const int32_t* tbl, int64_t tbl_stride,
                      const uint8_t* onehot_off, int flags, void* ws, size_t ws_bytes, cudaStream_t stream);
@@ -72,6 +73,10 @@ extern "C" int mm3d_conv_fwd(const float* in, int64_t n_in, int c_in, float* out
       return mm3d_conv_fwd_simt(in, n_in, c_in, out, n_out, c_out, weight, K, tbl, tbl_stride, onehot_off, flags,
                                 ws, ws_bytes, (cudaStream_t)stream);
     case MM3D_MODE_TF32:
+      // rows that are not whole 16-byte chunks (the 3-channel stem) stay on the FP32 SIMT kernel
+      if (!mm3d_conv_tc_supported(c_in, c_out, K))
+        return mm3d_conv_fwd_simt(in, n_in, c_in, out, n_out, c_out, weight, K, tbl, tbl_stride, onehot_off, flags,
+                                  ws, ws_bytes, (cudaStream_t)stream);
       return mm3d_conv_fwd_tc(in, n_in, c_in, out, n_out, c_out, weight, K, tbl, tbl_stride, onehot_off, flags,
                               ws, ws_bytes, (cudaStream_t)stream);
     default:

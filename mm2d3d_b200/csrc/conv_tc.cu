@@ -2,24 +2,28 @@
 //
 //   out[j,:] = sum_k in[tbl(j,k),:] . W'[k]          j in a tile of 128 output rows
 //
-// Output-stationary implicit GEMM: a CTA owns 128 output rows; for every kernel offset k the
-// 128 neighbour rows (zero where the neighbour is absent) are gathered into a K-major,
-// 128B-swizzled shared-memory tile and multiplied with W'[k] by tcgen05.mma (M=128, N=C_out,
-// kind::tf32), accumulating all K offsets in ONE TMEM accumulator.  No atomics, no read-modify-
-// write of `out`, one coalesced-by-row store per output row: deterministic.
+// Output-stationary implicit GEMM.  A CTA owns 128 output rows; the reduction dimension is the
+// "virtual K" = (kernel offset k, input channel ci) flattened, cut into K-blocks of 32 tf32
+// (= one 128-byte shared-memory row).  For every K-block the 128 gathered rows (zero where the
+// neighbour is absent) form a K-major SWIZZLE_128B tile that tcgen05.mma (M=128, N=C_out,
+// kind::tf32) multiplies with the matching block of the pre-swizzled weight image, accumulating
+// ALL offsets in one TMEM accumulator.  No atomics, no read-modify-write of `out`, each output row
+// stored once: deterministic.  Packing offsets back to back along K means a 16-channel layer needs
+// 14 K-blocks instead of 27 and no layer pays per-offset padding.
 //
-// Warp roles (192 threads):   warps 0-3  gather producers, then epilogue (TMEM lanes 32w..32w+31)
-//                             warp  4    MMA issuer (one lane) + TMEM allocator
-//                             warp  5    weight loader (cp.async.bulk of the pre-swizzled image)
-// Pipelines (mbarriers):      A ring  : a_full[S]  (128 producer arrivals)  / a_empty[S] (tcgen05.commit)
-//                             B ring  : b_full[2]  (expect_tx + bulk copy)  / b_empty[2] (tcgen05.commit)
-//                             accum   : acc_full   (tcgen05.commit)         / acc_empty  (128 arrivals)
+// Warp roles (320 threads):   warps 0-3  gather producers (cp.async, 8 lanes per 128-byte row piece)
+//                             warps 4-7  epilogue (TMEM lanes 32(w-4).. -> registers -> global)
+//                             warp  8    MMA issuer (one lane) + TMEM allocator
+//                             warp  9    weight loader (cp.async.bulk of the weight image)
+// Pipelines (mbarriers):      A ring   a_full[S] (128 cp.async arrivals) / a_empty[S] (tcgen05.commit)
+//                             B ring   b_full[2] (expect_tx + bulk copy) / b_empty[2] (tcgen05.commit)
+//                             accum    acc_full[2] (tcgen05.commit)      / acc_empty[2] (128 arrivals)
+//                             tables   tbl_full[2] (128 cp.async arrivals), reuse guarded by a named barrier
+// The accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the MMAs of i+1.
 //
-// Gather: 8 lanes per row read one 128-byte K-block of the row (a full L1 line per request) and
-// write it as one swizzled 128-byte smem row (a conflict-free quarter-warp store).  Absent
-// neighbours cost NO shared-memory traffic: tiles are zeroed once and a thread only re-zeroes a
-// slot it filled the previous time the stage was used -- the 3^3 tables are 10-30 % dense, so this
-// is what keeps the fill proportional to the real pairs instead of 27x the tile.
+// Absent neighbours cost NO shared-memory traffic: stages are zeroed once and a thread re-zeroes
+// (cp.async with src-size 0) only a slot it filled the previous time the stage was used -- the
+// 3^3 tables are 10-30 % dense, so the fill stays proportional to the real pairs.
 #include "common.cuh"
 
 namespace {
@@ -27,9 +31,10 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kKBlock = 32;                 // tf32 elements per 128-byte row of a K-block
 constexpr int kStageBytes = kTileM * 128;   // one A stage = one K-block of 128 rows = 16 KB
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
 constexpr int kProducers = 128;
 constexpr int kMaxStages = 6;
+constexpr int kMaxK = 27;
 constexpr uint32_t kSpinLimit = 1u << 22;
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -94,6 +99,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// 16-byte asynchronous copy global -> shared; src_bytes < 16 zero-fills the rest (0 = pure zero fill)
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one arrival when all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
@@ -128,29 +143,34 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
 struct TcParams {
   const float* in;
   float* out;
-  const float* wimg;  // [K][KB][n_pad][32] tf32, rows 128-byte swizzled
+  const float* wimg;  // [kbt][n_pad][32] tf32, rows 128-byte swizzled
   const int32_t* tbl;
   int64_t tbl_stride;
   const uint8_t* onehot_off;
-  int n_out, c_in, c_out, K, kb, n_pad, num_tiles, stages, tmem_cols;
+  int n_out, c_in, c_out, K;
+  int cq;         // 16-byte chunks per input row (c_in / 4)
+  int nq;         // K * cq   chunks of the virtual K
+  int kbt;        // K-blocks per tile = ceil(nq / 8)
+  int n_pad, num_tiles, stages, tmem_cols;
   int* err;
 };
 
-// weight image: wimg[k][kb][n][e] = Wsel(k)[kb*32+e][n] (0 beyond c_in / c_out), tf32-rounded,
-// 16-byte chunks of every 128-byte row XOR-swizzled with (n & 7) -- the byte image a
-// SWIZZLE_128B K-major B tile has in shared memory, so the kernel bulk-copies it verbatim.
+// Weight image: one [n_pad][32] block per K-block; element (n, e) of block kb is Wsel(k)[ci][n]
+// with (k, ci) = divmod(kb*32 + e, c_in) (0 beyond the virtual K / c_out), tf32-rounded, and the
+// 16-byte chunks of every 128-byte row XOR-swizzled with (n & 7): exactly the bytes a SWIZZLE_128B
+// K-major B tile has in shared memory, so the kernel bulk-copies it verbatim.
 __global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ img, int K, int c_in, int c_out,
-                               int kb, int n_pad, int transposed, int mirror) {
-  const int64_t total = (int64_t)K * kb * n_pad * kKBlock;
+                               int kbt, int n_pad, int transposed, int mirror) {
+  const int64_t total = (int64_t)kbt * n_pad * kKBlock;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int e_sw = (int)(i % kKBlock);
     const int n = (int)((i / kKBlock) % n_pad);
-    const int b = (int)((i / ((int64_t)kKBlock * n_pad)) % kb);
-    const int k = (int)(i / ((int64_t)kKBlock * n_pad * kb));
+    const int kb = (int)(i / ((int64_t)kKBlock * n_pad));
     const int chunk = (e_sw >> 2) ^ (n & 7);  // un-swizzle: which logical chunk lives here
-    const int ci = b * kKBlock + chunk * 4 + (e_sw & 3);
+    const int vk = kb * kKBlock + chunk * 4 + (e_sw & 3);
+    const int k = vk / c_in, ci = vk - k * c_in;
     float v = 0.f;
-    if (ci < c_in && n < c_out) {
+    if (k < K && n < c_out) {
       const int ks = mirror ? K - 1 - k : k;
       v = transposed ? __ldg(w + ((int64_t)ks * c_out + n) * c_in + ci)   // forward weight is [K][c_out][c_in]
                      : __ldg(w + ((int64_t)ks * c_in + ci) * c_out + n);  // [K][c_in][c_out]
@@ -159,33 +179,30 @@ __global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ 
   }
 }
 
-__device__ __forceinline__ int table_entry(const TcParams& p, int64_t row, int k) {
-  if (row >= p.n_out) return -1;
-  if (p.onehot_off) return (int)__ldg(p.onehot_off + row) == k ? __ldg(p.tbl + row) : -1;
-  return __ldg(p.tbl + (int64_t)k * p.tbl_stride + row);
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A stages][B x2][barriers][tmem ptr][abort]
+  // carve: [A stages][B x2][tables x2][barriers][tmem ptr][abort]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const int S = p.stages;
   const uint32_t b_bytes = (uint32_t)p.n_pad * 128u;
   const uint32_t b_stride = (b_bytes + 1023u) & ~1023u;
+  const uint32_t tbl_bytes = p.onehot_off ? (uint32_t)(kTileM * 4 + kTileM) : (uint32_t)(p.K * kTileM * 4);
+  const uint32_t tbl_buf = (tbl_bytes + 127u) & ~127u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + (uint32_t)S * kStageBytes;
-  const uint32_t bar_base = b_base + 2u * b_stride;
+  const uint32_t t_base = b_base + 2u * b_stride;
+  const uint32_t bar_base = t_base + 2u * tbl_buf;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar_base - smem_base));
-  // barrier indices
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(kMaxStages + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + s); };
   auto b_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 + s); };
-  const uint32_t acc_full = bar_base + 8u * (uint32_t)(2 * kMaxStages + 4);
-  const uint32_t acc_empty = bar_base + 8u * (uint32_t)(2 * kMaxStages + 5);
-  constexpr int kNumBars = 2 * kMaxStages + 6;
+  auto acc_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 4 + s); };
+  auto acc_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 6 + s); };
+  auto tbl_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 8 + s); };
+  constexpr int kNumBars = 2 * kMaxStages + 10;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNumBars);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + kNumBars + 1);
 
@@ -202,159 +219,181 @@ k_conv_tc(const TcParams p) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(b_full(s), 1);
       mbar_init(b_empty(s), 1);
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), kProducers);
+      mbar_init(tbl_full(s), kProducers);
     }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, kProducers);
     *abort_flag = 0;
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
+  if (warp == 8) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
   fence_proxy_async();  // the zero fill must be visible to the tensor core's (async-proxy) reads
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int items_per_tile = p.K * p.kb;
-  const int last_chunks = ((p.c_in - (p.kb - 1) * kKBlock) + 3) >> 2;  // 16-byte chunks of the last K-block
-  const bool vec_rows = (p.c_in & 3) == 0;
-
   if (warp < 4) {
-    // =================================================================== producers + epilogue
+    // =================================================================== gather producers
     const int g = threadIdx.x >> 3;  // row within a 16-row pass
     const int c = threadIdx.x & 7;   // 16-byte chunk within the 128-byte K-block row
     uint64_t filled = 0;             // bit (stage*8 + pass): this thread's slot holds data, not zeros
     uint32_t it = 0;                 // A-ring item counter
-    uint32_t tile_iter = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
+
+    // asynchronous copy of one tile's slice of the rule table into table buffer `buf`
+    auto load_table = [&](int tile, int buf) {
       const int64_t row0 = (int64_t)tile * kTileM;
-      int nb_next[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) nb_next[q] = table_entry(p, row0 + q * 16 + g, 0);
-      for (int k = 0; k < p.K; ++k) {
-        int nb[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) nb[q] = nb_next[q];
-        if (k + 1 < p.K) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) nb_next[q] = table_entry(p, row0 + q * 16 + g, k + 1);
+      const uint32_t dst = t_base + (uint32_t)buf * tbl_buf;
+      if (p.onehot_off) {
+        // parent[128] (int32) then off[128] (uint8)
+        for (int i = threadIdx.x; i < 32 + 8; i += kProducers) {
+          if (i < 32) {
+            const int64_t r = row0 + i * 4;
+            const int64_t left = (int64_t)p.n_out - r;
+            cp_async16(dst + i * 16, p.tbl + (left > 0 ? r : 0), left >= 4 ? 16u : left > 0 ? (uint32_t)left * 4u : 0u);
+          } else {
+            const int64_t r = row0 + (i - 32) * 16;
+            const int64_t left = (int64_t)p.n_out - r;
+            cp_async16(dst + kTileM * 4 + (i - 32) * 16, p.onehot_off + (left > 0 ? r : 0),
+                       left >= 16 ? 16u : left > 0 ? (uint32_t)left : 0u);
+          }
         }
-        for (int b = 0; b < p.kb; ++b, ++it) {
-          const int s = (int)(it % (uint32_t)S);
-          const uint32_t ph = (it / (uint32_t)S) & 1u;
-          const int nchunks = (b == p.kb - 1) ? last_chunks : 8;
-          const bool my_chunk = c < nchunks;
-          // issue the global loads before waiting for the stage
-          float4 v[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (nb[q] >= 0 && my_chunk) {
-              const float* src = p.in + (int64_t)nb[q] * p.c_in + b * kKBlock + c * 4;
-              if (vec_rows) {
-                v[q] = __ldg(reinterpret_cast<const float4*>(src));
-              } else {
-                const int rem = p.c_in - (b * kKBlock + c * 4);
-                v[q].x = __ldg(src);
-                if (rem > 1) v[q].y = __ldg(src + 1);
-                if (rem > 2) v[q].z = __ldg(src + 2);
-                if (rem > 3) v[q].w = __ldg(src + 3);
-              }
-            }
-          }
-          if (!mbar_wait(a_empty(s), ph ^ 1u, abort_flag)) goto done;
-          uint8_t* stage = smem + (size_t)s * kStageBytes;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int r = q * 16 + g;
-            const uint64_t bit = 1ull << (s * 8 + q);
-            const bool have = nb[q] >= 0 && my_chunk;
-            if (have || (filled & bit)) {
-              float4 o = make_float4(to_tf32(v[q].x), to_tf32(v[q].y), to_tf32(v[q].z), to_tf32(v[q].w));
-              *reinterpret_cast<float4*>(stage + r * 128 + ((c ^ (r & 7)) << 4)) = o;
-            }
-            filled = have ? (filled | bit) : (filled & ~bit);
-          }
-          fence_proxy_async();
-          mbar_arrive(a_full(s));
+      } else {
+        const int n_chunks = p.K * 32;  // 32 x 16-byte chunks per offset plane
+        for (int i = threadIdx.x; i < n_chunks; i += kProducers) {
+          const int k = i >> 5, ch = i & 31;
+          const int64_t r = row0 + ch * 4;
+          const int64_t left = (int64_t)p.n_out - r;
+          cp_async16(dst + (uint32_t)i * 16, p.tbl + (int64_t)k * p.tbl_stride + (left > 0 ? r : 0),
+                     left >= 4 ? 16u : left > 0 ? (uint32_t)left * 4u : 0u);
         }
       }
-      // ---- epilogue of this tile: TMEM -> registers -> global (each thread owns one output row)
-      if (!mbar_wait(acc_full, tile_iter & 1u, abort_flag)) goto done;
+      cp_async_arrive(tbl_full(buf));
+    };
+
+    uint32_t tile_iter = 0;
+    if ((int)blockIdx.x < p.num_tiles) load_table(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
+      const int buf = (int)(tile_iter & 1u);
+      // every producer has finished reading the other buffer (tile_iter-1): refill it for tile_iter+1
+      producer_bar_sync();
+      if (tile + (int)gridDim.x < p.num_tiles) load_table(tile + gridDim.x, buf ^ 1);
+      if (!mbar_wait(tbl_full(buf), (tile_iter >> 1) & 1u, abort_flag)) goto done;
+      const int32_t* tb = reinterpret_cast<const int32_t*>(smem + (t_base - smem_base) + (size_t)buf * tbl_buf);
+      const uint8_t* tb_off = reinterpret_cast<const uint8_t*>(tb) + kTileM * 4;
+      const int64_t row0 = (int64_t)tile * kTileM;
+      const int rows_left = (int)((int64_t)p.n_out - row0 < kTileM ? (int64_t)p.n_out - row0 : kTileM);
+
+      for (int kb = 0; kb < p.kbt; ++kb, ++it) {
+        const int s = (int)(it % (uint32_t)S);
+        const uint32_t ph = (it / (uint32_t)S) & 1u;
+        const int q = kb * 8 + c;  // chunk of the virtual K this lane copies
+        const bool q_ok = q < p.nq;
+        const int k = q_ok ? q / p.cq : 0;
+        const int cc = q - k * p.cq;
+        if (!mbar_wait(a_empty(s), ph ^ 1u, abort_flag)) goto done;
+        const uint32_t stage = a_base + (uint32_t)s * kStageBytes;
+#pragma unroll
+        for (int ps = 0; ps < 8; ++ps) {
+          const int r = ps * 16 + g;
+          int nb = -1;
+          if (q_ok && r < rows_left) {
+            if (p.onehot_off) nb = (int)tb_off[r] == k ? tb[r] : -1;
+            else nb = tb[k * kTileM + r];
+          }
+          const uint64_t bit = 1ull << (s * 8 + ps);
+          const uint32_t dst = stage + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+          if (nb >= 0) {
+            cp_async16(dst, p.in + (int64_t)nb * p.c_in + cc * 4, 16u);
+            filled |= bit;
+          } else if (filled & bit) {
+            cp_async16(dst, p.in, 0u);  // restore the zeros
+            filled &= ~bit;
+          }
+        }
+        cp_async_arrive(a_full(s));
+      }
+    }
+  } else if (warp < 8) {
+    // =================================================================== epilogue
+    const int ew = warp - 4;
+    uint32_t tile_iter = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
+      const int ab = (int)(tile_iter & 1u);
+      if (!mbar_wait(acc_full(ab), (tile_iter >> 1) & 1u, abort_flag)) goto done;
       tc_fence_after();
-      {
-        const int64_t row = row0 + warp * 32 + lane;
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-          float acc[16];
-          tmem_ld16(taddr + (uint32_t)c0, acc);
-          if (row < p.n_out) {
-            float* dst = p.out + row * p.c_out + c0;
-            if ((p.c_out & 3) == 0) {
+      const int64_t row = (int64_t)tile * kTileM + ew * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * p.n_pad);
+      for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+        float acc[16];
+        tmem_ld16(taddr + (uint32_t)c0, acc);
+        if (row < p.n_out) {
+          float* dst = p.out + row * p.c_out + c0;
+          if ((p.c_out & 3) == 0) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                if (c0 + j < p.c_out) *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-            } else {
+            for (int j = 0; j < 16; j += 4)
+              if (c0 + j < p.c_out) *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < p.c_out) dst[j] = acc[j];
-            }
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.c_out) dst[j] = acc[j];
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(acc_empty);
+      mbar_arrive(acc_empty(ab));
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // =================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(p.n_pad);
-      uint32_t it = 0, bit = 0, tile_iter = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
-        if (!mbar_wait(acc_empty, (tile_iter & 1u) ^ 1u, abort_flag)) break;
+      uint32_t it = 0, tile_iter = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++tile_iter) {
+        const int ab = (int)(tile_iter & 1u);
+        if (!mbar_wait(acc_empty(ab), ((tile_iter >> 1) & 1u) ^ 1u, abort_flag)) break;
         tc_fence_after();
-        bool ok = true;
-        for (int kk = 0; kk < items_per_tile && ok; ++kk, ++it, ++bit) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.n_pad);
+        for (int kb = 0; kb < p.kbt; ++kb, ++it) {
           const int s = (int)(it % (uint32_t)S);
-          const int bs = (int)(bit & 1u);
-          const int b = kk % p.kb;
-          if (!mbar_wait(b_full(bs), (bit >> 1) & 1u, abort_flag)) { ok = false; break; }
+          const int bs = (int)(it & 1u);
+          if (!mbar_wait(b_full(bs), (it >> 1) & 1u, abort_flag)) { ok = false; break; }
           if (!mbar_wait(a_full(s), (it / (uint32_t)S) & 1u, abort_flag)) { ok = false; break; }
           tc_fence_after();
-          const int ksteps = (b == p.kb - 1) ? ((p.c_in - b * kKBlock) + 7) >> 3 : kKBlock / 8;
+          const int rem = p.nq * 4 - kb * kKBlock;  // virtual-K elements left
+          const int ksteps = rem >= kKBlock ? kKBlock / 8 : (rem + 7) >> 3;
           const uint32_t a_addr = a_base + (uint32_t)s * kStageBytes;
           const uint32_t b_addr = b_base + (uint32_t)bs * b_stride;
           for (int ks = 0; ks < ksteps; ++ks)
-            umma_tf32(tmem_base, make_desc_sw128(a_addr + ks * 32), make_desc_sw128(b_addr + ks * 32), idesc,
-                      (kk | ks) != 0);
+            umma_tf32(d_tmem, make_desc_sw128(a_addr + ks * 32), make_desc_sw128(b_addr + ks * 32), idesc,
+                      (kb | ks) != 0);
           umma_commit(a_empty(s));
           umma_commit(b_empty(bs));
         }
-        if (!ok) break;
-        umma_commit(acc_full);
+        if (ok) umma_commit(acc_full(ab));
       }
     }
   } else {
     // =================================================================== weight loader
     if (lane == 0) {
-      uint32_t bit = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        bool ok = true;
-        for (int kk = 0; kk < items_per_tile; ++kk, ++bit) {
-          const int bs = (int)(bit & 1u);
-          if (!mbar_wait(b_empty(bs), ((bit >> 1) & 1u) ^ 1u, abort_flag)) { ok = false; break; }
+      uint32_t it = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+        for (int kb = 0; kb < p.kbt; ++kb, ++it) {
+          const int bs = (int)(it & 1u);
+          if (!mbar_wait(b_empty(bs), ((it >> 1) & 1u) ^ 1u, abort_flag)) { ok = false; break; }
           mbar_arrive_expect_tx(b_full(bs), b_bytes);
-          bulk_g2s(b_base + (uint32_t)bs * b_stride, p.wimg + (size_t)kk * p.n_pad * kKBlock, b_bytes, b_full(bs));
+          bulk_g2s(b_base + (uint32_t)bs * b_stride, p.wimg + (size_t)kb * p.n_pad * kKBlock, b_bytes, b_full(bs));
         }
-        if (!ok) break;
       }
     }
   }
 done:
+  asm volatile("cp.async.wait_all;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0 && *abort_flag && p.err) atomicExch(p.err, 1);
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -370,16 +409,22 @@ int pow2_cols(int n) {
 
 // ---- host entry points used by capi.cu -------------------------------------------------------
 
-static int tc_geometry(int c_in, int c_out, int* kb, int* n_pad) {
-  *kb = (c_in + kKBlock - 1) / kKBlock;
+static int tc_geometry(int c_in, int c_out, int K, int* kbt, int* n_pad) {
+  *kbt = (K * (c_in / 4) + 7) / 8;
   *n_pad = (c_out + 15) / 16 * 16;
-  return (*n_pad <= 256 && *kb >= 1) ? 0 : 1;
+  return (*n_pad <= 256 && (c_in % 4) == 0 && K <= kMaxK) ? 0 : 1;
+}
+
+// 1 when the tcgen05 kernel handles this shape (input rows must be whole 16-byte chunks)
+int mm3d_conv_tc_supported(int c_in, int c_out, int K) {
+  int kbt, n_pad;
+  return tc_geometry(c_in, c_out, K, &kbt, &n_pad) == 0;
 }
 
 size_t mm3d_conv_tc_workspace_bytes(int c_in, int c_out, int K) {
-  int kb, n_pad;
-  if (tc_geometry(c_in, c_out, &kb, &n_pad)) return 0;
-  return mm3d_align((size_t)K * kb * n_pad * 128);  // weight image
+  int kbt, n_pad;
+  if (tc_geometry(c_in, c_out, K, &kbt, &n_pad)) return 0;
+  return mm3d_align((size_t)kbt * n_pad * 128);  // weight image
 }
 
 // Sticky per-device error flag set by a kernel whose mbarrier pipeline timed out (never in a
@@ -410,30 +455,33 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
                      const float* weight, int K, const int32_t* tbl, int64_t tbl_stride,
                      const uint8_t* onehot_off, int flags, void* ws, size_t ws_bytes, cudaStream_t stream) {
   (void)n_in;
-  int kb, n_pad;
-  MM3D_REQUIRE(tc_geometry(c_in, c_out, &kb, &n_pad) == 0, MM3D_ERR_UNSUPPORTED, "tcgen05 conv: c_out %d > 256", c_out);
+  int kbt, n_pad;
+  MM3D_REQUIRE(tc_geometry(c_in, c_out, K, &kbt, &n_pad) == 0, MM3D_ERR_UNSUPPORTED,
+               "tcgen05 conv: unsupported shape c_in %d c_out %d K %d", c_in, c_out, K);
   MM3D_REQUIRE(n_out < (1ll << 31), MM3D_ERR_UNSUPPORTED, "tcgen05 conv: too many rows");
   MM3D_REQUIRE(ws && ws_bytes >= mm3d_conv_tc_workspace_bytes(c_in, c_out, K), MM3D_ERR_WORKSPACE,
                "tcgen05 conv: workspace too small");
-  MM3D_REQUIRE((((uintptr_t)in | (uintptr_t)out | (uintptr_t)ws) & 15) == 0, MM3D_ERR_INVALID,
-               "tcgen05 conv: pointers must be 16-byte aligned");
+  MM3D_REQUIRE((((uintptr_t)in | (uintptr_t)out | (uintptr_t)ws | (uintptr_t)tbl | (uintptr_t)onehot_off) & 15) == 0,
+               MM3D_ERR_INVALID, "tcgen05 conv: pointers must be 16-byte aligned");
+  MM3D_REQUIRE(onehot_off || (tbl_stride % 4) == 0, MM3D_ERR_INVALID, "tcgen05 conv: tbl_stride must be a multiple of 4");
   const bool tr = (flags & MM3D_CONV_TRANSPOSE_W) != 0, mir = (flags & MM3D_CONV_MIRROR_K) != 0;
   MM3D_REQUIRE(tr || !mir, MM3D_ERR_UNSUPPORTED, "MIRROR_K without TRANSPOSE_W not implemented");
   if (n_out == 0) return MM3D_OK;
 
   float* wimg = (float*)ws;
-  int* err = device_err_flag();
-  k_weight_image<<<mm3d_grid((int64_t)K * kb * n_pad * kKBlock, 256), 256, 0, stream>>>(weight, wimg, K, c_in, c_out, kb,
-                                                                                     n_pad, tr ? 1 : 0, mir ? 1 : 0);
+  k_weight_image<<<mm3d_grid((int64_t)kbt * n_pad * kKBlock, 256), 256, 0, stream>>>(weight, wimg, K, c_in, c_out, kbt,
+                                                                                 n_pad, tr ? 1 : 0, mir ? 1 : 0);
   TcParams p;
   p.in = in; p.out = out; p.wimg = wimg; p.tbl = tbl; p.tbl_stride = tbl_stride; p.onehot_off = onehot_off;
-  p.n_out = (int)n_out; p.c_in = c_in; p.c_out = c_out; p.K = K; p.kb = kb; p.n_pad = n_pad;
+  p.n_out = (int)n_out; p.c_in = c_in; p.c_out = c_out; p.K = K;
+  p.cq = c_in / 4; p.nq = K * p.cq; p.kbt = kbt; p.n_pad = n_pad;
   p.num_tiles = (int)mm3d_cdiv(n_out, kTileM);
   p.stages = 4;
-  p.tmem_cols = pow2_cols(n_pad);
-  p.err = err;
+  p.tmem_cols = pow2_cols(2 * n_pad);
+  p.err = device_err_flag();
   const uint32_t b_stride = ((uint32_t)n_pad * 128u + 1023u) & ~1023u;
-  const size_t smem = 1024 + (size_t)p.stages * kStageBytes + 2 * b_stride + 8 * (2 * kMaxStages + 6) + 64;
+  const uint32_t tbl_buf = ((onehot_off ? (uint32_t)(kTileM * 5) : (uint32_t)(K * kTileM * 4)) + 127u) & ~127u;
+  const size_t smem = 1024 + (size_t)p.stages * kStageBytes + 2 * b_stride + 2 * tbl_buf + 8 * (2 * kMaxStages + 10) + 64;
   static bool attr_set = false;
   if (!attr_set) {
     MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -445,7 +493,6 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
   const int by_tmem = 512 / p.tmem_cols;
   if (per_sm > by_tmem) per_sm = by_tmem;
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
   int grid = MM3D_NUM_SMS * per_sm;
   if (grid > p.num_tiles) grid = p.num_tiles;
   k_conv_tc<<<grid, kThreads, smem, stream>>>(p);

@@ -115,7 +115,7 @@ def conv_tables(meta, kind: str, spatial_in: int):
     """
     if kind == "smc":
         lv = meta.nbr(spatial_in)
-        t = _Table(lv.ptr(lv.o_nbr), lv.cap, None, lv.n, lv.n, 27)
+        t = _Table(lv.ptr(lv.o_nbr), lv.tstride, None, lv.n, lv.n, 27)
         return t, t, _lib.CONV_TRANSPOSE_W | _lib.CONV_MIRROR_K
     if kind == "down":
         fine, coarse = meta.down(spatial_in)
@@ -123,7 +123,7 @@ def conv_tables(meta, kind: str, spatial_in: int):
         fine, coarse = meta.down(int(spatial_in) * 2)
     else:
         raise ValueError(kind)
-    child = _Table(fine.ptr(fine.o_child), fine.cap, None, fine.n, coarse.n, 8)
+    child = _Table(fine.ptr(fine.o_child), fine.tstride, None, fine.n, coarse.n, 8)
     onehot = _Table(fine.ptr(fine.o_parent), 0, fine.ptr(fine.o_off), coarse.n, fine.n, 8)
     return (child, onehot, _lib.CONV_TRANSPOSE_W) if kind == "down" else (onehot, child, _lib.CONV_TRANSPOSE_W)
 

