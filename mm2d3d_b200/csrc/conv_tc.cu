@@ -11,14 +11,17 @@
 // stored once: deterministic.  Packing offsets back to back along K means a 16-channel layer needs
 // 14 K-blocks instead of 27 and no layer pays per-offset padding.
 //
-// Warp roles (320 threads):   warps 0-3  gather producers (cp.async, 8 lanes per 128-byte row piece)
-//                             warps 4-7  epilogue (TMEM lanes 32(w-4).. -> registers -> global)
-//                             warp  8    MMA issuer (one lane) + TMEM allocator
-//                             warp  9    weight loader (cp.async.bulk of the weight image)
-// Pipelines (mbarriers):      A ring   a_full[S] (128 cp.async arrivals) / a_empty[S] (tcgen05.commit)
-//                             B ring   b_full[2] (expect_tx + bulk copy) / b_empty[2] (tcgen05.commit)
-//                             accum    acc_full[2] (tcgen05.commit)      / acc_empty[2] (128 arrivals)
-//                             tables   tbl_full[2] (128 cp.async arrivals), reuse guarded by a named barrier
+// Warp roles (448 threads):   warps 0-7   gather producers (cp.async, 8 lanes per 128-byte row piece)
+//                             warps 8-11  epilogue (TMEM lanes 32(w-8).. -> registers -> global)
+//                             warp  12    MMA issuer (one lane) + TMEM allocator
+//                             warp  13    weight loader (cp.async.bulk of the weight image)
+// Pipelines (mbarriers):      A ring   a_full[S] (256 cp.async arrivals) / a_empty[S] (tcgen05.commit)
+//                             B ring   b_full[SB] (expect_tx + bulk copy) / b_empty[SB] (tcgen05.commit)
+//                             accum    acc_full[2] (tcgen05.commit)       / acc_empty[2] (128 arrivals)
+//                             tables   tbl_full[2] (256 cp.async arrivals), reuse guarded by a named barrier
+// The producer loop is the critical instruction stream (one 16-byte slot decision per lane and
+// pass), so it is branch-free, has the ring stage as a compile-time index (unrolled by S) and
+// advances (offset, channel-chunk) incrementally instead of dividing.
 // The accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the MMAs of i+1.
 //
 // Absent neighbours cost NO shared-memory traffic: stages are zeroed once and a thread re-zeroes
@@ -31,8 +34,10 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kKBlock = 32;                 // tf32 elements per 128-byte row of a K-block
 constexpr int kStageBytes = kTileM * 128;   // one A stage = one K-block of 128 rows = 16 KB
-constexpr int kThreads = 320;
-constexpr int kProducers = 128;
+constexpr int kProducers = 256;             // 8 warps: 32 rows x 8 chunk lanes per pass, 4 passes
+constexpr int kEpilogue = 128;
+constexpr int kThreads = kProducers + kEpilogue + 64;
+constexpr int kMaxBStages = 4;
 constexpr int kMaxStages = 6;
 constexpr int kMaxK = 27;
 constexpr uint32_t kSpinLimit = 1u << 22;
@@ -107,7 +112,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, u
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -151,7 +156,8 @@ struct TcParams {
   int cq;         // 16-byte chunks per input row (c_in / 4)
   int nq;         // K * cq   chunks of the virtual K
   int kbt;        // K-blocks per tile = ceil(nq / 8)
-  int n_pad, num_tiles, stages, tmem_cols;
+  int d8, m8;     // 8 / cq and 8 % cq: how (offset, chunk) advance from one K-block to the next
+  int n_pad, num_tiles, b_stages, tmem_cols;
   int* err;
 };
 
@@ -179,30 +185,31 @@ __global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ 
   }
 }
 
+template <int S, bool ONEHOT>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A stages][B x2][tables x2][barriers][tmem ptr][abort]
+  // carve: [A stages][B stages][tables x2][barriers][tmem ptr][abort]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int S = p.stages;
+  const int SB = p.b_stages;
   const uint32_t b_bytes = (uint32_t)p.n_pad * 128u;
   const uint32_t b_stride = (b_bytes + 1023u) & ~1023u;
-  const uint32_t tbl_bytes = p.onehot_off ? (uint32_t)(kTileM * 4 + kTileM) : (uint32_t)(p.K * kTileM * 4);
+  const uint32_t tbl_bytes = ONEHOT ? (uint32_t)(kTileM * 4 + kTileM) : (uint32_t)(p.K * kTileM * 4);
   const uint32_t tbl_buf = (tbl_bytes + 127u) & ~127u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + (uint32_t)S * kStageBytes;
-  const uint32_t t_base = b_base + 2u * b_stride;
+  const uint32_t t_base = b_base + (uint32_t)SB * b_stride;
   const uint32_t bar_base = t_base + 2u * tbl_buf;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar_base - smem_base));
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(kMaxStages + s); };
   auto b_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + s); };
-  auto b_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 + s); };
-  auto acc_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 4 + s); };
-  auto acc_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 6 + s); };
-  auto tbl_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 8 + s); };
-  constexpr int kNumBars = 2 * kMaxStages + 10;
+  auto b_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + kMaxBStages + s); };
+  auto acc_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 * kMaxBStages + s); };
+  auto acc_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 * kMaxBStages + 2 + s); };
+  auto tbl_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 * kMaxBStages + 4 + s); };
+  constexpr int kNumBars = 2 * kMaxStages + 2 * kMaxBStages + 6;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNumBars);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + kNumBars + 1);
 
@@ -216,47 +223,51 @@ k_conv_tc(const TcParams p) {
       mbar_init(a_full(s), kProducers);
       mbar_init(a_empty(s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < SB; ++s) {
       mbar_init(b_full(s), 1);
       mbar_init(b_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full(s), 1);
-      mbar_init(acc_empty(s), kProducers);
+      mbar_init(acc_empty(s), kEpilogue);
       mbar_init(tbl_full(s), kProducers);
     }
     *abort_flag = 0;
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
+  if (warp == 12) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
   fence_proxy_async();  // the zero fill must be visible to the tensor core's (async-proxy) reads
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // =================================================================== gather producers
-    const int g = threadIdx.x >> 3;  // row within a 16-row pass
+    const int g = threadIdx.x >> 3;  // row within a 32-row pass
     const int c = threadIdx.x & 7;   // 16-byte chunk within the 128-byte K-block row
-    uint64_t filled = 0;             // bit (stage*8 + pass): this thread's slot holds data, not zeros
-    uint32_t it = 0;                 // A-ring item counter
+    // this thread's slot in a stage: row g (+32 per pass), swizzled chunk
+    const uint32_t slot0 = a_base + (uint32_t)g * 128u + (uint32_t)((c ^ (g & 7)) << 4);
+    uint32_t filled[S];              // bit ps: the slot of pass ps holds data, not zeros
+#pragma unroll
+    for (int s = 0; s < S; ++s) filled[s] = 0;
 
     // asynchronous copy of one tile's slice of the rule table into table buffer `buf`
     auto load_table = [&](int tile, int buf) {
       const int64_t row0 = (int64_t)tile * kTileM;
       const uint32_t dst = t_base + (uint32_t)buf * tbl_buf;
-      if (p.onehot_off) {
+      if (ONEHOT) {
         // parent[128] (int32) then off[128] (uint8)
-        for (int i = threadIdx.x; i < 32 + 8; i += kProducers) {
-          if (i < 32) {
-            const int64_t r = row0 + i * 4;
-            const int64_t left = (int64_t)p.n_out - r;
-            cp_async16(dst + i * 16, p.tbl + (left > 0 ? r : 0), left >= 4 ? 16u : left > 0 ? (uint32_t)left * 4u : 0u);
-          } else {
-            const int64_t r = row0 + (i - 32) * 16;
-            const int64_t left = (int64_t)p.n_out - r;
-            cp_async16(dst + kTileM * 4 + (i - 32) * 16, p.onehot_off + (left > 0 ? r : 0),
-                       left >= 16 ? 16u : left > 0 ? (uint32_t)left : 0u);
-          }
+        const int i = threadIdx.x;
+        if (i < 32) {
+          const int64_t r = row0 + i * 4;
+          const int64_t left = (int64_t)p.n_out - r;
+          cp_async16(dst + i * 16, p.tbl + (left > 0 ? r : 0), left >= 4 ? 16u : left > 0 ? (uint32_t)left * 4u : 0u);
+        } else if (i < 40) {
+          const int64_t r = row0 + (i - 32) * 16;
+          const int64_t left = (int64_t)p.n_out - r;
+          cp_async16(dst + kTileM * 4 + (i - 32) * 16, p.onehot_off + (left > 0 ? r : 0),
+                     left >= 16 ? 16u : left > 0 ? (uint32_t)left : 0u);
         }
       } else {
         const int n_chunks = p.K * 32;  // 32 x 16-byte chunks per offset plane
@@ -271,52 +282,68 @@ k_conv_tc(const TcParams p) {
       cp_async_arrive(tbl_full(buf));
     };
 
-    uint32_t tile_iter = 0;
-    if ((int)blockIdx.x < p.num_tiles) load_table(blockIdx.x, 0);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
-      const int buf = (int)(tile_iter & 1u);
-      // every producer has finished reading the other buffer (tile_iter-1): refill it for tile_iter+1
-      producer_bar_sync();
-      if (tile + (int)gridDim.x < p.num_tiles) load_table(tile + gridDim.x, buf ^ 1);
-      if (!mbar_wait(tbl_full(buf), (tile_iter >> 1) & 1u, abort_flag)) goto done;
-      const int32_t* tb = reinterpret_cast<const int32_t*>(smem + (t_base - smem_base) + (size_t)buf * tbl_buf);
-      const uint8_t* tb_off = reinterpret_cast<const uint8_t*>(tb) + kTileM * 4;
-      const int64_t row0 = (int64_t)tile * kTileM;
-      const int rows_left = (int)((int64_t)p.n_out - row0 < kTileM ? (int64_t)p.n_out - row0 : kTileM);
-
-      for (int kb = 0; kb < p.kbt; ++kb, ++it) {
-        const int s = (int)(it % (uint32_t)S);
-        const uint32_t ph = (it / (uint32_t)S) & 1u;
-        const int q = kb * 8 + c;  // chunk of the virtual K this lane copies
-        const bool q_ok = q < p.nq;
-        const int k = q_ok ? q / p.cq : 0;
-        const int cc = q - k * p.cq;
-        if (!mbar_wait(a_empty(s), ph ^ 1u, abort_flag)) goto done;
-        const uint32_t stage = a_base + (uint32_t)s * kStageBytes;
+    int tile = blockIdx.x;
+    uint32_t tile_iter = 0, round = 0;
+    int kb = 0, k = 0, cc = 0, rows_left = 0;
+    const int32_t* tb = nullptr;
+    if (tile < p.num_tiles) load_table(tile, 0);
+    while (tile < p.num_tiles) {
 #pragma unroll
-        for (int ps = 0; ps < 8; ++ps) {
-          const int r = ps * 16 + g;
-          int nb = -1;
-          if (q_ok && r < rows_left) {
-            if (p.onehot_off) nb = (int)tb_off[r] == k ? tb[r] : -1;
-            else nb = tb[k * kTileM + r];
-          }
-          const uint64_t bit = 1ull << (s * 8 + ps);
-          const uint32_t dst = stage + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-          if (nb >= 0) {
-            cp_async16(dst, p.in + (int64_t)nb * p.c_in + cc * 4, 16u);
-            filled |= bit;
-          } else if (filled & bit) {
-            cp_async16(dst, p.in, 0u);  // restore the zeros
-            filled &= ~bit;
-          }
+      for (int s = 0; s < S; ++s) {
+        if (tile >= p.num_tiles) break;
+        if (kb == 0) {
+          // new tile: every producer is done with the other table buffer -> refill it for the
+          // tile after this one, then wait for this tile's table
+          const int buf = (int)(tile_iter & 1u);
+          producer_bar_sync();
+          if (tile + (int)gridDim.x < p.num_tiles) load_table(tile + gridDim.x, buf ^ 1);
+          if (!mbar_wait(tbl_full(buf), (tile_iter >> 1) & 1u, abort_flag)) goto done;
+          tb = reinterpret_cast<const int32_t*>(smem + (t_base - smem_base) + (size_t)buf * tbl_buf);
+          const int64_t left = (int64_t)p.n_out - (int64_t)tile * kTileM;
+          rows_left = left < kTileM ? (int)left : kTileM;
+          // (offset, chunk) of virtual-K chunk q = c
+          k = c / p.cq;
+          cc = c - k * p.cq;
         }
+        if (!mbar_wait(a_empty(s), (round & 1u) ^ 1u, abort_flag)) goto done;
+        const bool q_ok = kb * 8 + c < p.nq;
+        const int kt = q_ok ? k : 0;  // lanes past the end of the virtual K must not index past the table
+        const uint32_t src_off = (uint32_t)cc * 4u;
+        uint32_t f = filled[s], nf = 0;
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+          const int r = ps * 32 + g;
+          int nb;
+          if (ONEHOT) {
+            const int par = tb[r];
+            const int off = (int)reinterpret_cast<const uint8_t*>(tb)[kTileM * 4 + r];
+            nb = off == kt ? par : -1;
+          } else {
+            nb = tb[kt * kTileM + r];
+          }
+          const bool have = q_ok && r < rows_left && nb >= 0;
+          const float* src = have ? p.in + ((uint32_t)nb * (uint32_t)p.c_in + src_off) : p.in;
+          if (have || ((f >> ps) & 1u))
+            cp_async16(slot0 + (uint32_t)(s * kStageBytes + ps * 32 * 128), src, have ? 16u : 0u);
+          nf |= (have ? 1u : 0u) << ps;
+        }
+        filled[s] = nf;
         cp_async_arrive(a_full(s));
+        // advance to the next K-block
+        k += p.d8;
+        cc += p.m8;
+        if (cc >= p.cq) { cc -= p.cq; ++k; }
+        if (++kb == p.kbt) {
+          kb = 0;
+          tile += gridDim.x;
+          ++tile_iter;
+        }
       }
+      ++round;
     }
-  } else if (warp < 8) {
+  } else if (warp < 12) {
     // =================================================================== epilogue
-    const int ew = warp - 4;
+    const int ew = warp - 8;
     uint32_t tile_iter = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
       const int ab = (int)(tile_iter & 1u);
@@ -343,7 +370,7 @@ k_conv_tc(const TcParams p) {
       tc_fence_before();
       mbar_arrive(acc_empty(ab));
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // =================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(p.n_pad);
@@ -356,8 +383,8 @@ k_conv_tc(const TcParams p) {
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.n_pad);
         for (int kb = 0; kb < p.kbt; ++kb, ++it) {
           const int s = (int)(it % (uint32_t)S);
-          const int bs = (int)(it & 1u);
-          if (!mbar_wait(b_full(bs), (it >> 1) & 1u, abort_flag)) { ok = false; break; }
+          const int bs = (int)(it % (uint32_t)SB);
+          if (!mbar_wait(b_full(bs), (it / (uint32_t)SB) & 1u, abort_flag)) { ok = false; break; }
           if (!mbar_wait(a_full(s), (it / (uint32_t)S) & 1u, abort_flag)) { ok = false; break; }
           tc_fence_after();
           const int rem = p.nq * 4 - kb * kKBlock;  // virtual-K elements left
@@ -380,8 +407,8 @@ k_conv_tc(const TcParams p) {
       bool ok = true;
       for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
         for (int kb = 0; kb < p.kbt; ++kb, ++it) {
-          const int bs = (int)(it & 1u);
-          if (!mbar_wait(b_empty(bs), ((it >> 1) & 1u) ^ 1u, abort_flag)) { ok = false; break; }
+          const int bs = (int)(it % (uint32_t)SB);
+          if (!mbar_wait(b_empty(bs), ((it / (uint32_t)SB) & 1u) ^ 1u, abort_flag)) { ok = false; break; }
           mbar_arrive_expect_tx(b_full(bs), b_bytes);
           bulk_g2s(b_base + (uint32_t)bs * b_stride, p.wimg + (size_t)kb * p.n_pad * kKBlock, b_bytes, b_full(bs));
         }
@@ -393,7 +420,7 @@ done:
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0 && *abort_flag && p.err) atomicExch(p.err, 1);
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -405,6 +432,26 @@ int pow2_cols(int n) {
   return c;
 }
 
+template <int S, bool ONEHOT>
+int launch_conv_tc(const TcParams& p, size_t smem, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc<S, ONEHOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  // persistent CTAs: as many as fit (registers, shared memory, TMEM columns), tiles round-robin
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_conv_tc<S, ONEHOT>, kThreads, smem) != cudaSuccess)
+    per_sm = 1;
+  const int by_tmem = 512 / p.tmem_cols;
+  if (per_sm > by_tmem) per_sm = by_tmem;
+  if (per_sm < 1) per_sm = 1;
+  int grid = MM3D_NUM_SMS * per_sm;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  k_conv_tc<S, ONEHOT><<<grid, kThreads, smem, stream>>>(p);
+  return MM3D_OK;
+}
+
 }  // namespace
 
 // ---- host entry points used by capi.cu -------------------------------------------------------
@@ -412,7 +459,7 @@ int pow2_cols(int n) {
 static int tc_geometry(int c_in, int c_out, int K, int* kbt, int* n_pad) {
   *kbt = (K * (c_in / 4) + 7) / 8;
   *n_pad = (c_out + 15) / 16 * 16;
-  return (*n_pad <= 256 && (c_in % 4) == 0 && K <= kMaxK) ? 0 : 1;
+  return (*n_pad <= 256 && (c_in % 4) == 0 && c_in >= 4 && K <= kMaxK) ? 0 : 1;
 }
 
 // 1 when the tcgen05 kernel handles this shape (input rows must be whole 16-byte chunks)
@@ -454,11 +501,11 @@ extern "C" int mm3d_take_device_error(void) {
 int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
                      const float* weight, int K, const int32_t* tbl, int64_t tbl_stride,
                      const uint8_t* onehot_off, int flags, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  (void)n_in;
   int kbt, n_pad;
   MM3D_REQUIRE(tc_geometry(c_in, c_out, K, &kbt, &n_pad) == 0, MM3D_ERR_UNSUPPORTED,
                "tcgen05 conv: unsupported shape c_in %d c_out %d K %d", c_in, c_out, K);
-  MM3D_REQUIRE(n_out < (1ll << 31), MM3D_ERR_UNSUPPORTED, "tcgen05 conv: too many rows");
+  MM3D_REQUIRE(n_out < (1ll << 31) && n_in * (int64_t)c_in < (1ll << 32), MM3D_ERR_UNSUPPORTED,
+               "tcgen05 conv: tensor too large for 32-bit element offsets");
   MM3D_REQUIRE(ws && ws_bytes >= mm3d_conv_tc_workspace_bytes(c_in, c_out, K), MM3D_ERR_WORKSPACE,
                "tcgen05 conv: workspace too small");
   MM3D_REQUIRE((((uintptr_t)in | (uintptr_t)out | (uintptr_t)ws | (uintptr_t)tbl | (uintptr_t)onehot_off) & 15) == 0,
@@ -474,28 +521,22 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
   TcParams p;
   p.in = in; p.out = out; p.wimg = wimg; p.tbl = tbl; p.tbl_stride = tbl_stride; p.onehot_off = onehot_off;
   p.n_out = (int)n_out; p.c_in = c_in; p.c_out = c_out; p.K = K;
-  p.cq = c_in / 4; p.nq = K * p.cq; p.kbt = kbt; p.n_pad = n_pad;
+  p.cq = c_in / 4; p.nq = K * p.cq; p.kbt = kbt; p.d8 = 8 / p.cq; p.m8 = 8 % p.cq; p.n_pad = n_pad;
   p.num_tiles = (int)mm3d_cdiv(n_out, kTileM);
-  p.stages = 4;
   p.tmem_cols = pow2_cols(2 * n_pad);
   p.err = device_err_flag();
   const uint32_t b_stride = ((uint32_t)n_pad * 128u + 1023u) & ~1023u;
   const uint32_t tbl_buf = ((onehot_off ? (uint32_t)(kTileM * 5) : (uint32_t)(K * kTileM * 4)) + 127u) & ~127u;
-  const size_t smem = 1024 + (size_t)p.stages * kStageBytes + 2 * b_stride + 2 * tbl_buf + 8 * (2 * kMaxStages + 10) + 64;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
-  // persistent CTAs: as many as fit (registers, shared memory, TMEM columns), tiles round-robin
-  int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_conv_tc, kThreads, smem) != cudaSuccess) per_sm = 1;
-  const int by_tmem = 512 / p.tmem_cols;
-  if (per_sm > by_tmem) per_sm = by_tmem;
-  if (per_sm < 1) per_sm = 1;
-  int grid = MM3D_NUM_SMS * per_sm;
-  if (grid > p.num_tiles) grid = p.num_tiles;
-  k_conv_tc<<<grid, kThreads, smem, stream>>>(p);
+  // small N: 4 A + 4 B stages and two CTAs per SM; wide N: one CTA per SM with a 6-deep A ring
+  const bool wide = n_pad > 64;
+  const int S = wide ? 6 : 4;
+  p.b_stages = wide ? (n_pad > 128 ? 2 : 3) : 4;
+  const size_t smem = 1024 + (size_t)S * kStageBytes + (size_t)p.b_stages * b_stride + 2 * tbl_buf +
+                      8 * (2 * kMaxStages + 2 * kMaxBStages + 6) + 64;
+  int rc;
+  if (wide) rc = onehot_off ? launch_conv_tc<6, true>(p, smem, stream) : launch_conv_tc<6, false>(p, smem, stream);
+  else      rc = onehot_off ? launch_conv_tc<4, true>(p, smem, stream) : launch_conv_tc<4, false>(p, smem, stream);
+  if (rc) return rc;
   mm3d_count_launches(2);
   MM3D_CHECK_LAUNCH("mm3d_conv_fwd_tc");
   return MM3D_OK;
