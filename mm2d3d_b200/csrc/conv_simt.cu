@@ -181,12 +181,39 @@ k_conv_wgrad_simt(const float* __restrict__ in, const float* __restrict__ dout, 
     __syncthreads();
     for (int b0 = 0; b0 < total; b0 += kPairBatch) {
       const int nb_pairs = total - b0 < kPairBatch ? total - b0 : kPairBatch;
-      // stage rows: warp w copies pairs w, w+8, ...
-      for (int p = warp; p < nb_pairs; p += kWgThreads / 32) {
-        const float* src_a = in + (int64_t)s_pair_in[b0 + p] * c_in;
-        const float* src_d = dout + (base + s_pair_out[b0 + p]) * c_out;
-        for (int c = lane; c < c_in; c += 32) sA[p * c_in + c] = __ldg(src_a + c);
-        for (int c = lane; c < c_out; c += 32) sD[p * c_out + c] = __ldg(src_d + c);
+      // stage the batch: pair p is copied by 8 lanes, 16-byte pieces of the input row and then of
+      // the d_out row interleaved over the lanes, four loads in flight per thread
+      if (((c_in | c_out) & 3) == 0) {
+        const int p = threadIdx.x >> 3, l8 = threadIdx.x & 7;
+        if (p < nb_pairs) {
+          const float4* src_a = reinterpret_cast<const float4*>(in + (int64_t)s_pair_in[b0 + p] * c_in);
+          const float4* src_d = reinterpret_cast<const float4*>(dout + (base + s_pair_out[b0 + p]) * c_out);
+          float4* dst_a = reinterpret_cast<float4*>(sA + p * c_in);
+          float4* dst_d = reinterpret_cast<float4*>(sD + p * c_out);
+          const int qa = c_in >> 2, qt = (c_in + c_out) >> 2;
+          for (int c0 = l8; c0 < qt; c0 += 32) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int c = c0 + 8 * u;
+              if (c < qt) v[u] = c < qa ? __ldg(src_a + c) : __ldg(src_d + (c - qa));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int c = c0 + 8 * u;
+              if (c < qt) {
+                if (c < qa) dst_a[c] = v[u]; else dst_d[c - qa] = v[u];
+              }
+            }
+          }
+        }
+      } else {
+        for (int p = warp; p < nb_pairs; p += kWgThreads / 32) {
+          const float* src_a = in + (int64_t)s_pair_in[b0 + p] * c_in;
+          const float* src_d = dout + (base + s_pair_out[b0 + p]) * c_out;
+          for (int c = lane; c < c_in; c += 32) sA[p * c_in + c] = __ldg(src_a + c);
+          for (int c = lane; c < c_out; c += 32) sD[p * c_out + c] = __ldg(src_d + c);
+        }
       }
       __syncthreads();
       for (int p = 0; p < nb_pairs; ++p) {
@@ -286,12 +313,12 @@ int mm3d_conv_wgrad_simt(const float* in, int64_t n_in, int c_in, const float* d
   if (n_out == 0) return MM3D_OK;
   int ti = (c_in + 15) / 16, tj = (c_out + 15) / 16;
   if (ti == 9 || ti == 11) ++ti;  // only even tile heights are instantiated above 8
-  // ~3 waves of CTAs over the 148 SMs, at least 256 rows per chunk
-  int64_t chunks = mm3d_cdiv(3 * MM3D_NUM_SMS, K);
-  const int64_t max_chunks = mm3d_cdiv(n_out, kWgThreads);
-  if (chunks > max_chunks) chunks = max_chunks;
-  int rows_per_chunk = (int)(mm3d_cdiv(mm3d_cdiv(n_out, chunks), kWgThreads) * kWgThreads);
-  chunks = mm3d_cdiv(n_out, rows_per_chunk);
+  // Row chunks of 2048: the pairs of a 3^3 table are very unevenly spread over the offsets (the
+  // centre offset alone holds every row), so many small (chunk, offset) CTAs balance far better
+  // than a few big ones; CTAs whose offset has no pair in the chunk exit without touching d_weight.
+  int rows_per_chunk = 2048;
+  while (rows_per_chunk > kWgThreads && mm3d_cdiv(n_out, rows_per_chunk) * K < 4 * MM3D_NUM_SMS) rows_per_chunk >>= 1;
+  const int64_t chunks = mm3d_cdiv(n_out, rows_per_chunk);
   dim3 grid((unsigned)chunks, (unsigned)K);
   const size_t smem = sizeof(float) * kPairBatch * (size_t)(c_in + c_out);
   int miss = 1;

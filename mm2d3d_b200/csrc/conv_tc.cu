@@ -434,16 +434,22 @@ int pow2_cols(int n) {
 
 template <int S, bool ONEHOT>
 int launch_conv_tc(const TcParams& p, size_t smem, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int regs = 0;
+  if (!regs) {
     MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc<S, ONEHOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
+    MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc<S, ONEHOT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+    cudaFuncAttributes fa;
+    MM3D_CUDA(cudaFuncGetAttributes(&fa, k_conv_tc<S, ONEHOT>));
+    regs = fa.numRegs > 0 ? fa.numRegs : 64;
   }
-  // persistent CTAs: as many as fit (registers, shared memory, TMEM columns), tiles round-robin
-  int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_conv_tc<S, ONEHOT>, kThreads, smem) != cudaSuccess)
-    per_sm = 1;
+  // persistent CTAs: as many as fit (registers, shared memory, threads, TMEM columns); tiles round-robin
+  const int regs_alloc = (regs + 7) / 8 * 8;
+  int per_sm = 65536 / (regs_alloc * kThreads);
+  const int by_smem = (int)((227 * 1024) / (smem + 1024));
   const int by_tmem = 512 / p.tmem_cols;
+  if (per_sm > by_smem) per_sm = by_smem;
+  if (per_sm > 2048 / kThreads) per_sm = 2048 / kThreads;
   if (per_sm > by_tmem) per_sm = by_tmem;
   if (per_sm < 1) per_sm = 1;
   int grid = MM3D_NUM_SMS * per_sm;
