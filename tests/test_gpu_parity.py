@@ -363,22 +363,103 @@ def test_unetscn_full_config_one_scan():
     print("worst gradient error relative to the FP32 CPU oracle's own error", worst)
 
 
+def _emulate_tf32_convs():
+    """Context manager: the CPU oracle's convolutions with TF32 operand rounding in forward and
+    dgrad (FP32 accumulate, FP32 wgrad) -- the arithmetic of the tcgen05 TF32 mode."""
+    import contextlib
+
+    def trunc(t):
+        return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+    def rna(t):
+        return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    class Emul(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w, fn):
+            ctx.fn = fn
+            ctx.save_for_backward(x, w)
+            with torch.no_grad():
+                return fn(trunc(x), rna(w))
+
+        @staticmethod
+        def backward(ctx, g):
+            x, w = ctx.saved_tensors
+            with torch.enable_grad():
+                xx = x.detach().requires_grad_(True)
+                (gx,) = torch.autograd.grad(ctx.fn(xx, rna(w.detach())), xx, trunc(g))
+                ww = w.detach().requires_grad_(True)
+                (gw,) = torch.autograd.grad(ctx.fn(x.detach(), ww), ww, g)
+            return gx, gw, None
+
+    @contextlib.contextmanager
+    def cm():
+        orig = (O.submanifold_conv, O.conv_down, O.deconv_up)
+
+        def wrap(f):
+            def g(meta, s, x, w):
+                if x.dtype != torch.float32 or x.shape[1] % 4:
+                    return f(meta, s, x, w)
+                return Emul.apply(x, w, lambda a, b: f(meta, s, a, b))
+            return g
+        O.submanifold_conv, O.conv_down, O.deconv_up = (wrap(f) for f in orig)
+        try:
+            yield
+        finally:
+            O.submanifold_conv, O.conv_down, O.deconv_up = orig
+    return cm()
+
+
 def test_unetscn_full_config_tf32():
-    """Same network in the tcgen05 TF32 mode: 1e-2 bar (north_star), FP64 oracle as the truth."""
+    """Same network in the tcgen05 TF32 mode.  Forward: 1e-2 (north_star) against the FP64 oracle.
+    Whole-network GRADIENTS in TF32 are dominated by the arithmetic itself: the CPU oracle with its
+    convolution operands rounded to TF32 is ~1e-1 (relative L2) away from FP64 on this random-
+    initialised 60-layer BN/ReLU network (ReLU-mask flips), so the bar for the kernels is: no worse
+    than 1.5x the error of that TF32-emulating oracle, per tensor, and gradient direction preserved
+    (cosine > 0.97).  The per-op TF32 tests hold the strict 1e-2 per-op bar."""
+    import copy
+
     import mm2d3d_b200.scn as scn
     from mm2d3d_b200.unet import UNetSCN
     torch.manual_seed(6)
     locs, feats = synth.make_batch("nuscenes", batch=1, seed0=4)
+    coords, feats = torch.from_numpy(locs), torch.from_numpy(feats)
     net_ref = UNetSCN(in_channels=3, backend=scn_cpu)
     net = UNetSCN(in_channels=3).to(DEV)
     net.load_state_dict(net_ref.state_dict())
+    net64 = copy.deepcopy(net_ref).double()
+
+    def run(ref, dt, g=None):
+        xr = feats.clone().to(dt).requires_grad_(True)
+        out = ref([coords, xr])
+        g = torch.randn_like(out) if g is None else g.to(dt)
+        pr = dict(ref.named_parameters())
+        gr = torch.autograd.grad(out, [xr] + list(pr.values()), g)
+        return out, dict(zip(["feats"] + list(pr), gr)), g
+
+    out64, g64, g = run(net64, torch.float64)
+    with _emulate_tf32_convs():
+        _, gemu, _ = run(net_ref, torch.float32, g)
     scn.set_conv_mode("tf32")
     try:
-        worst = _run_pair(net_ref, net, torch.from_numpy(locs), torch.from_numpy(feats), TOL["tf32"])
+        x = feats.clone().to(DEV).requires_grad_(True)
+        out = net([coords.to(DEV), x])
+        p = dict(net.named_parameters())
+        names = list(g64)
+        gg = torch.autograd.grad(out, [x] + [p[k] for k in names[1:]], g.float().to(DEV))
     finally:
         scn.set_conv_mode("fp32")
     _no_device_error()
-    print("worst gradient rel err (tf32)", worst)
+    assert rel_err(out, out64) < TOL["tf32"], ("forward", rel_err(out, out64))
+    worst = 0.0
+    for name, a in zip(names, gg):
+        e_gpu, e_emu = rel_l2(a, g64[name]), rel_l2(gemu[name], g64[name])
+        a64, b64 = a.detach().double().cpu().flatten(), g64[name].flatten()
+        cos = float(torch.dot(a64, b64) / (a64.norm() * b64.norm()).clamp_min(1e-300))
+        worst = max(worst, e_gpu)
+        assert e_gpu <= max(TOL["tf32"], 1.5 * e_emu), (name, e_gpu, e_emu)
+        assert cos > 0.97, (name, cos)
+    print("worst whole-network gradient rel-L2 error in TF32 mode", worst)
 
 
 def test_module_surface_matches_reference_usage():
