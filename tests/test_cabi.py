@@ -41,3 +41,31 @@ def test_sm100a_code_is_embedded():
     from mm2d3d_b200 import build
     out = subprocess.run(["cuobjdump", "-lelf", build.LIB], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_reference_scn_unet_builds_on_cuda_module_surface():
+    """INTEGRATION.md option A: the reference's own 3d_net/scn_unet.py constructs its UNetSCN from
+    mm2d3d_b200.scn with SparseConvNet's parameter tree (construction needs no GPU)."""
+    import importlib.util
+    import sys
+
+    import pytest
+
+    from tests.conftest import REF_3D
+    path = os.path.join(REF_3D, "3d_net", "scn_unet.py")
+    if not os.path.exists(path):
+        pytest.skip("/root/reference not present")
+    import mm2d3d_b200.scn as scn
+    from mm2d3d_b200.unet import UNetSCN
+    sys.modules["sparseconvnet"] = scn
+    try:
+        spec = importlib.util.spec_from_file_location("ref_scn_unet_cuda", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        del sys.modules["sparseconvnet"]
+    ref_net = mod.UNetSCN(in_channels=3)
+    ours = UNetSCN(in_channels=3)
+    assert list(ref_net.state_dict().keys()) == list(ours.state_dict().keys())
+    assert all(a.shape == b.shape for a, b in zip(ref_net.state_dict().values(), ours.state_dict().values()))
+    assert sum(p.numel() for p in ref_net.parameters()) == 2_689_520
