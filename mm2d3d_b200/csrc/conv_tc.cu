@@ -18,18 +18,22 @@
 // Pipelines (mbarriers):      A ring   a_full[S] (256 cp.async arrivals) / a_empty[S] (tcgen05.commit)
 //                             B ring   b_full[SB] (expect_tx + bulk copy) / b_empty[SB] (tcgen05.commit)
 //                             accum    acc_full[2] (tcgen05.commit)       / acc_empty[2] (128 arrivals)
-//                             tables   tbl_full[2] (256 cp.async arrivals), reuse guarded by a named barrier
-// The producer loop is the critical instruction stream (one 16-byte slot decision per lane and
-// pass), so it is branch-free, has the ring stage as a compile-time index (unrolled by S) and
-// advances (offset, channel-chunk) incrementally instead of dividing.
 // The accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the MMAs of i+1.
+//
+// The producer loop is the critical instruction stream (one 16-byte slot decision per lane and
+// pass), so it is branch-free, has the ring stage as a compile-time index (unrolled by S), advances
+// (offset, channel-chunk) incrementally instead of dividing, and fetches the rule-table entries of
+// the NEXT K-block into registers while the current one is being copied (no table staging in
+// shared memory: the smem saved is what lets 2-3 CTAs share an SM and overlap their streams).
 //
 // Absent neighbours cost NO shared-memory traffic: stages are zeroed once and a thread re-zeroes
 // (cp.async with src-size 0) only a slot it filled the previous time the stage was used -- the
 // 3^3 tables are 10-30 % dense, so the fill stays proportional to the real pairs.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
+
+using namespace tc;
 
 constexpr int kTileM = 128;
 constexpr int kKBlock = 32;                 // tf32 elements per 128-byte row of a K-block
@@ -37,113 +41,9 @@ constexpr int kStageBytes = kTileM * 128;   // one A stage = one K-block of 128 
 constexpr int kProducers = 256;             // 8 warps: 32 rows x 8 chunk lanes per pass, 4 passes
 constexpr int kEpilogue = 128;
 constexpr int kThreads = kProducers + kEpilogue + 64;
-constexpr int kMaxBStages = 4;
 constexpr int kMaxStages = 6;
+constexpr int kMaxBStages = 4;
 constexpr int kMaxK = 27;
-constexpr uint32_t kSpinLimit = 1u << 22;
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok;
-}
-// Bounded wait: a broken pipeline sets *abort (shared) and the kernel's error flag instead of
-// hanging the GPU; every other wait sees the abort flag and leaves too.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
-  for (uint32_t i = 0; i < kSpinLimit; ++i) {
-    if (mbar_try_wait(bar, parity)) return true;
-    if ((i & 1023) == 1023 && *abort_flag) return false;
-  }
-  *abort_flag = 1;
-  return false;
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-// 16-byte asynchronous copy global -> shared; src_bytes < 16 zero-fills the rest (0 = pure zero fill)
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
-}
-// the mbarrier receives one arrival when all cp.async issued so far by this thread have landed
-__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
-// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major) | SBO>>4 [32,46) = 1024 B between
-// 8-row groups | version=1 [46,48) | layout=SWIZZLE_128B(2) [61,64)
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=B=TF32 [7,10)=[10,13)=2,
-// K-major A and B (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
-__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-}
 
 struct TcParams {
   const float* in;
@@ -189,18 +89,15 @@ template <int S, bool ONEHOT>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_tc(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A stages][B stages][tables x2][barriers][tmem ptr][abort]
+  // carve: [A stages][B stages][barriers][tmem ptr][abort]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const int SB = p.b_stages;
   const uint32_t b_bytes = (uint32_t)p.n_pad * 128u;
   const uint32_t b_stride = (b_bytes + 1023u) & ~1023u;
-  const uint32_t tbl_bytes = ONEHOT ? (uint32_t)(kTileM * 4 + kTileM) : (uint32_t)(p.K * kTileM * 4);
-  const uint32_t tbl_buf = (tbl_bytes + 127u) & ~127u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + (uint32_t)S * kStageBytes;
-  const uint32_t t_base = b_base + (uint32_t)SB * b_stride;
-  const uint32_t bar_base = t_base + 2u * tbl_buf;
+  const uint32_t bar_base = b_base + (uint32_t)SB * b_stride;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar_base - smem_base));
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(kMaxStages + s); };
@@ -208,8 +105,7 @@ k_conv_tc(const TcParams p) {
   auto b_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + kMaxBStages + s); };
   auto acc_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 * kMaxBStages + s); };
   auto acc_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 * kMaxBStages + 2 + s); };
-  auto tbl_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 * kMaxBStages + 4 + s); };
-  constexpr int kNumBars = 2 * kMaxStages + 2 * kMaxBStages + 6;
+  constexpr int kNumBars = 2 * kMaxStages + 2 * kMaxBStages + 4;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNumBars);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + kNumBars + 1);
 
@@ -230,7 +126,6 @@ k_conv_tc(const TcParams p) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full(s), 1);
       mbar_init(acc_empty(s), kEpilogue);
-      mbar_init(tbl_full(s), kProducers);
     }
     *abort_flag = 0;
     fence_barrier_init();
@@ -248,96 +143,79 @@ k_conv_tc(const TcParams p) {
     const int c = threadIdx.x & 7;   // 16-byte chunk within the 128-byte K-block row
     // this thread's slot in a stage: row g (+32 per pass), swizzled chunk
     const uint32_t slot0 = a_base + (uint32_t)g * 128u + (uint32_t)((c ^ (g & 7)) << 4);
-    uint32_t filled[S];              // bit ps: the slot of pass ps holds data, not zeros
+    const int k0 = c / p.cq, cc0 = c - k0 * p.cq;  // (offset, chunk) of virtual-K chunk q = c
+    uint32_t filled[S];                             // bit ps: the slot of pass ps holds data, not zeros
 #pragma unroll
     for (int s = 0; s < S; ++s) filled[s] = 0;
 
-    // asynchronous copy of one tile's slice of the rule table into table buffer `buf`
-    auto load_table = [&](int tile, int buf) {
-      const int64_t row0 = (int64_t)tile * kTileM;
-      const uint32_t dst = t_base + (uint32_t)buf * tbl_buf;
-      if (ONEHOT) {
-        // parent[128] (int32) then off[128] (uint8)
-        const int i = threadIdx.x;
-        if (i < 32) {
-          const int64_t r = row0 + i * 4;
-          const int64_t left = (int64_t)p.n_out - r;
-          cp_async16(dst + i * 16, p.tbl + (left > 0 ? r : 0), left >= 4 ? 16u : left > 0 ? (uint32_t)left * 4u : 0u);
-        } else if (i < 40) {
-          const int64_t r = row0 + (i - 32) * 16;
-          const int64_t left = (int64_t)p.n_out - r;
-          cp_async16(dst + kTileM * 4 + (i - 32) * 16, p.onehot_off + (left > 0 ? r : 0),
-                     left >= 16 ? 16u : left > 0 ? (uint32_t)left : 0u);
-        }
-      } else {
-        const int n_chunks = p.K * 32;  // 32 x 16-byte chunks per offset plane
-        for (int i = threadIdx.x; i < n_chunks; i += kProducers) {
-          const int k = i >> 5, ch = i & 31;
-          const int64_t r = row0 + ch * 4;
-          const int64_t left = (int64_t)p.n_out - r;
-          cp_async16(dst + (uint32_t)i * 16, p.tbl + (int64_t)k * p.tbl_stride + (left > 0 ? r : 0),
-                     left >= 4 ? 16u : left > 0 ? (uint32_t)left * 4u : 0u);
+    // rule-table entries of one K-block for this lane's 4 rows (-1 = absent / out of range)
+    int par_c[4], off_c[4], par_n[4], off_n[4];  // ONEHOT: parent / offset of the current and next tile
+    auto load_onehot = [&](int tile, int (&par)[4], int (&off)[4]) {
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        const int64_t row = (int64_t)tile * kTileM + ps * 32 + g;
+        const bool ok = tile < p.num_tiles && row < p.n_out;
+        par[ps] = ok ? __ldg(p.tbl + row) : -1;
+        off[ps] = ok ? (int)__ldg(p.onehot_off + row) : -1;
+      }
+    };
+    auto entries = [&](int tile, int kb, int k, const int (&par)[4], const int (&off)[4], int (&nb)[4]) {
+      const bool q_ok = tile < p.num_tiles && kb * 8 + c < p.nq;
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        if (ONEHOT) {
+          nb[ps] = (q_ok && off[ps] == k) ? par[ps] : -1;
+        } else {
+          const int64_t row = (int64_t)tile * kTileM + ps * 32 + g;
+          nb[ps] = (q_ok && row < p.n_out) ? __ldg(p.tbl + (int64_t)k * p.tbl_stride + row) : -1;
         }
       }
-      cp_async_arrive(tbl_full(buf));
     };
 
-    int tile = blockIdx.x;
-    uint32_t tile_iter = 0, round = 0;
-    int kb = 0, k = 0, cc = 0, rows_left = 0;
-    const int32_t* tb = nullptr;
-    if (tile < p.num_tiles) load_table(tile, 0);
+    int tile = blockIdx.x, kb = 0, k = k0, cc = cc0;
+    uint32_t round = 0;
+    int nb[4];
+    if (ONEHOT) {
+      load_onehot(tile, par_c, off_c);
+      load_onehot(tile + gridDim.x, par_n, off_n);
+    }
+    entries(tile, kb, k, par_c, off_c, nb);
     while (tile < p.num_tiles) {
 #pragma unroll
       for (int s = 0; s < S; ++s) {
         if (tile >= p.num_tiles) break;
-        if (kb == 0) {
-          // new tile: every producer is done with the other table buffer -> refill it for the
-          // tile after this one, then wait for this tile's table
-          const int buf = (int)(tile_iter & 1u);
-          producer_bar_sync();
-          if (tile + (int)gridDim.x < p.num_tiles) load_table(tile + gridDim.x, buf ^ 1);
-          if (!mbar_wait(tbl_full(buf), (tile_iter >> 1) & 1u, abort_flag)) goto done;
-          tb = reinterpret_cast<const int32_t*>(smem + (t_base - smem_base) + (size_t)buf * tbl_buf);
-          const int64_t left = (int64_t)p.n_out - (int64_t)tile * kTileM;
-          rows_left = left < kTileM ? (int)left : kTileM;
-          // (offset, chunk) of virtual-K chunk q = c
-          k = c / p.cq;
-          cc = c - k * p.cq;
-        }
+        // coordinates of the next K-block, and its table entries (in flight while this one is copied)
+        int n_tile = tile, n_kb = kb + 1, n_k = k + p.d8, n_cc = cc + p.m8;
+        if (n_cc >= p.cq) { n_cc -= p.cq; ++n_k; }
+        const bool new_tile = n_kb == p.kbt;
+        if (new_tile) { n_kb = 0; n_tile += gridDim.x; n_k = k0; n_cc = cc0; }
+        int nb_next[4];
+        if (ONEHOT && new_tile) entries(n_tile, n_kb, n_k, par_n, off_n, nb_next);
+        else entries(n_tile, n_kb, n_k, par_c, off_c, nb_next);
+
         if (!mbar_wait(a_empty(s), (round & 1u) ^ 1u, abort_flag)) goto done;
-        const bool q_ok = kb * 8 + c < p.nq;
-        const int kt = q_ok ? k : 0;  // lanes past the end of the virtual K must not index past the table
         const uint32_t src_off = (uint32_t)cc * 4u;
-        uint32_t f = filled[s], nf = 0;
+        const uint32_t f = filled[s];
+        uint32_t nf = 0;
 #pragma unroll
         for (int ps = 0; ps < 4; ++ps) {
-          const int r = ps * 32 + g;
-          int nb;
-          if (ONEHOT) {
-            const int par = tb[r];
-            const int off = (int)reinterpret_cast<const uint8_t*>(tb)[kTileM * 4 + r];
-            nb = off == kt ? par : -1;
-          } else {
-            nb = tb[kt * kTileM + r];
-          }
-          const bool have = q_ok && r < rows_left && nb >= 0;
-          const float* src = have ? p.in + ((uint32_t)nb * (uint32_t)p.c_in + src_off) : p.in;
+          const bool have = nb[ps] >= 0;
+          const float* src = have ? p.in + ((uint32_t)nb[ps] * (uint32_t)p.c_in + src_off) : p.in;
           if (have || ((f >> ps) & 1u))
             cp_async16(slot0 + (uint32_t)(s * kStageBytes + ps * 32 * 128), src, have ? 16u : 0u);
           nf |= (have ? 1u : 0u) << ps;
         }
         filled[s] = nf;
         cp_async_arrive(a_full(s));
-        // advance to the next K-block
-        k += p.d8;
-        cc += p.m8;
-        if (cc >= p.cq) { cc -= p.cq; ++k; }
-        if (++kb == p.kbt) {
-          kb = 0;
-          tile += gridDim.x;
-          ++tile_iter;
+
+        if (ONEHOT && new_tile) {
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) { par_c[ps] = par_n[ps]; off_c[ps] = off_n[ps]; }
+          load_onehot(n_tile + gridDim.x, par_n, off_n);
         }
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) nb[ps] = nb_next[ps];
+        tile = n_tile; kb = n_kb; k = n_k; cc = n_cc;
       }
       ++round;
     }
@@ -373,7 +251,7 @@ k_conv_tc(const TcParams p) {
   } else if (warp == 12) {
     // =================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(p.n_pad);
+      const uint32_t idesc = make_idesc_tf32(kTileM, p.n_pad);
       uint32_t it = 0, tile_iter = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++tile_iter) {
@@ -483,7 +361,7 @@ size_t mm3d_conv_tc_workspace_bytes(int c_in, int c_out, int K) {
 // Sticky per-device error flag set by a kernel whose mbarrier pipeline timed out (never in a
 // correct build; it turns a would-be GPU hang into a reportable error).
 static int* g_err_flag[64] = {nullptr};
-static int* device_err_flag() {
+int* mm3d_device_err_flag() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   if (!g_err_flag[dev]) {
@@ -496,7 +374,7 @@ static int* device_err_flag() {
 }
 
 extern "C" int mm3d_take_device_error(void) {
-  int* p = device_err_flag();
+  int* p = mm3d_device_err_flag();
   if (!p) return -1;
   int v = 0;
   if (cudaMemcpy(&v, p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
@@ -514,9 +392,8 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
                "tcgen05 conv: tensor too large for 32-bit element offsets");
   MM3D_REQUIRE(ws && ws_bytes >= mm3d_conv_tc_workspace_bytes(c_in, c_out, K), MM3D_ERR_WORKSPACE,
                "tcgen05 conv: workspace too small");
-  MM3D_REQUIRE((((uintptr_t)in | (uintptr_t)out | (uintptr_t)ws | (uintptr_t)tbl | (uintptr_t)onehot_off) & 15) == 0,
-               MM3D_ERR_INVALID, "tcgen05 conv: pointers must be 16-byte aligned");
-  MM3D_REQUIRE(onehot_off || (tbl_stride % 4) == 0, MM3D_ERR_INVALID, "tcgen05 conv: tbl_stride must be a multiple of 4");
+  MM3D_REQUIRE((((uintptr_t)in | (uintptr_t)out | (uintptr_t)ws) & 15) == 0, MM3D_ERR_INVALID,
+               "tcgen05 conv: pointers must be 16-byte aligned");
   const bool tr = (flags & MM3D_CONV_TRANSPOSE_W) != 0, mir = (flags & MM3D_CONV_MIRROR_K) != 0;
   MM3D_REQUIRE(tr || !mir, MM3D_ERR_UNSUPPORTED, "MIRROR_K without TRANSPOSE_W not implemented");
   if (n_out == 0) return MM3D_OK;
@@ -530,15 +407,14 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
   p.cq = c_in / 4; p.nq = K * p.cq; p.kbt = kbt; p.d8 = 8 / p.cq; p.m8 = 8 % p.cq; p.n_pad = n_pad;
   p.num_tiles = (int)mm3d_cdiv(n_out, kTileM);
   p.tmem_cols = pow2_cols(2 * n_pad);
-  p.err = device_err_flag();
+  p.err = mm3d_device_err_flag();
   const uint32_t b_stride = ((uint32_t)n_pad * 128u + 1023u) & ~1023u;
-  const uint32_t tbl_buf = ((onehot_off ? (uint32_t)(kTileM * 5) : (uint32_t)(K * kTileM * 4)) + 127u) & ~127u;
-  // small N: 4 A + 4 B stages and two CTAs per SM; wide N: one CTA per SM with a 6-deep A ring
-  const bool wide = n_pad > 64;
+  // narrow N: 4 A + 4 B stages, several CTAs per SM; wide N: one CTA per SM with a 6-deep A ring
+  const bool wide = n_pad > 96;
   const int S = wide ? 6 : 4;
   p.b_stages = wide ? (n_pad > 128 ? 2 : 3) : 4;
-  const size_t smem = 1024 + (size_t)S * kStageBytes + (size_t)p.b_stages * b_stride + 2 * tbl_buf +
-                      8 * (2 * kMaxStages + 2 * kMaxBStages + 6) + 64;
+  const size_t smem = 1024 + (size_t)S * kStageBytes + (size_t)p.b_stages * b_stride +
+                      8 * (2 * kMaxStages + 2 * kMaxBStages + 4) + 64;
   int rc;
   if (wide) rc = onehot_off ? launch_conv_tc<6, true>(p, smem, stream) : launch_conv_tc<6, false>(p, smem, stream);
   else      rc = onehot_off ? launch_conv_tc<4, true>(p, smem, stream) : launch_conv_tc<4, false>(p, smem, stream);
