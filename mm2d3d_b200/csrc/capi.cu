@@ -39,6 +39,11 @@ int mm3d_conv_wgrad_simt(const float* in, int64_t n_in, int c_in, const float* d
 // conv_tc.cu
 size_t mm3d_conv_tc_workspace_bytes(int c_in, int c_out, int K);
 int mm3d_conv_tc_supported(int c_in, int c_out, int K);
+// conv_tc_wgrad.cu
+int mm3d_conv_wgrad_tc_supported(int c_in, int c_out, int K);
+int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_out, int64_t n_out, int c_out,
+                       float* d_weight, int K, const int32_t* tbl, int64_t tbl_stride,
+                       const uint8_t* onehot_off, int accumulate, cudaStream_t stream);
 int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
                      const float* weight, int K, const int32_t* tbl, int64_t tbl_stride,
                      const uint8_t* onehot_off, int flags, void* ws, size_t ws_bytes, cudaStream_t stream);
@@ -92,8 +97,12 @@ extern "C" int mm3d_conv_wgrad(const float* in, int64_t n_in, int c_in, const fl
   int rc = check_conv_args(in, d_out, d_weight, tbl, n_in, n_out, c_in, c_out, K, tbl_stride, onehot_off);
   if (rc) return rc;
   switch (mode) {
+    case MM3D_MODE_TF32:
+      if (mm3d_conv_wgrad_tc_supported(c_in, c_out, K))
+        return mm3d_conv_wgrad_tc(in, n_in, c_in, d_out, n_out, c_out, d_weight, K, tbl, tbl_stride, onehot_off,
+                                  accumulate, (cudaStream_t)stream);
+      // fall through: shapes the tcgen05 kernel does not take (the 3-channel stem) use the FP32 kernel
     case MM3D_MODE_FP32:
-    case MM3D_MODE_TF32:  // wgrad has no tcgen05 kernel yet: the FP32 SIMT kernel serves both modes
       return mm3d_conv_wgrad_simt(in, n_in, c_in, d_out, n_out, c_out, d_weight, K, tbl, tbl_stride, onehot_off,
                                   accumulate, (cudaStream_t)stream);
     default:
