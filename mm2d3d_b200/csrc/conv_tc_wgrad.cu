@@ -4,10 +4,11 @@
 //
 // With the forward kernel's "virtual K" vk = k*C_in + ci (conv_tc.cu) this is, per tile of 128
 // output rows,   dWflat[vk][co] += A_tile^T [vk x 128] . G_tile [128 x co]
-// where A_tile is EXACTLY the gathered, zero-filled, 128B-swizzled stage the forward kernel builds
-// ([128 rows][32 vk] per K-block).  Read as an MN-major operand that same stage is a 32-wide slice
-// of M, so four consecutive K-blocks (stages 16 KB apart = the descriptor's LBO) form one M=128
-// operand and every 8 rows (one 1024-byte swizzle atom) are one tf32 K-step: 16 tcgen05.mma per
+// where A_tile is the gathered, zero-filled stage the forward kernel builds ([128 rows][32 vk] per
+// K-block), here written with the 32-byte-granule swizzle that MN-major tf32 operands require
+// (SWIZZLE_128B_BASE32B).  Read as an MN-major operand a stage is a 32-wide slice of M, so four
+// consecutive K-blocks (stages 16 KB apart = the descriptor's LBO) form one M=128 operand and
+// every 8 rows (two 4-row swizzle atoms, SBO = 512 B) are one tf32 K-step: 16 tcgen05.mma per
 // (tile, group of 4 K-blocks), accumulating the group's [128 vk x C_out] slab of dW in TMEM over all
 // tiles the CTA owns.  dout tiles are copied (no gather) into the same row-major swizzled form and
 // serve as the MN-major B operand.  Grid = (tile splits) x (group splits): a CTA keeps its TMEM
@@ -95,7 +96,7 @@ k_wgrad_tc(const WgParams p) {
   if (warp < 8) {
     // =================================================================== gather producers
     const int g = threadIdx.x >> 3, c = threadIdx.x & 7;
-    const uint32_t slot0 = a_base + (uint32_t)g * 128u + (uint32_t)((c ^ (g & 7)) << 4);
+    const uint32_t slot0 = a_base + (uint32_t)g * 128u + swz_base32(c, g);  // row g (+32 per pass)
     // (offset, chunk) of this lane's virtual-K chunk in the CTA's first K-block
     const int q0 = kb_lo * 8 + c;
     const int k0 = q0 / p.cq, cc0 = q0 - k0 * p.cq;
@@ -134,7 +135,7 @@ k_wgrad_tc(const WgParams p) {
       const uint32_t dst = g_base + (uint32_t)buf * g_bytes + (uint32_t)r * 128u;
       const int nch = p.c_out >> 2;
       for (int ch = threadIdx.x & 1; ch < nch; ch += 2)
-        cp_async16(dst + (uint32_t)(ch >> 3) * kStageBytes + (uint32_t)(((ch & 7) ^ (r & 7)) << 4), src + ch * 4,
+        cp_async16(dst + (uint32_t)(ch >> 3) * kStageBytes + swz_base32(ch & 7, r), src + ch * 4,
                    ok ? 16u : 0u);
       cp_async_arrive(g_full(buf));
     };
@@ -236,9 +237,10 @@ k_wgrad_tc(const WgParams p) {
           tc_fence_after();
           const uint32_t ab = a_base + (uint32_t)s0 * kStageBytes;
           const uint32_t d_tmem = tmem_base + (uint32_t)(gi * p.n_pad);
+          // per K-step of 8 rows: two 4-row swizzle atoms (SBO = 512 B), four 32-wide M / nblk N blocks (LBO)
           for (int r8 = 0; r8 < 16; ++r8)
-            umma_tf32(d_tmem, make_desc_sw128(ab + r8 * 1024, kStageBytes, 1024),
-                      make_desc_sw128(gb + r8 * 1024, kStageBytes, 1024), idesc, (tile_iter | (uint32_t)r8) != 0);
+            umma_tf32(d_tmem, make_desc_sw128_base32(ab + r8 * 1024, kStageBytes, 512),
+                      make_desc_sw128_base32(gb + r8 * 1024, kStageBytes, 512), idesc, (tile_iter | (uint32_t)r8) != 0);
           for (int j = 0; j < 4; ++j) umma_commit(a_empty(s0 + j));
           it += 4;
         }

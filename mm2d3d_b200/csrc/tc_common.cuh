@@ -106,6 +106,17 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// MN-major operands of 32-bit types (tf32) must use SWIZZLE_128B_BASE32B (layout type 1): rows of 128
+// bytes whose four 32-byte granules are XOR-ed with (row & 3) (cute Swizzle<2,5,2>), 4 K-rows per atom.
+// LBO = bytes between 32-element M/N blocks, SBO = bytes between 4-row K groups.
+__device__ __forceinline__ uint64_t make_desc_sw128_base32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+// byte offset of 16-byte chunk c (0..7) of row r inside a 128-byte row under that swizzle
+__device__ __forceinline__ uint32_t swz_base32(int c, int r) {
+  return (uint32_t)((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4));
+}
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=B=TF32 [7,10)=[10,13)=2,
 // a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
 __device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n, int a_mn_major = 0, int b_mn_major = 0) {
