@@ -31,6 +31,29 @@ template <> __device__ __forceinline__ void vstore<1>(float* p, const float (&v)
 // dynamic shared: 2*C doubles (accumulators) -- also reused as 2*C floats of scale/shift
 extern __shared__ double s_acc[];
 
+// Block reduction of per-thread FP32 partials (VEC channels each, thread layout rows_pass x cv):
+// partials go to shared memory, then one thread per channel sums the rows_pass values in FP64 and
+// issues ONE global FP64 atomic per channel and CTA.
+template <int VEC>
+__device__ __forceinline__ void block_flush(const float (&s)[VEC], const float (&q)[VEC], int c, int cv, int rows_pass,
+                                            int r, int v, double* __restrict__ sums) {
+  float* part = reinterpret_cast<float*>(s_acc);  // [2][rows_pass][c]
+  if (r < rows_pass) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      part[r * c + v * VEC + j] = s[j];
+      part[(rows_pass + r) * c + v * VEC + j] = q[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * c; i += kThreads) {
+    const int which = i >= c, ch = i - which * c;
+    double acc = 0.0;
+    for (int rr = 0; rr < rows_pass; ++rr) acc += (double)part[(which * rows_pass + rr) * c + ch];
+    atomicAdd(sums + i, acc);
+  }
+}
+
 // ---- forward statistics: sums[0..C) = sum x, sums[C..2C) = sum x^2
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
@@ -38,26 +61,29 @@ k_bn_stats(const float* __restrict__ x, int64_t n, int c, double* __restrict__ s
   const int cv = c / VEC;
   const int rows_pass = kThreads / cv;
   const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
-  for (int i = threadIdx.x; i < 2 * c; i += kThreads) s_acc[i] = 0.0;
-  __syncthreads();
-  if (r < rows_pass) {
-    float s[VEC], q[VEC];
+  float s[VEC], q[VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) s[j] = q[j] = 0.f;
-    for (int64_t row = (int64_t)blockIdx.x * rows_pass + r; row < n; row += (int64_t)gridDim.x * rows_pass) {
+  for (int j = 0; j < VEC; ++j) s[j] = q[j] = 0.f;
+  if (r < rows_pass) {
+    const int64_t stride = (int64_t)gridDim.x * rows_pass;
+    int64_t row = (int64_t)blockIdx.x * rows_pass + r;
+    for (; row + 3 * stride < n; row += 4 * stride) {  // four independent loads in flight
+      float t[4][VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) vload<VEC>(x + (row + u * stride) * c + v * VEC, t[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { s[j] += t[u][j]; q[j] = fmaf(t[u][j], t[u][j], q[j]); }
+    }
+    for (; row < n; row += stride) {
       float t[VEC];
       vload<VEC>(x + row * c + v * VEC, t);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) { s[j] += t[j]; q[j] = fmaf(t[j], t[j], q[j]); }
     }
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      atomicAdd(&s_acc[v * VEC + j], (double)s[j]);
-      atomicAdd(&s_acc[c + v * VEC + j], (double)q[j]);
-    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * c; i += kThreads) atomicAdd(sums + i, s_acc[i]);
+  block_flush<VEC>(s, q, c, cv, rows_pass, r, v, sums);
 }
 
 // ---- forward apply (+ finalise: save_mean / save_invstd / running stats by block 0)
@@ -126,39 +152,44 @@ k_bn_bwd_stats(const float* __restrict__ x, const float* __restrict__ dy, int64_
   const int cv = c / VEC;
   const int rows_pass = kThreads / cv;
   const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
-  for (int i = threadIdx.x; i < 2 * c; i += kThreads) s_acc[i] = 0.0;
-  __syncthreads();
+  float s[VEC], q[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) s[j] = q[j] = 0.f;
   if (r < rows_pass) {
-    float mean[VEC], invstd[VEC], scale[VEC], bet[VEC], s[VEC], q[VEC];
+    float mean[VEC], invstd[VEC], scale[VEC], bet[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       mean[j] = __ldg(save_mean + v * VEC + j);
       invstd[j] = __ldg(save_invstd + v * VEC + j);
       scale[j] = invstd[j] * __ldg(gamma + v * VEC + j);
       bet[j] = __ldg(beta + v * VEC + j);
-      s[j] = q[j] = 0.f;
     }
-    for (int64_t row = (int64_t)blockIdx.x * rows_pass + r; row < n; row += (int64_t)gridDim.x * rows_pass) {
-      float t[VEC], g[VEC];
-      vload<VEC>(x + row * c + v * VEC, t);
-      vload<VEC>(dy + row * c + v * VEC, g);
+    const int64_t stride = (int64_t)gridDim.x * rows_pass;
+    int64_t row = (int64_t)blockIdx.x * rows_pass + r;
+    for (; row < n; row += 2 * stride) {  // two rows (four loads) in flight
+      float t[2][VEC], g[2][VEC];
+      const bool second = row + stride < n;
+      vload<VEC>(x + row * c + v * VEC, t[0]);
+      vload<VEC>(dy + row * c + v * VEC, g[0]);
+      if (second) {
+        vload<VEC>(x + (row + stride) * c + v * VEC, t[1]);
+        vload<VEC>(dy + (row + stride) * c + v * VEC, g[1]);
+      }
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        const float xc = t[j] - mean[j];
-        const float o = fmaf(xc, scale[j], bet[j]);
-        const float d = o > 0.f ? g[j] : g[j] * leak;
-        s[j] += d;
-        q[j] = fmaf(d, xc * invstd[j], q[j]);
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !second) break;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float xc = t[u][j] - mean[j];
+          const float o = fmaf(xc, scale[j], bet[j]);
+          const float d = o > 0.f ? g[u][j] : g[u][j] * leak;
+          s[j] += d;
+          q[j] = fmaf(d, xc * invstd[j], q[j]);
+        }
       }
     }
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      atomicAdd(&s_acc[v * VEC + j], (double)s[j]);
-      atomicAdd(&s_acc[c + v * VEC + j], (double)q[j]);
-    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * c; i += kThreads) atomicAdd(sums + i, s_acc[i]);
+  block_flush<VEC>(s, q, c, cv, rows_pass, r, v, sums);
 }
 
 template <int VEC>
@@ -206,7 +237,7 @@ int bn_grid(int64_t n, int cv) {
   const int rows_pass = kThreads / cv;
   int64_t g = mm3d_cdiv(n, (int64_t)rows_pass * 4);  // >= 4 rows per thread when there is enough work
   if (g < 1) g = 1;
-  const int64_t cap = (int64_t)MM3D_NUM_SMS * 8;
+  const int64_t cap = (int64_t)MM3D_NUM_SMS * 4;
   return (int)(g < cap ? g : cap);
 }
 
@@ -233,7 +264,8 @@ extern "C" int mm3d_bnrelu_fwd(const float* x, float* y, int64_t n, int c, const
   if (n == 0) return MM3D_OK;
   double* sums = (double*)ws;
   const int grid = bn_grid(n, cv);
-  const size_t smem = sizeof(double) * 2 * c;
+  const size_t smem = sizeof(double) * 2 * c > sizeof(float) * 2 * (kThreads / cv) * (size_t)c
+                          ? sizeof(double) * 2 * c : sizeof(float) * 2 * (kThreads / cv) * (size_t)c;
   if (training) {
     MM3D_REQUIRE(save_mean && save_invstd && running_mean && running_var, MM3D_ERR_INVALID, "training needs stat buffers");
     MM3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c, stream));
@@ -264,7 +296,8 @@ extern "C" int mm3d_bnrelu_bwd(const float* x, const float* dy, float* dx, int64
     return MM3D_OK;
   }
   const int grid = bn_grid(n, cv);
-  const size_t smem = sizeof(double) * 2 * c;
+  const size_t smem = sizeof(double) * 2 * c > sizeof(float) * 2 * (kThreads / cv) * (size_t)c
+                          ? sizeof(double) * 2 * c : sizeof(float) * 2 * (kThreads / cv) * (size_t)c;
   BN_DISPATCH(k_bn_bwd_stats, x, dy, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums);
   BN_DISPATCH(k_bn_bwd_apply, x, dy, dx, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums, d_gamma,
               d_beta, training);

@@ -140,6 +140,14 @@ class TableConvFn(torch.autograd.Function):
             raise ValueError(f"{kind} convolution: input {tuple(x.shape)} / weight {tuple(w.shape)} do not match "
                              f"the active set ({fwd_t.n_in} rows, {fwd_t.K} offsets)")
         m = MODES[mode]
+        # tensor-core modes gather whole 16-byte row pieces: pad an odd channel count (the 3-channel
+        # stem) with zero channels instead of leaving that layer on the SIMT kernels
+        pad = (-c_in) % 4 if m != _lib.MODE_FP32 else 0
+        if pad:
+            x = torch.nn.functional.pad(x, (0, pad))
+            w = torch.nn.functional.pad(w, (0, 0, 0, pad))
+            c_in += pad
+        ctx.pad = pad
         out = torch.empty(fwd_t.n_out, c_out, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             wsb = lib.mm3d_conv_workspace_bytes(fwd_t.n_in, fwd_t.n_out, c_in, c_out, K, m)
@@ -170,10 +178,13 @@ class TableConvFn(torch.autograd.Function):
                                         bwd_t.tbl, bwd_t.stride, bwd_t.onehot, bwd_flags, m, ptr(ws), ws.numel(),
                                         stream), "mm3d_conv_fwd(dgrad)")
             if ctx.needs_input_grad[1]:
-                d_w = torch.empty(ctx.wshape, dtype=torch.float32, device=x.device)
+                d_w = torch.empty(w.shape, dtype=torch.float32, device=x.device)
                 check(lib.mm3d_conv_wgrad(ptr(x), fwd_t.n_in, c_in, ptr(d_out), fwd_t.n_out, c_out, ptr(d_w), K,
                                           fwd_t.tbl, fwd_t.stride, fwd_t.onehot, 0, m, ptr(ws), ws.numel(), stream),
                       "mm3d_conv_wgrad")
+        if ctx.pad:
+            d_x = d_x[:, :c_in - ctx.pad] if d_x is not None else None
+            d_w = d_w[..., :c_in - ctx.pad, :] if d_w is not None else None
         return d_x, d_w, None, None, None, None
 
 
