@@ -161,6 +161,31 @@ MM3D_API int mm3d_lift2d_fwd(const void* fmap, int dtype, int B, int C, int H, i
 MM3D_API int mm3d_lift2d_bwd(const void* d_out, int dtype, int B, int C, int H, int W, const int64_t* idx,
                     const int64_t* sample_offsets, int64_t n, void* d_fmap, mm3d_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Whole-network executor: UNetSCN (3d_net/scn_unet.py:90-126, VGG blocks, block_reps == 1) forward and
+ * backward as one call each -- the same kernels as above, driven natively instead of from ~110
+ * Python autograd nodes.  level_desc: 6 int64 per level {rows, nbr table ptr, table stride, parent ptr,
+ * off ptr, child ptr}.  params / grads: HOST arrays of device pointers in module-tree order:
+ *   stem.w | per level: pre_bn{gamma,beta,running_mean,running_var} pre.w [dn_bn{4} dn.w <deeper level>
+ *   up_bn{4} up.w post_bn{4} post.w] | head_bn{4}          (mm3d_unet_num_params slots; grads ignore
+ * the running-stat slots).  act: activations kept from forward to backward; tmp: backward temporaries.
+ * ---------------------------------------------------------------------------------------- */
+MM3D_API int64_t mm3d_unet_num_params(int num_planes);
+MM3D_API size_t mm3d_unet_act_bytes(int in_channels, int m, int num_planes, int mode, const int64_t* level_desc,
+                           int64_t n_points);
+MM3D_API size_t mm3d_unet_bwd_bytes(int in_channels, int m, int num_planes, int mode, const int64_t* level_desc,
+                           int64_t n_points);
+MM3D_API size_t mm3d_unet_scratch_bytes(int in_channels, int m, int num_planes, int mode);
+MM3D_API int mm3d_unet_forward(int in_channels, int m, int num_planes, int mode, int training, float eps, float momentum,
+                      const int64_t* level_desc, int64_t n_points, const int32_t* p2v, const int32_t* npts,
+                      const float* feats, float* out, void* const* params, void* act, size_t act_bytes,
+                      void* scratch, size_t scratch_bytes, mm3d_stream_t stream);
+MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode, int training,
+                       const int64_t* level_desc, int64_t n_points, const int32_t* p2v, const int32_t* npts,
+                       const float* d_out, float* d_feats, void* const* params, void* const* grads,
+                       void* act, size_t act_bytes, void* tmp, size_t tmp_bytes, void* scratch,
+                       size_t scratch_bytes, mm3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

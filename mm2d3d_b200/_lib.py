@@ -52,6 +52,12 @@ SIGNATURES = {
     "mm3d_bnrelu_bwd": (_i, [_p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _f, _i, _p, _sz, _p]),
     "mm3d_lift2d_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i64, _p, _p]),
     "mm3d_lift2d_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i64, _p, _p]),
+    "mm3d_unet_num_params": (_i64, [_i]),
+    "mm3d_unet_act_bytes": (_sz, [_i, _i, _i, _i, _p, _i64]),
+    "mm3d_unet_bwd_bytes": (_sz, [_i, _i, _i, _i, _p, _i64]),
+    "mm3d_unet_scratch_bytes": (_sz, [_i, _i, _i, _i]),
+    "mm3d_unet_forward": (_i, [_i, _i, _i, _i, _i, _f, _f, _p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p, _sz, _p]),
+    "mm3d_unet_backward": (_i, [_i, _i, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _sz, _p, _sz, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -1,0 +1,423 @@
+// Whole-network executor: UNetSCN forward and backward as ONE C-ABI call each.
+//
+// The per-layer entry points are enough for a drop-in, but driving ~110 autograd nodes from
+// Python costs ~8 ms of host time per step -- as much as the GPU work itself.  The executor walks
+// the fixed U-Net topology of 3d_net/scn_unet.py:55-84 (VGG blocks, block_reps == 1) natively:
+// it carves every activation out of one caller-provided workspace with a bump allocator that
+// forward and backward replay identically, and issues the same kernels the modules use.
+//
+//   level l (p = m(l+1), q = m(l+2)):
+//     X_l --BN--> A_l --SMC--> Y_l                                   ("pre" block)
+//     if l < L-1:  Y_l --BN--> B_l --Conv 2/2--> X_{l+1} ... R_{l+1} --BN--> E_l --Deconv 2/2--> F_l
+//                  J_l = [Y_l | F_l] --BN--> G_l --SMC(2p->p)--> R_l   ("post" block)
+//     else         R_l = Y_l
+//   stem: V (InputLayer mean) --SMC(in->m)--> X_0 ;  head: R_0 --BN--> Z --OutputLayer--> out
+//
+// Parameter pointers come in the module tree's order (Appendix B of SURVEY.md):
+//   stem.w | per level: pre_bn{gamma,beta,rmean,rvar} pre.w [dn_bn{4} dn.w <deeper level> up_bn{4}
+//   up.w post_bn{4} post.w] | head_bn{4}
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+struct LevelMeta {
+  int64_t n;
+  const int32_t* nbr;
+  int64_t tstride;
+  const int32_t* parent;
+  const uint8_t* off;
+  const int32_t* child;
+};
+
+struct Bump {
+  char* base;
+  size_t off, cap;
+  bool ok;
+  float* f(int64_t n, int64_t c) {
+    size_t bytes = mm3d_align(sizeof(float) * (size_t)n * (size_t)c);
+    size_t o = off;
+    off += bytes;
+    if (off > cap) ok = false;
+    return base ? reinterpret_cast<float*>(base + o) : nullptr;
+  }
+};
+
+struct LevelBufs {
+  float *X, *A, *Y, *B, *E, *F, *J, *G, *R;
+  float *s_pre, *s_dn, *s_up, *s_post;  // BN save_mean | save_invstd ([2][C])
+};
+
+struct Net {
+  int L, m, cin, cin_k;  // cin_k = stem input channels as seen by the kernels (padded to 4 in TC modes)
+  int mode;
+  std::vector<LevelMeta> lv;
+  std::vector<LevelBufs> b;
+  float *V, *Vp, *Z, *s_head;
+  int64_t n_points;
+  int planes(int l) const { return m * (l + 1); }
+};
+
+// the same carving in forward, backward and the size query
+void carve(Net& net, Bump& bp) {
+  const int64_t n0 = net.lv[0].n;
+  net.V = bp.f(n0, net.cin);
+  net.Vp = net.cin_k != net.cin ? bp.f(n0, net.cin_k) : net.V;
+  net.b.assign(net.L, LevelBufs());
+  for (int l = 0; l < net.L; ++l) {
+    const int64_t n = net.lv[l].n;
+    const int p = net.planes(l);
+    LevelBufs& B = net.b[l];
+    B.X = bp.f(n, p);
+    B.A = bp.f(n, p);
+    B.Y = bp.f(n, p);
+    B.s_pre = bp.f(2, p);
+    if (l + 1 < net.L) {
+      const int q = net.planes(l + 1);
+      B.B = bp.f(n, p);
+      B.s_dn = bp.f(2, p);
+      B.E = bp.f(net.lv[l + 1].n, q);
+      B.s_up = bp.f(2, q);
+      B.F = bp.f(n, p);
+      B.J = bp.f(n, 2 * p);
+      B.G = bp.f(n, 2 * p);
+      B.s_post = bp.f(2, 2 * p);
+      B.R = bp.f(n, p);
+    } else {
+      B.R = B.Y;
+    }
+  }
+  net.Z = bp.f(n0, net.m);
+  net.s_head = bp.f(2, net.m);
+}
+
+__global__ void k_copy_cols(const float* __restrict__ src, int64_t n, int c_src, float* __restrict__ dst, int c_dst,
+                            int dst_col0, int ncols, int src_col0) {
+  // dst[r, dst_col0 + j] = src[r, src_col0 + j], j < ncols  (other dst columns untouched)
+  const int64_t total = n * ncols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ncols;
+    const int j = (int)(i - r * ncols);
+    dst[r * c_dst + dst_col0 + j] = __ldg(src + r * c_src + src_col0 + j);
+  }
+}
+
+__global__ void k_pad_cols(const float* __restrict__ src, int64_t n, int c_src, float* __restrict__ dst, int c_dst) {
+  // dst[r, j] = j < c_src ? src[r, j] : 0   (c_dst >= c_src: pad;  c_dst < c_src: slice)
+  const int64_t total = n * c_dst;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c_dst;
+    const int j = (int)(i - r * c_dst);
+    dst[i] = j < c_src ? __ldg(src + r * c_src + j) : 0.f;
+  }
+}
+
+__global__ void k_split_add(const float* __restrict__ dj, const float* __restrict__ add, int64_t n, int p,
+                            float* __restrict__ dy, float* __restrict__ df) {
+  // dy = dj[:, :p] + add ; df = dj[:, p:]
+  const int64_t total = n * p;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / p;
+    const int j = (int)(i - r * p);
+    dy[i] = __ldg(dj + r * 2 * p + j) + __ldg(add + i);
+    if (df) df[i] = __ldg(dj + r * 2 * p + p + j);
+  }
+}
+
+struct Ctx {
+  Net* net;
+  void* const* params;
+  void* const* grads;  // backward only
+  void* scratch;
+  size_t scratch_bytes;
+  cudaStream_t stream;
+  float eps, momentum;
+  int training;
+  int pi;  // running parameter index
+  int rc;
+};
+
+#define EX(call)                   \
+  do {                             \
+    if (c.rc == 0) c.rc = (call);  \
+  } while (0)
+
+const float* P(Ctx& c, int i) { return (const float*)c.params[i]; }
+float* Gp(Ctx& c, int i) { return (float*)c.grads[i]; }
+
+void bn_fwd(Ctx& c, int pidx, const float* x, float* y, int64_t n, int ch, float* save) {
+  EX(mm3d_bnrelu_fwd(x, y, n, ch, P(c, pidx), P(c, pidx + 1), (float*)c.params[pidx + 2], (float*)c.params[pidx + 3], save,
+                     save + ch, c.eps, c.momentum, 0.f, c.training, c.scratch, c.scratch_bytes, c.stream));
+}
+void bn_bwd(Ctx& c, int pidx, const float* x, const float* dy, float* dx, int64_t n, int ch, const float* save) {
+  EX(mm3d_bnrelu_bwd(x, dy, dx, n, ch, P(c, pidx), P(c, pidx + 1), save, save + ch, Gp(c, pidx), Gp(c, pidx + 1), 0.f,
+                     c.training, c.scratch, c.scratch_bytes, c.stream));
+}
+enum Kind { SMC, DOWN, UP };
+// forward of layer type `kind` whose FINE level is l
+void conv_fwd(Ctx& c, Kind kind, int l, const float* in, int c_in, float* out, int c_out, const float* w) {
+  const LevelMeta& f = c.net->lv[l];
+  if (kind == SMC)
+    EX(mm3d_conv_fwd(in, f.n, c_in, out, f.n, c_out, w, 27, f.nbr, f.tstride, nullptr, 0, c.net->mode, c.scratch,
+                     c.scratch_bytes, c.stream));
+  else if (kind == DOWN)
+    EX(mm3d_conv_fwd(in, f.n, c_in, out, c.net->lv[l + 1].n, c_out, w, 8, f.child, f.tstride, nullptr, 0, c.net->mode,
+                     c.scratch, c.scratch_bytes, c.stream));
+  else
+    EX(mm3d_conv_fwd(in, c.net->lv[l + 1].n, c_in, out, f.n, c_out, w, 8, f.parent, 0, f.off, 0, c.net->mode, c.scratch,
+                     c.scratch_bytes, c.stream));
+}
+// dgrad (d_in from d_out) and wgrad of the same layer; c_in / c_out are the FORWARD layer's
+void conv_bwd(Ctx& c, Kind kind, int l, const float* in, int c_in, const float* d_out, int c_out, const float* w,
+              float* d_in, float* d_w) {
+  const LevelMeta& f = c.net->lv[l];
+  const int64_t nc = l + 1 < c.net->L ? c.net->lv[l + 1].n : 0;
+  const int md = c.net->mode;
+  if (kind == SMC) {
+    if (d_in)
+      EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, f.n, c_in, w, 27, f.nbr, f.tstride, nullptr,
+                       MM3D_CONV_TRANSPOSE_W | MM3D_CONV_MIRROR_K, md, c.scratch, c.scratch_bytes, c.stream));
+    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, f.n, c_out, d_w, 27, f.nbr, f.tstride, nullptr, 0, md, c.scratch,
+                       c.scratch_bytes, c.stream));
+  } else if (kind == DOWN) {  // in: fine rows, d_out: coarse rows
+    EX(mm3d_conv_fwd(d_out, nc, c_out, d_in, f.n, c_in, w, 8, f.parent, 0, f.off, MM3D_CONV_TRANSPOSE_W, md, c.scratch,
+                     c.scratch_bytes, c.stream));
+    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, nc, c_out, d_w, 8, f.child, f.tstride, nullptr, 0, md, c.scratch,
+                       c.scratch_bytes, c.stream));
+  } else {  // UP: in: coarse rows, d_out: fine rows
+    EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, nc, c_in, w, 8, f.child, f.tstride, nullptr, MM3D_CONV_TRANSPOSE_W, md,
+                     c.scratch, c.scratch_bytes, c.stream));
+    EX(mm3d_conv_wgrad(in, nc, c_in, d_out, f.n, c_out, d_w, 8, f.parent, 0, f.off, 0, md, c.scratch, c.scratch_bytes,
+                       c.stream));
+  }
+}
+
+void launch_copy_cols(Ctx& c, const float* src, int64_t n, int c_src, float* dst, int c_dst, int col0, int ncols) {
+  if (n == 0 || c.rc) return;
+  k_copy_cols<<<mm3d_grid(n * ncols, 256), 256, 0, c.stream>>>(src, n, c_src, dst, c_dst, col0, ncols, 0);
+  mm3d_count_launches(1);
+}
+void launch_pad_cols(Ctx& c, const float* src, int64_t n, int c_src, float* dst, int c_dst) {
+  if (n == 0 || c.rc) return;
+  k_pad_cols<<<mm3d_grid(n * c_dst, 256), 256, 0, c.stream>>>(src, n, c_src, dst, c_dst);
+  mm3d_count_launches(1);
+}
+
+// parameter index bookkeeping: number of pointer slots a level (and everything below it) uses
+int level_slots(int l, int L) { return l + 1 < L ? 5 + 5 + level_slots(l + 1, L) + 5 + 5 : 5; }
+
+void level_fwd(Ctx& c, int l, int pbase) {
+  Net& net = *c.net;
+  LevelBufs& B = net.b[l];
+  const int64_t n = net.lv[l].n;
+  const int p = net.planes(l);
+  bn_fwd(c, pbase, B.X, B.A, n, p, B.s_pre);
+  conv_fwd(c, SMC, l, B.A, p, B.Y, p, P(c, pbase + 4));
+  if (l + 1 < net.L) {
+    const int q = net.planes(l + 1);
+    const int dn = pbase + 5, deeper = pbase + 10, up = deeper + level_slots(l + 1, net.L), post = up + 5;
+    bn_fwd(c, dn, B.Y, B.B, n, p, B.s_dn);
+    conv_fwd(c, DOWN, l, B.B, p, net.b[l + 1].X, q, P(c, dn + 4));
+    level_fwd(c, l + 1, deeper);
+    bn_fwd(c, up, net.b[l + 1].R, B.E, net.lv[l + 1].n, q, B.s_up);
+    conv_fwd(c, UP, l, B.E, q, B.F, p, P(c, up + 4));
+    launch_copy_cols(c, B.Y, n, p, B.J, 2 * p, 0, p);
+    launch_copy_cols(c, B.F, n, p, B.J, 2 * p, p, p);
+    bn_fwd(c, post, B.J, B.G, n, 2 * p, B.s_post);
+    conv_fwd(c, SMC, l, B.G, 2 * p, B.R, p, P(c, post + 4));
+  }
+}
+
+// d_R: gradient w.r.t. the level's output R_l; returns (in d_X) the gradient w.r.t. X_l.
+// Gradient temporaries come from the backward bump allocator `g`.
+void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) {
+  Net& net = *c.net;
+  LevelBufs& B = net.b[l];
+  const int64_t n = net.lv[l].n;
+  const int p = net.planes(l);
+  const float* d_Y = d_R;
+  const size_t mark = g.off;
+  if (l + 1 < net.L) {
+    const int q = net.planes(l + 1);
+    const int64_t nc = net.lv[l + 1].n;
+    const int dn = pbase + 5, deeper = pbase + 10, up = deeper + level_slots(l + 1, net.L), post = up + 5;
+    float* d_G = g.f(n, 2 * p);
+    conv_bwd(c, SMC, l, B.G, 2 * p, d_R, p, P(c, post + 4), d_G, Gp(c, post + 4));
+    float* d_J = g.f(n, 2 * p);
+    bn_bwd(c, post, B.J, d_G, d_J, n, 2 * p, B.s_post);
+    float* d_F = g.f(n, p);
+    float* d_Yskip = g.f(n, p);
+    // d_F = d_J[:, p:]; the skip half is combined with the branch gradient further down
+    if (n && !c.rc) {
+      k_copy_cols<<<mm3d_grid(n * p, 256), 256, 0, c.stream>>>(d_J, n, 2 * p, d_F, p, 0, p, p);
+      mm3d_count_launches(1);
+    }
+    float* d_E = g.f(nc, q);
+    conv_bwd(c, UP, l, B.E, q, d_F, p, P(c, up + 4), d_E, Gp(c, up + 4));
+    float* d_Rn = g.f(nc, q);
+    bn_bwd(c, up, net.b[l + 1].R, d_E, d_Rn, nc, q, B.s_up);
+    float* d_Xn = g.f(nc, q);
+    level_bwd(c, g, l + 1, deeper, d_Rn, d_Xn);
+    float* d_B = g.f(n, p);
+    conv_bwd(c, DOWN, l, B.B, p, d_Xn, q, P(c, dn + 4), d_B, Gp(c, dn + 4));
+    float* d_Ybr = g.f(n, p);
+    bn_bwd(c, dn, B.Y, d_B, d_Ybr, n, p, B.s_dn);
+    // d_Y = d_J[:, :p] + d_Ybr
+    if (n && !c.rc) {
+      k_split_add<<<mm3d_grid(n * p, 256), 256, 0, c.stream>>>(d_J, d_Ybr, n, p, d_Yskip, nullptr);
+      mm3d_count_launches(1);
+    }
+    d_Y = d_Yskip;
+  }
+  float* d_A = g.f(n, p);
+  conv_bwd(c, SMC, l, B.A, p, d_Y, p, P(c, pbase + 4), d_A, Gp(c, pbase + 4));
+  bn_bwd(c, pbase, B.X, d_A, d_X, n, p, B.s_pre);
+  g.off = mark;  // temporaries of this level are dead once d_X is written (d_X belongs to the caller)
+}
+
+int fill_net(Net& net, int in_channels, int m, int num_planes, int mode, const int64_t* level_desc, int64_t n_points) {
+  MM3D_REQUIRE(num_planes >= 1 && num_planes <= 16 && m > 0 && in_channels > 0, MM3D_ERR_INVALID, "bad network shape");
+  net.L = num_planes; net.m = m; net.cin = in_channels; net.mode = mode; net.n_points = n_points;
+  net.cin_k = (mode != MM3D_MODE_FP32 && (in_channels & 3)) ? (in_channels + 3) / 4 * 4 : in_channels;
+  net.lv.resize(num_planes);
+  for (int l = 0; l < num_planes; ++l) {
+    const int64_t* d = level_desc + 6 * l;
+    net.lv[l] = LevelMeta{d[0], (const int32_t*)d[1], d[2], (const int32_t*)d[3], (const uint8_t*)d[4], (const int32_t*)d[5]};
+  }
+  return MM3D_OK;
+}
+
+size_t bwd_temp_bytes(const Net& net) {
+  // upper bound of the live gradient temporaries along the recursion
+  size_t total = 0;
+  for (int l = 0; l < net.L; ++l) {
+    const size_t n = (size_t)net.lv[l].n, p = (size_t)net.planes(l);
+    size_t rows = 0;
+    if (l + 1 < net.L) {
+      const size_t nc = (size_t)net.lv[l + 1].n, q = (size_t)net.planes(l + 1);
+      rows = n * (2 * p + 2 * p + p + p + p + p) + nc * (3 * q);
+    }
+    rows += n * p;
+    total += mm3d_align(sizeof(float) * rows) + 16 * 256;
+  }
+  const size_t n0 = (size_t)net.lv[0].n;
+  total += mm3d_align(4 * n0 * (size_t)net.m) * 3 + mm3d_align(4 * n0 * (size_t)(net.cin + net.cin_k)) * 2 + 8 * 256;
+  total += mm3d_align(4 * (size_t)27 * net.cin_k * net.m) * 2;
+  return total;
+}
+
+}  // namespace
+
+extern "C" {
+
+// level_desc: 6 int64 per level = {n rows, nbr table ptr, table stride, parent ptr, off ptr, child ptr}
+MM3D_API int64_t mm3d_unet_num_params(int num_planes) { return 1 + level_slots(0, num_planes) + 4; }
+
+MM3D_API size_t mm3d_unet_act_bytes(int in_channels, int m, int num_planes, int mode, const int64_t* level_desc,
+                                    int64_t n_points) {
+  Net net;
+  if (fill_net(net, in_channels, m, num_planes, mode, level_desc, n_points)) return 0;
+  Bump bp{nullptr, 0, ~(size_t)0, true};
+  carve(net, bp);
+  return bp.off + 256;
+}
+
+MM3D_API size_t mm3d_unet_bwd_bytes(int in_channels, int m, int num_planes, int mode, const int64_t* level_desc,
+                                    int64_t n_points) {
+  Net net;
+  if (fill_net(net, in_channels, m, num_planes, mode, level_desc, n_points)) return 0;
+  return bwd_temp_bytes(net);
+}
+
+MM3D_API size_t mm3d_unet_scratch_bytes(int in_channels, int m, int num_planes, int mode) {
+  size_t best = mm3d_bnrelu_workspace_bytes(2 * m * num_planes);
+  const int cin_k = (in_channels + 3) / 4 * 4;
+  size_t s = mm3d_conv_workspace_bytes(0, 0, cin_k, m, 27, mode);
+  if (s > best) best = s;
+  for (int l = 0; l < num_planes; ++l) {
+    const int p = m * (l + 1);
+    s = mm3d_conv_workspace_bytes(0, 0, 2 * p, p, 27, mode);
+    if (s > best) best = s;
+    s = mm3d_conv_workspace_bytes(0, 0, p + m, p, 8, mode);
+    if (s > best) best = s;
+  }
+  return best + mm3d_align(4 * (size_t)27 * cin_k * m) + 256;
+}
+
+MM3D_API int mm3d_unet_forward(int in_channels, int m, int num_planes, int mode, int training, float eps, float momentum,
+                               const int64_t* level_desc, int64_t n_points, const int32_t* p2v, const int32_t* npts,
+                               const float* feats, float* out, void* const* params, void* act, size_t act_bytes,
+                               void* scratch, size_t scratch_bytes, mm3d_stream_t stream_) {
+  Net net;
+  int rc = fill_net(net, in_channels, m, num_planes, mode, level_desc, n_points);
+  if (rc) return rc;
+  Bump bp{(char*)act, 0, act_bytes, true};
+  carve(net, bp);
+  MM3D_REQUIRE(bp.ok, MM3D_ERR_WORKSPACE, "activation workspace too small: need %zu have %zu", bp.off, act_bytes);
+  Ctx c{&net, params, nullptr, scratch, scratch_bytes, (cudaStream_t)stream_, eps, momentum, training, 0, 0};
+  const int64_t n0 = net.lv[0].n;
+  EX(mm3d_input_fwd(feats, p2v, npts, n_points, n0, in_channels, 4, net.V, c.stream));
+  const float* w_stem = P(c, 0);
+  if (net.cin_k != net.cin) {
+    // tensor-core modes gather whole 16-byte pieces: pad features and stem weight with zero channels
+    launch_pad_cols(c, net.V, n0, net.cin, net.Vp, net.cin_k);
+    float* wp = (float*)((char*)scratch + scratch_bytes - mm3d_align(4 * (size_t)27 * net.cin_k * m));
+    launch_pad_cols(c, w_stem, 27, net.cin * m, wp, net.cin_k * m);
+    w_stem = wp;
+  }
+  conv_fwd(c, SMC, 0, net.Vp, net.cin_k, net.b[0].X, m, w_stem);
+  level_fwd(c, 0, 1);
+  const int head = 1 + level_slots(0, net.L);
+  bn_fwd(c, head, net.b[0].R, net.Z, n0, m, net.s_head);
+  EX(mm3d_output_fwd(net.Z, p2v, n_points, m, out, c.stream));
+  return c.rc;
+}
+
+// grads: same slot order as params (running-stat slots ignored); d_feats may be NULL.
+MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode, int training,
+                                const int64_t* level_desc, int64_t n_points, const int32_t* p2v, const int32_t* npts,
+                                const float* d_out, float* d_feats, void* const* params, void* const* grads,
+                                void* act, size_t act_bytes, void* tmp, size_t tmp_bytes, void* scratch,
+                                size_t scratch_bytes, mm3d_stream_t stream_) {
+  Net net;
+  int rc = fill_net(net, in_channels, m, num_planes, mode, level_desc, n_points);
+  if (rc) return rc;
+  Bump bp{(char*)act, 0, act_bytes, true};
+  carve(net, bp);
+  MM3D_REQUIRE(bp.ok, MM3D_ERR_WORKSPACE, "activation workspace too small");
+  MM3D_REQUIRE(tmp_bytes >= bwd_temp_bytes(net), MM3D_ERR_WORKSPACE, "backward workspace too small");
+  Ctx c{&net, params, grads, scratch, scratch_bytes, (cudaStream_t)stream_, 0.f, 0.f, training, 0, 0};
+  Bump g{(char*)tmp, 0, tmp_bytes, true};
+  const int64_t n0 = net.lv[0].n;
+  const int head = 1 + level_slots(0, net.L);
+  float* d_Z = g.f(n0, m);
+  EX(mm3d_output_bwd(d_out, p2v, n_points, n0, m, d_Z, c.stream));
+  float* d_R0 = g.f(n0, m);
+  bn_bwd(c, head, net.b[0].R, d_Z, d_R0, n0, m, net.s_head);
+  float* d_X0 = g.f(n0, m);
+  level_bwd(c, g, 0, 1, d_R0, d_X0);
+  // stem
+  const float* w_stem = P(c, 0);
+  float* d_w = Gp(c, 0);
+  float* d_Vp = d_feats ? g.f(n0, net.cin_k) : nullptr;
+  if (net.cin_k != net.cin) {
+    float* wp = (float*)((char*)scratch + scratch_bytes - mm3d_align(4 * (size_t)27 * net.cin_k * m));
+    launch_pad_cols(c, w_stem, 27, net.cin * m, wp, net.cin_k * m);
+    float* d_wp = g.f(27, (int64_t)net.cin_k * m);
+    conv_bwd(c, SMC, 0, net.Vp, net.cin_k, d_X0, m, wp, d_Vp, d_wp);
+    launch_pad_cols(c, d_wp, 27, net.cin_k * m, d_w, net.cin * m);  // slice the real channels back out
+    if (d_feats) {
+      float* d_V = g.f(n0, net.cin);
+      launch_pad_cols(c, d_Vp, n0, net.cin_k, d_V, net.cin);
+      EX(mm3d_input_bwd(d_V, p2v, npts, n_points, net.cin, 4, d_feats, c.stream));
+    }
+  } else {
+    conv_bwd(c, SMC, 0, net.V, net.cin, d_X0, m, w_stem, d_Vp, d_w);
+    if (d_feats) EX(mm3d_input_bwd(d_Vp, p2v, npts, n_points, net.cin, 4, d_feats, c.stream));
+  }
+  MM3D_REQUIRE(g.ok, MM3D_ERR_WORKSPACE, "backward workspace overflow");
+  return c.rc;
+}
+
+}  // extern "C"

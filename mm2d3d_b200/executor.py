@@ -1,0 +1,142 @@
+"""Fused execution of ``UNetSCN``: the whole forward (and the whole backward) is ONE call into
+``libmm3d`` (``csrc/unet_exec.cu``) instead of ~110 Python autograd nodes.
+
+``UNetSCN.forward`` uses this path when the network has the reference's shape (VGG blocks,
+``block_reps == 1``, InputLayer mode 4 -- ``config/config.yaml:22-28``); any other configuration
+runs module by module.  Results are the same kernels in the same order, so parity is unchanged.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from . import functional as F
+from ._lib import check, lib
+from .metadata import Metadata
+
+
+def collect_slots(net):
+    """Parameters and BN buffers of ``net`` in the executor's slot order (module-tree order):
+    stem.w | per level: pre_bn{w,b,rm,rv} pre.w [dn_bn dn.w <deeper> up_bn up.w post_bn post.w] | head_bn."""
+
+    def bn(mod):
+        return [mod.weight, mod.bias, mod.running_mean, mod.running_var]
+
+    def level(seq):
+        mods = list(seq._modules.values())
+        out = bn(mods[0][0]) + [mods[0][1].weight]
+        if len(mods) > 1:
+            branch = list(mods[1][1]._modules.values())  # ConcatTable[Identity, Sequential[BN, Conv, U, BN, Deconv]]
+            out += bn(branch[0]) + [branch[1].weight]
+            out += level(branch[2])
+            out += bn(branch[3]) + [branch[4].weight]
+            out += bn(mods[3][0]) + [mods[3][1].weight]
+        return out
+
+    return [net.layer2.weight] + level(net.layer3) + bn(net.layer4)
+
+
+def fusable(net) -> bool:
+    from . import scn
+    if not isinstance(net.layer1, scn.InputLayer) or net.layer1.mode != 4:
+        return False
+    if getattr(net, "_block_reps", 1) != 1 or getattr(net, "_residual", False):
+        return False
+    for mod in net.modules():
+        if isinstance(mod, scn._ConvBase) and (mod.mode is not None or hasattr(mod, "bias")):
+            return False
+        if isinstance(mod, scn.BatchNormLeakyReLU) and mod.leakiness != 0:
+            return False
+    return True
+
+
+def _level_desc(meta: Metadata, num_planes: int, spatial0: int):
+    desc = (C.c_int64 * (6 * num_planes))()
+    s = spatial0
+    for l in range(num_planes):
+        lv = meta.nbr(s)
+        desc[6 * l + 0] = lv.n
+        desc[6 * l + 1] = lv.ptr(lv.o_nbr)
+        desc[6 * l + 2] = lv.tstride
+        if l + 1 < num_planes:
+            fine, _ = meta.down(s)
+            desc[6 * l + 3] = fine.ptr(fine.o_parent)
+            desc[6 * l + 4] = fine.ptr(fine.o_off)
+            desc[6 * l + 5] = fine.ptr(fine.o_child)
+        s //= 2
+    return desc
+
+
+class UNetSCNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, meta, cfg, *slots):
+        in_ch, m, L, mode, training, eps, momentum, spatial0 = cfg
+        feats = feats.float().contiguous()
+        dev = feats.device
+        n_points = meta.n_points
+        desc = _level_desc(meta, L, spatial0)
+        with torch.cuda.device(dev):
+            act_bytes = lib.mm3d_unet_act_bytes(in_ch, m, L, mode, desc, n_points)
+            act = torch.empty(act_bytes, dtype=torch.uint8, device=dev)
+            scr = F.scratch(lib.mm3d_unet_scratch_bytes(in_ch, m, L, mode), dev)
+            out = torch.empty(n_points, m, dtype=torch.float32, device=dev)
+            params = (C.c_void_p * len(slots))(*[t.data_ptr() for t in slots])
+            check(lib.mm3d_unet_forward(in_ch, m, L, mode, int(training), eps, momentum, desc, n_points, meta.p2v_ptr,
+                                        meta.npts_ptr, feats.data_ptr(), out.data_ptr(), params, act.data_ptr(), act_bytes,
+                                        scr.data_ptr(), scr.numel(), _lib.stream_ptr()), "mm3d_unet_forward")
+        ctx.meta, ctx.cfg, ctx.desc, ctx.act, ctx.slots = meta, cfg, desc, act, slots
+        ctx.feats_shape = feats.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        in_ch, m, L, mode, training, eps, momentum, spatial0 = ctx.cfg
+        meta, slots, desc, act = ctx.meta, ctx.slots, ctx.desc, ctx.act
+        d_out = d_out.float().contiguous()
+        dev = d_out.device
+        n_points = meta.n_points
+        need_feats = ctx.needs_input_grad[0]
+        with torch.cuda.device(dev):
+            # one flat buffer for every parameter gradient; the returned grads are views into it
+            numels = [t.numel() if t.requires_grad else 0 for t in slots]
+            flat = torch.empty(sum(numels), dtype=torch.float32, device=dev)
+            base = flat.data_ptr()
+            gptrs, grads, off = [], [], 0
+            for t, k in zip(slots, numels):
+                if k:
+                    gptrs.append(base + 4 * off)
+                    grads.append(flat[off:off + k].view_as(t))
+                    off += k
+                else:
+                    gptrs.append(None)
+                    grads.append(None)
+            d_feats = torch.empty(ctx.feats_shape, dtype=torch.float32, device=dev) if need_feats else None
+            if need_feats and ctx.feats_shape[0] > n_points:
+                d_feats.zero_()
+            tmp_bytes = lib.mm3d_unet_bwd_bytes(in_ch, m, L, mode, desc, n_points)
+            tmp = torch.empty(tmp_bytes, dtype=torch.uint8, device=dev)
+            scr = F.scratch(lib.mm3d_unet_scratch_bytes(in_ch, m, L, mode), dev)
+            params = (C.c_void_p * len(slots))(*[t.data_ptr() for t in slots])
+            gp = (C.c_void_p * len(slots))(*gptrs)
+            check(lib.mm3d_unet_backward(in_ch, m, L, mode, int(training), desc, n_points, meta.p2v_ptr, meta.npts_ptr,
+                                         d_out.data_ptr(), d_feats.data_ptr() if need_feats else None, params, gp,
+                                         act.data_ptr(), act.numel(), tmp.data_ptr(), tmp_bytes, scr.data_ptr(),
+                                         scr.numel(), _lib.stream_ptr()), "mm3d_unet_backward")
+        return (d_feats, None, None, *grads)
+
+
+def run(net, coords, feats):
+    if not feats.is_cuda:
+        raise RuntimeError("UNetSCN: features must be a CUDA tensor -- mm2d3d_b200 has no CPU path")
+    if coords.device != feats.device:
+        coords = coords.to(feats.device, non_blocking=True)
+    spatial0 = int(net.layer1.spatial_size[0])
+    L = net._num_planes
+    meta = Metadata(coords, spatial0, L)
+    bn0 = net.layer4
+    cfg = (net.in_channels, net.out_channels, L, _lib.MODES[F.DEFAULT_MODE], bool(net.training), float(bn0.eps),
+           float(bn0.momentum), spatial0)
+    with torch.autocast("cuda", enabled=False):
+        return UNetSCNFn.apply(feats, meta, cfg, *collect_slots(net))

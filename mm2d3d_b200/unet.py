@@ -80,6 +80,9 @@ class UNetSCN(nn.Module):
         if backend is None:
             from . import scn as backend  # CUDA implementation; raises if the library is missing
         scn = backend
+        self._native = scn.__name__ == "mm2d3d_b200.scn"
+        self._num_planes, self._block_reps, self._residual = num_planes, block_reps, residual_blocks
+        self.fused = True  # set False to run module by module (same kernels, ~110 autograd nodes)
         self.in_channels = in_channels
         self.out_channels = m
         self.full_scale = full_scale
@@ -94,6 +97,11 @@ class UNetSCN(nn.Module):
         self.layer5 = scn.OutputLayer(DIMENSION)
 
     def forward(self, x):
+        if self.fused and self._native:
+            from . import executor
+            if executor.fusable(self):
+                # whole forward (and backward) as one native call each: csrc/unet_exec.cu
+                return executor.run(self, x[0], x[1])
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4, self.layer5):
             x = layer(x)
         return x

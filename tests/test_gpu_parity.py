@@ -509,3 +509,42 @@ def test_tf32_matches_fp32_kernels_at_bench_size(kind, c_in, c_out):
     for a, b, what in zip(res["tf32"], res["fp32"], ("fwd", "dgrad", "wgrad")):
         assert rel_err(a, b) < 1e-2, (kind, c_in, c_out, what, rel_err(a, b))
     _no_device_error()
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_fused_executor_matches_module_path(mode):
+    """UNetSCN.forward defaults to the native whole-network executor (csrc/unet_exec.cu); it issues
+    the same kernels as the module-by-module path, so outputs, every gradient and the BN running
+    statistics must agree to FP32 round-off (BN / wgrad reductions use atomics)."""
+    import copy
+
+    import mm2d3d_b200.scn as scn
+    from mm2d3d_b200.unet import UNetSCN
+    torch.manual_seed(9)
+    locs, feats = synth.make_batch("nuscenes", batch=2, seed0=5)
+    coords, feats = torch.from_numpy(locs).to(DEV), torch.from_numpy(feats).to(DEV)
+    net_a = UNetSCN(in_channels=3).to(DEV)
+    net_b = copy.deepcopy(net_a)
+    net_b.fused = False
+    g = torch.randn(locs.shape[0], 16, device=DEV)
+    scn.set_conv_mode(mode)
+    try:
+        res = []
+        for net in (net_a, net_b):
+            x = feats.clone().requires_grad_(True)
+            out = net([coords, x])
+            grads = torch.autograd.grad(out, [x] + list(net.parameters()), g)
+            res.append((out, grads, [b.clone() for b in net.buffers()]))
+    finally:
+        scn.set_conv_mode("fp32")
+    _no_device_error()
+    tol = 1e-5 if mode == "fp32" else 1e-3
+    assert rel_err(res[0][0], res[1][0]) < tol
+    for a, b in zip(res[0][1], res[1][1]):
+        assert rel_l2(a, b) < 20 * tol
+    for a, b in zip(res[0][2], res[1][2]):
+        assert rel_err(a, b) < tol
+    # eval mode through the executor
+    net_a.eval(); net_b.eval()
+    with torch.no_grad():
+        assert rel_err(net_a([coords, feats]), net_b([coords, feats])) < tol
