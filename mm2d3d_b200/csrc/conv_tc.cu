@@ -11,25 +11,19 @@
 // stored once: deterministic.  Packing offsets back to back along K means a 16-channel layer needs
 // 14 K-blocks instead of 27 and no layer pays per-offset padding.
 //
-// Warp roles (448 threads):   warps 0-7   gather producers (cp.async, 8 lanes per 128-byte row piece)
-//                             warps 8-11  epilogue (TMEM lanes 32(w-8).. -> registers -> global)
-//                             warp  12    MMA issuer (one lane) + TMEM allocator
-//                             warp  13    weight loader (cp.async.bulk of the weight image)
-// Pipelines (mbarriers):      A ring   a_full[S] (256 cp.async arrivals) / a_empty[S] (tcgen05.commit)
+// Warp roles ((S+6) warps):   warps 0..S-1    gather producers, warp w OWNS ring stage w (tc_gather.cuh)
+//                             warps S..S+3    epilogue (TMEM lanes 32(w&3).. -> registers -> global)
+//                             warp  S+4       MMA issuer (one lane) + TMEM allocator
+//                             warp  S+5       weight loader (cp.async.bulk of the weight image)
+// Pipelines (mbarriers):      A ring   a_full[S] (32 cp.async arrivals)   / a_empty[S] (tcgen05.commit)
 //                             B ring   b_full[SB] (expect_tx + bulk copy) / b_empty[SB] (tcgen05.commit)
 //                             accum    acc_full[2] (tcgen05.commit)       / acc_empty[2] (128 arrivals)
 // The accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the MMAs of i+1.
 //
-// The producer loop is the critical instruction stream (one 16-byte slot decision per lane and
-// pass), so it is branch-free, has the ring stage as a compile-time index (unrolled by S), advances
-// (offset, channel-chunk) incrementally instead of dividing, and fetches the rule-table entries of
-// the NEXT K-block into registers while the current one is being copied (no table staging in
-// shared memory: the smem saved is what lets 2-3 CTAs share an SM and overlap their streams).
-//
-// Absent neighbours cost NO shared-memory traffic: stages are zeroed once and a thread re-zeroes
-// (cp.async with src-size 0) only a slot it filled the previous time the stage was used -- the
-// 3^3 tables are 10-30 % dense, so the fill stays proportional to the real pairs.
-#include "tc_common.cuh"
+// Absent neighbours cost neither instructions nor shared-memory traffic beyond one coalesced table
+// read per 32 rows: stages are zeroed once, the producer compacts the rows that need an action and
+// re-zeroes (cp.async with src-size 0) only slots that held data the last time the stage was used.
+#include "tc_gather.cuh"
 
 namespace {
 
@@ -38,25 +32,17 @@ using namespace tc;
 constexpr int kTileM = 128;
 constexpr int kKBlock = 32;                 // tf32 elements per 128-byte row of a K-block
 constexpr int kStageBytes = kTileM * 128;   // one A stage = one K-block of 128 rows = 16 KB
-constexpr int kProducers = 256;             // 8 warps: 32 rows x 8 chunk lanes per pass, 4 passes
 constexpr int kEpilogue = 128;
-constexpr int kThreads = kProducers + kEpilogue + 64;
 constexpr int kMaxStages = 6;
 constexpr int kMaxBStages = 4;
 constexpr int kMaxK = 27;
 
 struct TcParams {
-  const float* in;
+  GatherArgs ga;
   float* out;
   const float* wimg;  // [kbt][n_pad][32] tf32, rows 128-byte swizzled
-  const int32_t* tbl;
-  int64_t tbl_stride;
-  const uint8_t* onehot_off;
-  int n_out, c_in, c_out, K;
-  int cq;         // 16-byte chunks per input row (c_in / 4)
-  int nq;         // K * cq   chunks of the virtual K
-  int kbt;        // K-blocks per tile = ceil(nq / 8)
-  int d8, m8;     // 8 / cq and 8 % cq: how (offset, chunk) advance from one K-block to the next
+  int c_out;
+  int kbt;            // K-blocks per tile = ceil(K * cq / 8)
   int n_pad, num_tiles, b_stages, tmem_cols;
   int* err;
 };
@@ -86,10 +72,11 @@ __global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ 
 }
 
 template <int S, bool ONEHOT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__((S + 6) * 32, 1)
 k_conv_tc(const TcParams p) {
+  constexpr int kThreads = (S + 6) * 32;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A stages][B stages][barriers][tmem ptr][abort]
+  // carve: [A stages][B stages][producer lists][barriers][tmem ptr][abort]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const int SB = p.b_stages;
@@ -97,7 +84,8 @@ k_conv_tc(const TcParams p) {
   const uint32_t b_stride = (b_bytes + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + (uint32_t)S * kStageBytes;
-  const uint32_t bar_base = b_base + (uint32_t)SB * b_stride;
+  const uint32_t l_base = b_base + (uint32_t)SB * b_stride;
+  const uint32_t bar_base = l_base + (uint32_t)S * kListBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar_base - smem_base));
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(kMaxStages + s); };
@@ -116,7 +104,7 @@ k_conv_tc(const TcParams p) {
     reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(a_full(s), kProducers);
+      mbar_init(a_full(s), 32);
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < SB; ++s) {
@@ -130,98 +118,39 @@ k_conv_tc(const TcParams p) {
     *abort_flag = 0;
     fence_barrier_init();
   }
-  if (warp == 12) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
+  if (warp == S + 4) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
   fence_proxy_async();  // the zero fill must be visible to the tensor core's (async-proxy) reads
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 8) {
-    // =================================================================== gather producers
-    const int g = threadIdx.x >> 3;  // row within a 32-row pass
-    const int c = threadIdx.x & 7;   // 16-byte chunk within the 128-byte K-block row
-    // this thread's slot in a stage: row g (+32 per pass), swizzled chunk
-    const uint32_t slot0 = a_base + (uint32_t)g * 128u + (uint32_t)((c ^ (g & 7)) << 4);
-    const int k0 = c / p.cq, cc0 = c - k0 * p.cq;  // (offset, chunk) of virtual-K chunk q = c
-    uint32_t filled[S];                             // bit ps: the slot of pass ps holds data, not zeros
-#pragma unroll
-    for (int s = 0; s < S; ++s) filled[s] = 0;
-
-    // rule-table entries of one K-block for this lane's 4 rows (-1 = absent / out of range)
-    int par_c[4], off_c[4], par_n[4], off_n[4];  // ONEHOT: parent / offset of the current and next tile
-    auto load_onehot = [&](int tile, int (&par)[4], int (&off)[4]) {
-#pragma unroll
-      for (int ps = 0; ps < 4; ++ps) {
-        const int64_t row = (int64_t)tile * kTileM + ps * 32 + g;
-        const bool ok = tile < p.num_tiles && row < p.n_out;
-        par[ps] = ok ? __ldg(p.tbl + row) : -1;
-        off[ps] = ok ? (int)__ldg(p.onehot_off + row) : -1;
-      }
-    };
-    auto entries = [&](int tile, int kb, int k, const int (&par)[4], const int (&off)[4], int (&nb)[4]) {
-      const bool q_ok = tile < p.num_tiles && kb * 8 + c < p.nq;
-#pragma unroll
-      for (int ps = 0; ps < 4; ++ps) {
-        if (ONEHOT) {
-          nb[ps] = (q_ok && off[ps] == k) ? par[ps] : -1;
-        } else {
-          const int64_t row = (int64_t)tile * kTileM + ps * 32 + g;
-          nb[ps] = (q_ok && row < p.n_out) ? __ldg(p.tbl + (int64_t)k * p.tbl_stride + row) : -1;
-        }
-      }
-    };
-
-    int tile = blockIdx.x, kb = 0, k = k0, cc = cc0;
-    uint32_t round = 0;
-    int nb[4];
-    if (ONEHOT) {
-      load_onehot(tile, par_c, off_c);
-      load_onehot(tile + gridDim.x, par_n, off_n);
-    }
-    entries(tile, kb, k, par_c, off_c, nb);
+  if (warp < S) {
+    // =================================================================== gather producer: owns stage `warp`
+    const uint32_t stage = a_base + (uint32_t)warp * kStageBytes;
+    const uint32_t list = l_base + (uint32_t)warp * kListBytes;
+    uint32_t filled = 0, round = 0;
+    int lt = 0, kb = warp;  // item = (lt-th tile of this CTA, K-block kb); this warp takes every S-th item
+    while (kb >= p.kbt) { kb -= p.kbt; ++lt; }
+    int tile = blockIdx.x + lt * gridDim.x;
+    int nbv[4 * kMaxSegs];
+    load_entries<ONEHOT>(p.ga, tile < p.num_tiles, (int64_t)tile * kTileM, kb, lane, nbv);
     while (tile < p.num_tiles) {
+      int n_kb = kb + S, n_lt = lt;
+      while (n_kb >= p.kbt) { n_kb -= p.kbt; ++n_lt; }
+      const int n_tile = blockIdx.x + n_lt * gridDim.x;
+      int nbn[4 * kMaxSegs];  // the next item's table entries are in flight while this one is copied
+      load_entries<ONEHOT>(p.ga, n_tile < p.num_tiles, (int64_t)n_tile * kTileM, n_kb, lane, nbn);
+      if (!mbar_wait(a_empty(warp), (round & 1u) ^ 1u, abort_flag)) goto done;
+      gather_kblock<false>(p.ga, stage, kb, lane, nbv, filled, list, a_full(warp));
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
-        if (tile >= p.num_tiles) break;
-        // coordinates of the next K-block, and its table entries (in flight while this one is copied)
-        int n_tile = tile, n_kb = kb + 1, n_k = k + p.d8, n_cc = cc + p.m8;
-        if (n_cc >= p.cq) { n_cc -= p.cq; ++n_k; }
-        const bool new_tile = n_kb == p.kbt;
-        if (new_tile) { n_kb = 0; n_tile += gridDim.x; n_k = k0; n_cc = cc0; }
-        int nb_next[4];
-        if (ONEHOT && new_tile) entries(n_tile, n_kb, n_k, par_n, off_n, nb_next);
-        else entries(n_tile, n_kb, n_k, par_c, off_c, nb_next);
-
-        if (!mbar_wait(a_empty(s), (round & 1u) ^ 1u, abort_flag)) goto done;
-        const uint32_t src_off = (uint32_t)cc * 4u;
-        const uint32_t f = filled[s];
-        uint32_t nf = 0;
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) {
-          const bool have = nb[ps] >= 0;
-          const float* src = have ? p.in + ((uint32_t)nb[ps] * (uint32_t)p.c_in + src_off) : p.in;
-          if (have || ((f >> ps) & 1u))
-            cp_async16(slot0 + (uint32_t)(s * kStageBytes + ps * 32 * 128), src, have ? 16u : 0u);
-          nf |= (have ? 1u : 0u) << ps;
-        }
-        filled[s] = nf;
-        cp_async_arrive(a_full(s));
-
-        if (ONEHOT && new_tile) {
-#pragma unroll
-          for (int ps = 0; ps < 4; ++ps) { par_c[ps] = par_n[ps]; off_c[ps] = off_n[ps]; }
-          load_onehot(n_tile + gridDim.x, par_n, off_n);
-        }
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) nb[ps] = nb_next[ps];
-        tile = n_tile; kb = n_kb; k = n_k; cc = n_cc;
-      }
+      for (int i = 0; i < 4 * kMaxSegs; ++i) nbv[i] = nbn[i];
+      kb = n_kb; lt = n_lt; tile = n_tile;
       ++round;
     }
-  } else if (warp < 12) {
+  } else if (warp < S + 4) {
     // =================================================================== epilogue
-    const int ew = warp - 8;
+    const int ew = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
     uint32_t tile_iter = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
       const int ab = (int)(tile_iter & 1u);
@@ -232,7 +161,7 @@ k_conv_tc(const TcParams p) {
       for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
         float acc[16];
         tmem_ld16(taddr + (uint32_t)c0, acc);
-        if (row < p.n_out) {
+        if (row < p.ga.n_out) {
           float* dst = p.out + row * p.c_out + c0;
           if ((p.c_out & 3) == 0) {
 #pragma unroll
@@ -248,7 +177,7 @@ k_conv_tc(const TcParams p) {
       tc_fence_before();
       mbar_arrive(acc_empty(ab));
     }
-  } else if (warp == 12) {
+  } else if (warp == S + 4) {
     // =================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(kTileM, p.n_pad);
@@ -265,7 +194,7 @@ k_conv_tc(const TcParams p) {
           if (!mbar_wait(b_full(bs), (it / (uint32_t)SB) & 1u, abort_flag)) { ok = false; break; }
           if (!mbar_wait(a_full(s), (it / (uint32_t)S) & 1u, abort_flag)) { ok = false; break; }
           tc_fence_after();
-          const int rem = p.nq * 4 - kb * kKBlock;  // virtual-K elements left
+          const int rem = p.ga.nq * 4 - kb * kKBlock;  // virtual-K elements left
           const int ksteps = rem >= kKBlock ? kKBlock / 8 : (rem + 7) >> 3;
           const uint32_t a_addr = a_base + (uint32_t)s * kStageBytes;
           const uint32_t b_addr = b_base + (uint32_t)bs * b_stride;
@@ -298,7 +227,7 @@ done:
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0 && *abort_flag && p.err) atomicExch(p.err, 1);
-  if (warp == 12) {
+  if (warp == S + 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -312,6 +241,7 @@ int pow2_cols(int n) {
 
 template <int S, bool ONEHOT>
 int launch_conv_tc(const TcParams& p, size_t smem, cudaStream_t stream) {
+  constexpr int kThreads = (S + 6) * 32;
   static int regs = 0;
   if (!regs) {
     MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc<S, ONEHOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -343,10 +273,11 @@ int launch_conv_tc(const TcParams& p, size_t smem, cudaStream_t stream) {
 static int tc_geometry(int c_in, int c_out, int K, int* kbt, int* n_pad) {
   *kbt = (K * (c_in / 4) + 7) / 8;
   *n_pad = (c_out + 15) / 16 * 16;
-  return (*n_pad <= 256 && (c_in % 4) == 0 && c_in >= 4 && K <= kMaxK) ? 0 : 1;
+  // input rows must be whole 16-byte chunks, at least 4 of them (at most 3 segments per K-block)
+  return (*n_pad <= 256 && (c_in % 4) == 0 && c_in >= 16 && K <= kMaxK) ? 0 : 1;
 }
 
-// 1 when the tcgen05 kernel handles this shape (input rows must be whole 16-byte chunks)
+// 1 when the tcgen05 kernel handles this shape
 int mm3d_conv_tc_supported(int c_in, int c_out, int K) {
   int kbt, n_pad;
   return tc_geometry(c_in, c_out, K, &kbt, &n_pad) == 0;
@@ -402,9 +333,8 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
   k_weight_image<<<mm3d_grid((int64_t)kbt * n_pad * kKBlock, 256), 256, 0, stream>>>(weight, wimg, K, c_in, c_out, kbt,
                                                                                  n_pad, tr ? 1 : 0, mir ? 1 : 0);
   TcParams p;
-  p.in = in; p.out = out; p.wimg = wimg; p.tbl = tbl; p.tbl_stride = tbl_stride; p.onehot_off = onehot_off;
-  p.n_out = (int)n_out; p.c_in = c_in; p.c_out = c_out; p.K = K;
-  p.cq = c_in / 4; p.nq = K * p.cq; p.kbt = kbt; p.d8 = 8 / p.cq; p.m8 = 8 % p.cq; p.n_pad = n_pad;
+  p.ga = GatherArgs{in, tbl, tbl_stride, onehot_off, (int)n_out, c_in, K, c_in / 4, K * (c_in / 4)};
+  p.out = out; p.wimg = wimg; p.c_out = c_out; p.kbt = kbt; p.n_pad = n_pad;
   p.num_tiles = (int)mm3d_cdiv(n_out, kTileM);
   p.tmem_cols = pow2_cols(2 * n_pad);
   p.err = mm3d_device_err_flag();
@@ -413,7 +343,7 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
   const bool wide = n_pad > 96;
   const int S = wide ? 6 : 4;
   p.b_stages = wide ? (n_pad > 128 ? 2 : 3) : 4;
-  const size_t smem = 1024 + (size_t)S * kStageBytes + (size_t)p.b_stages * b_stride +
+  const size_t smem = 1024 + (size_t)S * kStageBytes + (size_t)p.b_stages * b_stride + (size_t)S * kListBytes +
                       8 * (2 * kMaxStages + 2 * kMaxBStages + 4) + 64;
   int rc;
   if (wide) rc = onehot_off ? launch_conv_tc<6, true>(p, smem, stream) : launch_conv_tc<6, false>(p, smem, stream);

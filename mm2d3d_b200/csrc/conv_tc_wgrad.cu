@@ -14,9 +14,9 @@
 // serve as the MN-major B operand.  Grid = (tile splits) x (group splits): a CTA keeps its TMEM
 // accumulators for its whole tile range and adds them to dW once (atomics: tile_splits * |dW|).
 //
-// Warp roles and the gather producers are those of conv_tc.cu (8 producer warps, 4 epilogue warps,
-// 1 MMA issuer); there is no weight loader -- B is produced by the gather warps.
-#include "tc_common.cuh"
+// Warp roles (14 warps): 0-7 gather producers (warp w owns ring stage w, tc_gather.cuh), 8-11
+// epilogue (TMEM -> atomics), 12 MMA issuer + TMEM allocator, 13 dout-tile loader.
+#include "tc_gather.cuh"
 
 namespace {
 
@@ -24,21 +24,15 @@ using namespace tc;
 
 constexpr int kTileM = 128;
 constexpr int kStageBytes = kTileM * 128;
-constexpr int kProducers = 256;
-constexpr int kEpilogue = 128;
-constexpr int kThreads = kProducers + kEpilogue + 32;
 constexpr int kStages = 8;  // two groups of four K-blocks
+constexpr int kThreads = (kStages + 6) * 32;
 constexpr int kMaxK = 27;
 
 struct WgParams {
-  const float* in;
+  GatherArgs ga;
   const float* dout;
   float* dw;
-  const int32_t* tbl;
-  int64_t tbl_stride;
-  const uint8_t* onehot_off;
-  int n_out, c_in, c_out, K;
-  int cq, nq, d8, m8;     // as in conv_tc.cu
+  int c_out;
   int n_pad, nblk;        // padded N, 32-wide N blocks of the dout tile
   int num_tiles, tile_splits, groups_total, gpc;  // gpc = groups per CTA
   int g_bufs, tmem_cols;
@@ -54,7 +48,8 @@ k_wgrad_tc(const WgParams p) {
   const uint32_t a_base = smem_base;
   const uint32_t g_bytes = (uint32_t)p.nblk * kStageBytes;
   const uint32_t g_base = a_base + kStages * kStageBytes;
-  const uint32_t bar_base = g_base + (uint32_t)p.g_bufs * g_bytes;
+  const uint32_t l_base = g_base + (uint32_t)p.g_bufs * g_bytes;
+  const uint32_t bar_base = l_base + kStages * kListBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar_base - smem_base));
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(kStages + s); };
@@ -75,11 +70,11 @@ k_wgrad_tc(const WgParams p) {
     reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(a_full(s), kProducers);
+      mbar_init(a_full(s), 32);
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(g_full(s), kProducers);
+      mbar_init(g_full(s), 32);
       mbar_init(g_empty(s), 1);
     }
     mbar_init(acc_full, 1);
@@ -93,134 +88,53 @@ k_wgrad_tc(const WgParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 8) {
-    // =================================================================== gather producers
-    const int g = threadIdx.x >> 3, c = threadIdx.x & 7;
-    const uint32_t slot0 = a_base + (uint32_t)g * 128u + swz_base32(c, g);  // row g (+32 per pass)
-    // (offset, chunk) of this lane's virtual-K chunk in the CTA's first K-block
-    const int q0 = kb_lo * 8 + c;
-    const int k0 = q0 / p.cq, cc0 = q0 - k0 * p.cq;
-    uint32_t filled[kStages];
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) filled[s] = 0;
-
-    int par_c[4], off_c[4], par_n[4], off_n[4];
-    auto load_onehot = [&](int tile, int (&par)[4], int (&off)[4]) {
-#pragma unroll
-      for (int ps = 0; ps < 4; ++ps) {
-        const int64_t row = (int64_t)tile * kTileM + ps * 32 + g;
-        const bool ok = tile < p.num_tiles && row < p.n_out;
-        par[ps] = ok ? __ldg(p.tbl + row) : -1;
-        off[ps] = ok ? (int)__ldg(p.onehot_off + row) : -1;
-      }
-    };
-    auto entries = [&](int tile, int kbi, int k, const int (&par)[4], const int (&off)[4], int (&nb)[4]) {
-      const bool q_ok = tile < p.num_tiles && (kb_lo + kbi) * 8 + c < p.nq;
-#pragma unroll
-      for (int ps = 0; ps < 4; ++ps) {
-        if (ONEHOT) {
-          nb[ps] = (q_ok && off[ps] == k) ? par[ps] : -1;
-        } else {
-          const int64_t row = (int64_t)tile * kTileM + ps * 32 + g;
-          nb[ps] = (q_ok && row < p.n_out) ? __ldg(p.tbl + (int64_t)k * p.tbl_stride + row) : -1;
-        }
-      }
-    };
-    // copy of a dout tile into G buffer `buf` (row r = t/2, chunks t&1, +2, ...)
-    auto load_g = [&](int tile, int buf) {
-      const int r = threadIdx.x >> 1;
-      const int64_t row = (int64_t)tile * kTileM + r;
-      const bool ok = row < p.n_out;
-      const float* src = p.dout + (ok ? row : 0) * p.c_out;
-      const uint32_t dst = g_base + (uint32_t)buf * g_bytes + (uint32_t)r * 128u;
-      const int nch = p.c_out >> 2;
-      for (int ch = threadIdx.x & 1; ch < nch; ch += 2)
-        cp_async16(dst + (uint32_t)(ch >> 3) * kStageBytes + swz_base32(ch & 7, r), src + ch * 4,
-                   ok ? 16u : 0u);
-      cp_async_arrive(g_full(buf));
-    };
-
-    int tile = split, kbi = 0, k = k0, cc = cc0;
-    uint32_t round = 0, tile_iter = 0;
-    int nb[4];
-    if (ONEHOT) {
-      load_onehot(tile, par_c, off_c);
-      load_onehot(tile + p.tile_splits, par_n, off_n);
-    }
-    entries(tile, kbi, k, par_c, off_c, nb);
+  if (warp < kStages) {
+    // =================================================================== gather producer: owns stage `warp`
+    const uint32_t stage = a_base + (uint32_t)warp * kStageBytes;
+    const uint32_t list = l_base + (uint32_t)warp * kListBytes;
+    uint32_t filled = 0, round = 0;
+    int lt = 0, kbi = warp;  // item = (lt-th tile of this CTA, local K-block kbi); every 8th item is ours
+    while (kbi >= kb_n) { kbi -= kb_n; ++lt; }
+    int tile = split + lt * p.tile_splits;
+    int nbv[4 * kMaxSegs];
+    load_entries<ONEHOT>(p.ga, tile < p.num_tiles, (int64_t)tile * kTileM, kb_lo + kbi, lane, nbv);
     while (tile < p.num_tiles) {
+      int n_kbi = kbi + kStages, n_lt = lt;
+      while (n_kbi >= kb_n) { n_kbi -= kb_n; ++n_lt; }
+      const int n_tile = split + n_lt * p.tile_splits;
+      int nbn[4 * kMaxSegs];
+      load_entries<ONEHOT>(p.ga, n_tile < p.num_tiles, (int64_t)n_tile * kTileM, kb_lo + n_kbi, lane, nbn);
+      if (!mbar_wait(a_empty(warp), (round & 1u) ^ 1u, abort_flag)) goto done;
+      gather_kblock<true>(p.ga, stage, kb_lo + kbi, lane, nbv, filled, list, a_full(warp));
 #pragma unroll
-      for (int s = 0; s < kStages; ++s) {
-        if (tile >= p.num_tiles) break;
-        if (kbi == 0) {
-          // new tile: its dout rows go to G buffer tile_iter % g_bufs once the MMAs of the tile that
-          // used the buffer before have drained
-          const int buf = (int)(tile_iter % (uint32_t)p.g_bufs);
-          const uint32_t use = tile_iter / (uint32_t)p.g_bufs;
-          if (!mbar_wait(g_empty(buf), (use & 1u) ^ 1u, abort_flag)) goto done;
-          load_g(tile, buf);
-        }
-        int n_tile = tile, n_kbi = kbi + 1, n_k = k + p.d8, n_cc = cc + p.m8;
-        if (n_cc >= p.cq) { n_cc -= p.cq; ++n_k; }
-        const bool new_tile = n_kbi == kb_n;
-        if (new_tile) { n_kbi = 0; n_tile += p.tile_splits; n_k = k0; n_cc = cc0; }
-        int nb_next[4];
-        if (ONEHOT && new_tile) entries(n_tile, n_kbi, n_k, par_n, off_n, nb_next);
-        else entries(n_tile, n_kbi, n_k, par_c, off_c, nb_next);
-
-        if (!mbar_wait(a_empty(s), (round & 1u) ^ 1u, abort_flag)) goto done;
-        const uint32_t src_off = (uint32_t)cc * 4u;
-        const uint32_t f = filled[s];
-        uint32_t nf = 0;
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) {
-          const bool have = nb[ps] >= 0;
-          const float* src = have ? p.in + ((uint32_t)nb[ps] * (uint32_t)p.c_in + src_off) : p.in;
-          if (have || ((f >> ps) & 1u))
-            cp_async16(slot0 + (uint32_t)(s * kStageBytes + ps * 32 * 128), src, have ? 16u : 0u);
-          nf |= (have ? 1u : 0u) << ps;
-        }
-        filled[s] = nf;
-        cp_async_arrive(a_full(s));
-
-        if (ONEHOT && new_tile) {
-#pragma unroll
-          for (int ps = 0; ps < 4; ++ps) { par_c[ps] = par_n[ps]; off_c[ps] = off_n[ps]; }
-          load_onehot(n_tile + p.tile_splits, par_n, off_n);
-        }
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) nb[ps] = nb_next[ps];
-        if (new_tile) ++tile_iter;
-        tile = n_tile; kbi = n_kbi; k = n_k; cc = n_cc;
-      }
+      for (int i = 0; i < 4 * kMaxSegs; ++i) nbv[i] = nbn[i];
+      kbi = n_kbi; lt = n_lt; tile = n_tile;
       ++round;
     }
   } else if (warp < 12) {
     // =================================================================== epilogue: TMEM -> dW (+=)
-    const int ew = warp - 8;
-    if (split < p.num_tiles) {
-      if (!mbar_wait(acc_full, 0u, abort_flag)) goto done;
-      tc_fence_after();
-      const int m = ew * 32 + lane;  // row of the group's [128 x N] slab
-      for (int gi = 0; gi < ng; ++gi) {
-        const int vk = (g0 + gi) * 128 + m;  // virtual-K row = k*c_in + ci  ->  dW row
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(gi * p.n_pad);
-        for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-          float acc[16];
-          tmem_ld16(taddr + (uint32_t)c0, acc);
-          if (vk < p.K * p.c_in) {
-            float* dst = p.dw + (int64_t)vk * p.c_out + c0;
+    const int ew = warp & 3;
+    if (!mbar_wait(acc_full, 0u, abort_flag)) goto done;
+    tc_fence_after();
+    const int m = ew * 32 + lane;  // row of the group's [128 x N] slab
+    for (int gi = 0; gi < ng; ++gi) {
+      const int vk = (g0 + gi) * 128 + m;  // virtual-K row = k*c_in + ci  ->  dW row
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(gi * p.n_pad);
+      for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+        float acc[16];
+        tmem_ld16(taddr + (uint32_t)c0, acc);
+        if (vk < p.ga.K * p.ga.c_in) {
+          float* dst = p.dw + (int64_t)vk * p.c_out + c0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c0 + j < p.c_out && acc[j] != 0.f) atomicAdd(dst + j, acc[j]);
-          }
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < p.c_out && acc[j] != 0.f) atomicAdd(dst + j, acc[j]);
         }
       }
-      tc_fence_before();
     }
-  } else {
+    tc_fence_before();
+  } else if (warp == 12) {
     // =================================================================== MMA issuer
-    if (lane == 0 && split < p.num_tiles) {
+    if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(128, p.n_pad, 1, 1);
       uint32_t it = 0, tile_iter = 0;
       bool ok = true;
@@ -247,6 +161,26 @@ k_wgrad_tc(const WgParams p) {
         if (ok) umma_commit(g_empty(buf));
       }
       if (ok) umma_commit(acc_full);
+    }
+  } else {
+    // =================================================================== dout-tile loader
+    const int nch = p.c_out >> 2;
+    uint32_t tile_iter = 0;
+    for (int tile = split; tile < p.num_tiles; tile += p.tile_splits, ++tile_iter) {
+      const int buf = (int)(tile_iter % (uint32_t)p.g_bufs);
+      const uint32_t use = tile_iter / (uint32_t)p.g_bufs;
+      if (!mbar_wait(g_empty(buf), (use & 1u) ^ 1u, abort_flag)) goto done;
+      const uint32_t gb = g_base + (uint32_t)buf * g_bytes;
+      for (int r0 = 0; r0 < kTileM; r0 += 4) {
+        const int r = r0 + (lane >> 3);
+        const int64_t row = (int64_t)tile * kTileM + r;
+        const bool ok = row < p.ga.n_out;
+        const float* src = p.dout + (ok ? row : 0) * p.c_out;
+        for (int ch = lane & 7; ch < nch; ch += 8)
+          cp_async16(gb + (uint32_t)(ch >> 3) * kStageBytes + (uint32_t)r * 128u + swz_base32(ch & 7, r), src + ch * 4,
+                     ok ? 16u : 0u);
+      }
+      cp_async_arrive(g_full(buf));
     }
   }
 done:
@@ -278,7 +212,7 @@ int launch_wgrad_tc(const WgParams& p, dim3 grid, size_t smem, cudaStream_t stre
 int* mm3d_device_err_flag();  // conv_tc.cu
 
 int mm3d_conv_wgrad_tc_supported(int c_in, int c_out, int K) {
-  return (c_in % 4) == 0 && c_in >= 4 && (c_out % 4) == 0 && c_out >= 4 && c_out <= 128 && K <= kMaxK;
+  return (c_in % 4) == 0 && c_in >= 16 && (c_out % 4) == 0 && c_out >= 4 && c_out <= 128 && K <= kMaxK;
 }
 
 int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_out, int64_t n_out, int c_out,
@@ -293,13 +227,12 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
   if (!accumulate) MM3D_CUDA(cudaMemsetAsync(d_weight, 0, sizeof(float) * (size_t)K * c_in * c_out, stream));
   if (n_out == 0) return MM3D_OK;
   WgParams p;
-  p.in = in; p.dout = d_out; p.dw = d_weight; p.tbl = tbl; p.tbl_stride = tbl_stride; p.onehot_off = onehot_off;
-  p.n_out = (int)n_out; p.c_in = c_in; p.c_out = c_out; p.K = K;
-  p.cq = c_in / 4; p.nq = K * p.cq; p.d8 = 8 / p.cq; p.m8 = 8 % p.cq;
+  p.ga = GatherArgs{in, tbl, tbl_stride, onehot_off, (int)n_out, c_in, K, c_in / 4, K * (c_in / 4)};
+  p.dout = d_out; p.dw = d_weight; p.c_out = c_out;
   p.n_pad = (c_out + 15) / 16 * 16;
   p.nblk = (p.n_pad + 31) / 32;
   p.num_tiles = (int)mm3d_cdiv(n_out, kTileM);
-  const int kbt = (p.nq + 7) / 8;
+  const int kbt = (p.ga.nq + 7) / 8;
   p.groups_total = (kbt + 3) / 4;
   int gpc = 512 / p.n_pad;  // TMEM: one [128 x n_pad] accumulator per group
   if (gpc > p.groups_total) gpc = p.groups_total;
@@ -314,7 +247,8 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
   p.tmem_cols = cols;
   p.g_bufs = p.nblk <= 2 ? 2 : 1;
   p.err = mm3d_device_err_flag();
-  const size_t smem = 1024 + (size_t)kStages * kStageBytes + (size_t)p.g_bufs * p.nblk * kStageBytes + 8 * (2 * kStages + 5) + 64;
+  const size_t smem = 1024 + (size_t)kStages * kStageBytes + (size_t)p.g_bufs * p.nblk * kStageBytes +
+                      (size_t)kStages * kListBytes + 8 * (2 * kStages + 5) + 64;
   dim3 grid((unsigned)tile_splits, (unsigned)group_splits);
   int rc = onehot_off ? launch_wgrad_tc<true>(p, grid, smem, stream) : launch_wgrad_tc<false>(p, grid, smem, stream);
   if (rc) return rc;

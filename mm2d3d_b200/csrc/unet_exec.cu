@@ -279,7 +279,9 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
 int fill_net(Net& net, int in_channels, int m, int num_planes, int mode, const int64_t* level_desc, int64_t n_points) {
   MM3D_REQUIRE(num_planes >= 1 && num_planes <= 16 && m > 0 && in_channels > 0, MM3D_ERR_INVALID, "bad network shape");
   net.L = num_planes; net.m = m; net.cin = in_channels; net.mode = mode; net.n_points = n_points;
-  net.cin_k = (mode != MM3D_MODE_FP32 && (in_channels & 3)) ? (in_channels + 3) / 4 * 4 : in_channels;
+  // tensor-core kernels gather whole 16-byte pieces of rows of >= 16 channels: pad the stem input
+  net.cin_k = in_channels;
+  if (mode != MM3D_MODE_FP32 && ((in_channels & 3) || in_channels < 16)) net.cin_k = in_channels < 16 ? 16 : (in_channels + 3) / 4 * 4;
   net.lv.resize(num_planes);
   for (int l = 0; l < num_planes; ++l) {
     const int64_t* d = level_desc + 6 * l;
@@ -332,7 +334,7 @@ MM3D_API size_t mm3d_unet_bwd_bytes(int in_channels, int m, int num_planes, int 
 
 MM3D_API size_t mm3d_unet_scratch_bytes(int in_channels, int m, int num_planes, int mode) {
   size_t best = mm3d_bnrelu_workspace_bytes(2 * m * num_planes);
-  const int cin_k = (in_channels + 3) / 4 * 4;
+  const int cin_k = in_channels < 16 ? 16 : (in_channels + 3) / 4 * 4;
   size_t s = mm3d_conv_workspace_bytes(0, 0, cin_k, m, 27, mode);
   if (s > best) best = s;
   for (int l = 0; l < num_planes; ++l) {

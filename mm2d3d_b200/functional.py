@@ -140,9 +140,11 @@ class TableConvFn(torch.autograd.Function):
             raise ValueError(f"{kind} convolution: input {tuple(x.shape)} / weight {tuple(w.shape)} do not match "
                              f"the active set ({fwd_t.n_in} rows, {fwd_t.K} offsets)")
         m = MODES[mode]
-        # tensor-core modes gather whole 16-byte row pieces: pad an odd channel count (the 3-channel
-        # stem) with zero channels instead of leaving that layer on the SIMT kernels
-        pad = (-c_in) % 4 if m != _lib.MODE_FP32 else 0
+        # tensor-core modes gather whole 16-byte pieces of rows of >= 16 channels: pad a narrow or odd
+        # channel count (the 3-channel stem) with zero channels instead of using the SIMT kernels
+        pad = 0
+        if m != _lib.MODE_FP32:
+            pad = 16 - c_in if c_in < 16 else (-c_in) % 4
         if pad:
             x = torch.nn.functional.pad(x, (0, pad))
             w = torch.nn.functional.pad(w, (0, 0, 0, pad))
