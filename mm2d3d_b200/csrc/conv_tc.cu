@@ -141,8 +141,9 @@ k_conv_tc(const TcParams p) {
       const int n_tile = blockIdx.x + n_lt * gridDim.x;
       int nbn[4 * kMaxSegs];  // the next item's table entries are in flight while this one is copied
       load_entries<ONEHOT>(p.ga, n_tile < p.num_tiles, (int64_t)n_tile * kTileM, n_kb, lane, nbn);
+      const int cnt = build_list(p.ga, kb, lane, nbv, filled, list);  // off the stage's critical path
       if (!mbar_wait(a_empty(warp), (round & 1u) ^ 1u, abort_flag)) goto done;
-      gather_kblock<false>(p.ga, stage, kb, lane, nbv, filled, list, a_full(warp));
+      issue_copies<false>(p.ga, stage, lane, cnt, list, a_full(warp));
 #pragma unroll
       for (int i = 0; i < 4 * kMaxSegs; ++i) nbv[i] = nbn[i];
       kb = n_kb; lt = n_lt; tile = n_tile;

@@ -104,8 +104,9 @@ k_wgrad_tc(const WgParams p) {
       const int n_tile = split + n_lt * p.tile_splits;
       int nbn[4 * kMaxSegs];
       load_entries<ONEHOT>(p.ga, n_tile < p.num_tiles, (int64_t)n_tile * kTileM, kb_lo + n_kbi, lane, nbn);
+      const int cnt = build_list(p.ga, kb_lo + kbi, lane, nbv, filled, list);  // off the stage's critical path
       if (!mbar_wait(a_empty(warp), (round & 1u) ^ 1u, abort_flag)) goto done;
-      gather_kblock<true>(p.ga, stage, kb_lo + kbi, lane, nbv, filled, list, a_full(warp));
+      issue_copies<true>(p.ga, stage, lane, cnt, list, a_full(warp));
 #pragma unroll
       for (int i = 0; i < 4 * kMaxSegs; ++i) nbv[i] = nbn[i];
       kbi = n_kbi; lt = n_lt; tile = n_tile;

@@ -75,69 +75,80 @@ __device__ __forceinline__ void load_entries(const GatherArgs& a, bool tile_ok, 
   }
 }
 
-// Fill stage `stage` (shared address of its [128 rows][128 B]) with K-block kb.  `filled` holds, per
-// lane, 8 column bits for each of its 4 rows (bit rg*8 + col = that slot holds data).  `list` is the
-// calling warp's private shared-memory list.  Ends with the lanes' cp.async arrivals on `full_bar`.
-template <bool BASE32>
-__device__ __forceinline__ void gather_kblock(const GatherArgs& a, uint32_t stage, int kb, int lane,
-                                              const int (&nbv)[4 * kMaxSegs], uint32_t& filled, uint32_t list,
-                                              uint32_t full_bar) {
+// Step 1 (needs no access to the stage, so it runs BEFORE the wait for the stage to be free):
+// decide, for K-block kb, which (row, columns) of the stage must be written or re-zeroed and compact
+// them into the warp's list.  `filled` holds, per lane, 8 column bits for each of its 4 rows
+// (bit rg*8 + col = that slot holds data) and is advanced to the state after this K-block.
+// All ballots are independent and the stores come last, so the 12 (segment, row group) tasks overlap.
+__device__ __forceinline__ int build_list(const GatherArgs& a, int kb, int lane, const int (&nbv)[4 * kMaxSegs],
+                                          uint32_t& filled, uint32_t list) {
   const int q0 = kb * 8;
   const int k_first = q0 / a.cq;
   int cc = q0 - k_first * a.cq, col = 0;
   const uint32_t lt = (1u << lane) - 1u;
-  int cnt = 0;
+  uint32_t meta[4 * (kMaxSegs + 1)], bal[4 * (kMaxSegs + 1)];
+  int src[4 * (kMaxSegs + 1)];
 #pragma unroll
   for (int sg = 0; sg <= kMaxSegs; ++sg) {
-    // segments of real offsets first; one trailing pseudo segment covers columns past the end of
-    // the virtual K so that stale data from an earlier K-block on this stage gets cleared
+    // real segments first; one trailing pseudo segment covers the columns past the end of the virtual
+    // K so that stale data from an earlier K-block on this stage gets cleared
     const int k = k_first + sg;
-    int ncols;
-    bool real;
-    if (sg < kMaxSegs && col < 8 && k < a.K) {
-      ncols = min(8 - col, a.cq - cc);
-      real = true;
-    } else {
-      ncols = 8 - col;
-      real = false;
-    }
-    if (ncols > 0) {
-      const uint32_t segmask = ((1u << ncols) - 1u) << col;
-      const int delta = cc - col + 8;  // source chunk = column + delta - 8
+    const bool real = sg < kMaxSegs && col < 8 && k < a.K;
+    const int ncols = real ? min(8 - col, a.cq - cc) : 8 - col;
+    const uint32_t segmask = ncols > 0 ? ((1u << ncols) - 1u) << col : 0u;
+    const int delta = cc - col + 8;  // source chunk = column + delta - 8
 #pragma unroll
-      for (int rg = 0; rg < 4; ++rg) {
-        const int nb = (real && sg < kMaxSegs) ? nbv[(sg < kMaxSegs ? sg : 0) * 4 + rg] : -1;
-        const bool have = nb >= 0;
-        const uint32_t old = (filled >> (rg * 8)) & 0xFFu;
-        const uint32_t fillm = have ? segmask : 0u;
-        const uint32_t clearm = old & segmask & ~fillm;
-        filled = (filled & ~(segmask << (rg * 8))) | (fillm << (rg * 8));
-        const bool act = (fillm | clearm) != 0u;
-        const uint32_t m = __ballot_sync(0xffffffffu, act);
-        if (act) {
-          const int pos = cnt + __popc(m & lt);
-          const uint32_t meta = (uint32_t)(rg * 32 + lane) | (fillm << 8) | (clearm << 16) | ((uint32_t)delta << 24);
-          asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(list + (uint32_t)pos * 8u), "r"((uint32_t)nb), "r"(meta) : "memory");
-        }
-        cnt += __popc(m);
-      }
-      col += ncols;
-      cc = 0;
+    for (int rg = 0; rg < 4; ++rg) {
+      const int nb = real ? nbv[(sg < kMaxSegs ? sg : 0) * 4 + rg] : -1;
+      const uint32_t old = (filled >> (rg * 8)) & 0xFFu;
+      const uint32_t fillm = nb >= 0 ? segmask : 0u;
+      const uint32_t clearm = old & segmask & ~fillm;
+      filled = (filled & ~(segmask << (rg * 8))) | (fillm << (rg * 8));
+      const bool act = (fillm | clearm) != 0u;
+      bal[sg * 4 + rg] = __ballot_sync(0xffffffffu, act);
+      meta[sg * 4 + rg] = act ? ((uint32_t)(rg * 32 + lane) | (fillm << 8) | (clearm << 16) | ((uint32_t)delta << 24)) : 0u;
+      src[sg * 4 + rg] = nb;
     }
-    if (!real) break;
+    col += ncols;
+    cc = 0;
+  }
+  int cnt = 0;
+#pragma unroll
+  for (int t = 0; t < 4 * (kMaxSegs + 1); ++t) {
+    if (meta[t]) {
+      const int pos = cnt + __popc(bal[t] & lt);
+      asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(list + (uint32_t)pos * 8u), "r"((uint32_t)src[t]), "r"(meta[t]) : "memory");
+    }
+    cnt += __popc(bal[t]);
   }
   __syncwarp();
+  return cnt;
+}
+
+// Step 2 (after the stage is free): walk the list, four rows per pass, 8 lanes per row, one 16-byte
+// cp.async (copy or zero fill) per lane; ends with the lanes' cp.async arrivals on `full_bar`.
+template <bool BASE32>
+__device__ __forceinline__ void issue_copies(const GatherArgs& a, uint32_t stage, int lane, int cnt, uint32_t list,
+                                             uint32_t full_bar) {
   const int c = lane & 7;
-  for (int e = lane >> 3; e < cnt; e += 4) {
-    uint32_t enb, meta;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(enb), "=r"(meta) : "r"(list + (uint32_t)e * 8u) : "memory");
-    const int r = (int)(meta & 0xFFu);
-    const uint32_t dst = stage + (uint32_t)r * 128u + chunk_off<BASE32>(c, r);
-    if ((meta >> (8 + c)) & 1u) {
-      const int src_chunk = c + (int)(meta >> 24) - 8;
-      cp_async16(dst, a.in + ((uint32_t)enb * (uint32_t)a.c_in + (uint32_t)src_chunk * 4u), 16u);
-    } else if ((meta >> (16 + c)) & 1u) {
-      cp_async16(dst, a.in, 0u);
+  for (int e0 = lane >> 3; e0 < cnt; e0 += 8) {
+    uint32_t enb[2], meta[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      meta[u] = 0;
+      if (e0 + 4 * u < cnt)
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(enb[u]), "=r"(meta[u]) : "r"(list + (uint32_t)(e0 + 4 * u) * 8u) : "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int r = (int)(meta[u] & 0xFFu);
+      const uint32_t dst = stage + (uint32_t)r * 128u + chunk_off<BASE32>(c, r);
+      if ((meta[u] >> (8 + c)) & 1u) {
+        const int src_chunk = c + (int)(meta[u] >> 24) - 8;
+        cp_async16(dst, a.in + ((uint32_t)enb[u] * (uint32_t)a.c_in + (uint32_t)src_chunk * 4u), 16u);
+      } else if ((meta[u] >> (16 + c)) & 1u) {
+        cp_async16(dst, a.in, 0u);
+      }
     }
   }
   cp_async_arrive(full_bar);
