@@ -11,18 +11,21 @@
 // stored once: deterministic.  Packing offsets back to back along K means a 16-channel layer needs
 // 14 K-blocks instead of 27 and no layer pays per-offset padding.
 //
-// Warp roles ((S+6) warps):   warps 0..S-1    gather producers, warp w OWNS ring stage w (tc_gather.cuh)
+// Warp roles ((S+5) warps):   warps 0..S-1    gather producers, warp w OWNS ring stage w (tc_gather.cuh)
+//                                             and bulk-copies that K-block's weight block (cp.async.bulk)
 //                             warps S..S+3    epilogue (TMEM lanes 32(w&3).. -> registers -> global)
 //                             warp  S+4       MMA issuer (one lane) + TMEM allocator
-//                             warp  S+5       weight loader (cp.async.bulk of the weight image)
-// Pipelines (mbarriers):      A ring   a_full[S] (32 cp.async arrivals)   / a_empty[S] (tcgen05.commit)
-//                             B ring   b_full[SB] (expect_tx + bulk copy) / b_empty[SB] (tcgen05.commit)
+// Pipelines (mbarriers):      ring     a_full[S] (32 cp.async arrivals + expect_tx of the weight block)
+//                                      / a_empty[S] (tcgen05.commit): ONE wait and ONE commit per K-block,
+//                                      because the single MMA-issuing thread is the serial resource
 //                             accum    acc_full[2] (tcgen05.commit)       / acc_empty[2] (128 arrivals)
 // The accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the MMAs of i+1.
 //
 // Absent neighbours cost neither instructions nor shared-memory traffic beyond one coalesced table
 // read per 32 rows: stages are zeroed once, the producer compacts the rows that need an action and
 // re-zeroes (cp.async with src-size 0) only slots that held data the last time the stage was used.
+#include <stdlib.h>
+
 #include "tc_gather.cuh"
 
 namespace {
@@ -34,7 +37,6 @@ constexpr int kKBlock = 32;                 // tf32 elements per 128-byte row of
 constexpr int kStageBytes = kTileM * 128;   // one A stage = one K-block of 128 rows = 16 KB
 constexpr int kEpilogue = 128;
 constexpr int kMaxStages = 6;
-constexpr int kMaxBStages = 4;
 constexpr int kMaxK = 27;
 
 struct TcParams {
@@ -45,6 +47,7 @@ struct TcParams {
   int kbt;            // K-blocks per tile = ceil(K * cq / 8)
   int n_pad, num_tiles, b_stages, tmem_cols;
   int* err;
+  long long* trace;  // debug: MMA-thread timestamps of CTA 0 (4 per item), or NULL
 };
 
 // Weight image: one [n_pad][32] block per K-block; element (n, e) of block kb is Wsel(k)[ci][n]
@@ -72,28 +75,25 @@ __global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ 
 }
 
 template <int S, bool ONEHOT>
-__global__ void __launch_bounds__((S + 6) * 32, 1)
+__global__ void __launch_bounds__((S + 5) * 32, 1)
 k_conv_tc(const TcParams p) {
-  constexpr int kThreads = (S + 6) * 32;
+  constexpr int kThreads = (S + 5) * 32;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A stages][B stages][producer lists][barriers][tmem ptr][abort]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int SB = p.b_stages;
   const uint32_t b_bytes = (uint32_t)p.n_pad * 128u;
   const uint32_t b_stride = (b_bytes + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + (uint32_t)S * kStageBytes;
-  const uint32_t l_base = b_base + (uint32_t)SB * b_stride;
+  const uint32_t l_base = b_base + (uint32_t)S * b_stride;  // one weight block per A stage
   const uint32_t bar_base = l_base + (uint32_t)S * kListBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar_base - smem_base));
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(kMaxStages + s); };
-  auto b_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + s); };
-  auto b_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + kMaxBStages + s); };
-  auto acc_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 * kMaxBStages + s); };
-  auto acc_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 * kMaxBStages + 2 + s); };
-  constexpr int kNumBars = 2 * kMaxStages + 2 * kMaxBStages + 4;
+  auto acc_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + s); };
+  auto acc_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 + s); };
+  constexpr int kNumBars = 2 * kMaxStages + 4;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNumBars);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + kNumBars + 1);
 
@@ -104,12 +104,8 @@ k_conv_tc(const TcParams p) {
     reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(a_full(s), 32);
+      mbar_init(a_full(s), 33);  // 32 cp.async arrivals (gathered rows) + 1 expect_tx arrival (weight block)
       mbar_init(a_empty(s), 1);
-    }
-    for (int s = 0; s < SB; ++s) {
-      mbar_init(b_full(s), 1);
-      mbar_init(b_empty(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full(s), 1);
@@ -143,6 +139,10 @@ k_conv_tc(const TcParams p) {
       load_entries<ONEHOT>(p.ga, n_tile < p.num_tiles, (int64_t)n_tile * kTileM, n_kb, lane, nbn);
       const int cnt = build_list(p.ga, kb, lane, nbv, filled, list);  // off the stage's critical path
       if (!mbar_wait(a_empty(warp), (round & 1u) ^ 1u, abort_flag)) goto done;
+      if (lane == 0) {  // this K-block's weight block rides on the same barrier as the gathered rows
+        mbar_arrive_expect_tx(a_full(warp), b_bytes);
+        bulk_g2s(b_base + (uint32_t)warp * b_stride, p.wimg + (size_t)kb * p.n_pad * kKBlock, b_bytes, a_full(warp));
+      }
       issue_copies<false>(p.ga, stage, lane, cnt, list, a_full(warp));
 #pragma unroll
       for (int i = 0; i < 4 * kMaxSegs; ++i) nbv[i] = nbn[i];
@@ -191,35 +191,22 @@ k_conv_tc(const TcParams p) {
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.n_pad);
         for (int kb = 0; kb < p.kbt; ++kb, ++it) {
           const int s = (int)(it % (uint32_t)S);
-          const int bs = (int)(it % (uint32_t)SB);
-          if (!mbar_wait(b_full(bs), (it / (uint32_t)SB) & 1u, abort_flag)) { ok = false; break; }
+          const bool tr = p.trace && blockIdx.x == 0 && it < 512;
+          if (tr) p.trace[4 * it + 0] = p.trace[4 * it + 1] = clock64();
           if (!mbar_wait(a_full(s), (it / (uint32_t)S) & 1u, abort_flag)) { ok = false; break; }
+          if (tr) p.trace[4 * it + 2] = clock64();
           tc_fence_after();
           const int rem = p.ga.nq * 4 - kb * kKBlock;  // virtual-K elements left
           const int ksteps = rem >= kKBlock ? kKBlock / 8 : (rem + 7) >> 3;
           const uint32_t a_addr = a_base + (uint32_t)s * kStageBytes;
-          const uint32_t b_addr = b_base + (uint32_t)bs * b_stride;
+          const uint32_t b_addr = b_base + (uint32_t)s * b_stride;
           for (int ks = 0; ks < ksteps; ++ks)
             umma_tf32(d_tmem, make_desc_sw128(a_addr + ks * 32), make_desc_sw128(b_addr + ks * 32), idesc,
                       (kb | ks) != 0);
-          umma_commit(a_empty(s));
-          umma_commit(b_empty(bs));
+          umma_commit(a_empty(s));  // frees the stage and its weight block
+          if (tr) p.trace[4 * it + 3] = clock64();
         }
         if (ok) umma_commit(acc_full(ab));
-      }
-    }
-  } else {
-    // =================================================================== weight loader
-    if (lane == 0) {
-      uint32_t it = 0;
-      bool ok = true;
-      for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
-        for (int kb = 0; kb < p.kbt; ++kb, ++it) {
-          const int bs = (int)(it % (uint32_t)SB);
-          if (!mbar_wait(b_empty(bs), ((it / (uint32_t)SB) & 1u) ^ 1u, abort_flag)) { ok = false; break; }
-          mbar_arrive_expect_tx(b_full(bs), b_bytes);
-          bulk_g2s(b_base + (uint32_t)bs * b_stride, p.wimg + (size_t)kb * p.n_pad * kKBlock, b_bytes, b_full(bs));
-        }
       }
     }
   }
@@ -242,7 +229,7 @@ int pow2_cols(int n) {
 
 template <int S, bool ONEHOT>
 int launch_conv_tc(const TcParams& p, size_t smem, cudaStream_t stream) {
-  constexpr int kThreads = (S + 6) * 32;
+  constexpr int kThreads = (S + 5) * 32;
   static int regs = 0;
   if (!regs) {
     MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc<S, ONEHOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -339,16 +326,21 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
   p.num_tiles = (int)mm3d_cdiv(n_out, kTileM);
   p.tmem_cols = pow2_cols(2 * n_pad);
   p.err = mm3d_device_err_flag();
+  {
+    const char* t = getenv("MM3D_TC_TRACE");  // debug: device pointer (decimal) of a 2048-entry int64 buffer
+    p.trace = t ? (long long*)strtoull(t, nullptr, 10) : nullptr;
+  }
   const uint32_t b_stride = ((uint32_t)n_pad * 128u + 1023u) & ~1023u;
-  // narrow N: 4 A + 4 B stages, several CTAs per SM; wide N: one CTA per SM with a 6-deep A ring
-  const bool wide = n_pad > 96;
-  const int S = wide ? 6 : 4;
-  p.b_stages = wide ? (n_pad > 128 ? 2 : 3) : 4;
-  const size_t smem = 1024 + (size_t)S * kStageBytes + (size_t)p.b_stages * b_stride + (size_t)S * kListBytes +
-                      8 * (2 * kMaxStages + 2 * kMaxBStages + 4) + 64;
+  // narrow N: 3 stages (48 KB + small weight blocks) so that three CTAs share an SM; mid: 4; wide: 6
+  const bool wide = n_pad > 96, narrow = n_pad <= 32;
+  const int S = wide ? 6 : narrow ? 3 : 4;
+  p.b_stages = S;
+  const size_t smem = 1024 + (size_t)S * kStageBytes + (size_t)S * b_stride + (size_t)S * kListBytes +
+                      8 * (2 * kMaxStages + 4) + 64;
   int rc;
-  if (wide) rc = onehot_off ? launch_conv_tc<6, true>(p, smem, stream) : launch_conv_tc<6, false>(p, smem, stream);
-  else      rc = onehot_off ? launch_conv_tc<4, true>(p, smem, stream) : launch_conv_tc<4, false>(p, smem, stream);
+  if (wide)        rc = onehot_off ? launch_conv_tc<6, true>(p, smem, stream) : launch_conv_tc<6, false>(p, smem, stream);
+  else if (narrow) rc = onehot_off ? launch_conv_tc<3, true>(p, smem, stream) : launch_conv_tc<3, false>(p, smem, stream);
+  else             rc = onehot_off ? launch_conv_tc<4, true>(p, smem, stream) : launch_conv_tc<4, false>(p, smem, stream);
   if (rc) return rc;
   mm3d_count_launches(2);
   MM3D_CHECK_LAUNCH("mm3d_conv_fwd_tc");

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--shape", default="nuscenes")
+    ap.add_argument("--noflush", action="store_true")
     a = ap.parse_args()
 
     dev = torch.device("cuda", 0)
@@ -68,7 +69,8 @@ def main():
     torch.cuda.synchronize()
     ts = []
     for _ in range(a.reps):
-        flush.zero_()
+        if not a.noflush:
+            flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         run()
