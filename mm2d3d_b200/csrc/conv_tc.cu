@@ -332,7 +332,7 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
   }
   const uint32_t b_stride = ((uint32_t)n_pad * 128u + 1023u) & ~1023u;
   // narrow N: 3 stages (48 KB + small weight blocks) so that three CTAs share an SM; mid: 4; wide: 6
-  const bool wide = n_pad > 96, narrow = n_pad <= 32;
+  const bool wide = n_pad > 96 && n_pad <= 128, narrow = n_pad <= 32;  // (N > 128: 24-32 KB weight blocks, 4 stages)
   const int S = wide ? 6 : narrow ? 3 : 4;
   p.b_stages = S;
   const size_t smem = 1024 + (size_t)S * kStageBytes + (size_t)S * b_stride + (size_t)S * kListBytes +
