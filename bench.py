@@ -205,13 +205,13 @@ def kernel_pass(net, locs_d, feats_d, mode, pk):
     for mod, x, meta, spatial in records:
         w = mod.weight.detach()
         K, c_in, c_out = w.shape[0], w.shape[2], w.shape[3]
-        if mode != "fp32" and (c_in < 16 or c_in % 4):
-            # the product path pads narrow / odd channel counts (the 3-channel stem) in tensor-core modes
-            pad = 16 - c_in if c_in < 16 else (-c_in) % 4
+        if mode != "fp32" and c_in % 16:
+            # the product path pads odd channel counts (the 3-channel stem) to 16 in tensor-core modes
+            pad = (-c_in) % 16
             x = torch.nn.functional.pad(x, (0, pad)).contiguous()
             w = torch.nn.functional.pad(w, (0, 0, 0, pad)).contiguous()
             c_in += pad
-        fwd_t, bwd_t, bwd_flags = F.conv_tables(meta, mod.kind, spatial)
+        fwd_t, bwd_t, bwd_flags = F.conv_tables(meta, mod.kind, spatial, plans=mode != "fp32")
         out = torch.empty(fwd_t.n_out, c_out, device=dev)
         dout = torch.randn(fwd_t.n_out, c_out, device=dev)
         dx = torch.empty(bwd_t.n_out, c_in, device=dev)
@@ -233,18 +233,18 @@ def kernel_pass(net, locs_d, feats_d, mode, pk):
 
         def f_fwd():
             _lib.check(lib.mm3d_conv_fwd(x.data_ptr(), fwd_t.n_in, c_in, out.data_ptr(), fwd_t.n_out, c_out,
-                                         w.data_ptr(), K, fwd_t.tbl, fwd_t.stride, fwd_t.onehot, 0, m,
-                                         ws.data_ptr(), ws.numel(), sp))
+                                         w.data_ptr(), K, fwd_t.tbl, fwd_t.stride, fwd_t.onehot, fwd_t.plan, fwd_t.plan_cap,
+                                         0, m, ws.data_ptr(), ws.numel(), sp))
 
         def f_dgrad():
             _lib.check(lib.mm3d_conv_fwd(dout.data_ptr(), bwd_t.n_in, c_out, dx.data_ptr(), bwd_t.n_out, c_in,
-                                         w.data_ptr(), K, bwd_t.tbl, bwd_t.stride, bwd_t.onehot, bwd_flags, m,
-                                         ws.data_ptr(), ws.numel(), sp))
+                                         w.data_ptr(), K, bwd_t.tbl, bwd_t.stride, bwd_t.onehot, bwd_t.plan, bwd_t.plan_cap,
+                                         bwd_flags, m, ws.data_ptr(), ws.numel(), sp))
 
         def f_wgrad():
             _lib.check(lib.mm3d_conv_wgrad(x.data_ptr(), fwd_t.n_in, c_in, dout.data_ptr(), fwd_t.n_out, c_out,
-                                           dw.data_ptr(), K, fwd_t.tbl, fwd_t.stride, fwd_t.onehot, 0, m,
-                                           ws.data_ptr(), ws.numel(), sp))
+                                           dw.data_ptr(), K, fwd_t.tbl, fwd_t.stride, fwd_t.onehot, fwd_t.plan,
+                                           fwd_t.plan_cap, 0, m, ws.data_ptr(), ws.numel(), sp))
 
         tbl_bytes = 4 * K * fwd_t.n_out if fwd_t.onehot is None else 5 * fwd_t.n_out
         alg_bytes = 4 * (fwd_t.n_in * c_in + fwd_t.n_out * c_out) + 4 * K * c_in * c_out + tbl_bytes

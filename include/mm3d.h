@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MM3D_ABI_VERSION 1
+#define MM3D_ABI_VERSION 2
 
 #define MM3D_OK 0
 #define MM3D_ERR_INVALID 1     /* bad argument */
@@ -103,6 +103,18 @@ MM3D_API int mm3d_build_nbr27(const uint64_t* keys, const int32_t* n_dev, int64_
                      const uint64_t* hash_keys, const int32_t* hash_vals, int64_t hash_cap,
                      int32_t* nbr_tbl, int64_t tbl_stride, mm3d_stream_t stream);
 
+/* Row plan of a rule table, used by the tensor-core convolution modes: the table's output rows
+ * ordered by neighbour mask (stable radix sort per 8192-row chunk), the table permuted into that
+ * order and one offset mask per tile of 128 rows, so the kernels skip (tile, offset) blocks without
+ * any input.  Built once per table (no SparseConvNet counterpart: its rule books are per-offset pair
+ * lists); every layer, direction and gradient that uses the table shares it.  `tbl`, `tbl_stride`,
+ * `onehot_off` as in mm3d_conv_fwd; the row count is read from *n_dev (<= n_cap).  Results of the
+ * convolutions do not depend on the plan's row order. */
+MM3D_API size_t mm3d_plan_bytes(int64_t n_cap, int K);
+MM3D_API int mm3d_build_plan(const int32_t* tbl, int64_t tbl_stride, const uint8_t* onehot_off,
+                    const int32_t* n_dev, int64_t n_cap, int K, void* plan, size_t plan_bytes,
+                    mm3d_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * I/O layers (replace SCN InputLayer_updateOutput/updateGradInput, OutputLayer_*).
  * mode 4 = mean of a voxel's points, 3 = sum.
@@ -124,16 +136,18 @@ MM3D_API int mm3d_output_bwd(const float* d_out, const int32_t* p2v, int64_t n_p
  * (onehot_off[j] == k ? tbl[j] : -1) with tbl = parent[] (the deconvolution's table).
  * Wsel(k) = W[k] ([c_in, c_out]), or with flags: W[k]^T and/or W[K-1-k].
  * The three layer types and their gradients are all instances.
+ * `plan` (with the capacity it was built for) is the table's row plan; the tensor-core modes
+ * require it, MM3D_MODE_FP32 ignores it (may be NULL).
  * ---------------------------------------------------------------------------------------- */
 MM3D_API size_t mm3d_conv_workspace_bytes(int64_t n_in, int64_t n_out, int c_in, int c_out, int K, int mode);
 MM3D_API int mm3d_conv_fwd(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
                   const float* weight, int K, const int32_t* tbl, int64_t tbl_stride,
-                  const uint8_t* onehot_off, int flags, int mode,
+                  const uint8_t* onehot_off, const void* plan, int64_t plan_cap, int flags, int mode,
                   void* ws, size_t ws_bytes, mm3d_stream_t stream);
 /* d_weight[k] (+)= sum_j in[tbl(j,k)]^T . d_out[j]   ([K, c_in, c_out]); accumulate=0 overwrites */
 MM3D_API int mm3d_conv_wgrad(const float* in, int64_t n_in, int c_in, const float* d_out, int64_t n_out,
                     int c_out, float* d_weight, int K, const int32_t* tbl, int64_t tbl_stride,
-                    const uint8_t* onehot_off, int accumulate, int mode,
+                    const uint8_t* onehot_off, const void* plan, int64_t plan_cap, int accumulate, int mode,
                     void* ws, size_t ws_bytes, mm3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -164,12 +178,14 @@ MM3D_API int mm3d_lift2d_bwd(const void* d_out, int dtype, int B, int C, int H, 
 /* ------------------------------------------------------------------------------------------
  * Whole-network executor: UNetSCN (3d_net/scn_unet.py:90-126, VGG blocks, block_reps == 1) forward and
  * backward as one call each -- the same kernels as above, driven natively instead of from ~110
- * Python autograd nodes.  level_desc: 6 int64 per level {rows, nbr table ptr, table stride, parent ptr,
- * off ptr, child ptr}.  params / grads: HOST arrays of device pointers in module-tree order:
+ * Python autograd nodes.  level_desc: MM3D_LEVEL_DESC_WORDS int64 per level {rows, nbr table ptr, table
+ * stride, parent ptr, off ptr, child ptr, plan of the 3^3 table, plan of the child table, plan of the
+ * (parent, off) table, plan capacity} (plans may be 0 in MM3D_MODE_FP32).  params / grads: HOST arrays of device pointers in module-tree order:
  *   stem.w | per level: pre_bn{gamma,beta,running_mean,running_var} pre.w [dn_bn{4} dn.w <deeper level>
  *   up_bn{4} up.w post_bn{4} post.w] | head_bn{4}          (mm3d_unet_num_params slots; grads ignore
  * the running-stat slots).  act: activations kept from forward to backward; tmp: backward temporaries.
  * ---------------------------------------------------------------------------------------- */
+#define MM3D_LEVEL_DESC_WORDS 10
 MM3D_API int64_t mm3d_unet_num_params(int num_planes);
 MM3D_API size_t mm3d_unet_act_bytes(int in_channels, int m, int num_planes, int mode, const int64_t* level_desc,
                            int64_t n_points);

@@ -11,7 +11,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmm3d.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+LEVEL_DESC_WORDS = 10
 
 MODE_FP32, MODE_TF32, MODE_BF16 = 0, 1, 2
 MODES = {"fp32": MODE_FP32, "tf32": MODE_TF32, "bf16": MODE_BF16}
@@ -45,8 +46,10 @@ SIGNATURES = {
     "mm3d_output_fwd": (_i, [_p, _p, _i64, _i, _p, _p]),
     "mm3d_output_bwd": (_i, [_p, _p, _i64, _i64, _i, _p, _p]),
     "mm3d_conv_workspace_bytes": (_sz, [_i64, _i64, _i, _i, _i, _i]),
-    "mm3d_conv_fwd": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i, _p, _i64, _p, _i, _i, _p, _sz, _p]),
-    "mm3d_conv_wgrad": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i, _p, _i64, _p, _i, _i, _p, _sz, _p]),
+    "mm3d_plan_bytes": (_sz, [_i64, _i]),
+    "mm3d_build_plan": (_i, [_p, _i64, _p, _p, _i64, _i, _p, _sz, _p]),
+    "mm3d_conv_fwd": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i, _p, _i64, _p, _p, _i64, _i, _i, _p, _sz, _p]),
+    "mm3d_conv_wgrad": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i, _p, _i64, _p, _p, _i64, _i, _i, _p, _sz, _p]),
     "mm3d_bnrelu_workspace_bytes": (_sz, [_i]),
     "mm3d_bnrelu_fwd": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i, _p, _sz, _p]),
     "mm3d_bnrelu_bwd": (_i, [_p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _f, _i, _p, _sz, _p]),

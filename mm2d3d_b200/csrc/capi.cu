@@ -42,11 +42,11 @@ int mm3d_conv_tc_supported(int c_in, int c_out, int K);
 // conv_tc_wgrad.cu
 int mm3d_conv_wgrad_tc_supported(int c_in, int c_out, int K);
 int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_out, int64_t n_out, int c_out,
-                       float* d_weight, int K, const int32_t* tbl, int64_t tbl_stride,
-                       const uint8_t* onehot_off, int accumulate, cudaStream_t stream);
+                       float* d_weight, int K, const void* plan, int64_t plan_cap, int accumulate,
+                       cudaStream_t stream);
 int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
-                     const float* weight, int K, const int32_t* tbl, int64_t tbl_stride,
-                     const uint8_t* onehot_off, int flags, void* ws, size_t ws_bytes, cudaStream_t stream);
+                     const float* weight, int K, const void* plan, int64_t plan_cap, int flags, void* ws,
+                     size_t ws_bytes, cudaStream_t stream);
 
 extern "C" size_t mm3d_conv_workspace_bytes(int64_t n_in, int64_t n_out, int c_in, int c_out, int K, int mode) {
   (void)n_in; (void)n_out; (void)mode;
@@ -69,7 +69,7 @@ static int check_conv_args(const void* in, const void* out, const void* w, const
 
 extern "C" int mm3d_conv_fwd(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
                              const float* weight, int K, const int32_t* tbl, int64_t tbl_stride,
-                             const uint8_t* onehot_off, int flags, int mode,
+                             const uint8_t* onehot_off, const void* plan, int64_t plan_cap, int flags, int mode,
                              void* ws, size_t ws_bytes, mm3d_stream_t stream) {
   int rc = check_conv_args(in, out, weight, tbl, n_in, n_out, c_in, c_out, K, tbl_stride, onehot_off);
   if (rc) return rc;
@@ -78,12 +78,13 @@ extern "C" int mm3d_conv_fwd(const float* in, int64_t n_in, int c_in, float* out
       return mm3d_conv_fwd_simt(in, n_in, c_in, out, n_out, c_out, weight, K, tbl, tbl_stride, onehot_off, flags,
                                 ws, ws_bytes, (cudaStream_t)stream);
     case MM3D_MODE_TF32:
-      // rows that are not whole 16-byte chunks (the 3-channel stem) stay on the FP32 SIMT kernel
+      // rows that are not whole 64-byte pieces (an unpadded 3-channel stem) stay on the FP32 SIMT kernel
       if (!mm3d_conv_tc_supported(c_in, c_out, K))
         return mm3d_conv_fwd_simt(in, n_in, c_in, out, n_out, c_out, weight, K, tbl, tbl_stride, onehot_off, flags,
                                   ws, ws_bytes, (cudaStream_t)stream);
-      return mm3d_conv_fwd_tc(in, n_in, c_in, out, n_out, c_out, weight, K, tbl, tbl_stride, onehot_off, flags,
-                              ws, ws_bytes, (cudaStream_t)stream);
+      MM3D_REQUIRE(plan, MM3D_ERR_INVALID, "mm3d_conv_fwd: tf32 mode needs the table's row plan (mm3d_build_plan)");
+      return mm3d_conv_fwd_tc(in, n_in, c_in, out, n_out, c_out, weight, K, plan, plan_cap, flags, ws, ws_bytes,
+                              (cudaStream_t)stream);
     default:
       MM3D_REQUIRE(false, MM3D_ERR_UNSUPPORTED, "conv mode %d not implemented in this build", mode);
   }
@@ -91,16 +92,18 @@ extern "C" int mm3d_conv_fwd(const float* in, int64_t n_in, int c_in, float* out
 
 extern "C" int mm3d_conv_wgrad(const float* in, int64_t n_in, int c_in, const float* d_out, int64_t n_out,
                                int c_out, float* d_weight, int K, const int32_t* tbl, int64_t tbl_stride,
-                               const uint8_t* onehot_off, int accumulate, int mode,
+                               const uint8_t* onehot_off, const void* plan, int64_t plan_cap, int accumulate, int mode,
                                void* ws, size_t ws_bytes, mm3d_stream_t stream) {
   (void)ws; (void)ws_bytes;
   int rc = check_conv_args(in, d_out, d_weight, tbl, n_in, n_out, c_in, c_out, K, tbl_stride, onehot_off);
   if (rc) return rc;
   switch (mode) {
     case MM3D_MODE_TF32:
-      if (mm3d_conv_wgrad_tc_supported(c_in, c_out, K))
-        return mm3d_conv_wgrad_tc(in, n_in, c_in, d_out, n_out, c_out, d_weight, K, tbl, tbl_stride, onehot_off,
-                                  accumulate, (cudaStream_t)stream);
+      if (mm3d_conv_wgrad_tc_supported(c_in, c_out, K)) {
+        MM3D_REQUIRE(plan, MM3D_ERR_INVALID, "mm3d_conv_wgrad: tf32 mode needs the table's row plan (mm3d_build_plan)");
+        return mm3d_conv_wgrad_tc(in, n_in, c_in, d_out, n_out, c_out, d_weight, K, plan, plan_cap, accumulate,
+                                  (cudaStream_t)stream);
+      }
       // fall through: shapes the tcgen05 kernel does not take (the 3-channel stem) use the FP32 kernel
     case MM3D_MODE_FP32:
       return mm3d_conv_wgrad_simt(in, n_in, c_in, d_out, n_out, c_out, d_weight, K, tbl, tbl_stride, onehot_off,

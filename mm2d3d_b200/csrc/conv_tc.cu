@@ -1,32 +1,29 @@
-// tcgen05 / TMEM rule-table convolution (forward and dgrad) for sm_100a.
+// tcgen05 / TMEM rule-table convolution (forward and dgrad) for sm_100a, driven by a row plan.
 //
-//   out[j,:] = sum_k in[tbl(j,k),:] . W'[k]          j in a tile of 128 output rows
+//   out[j,:] = sum_k in[tbl(j,k),:] . W'[k]          j in a tile of 128 output rows (plan.cuh)
 //
-// Output-stationary implicit GEMM.  A CTA owns 128 output rows; the reduction dimension is the
-// "virtual K" = (kernel offset k, input channel ci) flattened, cut into K-blocks of 32 tf32
-// (= one 128-byte shared-memory row).  For every K-block the 128 gathered rows (zero where the
+// Output-stationary implicit GEMM with block-sparse K.  A CTA owns tiles of 128 output rows in
+// plan order; the reduction runs over the tile's NON-EMPTY offsets only (tile_mask), each offset
+// cut into K-blocks of 32 input channels (= one 128-byte shared-memory row; the last block of an
+// offset may be 16 channels wide).  For every K-block the 128 gathered rows (zero where the
 // neighbour is absent) form a K-major SWIZZLE_128B tile that tcgen05.mma (M=128, N=C_out,
-// kind::tf32) multiplies with the matching block of the pre-swizzled weight image, accumulating
-// ALL offsets in one TMEM accumulator.  No atomics, no read-modify-write of `out`, each output row
-// stored once: deterministic.  Packing offsets back to back along K means a 16-channel layer needs
-// 14 K-blocks instead of 27 and no layer pays per-offset padding.
+// kind::tf32) multiplies with the matching block of the pre-swizzled weight image, accumulating all
+// offsets of the tile in one TMEM accumulator.  No atomics, no read-modify-write of `out`, each
+// output row stored once; the result does not depend on which rows share a tile.
 //
-// Warp roles ((S+5) warps):   warps 0..S-1    gather producers, warp w OWNS ring stage w (tc_gather.cuh)
-//                                             and bulk-copies that K-block's weight block (cp.async.bulk)
-//                             warps S..S+3    epilogue (TMEM lanes 32(w&3).. -> registers -> global)
+// Warp roles ((S+5) warps):   warps 0..S-1    gather producers, warp w OWNS ring stage w: 16-byte
+//                                             cp.async per (row, chunk), zero fill for absent rows,
+//                                             plus the bulk copy of the K-block's weight block
+//                             warps S..S+3    epilogue (TMEM lanes -> registers -> out[perm[row]])
 //                             warp  S+4       MMA issuer (one lane) + TMEM allocator
 // Pipelines (mbarriers):      ring     a_full[S] (32 cp.async arrivals + expect_tx of the weight block)
-//                                      / a_empty[S] (tcgen05.commit): ONE wait and ONE commit per K-block,
-//                                      because the single MMA-issuing thread is the serial resource
+//                                      / a_empty[S] (tcgen05.commit)
 //                             accum    acc_full[2] (tcgen05.commit)       / acc_empty[2] (128 arrivals)
 // The accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the MMAs of i+1.
-//
-// Absent neighbours cost neither instructions nor shared-memory traffic beyond one coalesced table
-// read per 32 rows: stages are zeroed once, the producer compacts the rows that need an action and
-// re-zeroes (cp.async with src-size 0) only slots that held data the last time the stage was used.
 #include <stdlib.h>
 
-#include "tc_gather.cuh"
+#include "plan.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -35,37 +32,43 @@ using namespace tc;
 constexpr int kTileM = 128;
 constexpr int kKBlock = 32;                 // tf32 elements per 128-byte row of a K-block
 constexpr int kStageBytes = kTileM * 128;   // one A stage = one K-block of 128 rows = 16 KB
+constexpr int kEntBytes = kTileM * 4;       // the K-block's 128 table entries
 constexpr int kEpilogue = 128;
 constexpr int kMaxStages = 6;
-constexpr int kMaxK = 27;
+constexpr int kMaxThreads = (kMaxStages + 5) * 32;
 
 struct TcParams {
-  GatherArgs ga;
+  const float* in;
   float* out;
-  const float* wimg;  // [kbt][n_pad][32] tf32, rows 128-byte swizzled
-  int c_out;
-  int kbt;            // K-blocks per tile = ceil(K * cq / 8)
-  int n_pad, num_tiles, b_stages, tmem_cols;
+  const float* wimg;  // [K][nb][n_pad][32] tf32, rows 128-byte swizzled
+  const int32_t* perm;
+  const uint32_t* tile_mask;
+  const int32_t* tbl;
+  int64_t tstride;
+  int c_in, c_out, K;
+  int nb;       // K-blocks per offset = ceil(c_in / 32)
+  int last_w;   // 16-byte chunks of an offset's last block (8, or 4 when c_in % 32 == 16)
+  int S;        // ring stages = producer warps
+  int n_pad, num_tiles, tmem_cols;
   int* err;
-  long long* trace;  // debug: MMA-thread timestamps of CTA 0 (4 per item), or NULL
 };
 
-// Weight image: one [n_pad][32] block per K-block; element (n, e) of block kb is Wsel(k)[ci][n]
-// with (k, ci) = divmod(kb*32 + e, c_in) (0 beyond the virtual K / c_out), tf32-rounded, and the
-// 16-byte chunks of every 128-byte row XOR-swizzled with (n & 7): exactly the bytes a SWIZZLE_128B
-// K-major B tile has in shared memory, so the kernel bulk-copies it verbatim.
-__global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ img, int K, int c_in, int c_out,
-                               int kbt, int n_pad, int transposed, int mirror) {
-  const int64_t total = (int64_t)kbt * n_pad * kKBlock;
+// Weight image: one [n_pad][32] block per (offset, channel block); element (n, e) of block (k, j) is
+// Wsel(k)[32 j + e][n] (0 beyond c_in / c_out), tf32-rounded, the 16-byte chunks of every 128-byte
+// row XOR-swizzled with (n & 7): exactly the bytes a SWIZZLE_128B K-major B tile has in shared
+// memory, so the kernel bulk-copies it verbatim.
+__global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ img, int K, int c_in, int c_out, int nb,
+                               int n_pad, int transposed, int mirror) {
+  const int64_t total = (int64_t)K * nb * n_pad * kKBlock;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int e_sw = (int)(i % kKBlock);
     const int n = (int)((i / kKBlock) % n_pad);
-    const int kb = (int)(i / ((int64_t)kKBlock * n_pad));
+    const int blk = (int)(i / ((int64_t)kKBlock * n_pad));
+    const int k = blk / nb, j = blk - k * nb;
     const int chunk = (e_sw >> 2) ^ (n & 7);  // un-swizzle: which logical chunk lives here
-    const int vk = kb * kKBlock + chunk * 4 + (e_sw & 3);
-    const int k = vk / c_in, ci = vk - k * c_in;
+    const int ci = j * kKBlock + chunk * 4 + (e_sw & 3);
     float v = 0.f;
-    if (k < K && n < c_out) {
+    if (ci < c_in && n < c_out) {
       const int ks = mirror ? K - 1 - k : k;
       v = transposed ? __ldg(w + ((int64_t)ks * c_out + n) * c_in + ci)   // forward weight is [K][c_out][c_in]
                      : __ldg(w + ((int64_t)ks * c_in + ci) * c_out + n);  // [K][c_in][c_out]
@@ -74,20 +77,45 @@ __global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ 
   }
 }
 
-template <int S, bool ONEHOT>
-__global__ void __launch_bounds__((S + 5) * 32, 1)
+// Walks the CTA's items in order: tiles blockIdx.x, +gridDim.x, ...; per tile the set bits of its
+// mask (ascending offset); per offset the nb channel blocks.  Every role runs its own copy.
+struct ItemWalk {
+  const uint32_t* tile_mask;
+  int num_tiles, step, nb;
+  int tile, k, j;
+  uint32_t rem;
+  __device__ __forceinline__ void init(const TcParams& p) {
+    tile_mask = p.tile_mask; num_tiles = p.num_tiles; step = (int)gridDim.x; nb = p.nb;
+    tile = (int)blockIdx.x; j = 0; rem = 0; k = 0;
+    if (tile < num_tiles) { rem = __ldg(tile_mask + tile); k = __ffs(rem) - 1; }
+  }
+  __device__ __forceinline__ bool valid() const { return tile < num_tiles; }
+  __device__ __forceinline__ void next() {
+    if (++j < nb) return;
+    j = 0;
+    rem &= rem - 1;
+    if (rem) { k = __ffs(rem) - 1; return; }
+    tile += step;
+    if (tile < num_tiles) { rem = __ldg(tile_mask + tile); k = __ffs(rem) - 1; }
+  }
+  // true when the current item is the last of its tile
+  __device__ __forceinline__ bool last_of_tile() const { return j == nb - 1 && (rem & (rem - 1)) == 0; }
+};
+
+__global__ void __launch_bounds__(kMaxThreads, 1)
 k_conv_tc(const TcParams p) {
-  constexpr int kThreads = (S + 5) * 32;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A stages][B stages][producer lists][barriers][tmem ptr][abort]
+  const int S = p.S;
+  const int nthreads = (S + 5) * 32;
+  // carve: [A stages][B stages][entry rows][barriers][tmem ptr][abort]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t b_bytes = (uint32_t)p.n_pad * 128u;
   const uint32_t b_stride = (b_bytes + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + (uint32_t)S * kStageBytes;
-  const uint32_t l_base = b_base + (uint32_t)S * b_stride;  // one weight block per A stage
-  const uint32_t bar_base = l_base + (uint32_t)S * kListBytes;
+  const uint32_t e_base = b_base + (uint32_t)S * b_stride;  // one weight block and one entry row per A stage
+  const uint32_t bar_base = e_base + (uint32_t)S * kEntBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar_base - smem_base));
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(kMaxStages + s); };
@@ -100,8 +128,6 @@ k_conv_tc(const TcParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- one-time setup
-  for (uint32_t i = threadIdx.x; i < (uint32_t)S * kStageBytes / 16; i += kThreads)
-    reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(a_full(s), 33);  // 32 cp.async arrivals (gathered rows) + 1 expect_tx arrival (weight block)
@@ -115,38 +141,66 @@ k_conv_tc(const TcParams p) {
     fence_barrier_init();
   }
   if (warp == S + 4) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
-  fence_proxy_async();  // the zero fill must be visible to the tensor core's (async-proxy) reads
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  (void)nthreads;
 
   if (warp < S) {
     // =================================================================== gather producer: owns stage `warp`
     const uint32_t stage = a_base + (uint32_t)warp * kStageBytes;
-    const uint32_t list = l_base + (uint32_t)warp * kListBytes;
-    uint32_t filled = 0, round = 0;
-    int lt = 0, kb = warp;  // item = (lt-th tile of this CTA, K-block kb); this warp takes every S-th item
-    while (kb >= p.kbt) { kb -= p.kbt; ++lt; }
-    int tile = blockIdx.x + lt * gridDim.x;
-    int nbv[4 * kMaxSegs];
-    load_entries<ONEHOT>(p.ga, tile < p.num_tiles, (int64_t)tile * kTileM, kb, lane, nbv);
-    while (tile < p.num_tiles) {
-      int n_kb = kb + S, n_lt = lt;
-      while (n_kb >= p.kbt) { n_kb -= p.kbt; ++n_lt; }
-      const int n_tile = blockIdx.x + n_lt * gridDim.x;
-      int nbn[4 * kMaxSegs];  // the next item's table entries are in flight while this one is copied
-      load_entries<ONEHOT>(p.ga, n_tile < p.num_tiles, (int64_t)n_tile * kTileM, n_kb, lane, nbn);
-      const int cnt = build_list(p.ga, kb, lane, nbv, filled, list);  // off the stage's critical path
+    const uint32_t ent = e_base + (uint32_t)warp * kEntBytes;
+    ItemWalk it;
+    it.init(p);
+    for (int i = 0; i < warp && it.valid(); ++i) it.next();  // this warp takes every S-th item
+    uint32_t round = 0;
+    int4 e = make_int4(-1, -1, -1, -1);  // entries of rows 4*lane .. 4*lane+3 of the current item
+    if (it.valid()) e = __ldg(reinterpret_cast<const int4*>(p.tbl + (int64_t)it.k * p.tstride + (int64_t)it.tile * kTileM) + lane);
+    while (it.valid()) {
+      const int k = it.k, j = it.j;
+      for (int i = 0; i < S && it.valid(); ++i) it.next();
+      int4 en = make_int4(-1, -1, -1, -1);  // the next item's entries are in flight while this one is copied
+      if (it.valid()) en = __ldg(reinterpret_cast<const int4*>(p.tbl + (int64_t)it.k * p.tstride + (int64_t)it.tile * kTileM) + lane);
       if (!mbar_wait(a_empty(warp), (round & 1u) ^ 1u, abort_flag)) goto done;
       if (lane == 0) {  // this K-block's weight block rides on the same barrier as the gathered rows
         mbar_arrive_expect_tx(a_full(warp), b_bytes);
-        bulk_g2s(b_base + (uint32_t)warp * b_stride, p.wimg + (size_t)kb * p.n_pad * kKBlock, b_bytes, a_full(warp));
+        bulk_g2s(b_base + (uint32_t)warp * b_stride, p.wimg + ((size_t)k * p.nb + j) * p.n_pad * kKBlock, b_bytes, a_full(warp));
       }
-      issue_copies<false>(p.ga, stage, lane, cnt, list, a_full(warp));
-#pragma unroll
-      for (int i = 0; i < 4 * kMaxSegs; ++i) nbv[i] = nbn[i];
-      kb = n_kb; lt = n_lt; tile = n_tile;
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ent + (uint32_t)lane * 16u), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w) : "memory");
+      __syncwarp();
+      const float* src0 = p.in + j * kKBlock;
+      const bool half = (j == p.nb - 1) && p.last_w == 4;
+      if (!half) {
+        // 8 lanes per row (one per 16-byte chunk), 4 rows per pass: a full 128-byte line per row
+        const int c = lane & 7, rsub = lane >> 3;
+        const float* srcc = src0 + c * 4;
+#pragma unroll 8
+        for (int r0 = 0; r0 < kTileM; r0 += 4) {
+          const int r = r0 + rsub;
+          int nb_row;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nb_row) : "r"(ent + (uint32_t)r * 4u) : "memory");
+          const uint32_t dst = stage + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+          const bool ok = nb_row >= 0;
+          cp_async16(dst, ok ? srcc + (size_t)(uint32_t)nb_row * (uint32_t)p.c_in : p.in, ok ? 16u : 0u);
+        }
+      } else {
+        // 16-channel tail block: 4 lanes per row, 8 rows per pass; chunks 4..7 are never read by the MMA
+        const int c = lane & 3, rsub = lane >> 2;
+        const float* srcc = src0 + c * 4;
+#pragma unroll 8
+        for (int r0 = 0; r0 < kTileM; r0 += 8) {
+          const int r = r0 + rsub;
+          int nb_row;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nb_row) : "r"(ent + (uint32_t)r * 4u) : "memory");
+          const uint32_t dst = stage + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+          const bool ok = nb_row >= 0;
+          cp_async16(dst, ok ? srcc + (size_t)(uint32_t)nb_row * (uint32_t)p.c_in : p.in, ok ? 16u : 0u);
+        }
+      }
+      cp_async_arrive(a_full(warp));
+      __syncwarp();  // the entry row is rewritten by the next item
+      e = en;
       ++round;
     }
   } else if (warp < S + 4) {
@@ -155,23 +209,23 @@ k_conv_tc(const TcParams p) {
     uint32_t tile_iter = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
       const int ab = (int)(tile_iter & 1u);
+      const int row = __ldg(p.perm + (int64_t)tile * kTileM + ew * 32 + lane);
       if (!mbar_wait(acc_full(ab), (tile_iter >> 1) & 1u, abort_flag)) goto done;
       tc_fence_after();
-      const int64_t row = (int64_t)tile * kTileM + ew * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * p.n_pad);
       for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
         float acc[16];
         tmem_ld16(taddr + (uint32_t)c0, acc);
-        if (row < p.ga.n_out) {
-          float* dst = p.out + row * p.c_out + c0;
+        if (row >= 0) {
+          float* dst = p.out + (int64_t)row * p.c_out + c0;
           if ((p.c_out & 3) == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              if (c0 + j < p.c_out) *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            for (int jj = 0; jj < 16; jj += 4)
+              if (c0 + jj < p.c_out) *reinterpret_cast<float4*>(dst + jj) = make_float4(acc[jj], acc[jj + 1], acc[jj + 2], acc[jj + 3]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c0 + j < p.c_out) dst[j] = acc[j];
+            for (int jj = 0; jj < 16; ++jj)
+              if (c0 + jj < p.c_out) dst[jj] = acc[jj];
           }
         }
       }
@@ -182,31 +236,36 @@ k_conv_tc(const TcParams p) {
     // =================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(kTileM, p.n_pad);
-      uint32_t it = 0, tile_iter = 0;
-      bool ok = true;
-      for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++tile_iter) {
+      ItemWalk it;
+      it.init(p);
+      uint32_t tile_iter = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      while (it.valid()) {
         const int ab = (int)(tile_iter & 1u);
         if (!mbar_wait(acc_empty(ab), ((tile_iter >> 1) & 1u) ^ 1u, abort_flag)) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.n_pad);
-        for (int kb = 0; kb < p.kbt; ++kb, ++it) {
-          const int s = (int)(it % (uint32_t)S);
-          const bool tr = p.trace && blockIdx.x == 0 && it < 512;
-          if (tr) p.trace[4 * it + 0] = p.trace[4 * it + 1] = clock64();
-          if (!mbar_wait(a_full(s), (it / (uint32_t)S) & 1u, abort_flag)) { ok = false; break; }
-          if (tr) p.trace[4 * it + 2] = clock64();
+        bool first = true, ok = true;
+        while (true) {
+          const bool last = it.last_of_tile();
+          const int ksteps = (it.j == p.nb - 1 ? p.last_w : 8) >> 1;
+          if (!mbar_wait(a_full(s), ph, abort_flag)) { ok = false; break; }
           tc_fence_after();
-          const int rem = p.ga.nq * 4 - kb * kKBlock;  // virtual-K elements left
-          const int ksteps = rem >= kKBlock ? kKBlock / 8 : (rem + 7) >> 3;
           const uint32_t a_addr = a_base + (uint32_t)s * kStageBytes;
           const uint32_t b_addr = b_base + (uint32_t)s * b_stride;
           for (int ks = 0; ks < ksteps; ++ks)
             umma_tf32(d_tmem, make_desc_sw128(a_addr + ks * 32), make_desc_sw128(b_addr + ks * 32), idesc,
-                      (kb | ks) != 0);
+                      (!first || ks != 0) ? 1u : 0u);
           umma_commit(a_empty(s));  // frees the stage and its weight block
-          if (tr) p.trace[4 * it + 3] = clock64();
+          first = false;
+          if (++s == S) { s = 0; ph ^= 1u; }
+          it.next();
+          if (last) break;
         }
-        if (ok) umma_commit(acc_full(ab));
+        if (!ok) break;
+        umma_commit(acc_full(ab));
+        ++tile_iter;
       }
     }
   }
@@ -227,54 +286,27 @@ int pow2_cols(int n) {
   return c;
 }
 
-template <int S, bool ONEHOT>
-int launch_conv_tc(const TcParams& p, size_t smem, cudaStream_t stream) {
-  constexpr int kThreads = (S + 5) * 32;
-  static int regs = 0;
-  if (!regs) {
-    MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc<S, ONEHOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc<S, ONEHOT>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   cudaSharedmemCarveoutMaxShared));
-    cudaFuncAttributes fa;
-    MM3D_CUDA(cudaFuncGetAttributes(&fa, k_conv_tc<S, ONEHOT>));
-    regs = fa.numRegs > 0 ? fa.numRegs : 64;
-  }
-  // persistent CTAs: as many as fit (registers, shared memory, threads, TMEM columns); tiles round-robin
-  const int regs_alloc = (regs + 7) / 8 * 8;
-  int per_sm = 65536 / (regs_alloc * kThreads);
-  const int by_smem = (int)((227 * 1024) / (smem + 1024));
-  const int by_tmem = 512 / p.tmem_cols;
-  if (per_sm > by_smem) per_sm = by_smem;
-  if (per_sm > 2048 / kThreads) per_sm = 2048 / kThreads;
-  if (per_sm > by_tmem) per_sm = by_tmem;
-  if (per_sm < 1) per_sm = 1;
-  int grid = MM3D_NUM_SMS * per_sm;
-  if (grid > p.num_tiles) grid = p.num_tiles;
-  k_conv_tc<S, ONEHOT><<<grid, kThreads, smem, stream>>>(p);
-  return MM3D_OK;
-}
-
 }  // namespace
 
 // ---- host entry points used by capi.cu -------------------------------------------------------
 
-static int tc_geometry(int c_in, int c_out, int K, int* kbt, int* n_pad) {
-  *kbt = (K * (c_in / 4) + 7) / 8;
+static int tc_geometry(int c_in, int c_out, int K, int* nb, int* n_pad) {
+  *nb = (c_in + 31) / 32;
   *n_pad = (c_out + 15) / 16 * 16;
-  // input rows must be whole 16-byte chunks, at least 4 of them (at most 3 segments per K-block)
-  return (*n_pad <= 256 && (c_in % 4) == 0 && c_in >= 16 && K <= kMaxK) ? 0 : 1;
+  // input rows are cut into 128-byte blocks with an optional 64-byte tail
+  return (*n_pad <= 256 && (c_in % 16) == 0 && K <= 32) ? 0 : 1;
 }
 
 // 1 when the tcgen05 kernel handles this shape
 int mm3d_conv_tc_supported(int c_in, int c_out, int K) {
-  int kbt, n_pad;
-  return tc_geometry(c_in, c_out, K, &kbt, &n_pad) == 0;
+  int nb, n_pad;
+  return tc_geometry(c_in, c_out, K, &nb, &n_pad) == 0;
 }
 
 size_t mm3d_conv_tc_workspace_bytes(int c_in, int c_out, int K) {
-  int kbt, n_pad;
-  if (tc_geometry(c_in, c_out, K, &kbt, &n_pad)) return 0;
-  return mm3d_align((size_t)kbt * n_pad * 128);  // weight image
+  int nb, n_pad;
+  if (tc_geometry(c_in, c_out, K, &nb, &n_pad)) return 0;
+  return mm3d_align((size_t)K * nb * n_pad * 128);  // weight image
 }
 
 // Sticky per-device error flag set by a kernel whose mbarrier pipeline timed out (never in a
@@ -302,13 +334,14 @@ extern "C" int mm3d_take_device_error(void) {
 }
 
 int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
-                     const float* weight, int K, const int32_t* tbl, int64_t tbl_stride,
-                     const uint8_t* onehot_off, int flags, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  int kbt, n_pad;
-  MM3D_REQUIRE(tc_geometry(c_in, c_out, K, &kbt, &n_pad) == 0, MM3D_ERR_UNSUPPORTED,
+                     const float* weight, int K, const void* plan, int64_t plan_cap, int flags, void* ws,
+                     size_t ws_bytes, cudaStream_t stream) {
+  int nb, n_pad;
+  MM3D_REQUIRE(tc_geometry(c_in, c_out, K, &nb, &n_pad) == 0, MM3D_ERR_UNSUPPORTED,
                "tcgen05 conv: unsupported shape c_in %d c_out %d K %d", c_in, c_out, K);
   MM3D_REQUIRE(n_out < (1ll << 31) && n_in * (int64_t)c_in < (1ll << 32), MM3D_ERR_UNSUPPORTED,
                "tcgen05 conv: tensor too large for 32-bit element offsets");
+  MM3D_REQUIRE(plan && plan_cap >= n_out, MM3D_ERR_INVALID, "tcgen05 conv: needs a row plan covering n_out rows");
   MM3D_REQUIRE(ws && ws_bytes >= mm3d_conv_tc_workspace_bytes(c_in, c_out, K), MM3D_ERR_WORKSPACE,
                "tcgen05 conv: workspace too small");
   MM3D_REQUIRE((((uintptr_t)in | (uintptr_t)out | (uintptr_t)ws) & 15) == 0, MM3D_ERR_INVALID,
@@ -318,30 +351,47 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
   if (n_out == 0) return MM3D_OK;
 
   float* wimg = (float*)ws;
-  k_weight_image<<<mm3d_grid((int64_t)kbt * n_pad * kKBlock, 256), 256, 0, stream>>>(weight, wimg, K, c_in, c_out, kbt,
-                                                                                 n_pad, tr ? 1 : 0, mir ? 1 : 0);
+  k_weight_image<<<mm3d_grid((int64_t)K * nb * n_pad * kKBlock, 256), 256, 0, stream>>>(weight, wimg, K, c_in, c_out, nb,
+                                                                                    n_pad, tr ? 1 : 0, mir ? 1 : 0);
+  const Mm3dPlanView pv = mm3d_plan_view(plan, plan_cap);
   TcParams p;
-  p.ga = GatherArgs{in, tbl, tbl_stride, onehot_off, (int)n_out, c_in, K, c_in / 4, K * (c_in / 4)};
-  p.out = out; p.wimg = wimg; p.c_out = c_out; p.kbt = kbt; p.n_pad = n_pad;
+  p.in = in; p.out = out; p.wimg = wimg;
+  p.perm = pv.perm; p.tile_mask = pv.tile_mask; p.tbl = pv.tbl; p.tstride = pv.stride;
+  p.c_in = c_in; p.c_out = c_out; p.K = K; p.nb = nb;
+  p.last_w = (c_in % 32) == 16 ? 4 : 8;
+  p.n_pad = n_pad;
   p.num_tiles = (int)mm3d_cdiv(n_out, kTileM);
   p.tmem_cols = pow2_cols(2 * n_pad);
   p.err = mm3d_device_err_flag();
-  {
-    const char* t = getenv("MM3D_TC_TRACE");  // debug: device pointer (decimal) of a 2048-entry int64 buffer
-    p.trace = t ? (long long*)strtoull(t, nullptr, 10) : nullptr;
-  }
   const uint32_t b_stride = ((uint32_t)n_pad * 128u + 1023u) & ~1023u;
-  // narrow N: 3 stages (48 KB + small weight blocks) so that three CTAs share an SM; mid: 4; wide: 6
-  const bool wide = n_pad > 96 && n_pad <= 128, narrow = n_pad <= 32;  // (N > 128: 24-32 KB weight blocks, 4 stages)
-  const int S = wide ? 6 : narrow ? 3 : 4;
-  p.b_stages = S;
-  const size_t smem = 1024 + (size_t)S * kStageBytes + (size_t)S * b_stride + (size_t)S * kListBytes +
-                      8 * (2 * kMaxStages + 4) + 64;
-  int rc;
-  if (wide)        rc = onehot_off ? launch_conv_tc<6, true>(p, smem, stream) : launch_conv_tc<6, false>(p, smem, stream);
-  else if (narrow) rc = onehot_off ? launch_conv_tc<3, true>(p, smem, stream) : launch_conv_tc<3, false>(p, smem, stream);
-  else             rc = onehot_off ? launch_conv_tc<4, true>(p, smem, stream) : launch_conv_tc<4, false>(p, smem, stream);
-  if (rc) return rc;
+  const size_t per_stage = (size_t)kStageBytes + b_stride + kEntBytes;
+  // as many stages as give two CTAs per SM; one CTA per SM when the weight blocks are large
+  int S = (int)((112 * 1024) / per_stage);
+  if (S < 3) S = (int)((224 * 1024) / per_stage);
+  if (S > kMaxStages) S = kMaxStages;
+  p.S = S;
+  const size_t smem = 1024 + (size_t)S * per_stage + 8 * (2 * kMaxStages + 4) + 64;
+  static int regs = 0;
+  if (!regs) {
+    MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    cudaFuncAttributes fa;
+    MM3D_CUDA(cudaFuncGetAttributes(&fa, k_conv_tc));
+    regs = fa.numRegs > 0 ? fa.numRegs : 64;
+  }
+  // persistent CTAs: as many as fit (registers, shared memory, threads, TMEM columns); tiles round-robin
+  const int threads = (S + 5) * 32;
+  const int regs_alloc = (regs + 7) / 8 * 8;
+  int per_sm = 65536 / (regs_alloc * threads);
+  const int by_smem = (int)((227 * 1024) / (smem + 1024));
+  const int by_tmem = 512 / p.tmem_cols;
+  if (per_sm > by_smem) per_sm = by_smem;
+  if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+  if (per_sm > by_tmem) per_sm = by_tmem;
+  if (per_sm < 1) per_sm = 1;
+  int grid = MM3D_NUM_SMS * per_sm;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  k_conv_tc<<<grid, threads, smem, stream>>>(p);
   mm3d_count_launches(2);
   MM3D_CHECK_LAUNCH("mm3d_conv_fwd_tc");
   return MM3D_OK;

@@ -29,6 +29,8 @@ struct LevelMeta {
   const int32_t* parent;
   const uint8_t* off;
   const int32_t* child;
+  const void *plan_smc, *plan_down, *plan_up;  // row plans of the three tables (tensor-core modes)
+  int64_t plan_cap;
 };
 
 struct Bump {
@@ -50,7 +52,7 @@ struct LevelBufs {
 };
 
 struct Net {
-  int L, m, cin, cin_k;  // cin_k = stem input channels as seen by the kernels (padded to 4 in TC modes)
+  int L, m, cin, cin_k;  // cin_k = stem input channels as seen by the kernels (padded to 16 in TC modes)
   int mode;
   std::vector<LevelMeta> lv;
   std::vector<LevelBufs> b;
@@ -159,14 +161,14 @@ enum Kind { SMC, DOWN, UP };
 void conv_fwd(Ctx& c, Kind kind, int l, const float* in, int c_in, float* out, int c_out, const float* w) {
   const LevelMeta& f = c.net->lv[l];
   if (kind == SMC)
-    EX(mm3d_conv_fwd(in, f.n, c_in, out, f.n, c_out, w, 27, f.nbr, f.tstride, nullptr, 0, c.net->mode, c.scratch,
-                     c.scratch_bytes, c.stream));
+    EX(mm3d_conv_fwd(in, f.n, c_in, out, f.n, c_out, w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap, 0,
+                     c.net->mode, c.scratch, c.scratch_bytes, c.stream));
   else if (kind == DOWN)
-    EX(mm3d_conv_fwd(in, f.n, c_in, out, c.net->lv[l + 1].n, c_out, w, 8, f.child, f.tstride, nullptr, 0, c.net->mode,
-                     c.scratch, c.scratch_bytes, c.stream));
+    EX(mm3d_conv_fwd(in, f.n, c_in, out, c.net->lv[l + 1].n, c_out, w, 8, f.child, f.tstride, nullptr, f.plan_down,
+                     f.plan_cap, 0, c.net->mode, c.scratch, c.scratch_bytes, c.stream));
   else
-    EX(mm3d_conv_fwd(in, c.net->lv[l + 1].n, c_in, out, f.n, c_out, w, 8, f.parent, 0, f.off, 0, c.net->mode, c.scratch,
-                     c.scratch_bytes, c.stream));
+    EX(mm3d_conv_fwd(in, c.net->lv[l + 1].n, c_in, out, f.n, c_out, w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap, 0,
+                     c.net->mode, c.scratch, c.scratch_bytes, c.stream));
 }
 // dgrad (d_in from d_out) and wgrad of the same layer; c_in / c_out are the FORWARD layer's
 void conv_bwd(Ctx& c, Kind kind, int l, const float* in, int c_in, const float* d_out, int c_out, const float* w,
@@ -176,20 +178,20 @@ void conv_bwd(Ctx& c, Kind kind, int l, const float* in, int c_in, const float* 
   const int md = c.net->mode;
   if (kind == SMC) {
     if (d_in)
-      EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, f.n, c_in, w, 27, f.nbr, f.tstride, nullptr,
+      EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, f.n, c_in, w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap,
                        MM3D_CONV_TRANSPOSE_W | MM3D_CONV_MIRROR_K, md, c.scratch, c.scratch_bytes, c.stream));
-    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, f.n, c_out, d_w, 27, f.nbr, f.tstride, nullptr, 0, md, c.scratch,
-                       c.scratch_bytes, c.stream));
+    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, f.n, c_out, d_w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap, 0,
+                       md, c.scratch, c.scratch_bytes, c.stream));
   } else if (kind == DOWN) {  // in: fine rows, d_out: coarse rows
-    EX(mm3d_conv_fwd(d_out, nc, c_out, d_in, f.n, c_in, w, 8, f.parent, 0, f.off, MM3D_CONV_TRANSPOSE_W, md, c.scratch,
-                     c.scratch_bytes, c.stream));
-    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, nc, c_out, d_w, 8, f.child, f.tstride, nullptr, 0, md, c.scratch,
-                       c.scratch_bytes, c.stream));
+    EX(mm3d_conv_fwd(d_out, nc, c_out, d_in, f.n, c_in, w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap,
+                     MM3D_CONV_TRANSPOSE_W, md, c.scratch, c.scratch_bytes, c.stream));
+    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, nc, c_out, d_w, 8, f.child, f.tstride, nullptr, f.plan_down, f.plan_cap, 0,
+                       md, c.scratch, c.scratch_bytes, c.stream));
   } else {  // UP: in: coarse rows, d_out: fine rows
-    EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, nc, c_in, w, 8, f.child, f.tstride, nullptr, MM3D_CONV_TRANSPOSE_W, md,
-                     c.scratch, c.scratch_bytes, c.stream));
-    EX(mm3d_conv_wgrad(in, nc, c_in, d_out, f.n, c_out, d_w, 8, f.parent, 0, f.off, 0, md, c.scratch, c.scratch_bytes,
-                       c.stream));
+    EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, nc, c_in, w, 8, f.child, f.tstride, nullptr, f.plan_down, f.plan_cap,
+                     MM3D_CONV_TRANSPOSE_W, md, c.scratch, c.scratch_bytes, c.stream));
+    EX(mm3d_conv_wgrad(in, nc, c_in, d_out, f.n, c_out, d_w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap, 0, md,
+                       c.scratch, c.scratch_bytes, c.stream));
   }
 }
 
@@ -279,13 +281,14 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
 int fill_net(Net& net, int in_channels, int m, int num_planes, int mode, const int64_t* level_desc, int64_t n_points) {
   MM3D_REQUIRE(num_planes >= 1 && num_planes <= 16 && m > 0 && in_channels > 0, MM3D_ERR_INVALID, "bad network shape");
   net.L = num_planes; net.m = m; net.cin = in_channels; net.mode = mode; net.n_points = n_points;
-  // tensor-core kernels gather whole 16-byte pieces of rows of >= 16 channels: pad the stem input
+  // tensor-core kernels gather rows in 64-byte pieces: pad the stem input to a multiple of 16 channels
   net.cin_k = in_channels;
-  if (mode != MM3D_MODE_FP32 && ((in_channels & 3) || in_channels < 16)) net.cin_k = in_channels < 16 ? 16 : (in_channels + 3) / 4 * 4;
+  if (mode != MM3D_MODE_FP32) net.cin_k = (in_channels + 15) / 16 * 16;
   net.lv.resize(num_planes);
   for (int l = 0; l < num_planes; ++l) {
-    const int64_t* d = level_desc + 6 * l;
-    net.lv[l] = LevelMeta{d[0], (const int32_t*)d[1], d[2], (const int32_t*)d[3], (const uint8_t*)d[4], (const int32_t*)d[5]};
+    const int64_t* d = level_desc + MM3D_LEVEL_DESC_WORDS * l;
+    net.lv[l] = LevelMeta{d[0], (const int32_t*)d[1], d[2], (const int32_t*)d[3], (const uint8_t*)d[4], (const int32_t*)d[5],
+                          (const void*)d[6], (const void*)d[7], (const void*)d[8], d[9]};
   }
   return MM3D_OK;
 }
@@ -313,7 +316,8 @@ size_t bwd_temp_bytes(const Net& net) {
 
 extern "C" {
 
-// level_desc: 6 int64 per level = {n rows, nbr table ptr, table stride, parent ptr, off ptr, child ptr}
+// level_desc: MM3D_LEVEL_DESC_WORDS int64 per level = {n rows, nbr table ptr, table stride, parent ptr, off ptr,
+// child ptr, plan of the 3^3 table, plan of the child table, plan of the (parent, off) table, plan capacity}
 MM3D_API int64_t mm3d_unet_num_params(int num_planes) { return 1 + level_slots(0, num_planes) + 4; }
 
 MM3D_API size_t mm3d_unet_act_bytes(int in_channels, int m, int num_planes, int mode, const int64_t* level_desc,
@@ -334,7 +338,7 @@ MM3D_API size_t mm3d_unet_bwd_bytes(int in_channels, int m, int num_planes, int 
 
 MM3D_API size_t mm3d_unet_scratch_bytes(int in_channels, int m, int num_planes, int mode) {
   size_t best = mm3d_bnrelu_workspace_bytes(2 * m * num_planes);
-  const int cin_k = in_channels < 16 ? 16 : (in_channels + 3) / 4 * 4;
+  const int cin_k = (in_channels + 15) / 16 * 16;
   size_t s = mm3d_conv_workspace_bytes(0, 0, cin_k, m, 27, mode);
   if (s > best) best = s;
   for (int l = 0; l < num_planes; ++l) {

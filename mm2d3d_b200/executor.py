@@ -52,19 +52,25 @@ def fusable(net) -> bool:
     return True
 
 
-def _level_desc(meta: Metadata, num_planes: int, spatial0: int):
-    desc = (C.c_int64 * (6 * num_planes))()
+def _level_desc(meta: Metadata, num_planes: int, spatial0: int, plans: bool):
+    W = _lib.LEVEL_DESC_WORDS
+    desc = (C.c_int64 * (W * num_planes))()
     s = spatial0
     for l in range(num_planes):
         lv = meta.nbr(s)
-        desc[6 * l + 0] = lv.n
-        desc[6 * l + 1] = lv.ptr(lv.o_nbr)
-        desc[6 * l + 2] = lv.tstride
+        desc[W * l + 0] = lv.n
+        desc[W * l + 1] = lv.ptr(lv.o_nbr)
+        desc[W * l + 2] = lv.tstride
+        if plans:
+            desc[W * l + 6], desc[W * l + 9] = meta.plan("smc", s)
         if l + 1 < num_planes:
             fine, _ = meta.down(s)
-            desc[6 * l + 3] = fine.ptr(fine.o_parent)
-            desc[6 * l + 4] = fine.ptr(fine.o_off)
-            desc[6 * l + 5] = fine.ptr(fine.o_child)
+            desc[W * l + 3] = fine.ptr(fine.o_parent)
+            desc[W * l + 4] = fine.ptr(fine.o_off)
+            desc[W * l + 5] = fine.ptr(fine.o_child)
+            if plans:
+                desc[W * l + 7] = meta.plan("down", s)[0]
+                desc[W * l + 8] = meta.plan("up", s)[0]
         s //= 2
     return desc
 
@@ -76,7 +82,7 @@ class UNetSCNFn(torch.autograd.Function):
         feats = feats.float().contiguous()
         dev = feats.device
         n_points = meta.n_points
-        desc = _level_desc(meta, L, spatial0)
+        desc = _level_desc(meta, L, spatial0, plans=mode != _lib.MODE_FP32)
         with torch.cuda.device(dev):
             act_bytes = lib.mm3d_unet_act_bytes(in_ch, m, L, mode, desc, n_points)
             act = torch.empty(act_bytes, dtype=torch.uint8, device=dev)

@@ -100,14 +100,16 @@ class OutputLayerFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------- convolutions
 class _Table:
     """Rule table of one convolution direction, in C-ABI terms."""
-    __slots__ = ("tbl", "stride", "onehot", "n_in", "n_out", "K")
+    __slots__ = ("tbl", "stride", "onehot", "n_in", "n_out", "K", "plan", "plan_cap")
 
-    def __init__(self, tbl, stride, onehot, n_in, n_out, K):
+    def __init__(self, tbl, stride, onehot, n_in, n_out, K, plan=(None, 0)):
         self.tbl, self.stride, self.onehot, self.n_in, self.n_out, self.K = tbl, stride, onehot, n_in, n_out, K
+        self.plan, self.plan_cap = plan
 
 
-def conv_tables(meta, kind: str, spatial_in: int):
-    """(forward table, dgrad table, dgrad flags) of a layer applied at ``spatial_in``.
+def conv_tables(meta, kind: str, spatial_in: int, plans: bool = False):
+    """(forward table, dgrad table, dgrad flags) of a layer applied at ``spatial_in``; with ``plans`` the
+    tables carry their row plans (tensor-core modes).
 
     smc : out rows = in rows, table = 3^3 neighbours; dgrad = same table, W^T with mirrored offsets.
     down: out rows = coarse, table = children [8];   dgrad = one-hot (parent, off) over fine rows, W^T.
@@ -115,16 +117,20 @@ def conv_tables(meta, kind: str, spatial_in: int):
     """
     if kind == "smc":
         lv = meta.nbr(spatial_in)
-        t = _Table(lv.ptr(lv.o_nbr), lv.tstride, None, lv.n, lv.n, 27)
+        t = _Table(lv.ptr(lv.o_nbr), lv.tstride, None, lv.n, lv.n, 27,
+                   meta.plan("smc", spatial_in) if plans else (None, 0))
         return t, t, _lib.CONV_TRANSPOSE_W | _lib.CONV_MIRROR_K
     if kind == "down":
-        fine, coarse = meta.down(spatial_in)
+        s_fine = int(spatial_in)
     elif kind == "up":
-        fine, coarse = meta.down(int(spatial_in) * 2)
+        s_fine = int(spatial_in) * 2
     else:
         raise ValueError(kind)
-    child = _Table(fine.ptr(fine.o_child), fine.tstride, None, fine.n, coarse.n, 8)
-    onehot = _Table(fine.ptr(fine.o_parent), 0, fine.ptr(fine.o_off), coarse.n, fine.n, 8)
+    fine, coarse = meta.down(s_fine)
+    child = _Table(fine.ptr(fine.o_child), fine.tstride, None, fine.n, coarse.n, 8,
+                   meta.plan("down", s_fine) if plans else (None, 0))
+    onehot = _Table(fine.ptr(fine.o_parent), 0, fine.ptr(fine.o_off), coarse.n, fine.n, 8,
+                    meta.plan("up", s_fine) if plans else (None, 0))
     return (child, onehot, _lib.CONV_TRANSPOSE_W) if kind == "down" else (onehot, child, _lib.CONV_TRANSPOSE_W)
 
 
@@ -135,16 +141,16 @@ class TableConvFn(torch.autograd.Function):
         _require_cuda(x, "convolution")
         x, w = _f32c(x), _f32c(weight)
         K, c_in, c_out = w.shape[0], w.shape[-2], w.shape[-1]
-        fwd_t, bwd_t, bwd_flags = conv_tables(meta, kind, spatial_in)
+        m = MODES[mode]
+        fwd_t, bwd_t, bwd_flags = conv_tables(meta, kind, spatial_in, plans=m != _lib.MODE_FP32)
         if x.shape[0] != fwd_t.n_in or x.shape[1] != c_in or K != fwd_t.K:
             raise ValueError(f"{kind} convolution: input {tuple(x.shape)} / weight {tuple(w.shape)} do not match "
                              f"the active set ({fwd_t.n_in} rows, {fwd_t.K} offsets)")
-        m = MODES[mode]
-        # tensor-core modes gather whole 16-byte pieces of rows of >= 16 channels: pad a narrow or odd
-        # channel count (the 3-channel stem) with zero channels instead of using the SIMT kernels
+        # tensor-core modes gather rows in 64-byte pieces: pad an odd channel count (the 3-channel
+        # stem) with zero channels instead of using the SIMT kernels
         pad = 0
         if m != _lib.MODE_FP32:
-            pad = 16 - c_in if c_in < 16 else (-c_in) % 4
+            pad = (-c_in) % 16
         if pad:
             x = torch.nn.functional.pad(x, (0, pad))
             w = torch.nn.functional.pad(w, (0, 0, 0, pad))
@@ -155,8 +161,8 @@ class TableConvFn(torch.autograd.Function):
             wsb = lib.mm3d_conv_workspace_bytes(fwd_t.n_in, fwd_t.n_out, c_in, c_out, K, m)
             ws = scratch(wsb, x.device)
             check(lib.mm3d_conv_fwd(ptr(x), fwd_t.n_in, c_in, ptr(out), fwd_t.n_out, c_out, ptr(w), K, fwd_t.tbl,
-                                    fwd_t.stride, fwd_t.onehot, 0, m, ptr(ws), ws.numel(), _lib.stream_ptr()),
-                  "mm3d_conv_fwd")
+                                    fwd_t.stride, fwd_t.onehot, fwd_t.plan, fwd_t.plan_cap, 0, m, ptr(ws), ws.numel(),
+                                    _lib.stream_ptr()), "mm3d_conv_fwd")
         ctx.save_for_backward(x, w)
         ctx.meta, ctx.tables, ctx.mode, ctx.wshape = meta, (fwd_t, bwd_t, bwd_flags), m, weight.shape
         return out
@@ -177,13 +183,13 @@ class TableConvFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 d_x = torch.empty(bwd_t.n_out, c_in, dtype=torch.float32, device=x.device)
                 check(lib.mm3d_conv_fwd(ptr(d_out), bwd_t.n_in, c_out, ptr(d_x), bwd_t.n_out, c_in, ptr(w), K,
-                                        bwd_t.tbl, bwd_t.stride, bwd_t.onehot, bwd_flags, m, ptr(ws), ws.numel(),
-                                        stream), "mm3d_conv_fwd(dgrad)")
+                                        bwd_t.tbl, bwd_t.stride, bwd_t.onehot, bwd_t.plan, bwd_t.plan_cap, bwd_flags, m,
+                                        ptr(ws), ws.numel(), stream), "mm3d_conv_fwd(dgrad)")
             if ctx.needs_input_grad[1]:
                 d_w = torch.empty(w.shape, dtype=torch.float32, device=x.device)
                 check(lib.mm3d_conv_wgrad(ptr(x), fwd_t.n_in, c_in, ptr(d_out), fwd_t.n_out, c_out, ptr(d_w), K,
-                                          fwd_t.tbl, fwd_t.stride, fwd_t.onehot, 0, m, ptr(ws), ws.numel(), stream),
-                      "mm3d_conv_wgrad")
+                                          fwd_t.tbl, fwd_t.stride, fwd_t.onehot, fwd_t.plan, fwd_t.plan_cap, 0, m, ptr(ws),
+                                          ws.numel(), stream), "mm3d_conv_wgrad")
         if ctx.pad:
             d_x = d_x[:, :c_in - ctx.pad] if d_x is not None else None
             d_w = d_w[..., :c_in - ctx.pad, :] if d_w is not None else None

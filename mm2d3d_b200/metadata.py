@@ -29,7 +29,7 @@ class Level:
     ``n`` = actual row count (host int, known after the build's sync)."""
 
     __slots__ = ("spatial", "cap", "tstride", "n", "buf", "base", "o_keys", "o_hkeys", "o_hvals", "hcap",
-                 "o_nbr", "o_parent", "o_off", "o_child", "has_nbr", "has_down", "count_slot")
+                 "o_nbr", "o_parent", "o_off", "o_child", "has_nbr", "has_down", "count_slot", "plans")
 
     def ptr(self, off):
         return self.base + off
@@ -106,6 +106,7 @@ class Metadata:
         lv.o_nbr, lv.o_parent, lv.o_off, lv.o_child = lay["nbr"], lay["parent"], lay["off"], lay["child"]
         lv.has_nbr = lv.has_down = False
         lv.count_slot = count_slot
+        lv.plans = {}
         return lv
 
     def _count_ptr(self, lv):
@@ -163,6 +164,47 @@ class Metadata:
                 self._build_down(fine, coarse, _lib.stream_ptr())
                 self._sync_counts()
         return fine, self.levels[s // 2]
+
+    def plan(self, kind: str, spatial_size: int):
+        """(device pointer, capacity) of the row plan (``csrc/plan.cuh``) of a rule table, built on first
+        use on the current stream (no host synchronisation).  ``kind``: ``"smc"`` = 3^3 table of the level,
+        ``"down"`` = child table of the 2/2 convolution FROM ``spatial_size`` (rows = coarse voxels),
+        ``"up"`` = its (parent, offset) table (rows = fine voxels).  The tensor-core modes need it."""
+        lv = self.nbr(spatial_size) if kind == "smc" else self.down(spatial_size)[0]
+        hit = lv.plans.get(kind)
+        if hit is None:
+            K = 27 if kind == "smc" else 8
+            with torch.cuda.device(self.device):
+                nbytes = lib.mm3d_plan_bytes(lv.cap, K)
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                if kind == "smc":
+                    tbl, stride, onehot, cnt = lv.ptr(lv.o_nbr), lv.tstride, None, self._count_ptr(lv)
+                elif kind == "down":
+                    tbl, stride, onehot = lv.ptr(lv.o_child), lv.tstride, None
+                    cnt = self._count_ptr(self.levels[int(spatial_size) // 2])
+                elif kind == "up":
+                    tbl, stride, onehot, cnt = lv.ptr(lv.o_parent), 0, lv.ptr(lv.o_off), self._count_ptr(lv)
+                else:
+                    raise ValueError(kind)
+                check(lib.mm3d_build_plan(tbl, stride, onehot, cnt, lv.cap, K, buf.data_ptr(), nbytes,
+                                          _lib.stream_ptr()), "mm3d_build_plan")
+            hit = lv.plans[kind] = (buf, lv.cap)
+        return hit[0].data_ptr(), hit[1]
+
+    def plan_tensors(self, kind: str, spatial_size: int):
+        """(perm int32 [T*128], tile_mask int32 [T], table int32 [K, T*128]) views of a plan (tests)."""
+        self.plan(kind, spatial_size)
+        lv = self.levels[int(spatial_size)]
+        buf, cap = lv.plans[kind]
+        K = 27 if kind == "smc" else 8
+        T = (cap + 127) // 128
+        al = lambda x: (x + 255) // 256 * 256
+        o_mask = al(T * 128 * 4)
+        o_tbl = o_mask + al(T * 4)
+        perm = buf[:T * 128 * 4].view(torch.int32)
+        mask = buf[o_mask:o_mask + T * 4].view(torch.int32)
+        tbl = buf[o_tbl:o_tbl + K * T * 128 * 4].view(torch.int32).view(K, T * 128)
+        return perm, mask, tbl
 
     # ------------------------------------------------------------------ inspection (tests)
     @property

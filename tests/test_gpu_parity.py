@@ -158,6 +158,55 @@ def test_structure_full_batch_properties():
         s //= 2
 
 
+def _natural_table(meta, kind, spatial):
+    if kind == "smc":
+        return meta.nbr_table(spatial).cpu().numpy()
+    parent, off, child = meta.down_tables(spatial)
+    if kind == "down":
+        return child.cpu().numpy()
+    parent, off = parent.cpu().numpy(), off.cpu().numpy()
+    t = np.full((parent.shape[0], 8), -1, np.int32)
+    t[np.arange(parent.shape[0]), off] = parent
+    return t
+
+
+@pytest.mark.parametrize("kind", ["smc", "down", "up"])
+@pytest.mark.parametrize("shape,batch", [("cloud", 0), ("nuscenes", 2)])
+def test_row_plan(kind, shape, batch):
+    """Row plans (csrc/plan.cu) are integer work: the permutation covers every row exactly once, the
+    permuted table equals the natural table under it, the tile masks are exact -- and ordering rows by
+    neighbour mask leaves fewer non-empty (tile, offset) blocks than the natural order."""
+    coords = _cloud(5, n=900, b=3, span=30) if shape == "cloud" else synth.make_batch("nuscenes", batch=batch)[0]
+    meta = _meta(coords, 4096, 2)
+    nat = _natural_table(meta, kind, 4096)  # [rows, K]
+    n, K = nat.shape
+    perm, mask, tbl = (t.cpu().numpy() for t in meta.plan_tensors(kind, 4096))
+    # rows are sorted inside chunks of 8192; padding (-1) only at the end of the last chunk's last tile
+    T = (n + 127) // 128
+    p = perm[:T * 128]
+    assert np.array_equal(np.sort(p[p >= 0]), np.arange(n))
+    assert np.all(p[:n] >= 0) and np.all(p[n:] == -1)
+    for c0 in range(0, n, 8192):
+        seg = p[c0:min(c0 + 8192, n)]
+        assert seg.min() >= c0 and seg.max() < c0 + 8192
+    want = np.full((K, T * 128), -1, np.int32)
+    want[:, :n] = nat[p[:n]].T
+    assert np.array_equal(tbl[:, :T * 128], want)
+    blocks = (want.reshape(K, T, 128) >= 0).any(2)  # [K, T]
+    want_mask = (blocks.astype(np.int64) << np.arange(K)[:, None]).sum(0)
+    want_mask[want_mask == 0] = 1
+    assert np.array_equal(mask[:T].astype(np.int64) & 0xFFFFFFFF, want_mask)
+    if shape == "nuscenes":
+        natural = np.full((K, T * 128), -1, np.int32)
+        natural[:, :n] = nat.T
+        nat_blocks = (natural.reshape(K, T, 128) >= 0).any(2).sum()
+        assert blocks.sum() < (0.7 if kind != "down" else 0.95) * nat_blocks, (kind, blocks.sum(), nat_blocks)
+    # deterministic: a second build gives the same plan
+    meta2 = _meta(coords, 4096, 2)
+    perm2, mask2, tbl2 = (t.cpu().numpy() for t in meta2.plan_tensors(kind, 4096))
+    assert np.array_equal(perm2[:T * 128], p) and np.array_equal(mask2[:T], mask[:T])
+
+
 # ------------------------------------------------------------------------------ single ops
 def test_io_layers():
     from mm2d3d_b200 import functional as F

@@ -36,7 +36,7 @@ def main():
     spatial = 4096 >> a.level
     if a.kind == "up":
         spatial //= 2  # input lives one level deeper
-    fwd_t, bwd_t, bwd_flags = F.conv_tables(meta, a.kind, spatial)
+    fwd_t, bwd_t, bwd_flags = F.conv_tables(meta, a.kind, spatial, plans=a.mode != "fp32")
     K = fwd_t.K
     lib = _lib.lib
     m = _lib.MODES[a.mode]
@@ -53,15 +53,15 @@ def main():
     def run():
         if a.dir == "fwd":
             _lib.check(lib.mm3d_conv_fwd(x.data_ptr(), fwd_t.n_in, a.cin, out.data_ptr(), fwd_t.n_out, a.cout,
-                                         w.data_ptr(), K, fwd_t.tbl, fwd_t.stride, fwd_t.onehot, 0, m,
+                                         w.data_ptr(), K, fwd_t.tbl, fwd_t.stride, fwd_t.onehot, fwd_t.plan, fwd_t.plan_cap, 0, m,
                                          ws.data_ptr(), ws.numel(), sp))
         elif a.dir == "dgrad":
             _lib.check(lib.mm3d_conv_fwd(dout.data_ptr(), bwd_t.n_in, a.cout, dx.data_ptr(), bwd_t.n_out, a.cin,
-                                         w.data_ptr(), K, bwd_t.tbl, bwd_t.stride, bwd_t.onehot, bwd_flags, m,
+                                         w.data_ptr(), K, bwd_t.tbl, bwd_t.stride, bwd_t.onehot, bwd_t.plan, bwd_t.plan_cap, bwd_flags, m,
                                          ws.data_ptr(), ws.numel(), sp))
         else:
             _lib.check(lib.mm3d_conv_wgrad(x.data_ptr(), fwd_t.n_in, a.cin, dout.data_ptr(), fwd_t.n_out, a.cout,
-                                           dw.data_ptr(), K, fwd_t.tbl, fwd_t.stride, fwd_t.onehot, 0, m,
+                                           dw.data_ptr(), K, fwd_t.tbl, fwd_t.stride, fwd_t.onehot, fwd_t.plan, fwd_t.plan_cap, 0, m,
                                            ws.data_ptr(), ws.numel(), sp))
 
     flush = torch.empty(384 << 20, dtype=torch.uint8, device=dev)
