@@ -34,7 +34,7 @@ constexpr int kKBlock = 32;                 // tf32 elements per 128-byte row of
 constexpr int kStageBytes = kTileM * 128;   // one A stage = one K-block of 128 rows = 16 KB
 constexpr int kEntBytes = kTileM * 4;       // the K-block's 128 table entries
 constexpr int kEpilogue = 128;
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 8;
 constexpr int kMaxThreads = (kMaxStages + 5) * 32;
 
 struct TcParams {
@@ -43,6 +43,7 @@ struct TcParams {
   const float* wimg;  // [K][nb][n_pad][32] tf32, rows 128-byte swizzled
   const int32_t* perm;
   const uint32_t* tile_mask;
+  const int32_t* order;
   const int32_t* tbl;
   int64_t tstride;
   int c_in, c_out, K;
@@ -50,6 +51,7 @@ struct TcParams {
   int last_w;   // 16-byte chunks of an offset's last block (8, or 4 when c_in % 32 == 16)
   int S;        // ring stages = producer warps
   int n_pad, num_tiles, tmem_cols;
+  int n_local;  // tiles per CTA (upper bound) = ceil(num_tiles / grid)
   int* err;
 };
 
@@ -77,26 +79,27 @@ __global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ 
   }
 }
 
-// Walks the CTA's items in order: tiles blockIdx.x, +gridDim.x, ...; per tile the set bits of its
-// mask (ascending offset); per offset the nb channel blocks.  Every role runs its own copy.
+// Walks the CTA's items in order: its tiles (dealt from the plan's cost-ordered list, kept in shared
+// memory with their masks); per tile the set bits of its mask (ascending offset); per offset the nb
+// channel blocks.  Every role runs its own copy.
 struct ItemWalk {
-  const uint32_t* tile_mask;
-  int num_tiles, step, nb;
-  int tile, k, j;
+  const uint32_t* lmask;  // shared memory: [n_local] masks, then [n_local] tile indices
+  int n_local, nb;
+  int lt, tile, k, j;
   uint32_t rem;
-  __device__ __forceinline__ void init(const TcParams& p) {
-    tile_mask = p.tile_mask; num_tiles = p.num_tiles; step = (int)gridDim.x; nb = p.nb;
-    tile = (int)blockIdx.x; j = 0; rem = 0; k = 0;
-    if (tile < num_tiles) { rem = __ldg(tile_mask + tile); k = __ffs(rem) - 1; }
+  __device__ __forceinline__ void init(const TcParams& p, const uint32_t* local_masks, int n_loc) {
+    lmask = local_masks; n_local = n_loc; nb = p.nb;
+    lt = 0; tile = 0; j = 0; rem = 0; k = 0;
+    if (lt < n_local) { rem = lmask[0]; tile = (int)lmask[n_local]; k = __ffs(rem) - 1; }
   }
-  __device__ __forceinline__ bool valid() const { return tile < num_tiles; }
+  __device__ __forceinline__ bool valid() const { return lt < n_local; }
   __device__ __forceinline__ void next() {
     if (++j < nb) return;
     j = 0;
     rem &= rem - 1;
     if (rem) { k = __ffs(rem) - 1; return; }
-    tile += step;
-    if (tile < num_tiles) { rem = __ldg(tile_mask + tile); k = __ffs(rem) - 1; }
+    ++lt;
+    if (lt < n_local) { rem = lmask[lt]; tile = (int)lmask[n_local + lt]; k = __ffs(rem) - 1; }
   }
   // true when the current item is the last of its tile
   __device__ __forceinline__ bool last_of_tile() const { return j == nb - 1 && (rem & (rem - 1)) == 0; }
@@ -115,7 +118,9 @@ k_conv_tc(const TcParams p) {
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + (uint32_t)S * kStageBytes;
   const uint32_t e_base = b_base + (uint32_t)S * b_stride;  // one weight block and one entry row per A stage
-  const uint32_t bar_base = e_base + (uint32_t)S * kEntBytes;
+  const uint32_t m_base = e_base + (uint32_t)S * kEntBytes;  // masks of this CTA's tiles
+  const uint32_t bar_base = m_base + (((uint32_t)p.n_local * 8u + 15u) & ~15u);
+  uint32_t* lmask = reinterpret_cast<uint32_t*>(smem + (m_base - smem_base));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar_base - smem_base));
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(kMaxStages + s); };
@@ -128,6 +133,14 @@ k_conv_tc(const TcParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- one-time setup
+  // this CTA's tiles (mm3d_plan_local_tile) and their masks live in shared memory: [masks][tile indices]
+  int n_local = p.n_local;
+  if (mm3d_plan_local_tile(p.order, p.num_tiles, (int)gridDim.x, (int)blockIdx.x, n_local - 1) < 0) --n_local;
+  for (int i = threadIdx.x; i < n_local; i += blockDim.x) {
+    const int t = mm3d_plan_local_tile(p.order, p.num_tiles, (int)gridDim.x, (int)blockIdx.x, i);
+    lmask[i] = __ldg(p.tile_mask + t);
+    lmask[n_local + i] = (uint32_t)t;
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(a_full(s), 33);  // 32 cp.async arrivals (gathered rows) + 1 expect_tx arrival (weight block)
@@ -152,7 +165,7 @@ k_conv_tc(const TcParams p) {
     const uint32_t stage = a_base + (uint32_t)warp * kStageBytes;
     const uint32_t ent = e_base + (uint32_t)warp * kEntBytes;
     ItemWalk it;
-    it.init(p);
+    it.init(p, lmask, n_local);
     for (int i = 0; i < warp && it.valid(); ++i) it.next();  // this warp takes every S-th item
     uint32_t round = 0;
     int4 e = make_int4(-1, -1, -1, -1);  // entries of rows 4*lane .. 4*lane+3 of the current item
@@ -206,9 +219,9 @@ k_conv_tc(const TcParams p) {
   } else if (warp < S + 4) {
     // =================================================================== epilogue
     const int ew = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
-    uint32_t tile_iter = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tile_iter) {
+    for (uint32_t tile_iter = 0; tile_iter < (uint32_t)n_local; ++tile_iter) {
       const int ab = (int)(tile_iter & 1u);
+      const int tile = (int)lmask[n_local + tile_iter];
       const int row = __ldg(p.perm + (int64_t)tile * kTileM + ew * 32 + lane);
       if (!mbar_wait(acc_full(ab), (tile_iter >> 1) & 1u, abort_flag)) goto done;
       tc_fence_after();
@@ -236,8 +249,9 @@ k_conv_tc(const TcParams p) {
     // =================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(kTileM, p.n_pad);
+      const uint64_t desc0 = make_desc_sw128(0);
       ItemWalk it;
-      it.init(p);
+      it.init(p, lmask, n_local);
       uint32_t tile_iter = 0;
       int s = 0;
       uint32_t ph = 0;
@@ -252,11 +266,14 @@ k_conv_tc(const TcParams p) {
           const int ksteps = (it.j == p.nb - 1 ? p.last_w : 8) >> 1;
           if (!mbar_wait(a_full(s), ph, abort_flag)) { ok = false; break; }
           tc_fence_after();
-          const uint32_t a_addr = a_base + (uint32_t)s * kStageBytes;
-          const uint32_t b_addr = b_base + (uint32_t)s * b_stride;
-          for (int ks = 0; ks < ksteps; ++ks)
-            umma_tf32(d_tmem, make_desc_sw128(a_addr + ks * 32), make_desc_sw128(b_addr + ks * 32), idesc,
-                      (!first || ks != 0) ? 1u : 0u);
+          const uint64_t a_desc = desc0 + desc_addr(a_base + (uint32_t)s * kStageBytes);
+          const uint64_t b_desc = desc0 + desc_addr(b_base + (uint32_t)s * b_stride);
+          umma_tf32(d_tmem, a_desc, b_desc, idesc, first ? 0u : 1u);
+          umma_tf32(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);  // +32 bytes per K-step of 8
+          if (ksteps == 4) {
+            umma_tf32(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+            umma_tf32(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+          }
           umma_commit(a_empty(s));  // frees the stage and its weight block
           first = false;
           if (++s == S) { s = 0; ph ^= 1u; }
@@ -356,7 +373,7 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
   const Mm3dPlanView pv = mm3d_plan_view(plan, plan_cap);
   TcParams p;
   p.in = in; p.out = out; p.wimg = wimg;
-  p.perm = pv.perm; p.tile_mask = pv.tile_mask; p.tbl = pv.tbl; p.tstride = pv.stride;
+  p.perm = pv.perm; p.tile_mask = pv.tile_mask; p.order = pv.order; p.tbl = pv.tbl; p.tstride = pv.stride;
   p.c_in = c_in; p.c_out = c_out; p.K = K; p.nb = nb;
   p.last_w = (c_in % 32) == 16 ? 4 : 8;
   p.n_pad = n_pad;
@@ -365,12 +382,13 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
   p.err = mm3d_device_err_flag();
   const uint32_t b_stride = ((uint32_t)n_pad * 128u + 1023u) & ~1023u;
   const size_t per_stage = (size_t)kStageBytes + b_stride + kEntBytes;
-  // as many stages as give two CTAs per SM; one CTA per SM when the weight blocks are large
-  int S = (int)((112 * 1024) / per_stage);
-  if (S < 3) S = (int)((224 * 1024) / per_stage);
+  // as many stages as give two CTAs per SM; one CTA per SM (deeper ring) when the weight blocks are
+  // large or there are no more tiles than SMs anyway
+  const int two = (int)((112 * 1024) / per_stage), one = (int)((222 * 1024) / per_stage);
+  int S = (p.num_tiles > MM3D_NUM_SMS && two >= 3) ? two : one;
   if (S > kMaxStages) S = kMaxStages;
   p.S = S;
-  const size_t smem = 1024 + (size_t)S * per_stage + 8 * (2 * kMaxStages + 4) + 64;
+  size_t smem = 1024 + (size_t)S * per_stage + 8 * (2 * kMaxStages + 4) + 64;
   static int regs = 0;
   if (!regs) {
     MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -391,6 +409,9 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
   if (per_sm < 1) per_sm = 1;
   int grid = MM3D_NUM_SMS * per_sm;
   if (grid > p.num_tiles) grid = p.num_tiles;
+  p.n_local = (p.num_tiles + grid - 1) / grid;
+  smem += ((size_t)p.n_local * 8 + 15) / 16 * 16;
+  MM3D_REQUIRE(smem <= 226 * 1024, MM3D_ERR_UNSUPPORTED, "tcgen05 conv: too many rows per CTA for the tile-mask cache");
   k_conv_tc<<<grid, threads, smem, stream>>>(p);
   mm3d_count_launches(2);
   MM3D_CHECK_LAUNCH("mm3d_conv_fwd_tc");

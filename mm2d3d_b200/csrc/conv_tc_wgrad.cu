@@ -13,8 +13,8 @@
 // 512 columns (grid.y) and a slice of the tiles (grid.x), skips tiles without any of its offsets,
 // and adds its accumulators to dW once at the end (atomics: tile_splits * |dW|).
 //
-// Warp roles (S+6 warps): 0..S-1 gather producers (warp w owns ring stage w), S..S+3 epilogue
-// (TMEM -> atomics), S+4 MMA issuer + TMEM allocator, S+5 dout-tile loader.
+// Warp roles (S+7 warps): 0..S-1 gather producers (warp w owns ring stage w), S..S+3 epilogue
+// (TMEM -> atomics), S+4 MMA issuer + TMEM allocator, S+5 / S+6 dout-tile loaders (64 rows each).
 #include "plan.cuh"
 #include "tc_common.cuh"
 
@@ -26,7 +26,8 @@ constexpr int kTileM = 128;
 constexpr int kStageBytes = kTileM * 128;
 constexpr int kEntBytes = kTileM * 4;
 constexpr int kMaxStages = 6;
-constexpr int kMaxThreads = (kMaxStages + 6) * 32;
+constexpr int kMaxGBufs = 4;
+constexpr int kMaxThreads = (kMaxStages + 7) * 32;
 
 struct WgParams {
   const float* in;
@@ -34,6 +35,7 @@ struct WgParams {
   float* dw;
   const int32_t* perm;
   const uint32_t* tile_mask;
+  const int32_t* order;
   const int32_t* tbl;
   int64_t tstride;
   int c_in, c_out, K;
@@ -42,28 +44,29 @@ struct WgParams {
   int mw;           // UMMA M: 64 (c_out <= 64) or 128
   int S, gbufs;
   int num_tiles, tile_splits, tmem_cols;
+  int n_local;  // tiles per CTA (upper bound)
   int* err;
 };
 
 // tiles of this CTA that contain at least one offset of its group, in order
 struct TileWalk {
-  const uint32_t* tile_mask;
-  int num_tiles, step, tile;
-  uint32_t gm, m;
+  const uint32_t* lmask;  // shared memory: [n_local] (mask & group) of this CTA's tiles, then [n_local] tile indices
+  int n_local, lt, tile;
+  uint32_t m;
   __device__ __forceinline__ void seek() {
-    while (tile < num_tiles) {
-      m = __ldg(tile_mask + tile) & gm;
-      if (m) return;
-      tile += step;
+    while (lt < n_local) {
+      m = lmask[lt];
+      if (m) { tile = (int)lmask[n_local + lt]; return; }
+      ++lt;
     }
     m = 0;
   }
-  __device__ __forceinline__ void init(const WgParams& p, uint32_t gmask) {
-    tile_mask = p.tile_mask; num_tiles = p.num_tiles; step = p.tile_splits; tile = (int)blockIdx.x; gm = gmask;
+  __device__ __forceinline__ void init(const WgParams& p, const uint32_t* local_masks, int n_loc) {
+    lmask = local_masks; n_local = n_loc; lt = 0; tile = 0;
     seek();
   }
-  __device__ __forceinline__ bool valid() const { return tile < num_tiles; }
-  __device__ __forceinline__ void next_tile() { tile += step; seek(); }
+  __device__ __forceinline__ bool valid() const { return lt < n_local; }
+  __device__ __forceinline__ void next_tile() { ++lt; seek(); }
 };
 
 // items = (tile, offset, channel block) over TileWalk
@@ -71,8 +74,8 @@ struct ItemWalk {
   TileWalk t;
   int nb, k, j;
   uint32_t rem;
-  __device__ __forceinline__ void init(const WgParams& p, uint32_t gmask) {
-    t.init(p, gmask); nb = p.nb; j = 0; rem = t.m; k = rem ? __ffs(rem) - 1 : 0;
+  __device__ __forceinline__ void init(const WgParams& p, const uint32_t* local_masks, int n_loc) {
+    t.init(p, local_masks, n_loc); nb = p.nb; j = 0; rem = t.m; k = rem ? __ffs(rem) - 1 : 0;
   }
   __device__ __forceinline__ bool valid() const { return t.valid(); }
   __device__ __forceinline__ void next() {
@@ -94,14 +97,16 @@ k_wgrad_tc(const WgParams p) {
   const uint32_t g_bytes = (uint32_t)(p.mw / 32) * kStageBytes;  // dout tile: mw/32 blocks of [128 rows][32 channels]
   const uint32_t g_base = a_base + (uint32_t)S * kStageBytes;
   const uint32_t e_base = g_base + (uint32_t)p.gbufs * g_bytes;
-  const uint32_t bar_base = e_base + (uint32_t)S * kEntBytes;
+  const uint32_t m_base = e_base + (uint32_t)(S + 1) * kEntBytes;  // (mask & group) and index of this CTA's tiles
+  const uint32_t bar_base = m_base + (((uint32_t)p.n_local * 8u + 15u) & ~15u);
+  uint32_t* lmask = reinterpret_cast<uint32_t*>(smem + (m_base - smem_base));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar_base - smem_base));
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(kMaxStages + s); };
   auto g_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + s); };
-  auto g_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 + s); };
-  const uint32_t acc_full = bar_base + 8u * (uint32_t)(2 * kMaxStages + 4);
-  constexpr int kNumBars = 2 * kMaxStages + 5;
+  auto g_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + kMaxGBufs + s); };
+  const uint32_t acc_full = bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 * kMaxGBufs);
+  constexpr int kNumBars = 2 * kMaxStages + 2 * kMaxGBufs + 1;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNumBars);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + kNumBars + 1);
 
@@ -110,13 +115,20 @@ k_wgrad_tc(const WgParams p) {
   const int kn = min(p.gk, p.K - k0);
   const uint32_t gmask = (kn >= 32 ? 0xFFFFFFFFu : ((1u << kn) - 1u)) << k0;
 
+  int n_local = p.n_local;
+  if (mm3d_plan_local_tile(p.order, p.num_tiles, p.tile_splits, (int)blockIdx.x, n_local - 1) < 0) --n_local;
+  for (int i = threadIdx.x; i < n_local; i += blockDim.x) {
+    const int t = mm3d_plan_local_tile(p.order, p.num_tiles, p.tile_splits, (int)blockIdx.x, i);
+    lmask[i] = __ldg(p.tile_mask + t) & gmask;
+    lmask[n_local + i] = (uint32_t)t;
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(a_full(s), 32);
       mbar_init(a_empty(s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(g_full(s), 32);
+    for (int s = 0; s < kMaxGBufs; ++s) {
+      mbar_init(g_full(s), 64);  // two loader warps
       mbar_init(g_empty(s), 1);
     }
     mbar_init(acc_full, 1);
@@ -134,7 +146,7 @@ k_wgrad_tc(const WgParams p) {
     const uint32_t stage = a_base + (uint32_t)warp * kStageBytes;
     const uint32_t ent = e_base + (uint32_t)warp * kEntBytes;
     ItemWalk it;
-    it.init(p, gmask);
+    it.init(p, lmask, n_local);
     for (int i = 0; i < warp && it.valid(); ++i) it.next();
     uint32_t round = 0;
     int4 e = make_int4(-1, -1, -1, -1);
@@ -184,10 +196,9 @@ k_wgrad_tc(const WgParams p) {
     const int ew = warp & 3;
     // offsets this CTA touched = OR of its tiles' masks (the MMA issuer derives the same set)
     uint32_t seen = 0;
-    for (int t = (int)blockIdx.x + lane * p.tile_splits; t < p.num_tiles; t += 32 * p.tile_splits) seen |= __ldg(p.tile_mask + t);
+    for (int i = lane; i < n_local; i += 32) seen |= lmask[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) seen |= __shfl_xor_sync(0xffffffffu, seen, o);
-    seen &= gmask;
     if (seen == 0) goto done;
     if (!mbar_wait(acc_full, 0u, abort_flag)) goto done;
     tc_fence_after();
@@ -195,7 +206,12 @@ k_wgrad_tc(const WgParams p) {
     // lane 32*(m/16) + m%16 (16 lanes per sub-partition)
     const int co = p.mw == 128 ? ew * 32 + lane : ew * 16 + lane;
     const bool lane_ok = (p.mw == 128 || lane < 16) && co < p.c_out;
-    for (uint32_t rem = seen; rem; rem &= rem - 1) {
+    // every CTA of a group flushes the same addresses: start each at a different offset so that the L2
+    // atomic units do not serialise on one line at a time
+    const int rot = k0 + (int)(blockIdx.x % (unsigned)kn);
+    const uint32_t hi = seen & ~((1u << rot) - 1u), lo = seen & ((1u << rot) - 1u);
+    for (int part = 0; part < 2; ++part)
+    for (uint32_t rem = part ? lo : hi; rem; rem &= rem - 1) {
       const int k = __ffs(rem) - 1;
       for (int j = 0; j < p.nb; ++j) {
         const int wj = (j == p.nb - 1 && p.last_w == 4) ? 16 : 32;
@@ -217,15 +233,16 @@ k_wgrad_tc(const WgParams p) {
     // =================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc32 = make_idesc_tf32(p.mw, 32, 1, 1), idesc16 = make_idesc_tf32(p.mw, 16, 1, 1);
+      const uint64_t desc0 = make_desc_sw128_base32(0, kStageBytes, 512);
       TileWalk tw;
-      tw.init(p, gmask);
+      tw.init(p, lmask, n_local);
       uint32_t gi = 0, seen = 0, ph = 0;
       int s = 0;
       bool ok = true, any = false;
       while (tw.valid() && ok) {
         const int buf = (int)(gi % (uint32_t)p.gbufs);
         if (!mbar_wait(g_full(buf), (gi / (uint32_t)p.gbufs) & 1u, abort_flag)) break;
-        const uint32_t gb = g_base + (uint32_t)buf * g_bytes;
+        const uint64_t g_desc = desc0 + desc_addr(g_base + (uint32_t)buf * g_bytes);
         for (uint32_t rem = tw.m; rem && ok; rem &= rem - 1) {
           const int k = __ffs(rem) - 1;
           const uint32_t acc0 = (seen >> k) & 1u;
@@ -233,13 +250,14 @@ k_wgrad_tc(const WgParams p) {
             if (!mbar_wait(a_full(s), ph, abort_flag)) { ok = false; break; }
             tc_fence_after();
             const bool half = (j == p.nb - 1) && p.last_w == 4;
-            const uint32_t ab = a_base + (uint32_t)s * kStageBytes;
+            const uint64_t a_desc = desc0 + desc_addr(a_base + (uint32_t)s * kStageBytes);
             const uint32_t d_tmem = tmem_base + (uint32_t)((k - k0) * p.c_in + j * 32);
-            // per K-step of 8 rows: two 4-row swizzle atoms (SBO = 512 B); A's 32-wide M blocks are LBO apart
-            for (int r8 = 0; r8 < 16; ++r8)
-              umma_tf32(d_tmem, make_desc_sw128_base32(gb + r8 * 1024, kStageBytes, 512),
-                        make_desc_sw128_base32(ab + r8 * 1024, kStageBytes, 512), half ? idesc16 : idesc32,
-                        (acc0 | (uint32_t)r8) != 0 ? 1u : 0u);
+            const uint32_t idesc = half ? idesc16 : idesc32;
+            // per K-step of 8 rows: two 4-row swizzle atoms (SBO = 512 B, 1024 B per step); the dout tile's
+            // 32-wide M blocks are LBO apart
+            umma_tf32(d_tmem, g_desc, a_desc, idesc, acc0);
+#pragma unroll
+            for (int r8 = 1; r8 < 16; ++r8) umma_tf32(d_tmem, g_desc + r8 * 64, a_desc + r8 * 64, idesc, 1u);
             umma_commit(a_empty(s));
             if (++s == S) { s = 0; ph ^= 1u; }
           }
@@ -254,20 +272,30 @@ k_wgrad_tc(const WgParams p) {
       if (ok && any) umma_commit(acc_full);
     }
   } else {
-    // =================================================================== dout-tile loader
+    // =================================================================== dout-tile loaders: 64 rows each
+    const int half = warp - (S + 5);  // rows 64*half .. 64*half + 63
     const int nch = p.c_out >> 2;
+    const uint32_t ent = e_base + (uint32_t)S * kEntBytes + (uint32_t)half * 256u;
     TileWalk tw;
-    tw.init(p, gmask);
+    tw.init(p, lmask, n_local);
     uint32_t gi = 0;
+    int2 pr = make_int2(-1, -1);  // rows 2*lane, 2*lane+1 of this half of the tile
+    if (tw.valid()) pr = __ldg(reinterpret_cast<const int2*>(p.perm + (int64_t)tw.tile * kTileM + half * 64) + lane);
     while (tw.valid()) {
+      tw.next_tile();
+      int2 prn = make_int2(-1, -1);
+      if (tw.valid()) prn = __ldg(reinterpret_cast<const int2*>(p.perm + (int64_t)tw.tile * kTileM + half * 64) + lane);
       const int buf = (int)(gi % (uint32_t)p.gbufs);
       if (!mbar_wait(g_empty(buf), ((gi / (uint32_t)p.gbufs) & 1u) ^ 1u, abort_flag)) goto done;
       const uint32_t gb = g_base + (uint32_t)buf * g_bytes;
-      const int32_t* prow = p.perm + (int64_t)tw.tile * kTileM;
+      asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ent + (uint32_t)lane * 8u), "r"(pr.x), "r"(pr.y) : "memory");
+      __syncwarp();
 #pragma unroll 4
-      for (int r0 = 0; r0 < kTileM; r0 += 4) {
-        const int r = r0 + (lane >> 3);
-        const int row = __ldg(prow + r);
+      for (int r0 = 0; r0 < 64; r0 += 4) {
+        const int rl = r0 + (lane >> 3);
+        const int r = half * 64 + rl;
+        int row;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(ent + (uint32_t)rl * 4u) : "memory");
         const bool ok = row >= 0;
         const float* src = p.dout + (int64_t)(ok ? row : 0) * p.c_out;
         for (int ch = lane & 7; ch < nch; ch += 8)
@@ -275,8 +303,9 @@ k_wgrad_tc(const WgParams p) {
                      ok ? 16u : 0u);
       }
       cp_async_arrive(g_full(buf));
+      __syncwarp();
+      pr = prn;
       ++gi;
-      tw.next_tile();
     }
   }
 done:
@@ -313,7 +342,7 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
   const Mm3dPlanView pv = mm3d_plan_view(plan, plan_cap);
   WgParams p;
   p.in = in; p.dout = d_out; p.dw = d_weight;
-  p.perm = pv.perm; p.tile_mask = pv.tile_mask; p.tbl = pv.tbl; p.tstride = pv.stride;
+  p.perm = pv.perm; p.tile_mask = pv.tile_mask; p.order = pv.order; p.tbl = pv.tbl; p.tstride = pv.stride;
   p.c_in = c_in; p.c_out = c_out; p.K = K;
   p.nb = (c_in + 31) / 32;
   p.last_w = (c_in % 32) == 16 ? 4 : 8;
@@ -326,17 +355,20 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
   int cols = 32;
   while (cols < gk * c_in) cols <<= 1;
   p.tmem_cols = cols;
-  const bool one_cta = cols > 256 || p.mw == 128;
-  p.gbufs = one_cta ? 2 : 1;
-  p.S = one_cta ? (p.mw == 128 ? 5 : 6) : 4;
-  const int per_sm = one_cta ? 1 : 2;
+  // one CTA per SM: 4 ring stages + as many dout-tile buffers as fit
+  p.S = 4;
+  p.gbufs = p.mw == 128 ? 2 : kMaxGBufs;
+  const int per_sm = 1;
   int tile_splits = MM3D_NUM_SMS * per_sm / groups;
   if (tile_splits < 1) tile_splits = 1;
   if (tile_splits > p.num_tiles) tile_splits = p.num_tiles;
   p.tile_splits = tile_splits;
   p.err = mm3d_device_err_flag();
-  const size_t smem = 1024 + (size_t)p.S * (kStageBytes + kEntBytes) + (size_t)p.gbufs * (p.mw / 32) * kStageBytes +
-                      8 * (2 * kMaxStages + 5) + 64;
+  p.n_local = (p.num_tiles + tile_splits - 1) / tile_splits;
+  const size_t smem = 1024 + (size_t)p.S * kStageBytes + (size_t)(p.S + 1) * kEntBytes +
+                      (size_t)p.gbufs * (p.mw / 32) * kStageBytes + ((size_t)p.n_local * 8 + 15) / 16 * 16 +
+                      8 * (2 * kMaxStages + 2 * kMaxGBufs + 1) + 64;
+  MM3D_REQUIRE(smem <= 226 * 1024, MM3D_ERR_UNSUPPORTED, "tcgen05 wgrad: too many rows per CTA for the tile-mask cache");
   static bool once = false;
   if (!once) {
     MM3D_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -344,7 +376,7 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
     once = true;
   }
   dim3 grid((unsigned)tile_splits, (unsigned)groups);
-  k_wgrad_tc<<<grid, (p.S + 6) * 32, smem, stream>>>(p);
+  k_wgrad_tc<<<grid, (p.S + 7) * 32, smem, stream>>>(p);
   mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_conv_wgrad_tc");
   return MM3D_OK;

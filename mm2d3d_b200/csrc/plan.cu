@@ -168,6 +168,43 @@ k_build_plan(const int32_t* __restrict__ tbl, int64_t tbl_stride, const uint8_t*
   }
 }
 
+// Tiles by descending number of non-empty offsets, stable.  One CTA, warp w owns the bin popcount == 32 - w:
+// it counts its tiles, the bins are scanned, then it compacts its tiles in order (ballot ranks).
+__global__ void __launch_bounds__(1024, 1)
+k_plan_order(const uint32_t* __restrict__ tile_mask, const int32_t* __restrict__ n_dev, int32_t* __restrict__ order) {
+  __shared__ int bin_base[32];
+  const int T = (int)(((int64_t)*n_dev + 127) / 128);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int want = 32 - warp;
+  int total = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    const bool mine = t < T && __popc(__ldg(tile_mask + t)) == want;
+    total += __popc(__ballot_sync(0xffffffffu, mine));
+  }
+  if (lane == 0) bin_base[warp] = total;
+  __syncthreads();
+  if (warp == 0) {
+    const int v = bin_base[lane];
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int x = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += x;
+    }
+    bin_base[lane] = incl - v;
+  }
+  __syncthreads();
+  int pos = bin_base[warp];
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    const bool mine = t < T && __popc(__ldg(tile_mask + t)) == want;
+    const unsigned bal = __ballot_sync(0xffffffffu, mine);
+    if (mine) order[pos + __popc(bal & ((1u << lane) - 1u))] = t;
+    pos += __popc(bal);
+  }
+}
+
 }  // namespace
 
 extern "C" size_t mm3d_plan_bytes(int64_t n_cap, int K) {
@@ -189,6 +226,7 @@ extern "C" int mm3d_build_plan(const int32_t* tbl, int64_t tbl_stride, const uin
   char* b = (char*)plan;
   int32_t* perm = (int32_t*)b;
   uint32_t* tmask = (uint32_t*)(b + mm3d_plan_off_mask(n_cap));
+  int32_t* order = (int32_t*)(b + mm3d_plan_off_order(n_cap));
   int32_t* ptbl = (int32_t*)(b + mm3d_plan_off_tbl(n_cap));
   const int64_t pstride = mm3d_plan_tiles(n_cap) * 128;
 
@@ -230,7 +268,8 @@ extern "C" int mm3d_build_plan(const int32_t* tbl, int64_t tbl_stride, const uin
     k_build_plan<false><<<grid, kThreads, smem, stream>>>(tbl, tbl_stride, onehot_off, n_dev, K, nbits, bp, perm, tmask,
                                                           ptbl, pstride);
   }
-  mm3d_count_launches(1);
+  k_plan_order<<<1, 1024, 0, stream>>>(tmask, n_dev, order);
+  mm3d_count_launches(2);
   MM3D_CHECK_LAUNCH("mm3d_build_plan");
   return MM3D_OK;
 }

@@ -8,6 +8,9 @@
 //
 //   perm      int32 [T*128]      tile t holds output rows perm[128 t .. 128 t + 127] (-1 = padding)
 //   tile_mask uint32[T]          bit k set  <=>  some row of tile t has an input at offset k
+//   order     int32 [T]          the tiles [0, ceil(n/128)) by descending popcount(mask) (stable): kernels deal
+//                                tiles to their CTAs from this list in serpentine order, which balances the
+//                                number of non-empty blocks per CTA (a tile has 1..K of them)
 //   tbl       int32 [K][T*128]   tbl[k][128 t + r] = input row of perm[128 t + r] at offset k, or -1
 //
 // with T = ceil(n_cap / 128).  Features stay in SparseConvNet row order everywhere; only the order
@@ -19,6 +22,7 @@
 struct Mm3dPlanView {
   const int32_t* perm;
   const uint32_t* tile_mask;
+  const int32_t* order;
   const int32_t* tbl;
   int64_t stride;  // T * 128
 };
@@ -28,8 +32,11 @@ __host__ __device__ inline int64_t mm3d_plan_tiles(int64_t n_cap) { return (n_ca
 __host__ __device__ inline size_t mm3d_plan_off_mask(int64_t n_cap) {
   return ((size_t)mm3d_plan_tiles(n_cap) * 128 * 4 + 255) / 256 * 256;
 }
-__host__ __device__ inline size_t mm3d_plan_off_tbl(int64_t n_cap) {
+__host__ __device__ inline size_t mm3d_plan_off_order(int64_t n_cap) {
   return mm3d_plan_off_mask(n_cap) + ((size_t)mm3d_plan_tiles(n_cap) * 4 + 255) / 256 * 256;
+}
+__host__ __device__ inline size_t mm3d_plan_off_tbl(int64_t n_cap) {
+  return mm3d_plan_off_order(n_cap) + ((size_t)mm3d_plan_tiles(n_cap) * 4 + 255) / 256 * 256;
 }
 __host__ __device__ inline size_t mm3d_plan_size(int64_t n_cap, int K) {
   return mm3d_plan_off_tbl(n_cap) + ((size_t)K * mm3d_plan_tiles(n_cap) * 128 * 4 + 255) / 256 * 256;
@@ -40,7 +47,15 @@ inline Mm3dPlanView mm3d_plan_view(const void* plan, int64_t n_cap) {
   Mm3dPlanView v;
   v.perm = (const int32_t*)b;
   v.tile_mask = (const uint32_t*)(b + mm3d_plan_off_mask(n_cap));
+  v.order = (const int32_t*)(b + mm3d_plan_off_order(n_cap));
   v.tbl = (const int32_t*)(b + mm3d_plan_off_tbl(n_cap));
   v.stride = mm3d_plan_tiles(n_cap) * 128;
   return v;
+}
+
+// The i-th tile of CTA `cta` out of `ctas`: position i*ctas + (cta, or mirrored on odd rounds) of the
+// cost-ordered tile list; -1 past the end.  Mirroring makes the per-CTA cost sums telescope to ~equal.
+__device__ __forceinline__ int mm3d_plan_local_tile(const int32_t* __restrict__ order, int num_tiles, int ctas, int cta, int i) {
+  const int64_t pos = (int64_t)i * ctas + ((i & 1) ? ctas - 1 - cta : cta);
+  return pos < num_tiles ? __ldg(order + pos) : -1;
 }

@@ -113,6 +113,9 @@ __device__ __forceinline__ uint64_t make_desc_sw128_base32(uint32_t saddr, uint3
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
+// Descriptors of one operand differ only in the start-address field: build the constant part once and add
+// (byte address >> 4); stepping the operand by `bytes` adds (bytes >> 4) (no carry: addresses < 256 KB).
+__device__ __forceinline__ uint64_t desc_addr(uint32_t saddr) { return (uint64_t)((saddr & 0x3FFFF) >> 4); }
 // byte offset of 16-byte chunk c (0..7) of row r inside a 128-byte row under that swizzle
 __device__ __forceinline__ uint32_t swz_base32(int c, int r) {
   return (uint32_t)((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4));

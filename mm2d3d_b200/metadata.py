@@ -192,7 +192,8 @@ class Metadata:
         return hit[0].data_ptr(), hit[1]
 
     def plan_tensors(self, kind: str, spatial_size: int):
-        """(perm int32 [T*128], tile_mask int32 [T], table int32 [K, T*128]) views of a plan (tests)."""
+        """(perm int32 [T*128], tile_mask int32 [T], table int32 [K, T*128], tile order int32 [T]) views of a
+        plan (tests)."""
         self.plan(kind, spatial_size)
         lv = self.levels[int(spatial_size)]
         buf, cap = lv.plans[kind]
@@ -200,11 +201,13 @@ class Metadata:
         T = (cap + 127) // 128
         al = lambda x: (x + 255) // 256 * 256
         o_mask = al(T * 128 * 4)
-        o_tbl = o_mask + al(T * 4)
+        o_order = o_mask + al(T * 4)
+        o_tbl = o_order + al(T * 4)
         perm = buf[:T * 128 * 4].view(torch.int32)
         mask = buf[o_mask:o_mask + T * 4].view(torch.int32)
         tbl = buf[o_tbl:o_tbl + K * T * 128 * 4].view(torch.int32).view(K, T * 128)
-        return perm, mask, tbl
+        order = buf[o_order:o_order + T * 4].view(torch.int32)
+        return perm, mask, tbl, order
 
     # ------------------------------------------------------------------ inspection (tests)
     @property

@@ -180,7 +180,7 @@ def test_row_plan(kind, shape, batch):
     meta = _meta(coords, 4096, 2)
     nat = _natural_table(meta, kind, 4096)  # [rows, K]
     n, K = nat.shape
-    perm, mask, tbl = (t.cpu().numpy() for t in meta.plan_tensors(kind, 4096))
+    perm, mask, tbl, order = (t.cpu().numpy() for t in meta.plan_tensors(kind, 4096))
     # rows are sorted inside chunks of 8192; padding (-1) only at the end of the last chunk's last tile
     T = (n + 127) // 128
     p = perm[:T * 128]
@@ -196,6 +196,10 @@ def test_row_plan(kind, shape, batch):
     want_mask = (blocks.astype(np.int64) << np.arange(K)[:, None]).sum(0)
     want_mask[want_mask == 0] = 1
     assert np.array_equal(mask[:T].astype(np.int64) & 0xFFFFFFFF, want_mask)
+    # tile order: every tile once, by descending number of non-empty offsets, ties in tile order
+    pc = blocks.sum(0)
+    pc[pc == 0] = 1
+    assert np.array_equal(order[:T], np.argsort(-pc, kind="stable"))
     if shape == "nuscenes":
         natural = np.full((K, T * 128), -1, np.int32)
         natural[:, :n] = nat.T
@@ -203,7 +207,7 @@ def test_row_plan(kind, shape, batch):
         assert blocks.sum() < (0.7 if kind != "down" else 0.95) * nat_blocks, (kind, blocks.sum(), nat_blocks)
     # deterministic: a second build gives the same plan
     meta2 = _meta(coords, 4096, 2)
-    perm2, mask2, tbl2 = (t.cpu().numpy() for t in meta2.plan_tensors(kind, 4096))
+    perm2, mask2, tbl2, _ = (t.cpu().numpy() for t in meta2.plan_tensors(kind, 4096))
     assert np.array_equal(perm2[:T * 128], p) and np.array_equal(mask2[:T], mask[:T])
 
 
