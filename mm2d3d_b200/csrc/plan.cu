@@ -1,13 +1,19 @@
 // Row plans (plan.cuh): order the output rows of a rule table by neighbour mask, permute the table
-// accordingly and record, per tile of 128 rows, which offsets are present at all.
+// accordingly, record per tile of 128 rows which offsets are present at all, and list the tiles by
+// cost.  One launch per table.
 //
 // One CTA owns a chunk of 8192 consecutive rows (64 tiles): it builds a sort key per row from the
-// table (bit per offset; for the 3^3 table the rarest offsets -- corners, then edges, then faces --
-// are the most significant bits, which measured best), sorts the chunk with a stable LSD radix sort
-// in shared memory (8-bit digits, per-warp histograms, match_any ranking: no atomics, so the order
-// is the same on every run), then writes the permutation, the permuted table (reads stay inside the
-// chunk's 32 KB window of each table plane) and the tile masks.  Sorting per chunk instead of
-// globally keeps it to one launch per table; it costs ~15 % more non-empty blocks than a global sort.
+// table, sorts the chunk with a stable LSD radix sort in shared memory (digits of up to 10 bits,
+// per-warp histograms, ballot ranking: no atomics, so the order is the same on every run), then
+// writes the permutation, the permuted table (reads stay inside the chunk's 32 KB window of each
+// table plane) and the tile masks.  Sorting per chunk instead of globally keeps it to one launch;
+// it costs ~15 % more non-empty blocks than a global sort.  The last CTA to finish orders the tiles.
+//
+// Sort keys.  3^3 table: bit 18 = "has any corner neighbour", bits 6..17 = the 12 edge offsets,
+// bits 0..5 = the 6 face offsets (the centre is always present): rarest first measured best, and
+// folding the 8 corner bits into one loses nothing measurable (0.194 vs 0.191 non-empty blocks)
+// while saving a radix pass.  Other dense tables: bit k = offset k present.  (parent, offset)
+// tables: the offset.
 #include "plan.cuh"
 
 namespace {
@@ -15,27 +21,31 @@ namespace {
 constexpr int kChunk = 8192;
 constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
-constexpr int kSeg = kChunk / kWarps;  // 256 consecutive elements per warp
-constexpr int kIters = kSeg / 32;      // 8
-constexpr int kPerThread = kChunk / kThreads;
+constexpr int kMaxIters = kChunk / kThreads;  // 8 rounds of 1024 elements
+constexpr int kDigitBits = 10;                // widest radix digit
 
 struct BitPos {
-  uint8_t p[32];  // sort-key bit of offset k (255 = not part of the key)
+  uint8_t p[32];   // sort-key bit of offset k
+  uint8_t en[32];  // 1 = offset k is part of the key
 };
 
 struct PlanSmem {
   uint32_t keys[2][kChunk];
   uint16_t idx[2][kChunk];
-  uint16_t hist[kWarps * 256];
+  uint16_t hist[kWarps << kDigitBits];
   uint32_t tmask[kChunk / 128];
   int warp_sums[kWarps];
+  int bin_base[32];
+  int is_last;
 };
 
-template <bool ONEHOT>
+// KT = compile-time bound of the offset loops (27, 8 or 32 = generic); K <= KT is the real count.
+template <int KT, bool ONEHOT>
 __global__ void __launch_bounds__(kThreads, 1)
 k_build_plan(const int32_t* __restrict__ tbl, int64_t tbl_stride, const uint8_t* __restrict__ onehot_off,
              const int32_t* __restrict__ n_dev, int K, int nbits, BitPos bp, int32_t* __restrict__ perm,
-             uint32_t* __restrict__ tile_mask, int32_t* __restrict__ ptbl, int64_t pstride) {
+             uint32_t* __restrict__ tile_mask, int32_t* __restrict__ order, int32_t* __restrict__ ptbl, int64_t pstride,
+             unsigned int* __restrict__ done_counter) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   PlanSmem& s = *reinterpret_cast<PlanSmem*>(smem_raw);
   const int64_t n = *n_dev;
@@ -43,20 +53,26 @@ k_build_plan(const int32_t* __restrict__ tbl, int64_t tbl_stride, const uint8_t*
   if (base >= n) return;
   const int cnt = (int)min((int64_t)kChunk, n - base);
   const int cnt_pad = (cnt + 127) & ~127;
+  const int iters = (cnt + kThreads - 1) / kThreads;  // rounds of 1024 elements that contain rows
+  const int n_sort = iters * kThreads;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t sentinel = nbits >= 32 ? 0xFFFFFFFFu : (1u << nbits) - 1u;  // sorts last (stable: after equal valid keys)
 
   // ---- keys
-  for (int i = tid; i < kChunk; i += kThreads) {
+  for (int i = tid; i < n_sort; i += kThreads) {
     uint32_t key = sentinel;
     if (i < cnt) {
       const int64_t row = base + i;
       if (ONEHOT) {
         key = (uint32_t)__ldg(onehot_off + row);
       } else {
+        int v[KT];  // all K loads of the row in flight at once
+#pragma unroll
+        for (int k = 0; k < KT; ++k) v[k] = k < K ? __ldg(tbl + (int64_t)k * tbl_stride + row) : -1;
+        asm volatile("" ::: "memory");  // keep the loads together (the compiler would sink each to its use)
         key = 0;
-        for (int k = 0; k < K; ++k)
-          if (bp.p[k] != 255 && __ldg(tbl + (int64_t)k * tbl_stride + row) >= 0) key |= 1u << bp.p[k];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) key |= ((uint32_t)(v[k] >= 0) & bp.en[k]) << bp.p[k];
       }
     }
     s.keys[0][i] = key;
@@ -65,32 +81,53 @@ k_build_plan(const int32_t* __restrict__ tbl, int64_t tbl_stride, const uint8_t*
   if (tid < kChunk / 128) s.tmask[tid] = 0;
   __syncthreads();
 
-  // ---- stable LSD radix sort of the chunk, 8 bits per pass
+  // ---- stable LSD radix sort of elements [0, n_sort): ceil(nbits / 10) passes.  Warp w owns the
+  // consecutive segment [w * seg, (w+1) * seg), seg = 32 * iters.  Ranking inside a warp uses one ballot per
+  // digit bit (lanes with my digit = AND over the bits of ballot or ~ballot) -- match_any is much slower
+  // here -- and the peer masks of the histogram phase are reused by the scatter.
   int cur = 0;
   const uint32_t lt = (1u << lane) - 1u;
-  for (int shift = 0; shift < nbits; shift += 8) {
-    for (int i = tid; i < kWarps * 256 / 2; i += kThreads) reinterpret_cast<uint32_t*>(s.hist)[i] = 0;
+  const int passes = (nbits + kDigitBits - 1) / kDigitBits;
+  const int dbits = (nbits + passes - 1) / passes;
+  const int nbins = 1 << dbits;
+  const int seg = 32 * iters;
+  for (int shift = 0; shift < nbits; shift += dbits) {
+    for (int i = tid; i < kWarps * nbins / 2; i += kThreads) reinterpret_cast<uint32_t*>(s.hist)[i] = 0;
     __syncthreads();
-    uint16_t* h = s.hist + warp * 256;
+    uint16_t* h = s.hist + warp * nbins;
     const uint32_t* kin = s.keys[cur];
     const uint16_t* iin = s.idx[cur];
+    uint32_t peers[kMaxIters];
     // per-warp digit histogram of the warp's segment
-#pragma unroll 1
-    for (int it = 0; it < kIters; ++it) {
-      const uint32_t d = (kin[warp * kSeg + it * 32 + lane] >> shift) & 255u;
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
-      if ((peers & lt) == 0) h[d] += (uint16_t)__popc(peers);
-      __syncwarp();
+#pragma unroll
+    for (int it = 0; it < kMaxIters; ++it) {
+      if (it < iters) {
+        const uint32_t d = (kin[warp * seg + it * 32 + lane] >> shift) & (uint32_t)(nbins - 1);
+        uint32_t pm = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < kDigitBits; ++b) {
+          if (b < dbits) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+            pm &= ((d >> b) & 1u) ? bal : ~bal;
+          }
+        }
+        peers[it] = pm;
+        if ((pm & lt) == 0) h[d] += (uint16_t)__popc(pm);
+        __syncwarp();
+      }
     }
     __syncthreads();
-    // exclusive scan over (digit major, warp minor)
+    // exclusive scan over (digit major, warp minor): nbins * 32 counters, consecutive ones per thread
     {
-      const int d = tid >> 2, w0 = (tid & 3) * 8;
-      int v[8], sum = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[j] = s.hist[(w0 + j) * 256 + d];
-        sum += v[j];
+      const int per = nbins * kWarps / kThreads;  // 32 (10 bits), 16, 8, ...; 0: only threads < nbins * 32 work
+      int sum = 0;
+      if (per >= 1) {
+        for (int j = 0; j < per; ++j) {
+          const int f = tid * per + j;  // flat index = digit * 32 + warp
+          sum += s.hist[(f & 31) * nbins + (f >> 5)];
+        }
+      } else if (tid < nbins * kWarps) {
+        sum = s.hist[(tid & 31) * nbins + (tid >> 5)];
       }
       int incl = sum;
 #pragma unroll
@@ -111,30 +148,38 @@ k_build_plan(const int32_t* __restrict__ tbl, int64_t tbl_stride, const uint8_t*
       }
       __syncthreads();
       int run = s.warp_sums[warp] + incl - sum;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s.hist[(w0 + j) * 256 + d] = (uint16_t)run;
-        run += v[j];
+      if (per >= 1) {
+        for (int j = 0; j < per; ++j) {
+          const int f = tid * per + j;
+          const int a = (f & 31) * nbins + (f >> 5);
+          const int v = s.hist[a];
+          s.hist[a] = (uint16_t)run;
+          run += v;
+        }
+      } else if (tid < nbins * kWarps) {
+        s.hist[(tid & 31) * nbins + (tid >> 5)] = (uint16_t)run;
       }
     }
     __syncthreads();
     // stable scatter
     uint32_t* kout = s.keys[cur ^ 1];
     uint16_t* iout = s.idx[cur ^ 1];
-#pragma unroll 1
-    for (int it = 0; it < kIters; ++it) {
-      const int i = warp * kSeg + it * 32 + lane;
-      const uint32_t key = kin[i];
-      const uint16_t id = iin[i];
-      const uint32_t d = (key >> shift) & 255u;
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
-      const int rank = __popc(peers & lt);
-      const int pos = (int)h[d] + rank;
-      __syncwarp();
-      if (rank == 0) h[d] = (uint16_t)(pos + __popc(peers));
-      __syncwarp();
-      kout[pos] = key;
-      iout[pos] = id;
+#pragma unroll
+    for (int it = 0; it < kMaxIters; ++it) {
+      if (it < iters) {
+        const int i = warp * seg + it * 32 + lane;
+        const uint32_t key = kin[i];
+        const uint16_t id = iin[i];
+        const uint32_t d = (key >> shift) & (uint32_t)(nbins - 1);
+        const uint32_t pm = peers[it];
+        const int rank = __popc(pm & lt);
+        const int pos = (int)h[d] + rank;
+        __syncwarp();
+        if (rank == 0) h[d] = (uint16_t)(pos + __popc(pm));
+        __syncwarp();
+        kout[pos] = key;
+        iout[pos] = id;
+      }
     }
     __syncthreads();
     cur ^= 1;
@@ -143,9 +188,7 @@ k_build_plan(const int32_t* __restrict__ tbl, int64_t tbl_stride, const uint8_t*
   // ---- permutation, permuted table, tile masks
   const uint16_t* sidx = s.idx[cur];
 #pragma unroll 1
-  for (int j = 0; j < kPerThread; ++j) {
-    const int i = tid + j * kThreads;  // warp-uniform tile: i >> 7
-    if (i >= cnt_pad) break;
+  for (int i = tid; i < cnt_pad; i += kThreads) {  // warp-uniform bound (multiple of 128) and tile (i >> 7)
     const int64_t r = i < cnt ? base + (int64_t)sidx[i] : -1;
     perm[base + i] = (int32_t)r;
     int par = -1, off = -1;
@@ -153,56 +196,94 @@ k_build_plan(const int32_t* __restrict__ tbl, int64_t tbl_stride, const uint8_t*
       par = __ldg(tbl + r);
       off = (int)__ldg(onehot_off + r);
     }
-    for (int k = 0; k < K; ++k) {
-      int e = -1;
-      if (r >= 0) e = ONEHOT ? (off == k ? par : -1) : __ldg(tbl + (int64_t)k * tbl_stride + r);
-      ptbl[(int64_t)k * pstride + base + i] = e;
-      const unsigned bal = __ballot_sync(0xffffffffu, e >= 0);
-      if (lane == 0 && bal) atomicOr(&s.tmask[i >> 7], 1u << k);
+    int v[KT];  // all K entries of the row in flight at once
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      v[k] = -1;
+      if (k < K && r >= 0) v[k] = ONEHOT ? (off == k ? par : -1) : __ldg(tbl + (int64_t)k * tbl_stride + r);
     }
+    asm volatile("" ::: "memory");
+    uint32_t wmask = 0;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      if (k < K) ptbl[(int64_t)k * pstride + base + i] = v[k];
+      if (__ballot_sync(0xffffffffu, v[k] >= 0)) wmask |= 1u << k;
+    }
+    if (lane == 0 && wmask) atomicOr(&s.tmask[i >> 7], wmask);
   }
   __syncthreads();
   if (tid < cnt_pad / 128) {
     const uint32_t m = s.tmask[tid];
     tile_mask[base / 128 + tid] = m ? m : 1u;  // a tile without any input still runs one (all-zero) block
   }
-}
 
-// Tiles by descending number of non-empty offsets, stable.  One CTA, warp w owns the bin popcount == 32 - w:
-// it counts its tiles, the bins are scanned, then it compacts its tiles in order (ballot ranks).
-__global__ void __launch_bounds__(1024, 1)
-k_plan_order(const uint32_t* __restrict__ tile_mask, const int32_t* __restrict__ n_dev, int32_t* __restrict__ order) {
-  __shared__ int bin_base[32];
-  const int T = (int)(((int64_t)*n_dev + 127) / 128);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int want = 32 - warp;
-  int total = 0;
-  for (int t0 = 0; t0 < T; t0 += 32) {
-    const int t = t0 + lane;
-    const bool mine = t < T && __popc(__ldg(tile_mask + t)) == want;
-    total += __popc(__ballot_sync(0xffffffffu, mine));
+  // ---- the last CTA to get here lists the tiles by descending number of non-empty offsets (stable):
+  // warp w owns the bin popcount == 32 - w, the bins are scanned, every warp compacts its tiles in order.
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int active = (unsigned int)((n + kChunk - 1) / kChunk);
+    const unsigned int prev = atomicAdd(done_counter, 1u);
+    s.is_last = prev == active - 1;
+    if (s.is_last) *done_counter = 0;  // ready for the next build on this stream
   }
-  if (lane == 0) bin_base[warp] = total;
+  __syncthreads();
+  if (!s.is_last) return;
+  __threadfence();
+  const int T = (int)((n + 127) / 128);
+  const int want = 32 - warp;
+  if (tid < 32) s.bin_base[tid] = 0;
+  __syncthreads();
+  for (int t = tid; t < T; t += kThreads) atomicAdd(&s.bin_base[32 - __popc(__ldcg(tile_mask + t))], 1);
   __syncthreads();
   if (warp == 0) {
-    const int v = bin_base[lane];
+    const int v = s.bin_base[lane];
     int incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int x = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += x;
     }
-    bin_base[lane] = incl - v;
+    s.bin_base[lane] = incl - v;
   }
   __syncthreads();
-  int pos = bin_base[warp];
+  int pos = s.bin_base[warp];
   for (int t0 = 0; t0 < T; t0 += 32) {
     const int t = t0 + lane;
-    const bool mine = t < T && __popc(__ldg(tile_mask + t)) == want;
+    const bool mine = t < T && __popc(__ldcg(tile_mask + t)) == want;
     const unsigned bal = __ballot_sync(0xffffffffu, mine);
     if (mine) order[pos + __popc(bal & ((1u << lane) - 1u))] = t;
     pos += __popc(bal);
   }
+}
+
+// per-device completion counter of the plan builder (zero between builds)
+unsigned int* g_done[64] = {nullptr};
+unsigned int* done_counter() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!g_done[dev]) {
+    unsigned int* p = nullptr;
+    if (cudaMalloc(&p, sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, sizeof(unsigned int));
+    g_done[dev] = p;
+  }
+  return g_done[dev];
+}
+
+template <int KT, bool ONEHOT>
+int launch_plan(unsigned grid, cudaStream_t stream, const int32_t* tbl, int64_t tbl_stride, const uint8_t* onehot_off,
+                const int32_t* n_dev, int K, int nbits, const BitPos& bp, int32_t* perm, uint32_t* tmask, int32_t* order,
+                int32_t* ptbl, int64_t pstride, unsigned int* counter) {
+  static bool once = false;
+  if (!once) {
+    MM3D_CUDA(cudaFuncSetAttribute(k_build_plan<KT, ONEHOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(PlanSmem)));
+    once = true;
+  }
+  k_build_plan<KT, ONEHOT><<<grid, kThreads, sizeof(PlanSmem), stream>>>(tbl, tbl_stride, onehot_off, n_dev, K, nbits, bp,
+                                                                        perm, tmask, order, ptbl, pstride, counter);
+  return MM3D_OK;
 }
 
 }  // namespace
@@ -229,47 +310,43 @@ extern "C" int mm3d_build_plan(const int32_t* tbl, int64_t tbl_stride, const uin
   int32_t* order = (int32_t*)(b + mm3d_plan_off_order(n_cap));
   int32_t* ptbl = (int32_t*)(b + mm3d_plan_off_tbl(n_cap));
   const int64_t pstride = mm3d_plan_tiles(n_cap) * 128;
+  unsigned int* counter = done_counter();
+  MM3D_REQUIRE(counter, MM3D_ERR_CUDA, "plan: could not allocate the completion counter");
 
   BitPos bp;
   int nbits;
-  for (int k = 0; k < 32; ++k) bp.p[k] = 255;
+  for (int k = 0; k < 32; ++k) bp.p[k] = 0, bp.en[k] = 0;
   if (onehot_off) {
     nbits = 1;
     while ((1 << nbits) < K) ++nbits;
   } else if (K == 27) {
-    // 3^3: centre (always present) left out; corners most significant, then edges, then faces
-    int bit = 25;
-    for (int cls = 3; cls >= 1; --cls)
-      for (int k = 0; k < 27; ++k) {
-        const int dx = k / 9 - 1, dy = (k / 3) % 3 - 1, dz = k % 3 - 1;
-        if (abs(dx) + abs(dy) + abs(dz) == cls) bp.p[k] = (uint8_t)bit--;
-      }
-    nbits = 26;
+    int edge = 17, face = 5;
+    for (int k = 0; k < 27; ++k) {
+      const int dx = k / 9 - 1, dy = (k / 3) % 3 - 1, dz = k % 3 - 1;
+      const int cls = abs(dx) + abs(dy) + abs(dz);
+      if (cls == 0) continue;
+      bp.en[k] = 1;
+      bp.p[k] = (uint8_t)(cls == 3 ? 18 : cls == 2 ? edge-- : face--);
+    }
+    nbits = 19;
   } else {
-    for (int k = 0; k < K; ++k) bp.p[k] = (uint8_t)k;
+    for (int k = 0; k < K; ++k) bp.p[k] = (uint8_t)k, bp.en[k] = 1;
     nbits = K;
   }
   const unsigned grid = (unsigned)mm3d_cdiv(n_cap, kChunk);
-  const size_t smem = sizeof(PlanSmem);
-  if (onehot_off) {
-    static bool once = false;
-    if (!once) {
-      MM3D_CUDA(cudaFuncSetAttribute(k_build_plan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      once = true;
-    }
-    k_build_plan<true><<<grid, kThreads, smem, stream>>>(tbl, tbl_stride, onehot_off, n_dev, K, nbits, bp, perm, tmask,
-                                                         ptbl, pstride);
-  } else {
-    static bool once = false;
-    if (!once) {
-      MM3D_CUDA(cudaFuncSetAttribute(k_build_plan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      once = true;
-    }
-    k_build_plan<false><<<grid, kThreads, smem, stream>>>(tbl, tbl_stride, onehot_off, n_dev, K, nbits, bp, perm, tmask,
-                                                          ptbl, pstride);
-  }
-  k_plan_order<<<1, 1024, 0, stream>>>(tmask, n_dev, order);
-  mm3d_count_launches(2);
+  int rc;
+  if (onehot_off && K <= 8)
+    rc = launch_plan<8, true>(grid, stream, tbl, tbl_stride, onehot_off, n_dev, K, nbits, bp, perm, tmask, order, ptbl, pstride, counter);
+  else if (onehot_off)
+    rc = launch_plan<32, true>(grid, stream, tbl, tbl_stride, onehot_off, n_dev, K, nbits, bp, perm, tmask, order, ptbl, pstride, counter);
+  else if (K == 27)
+    rc = launch_plan<27, false>(grid, stream, tbl, tbl_stride, onehot_off, n_dev, K, nbits, bp, perm, tmask, order, ptbl, pstride, counter);
+  else if (K <= 8)
+    rc = launch_plan<8, false>(grid, stream, tbl, tbl_stride, onehot_off, n_dev, K, nbits, bp, perm, tmask, order, ptbl, pstride, counter);
+  else
+    rc = launch_plan<32, false>(grid, stream, tbl, tbl_stride, onehot_off, n_dev, K, nbits, bp, perm, tmask, order, ptbl, pstride, counter);
+  if (rc) return rc;
+  mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_build_plan");
   return MM3D_OK;
 }
