@@ -114,6 +114,21 @@ MM3D_API size_t mm3d_plan_bytes(int64_t n_cap, int K);
 MM3D_API int mm3d_build_plan(const int32_t* tbl, int64_t tbl_stride, const uint8_t* onehot_off,
                     const int32_t* n_dev, int64_t n_cap, int K, void* plan, size_t plan_bytes,
                     mm3d_stream_t stream);
+/* Several plans in ONE launch (the tables of all levels of a forward: their builds are independent and each
+ * keeps only a few SMs busy).  n_rows_hint: the row count if the host knows it (sizes the launch; 0 = use
+ * n_cap); the authoritative count is still *n_dev and must not exceed the hint. */
+typedef struct mm3d_plan_desc {
+  const int32_t* tbl;
+  int64_t tbl_stride;
+  const uint8_t* onehot_off;
+  const int32_t* n_dev;
+  int64_t n_cap;
+  int64_t n_rows_hint;
+  int K;
+  void* plan;
+  size_t plan_bytes;
+} mm3d_plan_desc;
+MM3D_API int mm3d_build_plans(const mm3d_plan_desc* descs_host, int n_plans, mm3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * I/O layers (replace SCN InputLayer_updateOutput/updateGradInput, OutputLayer_*).

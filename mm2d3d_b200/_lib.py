@@ -48,6 +48,7 @@ SIGNATURES = {
     "mm3d_conv_workspace_bytes": (_sz, [_i64, _i64, _i, _i, _i, _i]),
     "mm3d_plan_bytes": (_sz, [_i64, _i]),
     "mm3d_build_plan": (_i, [_p, _i64, _p, _p, _i64, _i, _p, _sz, _p]),
+    "mm3d_build_plans": (_i, [_p, _i, _p]),
     "mm3d_conv_fwd": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i, _p, _i64, _p, _p, _i64, _i, _i, _p, _sz, _p]),
     "mm3d_conv_wgrad": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i, _p, _i64, _p, _p, _i64, _i, _i, _p, _sz, _p]),
     "mm3d_bnrelu_workspace_bytes": (_sz, [_i]),
@@ -62,6 +63,12 @@ SIGNATURES = {
     "mm3d_unet_forward": (_i, [_i, _i, _i, _i, _i, _f, _f, _p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p, _sz, _p]),
     "mm3d_unet_backward": (_i, [_i, _i, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _sz, _p, _sz, _p]),
 }
+
+class PlanDesc(C.Structure):
+    """``mm3d_plan_desc`` of include/mm3d.h."""
+    _fields_ = [("tbl", _p), ("tbl_stride", _i64), ("onehot_off", _p), ("n_dev", _p), ("n_cap", _i64),
+                ("n_rows_hint", _i64), ("K", _i), ("plan", _p), ("plan_bytes", _sz)]
+
 
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here = library / header mismatch

@@ -39,17 +39,42 @@ struct PlanSmem {
   int is_last;
 };
 
+// One table of a batched build: the launch covers `blocks` CTAs for it starting at CTA `block0`.
+struct PlanItem {
+  const int32_t* tbl;
+  int64_t tbl_stride;
+  const uint8_t* onehot_off;
+  const int32_t* n_dev;
+  int32_t* perm;
+  uint32_t* tile_mask;
+  int32_t* order;
+  int32_t* ptbl;
+  int64_t pstride;
+  int K, nbits, kind, block0;  // kind: 0 = 3^3 table, 1 = other dense table with K <= 8, 2 = (parent, offset) K <= 8,
+                               //       3 / 4 = generic dense / (parent, offset) with K <= 32
+};
+constexpr int kMaxBatch = 32;
+struct PlanBatch {
+  int n;
+  PlanItem item[kMaxBatch];
+  BitPos bp[2];  // [0] the 3^3 key layout, [1] identity (bit k = offset k)
+};
+
 // KT = compile-time bound of the offset loops (27, 8 or 32 = generic); K <= KT is the real count.
 template <int KT, bool ONEHOT>
-__global__ void __launch_bounds__(kThreads, 1)
-k_build_plan(const int32_t* __restrict__ tbl, int64_t tbl_stride, const uint8_t* __restrict__ onehot_off,
-             const int32_t* __restrict__ n_dev, int K, int nbits, BitPos bp, int32_t* __restrict__ perm,
-             uint32_t* __restrict__ tile_mask, int32_t* __restrict__ order, int32_t* __restrict__ ptbl, int64_t pstride,
-             unsigned int* __restrict__ done_counter) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  PlanSmem& s = *reinterpret_cast<PlanSmem*>(smem_raw);
-  const int64_t n = *n_dev;
-  const int64_t base = (int64_t)blockIdx.x * kChunk;
+__device__ __forceinline__ void build_plan_chunk(PlanSmem& s, const PlanItem& it_, const BitPos& bp, int chunk,
+                                                 unsigned int* __restrict__ done_counter) {
+  const int32_t* __restrict__ tbl = it_.tbl;
+  const int64_t tbl_stride = it_.tbl_stride;
+  const uint8_t* __restrict__ onehot_off = it_.onehot_off;
+  const int K = it_.K, nbits = it_.nbits;
+  int32_t* __restrict__ perm = it_.perm;
+  uint32_t* __restrict__ tile_mask = it_.tile_mask;
+  int32_t* __restrict__ order = it_.order;
+  int32_t* __restrict__ ptbl = it_.ptbl;
+  const int64_t pstride = it_.pstride;
+  const int64_t n = *it_.n_dev;
+  const int64_t base = (int64_t)chunk * kChunk;
   if (base >= n) return;
   const int cnt = (int)min((int64_t)kChunk, n - base);
   const int cnt_pad = (cnt + 127) & ~127;
@@ -222,7 +247,7 @@ k_build_plan(const int32_t* __restrict__ tbl, int64_t tbl_stride, const uint8_t*
   __threadfence();
   __syncthreads();
   if (tid == 0) {
-    const unsigned int active = (unsigned int)((n + kChunk - 1) / kChunk);
+    const unsigned int active = (unsigned int)((n + kChunk - 1) / kChunk);  // CTAs that got past the row-count test
     const unsigned int prev = atomicAdd(done_counter, 1u);
     s.is_last = prev == active - 1;
     if (s.is_last) *done_counter = 0;  // ready for the next build on this stream
@@ -248,42 +273,51 @@ k_build_plan(const int32_t* __restrict__ tbl, int64_t tbl_stride, const uint8_t*
   }
   __syncthreads();
   int pos = s.bin_base[warp];
-  for (int t0 = 0; t0 < T; t0 += 32) {
-    const int t = t0 + lane;
-    const bool mine = t < T && __popc(__ldcg(tile_mask + t)) == want;
-    const unsigned bal = __ballot_sync(0xffffffffu, mine);
-    if (mine) order[pos + __popc(bal & ((1u << lane) - 1u))] = t;
-    pos += __popc(bal);
+  uint32_t* sm = &s.keys[0][0];  // the sort buffers are free now: stage 16384 masks at a time
+  for (int b0 = 0; b0 < T; b0 += 2 * kChunk) {
+    const int nb = min(2 * kChunk, T - b0);
+    __syncthreads();
+    for (int t = tid; t < nb; t += kThreads) sm[t] = __ldcg(tile_mask + b0 + t);
+    __syncthreads();
+    for (int t0 = 0; t0 < nb; t0 += 32) {
+      const int t = t0 + lane;
+      const bool mine = t < nb && __popc(sm[t]) == want;
+      const unsigned bal = __ballot_sync(0xffffffffu, mine);
+      if (mine) order[pos + __popc(bal & ((1u << lane) - 1u))] = b0 + t;
+      pos += __popc(bal);
+    }
   }
 }
 
-// per-device completion counter of the plan builder (zero between builds)
+// per-device completion counters of the plan builder, one per table of a batch (zero between builds)
 unsigned int* g_done[64] = {nullptr};
-unsigned int* done_counter() {
+unsigned int* done_counters() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   if (!g_done[dev]) {
     unsigned int* p = nullptr;
-    if (cudaMalloc(&p, sizeof(unsigned int)) != cudaSuccess) return nullptr;
-    cudaMemset(p, 0, sizeof(unsigned int));
+    if (cudaMalloc(&p, kMaxBatch * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, kMaxBatch * sizeof(unsigned int));
     g_done[dev] = p;
   }
   return g_done[dev];
 }
 
-template <int KT, bool ONEHOT>
-int launch_plan(unsigned grid, cudaStream_t stream, const int32_t* tbl, int64_t tbl_stride, const uint8_t* onehot_off,
-                const int32_t* n_dev, int K, int nbits, const BitPos& bp, int32_t* perm, uint32_t* tmask, int32_t* order,
-                int32_t* ptbl, int64_t pstride, unsigned int* counter) {
-  static bool once = false;
-  if (!once) {
-    MM3D_CUDA(cudaFuncSetAttribute(k_build_plan<KT, ONEHOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)sizeof(PlanSmem)));
-    once = true;
+__global__ void __launch_bounds__(kThreads, 1)
+k_build_plans(const __grid_constant__ PlanBatch batch, unsigned int* __restrict__ done_counters) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  PlanSmem& s = *reinterpret_cast<PlanSmem*>(smem_raw);
+  int i = 0;
+  while (i + 1 < batch.n && (int)blockIdx.x >= batch.item[i + 1].block0) ++i;
+  const PlanItem& it = batch.item[i];
+  const int chunk = (int)blockIdx.x - it.block0;
+  switch (it.kind) {
+    case 0: build_plan_chunk<27, false>(s, it, batch.bp[0], chunk, done_counters + i); break;
+    case 1: build_plan_chunk<8, false>(s, it, batch.bp[1], chunk, done_counters + i); break;
+    case 2: build_plan_chunk<8, true>(s, it, batch.bp[1], chunk, done_counters + i); break;
+    case 3: build_plan_chunk<32, false>(s, it, batch.bp[1], chunk, done_counters + i); break;
+    default: build_plan_chunk<32, true>(s, it, batch.bp[1], chunk, done_counters + i); break;
   }
-  k_build_plan<KT, ONEHOT><<<grid, kThreads, sizeof(PlanSmem), stream>>>(tbl, tbl_stride, onehot_off, n_dev, K, nbits, bp,
-                                                                        perm, tmask, order, ptbl, pstride, counter);
-  return MM3D_OK;
 }
 
 }  // namespace
@@ -293,60 +327,79 @@ extern "C" size_t mm3d_plan_bytes(int64_t n_cap, int K) {
   return mm3d_plan_size(n_cap, K);
 }
 
-extern "C" int mm3d_build_plan(const int32_t* tbl, int64_t tbl_stride, const uint8_t* onehot_off,
-                               const int32_t* n_dev, int64_t n_cap, int K, void* plan, size_t plan_bytes,
-                               mm3d_stream_t stream_) {
+extern "C" int mm3d_build_plans(const mm3d_plan_desc* descs, int n_plans, mm3d_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  MM3D_REQUIRE(K > 0 && K <= 32, MM3D_ERR_INVALID, "plan: K must be in (0, 32]");
-  MM3D_REQUIRE(n_cap >= 0 && n_cap < (1ll << 31) - 128, MM3D_ERR_UNSUPPORTED, "plan: too many rows");
-  if (n_cap == 0) return MM3D_OK;
-  MM3D_REQUIRE(tbl && n_dev && plan, MM3D_ERR_INVALID, "plan: null pointer");
-  MM3D_REQUIRE(onehot_off || tbl_stride >= n_cap, MM3D_ERR_INVALID, "plan: tbl_stride < n_cap");
-  MM3D_REQUIRE(plan_bytes >= mm3d_plan_size(n_cap, K), MM3D_ERR_WORKSPACE, "plan: buffer too small");
-  MM3D_REQUIRE(((uintptr_t)plan & 255) == 0, MM3D_ERR_INVALID, "plan: buffer must be 256-byte aligned");
-  char* b = (char*)plan;
-  int32_t* perm = (int32_t*)b;
-  uint32_t* tmask = (uint32_t*)(b + mm3d_plan_off_mask(n_cap));
-  int32_t* order = (int32_t*)(b + mm3d_plan_off_order(n_cap));
-  int32_t* ptbl = (int32_t*)(b + mm3d_plan_off_tbl(n_cap));
-  const int64_t pstride = mm3d_plan_tiles(n_cap) * 128;
-  unsigned int* counter = done_counter();
-  MM3D_REQUIRE(counter, MM3D_ERR_CUDA, "plan: could not allocate the completion counter");
-
-  BitPos bp;
-  int nbits;
-  for (int k = 0; k < 32; ++k) bp.p[k] = 0, bp.en[k] = 0;
-  if (onehot_off) {
-    nbits = 1;
-    while ((1 << nbits) < K) ++nbits;
-  } else if (K == 27) {
+  MM3D_REQUIRE(n_plans >= 0 && (n_plans == 0 || descs), MM3D_ERR_INVALID, "plans: bad descriptor array");
+  unsigned int* counters = done_counters();
+  MM3D_REQUIRE(counters, MM3D_ERR_CUDA, "plans: could not allocate the completion counters");
+  static bool once = false;
+  if (!once) {
+    MM3D_CUDA(cudaFuncSetAttribute(k_build_plans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PlanSmem)));
+    once = true;
+  }
+  for (int first = 0; first < n_plans; first += kMaxBatch) {
+    PlanBatch batch;
+    batch.n = 0;
+    int blocks = 0;
+    // key layouts: 3^3 -> bit 18 = any corner, 17..6 = edges, 5..0 = faces (centre left out); else bit k = offset k
+    for (int k = 0; k < 32; ++k) {
+      batch.bp[0].p[k] = 0; batch.bp[0].en[k] = 0;
+      batch.bp[1].p[k] = (uint8_t)k; batch.bp[1].en[k] = 1;
+    }
     int edge = 17, face = 5;
     for (int k = 0; k < 27; ++k) {
       const int dx = k / 9 - 1, dy = (k / 3) % 3 - 1, dz = k % 3 - 1;
       const int cls = abs(dx) + abs(dy) + abs(dz);
       if (cls == 0) continue;
-      bp.en[k] = 1;
-      bp.p[k] = (uint8_t)(cls == 3 ? 18 : cls == 2 ? edge-- : face--);
+      batch.bp[0].en[k] = 1;
+      batch.bp[0].p[k] = (uint8_t)(cls == 3 ? 18 : cls == 2 ? edge-- : face--);
     }
-    nbits = 19;
-  } else {
-    for (int k = 0; k < K; ++k) bp.p[k] = (uint8_t)k, bp.en[k] = 1;
-    nbits = K;
+    for (int i = first; i < n_plans && i < first + kMaxBatch; ++i) {
+      const mm3d_plan_desc& d = descs[i];
+      MM3D_REQUIRE(d.K > 0 && d.K <= 32, MM3D_ERR_INVALID, "plan: K must be in (0, 32]");
+      MM3D_REQUIRE(d.n_cap >= 0 && d.n_cap < (1ll << 31) - 128, MM3D_ERR_UNSUPPORTED, "plan: too many rows");
+      if (d.n_cap == 0) continue;
+      MM3D_REQUIRE(d.tbl && d.n_dev && d.plan, MM3D_ERR_INVALID, "plan: null pointer");
+      MM3D_REQUIRE(d.onehot_off || d.tbl_stride >= d.n_cap, MM3D_ERR_INVALID, "plan: tbl_stride < n_cap");
+      MM3D_REQUIRE(d.plan_bytes >= mm3d_plan_size(d.n_cap, d.K), MM3D_ERR_WORKSPACE, "plan: buffer too small");
+      MM3D_REQUIRE(((uintptr_t)d.plan & 255) == 0, MM3D_ERR_INVALID, "plan: buffer must be 256-byte aligned");
+      const int64_t rows = d.n_rows_hint > 0 && d.n_rows_hint < d.n_cap ? d.n_rows_hint : d.n_cap;
+      char* b = (char*)d.plan;
+      PlanItem& it = batch.item[batch.n++];
+      it.tbl = d.tbl; it.tbl_stride = d.tbl_stride; it.onehot_off = d.onehot_off; it.n_dev = d.n_dev;
+      it.perm = (int32_t*)b;
+      it.tile_mask = (uint32_t*)(b + mm3d_plan_off_mask(d.n_cap));
+      it.order = (int32_t*)(b + mm3d_plan_off_order(d.n_cap));
+      it.ptbl = (int32_t*)(b + mm3d_plan_off_tbl(d.n_cap));
+      it.pstride = mm3d_plan_tiles(d.n_cap) * 128;
+      it.K = d.K;
+      if (d.onehot_off) {
+        it.nbits = 1;
+        while ((1 << it.nbits) < d.K) ++it.nbits;
+        it.kind = d.K <= 8 ? 2 : 4;
+      } else if (d.K == 27) {
+        it.nbits = 19;
+        it.kind = 0;
+      } else {
+        it.nbits = d.K;
+        it.kind = d.K <= 8 ? 1 : 3;
+      }
+      it.block0 = blocks;
+      blocks += (int)mm3d_cdiv(rows, kChunk);
+    }
+    if (blocks == 0) continue;
+    k_build_plans<<<(unsigned)blocks, kThreads, sizeof(PlanSmem), stream>>>(batch, counters);
+    mm3d_count_launches(1);
+    MM3D_CHECK_LAUNCH("mm3d_build_plans");
   }
-  const unsigned grid = (unsigned)mm3d_cdiv(n_cap, kChunk);
-  int rc;
-  if (onehot_off && K <= 8)
-    rc = launch_plan<8, true>(grid, stream, tbl, tbl_stride, onehot_off, n_dev, K, nbits, bp, perm, tmask, order, ptbl, pstride, counter);
-  else if (onehot_off)
-    rc = launch_plan<32, true>(grid, stream, tbl, tbl_stride, onehot_off, n_dev, K, nbits, bp, perm, tmask, order, ptbl, pstride, counter);
-  else if (K == 27)
-    rc = launch_plan<27, false>(grid, stream, tbl, tbl_stride, onehot_off, n_dev, K, nbits, bp, perm, tmask, order, ptbl, pstride, counter);
-  else if (K <= 8)
-    rc = launch_plan<8, false>(grid, stream, tbl, tbl_stride, onehot_off, n_dev, K, nbits, bp, perm, tmask, order, ptbl, pstride, counter);
-  else
-    rc = launch_plan<32, false>(grid, stream, tbl, tbl_stride, onehot_off, n_dev, K, nbits, bp, perm, tmask, order, ptbl, pstride, counter);
-  if (rc) return rc;
-  mm3d_count_launches(1);
-  MM3D_CHECK_LAUNCH("mm3d_build_plan");
   return MM3D_OK;
+}
+
+extern "C" int mm3d_build_plan(const int32_t* tbl, int64_t tbl_stride, const uint8_t* onehot_off,
+                               const int32_t* n_dev, int64_t n_cap, int K, void* plan, size_t plan_bytes,
+                               mm3d_stream_t stream) {
+  mm3d_plan_desc d;
+  d.tbl = tbl; d.tbl_stride = tbl_stride; d.onehot_off = onehot_off; d.n_dev = n_dev; d.n_cap = n_cap;
+  d.n_rows_hint = 0; d.K = K; d.plan = plan; d.plan_bytes = plan_bytes;
+  return mm3d_build_plans(&d, 1, stream);
 }

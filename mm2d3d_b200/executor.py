@@ -55,6 +55,14 @@ def fusable(net) -> bool:
 def _level_desc(meta: Metadata, num_planes: int, spatial0: int, plans: bool):
     W = _lib.LEVEL_DESC_WORDS
     desc = (C.c_int64 * (W * num_planes))()
+    if plans:  # every table of the forward in one launch
+        specs, s = [], spatial0
+        for l in range(num_planes):
+            specs.append(("smc", s))
+            if l + 1 < num_planes:
+                specs += [("down", s), ("up", s)]
+            s //= 2
+        meta.build_plans(specs)
     s = spatial0
     for l in range(num_planes):
         lv = meta.nbr(s)

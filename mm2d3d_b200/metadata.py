@@ -165,31 +165,54 @@ class Metadata:
                 self._sync_counts()
         return fine, self.levels[s // 2]
 
-    def plan(self, kind: str, spatial_size: int):
-        """(device pointer, capacity) of the row plan (``csrc/plan.cuh``) of a rule table, built on first
-        use on the current stream (no host synchronisation).  ``kind``: ``"smc"`` = 3^3 table of the level,
-        ``"down"`` = child table of the 2/2 convolution FROM ``spatial_size`` (rows = coarse voxels),
-        ``"up"`` = its (parent, offset) table (rows = fine voxels).  The tensor-core modes need it."""
-        lv = self.nbr(spatial_size) if kind == "smc" else self.down(spatial_size)[0]
-        hit = lv.plans.get(kind)
-        if hit is None:
-            K = 27 if kind == "smc" else 8
-            with torch.cuda.device(self.device):
-                nbytes = lib.mm3d_plan_bytes(lv.cap, K)
-                buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+    def _plan_level(self, kind, spatial_size):
+        return self.nbr(spatial_size) if kind == "smc" else self.down(spatial_size)[0]
+
+    def build_plans(self, specs):
+        """Build the row plans (``csrc/plan.cuh``) of several rule tables in ONE launch on the current stream
+        (no host synchronisation).  ``specs``: iterable of ``(kind, spatial_size)`` with ``kind`` ``"smc"`` =
+        3^3 table of the level, ``"down"`` = child table of the 2/2 convolution FROM ``spatial_size`` (rows =
+        coarse voxels), ``"up"`` = its (parent, offset) table (rows = fine voxels).  Already built plans are
+        skipped.  The tensor-core modes need them."""
+        todo = []
+        for kind, s in specs:
+            lv = self._plan_level(kind, s)
+            if kind not in lv.plans and (kind, int(s)) not in [(k, int(z)) for k, z, _ in todo]:
+                todo.append((kind, s, lv))
+        if not todo:
+            return
+        with torch.cuda.device(self.device):
+            sizes = []
+            for kind, s, lv in todo:
+                K = 27 if kind == "smc" else 8
+                sizes.append(_al(lib.mm3d_plan_bytes(lv.cap, K)))
+            buf = torch.empty(sum(sizes), dtype=torch.uint8, device=self.device)
+            descs = (_lib.PlanDesc * len(todo))()
+            off = 0
+            for d, (kind, s, lv), nbytes in zip(descs, todo, sizes):
                 if kind == "smc":
-                    tbl, stride, onehot, cnt = lv.ptr(lv.o_nbr), lv.tstride, None, self._count_ptr(lv)
+                    d.tbl, d.tbl_stride, d.onehot_off, cnt_lv = lv.ptr(lv.o_nbr), lv.tstride, None, lv
                 elif kind == "down":
-                    tbl, stride, onehot = lv.ptr(lv.o_child), lv.tstride, None
-                    cnt = self._count_ptr(self.levels[int(spatial_size) // 2])
+                    d.tbl, d.tbl_stride, d.onehot_off = lv.ptr(lv.o_child), lv.tstride, None
+                    cnt_lv = self.levels[int(s) // 2]
                 elif kind == "up":
-                    tbl, stride, onehot, cnt = lv.ptr(lv.o_parent), 0, lv.ptr(lv.o_off), self._count_ptr(lv)
+                    d.tbl, d.tbl_stride, d.onehot_off, cnt_lv = lv.ptr(lv.o_parent), 0, lv.ptr(lv.o_off), lv
                 else:
                     raise ValueError(kind)
-                check(lib.mm3d_build_plan(tbl, stride, onehot, cnt, lv.cap, K, buf.data_ptr(), nbytes,
-                                          _lib.stream_ptr()), "mm3d_build_plan")
-            hit = lv.plans[kind] = (buf, lv.cap)
-        return hit[0].data_ptr(), hit[1]
+                d.n_dev, d.n_cap, d.n_rows_hint = self._count_ptr(cnt_lv), lv.cap, (cnt_lv.n or 0)
+                d.K = 27 if kind == "smc" else 8
+                d.plan, d.plan_bytes = buf.data_ptr() + off, nbytes
+                lv.plans[kind] = (buf[off:off + nbytes], lv.cap)
+                off += nbytes
+            check(lib.mm3d_build_plans(descs, len(todo), _lib.stream_ptr()), "mm3d_build_plans")
+
+    def plan(self, kind: str, spatial_size: int):
+        """(device pointer, capacity) of one row plan, built on first use (see :meth:`build_plans`)."""
+        lv = self._plan_level(kind, spatial_size)
+        if kind not in lv.plans:
+            self.build_plans([(kind, spatial_size)])
+        buf, cap = lv.plans[kind]
+        return buf.data_ptr(), cap
 
     def plan_tensors(self, kind: str, spatial_size: int):
         """(perm int32 [T*128], tile_mask int32 [T], table int32 [K, T*128], tile order int32 [T]) views of a

@@ -94,13 +94,13 @@ def main():
 
     def plans():
         m = Metadata(locs, 4096, 7)
-        s = 4096
+        specs, s = [], 4096
         for l in range(7):
-            m.plan("smc", s)
+            specs.append(("smc", s))
             if l < 6:
-                m.plan("down", s)
-                m.plan("up", s)
+                specs += [("down", s), ("up", s)]
             s //= 2
+        m.build_plans(specs)
         return m
     t2, h2, _ = timed(plans)
     print(f"structure + 19 plans: GPU {t2:.2f} ms, host {h2:.2f} ms  -> plans {t2 - t:.2f} ms GPU")
