@@ -184,33 +184,8 @@ k_conv_tc(const TcParams p) {
       __syncwarp();
       const float* src0 = p.in + j * kKBlock;
       const bool half = (j == p.nb - 1) && p.last_w == 4;
-      if (!half) {
-        // 8 lanes per row (one per 16-byte chunk), 4 rows per pass: a full 128-byte line per row
-        const int c = lane & 7, rsub = lane >> 3;
-        const float* srcc = src0 + c * 4;
-#pragma unroll 8
-        for (int r0 = 0; r0 < kTileM; r0 += 4) {
-          const int r = r0 + rsub;
-          int nb_row;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nb_row) : "r"(ent + (uint32_t)r * 4u) : "memory");
-          const uint32_t dst = stage + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-          const bool ok = nb_row >= 0;
-          cp_async16(dst, ok ? srcc + (size_t)(uint32_t)nb_row * (uint32_t)p.c_in : p.in, ok ? 16u : 0u);
-        }
-      } else {
-        // 16-channel tail block: 4 lanes per row, 8 rows per pass; chunks 4..7 are never read by the MMA
-        const int c = lane & 3, rsub = lane >> 2;
-        const float* srcc = src0 + c * 4;
-#pragma unroll 8
-        for (int r0 = 0; r0 < kTileM; r0 += 8) {
-          const int r = r0 + rsub;
-          int nb_row;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nb_row) : "r"(ent + (uint32_t)r * 4u) : "memory");
-          const uint32_t dst = stage + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-          const bool ok = nb_row >= 0;
-          cp_async16(dst, ok ? srcc + (size_t)(uint32_t)nb_row * (uint32_t)p.c_in : p.in, ok ? 16u : 0u);
-        }
-      }
+      if (!half) gather_block<8, false>(stage, ent, p.in, src0, (uint32_t)p.c_in, lane);
+      else       gather_block<4, false>(stage, ent, p.in, src0, (uint32_t)p.c_in, lane);
       cp_async_arrive(a_full(warp));
       __syncwarp();  // the entry row is rewritten by the next item
       e = en;
@@ -223,7 +198,7 @@ k_conv_tc(const TcParams p) {
       const int ab = (int)(tile_iter & 1u);
       const int tile = (int)lmask[n_local + tile_iter];
       const int row = __ldg(p.perm + (int64_t)tile * kTileM + ew * 32 + lane);
-      if (!mbar_wait(acc_full(ab), (tile_iter >> 1) & 1u, abort_flag)) goto done;
+      if (!mbar_wait_sleep(acc_full(ab), (tile_iter >> 1) & 1u, abort_flag, 100)) goto done;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * p.n_pad);
       for (int c0 = 0; c0 < p.n_pad; c0 += 16) {

@@ -161,31 +161,8 @@ k_wgrad_tc(const WgParams p) {
       __syncwarp();
       const float* src0 = p.in + j * 32;
       const bool half = (j == p.nb - 1) && p.last_w == 4;
-      if (!half) {
-        const int c = lane & 7, rsub = lane >> 3;
-        const float* srcc = src0 + c * 4;
-#pragma unroll 8
-        for (int r0 = 0; r0 < kTileM; r0 += 4) {
-          const int r = r0 + rsub;
-          int nb_row;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nb_row) : "r"(ent + (uint32_t)r * 4u) : "memory");
-          const uint32_t dst = stage + (uint32_t)r * 128u + swz_base32(c, r);
-          const bool ok = nb_row >= 0;
-          cp_async16(dst, ok ? srcc + (size_t)(uint32_t)nb_row * (uint32_t)p.c_in : p.in, ok ? 16u : 0u);
-        }
-      } else {
-        const int c = lane & 3, rsub = lane >> 2;
-        const float* srcc = src0 + c * 4;
-#pragma unroll 8
-        for (int r0 = 0; r0 < kTileM; r0 += 8) {
-          const int r = r0 + rsub;
-          int nb_row;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nb_row) : "r"(ent + (uint32_t)r * 4u) : "memory");
-          const uint32_t dst = stage + (uint32_t)r * 128u + swz_base32(c, r);
-          const bool ok = nb_row >= 0;
-          cp_async16(dst, ok ? srcc + (size_t)(uint32_t)nb_row * (uint32_t)p.c_in : p.in, ok ? 16u : 0u);
-        }
-      }
+      if (!half) gather_block<8, true>(stage, ent, p.in, src0, (uint32_t)p.c_in, lane);
+      else       gather_block<4, true>(stage, ent, p.in, src0, (uint32_t)p.c_in, lane);
       cp_async_arrive(a_full(warp));
       __syncwarp();
       e = en;
@@ -200,7 +177,7 @@ k_wgrad_tc(const WgParams p) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) seen |= __shfl_xor_sync(0xffffffffu, seen, o);
     if (seen == 0) goto done;
-    if (!mbar_wait(acc_full, 0u, abort_flag)) goto done;
+    if (!mbar_wait_sleep(acc_full, 0u, abort_flag, 1000)) goto done;
     tc_fence_after();
     // accumulator row (= output channel) of this thread: M=128 -> lane i holds row i; M=64 -> row m sits in
     // lane 32*(m/16) + m%16 (16 lanes per sub-partition)
@@ -290,17 +267,21 @@ k_wgrad_tc(const WgParams p) {
       const uint32_t gb = g_base + (uint32_t)buf * g_bytes;
       asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ent + (uint32_t)lane * 8u), "r"(pr.x), "r"(pr.y) : "memory");
       __syncwarp();
-#pragma unroll 4
-      for (int r0 = 0; r0 < 64; r0 += 4) {
-        const int rl = r0 + (lane >> 3);
-        const int r = half * 64 + rl;
-        int row;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(row) : "r"(ent + (uint32_t)rl * 4u) : "memory");
-        const bool ok = row >= 0;
-        const float* src = p.dout + (int64_t)(ok ? row : 0) * p.c_out;
-        for (int ch = lane & 7; ch < nch; ch += 8)
-          cp_async16(gb + (uint32_t)(ch >> 3) * kStageBytes + (uint32_t)r * 128u + swz_base32(ch & 7, r), src + ch * 4,
-                     ok ? 16u : 0u);
+#pragma unroll 1
+      for (int r0 = 0; r0 < 64; r0 += 32) {
+        int rows[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rows[u]) : "r"(ent + (uint32_t)(r0 + u * 4 + (lane >> 3)) * 4u) : "memory");
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = half * 64 + r0 + u * 4 + (lane >> 3);
+          const bool ok = rows[u] >= 0;
+          const float* src = p.dout + (int64_t)(ok ? rows[u] : 0) * p.c_out;
+          for (int ch = lane & 7; ch < nch; ch += 8)
+            cp_async16(gb + (uint32_t)(ch >> 3) * kStageBytes + (uint32_t)r * 128u + swz_base32(ch & 7, r), src + ch * 4,
+                       ok ? 16u : 0u);
+        }
       }
       cp_async_arrive(g_full(buf));
       __syncwarp();

@@ -41,6 +41,17 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
   *abort_flag = 1;
   return false;
 }
+// Same, for waits that are expected to be long (an epilogue waiting for a whole tile or kernel): sleeps between
+// polls so that the warp does not take issue slots from the producers of its scheduler.
+__device__ __forceinline__ bool mbar_wait_sleep(uint32_t bar, uint32_t parity, volatile int* abort_flag, uint32_t ns) {
+  for (uint32_t i = 0; i < kSpinLimit; ++i) {
+    if (mbar_try_wait(bar, parity)) return true;
+    __nanosleep(ns);
+    if ((i & 255) == 255 && *abort_flag) return false;
+  }
+  *abort_flag = 1;
+  return false;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -77,6 +88,32 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, u
 // the mbarrier receives one arrival when all cp.async issued so far by this thread have landed
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// Gather one K-block: the 128 table entries sit in shared memory at `ent`; row r of the stage receives chunks
+// [0, W) of input row ent[r] starting at `src0` (or zeros when ent[r] < 0).  W = 8: 8 lanes per row, 4 rows per
+// pass; W = 4: 4 lanes per row, 8 rows per pass (chunks 4..7 of the stage are then never read).  Entries are
+// read eight passes at a time so that their shared-memory latency is paid once per batch, not once per row.
+template <int W, bool BASE32>
+__device__ __forceinline__ void gather_block(uint32_t stage, uint32_t ent, const float* __restrict__ base,
+                                             const float* __restrict__ src0, uint32_t row_floats, int lane) {
+  constexpr int kLanesPerRow = W, kRowsPerPass = 32 / W, kBatch = 8;
+  const int c = lane & (kLanesPerRow - 1), rsub = lane / kLanesPerRow;
+  const float* srcc = src0 + c * 4;
+#pragma unroll 1
+  for (int r0 = 0; r0 < 128; r0 += kRowsPerPass * kBatch) {
+    int rows[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u)
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rows[u]) : "r"(ent + (uint32_t)(r0 + u * kRowsPerPass + rsub) * 4u) : "memory");
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int r = r0 + u * kRowsPerPass + rsub;
+      const uint32_t off = BASE32 ? (uint32_t)((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4)) : (uint32_t)((c ^ (r & 7)) << 4);
+      const bool ok = rows[u] >= 0;
+      cp_async16(stage + (uint32_t)r * 128u + off, ok ? srcc + (size_t)(uint32_t)rows[u] * row_floats : base, ok ? 16u : 0u);
+    }
+  }
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
