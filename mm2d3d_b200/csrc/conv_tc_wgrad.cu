@@ -10,8 +10,9 @@
 // (16 tcgen05.mma of K=8 per stage), M = C_out (64 or 128 accumulator rows, taken from the dout
 // tile in 32-wide blocks), N = the stage's 32 (or 16) input channels.  Every (offset, channel block)
 // owns TMEM columns for the whole kernel; a CTA covers a group of offsets whose accumulators fit the
-// 512 columns (grid.y) and a slice of the tiles (grid.x), skips tiles without any of its offsets,
-// and adds its accumulators to dW once at the end (atomics: tile_splits * |dW|).
+// 512 columns and a slice of the tiles, skips tiles without any of its offsets, and adds its
+// accumulators to dW once at the end (atomics).  Groups and their CTA counts are balanced by the
+// expected frequency of the offsets (host side, mm3d_conv_wgrad_tc).
 //
 // Warp roles (S+7 warps): 0..S-1 gather producers (warp w owns ring stage w), S..S+3 epilogue
 // (TMEM -> atomics), S+4 MMA issuer + TMEM allocator, S+5 / S+6 dout-tile loaders (64 rows each).
@@ -40,11 +41,13 @@ struct WgParams {
   int64_t tstride;
   int c_in, c_out, K;
   int nb, last_w;   // channel blocks per offset, 16-byte chunks of the last one (8 or 4)
-  int gk;           // offsets per CTA group (grid.y groups)
   int mw;           // UMMA M: 64 (c_out <= 64) or 128
   int S, gbufs;
-  int num_tiles, tile_splits, tmem_cols;
-  int n_local;  // tiles per CTA (upper bound)
+  int num_tiles, tmem_cols;
+  int n_local;      // tiles per CTA (upper bound over the groups)
+  int groups;       // offset groups; group g owns the offsets of gmask[g] and CTAs [cta0[g], cta0[g+1])
+  uint32_t gmask[32];
+  uint16_t cta0[33];
   int* err;
 };
 
@@ -111,14 +114,16 @@ k_wgrad_tc(const WgParams p) {
   volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + kNumBars + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k0 = (int)blockIdx.y * p.gk;                 // first offset of this CTA's group
-  const int kn = min(p.gk, p.K - k0);
-  const uint32_t gmask = (kn >= 32 ? 0xFFFFFFFFu : ((1u << kn) - 1u)) << k0;
+  int grp = 0;  // this CTA's offset group, its index among the group's CTAs and their number
+  while (grp + 1 < p.groups && (int)blockIdx.x >= (int)p.cta0[grp + 1]) ++grp;
+  const uint32_t gmask = p.gmask[grp];
+  const int split = (int)blockIdx.x - (int)p.cta0[grp], splits = (int)p.cta0[grp + 1] - (int)p.cta0[grp];
+  const int kn = __popc(gmask);
 
   int n_local = p.n_local;
-  if (mm3d_plan_local_tile(p.order, p.num_tiles, p.tile_splits, (int)blockIdx.x, n_local - 1) < 0) --n_local;
+  while (n_local > 0 && mm3d_plan_local_tile(p.order, p.num_tiles, splits, split, n_local - 1) < 0) --n_local;
   for (int i = threadIdx.x; i < n_local; i += blockDim.x) {
-    const int t = mm3d_plan_local_tile(p.order, p.num_tiles, p.tile_splits, (int)blockIdx.x, i);
+    const int t = mm3d_plan_local_tile(p.order, p.num_tiles, splits, split, i);
     lmask[i] = __ldg(p.tile_mask + t) & gmask;
     lmask[n_local + i] = (uint32_t)t;
   }
@@ -185,14 +190,16 @@ k_wgrad_tc(const WgParams p) {
     const bool lane_ok = (p.mw == 128 || lane < 16) && co < p.c_out;
     // every CTA of a group flushes the same addresses: start each at a different offset so that the L2
     // atomic units do not serialise on one line at a time
-    const int rot = k0 + (int)(blockIdx.x % (unsigned)kn);
+    const int rot = (int)((unsigned)split * 5u % 32u);
     const uint32_t hi = seen & ~((1u << rot) - 1u), lo = seen & ((1u << rot) - 1u);
+    (void)kn;
     for (int part = 0; part < 2; ++part)
     for (uint32_t rem = part ? lo : hi; rem; rem &= rem - 1) {
       const int k = __ffs(rem) - 1;
       for (int j = 0; j < p.nb; ++j) {
         const int wj = (j == p.nb - 1 && p.last_w == 4) ? 16 : 32;
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((k - k0) * p.c_in + j * 32);
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) +
+                               (uint32_t)(__popc(gmask & ((1u << k) - 1u)) * p.c_in + j * 32);
         for (int c0 = 0; c0 < wj; c0 += 16) {
           float acc[16];
           tmem_ld16(taddr + (uint32_t)c0, acc);
@@ -228,7 +235,7 @@ k_wgrad_tc(const WgParams p) {
             tc_fence_after();
             const bool half = (j == p.nb - 1) && p.last_w == 4;
             const uint64_t a_desc = desc0 + desc_addr(a_base + (uint32_t)s * kStageBytes);
-            const uint32_t d_tmem = tmem_base + (uint32_t)((k - k0) * p.c_in + j * 32);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(__popc(gmask & ((1u << k) - 1u)) * p.c_in + j * 32);
             const uint32_t idesc = half ? idesc16 : idesc32;
             // per K-step of 8 rows: two 4-row swizzle atoms (SBO = 512 B, 1024 B per step); the dout tile's
             // 32-wide M blocks are LBO apart
@@ -331,7 +338,6 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
   p.num_tiles = (int)mm3d_cdiv(n_out, kTileM);
   int gk = 512 / c_in;  // TMEM: c_in accumulator columns per offset
   if (gk > K) gk = K;
-  p.gk = gk;
   const int groups = (K + gk - 1) / gk;
   int cols = 32;
   while (cols < gk * c_in) cols <<= 1;
@@ -339,13 +345,64 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
   // one CTA per SM: 4 ring stages + as many dout-tile buffers as fit
   p.S = 4;
   p.gbufs = p.mw == 128 ? 2 : kMaxGBufs;
-  const int per_sm = 1;
-  int tile_splits = MM3D_NUM_SMS * per_sm / groups;
-  if (tile_splits < 1) tile_splits = 1;
-  if (tile_splits > p.num_tiles) tile_splits = p.num_tiles;
-  p.tile_splits = tile_splits;
   p.err = mm3d_device_err_flag();
-  p.n_local = (p.num_tiles + tile_splits - 1) / tile_splits;
+  // Offsets -> groups and CTAs -> groups by expected work.  How often an offset occurs is data dependent; as a
+  // prior, the centre of a 3^3 table is present for every row, faces often, edges sometimes, corners rarely.
+  // Heaviest offsets are dealt first, each to the lightest group with a free accumulator slot; then every group
+  // gets CTAs in proportion to its weight (its tiles are split among them).
+  {
+    float w[32];
+    int idx[32];
+    for (int k = 0; k < K; ++k) {
+      idx[k] = k;
+      w[k] = 1.f;
+      if (K == 27) {
+        const int cls = abs(k / 9 - 1) + abs((k / 3) % 3 - 1) + abs(k % 3 - 1);
+        w[k] = cls == 0 ? 1.f : cls == 1 ? 0.4f : cls == 2 ? 0.15f : 0.03f;
+      }
+    }
+    for (int a = 0; a < K; ++a)
+      for (int b = a + 1; b < K; ++b)
+        if (w[idx[b]] > w[idx[a]]) { const int t = idx[a]; idx[a] = idx[b]; idx[b] = t; }
+    float gw[32];
+    int gn[32];
+    for (int g = 0; g < groups; ++g) { gw[g] = 0.f; gn[g] = 0; p.gmask[g] = 0; }
+    for (int a = 0; a < K; ++a) {
+      int best = -1;
+      for (int g = 0; g < groups; ++g)
+        if (gn[g] < gk && (best < 0 || gw[g] < gw[best])) best = g;
+      p.gmask[best] |= 1u << idx[a];
+      gw[best] += w[idx[a]] + 0.05f;  // + per-tile cost of loading the dout tile
+      ++gn[best];
+    }
+    int total_ctas = MM3D_NUM_SMS;
+    if (total_ctas < groups) total_ctas = groups;
+    float wsum = 0.f;
+    for (int g = 0; g < groups; ++g) wsum += gw[g];
+    int ctas[32], used = 0;
+    for (int g = 0; g < groups; ++g) {
+      ctas[g] = (int)(total_ctas * gw[g] / wsum);
+      if (ctas[g] < 1) ctas[g] = 1;
+      if (ctas[g] > p.num_tiles) ctas[g] = p.num_tiles;
+      used += ctas[g];
+    }
+    for (int spare = total_ctas - used; spare > 0;) {  // hand out the rest, heaviest load per CTA first
+      int best = -1;
+      for (int g = 0; g < groups; ++g)
+        if (ctas[g] < p.num_tiles && (best < 0 || gw[g] / ctas[g] > gw[best] / ctas[best])) best = g;
+      if (best < 0) break;
+      ++ctas[best];
+      --spare;
+    }
+    p.groups = groups;
+    p.cta0[0] = 0;
+    int min_ctas = ctas[0];
+    for (int g = 0; g < groups; ++g) {
+      p.cta0[g + 1] = (uint16_t)(p.cta0[g] + ctas[g]);
+      if (ctas[g] < min_ctas) min_ctas = ctas[g];
+    }
+    p.n_local = (p.num_tiles + min_ctas - 1) / min_ctas;
+  }
   const size_t smem = 1024 + (size_t)p.S * kStageBytes + (size_t)(p.S + 1) * kEntBytes +
                       (size_t)p.gbufs * (p.mw / 32) * kStageBytes + ((size_t)p.n_local * 8 + 15) / 16 * 16 +
                       8 * (2 * kMaxStages + 2 * kMaxGBufs + 1) + 64;
@@ -356,8 +413,7 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
     MM3D_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     once = true;
   }
-  dim3 grid((unsigned)tile_splits, (unsigned)groups);
-  k_wgrad_tc<<<grid, (p.S + 7) * 32, smem, stream>>>(p);
+  k_wgrad_tc<<<(unsigned)p.cta0[p.groups], (p.S + 7) * 32, smem, stream>>>(p);
   mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_conv_wgrad_tc");
   return MM3D_OK;
