@@ -34,7 +34,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("MM3D_BENCH_MODE", "fp32"), choices=["fp32", "tf32", "bf16"])
+    # BASELINE.json configs[1] names both arithmetic modes; the tensor-core one (tcgen05 kind::tf32, FP32
+    # accumulate, parity bar 1e-2) is the headline, the FP32 SIMT parity mode (1e-4) is timed beside it
+    ap.add_argument("--mode", default=os.environ.get("MM3D_BENCH_MODE", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--no-fp32-side", action="store_true", help="skip the short FP32-mode measurement")
     ap.add_argument("--shape", default="nuscenes", choices=["nuscenes", "semantickitti"])
     ap.add_argument("--batch", type=int, default=8, help="scans per GPU per step")
     ap.add_argument("--rotate", type=int, default=4, help="distinct resident input batches cycled through")
@@ -70,8 +73,15 @@ class ClockSampler:
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 3.0:  # nvidia-smi needs a moment before its first line
+                time.sleep(0.02)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Samples taken from now on are 'under load' (the timed region)."""
+        self.first = len(self.rows)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -87,7 +97,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        first = getattr(self, "first", 0)
+        rows = self.rows[first:] if len(self.rows) > first else self.rows[-1:]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -347,6 +359,10 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        for i in range(3):  # keep the GPU busy until the sampler's first in-load line is due
+            step(i)
+        barrier()
+        sampler.mark()
     launches0 = _lib.lib.mm3d_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -356,6 +372,15 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.lib.mm3d_kernel_launches() - launches0
+    if rank == 0 and ms < 400.0:  # a short timed region can fall between two 50 ms samples: run on under the sampler
+        t_end = time.time() + 0.4
+        i = 0
+        while time.time() < t_end:
+            step(i)
+            i += 1
+            if i % 8 == 0:
+                torch.cuda.synchronize()
+        barrier()
     clocks = sampler.stop() if rank == 0 else None
 
     # end to end: pinned host inputs -> device -> fwd+bwd (-> all-reduce) -> scalar back to the host
@@ -385,6 +410,34 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_reference_scans_per_s(5, 1, args.shape)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        fp32_side = None
+        if world == 1 and args.mode != "fp32" and not args.no_fp32_side:
+            scn_mod.set_conv_mode("fp32")
+            try:
+                for i in range(3):
+                    step(i)
+                barrier()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for i in range(8):
+                    step(i)
+                f1.record()
+                barrier()
+                fms = f0.elapsed_time(f1) / 8
+                fp32_side = {"value": args.batch / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms, "steps": 8, "dtype": "f32",
+                             "note": "same workload in the FP32 SIMT parity mode (activations/gradients within 1e-4)"}
+            finally:
+                scn_mod.set_conv_mode(args.mode)
+        if roofline is not None:
+            # DRAM traffic of the dominant kernel comes from a separate `ncu --set full` capture (profiles/)
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                key = roofline["kernel"].split(" @ ")[0] + f" rows {roofline['kernel'].split('(')[1].split(' rows')[0]} {args.mode}"
+                if key in tr:
+                    roofline["traffic"] = tr[key]["dram_bytes"]
+                    roofline["traffic_source"] = tr[key]["source"]
+            except Exception:
+                pass
         scans = world * args.batch * args.steps
         avg_pts = sum(n_points) / len(n_points)
         line = {
@@ -410,6 +463,8 @@ def run_ours(args):
         }
         if roofline is not None:
             line["roofline"] = roofline
+        if fp32_side is not None:
+            line["fp32_mode"] = fp32_side
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

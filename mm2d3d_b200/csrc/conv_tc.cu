@@ -221,8 +221,9 @@ k_conv_tc(const TcParams p) {
       mbar_arrive(acc_empty(ab));
     }
   } else if (warp == S + 4) {
-    // =================================================================== MMA issuer
-    if (lane == 0) {
+    // =================================================================== MMA issuer: the whole warp walks the
+    // items (warp-uniform control flow), one elected lane issues
+    {
       const uint32_t idesc = make_idesc_tf32(kTileM, p.n_pad);
       const uint64_t desc0 = make_desc_sw128(0);
       ItemWalk it;
@@ -241,22 +242,25 @@ k_conv_tc(const TcParams p) {
           const int ksteps = (it.j == p.nb - 1 ? p.last_w : 8) >> 1;
           if (!mbar_wait(a_full(s), ph, abort_flag)) { ok = false; break; }
           tc_fence_after();
-          const uint64_t a_desc = desc0 + desc_addr(a_base + (uint32_t)s * kStageBytes);
-          const uint64_t b_desc = desc0 + desc_addr(b_base + (uint32_t)s * b_stride);
-          umma_tf32(d_tmem, a_desc, b_desc, idesc, first ? 0u : 1u);
-          umma_tf32(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);  // +32 bytes per K-step of 8
-          if (ksteps == 4) {
-            umma_tf32(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
-            umma_tf32(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+          if (elect_one()) {
+            const uint64_t a_desc = desc0 + desc_addr(a_base + (uint32_t)s * kStageBytes);
+            const uint64_t b_desc = desc0 + desc_addr(b_base + (uint32_t)s * b_stride);
+            umma_tf32(d_tmem, a_desc, b_desc, idesc, first ? 0u : 1u);
+            umma_tf32(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);  // +32 bytes per K-step of 8
+            if (ksteps == 4) {
+              umma_tf32(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+              umma_tf32(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+            }
+            umma_commit(a_empty(s));  // frees the stage and its weight block
+            if (last) umma_commit(acc_full(ab));
           }
-          umma_commit(a_empty(s));  // frees the stage and its weight block
+          __syncwarp();
           first = false;
           if (++s == S) { s = 0; ph ^= 1u; }
           it.next();
           if (last) break;
         }
         if (!ok) break;
-        umma_commit(acc_full(ab));
         ++tile_iter;
       }
     }

@@ -214,8 +214,9 @@ k_wgrad_tc(const WgParams p) {
     }
     tc_fence_before();
   } else if (warp == S + 4) {
-    // =================================================================== MMA issuer
-    if (lane == 0) {
+    // =================================================================== MMA issuer: the whole warp walks the
+    // items (warp-uniform control flow), one elected lane issues
+    {
       const uint32_t idesc32 = make_idesc_tf32(p.mw, 32, 1, 1), idesc16 = make_idesc_tf32(p.mw, 16, 1, 1);
       const uint64_t desc0 = make_desc_sw128_base32(0, kStageBytes, 512);
       TileWalk tw;
@@ -225,7 +226,7 @@ k_wgrad_tc(const WgParams p) {
       bool ok = true, any = false;
       while (tw.valid() && ok) {
         const int buf = (int)(gi % (uint32_t)p.gbufs);
-        if (!mbar_wait(g_full(buf), (gi / (uint32_t)p.gbufs) & 1u, abort_flag)) break;
+        if (!mbar_wait(g_full(buf), (gi / (uint32_t)p.gbufs) & 1u, abort_flag)) { ok = false; break; }
         const uint64_t g_desc = desc0 + desc_addr(g_base + (uint32_t)buf * g_bytes);
         for (uint32_t rem = tw.m; rem && ok; rem &= rem - 1) {
           const int k = __ffs(rem) - 1;
@@ -233,27 +234,32 @@ k_wgrad_tc(const WgParams p) {
           for (int j = 0; j < p.nb; ++j) {
             if (!mbar_wait(a_full(s), ph, abort_flag)) { ok = false; break; }
             tc_fence_after();
-            const bool half = (j == p.nb - 1) && p.last_w == 4;
-            const uint64_t a_desc = desc0 + desc_addr(a_base + (uint32_t)s * kStageBytes);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(__popc(gmask & ((1u << k) - 1u)) * p.c_in + j * 32);
-            const uint32_t idesc = half ? idesc16 : idesc32;
-            // per K-step of 8 rows: two 4-row swizzle atoms (SBO = 512 B, 1024 B per step); the dout tile's
-            // 32-wide M blocks are LBO apart
-            umma_tf32(d_tmem, g_desc, a_desc, idesc, acc0);
+            if (elect_one()) {
+              const bool half = (j == p.nb - 1) && p.last_w == 4;
+              const uint64_t a_desc = desc0 + desc_addr(a_base + (uint32_t)s * kStageBytes);
+              const uint32_t d_tmem = tmem_base + (uint32_t)(__popc(gmask & ((1u << k) - 1u)) * p.c_in + j * 32);
+              const uint32_t idesc = half ? idesc16 : idesc32;
+              // per K-step of 8 rows: two 4-row swizzle atoms (SBO = 512 B, 1024 B per step); the dout tile's
+              // 32-wide M blocks are LBO apart
+              umma_tf32(d_tmem, g_desc, a_desc, idesc, acc0);
 #pragma unroll
-            for (int r8 = 1; r8 < 16; ++r8) umma_tf32(d_tmem, g_desc + r8 * 64, a_desc + r8 * 64, idesc, 1u);
-            umma_commit(a_empty(s));
+              for (int r8 = 1; r8 < 16; ++r8) umma_tf32(d_tmem, g_desc + r8 * 64, a_desc + r8 * 64, idesc, 1u);
+              umma_commit(a_empty(s));
+            }
+            __syncwarp();
             if (++s == S) { s = 0; ph ^= 1u; }
           }
           seen |= 1u << k;
         }
         if (!ok) break;
-        umma_commit(g_empty(buf));
+        if (elect_one()) umma_commit(g_empty(buf));
+        __syncwarp();
         any = true;
         ++gi;
         tw.next_tile();
       }
-      if (ok && any) umma_commit(acc_full);
+      if (ok && any && elect_one()) umma_commit(acc_full);
+      __syncwarp();
     }
   } else {
     // =================================================================== dout-tile loaders: 64 rows each
