@@ -16,6 +16,8 @@
 // Parameter pointers come in the module tree's order (Appendix B of SURVEY.md):
 //   stem.w | per level: pre_bn{gamma,beta,rmean,rvar} pre.w [dn_bn{4} dn.w <deeper level> up_bn{4}
 //   up.w post_bn{4} post.w] | head_bn{4}
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -127,6 +129,28 @@ __global__ void k_split_add(const float* __restrict__ dj, const float* __restric
   }
 }
 
+// Backward runs the weight gradients on a second stream: a layer's wgrad only feeds the optimiser, while its
+// dgrad is on the critical chain, and neither kernel fills the GPU alone at the deeper levels.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[64];
+  int n_ev = 0, next = 0;
+  bool ok = false;
+};
+SideStream* side_stream() {
+  static SideStream pool[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& s = pool[dev];
+  if (!s.ok) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (s.n_ev = 0; s.n_ev < 64; ++s.n_ev)
+      if (cudaEventCreateWithFlags(&s.ev[s.n_ev], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    s.ok = true;
+  }
+  return &s;
+}
+
 struct Ctx {
   Net* net;
   void* const* params;
@@ -138,7 +162,21 @@ struct Ctx {
   int training;
   int pi;  // running parameter index
   int rc;
+  SideStream* side = nullptr;  // backward only; NULL = everything on `stream`
 };
+
+// stream for a layer's weight gradient: the side stream once everything enqueued on the main stream so far
+// (the layer's d_out) is done
+cudaStream_t wgrad_stream(Ctx& c) {
+  if (!c.side || c.rc) return c.stream;
+  cudaEvent_t e = c.side->ev[c.side->next++ % c.side->n_ev];
+  if (cudaEventRecord(e, c.stream) != cudaSuccess || cudaStreamWaitEvent(c.side->stream, e, 0) != cudaSuccess) {
+    mm3d_set_error("unet backward: could not fork the weight-gradient stream");
+    c.rc = MM3D_ERR_CUDA;
+    return c.stream;
+  }
+  return c.side->stream;
+}
 
 #define EX(call)                   \
   do {                             \
@@ -176,22 +214,33 @@ void conv_bwd(Ctx& c, Kind kind, int l, const float* in, int c_in, const float* 
   const LevelMeta& f = c.net->lv[l];
   const int64_t nc = l + 1 < c.net->L ? c.net->lv[l + 1].n : 0;
   const int md = c.net->mode;
+  cudaStream_t ws = wgrad_stream(c);  // d_out is complete on the main stream at this point
   if (kind == SMC) {
+    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, f.n, c_out, d_w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap, 0,
+                       md, nullptr, 0, ws));
     if (d_in)
       EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, f.n, c_in, w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap,
                        MM3D_CONV_TRANSPOSE_W | MM3D_CONV_MIRROR_K, md, c.scratch, c.scratch_bytes, c.stream));
-    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, f.n, c_out, d_w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap, 0,
-                       md, c.scratch, c.scratch_bytes, c.stream));
   } else if (kind == DOWN) {  // in: fine rows, d_out: coarse rows
+    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, nc, c_out, d_w, 8, f.child, f.tstride, nullptr, f.plan_down, f.plan_cap, 0,
+                       md, nullptr, 0, ws));
     EX(mm3d_conv_fwd(d_out, nc, c_out, d_in, f.n, c_in, w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap,
                      MM3D_CONV_TRANSPOSE_W, md, c.scratch, c.scratch_bytes, c.stream));
-    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, nc, c_out, d_w, 8, f.child, f.tstride, nullptr, f.plan_down, f.plan_cap, 0,
-                       md, c.scratch, c.scratch_bytes, c.stream));
   } else {  // UP: in: coarse rows, d_out: fine rows
+    EX(mm3d_conv_wgrad(in, nc, c_in, d_out, f.n, c_out, d_w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap, 0, md,
+                       nullptr, 0, ws));
     EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, nc, c_in, w, 8, f.child, f.tstride, nullptr, f.plan_down, f.plan_cap,
                      MM3D_CONV_TRANSPOSE_W, md, c.scratch, c.scratch_bytes, c.stream));
-    EX(mm3d_conv_wgrad(in, nc, c_in, d_out, f.n, c_out, d_w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap, 0, md,
-                       c.scratch, c.scratch_bytes, c.stream));
+  }
+}
+
+// main stream waits for everything enqueued on the side stream so far
+void join_side(Ctx& c) {
+  if (!c.side || c.rc) return;
+  cudaEvent_t e = c.side->ev[c.side->next++ % c.side->n_ev];
+  if (cudaEventRecord(e, c.side->stream) != cudaSuccess || cudaStreamWaitEvent(c.stream, e, 0) != cudaSuccess) {
+    mm3d_set_error("unet backward: could not join the weight-gradient stream");
+    c.rc = MM3D_ERR_CUDA;
   }
 }
 
@@ -275,7 +324,8 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
   float* d_A = g.f(n, p);
   conv_bwd(c, SMC, l, B.A, p, d_Y, p, P(c, pbase + 4), d_A, Gp(c, pbase + 4));
   bn_bwd(c, pbase, B.X, d_A, d_X, n, p, B.s_pre);
-  g.off = mark;  // temporaries of this level are dead once d_X is written (d_X belongs to the caller)
+  if (!c.side) g.off = mark;  // temporaries of this level are dead once d_X is written -- unless the side stream
+                              // may still be reading a d_out (the workspace bound assumes no reuse anyway)
 }
 
 int fill_net(Net& net, int in_channels, int m, int num_planes, int mode, const int64_t* level_desc, int64_t n_points) {
@@ -394,6 +444,7 @@ MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode
   MM3D_REQUIRE(bp.ok, MM3D_ERR_WORKSPACE, "activation workspace too small");
   MM3D_REQUIRE(tmp_bytes >= bwd_temp_bytes(net), MM3D_ERR_WORKSPACE, "backward workspace too small");
   Ctx c{&net, params, grads, scratch, scratch_bytes, (cudaStream_t)stream_, 0.f, 0.f, training, 0, 0};
+  c.side = getenv("MM3D_NO_SIDE_STREAM") ? nullptr : side_stream();
   Bump g{(char*)tmp, 0, tmp_bytes, true};
   const int64_t n0 = net.lv[0].n;
   const int head = 1 + level_slots(0, net.L);
@@ -412,6 +463,7 @@ MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode
     launch_pad_cols(c, w_stem, 27, net.cin * m, wp, net.cin_k * m);
     float* d_wp = g.f(27, (int64_t)net.cin_k * m);
     conv_bwd(c, SMC, 0, net.Vp, net.cin_k, d_X0, m, wp, d_Vp, d_wp);
+    join_side(c);  // d_wp comes from the side stream
     launch_pad_cols(c, d_wp, 27, net.cin_k * m, d_w, net.cin * m);  // slice the real channels back out
     if (d_feats) {
       float* d_V = g.f(n0, net.cin);
@@ -422,6 +474,7 @@ MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode
     conv_bwd(c, SMC, 0, net.V, net.cin, d_X0, m, w_stem, d_Vp, d_w);
     if (d_feats) EX(mm3d_input_bwd(d_Vp, p2v, npts, n_points, net.cin, 4, d_feats, c.stream));
   }
+  join_side(c);  // everything after this call on `stream` sees the weight gradients
   MM3D_REQUIRE(g.ok, MM3D_ERR_WORKSPACE, "backward workspace overflow");
   return c.rc;
 }
