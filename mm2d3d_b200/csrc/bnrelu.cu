@@ -1,7 +1,9 @@
 // BatchNorm + (leaky) ReLU over the active rows of a sparse tensor (replaces
 // SparseConvNet's BatchNormalization_f_train / _f_test / _b, which launch <= 16 thread blocks).
 //
-// HBM-bound: forward = read x (stats) + read x + write y; backward = 2 x (read x, dy) + write dx.
+// HBM-bound: forward = read x (stats) + read x again (L2) + write y; backward = read x, dy + again (L2) +
+// write dx.  Training forward and backward are ONE launch each: per-CTA partial sums -> FP64 atomics ->
+// grid-wide barrier (all CTAs co-resident) -> every CTA normalises the rows it summed.
 // Layout: a CTA's 256 threads tile (rows_pass x CV) where CV = C / VEC channel vectors, so a
 // warp reads consecutive float4s of consecutive rows (fully coalesced) and every thread keeps
 // one fixed channel vector; per-thread FP32 partials are combined in FP64 (shared, then global
@@ -54,39 +56,7 @@ __device__ __forceinline__ void block_flush(const float (&s)[VEC], const float (
   }
 }
 
-// ---- forward statistics: sums[0..C) = sum x, sums[C..2C) = sum x^2
-template <int VEC>
-__global__ void __launch_bounds__(kThreads)
-k_bn_stats(const float* __restrict__ x, int64_t n, int c, double* __restrict__ sums) {
-  const int cv = c / VEC;
-  const int rows_pass = kThreads / cv;
-  const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
-  float s[VEC], q[VEC];
-#pragma unroll
-  for (int j = 0; j < VEC; ++j) s[j] = q[j] = 0.f;
-  if (r < rows_pass) {
-    const int64_t stride = (int64_t)gridDim.x * rows_pass;
-    int64_t row = (int64_t)blockIdx.x * rows_pass + r;
-    for (; row + 3 * stride < n; row += 4 * stride) {  // four independent loads in flight
-      float t[4][VEC];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) vload<VEC>(x + (row + u * stride) * c + v * VEC, t[u]);
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) { s[j] += t[u][j]; q[j] = fmaf(t[u][j], t[u][j], q[j]); }
-    }
-    for (; row < n; row += stride) {
-      float t[VEC];
-      vload<VEC>(x + row * c + v * VEC, t);
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) { s[j] += t[j]; q[j] = fmaf(t[j], t[j], q[j]); }
-    }
-  }
-  block_flush<VEC>(s, q, c, cv, rows_pass, r, v, sums);
-}
-
-// ---- forward apply (+ finalise: save_mean / save_invstd / running stats by block 0)
+// ---- inference forward: normalise with the running statistics (+ optional copy of them to save_*)
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
 k_bn_apply(const float* __restrict__ x, float* __restrict__ y, int64_t n, int c,
@@ -142,83 +112,190 @@ k_bn_apply(const float* __restrict__ x, float* __restrict__ y, int64_t n, int c,
   }
 }
 
-// ---- backward reductions: sums[0..C) = sum d, sums[C..2C) = sum d * xhat, d = dy * relu'(y)
+// ---- grid-wide barrier for the single-launch kernels below.  All CTAs of these grids are co-resident (the
+// grid is capped well below the device's capacity for 256-thread CTAs with a few KB of shared memory), so
+// waiting for the others is safe; the wait is bounded anyway and raises *err instead of hanging.
+// sync[0] counts arrivals, sync[1] counts CTAs that are done reading the totals: the last of those zeroes
+// the totals and both counters, so the workspace is clean for the next call on the stream.
+__device__ __forceinline__ bool grid_arrive_and_wait(unsigned int* sync, int* err) {
+  __shared__ int s_ok;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(sync, 1u);
+    int ok = 0;
+    for (unsigned int i = 0; i < (1u << 22); ++i) {
+      if (*reinterpret_cast<volatile unsigned int*>(sync) >= gridDim.x) { ok = 1; break; }
+      __nanosleep(64);
+    }
+    if (!ok && err) atomicExch(err, 1);
+    s_ok = ok;
+    __threadfence();
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
+__device__ __forceinline__ void grid_release(unsigned int* sync, double* sums, int n_sums) {
+  __shared__ int s_last;
+  __syncthreads();  // every thread of the CTA has read what it needs from sums
+  if (threadIdx.x == 0) s_last = atomicAdd(sync + 1, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {
+    for (int i = threadIdx.x; i < n_sums; i += kThreads) sums[i] = 0.0;
+    if (threadIdx.x == 0) { sync[0] = 0; sync[1] = 0; }
+  }
+}
+
+// ---- training forward in ONE launch: statistics, grid barrier, normalise + ReLU.  A CTA re-reads exactly the
+// rows it summed, so the second read comes from L2 / L1 instead of HBM.
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
-k_bn_bwd_stats(const float* __restrict__ x, const float* __restrict__ dy, int64_t n, int c,
+k_bn_fwd_fused(const float* __restrict__ x, float* __restrict__ y, int64_t n, int c,
                const float* __restrict__ gamma, const float* __restrict__ beta,
-               const float* __restrict__ save_mean, const float* __restrict__ save_invstd, float leak,
-               double* __restrict__ sums) {
+               float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+               double* sums, unsigned int* sync, float eps, float momentum, float leak, int* err) {
   const int cv = c / VEC;
   const int rows_pass = kThreads / cv;
   const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
-  float s[VEC], q[VEC];
+  const int64_t stride = (int64_t)gridDim.x * rows_pass;
+  {
+    float s[VEC], q[VEC];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) s[j] = q[j] = 0.f;
-  if (r < rows_pass) {
-    float mean[VEC], invstd[VEC], scale[VEC], bet[VEC];
+    for (int j = 0; j < VEC; ++j) s[j] = q[j] = 0.f;
+    if (r < rows_pass) {
+      int64_t row = (int64_t)blockIdx.x * rows_pass + r;
+      for (; row + 3 * stride < n; row += 4 * stride) {  // four independent loads in flight
+        float t[4][VEC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) vload<VEC>(x + (row + u * stride) * c + v * VEC, t[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) { s[j] += t[u][j]; q[j] = fmaf(t[u][j], t[u][j], q[j]); }
+      }
+      for (; row < n; row += stride) {
+        float t[VEC];
+        vload<VEC>(x + row * c + v * VEC, t);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { s[j] += t[j]; q[j] = fmaf(t[j], t[j], q[j]); }
+      }
+    }
+    block_flush<VEC>(s, q, c, cv, rows_pass, r, v, sums);
+  }
+  grid_arrive_and_wait(sync, err);
+  float* s_mean = reinterpret_cast<float*>(s_acc);
+  float* s_scale = s_mean + c;
+  __syncthreads();  // block_flush's use of the shared buffer is over
+  for (int i = threadIdx.x; i < c; i += kThreads) {
+    const double m = __ldcg(sums + i) / (double)n;
+    double var = __ldcg(sums + c + i) / (double)n - m * m;
+    if (var < 0.0) var = 0.0;
+    const float mean = (float)m, invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (blockIdx.x == 0) {
+      save_mean[i] = mean;
+      save_invstd[i] = invstd;
+      const double unbiased = var * ((double)n / (double)(n > 1 ? n - 1 : 1));
+      running_mean[i] = momentum * running_mean[i] + (1.f - momentum) * mean;
+      running_var[i] = momentum * running_var[i] + (1.f - momentum) * (float)unbiased;
+    }
+    s_mean[i] = mean;
+    s_scale[i] = invstd * gamma[i];
+  }
+  grid_release(sync, sums, 2 * c);
+  if (r >= rows_pass) return;
+  float mean[VEC], scale[VEC], bet[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    mean[j] = s_mean[v * VEC + j];
+    scale[j] = s_scale[v * VEC + j];
+    bet[j] = __ldg(beta + v * VEC + j);
+  }
+  for (int64_t row = (int64_t)blockIdx.x * rows_pass + r; row < n; row += stride) {
+    float t[VEC];
+    vload<VEC>(x + row * c + v * VEC, t);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      mean[j] = __ldg(save_mean + v * VEC + j);
-      invstd[j] = __ldg(save_invstd + v * VEC + j);
-      scale[j] = invstd[j] * __ldg(gamma + v * VEC + j);
-      bet[j] = __ldg(beta + v * VEC + j);
+      const float o = fmaf(t[j] - mean[j], scale[j], bet[j]);
+      t[j] = o > 0.f ? o : o * leak;
     }
-    const int64_t stride = (int64_t)gridDim.x * rows_pass;
-    int64_t row = (int64_t)blockIdx.x * rows_pass + r;
-    for (; row < n; row += 2 * stride) {  // two rows (four loads) in flight
-      float t[2][VEC], g[2][VEC];
-      const bool second = row + stride < n;
-      vload<VEC>(x + row * c + v * VEC, t[0]);
-      vload<VEC>(dy + row * c + v * VEC, g[0]);
-      if (second) {
-        vload<VEC>(x + (row + stride) * c + v * VEC, t[1]);
-        vload<VEC>(dy + (row + stride) * c + v * VEC, g[1]);
-      }
+    vstore<VEC>(y + row * c + v * VEC, t);
+  }
+}
+
+// ---- backward in ONE launch: reductions, grid barrier, dx (+ d_gamma / d_beta by CTA 0)
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int64_t n, int c,
+               const float* __restrict__ gamma, const float* __restrict__ beta,
+               const float* __restrict__ save_mean, const float* __restrict__ save_invstd, float leak,
+               double* sums, unsigned int* sync, float* d_gamma, float* d_beta, int training, int* err) {
+  const int cv = c / VEC;
+  const int rows_pass = kThreads / cv;
+  const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
+  const int64_t stride = (int64_t)gridDim.x * rows_pass;
+  float mean[VEC], invstd[VEC], scale[VEC], bet[VEC];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (u == 1 && !second) break;
+  for (int j = 0; j < VEC; ++j) mean[j] = invstd[j] = scale[j] = bet[j] = 0.f;
+  if (r < rows_pass) {
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          const float xc = t[u][j] - mean[j];
-          const float o = fmaf(xc, scale[j], bet[j]);
-          const float d = o > 0.f ? g[u][j] : g[u][j] * leak;
-          s[j] += d;
-          q[j] = fmaf(d, xc * invstd[j], q[j]);
+    for (int j = 0; j < VEC; ++j) {
+      const int ch = v * VEC + j;
+      mean[j] = __ldg(save_mean + ch);
+      invstd[j] = __ldg(save_invstd + ch);
+      scale[j] = invstd[j] * __ldg(gamma + ch);
+      bet[j] = __ldg(beta + ch);
+    }
+  }
+  {
+    float s[VEC], q[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) s[j] = q[j] = 0.f;
+    if (r < rows_pass) {
+      int64_t row = (int64_t)blockIdx.x * rows_pass + r;
+      for (; row < n; row += 2 * stride) {  // two rows (four loads) in flight
+        float t[2][VEC], g[2][VEC];
+        const bool second = row + stride < n;
+        vload<VEC>(x + row * c + v * VEC, t[0]);
+        vload<VEC>(dy + row * c + v * VEC, g[0]);
+        if (second) {
+          vload<VEC>(x + (row + stride) * c + v * VEC, t[1]);
+          vload<VEC>(dy + (row + stride) * c + v * VEC, g[1]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (u == 1 && !second) break;
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            const float xc = t[u][j] - mean[j];
+            const float o = fmaf(xc, scale[j], bet[j]);
+            const float d = o > 0.f ? g[u][j] : g[u][j] * leak;
+            s[j] += d;
+            q[j] = fmaf(d, xc * invstd[j], q[j]);
+          }
         }
       }
     }
+    block_flush<VEC>(s, q, c, cv, rows_pass, r, v, sums);
   }
-  block_flush<VEC>(s, q, c, cv, rows_pass, r, v, sums);
-}
-
-template <int VEC>
-__global__ void __launch_bounds__(kThreads)
-k_bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int64_t n, int c,
-               const float* __restrict__ gamma, const float* __restrict__ beta,
-               const float* __restrict__ save_mean, const float* __restrict__ save_invstd, float leak,
-               const double* __restrict__ sums, float* d_gamma, float* d_beta, int training) {
-  const int cv = c / VEC;
-  const int rows_pass = kThreads / cv;
-  const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
+  grid_arrive_and_wait(sync, err);
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < c; i += kThreads) {
-      d_beta[i] = (float)sums[i];
-      d_gamma[i] = (float)sums[c + i];
+      d_beta[i] = (float)__ldcg(sums + i);
+      d_gamma[i] = (float)__ldcg(sums + c + i);
     }
-  if (r >= rows_pass) return;
-  float mean[VEC], invstd[VEC], scale[VEC], bet[VEC], md[VEC], mdx[VEC];
+  float md[VEC], mdx[VEC];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    const int ch = v * VEC + j;
-    mean[j] = __ldg(save_mean + ch);
-    invstd[j] = __ldg(save_invstd + ch);
-    scale[j] = invstd[j] * __ldg(gamma + ch);
-    bet[j] = __ldg(beta + ch);
-    md[j] = training ? (float)(sums[ch] / (double)n) : 0.f;
-    mdx[j] = training ? (float)(sums[c + ch] / (double)n) : 0.f;
+  for (int j = 0; j < VEC; ++j) md[j] = mdx[j] = 0.f;
+  if (r < rows_pass && training) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      md[j] = (float)(__ldcg(sums + v * VEC + j) / (double)n);
+      mdx[j] = (float)(__ldcg(sums + c + v * VEC + j) / (double)n);
+    }
   }
-  for (int64_t row = (int64_t)blockIdx.x * rows_pass + r; row < n; row += (int64_t)gridDim.x * rows_pass) {
+  grid_release(sync, sums, 2 * c);
+  if (r >= rows_pass) return;
+  for (int64_t row = (int64_t)blockIdx.x * rows_pass + r; row < n; row += stride) {
     float t[VEC], g[VEC];
     vload<VEC>(x + row * c + v * VEC, t);
     vload<VEC>(dy + row * c + v * VEC, g);
@@ -237,13 +314,16 @@ int bn_grid(int64_t n, int cv) {
   const int rows_pass = kThreads / cv;
   int64_t g = mm3d_cdiv(n, (int64_t)rows_pass * 4);  // >= 4 rows per thread when there is enough work
   if (g < 1) g = 1;
-  const int64_t cap = (int64_t)MM3D_NUM_SMS * 4;
+  const int64_t cap = (int64_t)MM3D_NUM_SMS * 3;  // co-resident with room to spare (single-launch kernels wait on each other)
   return (int)(g < cap ? g : cap);
 }
 
 }  // namespace
 
-extern "C" size_t mm3d_bnrelu_workspace_bytes(int c) { return mm3d_align(sizeof(double) * 2 * (size_t)c); }
+int* mm3d_device_err_flag();  // conv_tc.cu
+
+// workspace: 2*c doubles of totals + two 32-bit counters of the grid barrier
+extern "C" size_t mm3d_bnrelu_workspace_bytes(int c) { return mm3d_align(sizeof(double) * 2 * (size_t)c + 16); }
 
 #define BN_DISPATCH(KERNEL, ...)                                                        \
   do {                                                                                  \
@@ -251,11 +331,11 @@ extern "C" size_t mm3d_bnrelu_workspace_bytes(int c) { return mm3d_align(sizeof(
     else      KERNEL<1><<<grid, kThreads, smem, stream>>>(__VA_ARGS__);                 \
   } while (0)
 
-extern "C" int mm3d_bnrelu_fwd(const float* x, float* y, int64_t n, int c, const float* gamma, const float* beta,
-                               float* running_mean, float* running_var, float* save_mean, float* save_invstd,
-                               float eps, float momentum, float leakiness, int training,
-                               void* ws, size_t ws_bytes, mm3d_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+// ws_clean: the workspace is known to be all zero (the kernels leave it that way), skip the memset
+int mm3d_bnrelu_fwd_impl(const float* x, float* y, int64_t n, int c, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                         float eps, float momentum, float leakiness, int training,
+                         void* ws, size_t ws_bytes, bool ws_clean, cudaStream_t stream) {
   MM3D_REQUIRE(c > 0 && n >= 0, MM3D_ERR_INVALID, "bad sizes");
   const bool vec4 = (c % 4 == 0) && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
   const int cv = vec4 ? c / 4 : c;
@@ -263,45 +343,63 @@ extern "C" int mm3d_bnrelu_fwd(const float* x, float* y, int64_t n, int c, const
   MM3D_REQUIRE(ws_bytes >= mm3d_bnrelu_workspace_bytes(c) && ws, MM3D_ERR_WORKSPACE, "bnrelu workspace too small");
   if (n == 0) return MM3D_OK;
   double* sums = (double*)ws;
+  unsigned int* sync = (unsigned int*)(sums + 2 * c);
   const int grid = bn_grid(n, cv);
   const size_t smem = sizeof(double) * 2 * c > sizeof(float) * 2 * (kThreads / cv) * (size_t)c
                           ? sizeof(double) * 2 * c : sizeof(float) * 2 * (kThreads / cv) * (size_t)c;
   if (training) {
     MM3D_REQUIRE(save_mean && save_invstd && running_mean && running_var, MM3D_ERR_INVALID, "training needs stat buffers");
-    MM3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c, stream));
-    BN_DISPATCH(k_bn_stats, x, n, c, sums);
+    if (!ws_clean) MM3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c + 16, stream));
+    BN_DISPATCH(k_bn_fwd_fused, x, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, sums, sync,
+                eps, momentum, leakiness, mm3d_device_err_flag());
+  } else {
+    BN_DISPATCH(k_bn_apply, x, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, sums, eps,
+                momentum, leakiness, training);
   }
-  BN_DISPATCH(k_bn_apply, x, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, sums, eps,
-              momentum, leakiness, training);
-  mm3d_count_launches(training ? 2 : 1);
+  mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_bnrelu_fwd");
   return MM3D_OK;
 }
 
-extern "C" int mm3d_bnrelu_bwd(const float* x, const float* dy, float* dx, int64_t n, int c, const float* gamma,
-                               const float* beta, const float* save_mean, const float* save_invstd,
-                               float* d_gamma, float* d_beta, float leakiness, int training,
-                               void* ws, size_t ws_bytes, mm3d_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+int mm3d_bnrelu_bwd_impl(const float* x, const float* dy, float* dx, int64_t n, int c, const float* gamma,
+                         const float* beta, const float* save_mean, const float* save_invstd,
+                         float* d_gamma, float* d_beta, float leakiness, int training,
+                         void* ws, size_t ws_bytes, bool ws_clean, cudaStream_t stream) {
   MM3D_REQUIRE(c > 0 && n >= 0, MM3D_ERR_INVALID, "bad sizes");
   const bool vec4 = (c % 4 == 0) && ((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0);
   const int cv = vec4 ? c / 4 : c;
   MM3D_REQUIRE(cv <= kThreads, MM3D_ERR_UNSUPPORTED, "BatchNorm with %d channels not supported", c);
   MM3D_REQUIRE(ws_bytes >= mm3d_bnrelu_workspace_bytes(c) && ws, MM3D_ERR_WORKSPACE, "bnrelu workspace too small");
   double* sums = (double*)ws;
-  MM3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c, stream));
+  unsigned int* sync = (unsigned int*)(sums + 2 * c);
   if (n == 0) {
     MM3D_CUDA(cudaMemsetAsync(d_gamma, 0, sizeof(float) * c, stream));
     MM3D_CUDA(cudaMemsetAsync(d_beta, 0, sizeof(float) * c, stream));
     return MM3D_OK;
   }
+  if (!ws_clean) MM3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c + 16, stream));
   const int grid = bn_grid(n, cv);
   const size_t smem = sizeof(double) * 2 * c > sizeof(float) * 2 * (kThreads / cv) * (size_t)c
                           ? sizeof(double) * 2 * c : sizeof(float) * 2 * (kThreads / cv) * (size_t)c;
-  BN_DISPATCH(k_bn_bwd_stats, x, dy, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums);
-  BN_DISPATCH(k_bn_bwd_apply, x, dy, dx, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums, d_gamma,
-              d_beta, training);
-  mm3d_count_launches(2);
+  BN_DISPATCH(k_bn_bwd_fused, x, dy, dx, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums, sync, d_gamma,
+              d_beta, training, mm3d_device_err_flag());
+  mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_bnrelu_bwd");
   return MM3D_OK;
+}
+
+extern "C" int mm3d_bnrelu_fwd(const float* x, float* y, int64_t n, int c, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                               float eps, float momentum, float leakiness, int training,
+                               void* ws, size_t ws_bytes, mm3d_stream_t stream) {
+  return mm3d_bnrelu_fwd_impl(x, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, eps, momentum,
+                              leakiness, training, ws, ws_bytes, false, (cudaStream_t)stream);
+}
+
+extern "C" int mm3d_bnrelu_bwd(const float* x, const float* dy, float* dx, int64_t n, int c, const float* gamma,
+                               const float* beta, const float* save_mean, const float* save_invstd,
+                               float* d_gamma, float* d_beta, float leakiness, int training,
+                               void* ws, size_t ws_bytes, mm3d_stream_t stream) {
+  return mm3d_bnrelu_bwd_impl(x, dy, dx, n, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, leakiness, training,
+                              ws, ws_bytes, false, (cudaStream_t)stream);
 }

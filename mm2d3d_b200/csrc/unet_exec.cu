@@ -22,6 +22,16 @@
 
 #include "common.cuh"
 
+// bnrelu.cu
+int mm3d_bnrelu_fwd_impl(const float* x, float* y, int64_t n, int c, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, float* save_mean, float* save_invstd, float eps,
+                         float momentum, float leakiness, int training, void* ws, size_t ws_bytes, bool ws_clean,
+                         cudaStream_t stream);
+int mm3d_bnrelu_bwd_impl(const float* x, const float* dy, float* dx, int64_t n, int c, const float* gamma,
+                         const float* beta, const float* save_mean, const float* save_invstd, float* d_gamma,
+                         float* d_beta, float leakiness, int training, void* ws, size_t ws_bytes, bool ws_clean,
+                         cudaStream_t stream);
+
 namespace {
 
 struct LevelMeta {
@@ -163,6 +173,8 @@ struct Ctx {
   int pi;  // running parameter index
   int rc;
   SideStream* side = nullptr;  // backward only; NULL = everything on `stream`
+  void* bn_ws = nullptr;       // BatchNorm totals + barrier counters: zeroed once per call, the kernels keep it clean
+  size_t bn_ws_bytes = 0;
 };
 
 // stream for a layer's weight gradient: the side stream once everything enqueued on the main stream so far
@@ -187,12 +199,12 @@ const float* P(Ctx& c, int i) { return (const float*)c.params[i]; }
 float* Gp(Ctx& c, int i) { return (float*)c.grads[i]; }
 
 void bn_fwd(Ctx& c, int pidx, const float* x, float* y, int64_t n, int ch, float* save) {
-  EX(mm3d_bnrelu_fwd(x, y, n, ch, P(c, pidx), P(c, pidx + 1), (float*)c.params[pidx + 2], (float*)c.params[pidx + 3], save,
-                     save + ch, c.eps, c.momentum, 0.f, c.training, c.scratch, c.scratch_bytes, c.stream));
+  EX(mm3d_bnrelu_fwd_impl(x, y, n, ch, P(c, pidx), P(c, pidx + 1), (float*)c.params[pidx + 2], (float*)c.params[pidx + 3],
+                          save, save + ch, c.eps, c.momentum, 0.f, c.training, c.bn_ws, c.bn_ws_bytes, true, c.stream));
 }
 void bn_bwd(Ctx& c, int pidx, const float* x, const float* dy, float* dx, int64_t n, int ch, const float* save) {
-  EX(mm3d_bnrelu_bwd(x, dy, dx, n, ch, P(c, pidx), P(c, pidx + 1), save, save + ch, Gp(c, pidx), Gp(c, pidx + 1), 0.f,
-                     c.training, c.scratch, c.scratch_bytes, c.stream));
+  EX(mm3d_bnrelu_bwd_impl(x, dy, dx, n, ch, P(c, pidx), P(c, pidx + 1), save, save + ch, Gp(c, pidx), Gp(c, pidx + 1), 0.f,
+                          c.training, c.bn_ws, c.bn_ws_bytes, true, c.stream));
 }
 enum Kind { SMC, DOWN, UP };
 // forward of layer type `kind` whose FINE level is l
@@ -398,7 +410,19 @@ MM3D_API size_t mm3d_unet_scratch_bytes(int in_channels, int m, int num_planes, 
     s = mm3d_conv_workspace_bytes(0, 0, p + m, p, 8, mode);
     if (s > best) best = s;
   }
-  return best + mm3d_align(4 * (size_t)27 * cin_k * m) + 256;
+  return best + mm3d_bnrelu_workspace_bytes(2 * m * num_planes) + mm3d_align(4 * (size_t)27 * cin_k * m) + 256;
+}
+
+// carve the executor's private tail of the scratch buffer: [... | BatchNorm workspace | padded stem weight]
+int carve_tail(Ctx& c, const Net& net) {
+  const size_t wp_bytes = mm3d_align(4 * (size_t)27 * net.cin_k * net.m);
+  c.bn_ws_bytes = mm3d_bnrelu_workspace_bytes(2 * net.m * net.L);
+  MM3D_REQUIRE(c.scratch_bytes >= wp_bytes + c.bn_ws_bytes + 256, MM3D_ERR_WORKSPACE, "unet scratch too small");
+  const size_t end = c.scratch_bytes / 256 * 256;
+  c.bn_ws = (char*)c.scratch + end - wp_bytes - c.bn_ws_bytes;
+  c.scratch_bytes = end - wp_bytes - c.bn_ws_bytes;  // what the convolutions may use
+  MM3D_CUDA(cudaMemsetAsync(c.bn_ws, 0, c.bn_ws_bytes, c.stream));
+  return MM3D_OK;
 }
 
 MM3D_API int mm3d_unet_forward(int in_channels, int m, int num_planes, int mode, int training, float eps, float momentum,
@@ -412,13 +436,16 @@ MM3D_API int mm3d_unet_forward(int in_channels, int m, int num_planes, int mode,
   carve(net, bp);
   MM3D_REQUIRE(bp.ok, MM3D_ERR_WORKSPACE, "activation workspace too small: need %zu have %zu", bp.off, act_bytes);
   Ctx c{&net, params, nullptr, scratch, scratch_bytes, (cudaStream_t)stream_, eps, momentum, training, 0, 0};
+  float* const wp_buf = (float*)((char*)scratch + scratch_bytes / 256 * 256 - mm3d_align(4 * (size_t)27 * net.cin_k * m));
+  rc = carve_tail(c, net);
+  if (rc) return rc;
   const int64_t n0 = net.lv[0].n;
   EX(mm3d_input_fwd(feats, p2v, npts, n_points, n0, in_channels, 4, net.V, c.stream));
   const float* w_stem = P(c, 0);
   if (net.cin_k != net.cin) {
     // tensor-core modes gather whole 16-byte pieces: pad features and stem weight with zero channels
     launch_pad_cols(c, net.V, n0, net.cin, net.Vp, net.cin_k);
-    float* wp = (float*)((char*)scratch + scratch_bytes - mm3d_align(4 * (size_t)27 * net.cin_k * m));
+    float* wp = wp_buf;
     launch_pad_cols(c, w_stem, 27, net.cin * m, wp, net.cin_k * m);
     w_stem = wp;
   }
@@ -445,6 +472,9 @@ MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode
   MM3D_REQUIRE(tmp_bytes >= bwd_temp_bytes(net), MM3D_ERR_WORKSPACE, "backward workspace too small");
   Ctx c{&net, params, grads, scratch, scratch_bytes, (cudaStream_t)stream_, 0.f, 0.f, training, 0, 0};
   c.side = getenv("MM3D_NO_SIDE_STREAM") ? nullptr : side_stream();
+  float* const wp_buf = (float*)((char*)scratch + scratch_bytes / 256 * 256 - mm3d_align(4 * (size_t)27 * net.cin_k * m));
+  rc = carve_tail(c, net);
+  if (rc) return rc;
   Bump g{(char*)tmp, 0, tmp_bytes, true};
   const int64_t n0 = net.lv[0].n;
   const int head = 1 + level_slots(0, net.L);
@@ -459,7 +489,7 @@ MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode
   float* d_w = Gp(c, 0);
   float* d_Vp = d_feats ? g.f(n0, net.cin_k) : nullptr;
   if (net.cin_k != net.cin) {
-    float* wp = (float*)((char*)scratch + scratch_bytes - mm3d_align(4 * (size_t)27 * net.cin_k * m));
+    float* wp = wp_buf;
     launch_pad_cols(c, w_stem, 27, net.cin * m, wp, net.cin_k * m);
     float* d_wp = g.f(27, (int64_t)net.cin_k * m);
     conv_bwd(c, SMC, 0, net.Vp, net.cin_k, d_X0, m, wp, d_Vp, d_wp);
