@@ -314,7 +314,9 @@ int bn_grid(int64_t n, int cv) {
   const int rows_pass = kThreads / cv;
   int64_t g = mm3d_cdiv(n, (int64_t)rows_pass * 4);  // >= 4 rows per thread when there is enough work
   if (g < 1) g = 1;
-  const int64_t cap = (int64_t)MM3D_NUM_SMS * 3;  // co-resident with room to spare (single-launch kernels wait on each other)
+  // Single-launch kernels wait on each other, so every CTA must be resident at once -- also next to a weight-
+  // gradient CTA of the side stream (352 threads x 64 registers): two 256-thread CTAs x 64 registers per SM fit.
+  const int64_t cap = (int64_t)MM3D_NUM_SMS * 2;
   return (int)(g < cap ? g : cap);
 }
 

@@ -148,7 +148,7 @@ def run(net, coords, feats):
         coords = coords.to(feats.device, non_blocking=True)
     spatial0 = int(net.layer1.spatial_size[0])
     L = net._num_planes
-    meta = Metadata(coords, spatial0, L)
+    meta = Metadata(coords, spatial0, L, plans=F.DEFAULT_MODE != "fp32")
     bn0 = net.layer4
     cfg = (net.in_channels, net.out_channels, L, _lib.MODES[F.DEFAULT_MODE], bool(net.training), float(bn0.eps),
            float(bn0.momentum), spatial0)

@@ -38,7 +38,9 @@ class Level:
 class Metadata:
     MAX_LEVELS = 16
 
-    def __init__(self, coords: torch.Tensor, spatial_size: int, prebuild_levels: int = 1):
+    _side = {}  # per-device side stream for the neighbour tables
+
+    def __init__(self, coords: torch.Tensor, spatial_size: int, prebuild_levels: int = 1, plans: bool = False):
         if coords.dim() != 2 or coords.shape[1] != 4:
             raise ValueError("coords must be [N, 4] = (x, y, z, batch)")
         if not coords.is_cuda:
@@ -76,10 +78,33 @@ class Metadata:
             check(lib.mm3d_voxelize(coords.data_ptr(), n, self.spatial_size0, l0.ptr(l0.o_hkeys), l0.ptr(l0.o_hvals),
                                     l0.hcap, base + self._o_p2v, l0.ptr(l0.o_keys), base + self._o_npts,
                                     cp, cp + 4 * self.MAX_LEVELS, self._ws[0], self._ws[1], stream), "mm3d_voxelize")
-            self._build_nbr(l0, stream)
+            # The level chain (coarsen l -> l+1) is a sequence of small latency-bound kernels; the 3^3 table of a
+            # level only needs that level's hash, so it runs beside the chain on a second stream.
+            main = torch.cuda.current_stream()
+            side = self._side.get(self.device.index)
+            if side is None:
+                side = self._side[self.device.index] = torch.cuda.Stream(device=self.device)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            self._build_nbr(l0, side.cuda_stream)
             for i in range(1, L):
                 self._build_down(self._order[i - 1], self._order[i], stream)
-                self._build_nbr(self._order[i], stream)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                side.wait_event(ready)
+                self._build_nbr(self._order[i], side.cuda_stream)
+            done = torch.cuda.Event()
+            done.record(side)
+            main.wait_event(done)
+            if plans:
+                # row plans of every table, before the host learns the row counts (launch sized by capacity)
+                specs = []
+                for i, s in enumerate(sizes):
+                    specs.append(("smc", s))
+                    if i + 1 < L:
+                        specs += [("down", s), ("up", s)]
+                self.build_plans(specs)
             self._sync_counts()
 
     # ------------------------------------------------------------------ construction helpers
@@ -199,7 +224,7 @@ class Metadata:
                     d.tbl, d.tbl_stride, d.onehot_off, cnt_lv = lv.ptr(lv.o_parent), 0, lv.ptr(lv.o_off), lv
                 else:
                     raise ValueError(kind)
-                d.n_dev, d.n_cap, d.n_rows_hint = self._count_ptr(cnt_lv), lv.cap, (cnt_lv.n or 0)
+                d.n_dev, d.n_cap, d.n_rows_hint = self._count_ptr(cnt_lv), lv.cap, (cnt_lv.n or 0)  # 0: size by capacity
                 d.K = 27 if kind == "smc" else 8
                 d.plan, d.plan_bytes = buf.data_ptr() + off, nbytes
                 lv.plans[kind] = (buf[off:off + nbytes], lv.cap)

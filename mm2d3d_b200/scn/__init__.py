@@ -127,7 +127,7 @@ class InputLayer(nn.Module):
             raise RuntimeError("InputLayer: features must be a CUDA tensor -- mm2d3d_b200 has no CPU path")
         if coords.device != feats.device:
             coords = coords.to(feats.device, non_blocking=True)
-        meta = Metadata(coords, int(self.spatial_size[0]), self.prebuild_levels)
+        meta = Metadata(coords, int(self.spatial_size[0]), self.prebuild_levels, plans=F.DEFAULT_MODE != "fp32")
         return SparseConvNetTensor(F.InputLayerFn.apply(feats, meta, self.mode), meta, self.spatial_size)
 
 
