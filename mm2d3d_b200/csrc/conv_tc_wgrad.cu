@@ -11,8 +11,9 @@
 // tile in 32-wide blocks), N = the stage's 32 (or 16) input channels.  Every (offset, channel block)
 // owns TMEM columns for the whole kernel; a CTA covers a group of offsets whose accumulators fit the
 // 512 columns and a slice of the tiles, skips tiles without any of its offsets, and adds its
-// accumulators to dW once at the end (atomics).  Groups and their CTA counts are balanced by the
-// expected frequency of the offsets (host side, mm3d_conv_wgrad_tc).
+// accumulators to dW once at the end (atomics).  Offsets are dealt to groups by class (centre, faces,
+// edges, corners); how many CTAs a group gets is decided in the kernel from the plan's per-offset tile
+// counts, so the CTAs carry equal work whatever the geometry of the scans.
 //
 // Warp roles (S+7 warps): 0..S-1 gather producers (warp w owns ring stage w), S..S+3 epilogue
 // (TMEM -> atomics), S+4 MMA issuer + TMEM allocator, S+5 / S+6 dout-tile loaders (64 rows each).
@@ -37,6 +38,7 @@ struct WgParams {
   const int32_t* perm;
   const uint32_t* tile_mask;
   const int32_t* order;
+  const uint32_t* off_tiles;
   const int32_t* tbl;
   int64_t tstride;
   int c_in, c_out, K;
@@ -44,10 +46,9 @@ struct WgParams {
   int mw;           // UMMA M: 64 (c_out <= 64) or 128
   int S, gbufs;
   int num_tiles, tmem_cols;
-  int n_local;      // tiles per CTA (upper bound over the groups)
-  int groups;       // offset groups; group g owns the offsets of gmask[g] and CTAs [cta0[g], cta0[g+1])
+  int n_local;      // tiles per CTA (upper bound: every group gets at least ceil(num_tiles / n_local) CTAs)
+  int groups;       // offset groups; group g owns the offsets of gmask[g]; its CTAs are decided in the kernel
   uint32_t gmask[32];
-  uint16_t cta0[33];
   int* err;
 };
 
@@ -114,11 +115,64 @@ k_wgrad_tc(const WgParams p) {
   volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + kNumBars + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- CTAs -> offset groups in proportion to the groups' work, from the plan's per-offset tile counts
+  // (every CTA computes the same table; lane g of warp 0 owns group g): cost = 2 nb * sum_k tiles(k) for the
+  // gathers and MMAs + 3 * max_k tiles(k) for the dout tiles.
+  __shared__ int s_cta0[33];
+  if (warp == 0) {
+    const int nctas = (int)gridDim.x;
+    float cost = 0.f;
+    if (lane < p.groups) {
+      uint32_t sum = 0, mx = 0;
+      for (uint32_t r = p.gmask[lane]; r; r &= r - 1) {
+        const uint32_t c = __ldg(p.off_tiles + (__ffs(r) - 1));
+        sum += c;
+        mx = max(mx, c);
+      }
+      cost = (float)(2u * (uint32_t)p.nb * sum + 3u * mx) + 1.f;
+    }
+    float total = cost;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    const int min_ct = (p.num_tiles + p.n_local - 1) / p.n_local;
+    int ct = 0;
+    if (lane < p.groups) ct = max(min_ct, min(p.num_tiles, (int)((float)nctas * cost / total)));
+    int used = ct;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) used += __shfl_xor_sync(0xffffffffu, used, o);
+    for (int guard = 0; used != nctas && guard < 4 * 148; ++guard) {
+      // hand out spare CTAs to the group with the most work per CTA / take surplus from the one with the least
+      const bool add = used < nctas;
+      float load = -1.f;
+      if (lane < p.groups && (add ? ct < p.num_tiles : ct > min_ct)) load = add ? cost / (float)ct : (float)ct / cost;
+      float best = load;
+      int who = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+        if (ob > best || (ob == best && ow < who)) { best = ob; who = ow; }
+      }
+      if (best < 0.f) break;
+      if (lane == who) ct += add ? 1 : -1;
+      used += add ? 1 : -1;
+    }
+    int incl = ct;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int x = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += x;
+    }
+    s_cta0[lane + 1] = incl;
+    if (lane == 0) s_cta0[0] = 0;
+  }
+  __syncthreads();
   int grp = 0;  // this CTA's offset group, its index among the group's CTAs and their number
-  while (grp + 1 < p.groups && (int)blockIdx.x >= (int)p.cta0[grp + 1]) ++grp;
+  while (grp + 1 < p.groups && (int)blockIdx.x >= s_cta0[grp + 1]) ++grp;
   const uint32_t gmask = p.gmask[grp];
-  const int split = (int)blockIdx.x - (int)p.cta0[grp], splits = (int)p.cta0[grp + 1] - (int)p.cta0[grp];
+  const int split = (int)blockIdx.x - s_cta0[grp], splits = s_cta0[grp + 1] - s_cta0[grp];
   const int kn = __popc(gmask);
+  if (split >= splits) return;  // (only if the shares could not be made to add up: more CTAs than tiles)
 
   int n_local = p.n_local;
   while (n_local > 0 && mm3d_plan_local_tile(p.order, p.num_tiles, splits, split, n_local - 1) < 0) --n_local;
@@ -336,7 +390,8 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
   const Mm3dPlanView pv = mm3d_plan_view(plan, plan_cap);
   WgParams p;
   p.in = in; p.dout = d_out; p.dw = d_weight;
-  p.perm = pv.perm; p.tile_mask = pv.tile_mask; p.order = pv.order; p.tbl = pv.tbl; p.tstride = pv.stride;
+  p.perm = pv.perm; p.tile_mask = pv.tile_mask; p.order = pv.order; p.off_tiles = pv.off_tiles; p.tbl = pv.tbl;
+  p.tstride = pv.stride;
   p.c_in = c_in; p.c_out = c_out; p.K = K;
   p.nb = (c_in + 31) / 32;
   p.last_w = (c_in % 32) == 16 ? 4 : 8;
@@ -381,33 +436,16 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
       gw[best] += w[idx[a]] + 0.05f;  // + per-tile cost of loading the dout tile
       ++gn[best];
     }
-    int total_ctas = MM3D_NUM_SMS;
-    if (total_ctas < groups) total_ctas = groups;
-    float wsum = 0.f;
-    for (int g = 0; g < groups; ++g) wsum += gw[g];
-    int ctas[32], used = 0;
-    for (int g = 0; g < groups; ++g) {
-      ctas[g] = (int)(total_ctas * gw[g] / wsum);
-      if (ctas[g] < 1) ctas[g] = 1;
-      if (ctas[g] > p.num_tiles) ctas[g] = p.num_tiles;
-      used += ctas[g];
-    }
-    for (int spare = total_ctas - used; spare > 0;) {  // hand out the rest, heaviest load per CTA first
-      int best = -1;
-      for (int g = 0; g < groups; ++g)
-        if (ctas[g] < p.num_tiles && (best < 0 || gw[g] / ctas[g] > gw[best] / ctas[best])) best = g;
-      if (best < 0) break;
-      ++ctas[best];
-      --spare;
-    }
     p.groups = groups;
-    p.cta0[0] = 0;
-    int min_ctas = ctas[0];
-    for (int g = 0; g < groups; ++g) {
-      p.cta0[g + 1] = (uint16_t)(p.cta0[g] + ctas[g]);
-      if (ctas[g] < min_ctas) min_ctas = ctas[g];
-    }
-    p.n_local = (p.num_tiles + min_ctas - 1) / min_ctas;
+  }
+  // CTA shares of the groups are computed in the kernel from measured offset frequencies; here only the bound
+  // on tiles per CTA (size of the shared-memory tile list): every group gets >= ceil(num_tiles / n_local) CTAs
+  int total_ctas = MM3D_NUM_SMS;
+  if (total_ctas < groups) total_ctas = groups;
+  {
+    int per_group_min = total_ctas / groups / 3;
+    if (per_group_min < 1) per_group_min = 1;
+    p.n_local = (p.num_tiles + per_group_min - 1) / per_group_min;
   }
   const size_t smem = 1024 + (size_t)p.S * kStageBytes + (size_t)(p.S + 1) * kEntBytes +
                       (size_t)p.gbufs * (p.mw / 32) * kStageBytes + ((size_t)p.n_local * 8 + 15) / 16 * 16 +
@@ -419,7 +457,7 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
     MM3D_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     once = true;
   }
-  k_wgrad_tc<<<(unsigned)p.cta0[p.groups], (p.S + 7) * 32, smem, stream>>>(p);
+  k_wgrad_tc<<<(unsigned)total_ctas, (p.S + 7) * 32, smem, stream>>>(p);
   mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_conv_wgrad_tc");
   return MM3D_OK;

@@ -36,6 +36,7 @@ struct PlanSmem {
   uint32_t tmask[kChunk / 128];
   int warp_sums[kWarps];
   int bin_base[32];
+  int off_cnt[32];
   int is_last;
 };
 
@@ -48,6 +49,7 @@ struct PlanItem {
   int32_t* perm;
   uint32_t* tile_mask;
   int32_t* order;
+  uint32_t* off_tiles;
   int32_t* ptbl;
   int64_t pstride;
   int K, nbits, kind, block0;  // kind: 0 = 3^3 table, 1 = other dense table with K <= 8, 2 = (parent, offset) K <= 8,
@@ -71,6 +73,7 @@ __device__ __forceinline__ void build_plan_chunk(PlanSmem& s, const PlanItem& it
   int32_t* __restrict__ perm = it_.perm;
   uint32_t* __restrict__ tile_mask = it_.tile_mask;
   int32_t* __restrict__ order = it_.order;
+  uint32_t* __restrict__ off_tiles = it_.off_tiles;
   int32_t* __restrict__ ptbl = it_.ptbl;
   const int64_t pstride = it_.pstride;
   const int64_t n = *it_.n_dev;
@@ -258,9 +261,15 @@ __device__ __forceinline__ void build_plan_chunk(PlanSmem& s, const PlanItem& it
   const int T = (int)((n + 127) / 128);
   const int want = 32 - warp;
   if (tid < 32) s.bin_base[tid] = 0;
+  if (tid < 32) s.off_cnt[tid] = 0;
   __syncthreads();
-  for (int t = tid; t < T; t += kThreads) atomicAdd(&s.bin_base[32 - __popc(__ldcg(tile_mask + t))], 1);
+  for (int t = tid; t < T; t += kThreads) {
+    const uint32_t m = __ldcg(tile_mask + t);
+    atomicAdd(&s.bin_base[32 - __popc(m)], 1);
+    for (uint32_t r = m; r; r &= r - 1) atomicAdd(&s.off_cnt[__ffs(r) - 1], 1);
+  }
   __syncthreads();
+  if (tid < 32) off_tiles[tid] = (uint32_t)s.off_cnt[tid];
   if (warp == 0) {
     const int v = s.bin_base[lane];
     int incl = v;
@@ -370,6 +379,7 @@ extern "C" int mm3d_build_plans(const mm3d_plan_desc* descs, int n_plans, mm3d_s
       it.perm = (int32_t*)b;
       it.tile_mask = (uint32_t*)(b + mm3d_plan_off_mask(d.n_cap));
       it.order = (int32_t*)(b + mm3d_plan_off_order(d.n_cap));
+      it.off_tiles = (uint32_t*)(b + mm3d_plan_off_cnt(d.n_cap));
       it.ptbl = (int32_t*)(b + mm3d_plan_off_tbl(d.n_cap));
       it.pstride = mm3d_plan_tiles(d.n_cap) * 128;
       it.K = d.K;

@@ -11,6 +11,8 @@
 //   order     int32 [T]          the tiles [0, ceil(n/128)) by descending popcount(mask) (stable): kernels deal
 //                                tiles to their CTAs from this list in serpentine order, which balances the
 //                                number of non-empty blocks per CTA (a tile has 1..K of them)
+//   off_tiles uint32[32]         number of tiles that contain offset k (the weight-gradient kernel shares its CTAs
+//                                among offset groups in proportion)
 //   tbl       int32 [K][T*128]   tbl[k][128 t + r] = input row of perm[128 t + r] at offset k, or -1
 //
 // with T = ceil(n_cap / 128).  Features stay in SparseConvNet row order everywhere; only the order
@@ -23,6 +25,7 @@ struct Mm3dPlanView {
   const int32_t* perm;
   const uint32_t* tile_mask;
   const int32_t* order;
+  const uint32_t* off_tiles;
   const int32_t* tbl;
   int64_t stride;  // T * 128
 };
@@ -35,9 +38,10 @@ __host__ __device__ inline size_t mm3d_plan_off_mask(int64_t n_cap) {
 __host__ __device__ inline size_t mm3d_plan_off_order(int64_t n_cap) {
   return mm3d_plan_off_mask(n_cap) + ((size_t)mm3d_plan_tiles(n_cap) * 4 + 255) / 256 * 256;
 }
-__host__ __device__ inline size_t mm3d_plan_off_tbl(int64_t n_cap) {
+__host__ __device__ inline size_t mm3d_plan_off_cnt(int64_t n_cap) {
   return mm3d_plan_off_order(n_cap) + ((size_t)mm3d_plan_tiles(n_cap) * 4 + 255) / 256 * 256;
 }
+__host__ __device__ inline size_t mm3d_plan_off_tbl(int64_t n_cap) { return mm3d_plan_off_cnt(n_cap) + 256; }
 __host__ __device__ inline size_t mm3d_plan_size(int64_t n_cap, int K) {
   return mm3d_plan_off_tbl(n_cap) + ((size_t)K * mm3d_plan_tiles(n_cap) * 128 * 4 + 255) / 256 * 256;
 }
@@ -48,6 +52,7 @@ inline Mm3dPlanView mm3d_plan_view(const void* plan, int64_t n_cap) {
   v.perm = (const int32_t*)b;
   v.tile_mask = (const uint32_t*)(b + mm3d_plan_off_mask(n_cap));
   v.order = (const int32_t*)(b + mm3d_plan_off_order(n_cap));
+  v.off_tiles = (const uint32_t*)(b + mm3d_plan_off_cnt(n_cap));
   v.tbl = (const int32_t*)(b + mm3d_plan_off_tbl(n_cap));
   v.stride = mm3d_plan_tiles(n_cap) * 128;
   return v;

@@ -250,7 +250,7 @@ class Metadata:
         al = lambda x: (x + 255) // 256 * 256
         o_mask = al(T * 128 * 4)
         o_order = o_mask + al(T * 4)
-        o_tbl = o_order + al(T * 4)
+        o_tbl = o_order + al(T * 4) + 256
         perm = buf[:T * 128 * 4].view(torch.int32)
         mask = buf[o_mask:o_mask + T * 4].view(torch.int32)
         tbl = buf[o_tbl:o_tbl + K * T * 128 * 4].view(torch.int32).view(K, T * 128)
