@@ -304,7 +304,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; this script prints ONE JSON line
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     from mm2d3d_b200 import _lib, synth
     from mm2d3d_b200 import scn as scn_mod
@@ -359,9 +362,10 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        for i in range(3):  # keep the GPU busy until the sampler's first in-load line is due
-            step(i)
-        barrier()
+    for i in range(3):  # (every rank: steps contain a collective) keep the GPU busy until the sampler's first in-load line is due
+        step(i)
+    barrier()
+    if rank == 0:
         sampler.mark()
     launches0 = _lib.lib.mm3d_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -372,15 +376,16 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.lib.mm3d_kernel_launches() - launches0
-    if rank == 0 and ms < 400.0:  # a short timed region can fall between two 50 ms samples: run on under the sampler
-        t_end = time.time() + 0.4
-        i = 0
-        while time.time() < t_end:
-            step(i)
-            i += 1
-            if i % 8 == 0:
-                torch.cuda.synchronize()
-        barrier()
+    # a short timed region can fall between two 50 ms samples: run on under the sampler for ~0.4 s (the same number
+    # of extra steps on every rank, decided by rank 0, because steps contain a collective)
+    extra = torch.tensor([max(0, int(400.0 / max(ms / args.steps, 1e-3)) - args.steps)], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.broadcast(extra, 0)
+    for i in range(int(extra.item())):
+        step(i)
+        if i % 8 == 7:
+            torch.cuda.synchronize()
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
 
     # end to end: pinned host inputs -> device -> fwd+bwd (-> all-reduce) -> scalar back to the host
