@@ -538,6 +538,61 @@ def test_module_surface_matches_reference_usage():
     assert out16.dtype == torch.float32
 
 
+def _line_cloud(n_vox, seed):
+    """`n_vox` distinct voxels along a jagged line (every voxel has neighbours, some have children siblings)."""
+    rng = np.random.default_rng(seed)
+    x = np.arange(n_vox) // 3 + 10
+    y = (np.arange(n_vox) % 3) + 20 + (rng.integers(0, 2, n_vox) * (np.arange(n_vox) % 7 == 0))
+    z = np.full(n_vox, 30) + (np.arange(n_vox) % 3 == 2)
+    c = np.stack([x, y, z, np.zeros(n_vox, np.int64)], 1).astype(np.int64)
+    return np.unique(c, axis=0)
+
+
+@pytest.mark.parametrize("n_vox", [1, 2, 127, 128, 129, 1000, 8191, 8192, 8193, 20000])
+def test_tf32_edge_sizes(n_vox):
+    """Row counts around the tile (128) and plan-chunk (8192) boundaries, single rows, ragged tails: the
+    tensor-core kernels (plans, block-sparse K, wgrad groups) against the FP32 kernels, all three layer types."""
+    from mm2d3d_b200 import functional as F
+    coords = _line_cloud(n_vox, n_vox)
+    assert coords[:, 0].max() < 8192
+    meta = _meta(coords, 8192, 2)
+    torch.manual_seed(n_vox)
+    for kind, c_in, c_out in (("smc", 16, 32), ("smc", 96, 48), ("down", 32, 48), ("up", 48, 32)):
+        spatial_in = 4096 if kind == "up" else 8192
+        fwd_t, _, _ = F.conv_tables(meta, kind, spatial_in)
+        x = torch.randn(fwd_t.n_in, c_in, device=DEV)
+        w = torch.randn(fwd_t.K, 1, c_in, c_out, device=DEV) / (c_in ** 0.5)
+        g = torch.randn(fwd_t.n_out, c_out, device=DEV)
+        res = {}
+        for mode in ("fp32", "tf32"):
+            xx, ww = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+            y = F.TableConvFn.apply(xx, ww, meta, kind, spatial_in, mode)
+            gx, gw = torch.autograd.grad(y, (xx, ww), g)
+            res[mode] = (y, gx, gw)
+        for a, b, what in zip(res["tf32"], res["fp32"], ("fwd", "dgrad", "wgrad")):
+            assert rel_err(a, b) < 1e-2, (n_vox, kind, what, rel_err(a, b))
+    _no_device_error()
+
+
+def test_tf32_forward_is_bit_reproducible():
+    """Forward and dgrad of the tensor-core path do not depend on run-to-run scheduling (no atomics, fixed
+    accumulation order per output row)."""
+    from mm2d3d_b200 import functional as F
+    locs, _ = synth.make_batch("nuscenes", batch=2, seed0=3)
+    torch.manual_seed(5)
+    outs = []
+    for _ in range(2):
+        meta = _meta(locs, 4096, 2)
+        t, _, _ = F.conv_tables(meta, "smc", 4096)
+        g = torch.Generator(device=DEV).manual_seed(1)
+        x = torch.randn(t.n_in, 32, device=DEV, generator=g).requires_grad_(True)
+        w = torch.randn(27, 1, 32, 48, device=DEV, generator=g)
+        y = F.TableConvFn.apply(x, w, meta, "smc", 4096, "tf32")
+        gx, = torch.autograd.grad(y, x, torch.ones_like(y))
+        outs.append((y.detach().clone(), gx.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 @pytest.mark.parametrize("kind,c_in,c_out", [("smc", 16, 16), ("smc", 64, 32), ("down", 16, 32), ("up", 32, 16)])
 def test_tf32_matches_fp32_kernels_at_bench_size(kind, c_in, c_out):
     """Batch-8 nuScenes-shaped structure (BASELINE configs[1] size, ~238k rows, 1860 tiles): every
