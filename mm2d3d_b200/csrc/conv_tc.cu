@@ -79,6 +79,40 @@ __global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ 
   }
 }
 
+// Several weight images in one launch (the whole network's, built once per direction by the executor).
+struct WImgItem {
+  const float* w;
+  float* img;
+  int K, c_in, c_out, nb, n_pad, transposed, mirror, block0;
+};
+constexpr int kMaxImgBatch = 32;
+struct WImgBatch {
+  int n;
+  WImgItem item[kMaxImgBatch];
+};
+__global__ void k_weight_images(const __grid_constant__ WImgBatch b) {
+  int i = 0;
+  while (i + 1 < b.n && (int)blockIdx.x >= b.item[i + 1].block0) ++i;
+  const WImgItem& it = b.item[i];
+  const int64_t total = (int64_t)it.K * it.nb * it.n_pad * kKBlock;
+  const int nblk = (i + 1 < b.n ? b.item[i + 1].block0 : (int)gridDim.x) - it.block0;
+  for (int64_t e = (int64_t)((int)blockIdx.x - it.block0) * blockDim.x + threadIdx.x; e < total; e += (int64_t)nblk * blockDim.x) {
+    const int e_sw = (int)(e % kKBlock);
+    const int n = (int)((e / kKBlock) % it.n_pad);
+    const int blk = (int)(e / ((int64_t)kKBlock * it.n_pad));
+    const int k = blk / it.nb, j = blk - k * it.nb;
+    const int chunk = (e_sw >> 2) ^ (n & 7);
+    const int ci = j * kKBlock + chunk * 4 + (e_sw & 3);
+    float v = 0.f;
+    if (ci < it.c_in && n < it.c_out) {
+      const int ks = it.mirror ? it.K - 1 - k : k;
+      v = it.transposed ? __ldg(it.w + ((int64_t)ks * it.c_out + n) * it.c_in + ci)
+                        : __ldg(it.w + ((int64_t)ks * it.c_in + ci) * it.c_out + n);
+    }
+    it.img[e] = to_tf32(v);
+  }
+}
+
 // Walks the CTA's items in order: its tiles (dealt from the plan's cost-ordered list, kept in shared
 // memory with their masks); per tile the set bits of its mask (ascending offset); per offset the nb
 // channel blocks.  Every role runs its own copy.
@@ -329,26 +363,66 @@ extern "C" int mm3d_take_device_error(void) {
   return v;
 }
 
+// images of several layers in one launch; descs[i] = {weight, image buffer (mm3d_conv_tc_workspace_bytes), K, c_in,
+// c_out, flags}
+int mm3d_conv_tc_build_images(const float* const* weights, float* const* images, const int* K, const int* c_in,
+                              const int* c_out, const int* flags, int n, cudaStream_t stream) {
+  for (int first = 0; first < n; first += kMaxImgBatch) {
+    WImgBatch b;
+    b.n = 0;
+    int blocks = 0;
+    for (int i = first; i < n && i < first + kMaxImgBatch; ++i) {
+      WImgItem& it = b.item[b.n++];
+      MM3D_REQUIRE(tc_geometry(c_in[i], c_out[i], K[i], &it.nb, &it.n_pad) == 0, MM3D_ERR_UNSUPPORTED,
+                   "tcgen05 conv: unsupported shape c_in %d c_out %d K %d", c_in[i], c_out[i], K[i]);
+      it.w = weights[i]; it.img = images[i]; it.K = K[i]; it.c_in = c_in[i]; it.c_out = c_out[i];
+      it.transposed = (flags[i] & MM3D_CONV_TRANSPOSE_W) ? 1 : 0;
+      it.mirror = (flags[i] & MM3D_CONV_MIRROR_K) ? 1 : 0;
+      it.block0 = blocks;
+      int nb_blocks = (int)mm3d_cdiv((int64_t)it.K * it.nb * it.n_pad * kKBlock, 256 * 8);
+      blocks += nb_blocks < 1 ? 1 : nb_blocks;
+    }
+    if (blocks == 0) continue;
+    k_weight_images<<<blocks, 256, 0, stream>>>(b);
+    mm3d_count_launches(1);
+    MM3D_CHECK_LAUNCH("mm3d_conv_tc_build_images");
+  }
+  return MM3D_OK;
+}
+
+int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
+                         const float* wimg, int K, const void* plan, int64_t plan_cap, cudaStream_t stream);
+
 int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
                      const float* weight, int K, const void* plan, int64_t plan_cap, int flags, void* ws,
                      size_t ws_bytes, cudaStream_t stream) {
   int nb, n_pad;
   MM3D_REQUIRE(tc_geometry(c_in, c_out, K, &nb, &n_pad) == 0, MM3D_ERR_UNSUPPORTED,
                "tcgen05 conv: unsupported shape c_in %d c_out %d K %d", c_in, c_out, K);
-  MM3D_REQUIRE(n_out < (1ll << 31) && n_in * (int64_t)c_in < (1ll << 32), MM3D_ERR_UNSUPPORTED,
-               "tcgen05 conv: tensor too large for 32-bit element offsets");
-  MM3D_REQUIRE(plan && plan_cap >= n_out, MM3D_ERR_INVALID, "tcgen05 conv: needs a row plan covering n_out rows");
   MM3D_REQUIRE(ws && ws_bytes >= mm3d_conv_tc_workspace_bytes(c_in, c_out, K), MM3D_ERR_WORKSPACE,
                "tcgen05 conv: workspace too small");
-  MM3D_REQUIRE((((uintptr_t)in | (uintptr_t)out | (uintptr_t)ws) & 15) == 0, MM3D_ERR_INVALID,
-               "tcgen05 conv: pointers must be 16-byte aligned");
   const bool tr = (flags & MM3D_CONV_TRANSPOSE_W) != 0, mir = (flags & MM3D_CONV_MIRROR_K) != 0;
   MM3D_REQUIRE(tr || !mir, MM3D_ERR_UNSUPPORTED, "MIRROR_K without TRANSPOSE_W not implemented");
   if (n_out == 0) return MM3D_OK;
-
   float* wimg = (float*)ws;
   k_weight_image<<<mm3d_grid((int64_t)K * nb * n_pad * kKBlock, 256), 256, 0, stream>>>(weight, wimg, K, c_in, c_out, nb,
                                                                                     n_pad, tr ? 1 : 0, mir ? 1 : 0);
+  mm3d_count_launches(1);
+  return mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, wimg, K, plan, plan_cap, stream);
+}
+
+// the convolution proper, from a prebuilt weight image
+int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
+                         const float* wimg, int K, const void* plan, int64_t plan_cap, cudaStream_t stream) {
+  int nb, n_pad;
+  MM3D_REQUIRE(tc_geometry(c_in, c_out, K, &nb, &n_pad) == 0, MM3D_ERR_UNSUPPORTED,
+               "tcgen05 conv: unsupported shape c_in %d c_out %d K %d", c_in, c_out, K);
+  MM3D_REQUIRE(n_out < (1ll << 31) && n_in * (int64_t)c_in < (1ll << 32), MM3D_ERR_UNSUPPORTED,
+               "tcgen05 conv: tensor too large for 32-bit element offsets");
+  MM3D_REQUIRE(plan && plan_cap >= n_out, MM3D_ERR_INVALID, "tcgen05 conv: needs a row plan covering n_out rows");
+  MM3D_REQUIRE((((uintptr_t)in | (uintptr_t)out | (uintptr_t)wimg) & 15) == 0, MM3D_ERR_INVALID,
+               "tcgen05 conv: pointers must be 16-byte aligned");
+  if (n_out == 0) return MM3D_OK;
   const Mm3dPlanView pv = mm3d_plan_view(plan, plan_cap);
   TcParams p;
   p.in = in; p.out = out; p.wimg = wimg;
@@ -392,7 +466,7 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
   smem += ((size_t)p.n_local * 8 + 15) / 16 * 16;
   MM3D_REQUIRE(smem <= 226 * 1024, MM3D_ERR_UNSUPPORTED, "tcgen05 conv: too many rows per CTA for the tile-mask cache");
   k_conv_tc<<<grid, threads, smem, stream>>>(p);
-  mm3d_count_launches(2);
+  mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_conv_fwd_tc");
   return MM3D_OK;
 }

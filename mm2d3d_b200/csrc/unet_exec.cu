@@ -32,6 +32,14 @@ int mm3d_bnrelu_bwd_impl(const float* x, const float* dy, float* dx, int64_t n, 
                          float* d_beta, float leakiness, int training, void* ws, size_t ws_bytes, bool ws_clean,
                          cudaStream_t stream);
 
+// conv_tc.cu
+size_t mm3d_conv_tc_workspace_bytes(int c_in, int c_out, int K);
+int mm3d_conv_tc_supported(int c_in, int c_out, int K);
+int mm3d_conv_tc_build_images(const float* const* weights, float* const* images, const int* K, const int* c_in,
+                              const int* c_out, const int* flags, int n, cudaStream_t stream);
+int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
+                         const float* wimg, int K, const void* plan, int64_t plan_cap, cudaStream_t stream);
+
 namespace {
 
 struct LevelMeta {
@@ -175,6 +183,11 @@ struct Ctx {
   SideStream* side = nullptr;  // backward only; NULL = everything on `stream`
   void* bn_ws = nullptr;       // BatchNorm totals + barrier counters: zeroed once per call, the kernels keep it clean
   size_t bn_ws_bytes = 0;
+  // tensor-core modes: the weight images of all layers of this direction, built by one launch up front
+  void* img_ws = nullptr;
+  size_t img_ws_bytes = 0;
+  std::vector<const float*> img_key;  // weight pointer ...
+  std::vector<const float*> img_val;  // ... -> its image
 };
 
 // stream for a layer's weight gradient: the side stream once everything enqueued on the main stream so far
@@ -207,9 +220,22 @@ void bn_bwd(Ctx& c, int pidx, const float* x, const float* dy, float* dx, int64_
                           c.training, c.bn_ws, c.bn_ws_bytes, true, c.stream));
 }
 enum Kind { SMC, DOWN, UP };
+
+const float* find_img(const Ctx& c, const float* w) {
+  for (size_t i = 0; i < c.img_key.size(); ++i)
+    if (c.img_key[i] == w) return c.img_val[i];
+  return nullptr;
+}
 // forward of layer type `kind` whose FINE level is l
 void conv_fwd(Ctx& c, Kind kind, int l, const float* in, int c_in, float* out, int c_out, const float* w) {
   const LevelMeta& f = c.net->lv[l];
+  if (const float* im = find_img(c, w)) {  // prebuilt weight image: the tcgen05 kernel directly
+    const int64_t nc = l + 1 < c.net->L ? c.net->lv[l + 1].n : 0;
+    if (kind == SMC) EX(mm3d_conv_fwd_tc_img(in, f.n, c_in, out, f.n, c_out, im, 27, f.plan_smc, f.plan_cap, c.stream));
+    else if (kind == DOWN) EX(mm3d_conv_fwd_tc_img(in, f.n, c_in, out, nc, c_out, im, 8, f.plan_down, f.plan_cap, c.stream));
+    else EX(mm3d_conv_fwd_tc_img(in, nc, c_in, out, f.n, c_out, im, 8, f.plan_up, f.plan_cap, c.stream));
+    return;
+  }
   if (kind == SMC)
     EX(mm3d_conv_fwd(in, f.n, c_in, out, f.n, c_out, w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap, 0,
                      c.net->mode, c.scratch, c.scratch_bytes, c.stream));
@@ -227,20 +253,27 @@ void conv_bwd(Ctx& c, Kind kind, int l, const float* in, int c_in, const float* 
   const int64_t nc = l + 1 < c.net->L ? c.net->lv[l + 1].n : 0;
   const int md = c.net->mode;
   cudaStream_t ws = wgrad_stream(c);  // d_out is complete on the main stream at this point
+  const float* im = find_img(c, w);   // prebuilt dgrad image (tensor-core modes)
   if (kind == SMC) {
     EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, f.n, c_out, d_w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap, 0,
                        md, nullptr, 0, ws));
-    if (d_in)
+    if (d_in && im)
+      EX(mm3d_conv_fwd_tc_img(d_out, f.n, c_out, d_in, f.n, c_in, im, 27, f.plan_smc, f.plan_cap, c.stream));
+    else if (d_in)
       EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, f.n, c_in, w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap,
                        MM3D_CONV_TRANSPOSE_W | MM3D_CONV_MIRROR_K, md, c.scratch, c.scratch_bytes, c.stream));
   } else if (kind == DOWN) {  // in: fine rows, d_out: coarse rows
     EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, nc, c_out, d_w, 8, f.child, f.tstride, nullptr, f.plan_down, f.plan_cap, 0,
                        md, nullptr, 0, ws));
+    if (im) EX(mm3d_conv_fwd_tc_img(d_out, nc, c_out, d_in, f.n, c_in, im, 8, f.plan_up, f.plan_cap, c.stream));
+    else
     EX(mm3d_conv_fwd(d_out, nc, c_out, d_in, f.n, c_in, w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap,
                      MM3D_CONV_TRANSPOSE_W, md, c.scratch, c.scratch_bytes, c.stream));
   } else {  // UP: in: coarse rows, d_out: fine rows
     EX(mm3d_conv_wgrad(in, nc, c_in, d_out, f.n, c_out, d_w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap, 0, md,
                        nullptr, 0, ws));
+    if (im) EX(mm3d_conv_fwd_tc_img(d_out, f.n, c_out, d_in, nc, c_in, im, 8, f.plan_down, f.plan_cap, c.stream));
+    else
     EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, nc, c_in, w, 8, f.child, f.tstride, nullptr, f.plan_down, f.plan_cap,
                      MM3D_CONV_TRANSPOSE_W, md, c.scratch, c.scratch_bytes, c.stream));
   }
@@ -269,6 +302,65 @@ void launch_pad_cols(Ctx& c, const float* src, int64_t n, int c_src, float* dst,
 
 // parameter index bookkeeping: number of pointer slots a level (and everything below it) uses
 int level_slots(int l, int L) { return l + 1 < L ? 5 + 5 + level_slots(l + 1, L) + 5 + 5 : 5; }
+
+struct ConvInfo {
+  int pidx, K, c_in, c_out, smc;
+};
+// every convolution of the network below level l (slot layout as in level_fwd)
+void list_convs(const Net& net, int l, int pbase, std::vector<ConvInfo>& v) {
+  const int p = net.planes(l);
+  v.push_back({pbase + 4, 27, p, p, 1});
+  if (l + 1 < net.L) {
+    const int q = net.planes(l + 1);
+    const int dn = pbase + 5, deeper = pbase + 10, up = deeper + level_slots(l + 1, net.L), post = up + 5;
+    v.push_back({dn + 4, 8, p, q, 0});
+    list_convs(net, l + 1, deeper, v);
+    v.push_back({up + 4, 8, q, p, 0});
+    v.push_back({post + 4, 27, 2 * p, p, 1});
+  }
+}
+
+size_t img_region_bytes(const Net& net) {
+  if (net.mode == MM3D_MODE_FP32) return 0;
+  std::vector<ConvInfo> v;
+  v.push_back({0, 27, net.cin_k, net.m, 1});
+  list_convs(net, 0, 1, v);
+  size_t fwd = 0, bwd = 0;
+  for (const ConvInfo& ci : v) {
+    fwd += mm3d_align(mm3d_conv_tc_workspace_bytes(ci.c_in, ci.c_out, ci.K));
+    bwd += mm3d_align(mm3d_conv_tc_workspace_bytes(ci.c_out, ci.c_in, ci.K));
+  }
+  return (fwd > bwd ? fwd : bwd) + 256;
+}
+
+// One launch builds the weight images of every layer for this direction (dgrad: W^T, mirrored for 3^3 layers).
+int build_images(Ctx& c, bool backward, const float* w_stem) {
+  const Net& net = *c.net;
+  if (net.mode == MM3D_MODE_FP32 || !c.img_ws) return MM3D_OK;
+  std::vector<ConvInfo> v;
+  v.push_back({0, 27, net.cin_k, net.m, 1});
+  list_convs(net, 0, 1, v);
+  std::vector<const float*> w;
+  std::vector<float*> img;
+  std::vector<int> K, ci, co, fl;
+  char* at = (char*)c.img_ws;
+  for (const ConvInfo& x : v) {
+    const int a = backward ? x.c_out : x.c_in, b = backward ? x.c_in : x.c_out;
+    if (!mm3d_conv_tc_supported(a, b, x.K)) continue;
+    const size_t bytes = mm3d_align(mm3d_conv_tc_workspace_bytes(a, b, x.K));
+    MM3D_REQUIRE((size_t)(at - (char*)c.img_ws) + bytes <= c.img_ws_bytes, MM3D_ERR_WORKSPACE, "weight image region too small");
+    w.push_back(x.pidx == 0 ? w_stem : (const float*)c.params[x.pidx]);
+    img.push_back((float*)at);
+    K.push_back(x.K); ci.push_back(a); co.push_back(b);
+    fl.push_back(backward ? (MM3D_CONV_TRANSPOSE_W | (x.smc ? MM3D_CONV_MIRROR_K : 0)) : 0);
+    at += bytes;
+  }
+  int rc = mm3d_conv_tc_build_images(w.data(), img.data(), K.data(), ci.data(), co.data(), fl.data(), (int)w.size(), c.stream);
+  if (rc) return rc;
+  c.img_key.assign(w.begin(), w.end());
+  c.img_val.assign(img.begin(), img.end());
+  return MM3D_OK;
+}
 
 void level_fwd(Ctx& c, int l, int pbase) {
   Net& net = *c.net;
@@ -410,17 +502,23 @@ MM3D_API size_t mm3d_unet_scratch_bytes(int in_channels, int m, int num_planes, 
     s = mm3d_conv_workspace_bytes(0, 0, p + m, p, 8, mode);
     if (s > best) best = s;
   }
-  return best + mm3d_bnrelu_workspace_bytes(2 * m * num_planes) + mm3d_align(4 * (size_t)27 * cin_k * m) + 256;
+  Net shape;
+  shape.L = num_planes; shape.m = m; shape.cin = in_channels; shape.cin_k = cin_k; shape.mode = mode;
+  return best + img_region_bytes(shape) + mm3d_bnrelu_workspace_bytes(2 * m * num_planes) +
+         mm3d_align(4 * (size_t)27 * cin_k * m) + 256;
 }
 
 // carve the executor's private tail of the scratch buffer: [... | BatchNorm workspace | padded stem weight]
 int carve_tail(Ctx& c, const Net& net) {
   const size_t wp_bytes = mm3d_align(4 * (size_t)27 * net.cin_k * net.m);
   c.bn_ws_bytes = mm3d_bnrelu_workspace_bytes(2 * net.m * net.L);
-  MM3D_REQUIRE(c.scratch_bytes >= wp_bytes + c.bn_ws_bytes + 256, MM3D_ERR_WORKSPACE, "unet scratch too small");
+  c.img_ws_bytes = img_region_bytes(net) / 256 * 256;
+  MM3D_REQUIRE(c.scratch_bytes >= wp_bytes + c.bn_ws_bytes + c.img_ws_bytes + 256, MM3D_ERR_WORKSPACE,
+               "unet scratch too small");
   const size_t end = c.scratch_bytes / 256 * 256;
   c.bn_ws = (char*)c.scratch + end - wp_bytes - c.bn_ws_bytes;
-  c.scratch_bytes = end - wp_bytes - c.bn_ws_bytes;  // what the convolutions may use
+  c.img_ws = c.img_ws_bytes ? (char*)c.bn_ws - c.img_ws_bytes : nullptr;
+  c.scratch_bytes = end - wp_bytes - c.bn_ws_bytes - c.img_ws_bytes;  // what the convolutions may use
   MM3D_CUDA(cudaMemsetAsync(c.bn_ws, 0, c.bn_ws_bytes, c.stream));
   return MM3D_OK;
 }
@@ -449,6 +547,7 @@ MM3D_API int mm3d_unet_forward(int in_channels, int m, int num_planes, int mode,
     launch_pad_cols(c, w_stem, 27, net.cin * m, wp, net.cin_k * m);
     w_stem = wp;
   }
+  EX(build_images(c, false, w_stem));
   conv_fwd(c, SMC, 0, net.Vp, net.cin_k, net.b[0].X, m, w_stem);
   level_fwd(c, 0, 1);
   const int head = 1 + level_slots(0, net.L);
@@ -478,6 +577,14 @@ MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode
   Bump g{(char*)tmp, 0, tmp_bytes, true};
   const int64_t n0 = net.lv[0].n;
   const int head = 1 + level_slots(0, net.L);
+  {  // stem weight as the kernels see it (zero-padded input channels), then every layer's dgrad weight image
+    const float* w_stem_k = P(c, 0);
+    if (net.cin_k != net.cin) {
+      launch_pad_cols(c, w_stem_k, 27, net.cin * m, wp_buf, net.cin_k * m);
+      w_stem_k = wp_buf;
+    }
+    EX(build_images(c, true, w_stem_k));
+  }
   float* d_Z = g.f(n0, m);
   EX(mm3d_output_bwd(d_out, p2v, n_points, n0, m, d_Z, c.stream));
   float* d_R0 = g.f(n0, m);
@@ -489,8 +596,7 @@ MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode
   float* d_w = Gp(c, 0);
   float* d_Vp = d_feats ? g.f(n0, net.cin_k) : nullptr;
   if (net.cin_k != net.cin) {
-    float* wp = wp_buf;
-    launch_pad_cols(c, w_stem, 27, net.cin * m, wp, net.cin_k * m);
+    float* wp = wp_buf;  // padded at the start of this call
     float* d_wp = g.f(27, (int64_t)net.cin_k * m);
     conv_bwd(c, SMC, 0, net.Vp, net.cin_k, d_X0, m, wp, d_Vp, d_wp);
     join_side(c);  // d_wp comes from the side stream
