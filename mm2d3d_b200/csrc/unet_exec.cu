@@ -186,6 +186,8 @@ struct Ctx {
   // tensor-core modes: the weight images of all layers of this direction, built by one launch up front
   void* img_ws = nullptr;
   size_t img_ws_bytes = 0;
+  const char *grad_lo = nullptr, *grad_hi = nullptr;  // span of the caller's gradient buffers when contiguous
+  int wgrad_acc = 0;  // 1: the weight-gradient buffers were zeroed by one memset up front, wgrad kernels accumulate
   std::vector<const float*> img_key;  // weight pointer ...
   std::vector<const float*> img_val;  // ... -> its image
 };
@@ -254,8 +256,10 @@ void conv_bwd(Ctx& c, Kind kind, int l, const float* in, int c_in, const float* 
   const int md = c.net->mode;
   cudaStream_t ws = wgrad_stream(c);  // d_out is complete on the main stream at this point
   const float* im = find_img(c, w);   // prebuilt dgrad image (tensor-core modes)
+  // parameter gradients inside the caller's (pre-zeroed) flat buffer accumulate; temporaries are overwritten
+  const int acc = c.wgrad_acc && c.grad_lo <= (const char*)d_w && (const char*)d_w < c.grad_hi;
   if (kind == SMC) {
-    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, f.n, c_out, d_w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap, 0,
+    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, f.n, c_out, d_w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap, acc,
                        md, nullptr, 0, ws));
     if (d_in && im)
       EX(mm3d_conv_fwd_tc_img(d_out, f.n, c_out, d_in, f.n, c_in, im, 27, f.plan_smc, f.plan_cap, c.stream));
@@ -263,14 +267,14 @@ void conv_bwd(Ctx& c, Kind kind, int l, const float* in, int c_in, const float* 
       EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, f.n, c_in, w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap,
                        MM3D_CONV_TRANSPOSE_W | MM3D_CONV_MIRROR_K, md, c.scratch, c.scratch_bytes, c.stream));
   } else if (kind == DOWN) {  // in: fine rows, d_out: coarse rows
-    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, nc, c_out, d_w, 8, f.child, f.tstride, nullptr, f.plan_down, f.plan_cap, 0,
+    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, nc, c_out, d_w, 8, f.child, f.tstride, nullptr, f.plan_down, f.plan_cap, acc,
                        md, nullptr, 0, ws));
     if (im) EX(mm3d_conv_fwd_tc_img(d_out, nc, c_out, d_in, f.n, c_in, im, 8, f.plan_up, f.plan_cap, c.stream));
     else
     EX(mm3d_conv_fwd(d_out, nc, c_out, d_in, f.n, c_in, w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap,
                      MM3D_CONV_TRANSPOSE_W, md, c.scratch, c.scratch_bytes, c.stream));
   } else {  // UP: in: coarse rows, d_out: fine rows
-    EX(mm3d_conv_wgrad(in, nc, c_in, d_out, f.n, c_out, d_w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap, 0, md,
+    EX(mm3d_conv_wgrad(in, nc, c_in, d_out, f.n, c_out, d_w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap, acc, md,
                        nullptr, 0, ws));
     if (im) EX(mm3d_conv_fwd_tc_img(d_out, f.n, c_out, d_in, nc, c_in, im, 8, f.plan_down, f.plan_cap, c.stream));
     else
@@ -577,6 +581,34 @@ MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode
   Bump g{(char*)tmp, 0, tmp_bytes, true};
   const int64_t n0 = net.lv[0].n;
   const int head = 1 + level_slots(0, net.L);
+  {  // One memset instead of one per layer when the gradient buffers are one contiguous block (the shipped host
+     // code hands out views of one flat tensor): slot sizes follow from the network shape.
+    std::vector<ConvInfo> v;
+    v.push_back({0, 27, net.cin, net.m, 1});
+    list_convs(net, 0, 1, v);
+    const char *lo = nullptr, *hi = nullptr;
+    size_t bytes = 0;
+    bool all = true;
+    for (const ConvInfo& x : v) {
+      const char* g0 = (const char*)grads[x.pidx];
+      if (!g0) { all = false; break; }
+      const size_t nb_ = sizeof(float) * (size_t)x.K * x.c_in * x.c_out;
+      if (!lo || g0 < lo) lo = g0;
+      if (!hi || g0 + nb_ > hi) hi = g0 + nb_;
+      bytes += nb_;
+    }
+    // BatchNorm gradients (2 * channels each) may sit in between: allow the span to be at most their size larger
+    size_t bn_bytes = 0;
+    for (int l = 0; l < net.L; ++l) {
+      const size_t pl = (size_t)net.planes(l);
+      bn_bytes += sizeof(float) * 2 * (l + 1 < net.L ? 4 * pl + (size_t)net.planes(l + 1) : pl);  // pre, dn, up, post
+    }
+    bn_bytes += sizeof(float) * 2 * (size_t)net.m;  // head
+    if (all && lo && (size_t)(hi - lo) <= bytes + bn_bytes) {
+      MM3D_CUDA(cudaMemsetAsync((void*)lo, 0, (size_t)(hi - lo), c.stream));
+      c.grad_lo = lo; c.grad_hi = hi; c.wgrad_acc = 1;
+    }
+  }
   {  // stem weight as the kernels see it (zero-padded input channels), then every layer's dgrad weight image
     const float* w_stem_k = P(c, 0);
     if (net.cin_k != net.cin) {
