@@ -154,6 +154,8 @@ k_bn_fwd_fused(const float* __restrict__ x, float* __restrict__ y, int64_t n, in
                const float* __restrict__ gamma, const float* __restrict__ beta,
                float* running_mean, float* running_var, float* save_mean, float* save_invstd,
                double* sums, unsigned int* sync, float eps, float momentum, float leak, int* err) {
+  mm3d_griddep_launch();
+  mm3d_griddep_wait();
   const int cv = c / VEC;
   const int rows_pass = kThreads / cv;
   const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
@@ -229,6 +231,8 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ dy, float*
                const float* __restrict__ gamma, const float* __restrict__ beta,
                const float* __restrict__ save_mean, const float* __restrict__ save_invstd, float leak,
                double* sums, unsigned int* sync, float* d_gamma, float* d_beta, int training, int* err) {
+  mm3d_griddep_launch();
+  mm3d_griddep_wait();
   const int cv = c / VEC;
   const int rows_pass = kThreads / cv;
   const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
@@ -332,6 +336,11 @@ extern "C" size_t mm3d_bnrelu_workspace_bytes(int c) { return mm3d_align(sizeof(
     if (vec4) KERNEL<4><<<grid, kThreads, smem, stream>>>(__VA_ARGS__);                 \
     else      KERNEL<1><<<grid, kThreads, smem, stream>>>(__VA_ARGS__);                 \
   } while (0)
+#define BN_DISPATCH_PDL(KERNEL, ...)                                                                        \
+  do {                                                                                                      \
+    if (vec4) MM3D_CUDA(mm3d_launch_pdl(KERNEL<4>, dim3(grid), dim3(kThreads), smem, stream, __VA_ARGS__)); \
+    else      MM3D_CUDA(mm3d_launch_pdl(KERNEL<1>, dim3(grid), dim3(kThreads), smem, stream, __VA_ARGS__)); \
+  } while (0)
 
 // ws_clean: the workspace is known to be all zero (the kernels leave it that way), skip the memset
 int mm3d_bnrelu_fwd_impl(const float* x, float* y, int64_t n, int c, const float* gamma, const float* beta,
@@ -352,7 +361,7 @@ int mm3d_bnrelu_fwd_impl(const float* x, float* y, int64_t n, int c, const float
   if (training) {
     MM3D_REQUIRE(save_mean && save_invstd && running_mean && running_var, MM3D_ERR_INVALID, "training needs stat buffers");
     if (!ws_clean) MM3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c + 16, stream));
-    BN_DISPATCH(k_bn_fwd_fused, x, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, sums, sync,
+    BN_DISPATCH_PDL(k_bn_fwd_fused, x, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, sums, sync,
                 eps, momentum, leakiness, mm3d_device_err_flag());
   } else {
     BN_DISPATCH(k_bn_apply, x, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, sums, eps,
@@ -383,7 +392,7 @@ int mm3d_bnrelu_bwd_impl(const float* x, const float* dy, float* dx, int64_t n, 
   const int grid = bn_grid(n, cv);
   const size_t smem = sizeof(double) * 2 * c > sizeof(float) * 2 * (kThreads / cv) * (size_t)c
                           ? sizeof(double) * 2 * c : sizeof(float) * 2 * (kThreads / cv) * (size_t)c;
-  BN_DISPATCH(k_bn_bwd_fused, x, dy, dx, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums, sync, d_gamma,
+  BN_DISPATCH_PDL(k_bn_bwd_fused, x, dy, dx, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums, sync, d_gamma,
               d_beta, training, mm3d_device_err_flag());
   mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_bnrelu_bwd");

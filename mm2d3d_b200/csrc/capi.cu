@@ -1,5 +1,6 @@
 // C-ABI glue: error state, version, mode dispatch of the convolution entry points.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -16,6 +17,12 @@ void mm3d_set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void mm3d_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 extern "C" long long mm3d_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+bool mm3d_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) on = getenv("MM3D_NO_PDL") ? 0 : 1;
+  return on != 0;
+}
 
 extern "C" const char* mm3d_last_error(void) { return g_err; }
 extern "C" int mm3d_abi_version(void) { return MM3D_ABI_VERSION; }

@@ -49,6 +49,37 @@ static inline int mm3d_grid(int64_t n, int block, int ctas_per_sm = 8) {
   return (int)(g < cap ? g : cap);
 }
 
+// ---- programmatic dependent launch: a kernel launched with mm3d_launch_pdl may start (block scheduling, its
+// prologue up to mm3d_griddep_wait()) while the previous kernel of the stream is still draining; everything
+// that reads or writes global memory comes after mm3d_griddep_wait(), which returns once the previous kernel
+// has completed and its writes are visible.  Kernels call mm3d_griddep_launch() early so that their own
+// successor can be scheduled as soon as SM resources free up.  MM3D_NO_PDL=1 launches plainly.
+#ifdef __CUDACC__
+__device__ __forceinline__ void mm3d_griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void mm3d_griddep_launch() {
+#ifdef MM3D_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+bool mm3d_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t mm3d_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                   Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = mm3d_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 #define MM3D_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
 
 __host__ __device__ __forceinline__ uint64_t mm3d_pack_key(uint64_t x, uint64_t y, uint64_t z, uint64_t b) {

@@ -166,15 +166,9 @@ k_conv_tc(const TcParams p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // ---- one-time setup
-  // this CTA's tiles (mm3d_plan_local_tile) and their masks live in shared memory: [masks][tile indices]
-  int n_local = p.n_local;
-  if (mm3d_plan_local_tile(p.order, p.num_tiles, (int)gridDim.x, (int)blockIdx.x, n_local - 1) < 0) --n_local;
-  for (int i = threadIdx.x; i < n_local; i += blockDim.x) {
-    const int t = mm3d_plan_local_tile(p.order, p.num_tiles, (int)gridDim.x, (int)blockIdx.x, i);
-    lmask[i] = __ldg(p.tile_mask + t);
-    lmask[n_local + i] = (uint32_t)t;
-  }
+  // ---- one-time setup.  Nothing before mm3d_griddep_wait() touches global memory (the previous kernel of the
+  // stream may still be running: programmatic dependent launch).
+  mm3d_griddep_launch();
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(a_full(s), 33);  // 32 cp.async arrivals (gathered rows) + 1 expect_tx arrival (weight block)
@@ -188,6 +182,15 @@ k_conv_tc(const TcParams p) {
     fence_barrier_init();
   }
   if (warp == S + 4) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
+  mm3d_griddep_wait();
+  // this CTA's tiles (mm3d_plan_local_tile) and their masks live in shared memory: [masks][tile indices]
+  int n_local = p.n_local;
+  if (mm3d_plan_local_tile(p.order, p.num_tiles, (int)gridDim.x, (int)blockIdx.x, n_local - 1) < 0) --n_local;
+  for (int i = threadIdx.x; i < n_local; i += blockDim.x) {
+    const int t = mm3d_plan_local_tile(p.order, p.num_tiles, (int)gridDim.x, (int)blockIdx.x, i);
+    lmask[i] = __ldg(p.tile_mask + t);
+    lmask[n_local + i] = (uint32_t)t;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -465,7 +468,7 @@ int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, in
   p.n_local = (p.num_tiles + grid - 1) / grid;
   smem += ((size_t)p.n_local * 8 + 15) / 16 * 16;
   MM3D_REQUIRE(smem <= 226 * 1024, MM3D_ERR_UNSUPPORTED, "tcgen05 conv: too many rows per CTA for the tile-mask cache");
-  k_conv_tc<<<grid, threads, smem, stream>>>(p);
+  MM3D_CUDA(mm3d_launch_pdl(k_conv_tc, dim3(grid), dim3(threads), smem, stream, p));
   mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_conv_fwd_tc");
   return MM3D_OK;

@@ -115,6 +115,8 @@ k_wgrad_tc(const WgParams p) {
   volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + kNumBars + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  mm3d_griddep_launch();
+  mm3d_griddep_wait();  // (everything below reads the plan; the wgrad stream's kernels follow each other closely)
   // ---- CTAs -> offset groups in proportion to the groups' work, from the plan's per-offset tile counts
   // (every CTA computes the same table; lane g of warp 0 owns group g): cost = 2 nb * sum_k tiles(k) for the
   // gathers and MMAs + 3 * max_k tiles(k) for the dout tiles.
@@ -457,7 +459,7 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
     MM3D_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     once = true;
   }
-  k_wgrad_tc<<<(unsigned)total_ctas, (p.S + 7) * 32, smem, stream>>>(p);
+  MM3D_CUDA(mm3d_launch_pdl(k_wgrad_tc, dim3((unsigned)total_ctas), dim3((p.S + 7) * 32), smem, stream, p));
   mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_conv_wgrad_tc");
   return MM3D_OK;

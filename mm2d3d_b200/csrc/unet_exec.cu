@@ -116,6 +116,8 @@ void carve(Net& net, Bump& bp) {
 
 __global__ void k_copy_cols(const float* __restrict__ src, int64_t n, int c_src, float* __restrict__ dst, int c_dst,
                             int dst_col0, int ncols, int src_col0) {
+  mm3d_griddep_launch();
+  mm3d_griddep_wait();
   // dst[r, dst_col0 + j] = src[r, src_col0 + j], j < ncols  (other dst columns untouched)
   const int64_t total = n * ncols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -126,6 +128,8 @@ __global__ void k_copy_cols(const float* __restrict__ src, int64_t n, int c_src,
 }
 
 __global__ void k_pad_cols(const float* __restrict__ src, int64_t n, int c_src, float* __restrict__ dst, int c_dst) {
+  mm3d_griddep_launch();
+  mm3d_griddep_wait();
   // dst[r, j] = j < c_src ? src[r, j] : 0   (c_dst >= c_src: pad;  c_dst < c_src: slice)
   const int64_t total = n * c_dst;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -137,6 +141,8 @@ __global__ void k_pad_cols(const float* __restrict__ src, int64_t n, int c_src, 
 
 __global__ void k_split_add(const float* __restrict__ dj, const float* __restrict__ add, int64_t n, int p,
                             float* __restrict__ dy, float* __restrict__ df) {
+  mm3d_griddep_launch();
+  mm3d_griddep_wait();
   // dy = dj[:, :p] + add ; df = dj[:, p:]
   const int64_t total = n * p;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -295,12 +301,12 @@ void join_side(Ctx& c) {
 
 void launch_copy_cols(Ctx& c, const float* src, int64_t n, int c_src, float* dst, int c_dst, int col0, int ncols) {
   if (n == 0 || c.rc) return;
-  k_copy_cols<<<mm3d_grid(n * ncols, 256), 256, 0, c.stream>>>(src, n, c_src, dst, c_dst, col0, ncols, 0);
+  if (mm3d_launch_pdl(k_copy_cols, dim3(mm3d_grid(n * ncols, 256)), dim3(256), 0, c.stream, src, n, c_src, dst, c_dst, col0, ncols, 0) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
   mm3d_count_launches(1);
 }
 void launch_pad_cols(Ctx& c, const float* src, int64_t n, int c_src, float* dst, int c_dst) {
   if (n == 0 || c.rc) return;
-  k_pad_cols<<<mm3d_grid(n * c_dst, 256), 256, 0, c.stream>>>(src, n, c_src, dst, c_dst);
+  if (mm3d_launch_pdl(k_pad_cols, dim3(mm3d_grid(n * c_dst, 256)), dim3(256), 0, c.stream, src, n, c_src, dst, c_dst) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
   mm3d_count_launches(1);
 }
 
@@ -409,7 +415,7 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
     float* d_Yskip = g.f(n, p);
     // d_F = d_J[:, p:]; the skip half is combined with the branch gradient further down
     if (n && !c.rc) {
-      k_copy_cols<<<mm3d_grid(n * p, 256), 256, 0, c.stream>>>(d_J, n, 2 * p, d_F, p, 0, p, p);
+      if (mm3d_launch_pdl(k_copy_cols, dim3(mm3d_grid(n * p, 256)), dim3(256), 0, c.stream, (const float*)d_J, n, 2 * p, d_F, p, 0, p, p) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
       mm3d_count_launches(1);
     }
     float* d_E = g.f(nc, q);
@@ -424,7 +430,7 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
     bn_bwd(c, dn, B.Y, d_B, d_Ybr, n, p, B.s_dn);
     // d_Y = d_J[:, :p] + d_Ybr
     if (n && !c.rc) {
-      k_split_add<<<mm3d_grid(n * p, 256), 256, 0, c.stream>>>(d_J, d_Ybr, n, p, d_Yskip, nullptr);
+      if (mm3d_launch_pdl(k_split_add, dim3(mm3d_grid(n * p, 256)), dim3(256), 0, c.stream, (const float*)d_J, (const float*)d_Ybr, n, p, d_Yskip, (float*)nullptr) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
       mm3d_count_launches(1);
     }
     d_Y = d_Yskip;
