@@ -21,6 +21,7 @@ __device__ __forceinline__ uint32_t pow2ceil_u32(uint32_t v) {
 // ---- per-level setup: probe mask from the (device-side) item count, zero the output count
 __global__ void k_setup(const int32_t* __restrict__ n_dev, int64_t n_host, int64_t hash_cap,
                         int32_t* hash_mask_dev, int32_t* n_out_dev, int32_t* n_items_dev) {
+  mm3d_griddep_wait();  // programmatic dependent launch: the previous kernel's writes are visible from here
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int64_t n = n_dev ? (int64_t)*n_dev : n_host;
     uint32_t want = pow2ceil_u32((uint32_t)(2 * n < 32 ? 32 : 2 * n));
@@ -34,6 +35,7 @@ __global__ void k_setup(const int32_t* __restrict__ n_dev, int64_t n_host, int64
 __global__ void k_clear(uint64_t* __restrict__ hash_keys, int32_t* __restrict__ slot_min,
                         const int32_t* __restrict__ hash_mask_dev, const int32_t* __restrict__ n_items_dev,
                         int32_t* __restrict__ fill_buf, int fill_planes, int64_t fill_stride, int32_t fill_val) {
+  mm3d_griddep_wait();  // programmatic dependent launch: the previous kernel's writes are visible from here
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   const int64_t slots = (int64_t)(uint32_t)*hash_mask_dev + 1;
@@ -77,6 +79,7 @@ template <class Src>
 __global__ void k_insert(Src src, const int32_t* __restrict__ n_items_dev, uint64_t* hash_keys,
                          int32_t* slot_min, const int32_t* __restrict__ hash_mask_dev,
                          int32_t* __restrict__ item_slot) {
+  mm3d_griddep_wait();  // programmatic dependent launch: the previous kernel's writes are visible from here
   const int64_t n = *n_items_dev;
   const uint32_t mask = (uint32_t)*hash_mask_dev;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -137,6 +140,7 @@ __device__ __forceinline__ int thread_flags(const int32_t* __restrict__ item_slo
 __global__ void __launch_bounds__(kScanThreads)
 k_count(const int32_t* __restrict__ item_slot, const int32_t* __restrict__ slot_min,
         const int32_t* __restrict__ n_items_dev, int32_t* __restrict__ block_sums) {
+  mm3d_griddep_wait();  // programmatic dependent launch: the previous kernel's writes are visible from here
   const int64_t n = *n_items_dev;
   const int64_t base = (int64_t)blockIdx.x * kItemsPerBlock + threadIdx.x * kItemsPerThread;
   int c = base < n ? __popc(thread_flags(item_slot, slot_min, base, n)) : 0;
@@ -148,6 +152,7 @@ k_count(const int32_t* __restrict__ item_slot, const int32_t* __restrict__ slot_
 // exclusive scan of the per-block counts by ONE block (counts are few: n_cap / 1024)
 __global__ void __launch_bounds__(kScanThreads)
 k_scan_blocks(int32_t* __restrict__ block_sums, int nblocks, int32_t* __restrict__ n_out_dev) {
+  mm3d_griddep_wait();  // programmatic dependent launch: the previous kernel's writes are visible from here
   int carry = 0;
   for (int base = 0; base < nblocks; base += kScanThreads) {
     int i = base + threadIdx.x;
@@ -165,6 +170,7 @@ k_assign(const int32_t* __restrict__ item_slot, const int32_t* __restrict__ slot
          const int32_t* __restrict__ n_items_dev, const int32_t* __restrict__ block_offs,
          const uint64_t* __restrict__ hash_keys, int32_t* __restrict__ hash_vals,
          uint64_t* __restrict__ uniq_keys) {
+  mm3d_griddep_wait();  // programmatic dependent launch: the previous kernel's writes are visible from here
   const int64_t n = *n_items_dev;
   const int64_t base = (int64_t)blockIdx.x * kItemsPerBlock + threadIdx.x * kItemsPerThread;
   const int f = base < n ? thread_flags(item_slot, slot_min, base, n) : 0;
@@ -185,6 +191,7 @@ k_assign(const int32_t* __restrict__ item_slot, const int32_t* __restrict__ slot
 __global__ void k_ids_level0(const int32_t* __restrict__ item_slot, const int32_t* __restrict__ hash_vals,
                              const int32_t* __restrict__ n_items_dev, int32_t* __restrict__ p2v,
                              int32_t* __restrict__ npts) {
+  mm3d_griddep_wait();  // programmatic dependent launch: the previous kernel's writes are visible from here
   const int64_t n = *n_items_dev;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t v = hash_vals[item_slot[i]];
@@ -197,6 +204,7 @@ __global__ void k_ids_coarsen(const int32_t* __restrict__ item_slot, const int32
                               const int32_t* __restrict__ n_items_dev, const uint64_t* __restrict__ fine_keys,
                               int32_t* __restrict__ parent, uint8_t* __restrict__ off,
                               int32_t* __restrict__ child_tbl, int64_t tbl_stride) {
+  mm3d_griddep_wait();  // programmatic dependent launch: the previous kernel's writes are visible from here
   const int64_t n = *n_items_dev;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t q = hash_vals[item_slot[i]];
@@ -212,6 +220,7 @@ __global__ void k_ids_coarsen(const int32_t* __restrict__ item_slot, const int32
 __global__ void k_nbr27(const uint64_t* __restrict__ keys, const int32_t* __restrict__ n_dev, int spatial,
                         const uint64_t* __restrict__ hash_keys, const int32_t* __restrict__ hash_vals,
                         const int32_t* __restrict__ hash_mask_dev, int32_t* __restrict__ tbl, int64_t tbl_stride) {
+  mm3d_griddep_wait();  // programmatic dependent launch: the previous kernel's writes are visible from here
   const int64_t n = *n_dev;
   const uint32_t mask = (uint32_t)*hash_mask_dev;
   const int64_t total = 27 * n;
@@ -293,16 +302,16 @@ extern "C" int mm3d_voxelize(const int64_t* coords, int64_t n_points, int spatia
   int rc = carve_ws(ws, ws_bytes, n_points, hash_cap, &w);
   if (rc) return rc;
   int32_t* mask_dev = mask_slot(hash_vals, hash_cap);
-  k_setup<<<1, 32, 0, stream>>>(nullptr, n_points, hash_cap - 1, mask_dev, n_vox_dev, w.n_items);
-  k_clear<<<mm3d_grid(hash_cap, 256), 256, 0, stream>>>(hash_keys, w.slot_min, mask_dev, w.n_items, npts, 1, 0, 0);
+  MM3D_CUDA(mm3d_launch_pdl(k_setup, dim3(1), dim3(32), 0, stream, nullptr, n_points, hash_cap - 1, mask_dev, n_vox_dev, w.n_items));
+  MM3D_CUDA(mm3d_launch_pdl(k_clear, dim3(mm3d_grid(hash_cap, 256)), dim3(256), 0, stream, hash_keys, w.slot_min, mask_dev, w.n_items, npts, 1, 0, 0));
   if (n_points > 0) {
     SrcCoords src{coords, spatial_size, status_dev};
-    k_insert<<<mm3d_grid(n_points, 256), 256, 0, stream>>>(src, w.n_items, hash_keys, w.slot_min, mask_dev, w.item_slot);
-    k_count<<<w.nblocks, kScanThreads, 0, stream>>>(w.item_slot, w.slot_min, w.n_items, w.block_sums);
-    k_scan_blocks<<<1, kScanThreads, 0, stream>>>(w.block_sums, w.nblocks, n_vox_dev);
-    k_assign<<<w.nblocks, kScanThreads, 0, stream>>>(w.item_slot, w.slot_min, w.n_items, w.block_sums,
-                                                     hash_keys, hash_vals, vox_keys);
-    k_ids_level0<<<mm3d_grid(n_points, 256), 256, 0, stream>>>(w.item_slot, hash_vals, w.n_items, p2v, npts);
+    MM3D_CUDA(mm3d_launch_pdl(k_insert<SrcCoords>, dim3(mm3d_grid(n_points, 256)), dim3(256), 0, stream, src, w.n_items, hash_keys, w.slot_min, mask_dev, w.item_slot));
+    MM3D_CUDA(mm3d_launch_pdl(k_count, dim3(w.nblocks), dim3(kScanThreads), 0, stream, w.item_slot, w.slot_min, w.n_items, w.block_sums));
+    MM3D_CUDA(mm3d_launch_pdl(k_scan_blocks, dim3(1), dim3(kScanThreads), 0, stream, w.block_sums, w.nblocks, n_vox_dev));
+    MM3D_CUDA(mm3d_launch_pdl(k_assign, dim3(w.nblocks), dim3(kScanThreads), 0, stream, w.item_slot, w.slot_min, w.n_items, w.block_sums,
+                                                     hash_keys, hash_vals, vox_keys));
+    MM3D_CUDA(mm3d_launch_pdl(k_ids_level0, dim3(mm3d_grid(n_points, 256)), dim3(256), 0, stream, w.item_slot, hash_vals, w.n_items, p2v, npts));
   }
   mm3d_count_launches(n_points > 0 ? 7 : 2);
   MM3D_CHECK_LAUNCH("mm3d_voxelize");
@@ -321,19 +330,19 @@ extern "C" int mm3d_coarsen(const uint64_t* fine_keys, const int32_t* n_fine_dev
   int rc = carve_ws(ws, ws_bytes, n_fine_cap, hash_cap, &w);
   if (rc) return rc;
   int32_t* mask_dev = mask_slot(hash_vals, hash_cap);
-  k_setup<<<1, 32, 0, stream>>>(n_fine_dev, 0, hash_cap - 1, mask_dev, n_coarse_dev, w.n_items);
+  MM3D_CUDA(mm3d_launch_pdl(k_setup, dim3(1), dim3(32), 0, stream, n_fine_dev, 0, hash_cap - 1, mask_dev, n_coarse_dev, w.n_items));
   // child table: -1 over (at most) n_fine rows of each of the 8 planes; coarse rows <= fine rows
-  k_clear<<<mm3d_grid(hash_cap, 256), 256, 0, stream>>>(hash_keys, w.slot_min, mask_dev, w.n_items,
-                                                        child_tbl, 8, tbl_stride, -1);
+  MM3D_CUDA(mm3d_launch_pdl(k_clear, dim3(mm3d_grid(hash_cap, 256)), dim3(256), 0, stream, hash_keys, w.slot_min, mask_dev, w.n_items,
+                                                        child_tbl, 8, tbl_stride, -1));
   if (n_fine_cap > 0) {
     SrcCoarsen src{fine_keys};
-    k_insert<<<mm3d_grid(n_fine_cap, 256), 256, 0, stream>>>(src, w.n_items, hash_keys, w.slot_min, mask_dev, w.item_slot);
-    k_count<<<w.nblocks, kScanThreads, 0, stream>>>(w.item_slot, w.slot_min, w.n_items, w.block_sums);
-    k_scan_blocks<<<1, kScanThreads, 0, stream>>>(w.block_sums, w.nblocks, n_coarse_dev);
-    k_assign<<<w.nblocks, kScanThreads, 0, stream>>>(w.item_slot, w.slot_min, w.n_items, w.block_sums,
-                                                     hash_keys, hash_vals, coarse_keys);
-    k_ids_coarsen<<<mm3d_grid(n_fine_cap, 256), 256, 0, stream>>>(w.item_slot, hash_vals, w.n_items, fine_keys,
-                                                                 parent, off, child_tbl, tbl_stride);
+    MM3D_CUDA(mm3d_launch_pdl(k_insert<SrcCoarsen>, dim3(mm3d_grid(n_fine_cap, 256)), dim3(256), 0, stream, src, w.n_items, hash_keys, w.slot_min, mask_dev, w.item_slot));
+    MM3D_CUDA(mm3d_launch_pdl(k_count, dim3(w.nblocks), dim3(kScanThreads), 0, stream, w.item_slot, w.slot_min, w.n_items, w.block_sums));
+    MM3D_CUDA(mm3d_launch_pdl(k_scan_blocks, dim3(1), dim3(kScanThreads), 0, stream, w.block_sums, w.nblocks, n_coarse_dev));
+    MM3D_CUDA(mm3d_launch_pdl(k_assign, dim3(w.nblocks), dim3(kScanThreads), 0, stream, w.item_slot, w.slot_min, w.n_items, w.block_sums,
+                                                     hash_keys, hash_vals, coarse_keys));
+    MM3D_CUDA(mm3d_launch_pdl(k_ids_coarsen, dim3(mm3d_grid(n_fine_cap, 256)), dim3(256), 0, stream, w.item_slot, hash_vals, w.n_items, fine_keys,
+                                                                 parent, off, child_tbl, tbl_stride));
   }
   mm3d_count_launches(n_fine_cap > 0 ? 7 : 2);
   MM3D_CHECK_LAUNCH("mm3d_coarsen");
@@ -347,8 +356,8 @@ extern "C" int mm3d_build_nbr27(const uint64_t* keys, const int32_t* n_dev, int6
   MM3D_REQUIRE(tbl_stride >= n_cap, MM3D_ERR_INVALID, "tbl_stride must be >= n_cap");
   MM3D_REQUIRE(spatial_size > 0 && spatial_size <= 65536, MM3D_ERR_INVALID, "spatial_size must be in (0, 65536]");
   if (n_cap > 0)
-    k_nbr27<<<mm3d_grid(27 * n_cap, 256), 256, 0, stream>>>(keys, n_dev, spatial_size, hash_keys, hash_vals,
-                                                           hash_vals + (hash_cap - 1), nbr_tbl, tbl_stride);
+    MM3D_CUDA(mm3d_launch_pdl(k_nbr27, dim3(mm3d_grid(27 * n_cap, 256)), dim3(256), 0, stream, keys, n_dev, spatial_size, hash_keys, hash_vals,
+                                                           hash_vals + (hash_cap - 1), nbr_tbl, tbl_stride));
   mm3d_count_launches(n_cap > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_build_nbr27");
   return MM3D_OK;
