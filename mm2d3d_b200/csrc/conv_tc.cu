@@ -91,6 +91,7 @@ struct WImgBatch {
   WImgItem item[kMaxImgBatch];
 };
 __global__ void k_weight_images(const __grid_constant__ WImgBatch b) {
+  mm3d_griddep_wait();
   int i = 0;
   while (i + 1 < b.n && (int)blockIdx.x >= b.item[i + 1].block0) ++i;
   const WImgItem& it = b.item[i];
@@ -386,7 +387,7 @@ int mm3d_conv_tc_build_images(const float* const* weights, float* const* images,
       blocks += nb_blocks < 1 ? 1 : nb_blocks;
     }
     if (blocks == 0) continue;
-    k_weight_images<<<blocks, 256, 0, stream>>>(b);
+    MM3D_CUDA(mm3d_launch_pdl(k_weight_images, dim3(blocks), dim3(256), 0, stream, b));
     mm3d_count_launches(1);
     MM3D_CHECK_LAUNCH("mm3d_conv_tc_build_images");
   }

@@ -16,6 +16,7 @@ namespace {
 __global__ void k_input_fwd(const float* __restrict__ feats, const int32_t* __restrict__ p2v,
                             const int32_t* __restrict__ npts, int64_t n_points, int c, int mode,
                             float* __restrict__ out) {
+  mm3d_griddep_wait();
   const int64_t total = n_points * c;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i / c;
@@ -34,6 +35,7 @@ __global__ void k_input_fwd(const float* __restrict__ feats, const int32_t* __re
 __global__ void k_input_bwd(const float* __restrict__ d_vox, const int32_t* __restrict__ p2v,
                             const int32_t* __restrict__ npts, int64_t n_points, int c, int mode,
                             float* __restrict__ d_feats) {
+  mm3d_griddep_wait();
   const int64_t total = n_points * c;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i / c;
@@ -49,6 +51,7 @@ __global__ void k_input_bwd(const float* __restrict__ d_vox, const int32_t* __re
 template <int VEC>
 __global__ void k_output_fwd(const float* __restrict__ vox, const int32_t* __restrict__ p2v,
                              int64_t n_points, int cv, float* __restrict__ out) {
+  mm3d_griddep_wait();
   const int64_t total = n_points * cv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i / cv;
@@ -64,6 +67,7 @@ __global__ void k_output_fwd(const float* __restrict__ vox, const int32_t* __res
 
 __global__ void k_output_bwd(const float* __restrict__ d_out, const int32_t* __restrict__ p2v,
                              int64_t n_points, int c, float* __restrict__ d_vox) {
+  mm3d_griddep_wait();
   const int64_t total = n_points * c;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t p = i / c;
@@ -132,7 +136,7 @@ extern "C" int mm3d_input_fwd(const float* feats, const int32_t* p2v, const int3
   MM3D_REQUIRE(c > 0 && n_points >= 0 && n_vox >= 0, MM3D_ERR_INVALID, "bad sizes");
   if (n_vox > 0) MM3D_CUDA(cudaMemsetAsync(out_vox, 0, sizeof(float) * (size_t)n_vox * c, stream));
   if (n_points > 0)
-    k_input_fwd<<<mm3d_grid(n_points * c, 256), 256, 0, stream>>>(feats, p2v, npts, n_points, c, mode, out_vox);
+    MM3D_CUDA(mm3d_launch_pdl(k_input_fwd, dim3(mm3d_grid(n_points * c, 256)), dim3(256), 0, stream, feats, p2v, npts, n_points, c, mode, out_vox));
   mm3d_count_launches(n_points > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_input_fwd");
   return MM3D_OK;
@@ -143,7 +147,7 @@ extern "C" int mm3d_input_bwd(const float* d_vox, const int32_t* p2v, const int3
   cudaStream_t stream = (cudaStream_t)stream_;
   MM3D_REQUIRE(mode == 3 || mode == 4, MM3D_ERR_UNSUPPORTED, "InputLayer mode %d not implemented", mode);
   if (n_points > 0)
-    k_input_bwd<<<mm3d_grid(n_points * c, 256), 256, 0, stream>>>(d_vox, p2v, npts, n_points, c, mode, d_feats);
+    MM3D_CUDA(mm3d_launch_pdl(k_input_bwd, dim3(mm3d_grid(n_points * c, 256)), dim3(256), 0, stream, d_vox, p2v, npts, n_points, c, mode, d_feats));
   mm3d_count_launches(n_points > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_input_bwd");
   return MM3D_OK;
@@ -155,9 +159,9 @@ extern "C" int mm3d_output_fwd(const float* vox, const int32_t* p2v, int64_t n_p
   if (n_points > 0) {
     const bool vec = (c % 4 == 0) && (((uintptr_t)vox | (uintptr_t)out) & 15) == 0;
     if (vec)
-      k_output_fwd<4><<<mm3d_grid(n_points * (c / 4), 256), 256, 0, stream>>>(vox, p2v, n_points, c / 4, out);
+      MM3D_CUDA(mm3d_launch_pdl(k_output_fwd<4>, dim3(mm3d_grid(n_points * (c / 4), 256)), dim3(256), 0, stream, vox, p2v, n_points, c / 4, out));
     else
-      k_output_fwd<1><<<mm3d_grid(n_points * c, 256), 256, 0, stream>>>(vox, p2v, n_points, c, out);
+      MM3D_CUDA(mm3d_launch_pdl(k_output_fwd<1>, dim3(mm3d_grid(n_points * c, 256)), dim3(256), 0, stream, vox, p2v, n_points, c, out));
   }
   mm3d_count_launches(n_points > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_output_fwd");
@@ -169,7 +173,7 @@ extern "C" int mm3d_output_bwd(const float* d_out, const int32_t* p2v, int64_t n
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_vox > 0) MM3D_CUDA(cudaMemsetAsync(d_vox, 0, sizeof(float) * (size_t)n_vox * c, stream));
   if (n_points > 0)
-    k_output_bwd<<<mm3d_grid(n_points * c, 256), 256, 0, stream>>>(d_out, p2v, n_points, c, d_vox);
+    MM3D_CUDA(mm3d_launch_pdl(k_output_bwd, dim3(mm3d_grid(n_points * c, 256)), dim3(256), 0, stream, d_out, p2v, n_points, c, d_vox));
   mm3d_count_launches(n_points > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_output_bwd");
   return MM3D_OK;

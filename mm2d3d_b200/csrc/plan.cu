@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 k_build_plans(const __grid_constant__ PlanBatch batch, unsigned int* __restrict__ done_counters) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   PlanSmem& s = *reinterpret_cast<PlanSmem*>(smem_raw);
+  mm3d_griddep_wait();
   int i = 0;
   while (i + 1 < batch.n && (int)blockIdx.x >= batch.item[i + 1].block0) ++i;
   const PlanItem& it = batch.item[i];
@@ -398,7 +399,7 @@ extern "C" int mm3d_build_plans(const mm3d_plan_desc* descs, int n_plans, mm3d_s
       blocks += (int)mm3d_cdiv(rows, kChunk);
     }
     if (blocks == 0) continue;
-    k_build_plans<<<(unsigned)blocks, kThreads, sizeof(PlanSmem), stream>>>(batch, counters);
+    MM3D_CUDA(mm3d_launch_pdl(k_build_plans, dim3((unsigned)blocks), dim3(kThreads), sizeof(PlanSmem), stream, batch, counters));
     mm3d_count_launches(1);
     MM3D_CHECK_LAUNCH("mm3d_build_plans");
   }

@@ -39,6 +39,23 @@ def collect_slots(net):
 
 
 def fusable(net) -> bool:
+    """Whether ``net`` has the shape the executor implements.  The module walk costs ~0.35 ms, so the answer is
+    cached on the network together with what it depends on (per-layer conv modes, leakiness, InputLayer mode)."""
+    from . import scn
+    mods = getattr(net, "_exec_mods", None)
+    if mods is None:
+        mods = net._exec_mods = [m for m in net.modules() if isinstance(m, (scn._ConvBase, scn.BatchNormLeakyReLU))]
+    key = (net.layer1.mode if isinstance(net.layer1, scn.InputLayer) else None,
+           tuple((m.mode, hasattr(m, "bias")) if isinstance(m, scn._ConvBase) else m.leakiness for m in mods))
+    cached = getattr(net, "_exec_fusable", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    ok = _fusable(net)
+    net._exec_fusable = (key, ok)
+    return ok
+
+
+def _fusable(net) -> bool:
     from . import scn
     if not isinstance(net.layer1, scn.InputLayer) or net.layer1.mode != 4:
         return False
