@@ -378,7 +378,8 @@ def run_ours(args):
     launches = _lib.lib.mm3d_kernel_launches() - launches0
     # a short timed region can fall between two 50 ms samples: run on under the sampler for ~0.4 s (the same number
     # of extra steps on every rank, decided by rank 0, because steps contain a collective)
-    extra = torch.tensor([max(0, int(400.0 / max(ms / args.steps, 1e-3)) - args.steps)], device=dev, dtype=torch.int64)
+    extra = torch.tensor([0 if os.environ.get("MM3D_BENCH_NO_RUNON") else
+                          max(0, int(400.0 / max(ms / args.steps, 1e-3)) - args.steps)], device=dev, dtype=torch.int64)
     if world > 1:
         dist.broadcast(extra, 0)
     for i in range(int(extra.item())):

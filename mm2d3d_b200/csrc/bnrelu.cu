@@ -212,7 +212,22 @@ k_bn_fwd_fused(const float* __restrict__ x, float* __restrict__ y, int64_t n, in
     scale[j] = s_scale[v * VEC + j];
     bet[j] = __ldg(beta + v * VEC + j);
   }
-  for (int64_t row = (int64_t)blockIdx.x * rows_pass + r; row < n; row += stride) {
+  int64_t row = (int64_t)blockIdx.x * rows_pass + r;
+  for (; row + 3 * stride < n; row += 4 * stride) {  // four independent loads in flight
+    float t[4][VEC];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) vload<VEC>(x + (row + u * stride) * c + v * VEC, t[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float o = fmaf(t[u][j] - mean[j], scale[j], bet[j]);
+        t[u][j] = o > 0.f ? o : o * leak;
+      }
+      vstore<VEC>(y + (row + u * stride) * c + v * VEC, t[u]);
+    }
+  }
+  for (; row < n; row += stride) {
     float t[VEC];
     vload<VEC>(x + row * c + v * VEC, t);
 #pragma unroll
@@ -299,7 +314,27 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ dy, float*
   }
   grid_release(sync, sums, 2 * c);
   if (r >= rows_pass) return;
-  for (int64_t row = (int64_t)blockIdx.x * rows_pass + r; row < n; row += stride) {
+  int64_t row = (int64_t)blockIdx.x * rows_pass + r;
+  for (; row + stride < n; row += 2 * stride) {  // two rows (four loads) in flight
+    float t[2][VEC], g[2][VEC];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      vload<VEC>(x + (row + u * stride) * c + v * VEC, t[u]);
+      vload<VEC>(dy + (row + u * stride) * c + v * VEC, g[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const float xc = t[u][j] - mean[j];
+        const float o = fmaf(xc, scale[j], bet[j]);
+        const float d = o > 0.f ? g[u][j] : g[u][j] * leak;
+        g[u][j] = scale[j] * (d - md[j] - xc * invstd[j] * mdx[j]);
+      }
+      vstore<VEC>(dx + (row + u * stride) * c + v * VEC, g[u]);
+    }
+  }
+  for (; row < n; row += stride) {
     float t[VEC], g[VEC];
     vload<VEC>(x + row * c + v * VEC, t);
     vload<VEC>(dy + row * c + v * VEC, g);
