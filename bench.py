@@ -305,9 +305,19 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; this script prints ONE JSON line
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        # NCCL prints its version banner on stdout when the communicator is created; this script's stdout is ONE
+        # JSON line, so stdout points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     from mm2d3d_b200 import _lib, synth
     from mm2d3d_b200 import scn as scn_mod
