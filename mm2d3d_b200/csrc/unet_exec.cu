@@ -119,11 +119,36 @@ __global__ void k_copy_cols(const float* __restrict__ src, int64_t n, int c_src,
   mm3d_griddep_launch();
   mm3d_griddep_wait();
   // dst[r, dst_col0 + j] = src[r, src_col0 + j], j < ncols  (other dst columns untouched)
+  if (((ncols | c_src | c_dst | dst_col0 | src_col0) & 3) == 0) {  // whole float4s (every layer of the network)
+    const int nv = ncols >> 2;
+    const int64_t total = n * nv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i / nv;
+      const int j = (int)(i - r * nv) << 2;
+      *reinterpret_cast<float4*>(dst + r * c_dst + dst_col0 + j) =
+          __ldg(reinterpret_cast<const float4*>(src + r * c_src + src_col0 + j));
+    }
+    return;
+  }
   const int64_t total = n * ncols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / ncols;
     const int j = (int)(i - r * ncols);
     dst[r * c_dst + dst_col0 + j] = __ldg(src + r * c_src + src_col0 + j);
+  }
+}
+
+// JoinTable: J = [A | B] (both [n, p], p a multiple of 4) in one pass
+__global__ void k_concat2(const float* __restrict__ a, const float* __restrict__ b, int64_t n, int p, float* __restrict__ j_out) {
+  mm3d_griddep_launch();
+  mm3d_griddep_wait();
+  const int pv = p >> 2;
+  const int64_t total = n * 2 * pv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (2 * pv);
+    const int v = (int)(i - r * 2 * pv);  // float4 column of J
+    const float* src = v < pv ? a + r * p + (v << 2) : b + r * p + ((v - pv) << 2);
+    *reinterpret_cast<float4*>(j_out + r * 2 * p + (v << 2)) = __ldg(reinterpret_cast<const float4*>(src));
   }
 }
 
@@ -144,6 +169,19 @@ __global__ void k_split_add(const float* __restrict__ dj, const float* __restric
   mm3d_griddep_launch();
   mm3d_griddep_wait();
   // dy = dj[:, :p] + add ; df = dj[:, p:]
+  if ((p & 3) == 0) {
+    const int pv = p >> 2;
+    const int64_t total = n * pv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i / pv;
+      const int j = (int)(i - r * pv) << 2;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(dj + r * 2 * p + j));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(add + r * p + j));
+      *reinterpret_cast<float4*>(dy + r * p + j) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      if (df) *reinterpret_cast<float4*>(df + r * p + j) = __ldg(reinterpret_cast<const float4*>(dj + r * 2 * p + p + j));
+    }
+    return;
+  }
   const int64_t total = n * p;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / p;
@@ -301,7 +339,7 @@ void join_side(Ctx& c) {
 
 void launch_copy_cols(Ctx& c, const float* src, int64_t n, int c_src, float* dst, int c_dst, int col0, int ncols) {
   if (n == 0 || c.rc) return;
-  if (mm3d_launch_pdl(k_copy_cols, dim3(mm3d_grid(n * ncols, 256)), dim3(256), 0, c.stream, src, n, c_src, dst, c_dst, col0, ncols, 0) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
+  if (mm3d_launch_pdl(k_copy_cols, dim3(mm3d_grid(n * ncols / 4 + 1, 256)), dim3(256), 0, c.stream, src, n, c_src, dst, c_dst, col0, ncols, 0) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
   mm3d_count_launches(1);
 }
 void launch_pad_cols(Ctx& c, const float* src, int64_t n, int c_src, float* dst, int c_dst) {
@@ -387,8 +425,17 @@ void level_fwd(Ctx& c, int l, int pbase) {
     level_fwd(c, l + 1, deeper);
     bn_fwd(c, up, net.b[l + 1].R, B.E, net.lv[l + 1].n, q, B.s_up);
     conv_fwd(c, UP, l, B.E, q, B.F, p, P(c, up + 4));
-    launch_copy_cols(c, B.Y, n, p, B.J, 2 * p, 0, p);
-    launch_copy_cols(c, B.F, n, p, B.J, 2 * p, p, p);
+    if ((p & 3) == 0) {
+      if (n && !c.rc) {
+        if (mm3d_launch_pdl(k_concat2, dim3(mm3d_grid(n * p / 2 + 1, 256)), dim3(256), 0, c.stream, (const float*)B.Y,
+                            (const float*)B.F, n, p, B.J) != cudaSuccess)
+          c.rc = MM3D_ERR_CUDA;
+        mm3d_count_launches(1);
+      }
+    } else {
+      launch_copy_cols(c, B.Y, n, p, B.J, 2 * p, 0, p);
+      launch_copy_cols(c, B.F, n, p, B.J, 2 * p, p, p);
+    }
     bn_fwd(c, post, B.J, B.G, n, 2 * p, B.s_post);
     conv_fwd(c, SMC, l, B.G, 2 * p, B.R, p, P(c, post + 4));
   }
@@ -415,7 +462,7 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
     float* d_Yskip = g.f(n, p);
     // d_F = d_J[:, p:]; the skip half is combined with the branch gradient further down
     if (n && !c.rc) {
-      if (mm3d_launch_pdl(k_copy_cols, dim3(mm3d_grid(n * p, 256)), dim3(256), 0, c.stream, (const float*)d_J, n, 2 * p, d_F, p, 0, p, p) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
+      if (mm3d_launch_pdl(k_copy_cols, dim3(mm3d_grid(n * p / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)d_J, n, 2 * p, d_F, p, 0, p, p) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
       mm3d_count_launches(1);
     }
     float* d_E = g.f(nc, q);
@@ -430,7 +477,7 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
     bn_bwd(c, dn, B.Y, d_B, d_Ybr, n, p, B.s_dn);
     // d_Y = d_J[:, :p] + d_Ybr
     if (n && !c.rc) {
-      if (mm3d_launch_pdl(k_split_add, dim3(mm3d_grid(n * p, 256)), dim3(256), 0, c.stream, (const float*)d_J, (const float*)d_Ybr, n, p, d_Yskip, (float*)nullptr) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
+      if (mm3d_launch_pdl(k_split_add, dim3(mm3d_grid(n * p / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)d_J, (const float*)d_Ybr, n, p, d_Yskip, (float*)nullptr) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
       mm3d_count_launches(1);
     }
     d_Y = d_Yskip;
