@@ -150,7 +150,7 @@ __device__ __forceinline__ void grid_release(unsigned int* sync, double* sums, i
 // rows it summed, so the second read comes from L2 / L1 instead of HBM.
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
-k_bn_fwd_fused(const float* __restrict__ x, float* __restrict__ y, int64_t n, int c,
+k_bn_fwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int c_lo, float* __restrict__ y, int64_t n, int c,
                const float* __restrict__ gamma, const float* __restrict__ beta,
                float* running_mean, float* running_var, float* save_mean, float* save_invstd,
                double* sums, unsigned int* sync, float eps, float momentum, float leak, int* err) {
@@ -160,6 +160,11 @@ k_bn_fwd_fused(const float* __restrict__ x, float* __restrict__ y, int64_t n, in
   const int rows_pass = kThreads / cv;
   const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
   const int64_t stride = (int64_t)gridDim.x * rows_pass;
+  // x may be given as two column blocks [x | x_hi] (JoinTable without materialising the concatenation): this
+  // thread's channel vector of row i is xb[i * xld]
+  const bool hi = c_lo > 0 && v * VEC >= c_lo;
+  const float* xb = (x_hi && hi) ? x_hi + (v * VEC - c_lo) : x + v * VEC;
+  const int64_t xld = x_hi ? (hi ? c - c_lo : c_lo) : c;
   {
     float s[VEC], q[VEC];
 #pragma unroll
@@ -169,7 +174,7 @@ k_bn_fwd_fused(const float* __restrict__ x, float* __restrict__ y, int64_t n, in
       for (; row + 3 * stride < n; row += 4 * stride) {  // four independent loads in flight
         float t[4][VEC];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) vload<VEC>(x + (row + u * stride) * c + v * VEC, t[u]);
+        for (int u = 0; u < 4; ++u) vload<VEC>(xb + (row + u * stride) * xld, t[u]);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -177,7 +182,7 @@ k_bn_fwd_fused(const float* __restrict__ x, float* __restrict__ y, int64_t n, in
       }
       for (; row < n; row += stride) {
         float t[VEC];
-        vload<VEC>(x + row * c + v * VEC, t);
+        vload<VEC>(xb + row * xld, t);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) { s[j] += t[j]; q[j] = fmaf(t[j], t[j], q[j]); }
       }
@@ -216,7 +221,7 @@ k_bn_fwd_fused(const float* __restrict__ x, float* __restrict__ y, int64_t n, in
   for (; row + 3 * stride < n; row += 4 * stride) {  // four independent loads in flight
     float t[4][VEC];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) vload<VEC>(x + (row + u * stride) * c + v * VEC, t[u]);
+    for (int u = 0; u < 4; ++u) vload<VEC>(xb + (row + u * stride) * xld, t[u]);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
 #pragma unroll
@@ -229,7 +234,7 @@ k_bn_fwd_fused(const float* __restrict__ x, float* __restrict__ y, int64_t n, in
   }
   for (; row < n; row += stride) {
     float t[VEC];
-    vload<VEC>(x + row * c + v * VEC, t);
+    vload<VEC>(xb + row * xld, t);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const float o = fmaf(t[j] - mean[j], scale[j], bet[j]);
@@ -242,7 +247,8 @@ k_bn_fwd_fused(const float* __restrict__ x, float* __restrict__ y, int64_t n, in
 // ---- backward in ONE launch: reductions, grid barrier, dx (+ d_gamma / d_beta by CTA 0)
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
-k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int64_t n, int c,
+k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int c_lo, const float* __restrict__ dy,
+               float* __restrict__ dx, float* __restrict__ dx_hi, int64_t n, int c,
                const float* __restrict__ gamma, const float* __restrict__ beta,
                const float* __restrict__ save_mean, const float* __restrict__ save_invstd, float leak,
                double* sums, unsigned int* sync, float* d_gamma, float* d_beta, int training, int* err) {
@@ -252,6 +258,13 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ dy, float*
   const int rows_pass = kThreads / cv;
   const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
   const int64_t stride = (int64_t)gridDim.x * rows_pass;
+  // x may be given as two column blocks [x | x_hi] (JoinTable without materialising the concatenation): this
+  // thread's channel vector of row i is xb[i * xld]
+  const bool hi = c_lo > 0 && v * VEC >= c_lo;
+  const float* xb = (x_hi && hi) ? x_hi + (v * VEC - c_lo) : x + v * VEC;
+  const int64_t xld = x_hi ? (hi ? c - c_lo : c_lo) : c;
+  float* dxb = (dx_hi && hi) ? dx_hi + (v * VEC - c_lo) : dx + v * VEC;
+  const int64_t dxld = dx_hi ? (hi ? c - c_lo : c_lo) : c;
   float mean[VEC], invstd[VEC], scale[VEC], bet[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) mean[j] = invstd[j] = scale[j] = bet[j] = 0.f;
@@ -274,10 +287,10 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ dy, float*
       for (; row < n; row += 2 * stride) {  // two rows (four loads) in flight
         float t[2][VEC], g[2][VEC];
         const bool second = row + stride < n;
-        vload<VEC>(x + row * c + v * VEC, t[0]);
+        vload<VEC>(xb + row * xld, t[0]);
         vload<VEC>(dy + row * c + v * VEC, g[0]);
         if (second) {
-          vload<VEC>(x + (row + stride) * c + v * VEC, t[1]);
+          vload<VEC>(xb + (row + stride) * xld, t[1]);
           vload<VEC>(dy + (row + stride) * c + v * VEC, g[1]);
         }
 #pragma unroll
@@ -319,7 +332,7 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ dy, float*
     float t[2][VEC], g[2][VEC];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      vload<VEC>(x + (row + u * stride) * c + v * VEC, t[u]);
+      vload<VEC>(xb + (row + u * stride) * xld, t[u]);
       vload<VEC>(dy + (row + u * stride) * c + v * VEC, g[u]);
     }
 #pragma unroll
@@ -331,12 +344,12 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ dy, float*
         const float d = o > 0.f ? g[u][j] : g[u][j] * leak;
         g[u][j] = scale[j] * (d - md[j] - xc * invstd[j] * mdx[j]);
       }
-      vstore<VEC>(dx + (row + u * stride) * c + v * VEC, g[u]);
+      vstore<VEC>(dxb + (row + u * stride) * dxld, g[u]);
     }
   }
   for (; row < n; row += stride) {
     float t[VEC], g[VEC];
-    vload<VEC>(x + row * c + v * VEC, t);
+    vload<VEC>(xb + row * xld, t);
     vload<VEC>(dy + row * c + v * VEC, g);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -345,7 +358,7 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ dy, float*
       const float d = o > 0.f ? g[j] : g[j] * leak;
       g[j] = scale[j] * (d - md[j] - xc * invstd[j] * mdx[j]);
     }
-    vstore<VEC>(dx + row * c + v * VEC, g);
+    vstore<VEC>(dxb + row * dxld, g);
   }
 }
 
@@ -378,15 +391,17 @@ extern "C" size_t mm3d_bnrelu_workspace_bytes(int c) { return mm3d_align(sizeof(
   } while (0)
 
 // ws_clean: the workspace is known to be all zero (the kernels leave it that way), skip the memset
-int mm3d_bnrelu_fwd_impl(const float* x, float* y, int64_t n, int c, const float* gamma, const float* beta,
+int mm3d_bnrelu_fwd_impl(const float* x, const float* x_hi, int c_lo, float* y, int64_t n, int c, const float* gamma,
+                         const float* beta,
                          float* running_mean, float* running_var, float* save_mean, float* save_invstd,
                          float eps, float momentum, float leakiness, int training,
                          void* ws, size_t ws_bytes, bool ws_clean, cudaStream_t stream) {
   MM3D_REQUIRE(c > 0 && n >= 0, MM3D_ERR_INVALID, "bad sizes");
-  const bool vec4 = (c % 4 == 0) && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
+  const bool vec4 = (c % 4 == 0) && (c_lo % 4 == 0) && ((((uintptr_t)x | (uintptr_t)x_hi | (uintptr_t)y) & 15) == 0);
   const int cv = vec4 ? c / 4 : c;
   MM3D_REQUIRE(cv <= kThreads, MM3D_ERR_UNSUPPORTED, "BatchNorm with %d channels not supported", c);
   MM3D_REQUIRE(ws_bytes >= mm3d_bnrelu_workspace_bytes(c) && ws, MM3D_ERR_WORKSPACE, "bnrelu workspace too small");
+  MM3D_REQUIRE(!x_hi || (training && c_lo > 0 && c_lo < c), MM3D_ERR_INVALID, "split input needs training mode and 0 < c_lo < c");
   if (n == 0) return MM3D_OK;
   double* sums = (double*)ws;
   unsigned int* sync = (unsigned int*)(sums + 2 * c);
@@ -396,7 +411,7 @@ int mm3d_bnrelu_fwd_impl(const float* x, float* y, int64_t n, int c, const float
   if (training) {
     MM3D_REQUIRE(save_mean && save_invstd && running_mean && running_var, MM3D_ERR_INVALID, "training needs stat buffers");
     if (!ws_clean) MM3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c + 16, stream));
-    BN_DISPATCH_PDL(k_bn_fwd_fused, x, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, sums, sync,
+    BN_DISPATCH_PDL(k_bn_fwd_fused, x, x_hi, c_lo, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, sums, sync,
                 eps, momentum, leakiness, mm3d_device_err_flag());
   } else {
     BN_DISPATCH(k_bn_apply, x, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, sums, eps,
@@ -407,12 +422,13 @@ int mm3d_bnrelu_fwd_impl(const float* x, float* y, int64_t n, int c, const float
   return MM3D_OK;
 }
 
-int mm3d_bnrelu_bwd_impl(const float* x, const float* dy, float* dx, int64_t n, int c, const float* gamma,
-                         const float* beta, const float* save_mean, const float* save_invstd,
+int mm3d_bnrelu_bwd_impl(const float* x, const float* x_hi, int c_lo, const float* dy, float* dx, float* dx_hi,
+                         int64_t n, int c, const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
                          float* d_gamma, float* d_beta, float leakiness, int training,
                          void* ws, size_t ws_bytes, bool ws_clean, cudaStream_t stream) {
   MM3D_REQUIRE(c > 0 && n >= 0, MM3D_ERR_INVALID, "bad sizes");
-  const bool vec4 = (c % 4 == 0) && ((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0);
+  const bool vec4 = (c % 4 == 0) && (c_lo % 4 == 0) &&
+                    ((((uintptr_t)x | (uintptr_t)x_hi | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dx_hi) & 15) == 0);
   const int cv = vec4 ? c / 4 : c;
   MM3D_REQUIRE(cv <= kThreads, MM3D_ERR_UNSUPPORTED, "BatchNorm with %d channels not supported", c);
   MM3D_REQUIRE(ws_bytes >= mm3d_bnrelu_workspace_bytes(c) && ws, MM3D_ERR_WORKSPACE, "bnrelu workspace too small");
@@ -427,7 +443,7 @@ int mm3d_bnrelu_bwd_impl(const float* x, const float* dy, float* dx, int64_t n, 
   const int grid = bn_grid(n, cv);
   const size_t smem = sizeof(double) * 2 * c > sizeof(float) * 2 * (kThreads / cv) * (size_t)c
                           ? sizeof(double) * 2 * c : sizeof(float) * 2 * (kThreads / cv) * (size_t)c;
-  BN_DISPATCH_PDL(k_bn_bwd_fused, x, dy, dx, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums, sync, d_gamma,
+  BN_DISPATCH_PDL(k_bn_bwd_fused, x, x_hi, c_lo, dy, dx, dx_hi, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums, sync, d_gamma,
               d_beta, training, mm3d_device_err_flag());
   mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_bnrelu_bwd");
@@ -438,7 +454,7 @@ extern "C" int mm3d_bnrelu_fwd(const float* x, float* y, int64_t n, int c, const
                                float* running_mean, float* running_var, float* save_mean, float* save_invstd,
                                float eps, float momentum, float leakiness, int training,
                                void* ws, size_t ws_bytes, mm3d_stream_t stream) {
-  return mm3d_bnrelu_fwd_impl(x, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, eps, momentum,
+  return mm3d_bnrelu_fwd_impl(x, nullptr, 0, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, eps, momentum,
                               leakiness, training, ws, ws_bytes, false, (cudaStream_t)stream);
 }
 
@@ -446,6 +462,6 @@ extern "C" int mm3d_bnrelu_bwd(const float* x, const float* dy, float* dx, int64
                                const float* beta, const float* save_mean, const float* save_invstd,
                                float* d_gamma, float* d_beta, float leakiness, int training,
                                void* ws, size_t ws_bytes, mm3d_stream_t stream) {
-  return mm3d_bnrelu_bwd_impl(x, dy, dx, n, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, leakiness, training,
+  return mm3d_bnrelu_bwd_impl(x, nullptr, 0, dy, dx, nullptr, n, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, leakiness, training,
                               ws, ws_bytes, false, (cudaStream_t)stream);
 }

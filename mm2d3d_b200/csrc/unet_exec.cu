@@ -23,14 +23,14 @@
 #include "common.cuh"
 
 // bnrelu.cu
-int mm3d_bnrelu_fwd_impl(const float* x, float* y, int64_t n, int c, const float* gamma, const float* beta,
-                         float* running_mean, float* running_var, float* save_mean, float* save_invstd, float eps,
-                         float momentum, float leakiness, int training, void* ws, size_t ws_bytes, bool ws_clean,
-                         cudaStream_t stream);
-int mm3d_bnrelu_bwd_impl(const float* x, const float* dy, float* dx, int64_t n, int c, const float* gamma,
-                         const float* beta, const float* save_mean, const float* save_invstd, float* d_gamma,
-                         float* d_beta, float leakiness, int training, void* ws, size_t ws_bytes, bool ws_clean,
-                         cudaStream_t stream);
+int mm3d_bnrelu_fwd_impl(const float* x, const float* x_hi, int c_lo, float* y, int64_t n, int c, const float* gamma,
+                         const float* beta, float* running_mean, float* running_var, float* save_mean,
+                         float* save_invstd, float eps, float momentum, float leakiness, int training, void* ws,
+                         size_t ws_bytes, bool ws_clean, cudaStream_t stream);
+int mm3d_bnrelu_bwd_impl(const float* x, const float* x_hi, int c_lo, const float* dy, float* dx, float* dx_hi,
+                         int64_t n, int c, const float* gamma, const float* beta, const float* save_mean,
+                         const float* save_invstd, float* d_gamma, float* d_beta, float leakiness, int training,
+                         void* ws, size_t ws_bytes, bool ws_clean, cudaStream_t stream);
 
 // conv_tc.cu
 size_t mm3d_conv_tc_workspace_bytes(int c_in, int c_out, int K);
@@ -164,21 +164,21 @@ __global__ void k_pad_cols(const float* __restrict__ src, int64_t n, int c_src, 
   }
 }
 
-__global__ void k_split_add(const float* __restrict__ dj, const float* __restrict__ add, int64_t n, int p,
+__global__ void k_split_add(const float* __restrict__ dj, int ldj, const float* __restrict__ add, int64_t n, int p,
                             float* __restrict__ dy, float* __restrict__ df) {
   mm3d_griddep_launch();
   mm3d_griddep_wait();
-  // dy = dj[:, :p] + add ; df = dj[:, p:]
+  // dy = dj[:, :p] + add ; df = dj[:, p:]   (dj rows are ldj floats apart; df only with ldj == 2p)
   if ((p & 3) == 0) {
     const int pv = p >> 2;
     const int64_t total = n * pv;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
       const int64_t r = i / pv;
       const int j = (int)(i - r * pv) << 2;
-      const float4 a = __ldg(reinterpret_cast<const float4*>(dj + r * 2 * p + j));
+      const float4 a = __ldg(reinterpret_cast<const float4*>(dj + r * ldj + j));
       const float4 b = __ldg(reinterpret_cast<const float4*>(add + r * p + j));
       *reinterpret_cast<float4*>(dy + r * p + j) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-      if (df) *reinterpret_cast<float4*>(df + r * p + j) = __ldg(reinterpret_cast<const float4*>(dj + r * 2 * p + p + j));
+      if (df) *reinterpret_cast<float4*>(df + r * p + j) = __ldg(reinterpret_cast<const float4*>(dj + r * ldj + p + j));
     }
     return;
   }
@@ -186,8 +186,8 @@ __global__ void k_split_add(const float* __restrict__ dj, const float* __restric
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / p;
     const int j = (int)(i - r * p);
-    dy[i] = __ldg(dj + r * 2 * p + j) + __ldg(add + i);
-    if (df) df[i] = __ldg(dj + r * 2 * p + p + j);
+    dy[i] = __ldg(dj + r * ldj + j) + __ldg(add + i);
+    if (df) df[i] = __ldg(dj + r * ldj + p + j);
   }
 }
 
@@ -257,12 +257,16 @@ cudaStream_t wgrad_stream(Ctx& c) {
 const float* P(Ctx& c, int i) { return (const float*)c.params[i]; }
 float* Gp(Ctx& c, int i) { return (float*)c.grads[i]; }
 
-void bn_fwd(Ctx& c, int pidx, const float* x, float* y, int64_t n, int ch, float* save) {
-  EX(mm3d_bnrelu_fwd_impl(x, y, n, ch, P(c, pidx), P(c, pidx + 1), (float*)c.params[pidx + 2], (float*)c.params[pidx + 3],
+// x_hi != NULL: the input is the column blocks [x | x_hi] ([n, c_lo] and [n, ch - c_lo]) -- JoinTable without
+// materialising the concatenation (training mode only)
+void bn_fwd(Ctx& c, int pidx, const float* x, float* y, int64_t n, int ch, float* save, const float* x_hi = nullptr,
+            int c_lo = 0) {
+  EX(mm3d_bnrelu_fwd_impl(x, x_hi, c_lo, y, n, ch, P(c, pidx), P(c, pidx + 1), (float*)c.params[pidx + 2], (float*)c.params[pidx + 3],
                           save, save + ch, c.eps, c.momentum, 0.f, c.training, c.bn_ws, c.bn_ws_bytes, true, c.stream));
 }
-void bn_bwd(Ctx& c, int pidx, const float* x, const float* dy, float* dx, int64_t n, int ch, const float* save) {
-  EX(mm3d_bnrelu_bwd_impl(x, dy, dx, n, ch, P(c, pidx), P(c, pidx + 1), save, save + ch, Gp(c, pidx), Gp(c, pidx + 1), 0.f,
+void bn_bwd(Ctx& c, int pidx, const float* x, const float* dy, float* dx, int64_t n, int ch, const float* save,
+            const float* x_hi = nullptr, int c_lo = 0, float* dx_hi = nullptr) {
+  EX(mm3d_bnrelu_bwd_impl(x, x_hi, c_lo, dy, dx, dx_hi, n, ch, P(c, pidx), P(c, pidx + 1), save, save + ch, Gp(c, pidx), Gp(c, pidx + 1), 0.f,
                           c.training, c.bn_ws, c.bn_ws_bytes, true, c.stream));
 }
 enum Kind { SMC, DOWN, UP };
@@ -425,18 +429,23 @@ void level_fwd(Ctx& c, int l, int pbase) {
     level_fwd(c, l + 1, deeper);
     bn_fwd(c, up, net.b[l + 1].R, B.E, net.lv[l + 1].n, q, B.s_up);
     conv_fwd(c, UP, l, B.E, q, B.F, p, P(c, up + 4));
-    if ((p & 3) == 0) {
-      if (n && !c.rc) {
-        if (mm3d_launch_pdl(k_concat2, dim3(mm3d_grid(n * p / 2 + 1, 256)), dim3(256), 0, c.stream, (const float*)B.Y,
-                            (const float*)B.F, n, p, B.J) != cudaSuccess)
-          c.rc = MM3D_ERR_CUDA;
-        mm3d_count_launches(1);
-      }
+    if ((p & 3) == 0 && c.training) {
+      // JoinTable is never materialised: BatchNorm reads the two column blocks [Y | F] directly
+      bn_fwd(c, post, B.Y, B.G, n, 2 * p, B.s_post, B.F, p);
     } else {
-      launch_copy_cols(c, B.Y, n, p, B.J, 2 * p, 0, p);
-      launch_copy_cols(c, B.F, n, p, B.J, 2 * p, p, p);
+      if ((p & 3) == 0) {
+        if (n && !c.rc) {
+          if (mm3d_launch_pdl(k_concat2, dim3(mm3d_grid(n * p / 2 + 1, 256)), dim3(256), 0, c.stream, (const float*)B.Y,
+                              (const float*)B.F, n, p, B.J) != cudaSuccess)
+            c.rc = MM3D_ERR_CUDA;
+          mm3d_count_launches(1);
+        }
+      } else {
+        launch_copy_cols(c, B.Y, n, p, B.J, 2 * p, 0, p);
+        launch_copy_cols(c, B.F, n, p, B.J, 2 * p, p, p);
+      }
+      bn_fwd(c, post, B.J, B.G, n, 2 * p, B.s_post);
     }
-    bn_fwd(c, post, B.J, B.G, n, 2 * p, B.s_post);
     conv_fwd(c, SMC, l, B.G, 2 * p, B.R, p, P(c, post + 4));
   }
 }
@@ -456,14 +465,19 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
     const int dn = pbase + 5, deeper = pbase + 10, up = deeper + level_slots(l + 1, net.L), post = up + 5;
     float* d_G = g.f(n, 2 * p);
     conv_bwd(c, SMC, l, B.G, 2 * p, d_R, p, P(c, post + 4), d_G, Gp(c, post + 4));
-    float* d_J = g.f(n, 2 * p);
-    bn_bwd(c, post, B.J, d_G, d_J, n, 2 * p, B.s_post);
+    const bool split = (p & 3) == 0 && c.training;  // as in the forward: [Y | F] was never concatenated
+    float* d_J = g.f(n, split ? p : 2 * p);         // split: only the skip half d_J[:, :p]
     float* d_F = g.f(n, p);
     float* d_Yskip = g.f(n, p);
-    // d_F = d_J[:, p:]; the skip half is combined with the branch gradient further down
-    if (n && !c.rc) {
-      if (mm3d_launch_pdl(k_copy_cols, dim3(mm3d_grid(n * p / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)d_J, n, 2 * p, d_F, p, 0, p, p) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
-      mm3d_count_launches(1);
+    if (split) {
+      bn_bwd(c, post, B.Y, d_G, d_J, n, 2 * p, B.s_post, B.F, p, d_F);
+    } else {
+      bn_bwd(c, post, B.J, d_G, d_J, n, 2 * p, B.s_post);
+      // d_F = d_J[:, p:]; the skip half is combined with the branch gradient further down
+      if (n && !c.rc) {
+        if (mm3d_launch_pdl(k_copy_cols, dim3(mm3d_grid(n * p / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)d_J, n, 2 * p, d_F, p, 0, p, p) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
+        mm3d_count_launches(1);
+      }
     }
     float* d_E = g.f(nc, q);
     conv_bwd(c, UP, l, B.E, q, d_F, p, P(c, up + 4), d_E, Gp(c, up + 4));
@@ -477,7 +491,7 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
     bn_bwd(c, dn, B.Y, d_B, d_Ybr, n, p, B.s_dn);
     // d_Y = d_J[:, :p] + d_Ybr
     if (n && !c.rc) {
-      if (mm3d_launch_pdl(k_split_add, dim3(mm3d_grid(n * p / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)d_J, (const float*)d_Ybr, n, p, d_Yskip, (float*)nullptr) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
+      if (mm3d_launch_pdl(k_split_add, dim3(mm3d_grid(n * p / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)d_J, split ? p : 2 * p, (const float*)d_Ybr, n, p, d_Yskip, (float*)nullptr) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
       mm3d_count_launches(1);
     }
     d_Y = d_Yskip;
