@@ -38,6 +38,13 @@ void mm3d_count_launches(int n);  // bookkeeping for mm3d_kernel_launches()
     }                                                                                \
   } while (0)
 
+// index of the current device for per-device one-time setup (function attributes are per device)
+static inline int mm3d_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  return dev;
+}
+
 static inline int64_t mm3d_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t mm3d_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 

@@ -144,7 +144,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1)
 k_conv_tc(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int S = p.S;
-  const int nthreads = (S + 5) * 32;
   // carve: [A stages][B stages][entry rows][barriers][tmem ptr][abort]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -196,7 +195,6 @@ k_conv_tc(const TcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  (void)nthreads;
 
   if (warp < S) {
     // =================================================================== gather producer: owns stage `warp`
@@ -446,7 +444,8 @@ int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, in
   if (S > kMaxStages) S = kMaxStages;
   p.S = S;
   size_t smem = 1024 + (size_t)S * per_stage + 8 * (2 * kMaxStages + 4) + 64;
-  static int regs = 0;
+  static int regs_dev[64] = {0};
+  int& regs = regs_dev[mm3d_device_slot()];
   if (!regs) {
     MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

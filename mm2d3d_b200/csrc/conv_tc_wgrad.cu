@@ -453,7 +453,8 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
                       (size_t)p.gbufs * (p.mw / 32) * kStageBytes + ((size_t)p.n_local * 8 + 15) / 16 * 16 +
                       8 * (2 * kMaxStages + 2 * kMaxGBufs + 1) + 64;
   MM3D_REQUIRE(smem <= 226 * 1024, MM3D_ERR_UNSUPPORTED, "tcgen05 wgrad: too many rows per CTA for the tile-mask cache");
-  static bool once = false;
+  static bool once_dev[64] = {false};
+  bool& once = once_dev[mm3d_device_slot()];
   if (!once) {
     MM3D_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     MM3D_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -342,7 +342,8 @@ extern "C" int mm3d_build_plans(const mm3d_plan_desc* descs, int n_plans, mm3d_s
   MM3D_REQUIRE(n_plans >= 0 && (n_plans == 0 || descs), MM3D_ERR_INVALID, "plans: bad descriptor array");
   unsigned int* counters = done_counters();
   MM3D_REQUIRE(counters, MM3D_ERR_CUDA, "plans: could not allocate the completion counters");
-  static bool once = false;
+  static bool once_dev[64] = {false};
+  bool& once = once_dev[mm3d_device_slot()];
   if (!once) {
     MM3D_CUDA(cudaFuncSetAttribute(k_build_plans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PlanSmem)));
     once = true;

@@ -99,11 +99,9 @@ class Metadata:
             main.wait_event(done)
             if plans:
                 # row plans of every table, before the host learns the row counts (launch sized by capacity)
-                specs = []
-                for i, s in enumerate(sizes):
-                    specs.append(("smc", s))
-                    if i + 1 < L:
-                        specs += [("down", s), ("up", s)]
+                # heaviest tables first (3^3: 27 offsets per row): the launch is ~1.6 waves of one-per-SM CTAs and the
+                # hardware hands out CTAs in index order, so the second wave should be the light ones
+                specs = [("smc", s) for s in sizes] + [("down", s) for s in sizes[:-1]] + [("up", s) for s in sizes[:-1]]
                 self.build_plans(specs)
             self._sync_counts()
 
