@@ -131,6 +131,19 @@ typedef struct mm3d_plan_desc {
 MM3D_API int mm3d_build_plans(const mm3d_plan_desc* descs_host, int n_plans, mm3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Points (metres) -> voxel coordinates: the reference's augment_and_scale_3d
+ * (lib/utils/augmentation_3d.py:83-158) + integer cast + receptive-field filter
+ * (lib/dataset/nuscenes_dataloader.py:312-327) for a collated batch.  points float32 [n,3]; sample_offsets
+ * int64 [B+1]; rot float32 [B,3,3] (applied as points.dot(rot)); transl_u float64 [B,3] uniform draws of the
+ * random translation or NULL (transl=False).  Outputs: coords int64 [n,4] (x,y,z,sample), keep uint8 [n]
+ * (inside [0, full_scale)^3), min_value float32 [B,3], offset float64 [B,3] -- what the reference returns.
+ * ---------------------------------------------------------------------------------------- */
+MM3D_API size_t mm3d_scale_points_workspace_bytes(int B);
+MM3D_API int mm3d_scale_points(const float* points, const int64_t* sample_offsets, int B, int64_t n, const float* rot,
+                      float scale, int full_scale, const double* transl_u, int64_t* coords, uint8_t* keep,
+                      float* min_value, double* offset, void* ws, size_t ws_bytes, mm3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * I/O layers (replace SCN InputLayer_updateOutput/updateGradInput, OutputLayer_*).
  * mode 4 = mean of a voxel's points, 3 = sum.
  * ---------------------------------------------------------------------------------------- */

@@ -41,6 +41,8 @@ SIGNATURES = {
     "mm3d_voxelize": (_i, [_p, _i64, _i, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mm3d_coarsen": (_i, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64, _p, _p, _sz, _p]),
     "mm3d_build_nbr27": (_i, [_p, _p, _i64, _i, _p, _p, _i64, _p, _i64, _p]),
+    "mm3d_scale_points_workspace_bytes": (_sz, [_i]),
+    "mm3d_scale_points": (_i, [_p, _p, _i, _i64, _p, _f, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mm3d_input_fwd": (_i, [_p, _p, _p, _i64, _i64, _i, _i, _p, _p]),
     "mm3d_input_bwd": (_i, [_p, _p, _p, _i64, _i, _i, _p, _p]),
     "mm3d_output_fwd": (_i, [_p, _p, _i64, _i, _p, _p]),

@@ -1,0 +1,68 @@
+"""Points (metres) -> SparseConvNet voxel coordinates on the GPU: the reference's ``augment_and_scale_3d``
+(``lib/utils/augmentation_3d.py:83-158``) with the integer cast and receptive-field filter that follow it in the
+data loaders (``lib/dataset/nuscenes_dataloader.py:312-327``), for a whole collated batch in one call.
+
+The random draws stay on the host and follow the reference's order on ``numpy.random`` exactly
+(:func:`draw_augmentation`); the data-dependent work -- rotation, scaling, per-sample min / max, translation,
+``astype(int64)``, the ``[0, full_scale)`` test -- is ``mm3d_scale_points`` (``csrc/augment.cu``).
+SURVEY.md section 8(f), row 1.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+
+def draw_augmentation(noisy_rot=0.0, flip_x=0.0, flip_y=0.0, rot_z=0.0, rot_y=0.0, transl=False, rng=np.random):
+    """The random part of ``augment_and_scale_3d``: returns ``(rot_matrix float32 [3,3], u float64 [3] or None)``.
+    Same calls, in the same order, on ``rng`` (default: the global ``numpy.random`` the reference uses), so a seeded
+    stream gives the reference's matrix and translation draws."""
+    rot = np.eye(3, dtype=np.float32)
+    if noisy_rot > 0 or flip_x > 0 or flip_y > 0 or rot_z > 0 or rot_y > 0:
+        if noisy_rot > 0:
+            rot += rng.randn(3, 3) * noisy_rot
+        if flip_x > 0:
+            rot[0][0] *= rng.randint(0, 2) * 2 - 1
+        if flip_y > 0:
+            rot[1][1] *= rng.randint(0, 2) * 2 - 1
+        if rot_z > 0:
+            theta = rng.rand() * rot_z
+            rot = rot.dot(np.array([[np.cos(theta), -np.sin(theta), 0], [np.sin(theta), np.cos(theta), 0], [0, 0, 1]],
+                                   dtype=np.float32))
+        if rot_y > 0:
+            theta = rng.rand() * rot_y
+            rot = rot.dot(np.array([[np.cos(theta), 0, np.sin(theta)], [0, 1, 0], [-np.sin(theta), 0, np.cos(theta)]],
+                                   dtype=np.float32))
+    u = rng.rand(3) if transl else None
+    return rot, u
+
+
+def scale_points(points: torch.Tensor, sample_offsets, rot, transl_u, scale: float, full_scale: int):
+    """``points`` float32 CUDA ``[N, 3]`` (samples concatenated), ``sample_offsets`` ``[B+1]`` row ranges, ``rot``
+    ``[B, 3, 3]`` float32 (identity = no augmentation), ``transl_u`` ``[B, 3]`` float64 uniform draws or ``None``.
+
+    Returns ``(coords int64 [N, 4] = (x, y, z, sample), keep bool [N], min_value float32 [B, 3], offset float64
+    [B, 3])``; ``coords[keep]`` is what the reference's collate hands to ``scn.InputLayer``."""
+    if not points.is_cuda:
+        raise RuntimeError("scale_points: expected a CUDA tensor -- mm2d3d_b200 has no CPU path")
+    dev = points.device
+    points = points.float().contiguous()
+    n = points.shape[0]
+    offs = torch.as_tensor(np.asarray(sample_offsets, dtype=np.int64)).to(dev)
+    B = offs.numel() - 1
+    rot_d = torch.as_tensor(np.ascontiguousarray(np.asarray(rot, dtype=np.float32).reshape(B, 9))).to(dev)
+    u_d = None if transl_u is None else torch.as_tensor(np.ascontiguousarray(np.asarray(transl_u, dtype=np.float64).reshape(B, 3))).to(dev)
+    coords = torch.empty(n, 4, dtype=torch.int64, device=dev)
+    keep = torch.empty(n, dtype=torch.uint8, device=dev)
+    min_value = torch.zeros(B, 3, dtype=torch.float32, device=dev)
+    offset = torch.zeros(B, 3, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        ws = torch.empty(lib.mm3d_scale_points_workspace_bytes(B), dtype=torch.uint8, device=dev)
+        check(lib.mm3d_scale_points(points.data_ptr(), offs.data_ptr(), B, n, rot_d.data_ptr(), float(scale), int(full_scale),
+                                    None if u_d is None else u_d.data_ptr(), coords.data_ptr(), keep.data_ptr(),
+                                    min_value.data_ptr(), offset.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()),
+              "mm3d_scale_points")
+    return coords, keep.bool(), min_value, offset

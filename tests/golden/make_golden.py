@@ -9,6 +9,8 @@ the lift fixture):  ``python tests/golden/make_golden.py``.
   oracle/__init__.py): a small UNetSCN (m=4, 4 planes, full_scale 64) forward + backward with
   seeded weights on a seeded 2-sample cloud: inputs, parameters, output, all gradients.
 * ``structure_small.npz`` -- oracle voxel ids / level coords / rule tables for a seeded cloud.
+* ``augment_ref.npz`` -- produced by the REFERENCE ITSELF: ``augment_and_scale_3d``
+  (``lib/utils/augmentation_3d.py``) + the loader's integer cast and range filter.
 """
 import importlib.util
 import os
@@ -116,10 +118,64 @@ def structure_small():
     np.savez_compressed(os.path.join(HERE, "structure_small.npz"), **blob)
 
 
+def augment_from_reference():
+    """``augment_ref.npz`` -- produced by the REFERENCE ITSELF: ``augment_and_scale_3d``
+    (``lib/utils/augmentation_3d.py:83-158``) is imported and run with a seeded ``numpy.random`` on three synthetic
+    sweeps with different settings, followed by the data loader's ``astype(int64)`` + range filter
+    (``nuscenes_dataloader.py:323-327``).  The random draws are replayed with ``mm2d3d_b200.augment.draw_augmentation``
+    on the same seed (asserted equal to what the reference returned)."""
+    from mm2d3d_b200 import synth
+    from mm2d3d_b200.augment import draw_augmentation
+    spec = importlib.util.spec_from_file_location("ref_aug", "/root/reference/lib/utils/augmentation_3d.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    settings = [
+        dict(),                                                                  # validation: no augmentation
+        dict(noisy_rot=0.1, flip_x=0.5, rot_z=6.2831, transl=True),              # nuScenes training settings
+        dict(noisy_rot=0.1, flip_y=0.5, rot_y=6.2831, transl=True),              # camera-coordinate variant
+    ]
+    scale, full_scale = 20, 4096
+    pts, offs, rots, us, coords, keeps, mins, offsets = [], [0], [], [], [], [], [], []
+    for i, kw in enumerate(settings):
+        p = synth.raycast_points("nuscenes", seed=40 + i)[::3].copy()
+        np.random.seed(100 + i)
+        c, min_value, offset, rot = ref.augment_and_scale_3d(p, scale, full_scale, **kw)
+        np.random.seed(100 + i)
+        rot2, u = draw_augmentation(**kw)
+        assert np.array_equal(rot, rot2) and rot.dtype == np.float32
+        ci = c.astype(np.int64)
+        idxs = (ci.min(1) >= 0) * (ci.max(1) < full_scale)
+        pts.append(p); offs.append(offs[-1] + p.shape[0]); rots.append(rot)
+        us.append(u if u is not None else np.zeros(3)); coords.append(ci); keeps.append(idxs)
+        mins.append(min_value.astype(np.float32)); offsets.append(np.asarray(offset, dtype=np.float64))
+    # the same sweeps through a receptive field they do not fit into (no translation): exercises the range filter
+    small = 1500
+    coords_s, keep_s = [], []
+    for i, kw in enumerate(settings):
+        kw = dict(kw, transl=False)
+        np.random.seed(100 + i)
+        c, _, _, rot = ref.augment_and_scale_3d(pts[i], scale, small, **kw)
+        assert np.array_equal(rot, rots[i])
+        ci = c.astype(np.int64)
+        coords_s.append(ci)
+        keep_s.append((ci.min(1) >= 0) * (ci.max(1) < small))
+    np.savez_compressed(os.path.join(HERE, "augment_ref.npz"), points=np.concatenate(pts), offsets=np.array(offs),
+                        small_full_scale=small, coords_small=np.concatenate(coords_s), keep_small=np.concatenate(keep_s),
+                        rot=np.stack(rots), u=np.stack(us), transl=np.array([bool(s.get("transl")) for s in settings]),
+                        coords=np.concatenate(coords), keep=np.concatenate(keeps), min_value=np.stack(mins),
+                        offset=np.stack(offsets), scale=scale, full_scale=full_scale)
+
+
 if __name__ == "__main__":
-    lift_from_reference()
-    unet_small()
-    structure_small()
+    only = sys.argv[1] if len(sys.argv) > 1 else None  # e.g. `make_golden.py augment` regenerates one fixture
+    if only in (None, "lift"):
+        lift_from_reference()
+    if only in (None, "unet"):
+        unet_small()
+    if only in (None, "structure"):
+        structure_small()
+    if only in (None, "augment"):
+        augment_from_reference()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

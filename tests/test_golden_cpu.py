@@ -51,3 +51,19 @@ def test_unet_small_fixture_reproduces():
     assert torch.allclose(out, torch.from_numpy(z["out"]), atol=1e-12)
     (gx,) = torch.autograd.grad(out, x, torch.from_numpy(z["grad_out"]))
     assert torch.allclose(gx, torch.from_numpy(z["grad_feats"]), atol=1e-12)
+
+
+def test_augment_oracle_matches_reference_fixture():
+    """augment_ref.npz was produced by the reference's own augment_and_scale_3d (make_golden.py)."""
+    from oracle import augment_oracle
+    z = np.load(os.path.join(G, "augment_ref.npz"))
+    offs = z["offsets"]
+    for i in range(len(offs) - 1):
+        p = z["points"][offs[i]:offs[i + 1]]
+        u = z["u"][i] if z["transl"][i] else None
+        ci, keep, mn, off = augment_oracle.scale_points(p, z["rot"][i], u, int(z["scale"]), int(z["full_scale"]))
+        assert np.array_equal(ci, z["coords"][offs[i]:offs[i + 1]]) and np.array_equal(keep, z["keep"][offs[i]:offs[i + 1]])
+        assert np.array_equal(mn, z["min_value"][i]) and np.array_equal(off, z["offset"][i])
+        ci, keep, _, _ = augment_oracle.scale_points(p, z["rot"][i], None, int(z["scale"]), int(z["small_full_scale"]))
+        assert np.array_equal(ci, z["coords_small"][offs[i]:offs[i + 1]])
+        assert np.array_equal(keep, z["keep_small"][offs[i]:offs[i + 1]]) and 0 < keep.mean() < 1

@@ -656,3 +656,39 @@ def test_fused_executor_matches_module_path(mode):
     net_a.eval(); net_b.eval()
     with torch.no_grad():
         assert rel_err(net_a([coords, feats]), net_b([coords, feats])) < tol
+
+
+# ------------------------------------------------------------------------------ points -> voxel coordinates
+def test_scale_points_reference_fixture():
+    """mm3d_scale_points against tests/golden/augment_ref.npz, which the reference's own augment_and_scale_3d +
+    integer cast + range filter produced (make_golden.py).  Integer work: min_value, the no-augmentation sample
+    and everything downstream of the rotation are bit-exact; the rotation itself is a float32 BLAS dot product in
+    the reference whose rounding numpy does not pin, so for augmented samples a coordinate may differ by one voxel
+    where the float value sits on an integer boundary -- at most 1e-4 of the points, never by more than 1."""
+    from mm2d3d_b200.augment import scale_points
+    z = np.load(os.path.join(G, "augment_ref.npz"))
+    pts = torch.from_numpy(z["points"]).to(DEV)
+    offs = z["offsets"]
+    u = z["u"] * z["transl"][:, None]  # samples without translation: zero draws = zero offset
+    for full_scale, want_c, want_k, transl_u in ((int(z["full_scale"]), z["coords"], z["keep"], u),
+                                                  (int(z["small_full_scale"]), z["coords_small"], z["keep_small"], None)):
+        coords, keep, mn, off = scale_points(pts, offs, z["rot"], transl_u, float(z["scale"]), full_scale)
+        coords, keep = coords.cpu().numpy(), keep.cpu().numpy()
+        assert np.array_equal(coords[:, 3], np.repeat(np.arange(len(offs) - 1), np.diff(offs)))
+        for i in range(len(offs) - 1):
+            sl = slice(offs[i], offs[i + 1])
+            d = np.abs(coords[sl, :3] - want_c[sl])
+            identity = np.array_equal(z["rot"][i], np.eye(3, dtype=np.float32))
+            if identity:
+                assert d.max() == 0 and np.array_equal(keep[sl], want_k[sl])
+                assert np.array_equal(mn[i].cpu().numpy(), z["min_value"][i])
+            else:
+                assert d.max() <= 1 and (d > 0).any(1).mean() <= 1e-4, (i, d.max(), (d > 0).any(1).mean())
+                assert (keep[sl] != want_k[sl]).mean() <= 1e-4
+                assert np.allclose(mn[i].cpu().numpy(), z["min_value"][i], rtol=1e-6, atol=1e-3)
+            if transl_u is not None:
+                assert np.allclose(off[i].cpu().numpy(), z["offset"][i], rtol=1e-6, atol=1e-3)
+    # the filtered coordinates feed InputLayer directly
+    meta = _meta(coords[keep], 4096, 2)
+    ref = O.Metadata(coords[keep], 4096)
+    assert np.array_equal(meta.p2v().cpu().numpy(), ref.p2v)
