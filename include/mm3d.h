@@ -203,6 +203,14 @@ MM3D_API int mm3d_lift2d_fwd(const void* fmap, int dtype, int B, int C, int H, i
 MM3D_API int mm3d_lift2d_bwd(const void* d_out, int dtype, int B, int C, int H, int W, const int64_t* idx,
                     const int64_t* sample_offsets, int64_t n, void* d_fmap, mm3d_stream_t stream);
 
+/* Point values -> image (the loaders' sparse depth and 2D label maps, lib/dataset/nuscenes_dataloader.py:275-278):
+ * out[b, idx[i,0], idx[i,1]] = vals[i] over a map pre-filled with `fill`; where several points share a pixel the
+ * last one wins, like numpy's indexed assignment.  idx int64 [n,2] (row, col), sample_offsets int64 [B+1],
+ * out float32 [B,H,W]; ws: mm3d_raster2d_workspace_bytes. */
+MM3D_API size_t mm3d_raster2d_workspace_bytes(int B, int H, int W);
+MM3D_API int mm3d_raster2d(const int64_t* idx, const int64_t* sample_offsets, int B, int H, int W, int64_t n,
+                  const float* vals, float fill, float* out, void* ws, size_t ws_bytes, mm3d_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Whole-network executor: UNetSCN (3d_net/scn_unet.py:90-126, VGG blocks, block_reps == 1) forward and
  * backward as one call each -- the same kernels as above, driven natively instead of from ~110

@@ -212,3 +212,73 @@ extern "C" int mm3d_lift2d_bwd(const void* d_out, int dtype, int B, int C, int H
   MM3D_CHECK_LAUNCH("mm3d_lift2d_bwd");
   return MM3D_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Point values -> image: the loaders' sparse depth / 2D label maps
+//     depth = zeros(H, W); depth[idx[:,0], idx[:,1]] = z            (lib/dataset/nuscenes_dataloader.py:275-278)
+// numpy assigns repeated indices in order, so the LAST point of a pixel wins: pass 1 records the largest
+// point index per pixel (atomicMax), pass 2 writes that point's value -- deterministic, same result.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void k_raster_fill(float* __restrict__ out, int32_t* __restrict__ winner, int64_t total, float fill) {
+  mm3d_griddep_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    out[i] = fill;
+    winner[i] = -1;
+  }
+}
+
+__device__ __forceinline__ int64_t raster_pixel(const int64_t* __restrict__ idx, const int64_t* __restrict__ offs, int B,
+                                                int H, int W, int64_t i) {
+  int lo = 0, hi = B - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(offs + mid) <= i) lo = mid; else hi = mid - 1;
+  }
+  const int64_t r = __ldg(idx + 2 * i), c = __ldg(idx + 2 * i + 1);
+  if ((uint64_t)r >= (uint64_t)H || (uint64_t)c >= (uint64_t)W) return -1;
+  return ((int64_t)lo * H + r) * W + c;
+}
+
+__global__ void k_raster_winner(const int64_t* __restrict__ idx, const int64_t* __restrict__ offs, int B, int H, int W,
+                                int64_t n, int32_t* __restrict__ winner) {
+  mm3d_griddep_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t px = raster_pixel(idx, offs, B, H, W, i);
+    if (px >= 0) atomicMax(winner + px, (int32_t)i);
+  }
+}
+
+__global__ void k_raster_write(const int64_t* __restrict__ idx, const int64_t* __restrict__ offs, int B, int H, int W,
+                               int64_t n, const float* __restrict__ vals, const int32_t* __restrict__ winner,
+                               float* __restrict__ out) {
+  mm3d_griddep_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t px = raster_pixel(idx, offs, B, H, W, i);
+    if (px >= 0 && winner[px] == (int32_t)i) out[px] = __ldg(vals + i);
+  }
+}
+
+}  // namespace
+
+extern "C" size_t mm3d_raster2d_workspace_bytes(int B, int H, int W) { return mm3d_align(sizeof(int32_t) * (size_t)B * H * W); }
+
+extern "C" int mm3d_raster2d(const int64_t* idx, const int64_t* sample_offsets, int B, int H, int W, int64_t n,
+                             const float* vals, float fill, float* out, void* ws, size_t ws_bytes, mm3d_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MM3D_REQUIRE(B > 0 && H > 0 && W > 0 && n >= 0 && n < (1ll << 31), MM3D_ERR_INVALID, "raster2d: bad sizes");
+  MM3D_REQUIRE(out && ws && ws_bytes >= mm3d_raster2d_workspace_bytes(B, H, W), MM3D_ERR_WORKSPACE, "raster2d: workspace too small");
+  const int64_t total = (int64_t)B * H * W;
+  int32_t* winner = (int32_t*)ws;
+  MM3D_CUDA(mm3d_launch_pdl(k_raster_fill, dim3(mm3d_grid(total, 256)), dim3(256), 0, stream, out, winner, total, fill));
+  if (n > 0) {
+    MM3D_REQUIRE(idx && sample_offsets && vals, MM3D_ERR_INVALID, "raster2d: null pointer");
+    MM3D_CUDA(mm3d_launch_pdl(k_raster_winner, dim3(mm3d_grid(n, 256)), dim3(256), 0, stream, idx, sample_offsets, B, H, W, n, winner));
+    MM3D_CUDA(mm3d_launch_pdl(k_raster_write, dim3(mm3d_grid(n, 256)), dim3(256), 0, stream, idx, sample_offsets, B, H, W, n, vals,
+                              (const int32_t*)winner, out));
+  }
+  mm3d_count_launches(n > 0 ? 3 : 1);
+  MM3D_CHECK_LAUNCH("mm3d_raster2d");
+  return MM3D_OK;
+}

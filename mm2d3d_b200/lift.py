@@ -48,3 +48,32 @@ def lift2d(fmap: torch.Tensor, img_indices) -> torch.Tensor:
     if len(img_indices.counts) != fmap.shape[0]:
         raise ValueError("lift2d: one index array per sample expected")
     return Lift2DFn.apply(fmap, img_indices.idx, img_indices.offsets)
+
+
+def rasterize_points(img_indices, values, height: int, width: int, fill: float = 0.0) -> torch.Tensor:
+    """Per-point values -> ``[B, H, W]`` float32 maps pre-filled with ``fill``.
+
+    The loaders' sparse depth map and 2D label map (``lib/dataset/nuscenes_dataloader.py:275-278`` and
+    ``:287-292``)::
+
+        depth = np.zeros((H, W));             depth[idx[:, 0], idx[:, 1]] = pts_cam_coord[:, 2]
+        seg_labels_2d = np.ones((H, W)) * -100;  seg_labels_2d[idx[:, 0], idx[:, 1]] = seg_label
+
+    Where several points fall on one pixel the last one wins, as numpy's indexed assignment does.
+    ``values``: float32 CUDA tensor ``[sum N_i]`` in the order of the concatenated index arrays.
+    """
+    if not values.is_cuda:
+        raise RuntimeError("rasterize_points: CUDA tensor expected (there is no CPU path)")
+    if not isinstance(img_indices, LiftIndices):
+        img_indices = LiftIndices(img_indices, values.device)
+    B = len(img_indices.counts)
+    vals = values.detach().to(torch.float32).contiguous().reshape(-1)
+    if vals.numel() != img_indices.n:
+        raise ValueError("rasterize_points: one value per point expected")
+    out = torch.empty((B, int(height), int(width)), dtype=torch.float32, device=values.device)
+    ws_bytes = _lib.lib.mm3d_raster2d_workspace_bytes(B, int(height), int(width))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=values.device)
+    _lib.check(_lib.lib.mm3d_raster2d(_lib.ptr(img_indices.idx), _lib.ptr(img_indices.offsets), B, int(height), int(width),
+                                      img_indices.n, _lib.ptr(vals), float(fill), _lib.ptr(out), _lib.ptr(ws), ws_bytes,
+                                      _lib.stream_ptr()), "mm3d_raster2d")
+    return out

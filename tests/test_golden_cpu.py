@@ -67,3 +67,18 @@ def test_augment_oracle_matches_reference_fixture():
         ci, keep, _, _ = augment_oracle.scale_points(p, z["rot"][i], None, int(z["scale"]), int(z["small_full_scale"]))
         assert np.array_equal(ci, z["coords_small"][offs[i]:offs[i + 1]])
         assert np.array_equal(keep, z["keep_small"][offs[i]:offs[i + 1]]) and 0 < keep.mean() < 1
+
+
+def test_raster_oracle_last_point_wins():
+    """The duplicate-pixel rule the CUDA rasteriser has to reproduce (nuscenes_dataloader.py:274-278)."""
+    from oracle import raster_oracle
+    idx = np.array([[1, 2], [0, 0], [1, 2], [3, 1], [1, 2]], dtype=np.int64)
+    vals = np.array([5.0, 7.0, 6.0, 8.0, 9.0], dtype=np.float32)
+    m = raster_oracle.rasterize(idx, vals, 4, 3, -100.0)
+    assert m[1, 2] == 9.0 and m[0, 0] == 7.0 and m[3, 1] == 8.0
+    assert (m == -100.0).sum() == 4 * 3 - 3
+    fidx, (fm,) = raster_oracle.fliplr(idx, [m], 3)
+    assert np.array_equal(raster_oracle.rasterize(fidx, vals, 4, 3, -100.0), fm)
+    img = np.arange(3 * 4 * 3, dtype=np.float32).reshape(3, 4, 3)
+    f = raster_oracle.rgb_feats(img, idx)
+    assert f.shape == (5, 3) and np.array_equal(f[0], img[:, 1, 2])

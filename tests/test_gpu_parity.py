@@ -692,3 +692,33 @@ def test_scale_points_reference_fixture():
     meta = _meta(coords[keep], 4096, 2)
     ref = O.Metadata(coords[keep], 4096)
     assert np.array_equal(meta.p2v().cpu().numpy(), ref.p2v)
+
+
+@pytest.mark.parametrize("sizes", [[4000, 3000], [0, 17], [1], [20000, 20000, 1, 0]])
+def test_rasterize_points_matches_numpy_assignment(sizes):
+    """Sparse depth / 2D label maps (nuscenes_dataloader.py:274-278): bit-exact, including which of several points on one
+    pixel wins, and consistent with the loaders' horizontal flip; RGB point features (:364-367) through lift2d."""
+    from mm2d3d_b200.lift import LiftIndices, lift2d, rasterize_points
+    from oracle import raster_oracle
+    rng = np.random.default_rng(5)
+    H, W = 45, 80                                  # small map -> many duplicate pixels
+    idx = [np.stack([rng.integers(0, H, n), rng.integers(0, W, n)], 1).astype(np.int64) for n in sizes]
+    depth = [rng.uniform(0.5, 60.0, n).astype(np.float32) for n in sizes]
+    label = [rng.integers(0, 10, n).astype(np.float32) for n in sizes]
+    li = LiftIndices(idx, DEV)
+    d = rasterize_points(li, torch.from_numpy(np.concatenate(depth)).to(DEV), H, W, 0.0).cpu().numpy()
+    l = rasterize_points(li, torch.from_numpy(np.concatenate(label)).to(DEV), H, W, -100.0).cpu().numpy()
+    for b in range(len(sizes)):
+        want_d = raster_oracle.rasterize(idx[b], depth[b], H, W, 0.0)
+        want_l = raster_oracle.rasterize(idx[b], label[b], H, W, -100.0)
+        assert np.array_equal(d[b], want_d.astype(np.float32))
+        assert np.array_equal(l[b], want_l.astype(np.float32))
+    # flip: rasterising the flipped indices equals flipping the maps
+    fl = [raster_oracle.fliplr(ix, [], W)[0] for ix in idx]
+    d_f = rasterize_points(fl, torch.from_numpy(np.concatenate(depth)).to(DEV), H, W, 0.0).cpu().numpy()
+    assert np.array_equal(d_f, d[:, :, ::-1])
+    # RGB features of the points = the lift of the image
+    img = rng.random((len(sizes), 3, H, W)).astype(np.float32)
+    got = lift2d(torch.from_numpy(img).to(DEV), li).cpu().numpy()
+    want = np.concatenate([raster_oracle.rgb_feats(img[b], idx[b]) for b in range(len(sizes))], 0)
+    assert np.array_equal(got, want)
