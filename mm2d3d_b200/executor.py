@@ -158,14 +158,58 @@ class UNetSCNFn(torch.autograd.Function):
         return (d_feats, None, None, *grads)
 
 
+class PreparedScans:
+    """Sparse structure of one batch (voxels, rule tables, row plans), built ahead of the forward that uses it --
+    typically on a side stream while the previous step still computes, the way a prefetching data loader prepares
+    the next batch.  Pass it to ``UNetSCN.forward`` in place of the coordinate tensor."""
+
+    __slots__ = ("meta", "event", "stream", "mode", "spatial0", "levels")
+
+    def __init__(self, meta, mode, spatial0, levels):
+        self.meta, self.mode, self.spatial0, self.levels = meta, mode, spatial0, levels
+        self.stream = torch.cuda.current_stream(meta.device)
+        self.event = torch.cuda.Event()
+        self.event.record(self.stream)
+
+    @property
+    def n_points(self):
+        return self.meta.n_points
+
+
+def prepare(net, coords, wait=False):
+    """Enqueue the structure build for ``coords`` ([N, 4] int64: x, y, z, batch) on the CURRENT stream and return a
+    :class:`PreparedScans`.  Nothing blocks here unless ``wait``: the one host synchronisation of a build (reading
+    the row counts) is deferred to the forward that uses the structure, by which time a build enqueued one step
+    ahead has long finished."""
+    if not isinstance(coords, torch.Tensor) or not coords.is_cuda:
+        raise RuntimeError("UNetSCN.prepare: coordinates must be a CUDA tensor -- mm2d3d_b200 has no CPU path")
+    spatial0 = int(net.layer1.spatial_size[0])
+    L = net._num_planes
+    with torch.cuda.device(coords.device):
+        meta = Metadata(coords, spatial0, L, plans=F.DEFAULT_MODE != "fp32", defer_sync=not wait)
+        return PreparedScans(meta, F.DEFAULT_MODE, spatial0, L)
+
+
 def run(net, coords, feats):
     if not feats.is_cuda:
         raise RuntimeError("UNetSCN: features must be a CUDA tensor -- mm2d3d_b200 has no CPU path")
-    if coords.device != feats.device:
-        coords = coords.to(feats.device, non_blocking=True)
     spatial0 = int(net.layer1.spatial_size[0])
     L = net._num_planes
-    meta = Metadata(coords, spatial0, L, plans=F.DEFAULT_MODE != "fp32")
+    if isinstance(coords, PreparedScans):
+        prep = coords
+        if (prep.mode, prep.spatial0, prep.levels) != (F.DEFAULT_MODE, spatial0, L) or prep.meta.device != feats.device:
+            raise ValueError("UNetSCN: the prepared structure was built for another network, device or convolution mode")
+        meta = prep.meta.finish()
+        cur = torch.cuda.current_stream(feats.device)
+        if cur != prep.stream:
+            cur.wait_event(prep.event)
+            meta.record_stream(cur)
+    else:
+        if coords.device != feats.device:
+            coords = coords.to(feats.device, non_blocking=True)
+        meta = Metadata(coords, spatial0, L, plans=F.DEFAULT_MODE != "fp32")
+    if feats.shape[0] < meta.n_points:
+        raise ValueError(f"UNetSCN: {feats.shape[0]} feature rows for {meta.n_points} points")
     bn0 = net.layer4
     cfg = (net.in_channels, net.out_channels, L, _lib.MODES[F.DEFAULT_MODE], bool(net.training), float(bn0.eps),
            float(bn0.momentum), spatial0)

@@ -40,13 +40,18 @@ class Metadata:
 
     _side = {}  # per-device side stream for the neighbour tables
 
-    def __init__(self, coords: torch.Tensor, spatial_size: int, prebuild_levels: int = 1, plans: bool = False):
+    def __init__(self, coords: torch.Tensor, spatial_size: int, prebuild_levels: int = 1, plans: bool = False,
+                 defer_sync: bool = False):
+        """``defer_sync``: enqueue the build and an asynchronous read-back of the row counts, but do not wait for
+        them; :meth:`finish` (called by every accessor that needs a row count) does.  Lets a caller enqueue a build
+        on a side stream and keep launching other work."""
         if coords.dim() != 2 or coords.shape[1] != 4:
             raise ValueError("coords must be [N, 4] = (x, y, z, batch)")
         if not coords.is_cuda:
             coords = coords.cuda(non_blocking=True)
         coords = coords.to(torch.int64).contiguous()
         self.device = coords.device
+        self._pending = None
         self.n_points = int(coords.shape[0])
         self.spatial_size0 = int(spatial_size)
         self.levels: dict[int, Level] = {}
@@ -103,7 +108,14 @@ class Metadata:
                 # hardware hands out CTAs in index order, so the second wave should be the light ones
                 specs = [("smc", s) for s in sizes] + [("down", s) for s in sizes[:-1]] + [("up", s) for s in sizes[:-1]]
                 self.build_plans(specs)
-            self._sync_counts()
+            if defer_sync:
+                host = torch.empty(self.MAX_LEVELS + 1, dtype=torch.int32, pin_memory=True)
+                host.copy_(self._counts, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                self._pending = (host, ev)
+            else:
+                self._sync_counts()
 
     # ------------------------------------------------------------------ construction helpers
     @staticmethod
@@ -148,19 +160,43 @@ class Metadata:
                                self._ws[0], self._ws[1], stream), "mm3d_coarsen")
         fine.has_down = True
 
-    def _sync_counts(self):
-        host = self._counts.cpu()  # the one host synchronisation of a build
+    def finish(self):
+        """Wait for a deferred build's row counts (no-op otherwise)."""
+        if self._pending is not None:
+            host, ev = self._pending
+            self._pending = None
+            ev.synchronize()
+            self._sync_counts(host)
+        return self
+
+    def _sync_counts(self, host=None):
+        if host is None:
+            host = self._counts.cpu()  # the one host synchronisation of a build
         if int(host[self.MAX_LEVELS]) & _lib.STATUS_BAD_COORD:
             raise ValueError("InputLayer: coordinates must lie in [0, spatial_size) and batch index in [0, 32768)")
         for lv in self._order:
             if lv.n is None:
                 lv.n = int(host[lv.count_slot])
 
+    def record_stream(self, stream):
+        """Tell the caching allocator that ``stream`` uses this structure's buffers (needed when the structure
+        was built on another stream than the one the network runs on, see ``UNetSCN.prepare``)."""
+        seen = set()
+        bufs = [self._buf, self._counts] + [lv.buf for lv in self._order]
+        bufs += [pl[0] for lv in self._order for pl in lv.plans.values()]
+        for b in bufs:
+            key = b.untyped_storage().data_ptr()
+            if key not in seen:
+                seen.add(key)
+                b.record_stream(stream)
+
     # ------------------------------------------------------------------ lookups used by the layers
     def level(self, spatial_size: int) -> Level:
+        self.finish()
         return self.levels[int(spatial_size)]
 
     def nbr(self, spatial_size: int) -> Level:
+        self.finish()
         lv = self.levels[int(spatial_size)]
         if not lv.has_nbr:
             with torch.cuda.device(self.device):
@@ -170,6 +206,7 @@ class Metadata:
     def down(self, spatial_size: int):
         """(fine level, coarse level) of the 2/2 convolution from ``spatial_size``; built lazily
         (one extra host sync) when it was not part of the pre-built pyramid."""
+        self.finish()
         s = int(spatial_size)
         fine = self.levels[s]
         if not fine.has_down:
@@ -266,6 +303,7 @@ class Metadata:
 
     @property
     def n_voxels(self):
+        self.finish()
         return self._order[0].n
 
     def _view(self, buf, byte_off, dtype, numel):
@@ -284,7 +322,7 @@ class Metadata:
 
     def coords_at(self, spatial_size) -> torch.Tensor:
         """int64 [n, 4] (x, y, z, batch) of the level's rows, decoded from the keys."""
-        lv = self.levels[int(spatial_size)]
+        lv = self.level(spatial_size)
         k = self._lv_view(lv, lv.o_keys, torch.int64, lv.n)
         return torch.stack([(k >> 32) & 0xFFFF, (k >> 16) & 0xFFFF, k & 0xFFFF, k >> 48], 1)
 

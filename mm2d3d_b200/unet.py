@@ -96,6 +96,14 @@ class UNetSCN(nn.Module):
         self.layer4 = scn.BatchNormReLU(m)
         self.layer5 = scn.OutputLayer(DIMENSION)
 
+    def prepare(self, coords, wait=False):
+        """Enqueue the sparse-structure build of a batch ahead of time on the current stream (see
+        ``executor.PreparedScans``); ``forward([prepared, feats])`` then skips the structure build."""
+        from . import executor
+        if not (self.fused and self._native and executor.fusable(self)):
+            raise RuntimeError("UNetSCN.prepare needs the fused executor (native backend, fused=True)")
+        return executor.prepare(self, coords, wait)
+
     def forward(self, x):
         if self.fused and self._native:
             from . import executor

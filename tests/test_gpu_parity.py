@@ -722,3 +722,65 @@ def test_rasterize_points_matches_numpy_assignment(sizes):
     got = lift2d(torch.from_numpy(img).to(DEV), li).cpu().numpy()
     want = np.concatenate([raster_oracle.rgb_feats(img[b], idx[b]) for b in range(len(sizes))], 0)
     assert np.array_equal(got, want)
+
+
+def test_prepared_structure_on_side_stream_matches_inline():
+    """UNetSCN.prepare(): structure built one step ahead on another stream gives the same bits as the inline build,
+    over several steps with rotating batches (exercises allocator reuse across the two streams)."""
+    from mm2d3d_b200.unet import UNetSCN
+    from mm2d3d_b200 import scn as scn_mod
+    torch.manual_seed(3)
+    net = UNetSCN(in_channels=3, m=16, num_planes=4, full_scale=256).to(DEV)
+    batches = []
+    for r in range(3):
+        locs, feats = synth.make_batch("nuscenes", batch=2, seed0=40 + 2 * r)
+        locs[:, :3] //= 16
+        # one point per voxel: the Input/OutputLayer sums over duplicate points are float atomics (order-dependent
+        # rounding, which TF32 rounding and ReLU gates amplify); without duplicates the TF32 data path is bit-reproducible
+        locs, first = np.unique(locs, axis=0, return_index=True)
+        batches.append((torch.from_numpy(locs).to(DEV), torch.from_numpy(feats[first]).to(DEV)))
+    for mode in ("tf32", "fp32"):
+        scn_mod.set_conv_mode(mode)
+        try:
+            def run(prep_of):
+                outs = []
+                for i in range(7):
+                    locs, feats = batches[i % 3]
+                    x = feats.clone().requires_grad_(True)
+                    net.zero_grad(set_to_none=True)
+                    out = net([prep_of(i, locs), x])
+                    out.square().sum().backward()
+                    outs.append((out.detach().clone(), x.grad.clone(), net.layer2.weight.grad.clone()))
+                torch.cuda.synchronize()
+                return outs
+
+            inline = run(lambda i, locs: locs)
+            side = torch.cuda.Stream(device=DEV, priority=-1)
+            ahead = {}
+
+            def prep_of(i, locs):
+                if i not in ahead:
+                    with torch.cuda.stream(side):
+                        ahead[i] = net.prepare(locs)
+                cur = ahead.pop(i)
+                with torch.cuda.stream(side):  # next step's structure while this one is being enqueued
+                    ahead[i + 1] = net.prepare(batches[(i + 1) % 3][0])
+                return cur
+
+            piped = run(prep_of)
+            for step, ((a, b, c), (d, e, f)) in enumerate(zip(inline, piped)):
+                if mode == "tf32":
+                    # forward and d_feats have no atomics in this mode: identical bits
+                    assert torch.equal(a, d) and torch.equal(b, e), (mode, step)
+                    assert float((c - f).abs().max()) <= 1e-5 * float(c.abs().max()), (mode, step)
+                else:
+                    # the FP32 kernels accumulate with atomics (order-dependent rounding, amplified by ReLU gates)
+                    assert float((a - d).abs().max()) <= 1e-4 * float(a.abs().max()), (mode, step)
+                    assert float((b - e).abs().max()) <= 5e-3 * float(b.abs().max()), (mode, step)
+                    assert float((c - f).abs().max()) <= 5e-3 * float(c.abs().max()), (mode, step)
+            stale = ahead.popitem()[1]
+            scn_mod.set_conv_mode("tf32" if mode == "fp32" else "fp32")
+            with pytest.raises(ValueError):  # a structure prepared for another convolution mode is refused
+                net([stale, batches[1][1]])
+        finally:
+            scn_mod.set_conv_mode("fp32")
