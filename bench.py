@@ -489,6 +489,9 @@ def run_ours(args):
         if not args.no_kernel_pass:
             roofline, rows = kernel_pass(net, resident[0][0], resident[0][1], args.mode, pk)
             roofline["share_of_step"] = roofline["conv_total_ms"] / (ms / args.steps)
+            roofline["share_note"] = ("conv_total_ms sums launches timed one by one with a cold L2; inside a step the weight-"
+                                      "gradient kernels run on a second stream beside dgrad/BatchNorm and the caches are warm, "
+                                      "so the sum can exceed the step time")
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             with open(os.path.join(ROOT, "gpurun_out", f"kernel_pass_{args.mode}.json"), "w") as f:
                 json.dump(rows, f, indent=0)
