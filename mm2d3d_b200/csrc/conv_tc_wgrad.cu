@@ -17,6 +17,7 @@
 //
 // Warp roles (S+7 warps): 0..S-1 gather producers (warp w owns ring stage w), S..S+3 epilogue
 // (TMEM -> atomics), S+4 MMA issuer + TMEM allocator, S+5 / S+6 dout-tile loaders (64 rows each).
+#include <cstdlib>
 #include "plan.cuh"
 #include "tc_common.cuh"
 
@@ -444,15 +445,11 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
   // on tiles per CTA (size of the shared-memory tile list): every group gets >= ceil(num_tiles / n_local) CTAs
   int total_ctas = MM3D_NUM_SMS;
   if (total_ctas < groups) total_ctas = groups;
-  {
-    int per_group_min = total_ctas / groups / 3;
-    if (per_group_min < 1) per_group_min = 1;
-    p.n_local = (p.num_tiles + per_group_min - 1) / per_group_min;
-  }
-  const size_t smem = 1024 + (size_t)p.S * kStageBytes + (size_t)(p.S + 1) * kEntBytes +
-                      (size_t)p.gbufs * (p.mw / 32) * kStageBytes + ((size_t)p.n_local * 8 + 15) / 16 * 16 +
-                      8 * (2 * kMaxStages + 2 * kMaxGBufs + 1) + 64;
-  MM3D_REQUIRE(smem <= 226 * 1024, MM3D_ERR_UNSUPPORTED, "tcgen05 wgrad: too many rows per CTA for the tile-mask cache");
+  int per_group_min = total_ctas / groups / 3;
+  if (per_group_min < 1) per_group_min = 1;
+  const size_t smem_fixed = 1024 + (size_t)p.S * kStageBytes + (size_t)(p.S + 1) * kEntBytes +
+                            (size_t)p.gbufs * (p.mw / 32) * kStageBytes + 8 * (2 * kMaxStages + 2 * kMaxGBufs + 1) + 64;
+  MM3D_REQUIRE(smem_fixed + 1024 <= 226 * 1024, MM3D_ERR_UNSUPPORTED, "tcgen05 wgrad: shared memory budget exceeded");
   static bool once_dev[64] = {false};
   bool& once = once_dev[mm3d_device_slot()];
   if (!once) {
@@ -460,8 +457,25 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
     MM3D_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     once = true;
   }
-  MM3D_CUDA(mm3d_launch_pdl(k_wgrad_tc, dim3((unsigned)total_ctas), dim3((p.S + 7) * 32), smem, stream, p));
-  mm3d_count_launches(1);
+  // The kernel keeps the list of a CTA's tiles (index + mask, 8 bytes each) in shared memory.  Row counts whose list
+  // does not fit next to the stages are processed in several launches over consecutive pieces of the plan's tile
+  // order (the kernel only ever adds into d_weight, so the pieces simply accumulate).
+  int64_t max_local = (int64_t)((226 * 1024 - smem_fixed) / 8) & ~(int64_t)1;
+  if (const char* e = getenv("MM3D_WGRAD_MAX_LOCAL")) {  // tests: force the multi-launch path at small sizes
+    const int64_t v = atoll(e);
+    if (v >= 2 && v < max_local) max_local = v & ~(int64_t)1;
+  }
+  const int64_t max_tiles = max_local * per_group_min;
+  const int all_tiles = p.num_tiles;
+  for (int64_t start = 0; start < all_tiles; start += max_tiles) {
+    const int cnt = (int)(all_tiles - start < max_tiles ? all_tiles - start : max_tiles);
+    p.order = pv.order + start;
+    p.num_tiles = cnt;
+    p.n_local = (cnt + per_group_min - 1) / per_group_min;
+    const size_t smem = smem_fixed + ((size_t)p.n_local * 8 + 15) / 16 * 16;
+    MM3D_CUDA(mm3d_launch_pdl(k_wgrad_tc, dim3((unsigned)total_ctas), dim3((p.S + 7) * 32), smem, stream, p));
+    mm3d_count_launches(1);
+  }
   MM3D_CHECK_LAUNCH("mm3d_conv_wgrad_tc");
   return MM3D_OK;
 }

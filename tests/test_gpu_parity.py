@@ -784,3 +784,37 @@ def test_prepared_structure_on_side_stream_matches_inline():
                 net([stale, batches[1][1]])
         finally:
             scn_mod.set_conv_mode("fp32")
+
+
+def test_tf32_wgrad_in_several_launches(monkeypatch):
+    """Row counts whose per-CTA tile list does not fit in shared memory are processed in several launches over
+    pieces of the plan's tile order (happens from ~300 k rows at 192 channels); forced here at 20 k rows."""
+    from mm2d3d_b200 import _lib
+    from mm2d3d_b200 import functional as F
+    from mm2d3d_b200.metadata import Metadata
+    locs, _ = synth.make_batch("nuscenes", batch=1, seed0=3)
+    meta = Metadata(torch.from_numpy(locs).to(DEV), 4096, 1, plans=True)
+    t, _, _ = F.conv_tables(meta, "smc", 4096, plans=True)
+    n, ci, co = t.n_out, 32, 48
+    torch.manual_seed(1)
+    x, dout = torch.randn(n, ci, device=DEV), torch.randn(n, co, device=DEV)
+    lib, sp = _lib.lib, _lib.stream_ptr()
+
+    def wgrad(mode):
+        dw = torch.empty(27, 1, ci, co, device=DEV)
+        m = _lib.MODES[mode]
+        plan, cap = (t.plan, t.plan_cap) if mode == "tf32" else (None, 0)
+        _lib.check(lib.mm3d_conv_wgrad(x.data_ptr(), n, ci, dout.data_ptr(), n, co, dw.data_ptr(), 27, t.tbl, t.stride, None,
+                                       plan, cap, 0, m, None, 0, sp))
+        torch.cuda.synchronize()
+        return dw
+
+    ref = wgrad("fp32")
+    one = wgrad("tf32")
+    monkeypatch.setenv("MM3D_WGRAD_MAX_LOCAL", "4")
+    many = wgrad("tf32")
+    assert lib.mm3d_take_device_error() == 0
+    scale = float(ref.abs().max())
+    assert float((one - ref).abs().max()) < 1e-2 * scale
+    assert float((many - ref).abs().max()) < 1e-2 * scale
+    assert float((many - one).abs().max()) < 1e-5 * scale  # same products, different accumulation order
