@@ -475,7 +475,7 @@ def run_ours(args):
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     pending.clear()
-    if acc != acc:
+    if acc != acc and not os.environ.get("MM3D_ABL_SKIP"):  # (timing experiments with kernels switched off produce garbage)
         raise SystemExit("bench.py: the end-to-end loop produced NaN")
 
     if world > 1:

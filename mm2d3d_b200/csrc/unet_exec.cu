@@ -18,6 +18,7 @@
 //   up.w post_bn{4} post.w] | head_bn{4}
 #include <stdlib.h>
 
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -249,6 +250,13 @@ cudaStream_t wgrad_stream(Ctx& c) {
   return c.side->stream;
 }
 
+// Timing experiments only (results are garbage, never set in tests or by the bench): MM3D_ABL_SKIP lists kernel
+// families the executor does not launch -- any of "bn", "wgrad", "conv" (forward + dgrad).
+bool abl_skip(const char* what) {
+  static const char* e = getenv("MM3D_ABL_SKIP");
+  return e && strstr(e, what) != nullptr;
+}
+
 #define EX(call)                   \
   do {                             \
     if (c.rc == 0) c.rc = (call);  \
@@ -261,11 +269,13 @@ float* Gp(Ctx& c, int i) { return (float*)c.grads[i]; }
 // materialising the concatenation (training mode only)
 void bn_fwd(Ctx& c, int pidx, const float* x, float* y, int64_t n, int ch, float* save, const float* x_hi = nullptr,
             int c_lo = 0) {
+  if (abl_skip("bn")) return;
   EX(mm3d_bnrelu_fwd_impl(x, x_hi, c_lo, y, n, ch, P(c, pidx), P(c, pidx + 1), (float*)c.params[pidx + 2], (float*)c.params[pidx + 3],
                           save, save + ch, c.eps, c.momentum, 0.f, c.training, c.bn_ws, c.bn_ws_bytes, true, c.stream));
 }
 void bn_bwd(Ctx& c, int pidx, const float* x, const float* dy, float* dx, int64_t n, int ch, const float* save,
             const float* x_hi = nullptr, int c_lo = 0, float* dx_hi = nullptr) {
+  if (abl_skip("bn")) return;
   EX(mm3d_bnrelu_bwd_impl(x, x_hi, c_lo, dy, dx, dx_hi, n, ch, P(c, pidx), P(c, pidx + 1), save, save + ch, Gp(c, pidx), Gp(c, pidx + 1), 0.f,
                           c.training, c.bn_ws, c.bn_ws_bytes, true, c.stream));
 }
@@ -278,6 +288,7 @@ const float* find_img(const Ctx& c, const float* w) {
 }
 // forward of layer type `kind` whose FINE level is l
 void conv_fwd(Ctx& c, Kind kind, int l, const float* in, int c_in, float* out, int c_out, const float* w) {
+  if (abl_skip("conv")) return;
   const LevelMeta& f = c.net->lv[l];
   if (const float* im = find_img(c, w)) {  // prebuilt weight image: the tcgen05 kernel directly
     const int64_t nc = l + 1 < c.net->L ? c.net->lv[l + 1].n : 0;
@@ -306,28 +317,32 @@ void conv_bwd(Ctx& c, Kind kind, int l, const float* in, int c_in, const float* 
   const float* im = find_img(c, w);   // prebuilt dgrad image (tensor-core modes)
   // parameter gradients inside the caller's (pre-zeroed) flat buffer accumulate; temporaries are overwritten
   const int acc = c.wgrad_acc && c.grad_lo <= (const char*)d_w && (const char*)d_w < c.grad_hi;
+  const bool do_wg = !abl_skip("wgrad"), do_dg = !abl_skip("conv");
   if (kind == SMC) {
-    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, f.n, c_out, d_w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap, acc,
-                       md, nullptr, 0, ws));
-    if (d_in && im)
+    if (do_wg)
+      EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, f.n, c_out, d_w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap, acc,
+                         md, nullptr, 0, ws));
+    if (d_in && im && do_dg)
       EX(mm3d_conv_fwd_tc_img(d_out, f.n, c_out, d_in, f.n, c_in, im, 27, f.plan_smc, f.plan_cap, c.stream));
-    else if (d_in)
+    else if (d_in && do_dg)
       EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, f.n, c_in, w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap,
                        MM3D_CONV_TRANSPOSE_W | MM3D_CONV_MIRROR_K, md, c.scratch, c.scratch_bytes, c.stream));
   } else if (kind == DOWN) {  // in: fine rows, d_out: coarse rows
-    EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, nc, c_out, d_w, 8, f.child, f.tstride, nullptr, f.plan_down, f.plan_cap, acc,
-                       md, nullptr, 0, ws));
-    if (im) EX(mm3d_conv_fwd_tc_img(d_out, nc, c_out, d_in, f.n, c_in, im, 8, f.plan_up, f.plan_cap, c.stream));
-    else
-    EX(mm3d_conv_fwd(d_out, nc, c_out, d_in, f.n, c_in, w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap,
-                     MM3D_CONV_TRANSPOSE_W, md, c.scratch, c.scratch_bytes, c.stream));
+    if (do_wg)
+      EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, nc, c_out, d_w, 8, f.child, f.tstride, nullptr, f.plan_down, f.plan_cap, acc,
+                         md, nullptr, 0, ws));
+    if (im && do_dg) EX(mm3d_conv_fwd_tc_img(d_out, nc, c_out, d_in, f.n, c_in, im, 8, f.plan_up, f.plan_cap, c.stream));
+    else if (do_dg)
+      EX(mm3d_conv_fwd(d_out, nc, c_out, d_in, f.n, c_in, w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap,
+                       MM3D_CONV_TRANSPOSE_W, md, c.scratch, c.scratch_bytes, c.stream));
   } else {  // UP: in: coarse rows, d_out: fine rows
-    EX(mm3d_conv_wgrad(in, nc, c_in, d_out, f.n, c_out, d_w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap, acc, md,
-                       nullptr, 0, ws));
-    if (im) EX(mm3d_conv_fwd_tc_img(d_out, f.n, c_out, d_in, nc, c_in, im, 8, f.plan_down, f.plan_cap, c.stream));
-    else
-    EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, nc, c_in, w, 8, f.child, f.tstride, nullptr, f.plan_down, f.plan_cap,
-                     MM3D_CONV_TRANSPOSE_W, md, c.scratch, c.scratch_bytes, c.stream));
+    if (do_wg)
+      EX(mm3d_conv_wgrad(in, nc, c_in, d_out, f.n, c_out, d_w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap, acc, md,
+                         nullptr, 0, ws));
+    if (im && do_dg) EX(mm3d_conv_fwd_tc_img(d_out, f.n, c_out, d_in, nc, c_in, im, 8, f.plan_down, f.plan_cap, c.stream));
+    else if (do_dg)
+      EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, nc, c_in, w, 8, f.child, f.tstride, nullptr, f.plan_down, f.plan_cap,
+                       MM3D_CONV_TRANSPOSE_W, md, c.scratch, c.scratch_bytes, c.stream));
   }
 }
 
