@@ -211,6 +211,22 @@ MM3D_API size_t mm3d_raster2d_workspace_bytes(int B, int H, int W);
 MM3D_API int mm3d_raster2d(const int64_t* idx, const int64_t* sample_offsets, int B, int H, int W, int64_t n,
                   const float* vals, float fill, float* out, void* ws, size_t ws_bytes, mm3d_stream_t stream);
 
+/* Point-wise prologue and loss around the 3D network.
+ * RGB mask, 3d_net/model.py:46-48:  s = sigmoid(x . w + b); y = x * s   (x, y float32 [n, c], c <= 8; w [c], b [1];
+ * s_out [n] keeps the gate for the backward pass; y may be x).  Backward: dx (may be NULL) [n, c], dw [c], db [1];
+ * x is the UNMASKED input; ws: (c + 1) doubles. */
+MM3D_API int mm3d_rgb_mask_fwd(const float* x, int64_t n, int c, const float* w, const float* b, float* y, float* s_out,
+                      mm3d_stream_t stream);
+MM3D_API int mm3d_rgb_mask_bwd(const float* x, const float* s, const float* dy, int64_t n, int c, const float* w, float* dx,
+                      float* dw, float* db, void* ws, size_t ws_bytes, mm3d_stream_t stream);
+/* Cross-modal loss, train.py:157-184:  loss[0] = mean over the n rows of sum_c q_c (log q_c - log p_c) with
+ * p = softmax(pred[n, :]), q = softmax(target[n, :]) (target detached); pred, target float32 [n, C] logits; ws: one
+ * double.  Backward: dpred = dloss[0] * (p - q) / n. */
+MM3D_API int mm3d_kl_logits_fwd(const float* pred, const float* target, int64_t n, int C, float* loss, void* ws, size_t ws_bytes,
+                       mm3d_stream_t stream);
+MM3D_API int mm3d_kl_logits_bwd(const float* pred, const float* target, int64_t n, int C, const float* dloss, float* dpred,
+                       mm3d_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Whole-network executor: UNetSCN (3d_net/scn_unet.py:90-126, VGG blocks, block_reps == 1) forward and
  * backward as one call each -- the same kernels as above, driven natively instead of from ~110

@@ -60,6 +60,10 @@ SIGNATURES = {
     "mm3d_lift2d_bwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i64, _p, _p]),
     "mm3d_raster2d_workspace_bytes": (_sz, [_i, _i, _i]),
     "mm3d_raster2d": (_i, [_p, _p, _i, _i, _i, _i64, _p, _f, _p, _p, _sz, _p]),
+    "mm3d_rgb_mask_fwd": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p]),
+    "mm3d_rgb_mask_bwd": (_i, [_p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "mm3d_kl_logits_fwd": (_i, [_p, _p, _i64, _i, _p, _p, _sz, _p]),
+    "mm3d_kl_logits_bwd": (_i, [_p, _p, _i64, _i, _p, _p, _p]),
     "mm3d_unet_num_params": (_i64, [_i]),
     "mm3d_unet_act_bytes": (_sz, [_i, _i, _i, _i, _p, _i64]),
     "mm3d_unet_bwd_bytes": (_sz, [_i, _i, _i, _i, _p, _i64]),

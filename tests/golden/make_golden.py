@@ -11,6 +11,8 @@ the lift fixture):  ``python tests/golden/make_golden.py``.
 * ``structure_small.npz`` -- oracle voxel ids / level coords / rule tables for a seeded cloud.
 * ``augment_ref.npz`` -- produced by the REFERENCE ITSELF: ``augment_and_scale_3d``
   (``lib/utils/augmentation_3d.py``) + the loader's integer cast and range filter.
+* ``heads_ref.npz`` -- RGB mask by the REFERENCE's ``Net3DSeg.forward`` (``3d_net/model.py:44-58``, backbone replaced by
+  a pass-through), cross-modal KL term by the torch lines of ``train.py:157-184``.
 """
 import importlib.util
 import os
@@ -166,6 +168,53 @@ def augment_from_reference():
                         offset=np.stack(offsets), scale=scale, full_scale=full_scale)
 
 
+REF_3D_DIR = "/root/reference/experiments_USA_SING/rgbd_rgbxyz_sigmoid_for_rgb/3d_net"
+
+
+def heads_from_reference():
+    """``heads_ref.npz``: the RGB mask computed by the reference's own ``Net3DSeg.forward`` (CPU; its sparse backbone is
+    replaced by a pass-through that returns the -- already masked -- point features, and the heads by 16-channel-free
+    stand-ins), with autograd gradients; and the cross-modal KL term computed by the torch lines of
+    ``train.py:157-184``."""
+    import torch.nn as nn
+    src = open(os.path.join(REF_3D_DIR, "model.py")).read().replace("from .scn_unet import UNetSCN", "UNetSCN = None")
+    mod = type(sys)("ref_3d_model")
+    exec(compile(src, os.path.join(REF_3D_DIR, "model.py"), "exec"), mod.__dict__)
+
+    class PassThrough(nn.Module):  # stands in for UNetSCN: hands the (masked) features on
+        out_channels = 3
+
+        def forward(self, x):
+            return x[1]
+
+    mod.UNetSCN = lambda **kw: PassThrough()
+    mod.L2G_classifier_3D = lambda c, k: nn.Identity()
+    torch.manual_seed(11)
+    net = mod.Net3DSeg(num_classes=6, dual_head=True, backbone_3d_kwargs={})
+    rng = np.random.default_rng(11)
+    feats = torch.from_numpy(rng.random((2000, 3), dtype=np.float32))
+    w = net.linear_rgb_mask.weight.detach().clone()
+    b = net.linear_rgb_mask.bias.detach().clone()
+    x_in = feats.clone()
+    _, masked, _ = net({"x": [torch.zeros(2000, 4, dtype=torch.int64), x_in]})   # model.py:44-58
+    g = torch.from_numpy(rng.standard_normal((2000, 3)).astype(np.float32))
+    net.zero_grad()
+    x_leaf = feats.clone().requires_grad_(True)
+    m = torch.sigmoid(net.linear_rgb_mask(x_leaf))
+    (x_leaf * m).backward(g)                                                      # same ops, out of place, for dx
+    # cross-modal loss (train.py:157-184)
+    import torch.nn.functional as F
+    pred = torch.from_numpy((3 * rng.standard_normal((1500, 6))).astype(np.float32)).requires_grad_(True)
+    target = torch.from_numpy((3 * rng.standard_normal((1500, 6))).astype(np.float32))
+    loss = F.kl_div(F.log_softmax(pred, dim=1), F.softmax(target.detach(), dim=1), reduction="none").sum(1).mean()
+    loss.backward()
+    np.savez_compressed(os.path.join(HERE, "heads_ref.npz"), feats=feats.numpy(), w=w.numpy(), b=b.numpy(),
+                        masked=masked.detach().numpy(), g=g.numpy(), dx=x_leaf.grad.numpy(),
+                        dw=net.linear_rgb_mask.weight.grad.numpy(), db=net.linear_rgb_mask.bias.grad.numpy(),
+                        pred=pred.detach().numpy(), target=target.numpy(), loss=loss.detach().numpy(),
+                        dpred=pred.grad.numpy())
+
+
 if __name__ == "__main__":
     only = sys.argv[1] if len(sys.argv) > 1 else None  # e.g. `make_golden.py augment` regenerates one fixture
     if only in (None, "lift"):
@@ -176,6 +225,8 @@ if __name__ == "__main__":
         structure_small()
     if only in (None, "augment"):
         augment_from_reference()
+    if only in (None, "heads"):
+        heads_from_reference()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

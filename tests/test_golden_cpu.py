@@ -82,3 +82,21 @@ def test_raster_oracle_last_point_wins():
     img = np.arange(3 * 4 * 3, dtype=np.float32).reshape(3, 4, 3)
     f = raster_oracle.rgb_feats(img, idx)
     assert f.shape == (5, 3) and np.array_equal(f[0], img[:, 1, 2])
+
+
+def test_heads_oracle_matches_reference_fixture():
+    """RGB mask vs what the reference's own Net3DSeg.forward produced; KL term vs the reference's torch lines."""
+    import torch
+    from oracle import heads_oracle
+    z = np.load(os.path.join(G, "heads_ref.npz"))
+    x = torch.from_numpy(z["feats"]).requires_grad_(True)
+    w, b = torch.from_numpy(z["w"]).requires_grad_(True), torch.from_numpy(z["b"]).requires_grad_(True)
+    y = heads_oracle.rgb_mask(x, w, b)
+    assert np.array_equal(y.detach().numpy(), z["masked"])
+    y.backward(torch.from_numpy(z["g"]))
+    assert np.allclose(x.grad.numpy(), z["dx"], rtol=0, atol=0) and np.allclose(w.grad.numpy(), z["dw"], rtol=1e-6)
+    pred = torch.from_numpy(z["pred"]).requires_grad_(True)
+    loss = heads_oracle.cross_modal_kl(pred, torch.from_numpy(z["target"]))
+    assert float(loss.detach()) == float(z["loss"])
+    loss.backward()
+    assert np.array_equal(pred.grad.numpy(), z["dpred"])

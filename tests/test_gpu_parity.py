@@ -818,3 +818,30 @@ def test_tf32_wgrad_in_several_launches(monkeypatch):
     assert float((one - ref).abs().max()) < 1e-2 * scale
     assert float((many - ref).abs().max()) < 1e-2 * scale
     assert float((many - one).abs().max()) < 1e-5 * scale  # same products, different accumulation order
+
+
+def test_heads_reference_fixture():
+    """RGB-mask prologue and cross-modal KL term against tests/golden/heads_ref.npz, which the
+    reference's Net3DSeg.forward / torch lines produced: forward 1e-6, gradients 1e-5 relative to the tensor scale."""
+    from mm2d3d_b200.heads import cross_modal_kl, rgb_mask
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "heads_ref.npz"))
+    dev = lambda k: torch.from_numpy(z[k]).to(DEV)
+    x, w, b = dev("feats").requires_grad_(True), dev("w").requires_grad_(True), dev("b").requires_grad_(True)
+    y = rgb_mask(x, w, b)
+    assert float((y.detach().cpu() - torch.from_numpy(z["masked"])).abs().max()) < 1e-6
+    y.backward(dev("g"))
+    for got, key in ((x.grad, "dx"), (w.grad, "dw"), (b.grad, "db")):
+        want = torch.from_numpy(z[key])
+        assert got.shape == want.shape
+        assert float((got.cpu() - want).abs().max()) <= 1e-5 * max(float(want.abs().max()), 1.0), key
+    pred = dev("pred").requires_grad_(True)
+    loss = cross_modal_kl(pred, dev("target"))
+    assert abs(float(loss.detach()) - float(z["loss"])) <= 1e-6 * abs(float(z["loss"]))
+    (2.5 * loss).backward()
+    want = 2.5 * torch.from_numpy(z["dpred"])
+    assert float((pred.grad.cpu() - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    # a data tensor that does not need a gradient, larger batch, odd sizes
+    x2 = torch.rand(100003, 3, device=DEV)
+    y2 = rgb_mask(x2, w.detach(), b.detach())
+    ref = x2 * torch.sigmoid(x2 @ w.detach().t() + b.detach())
+    assert float((y2 - ref).abs().max()) < 1e-6
