@@ -397,6 +397,8 @@ def run_ours(args):
             ev.record(copy_stream)
         pending[i] = (locs_d, feats_d, ev, prep)
 
+    res_ring = [torch.empty((), dtype=torch.float32, pin_memory=True) for _ in range(4)]
+
     def step_e2e(i):
         if i not in pending:
             upload(i)
@@ -412,7 +414,7 @@ def run_ours(args):
         out.backward(gout)
         flat.all_reduce_mean()
         res = (out.detach() * gout).sum()  # the step's scalar result ...
-        host_res = torch.empty((), dtype=res.dtype, pin_memory=True)
+        host_res = res_ring[i % len(res_ring)]  # pinned once: page-locking per step serialises in the driver at N > 1
         host_res.copy_(res, non_blocking=True)  # ... goes back to the host; it is waited for (and used) one step later,
         done = torch.cuda.Event()               # after the next step has been enqueued (lazy loss logging)
         done.record()

@@ -18,4 +18,12 @@ PARITY STATUS
 * 2D->3D lift (``lift_oracle``): pinned against the reference itself
   (``2d_net/model.py:131-137,163-173`` imported in the build container; fixtures
   under ``tests/golden`` with the generating script).
+* points -> voxel coordinates (``augment_oracle``): pinned against the reference itself
+  (``augment_and_scale_3d`` of ``lib/utils/augmentation_3d.py`` imported and run; ``augment_ref.npz``).
+* RGB mask / cross-modal KL term (``heads_oracle``): the mask is pinned against the reference's own
+  ``Net3DSeg.forward`` (``3d_net/model.py:44-58``, backbone replaced by a pass-through so it runs on CPU), the loss
+  against the torch lines of ``train.py:157-184`` (``heads_ref.npz``).
+* point values -> image maps (``raster_oracle``): the loaders build these inline in ``__getitem__`` (needs the dataset
+  on disk), so the numpy statements of ``lib/dataset/nuscenes_dataloader.py:274-278`` are restated; numpy's indexed
+  assignment is the definition -- **no reference-produced fixture**.
 """
