@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: UNetSCN forward+backward on synthetic nuScenes-shaped scans.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fp32|tf32|bf16] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fp32|tf32] [--impl ours|reference]
 
 One "step" = one pass of the hot path over one batch (default 8 scans per GPU, BASELINE.json
 configs[1]): structure build (voxel hash, 7-level pyramid, rule tables), UNetSCN forward, backward

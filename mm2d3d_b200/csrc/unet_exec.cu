@@ -520,6 +520,7 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
 
 int fill_net(Net& net, int in_channels, int m, int num_planes, int mode, const int64_t* level_desc, int64_t n_points) {
   MM3D_REQUIRE(num_planes >= 1 && num_planes <= 16 && m > 0 && in_channels > 0, MM3D_ERR_INVALID, "bad network shape");
+  MM3D_REQUIRE(mode == MM3D_MODE_FP32 || mode == MM3D_MODE_TF32, MM3D_ERR_UNSUPPORTED, "conv mode %d not implemented in this build", mode);
   net.L = num_planes; net.m = m; net.cin = in_channels; net.mode = mode; net.n_points = n_points;
   // tensor-core kernels gather rows in 64-byte pieces: pad the stem input to a multiple of 16 channels
   net.cin_k = in_channels;

@@ -27,9 +27,12 @@ __all__ = [
 
 
 def set_conv_mode(mode: str) -> None:
-    """Arithmetic of the sparse convolutions: "fp32" (SIMT, parity), "tf32" or "bf16" (tcgen05)."""
+    """Arithmetic of the sparse convolutions: "fp32" (SIMT, parity) or "tf32" (tcgen05); "bf16" is reserved."""
     if mode not in _lib.MODES:
         raise ValueError(f"unknown mode {mode!r}; expected one of {sorted(_lib.MODES)}")
+    if mode == "bf16":
+        # the ABI reserves the mode; the kernels of this build take FP32 (SIMT) or TF32 (tcgen05) operands only
+        raise NotImplementedError("conv mode 'bf16' is not implemented in this build; use 'tf32' or 'fp32'")
     F.DEFAULT_MODE = mode
 
 
