@@ -479,7 +479,7 @@ def run_ours(args):
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     pending.clear()
-    if acc != acc and not os.environ.get("MM3D_ABL_SKIP"):  # (timing experiments with kernels switched off produce garbage)
+    if acc != acc:
         raise SystemExit("bench.py: the end-to-end loop produced NaN")
 
     if world > 1:
@@ -571,6 +571,9 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    if os.environ.get("MM3D_ABL_SKIP"):
+        # ablation builds (-DMM3D_ABLATION) skip kernel families: never a benchmark number
+        raise SystemExit("bench.py: MM3D_ABL_SKIP is set -- refusing to print a benchmark line for an ablated run")
     if args.impl == "reference":
         run_reference(args)
     else:

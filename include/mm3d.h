@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MM3D_ABI_VERSION 2
+#define MM3D_ABI_VERSION 3
 
 #define MM3D_OK 0
 #define MM3D_ERR_INVALID 1     /* bad argument */
@@ -59,8 +59,12 @@ MM3D_API const char* mm3d_last_error(void);
 MM3D_API int mm3d_device_supports_tc(void);
 /* number of CUDA kernels this library has launched in this process (for the benchmark's gpu_launches) */
 MM3D_API long long mm3d_kernel_launches(void);
-/* Synchronises the device and returns (and clears) the sticky error flag a kernel raises when its
- * internal pipeline timed out: 0 = none, 1 = raised, <0 = could not be read.  Debug / test aid. */
+/* Returns (and clears) the current device's sticky error bits: 1 = a kernel's bounded internal wait (mbarrier
+ * pipeline, BatchNorm grid barrier) timed out -- its results are garbage; 2 = mm3d_lift2d_* met an index outside
+ * the image (that point was skipped).  0 = none, <0 = could not be read.  The bits live in mapped pinned host
+ * memory, so this call neither synchronises nor touches the device: it reports what the kernels that have
+ * finished so far raised (synchronise first to cover everything enqueued).  The Python host polls it at every
+ * network forward / backward and raises. */
 MM3D_API int mm3d_take_device_error(void);
 
 /* ------------------------------------------------------------------------------------------
@@ -172,6 +176,11 @@ MM3D_API int mm3d_conv_fwd(const float* in, int64_t n_in, int c_in, float* out, 
                   const float* weight, int K, const int32_t* tbl, int64_t tbl_stride,
                   const uint8_t* onehot_off, const void* plan, int64_t plan_cap, int flags, int mode,
                   void* ws, size_t ws_bytes, mm3d_stream_t stream);
+/* Tensor-core modes: the gathered operand (`in` of mm3d_conv_fwd, `in` and `d_out` of mm3d_conv_wgrad) is read by
+ * a kind::tf32 MMA, which ignores the low 13 mantissa bits.  Callers get round-to-nearest instead of truncation by
+ * passing tensors whose values are already TF32 (mm3d_round_tf32; the whole-network executor's producers -- BatchNorm,
+ * skip-gradient sum, stem padding -- store rounded values themselves).  Weights are rounded inside. */
+MM3D_API int mm3d_round_tf32(const float* in, float* out, int64_t n, mm3d_stream_t stream);
 /* d_weight[k] (+)= sum_j in[tbl(j,k)]^T . d_out[j]   ([K, c_in, c_out]); accumulate=0 overwrites */
 MM3D_API int mm3d_conv_wgrad(const float* in, int64_t n_in, int c_in, const float* d_out, int64_t n_out,
                     int c_out, float* d_weight, int K, const int32_t* tbl, int64_t tbl_stride,

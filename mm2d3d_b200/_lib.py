@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmm3d.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 LEVEL_DESC_WORDS = 10
 
 MODE_FP32, MODE_TF32, MODE_BF16 = 0, 1, 2
@@ -52,6 +52,7 @@ SIGNATURES = {
     "mm3d_build_plan": (_i, [_p, _i64, _p, _p, _i64, _i, _p, _sz, _p]),
     "mm3d_build_plans": (_i, [_p, _i, _p]),
     "mm3d_conv_fwd": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i, _p, _i64, _p, _p, _i64, _i, _i, _p, _sz, _p]),
+    "mm3d_round_tf32": (_i, [_p, _p, _i64, _p]),
     "mm3d_conv_wgrad": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i, _p, _i64, _p, _p, _i64, _i, _i, _p, _sz, _p]),
     "mm3d_bnrelu_workspace_bytes": (_sz, [_i]),
     "mm3d_bnrelu_fwd": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i, _p, _sz, _p]),
@@ -95,6 +96,18 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = lib.mm3d_last_error().decode("utf-8", "replace")
         raise Mm3dError(f"{what or 'libmm3d'} failed (code {rc}): {msg}")
+
+
+def raise_device_errors(where: str = "") -> None:
+    """Poll the sticky device-error bits (mapped host memory: no synchronisation, no CUDA call) and raise."""
+    bits = lib.mm3d_take_device_error()
+    if bits > 0:
+        what = []
+        if bits & 1:
+            what.append("a kernel's internal pipeline or grid barrier timed out (results of that launch are garbage)")
+        if bits & 2:
+            what.append("lift2d met a pixel index outside the feature map")
+        raise Mm3dError(f"{where or 'libmm3d'}: device-side error reported: " + "; ".join(what))
 
 
 def ptr(t):

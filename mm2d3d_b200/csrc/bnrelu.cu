@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kThreads)
 k_bn_apply(const float* __restrict__ x, float* __restrict__ y, int64_t n, int c,
            const float* __restrict__ gamma, const float* __restrict__ beta,
            float* running_mean, float* running_var, float* save_mean, float* save_invstd,
-           const double* __restrict__ sums, float eps, float momentum, float leak, int training) {
+           const double* __restrict__ sums, float eps, float momentum, float leak, int training, int round_tf32) {
   float* s_mean = reinterpret_cast<float*>(s_acc);
   float* s_scale = s_mean + c;
   for (int i = threadIdx.x; i < c; i += kThreads) {
@@ -107,6 +107,7 @@ k_bn_apply(const float* __restrict__ x, float* __restrict__ y, int64_t n, int c,
     for (int j = 0; j < VEC; ++j) {
       const float o = fmaf(t[j] - mean[j], scale[j], bet[j]);
       t[j] = o > 0.f ? o : o * leak;
+      if (round_tf32) t[j] = mm3d_rna_tf32(t[j]);
     }
     vstore<VEC>(y + row * c + v * VEC, t);
   }
@@ -128,7 +129,7 @@ __device__ __forceinline__ bool grid_arrive_and_wait(unsigned int* sync, int* er
       if (*reinterpret_cast<volatile unsigned int*>(sync) >= gridDim.x) { ok = 1; break; }
       __nanosleep(64);
     }
-    if (!ok && err) atomicExch(err, 1);
+    if (!ok) mm3d_raise(err);
     s_ok = ok;
     __threadfence();
   }
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(kThreads)
 k_bn_fwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int c_lo, float* __restrict__ y, int64_t n, int c,
                const float* __restrict__ gamma, const float* __restrict__ beta,
                float* running_mean, float* running_var, float* save_mean, float* save_invstd,
-               double* sums, unsigned int* sync, float eps, float momentum, float leak, int* err) {
+               double* sums, unsigned int* sync, float eps, float momentum, float leak, int round_tf32, int* err) {
   mm3d_griddep_launch();
   mm3d_griddep_wait();
   const int cv = c / VEC;
@@ -228,6 +229,7 @@ k_bn_fwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
       for (int j = 0; j < VEC; ++j) {
         const float o = fmaf(t[u][j] - mean[j], scale[j], bet[j]);
         t[u][j] = o > 0.f ? o : o * leak;
+        if (round_tf32) t[u][j] = mm3d_rna_tf32(t[u][j]);
       }
       vstore<VEC>(y + (row + u * stride) * c + v * VEC, t[u]);
     }
@@ -239,6 +241,7 @@ k_bn_fwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
     for (int j = 0; j < VEC; ++j) {
       const float o = fmaf(t[j] - mean[j], scale[j], bet[j]);
       t[j] = o > 0.f ? o : o * leak;
+      if (round_tf32) t[j] = mm3d_rna_tf32(t[j]);
     }
     vstore<VEC>(y + row * c + v * VEC, t);
   }
@@ -251,7 +254,7 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
                float* __restrict__ dx, float* __restrict__ dx_hi, int64_t n, int c,
                const float* __restrict__ gamma, const float* __restrict__ beta,
                const float* __restrict__ save_mean, const float* __restrict__ save_invstd, float leak,
-               double* sums, unsigned int* sync, float* d_gamma, float* d_beta, int training, int* err) {
+               double* sums, unsigned int* sync, float* d_gamma, float* d_beta, int training, int round_flags, int* err) {
   mm3d_griddep_launch();
   mm3d_griddep_wait();
   const int cv = c / VEC;
@@ -265,6 +268,9 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
   const int64_t xld = x_hi ? (hi ? c - c_lo : c_lo) : c;
   float* dxb = (dx_hi && hi) ? dx_hi + (v * VEC - c_lo) : dx + v * VEC;
   const int64_t dxld = dx_hi ? (hi ? c - c_lo : c_lo) : c;
+  // round_flags bit 0: dx (or its low column block) feeds a TF32 convolution as d_out -> store RNA-rounded values;
+  // bit 1: same for the high column block dx_hi
+  const bool rnd = (round_flags & ((dx_hi && hi) ? 2 : 1)) != 0;
   float mean[VEC], invstd[VEC], scale[VEC], bet[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) mean[j] = invstd[j] = scale[j] = bet[j] = 0.f;
@@ -310,10 +316,10 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
     block_flush<VEC>(s, q, c, cv, rows_pass, r, v, sums);
   }
   grid_arrive_and_wait(sync, err);
-  if (blockIdx.x == 0)
+  if (blockIdx.x == 0)  // (frozen affine parameters: NULL gradient pointers)
     for (int i = threadIdx.x; i < c; i += kThreads) {
-      d_beta[i] = (float)__ldcg(sums + i);
-      d_gamma[i] = (float)__ldcg(sums + c + i);
+      if (d_beta) d_beta[i] = (float)__ldcg(sums + i);
+      if (d_gamma) d_gamma[i] = (float)__ldcg(sums + c + i);
     }
   float md[VEC], mdx[VEC];
 #pragma unroll
@@ -343,6 +349,7 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
         const float o = fmaf(xc, scale[j], bet[j]);
         const float d = o > 0.f ? g[u][j] : g[u][j] * leak;
         g[u][j] = scale[j] * (d - md[j] - xc * invstd[j] * mdx[j]);
+        if (rnd) g[u][j] = mm3d_rna_tf32(g[u][j]);
       }
       vstore<VEC>(dxb + (row + u * stride) * dxld, g[u]);
     }
@@ -357,18 +364,36 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
       const float o = fmaf(xc, scale[j], bet[j]);
       const float d = o > 0.f ? g[j] : g[j] * leak;
       g[j] = scale[j] * (d - md[j] - xc * invstd[j] * mdx[j]);
+      if (rnd) g[j] = mm3d_rna_tf32(g[j]);
     }
     vstore<VEC>(dxb + row * dxld, g);
   }
 }
 
-int bn_grid(int64_t n, int cv) {
+// Single-launch kernels wait on each other, so every CTA of the grid must be able to be resident at once: the grid
+// is capped at (CTAs per SM the occupancy API reports for this kernel and shared-memory size, at most 2) x (the
+// device's real SM count).  Kernels of other streams (the weight-gradient CTAs of the side stream) may delay a
+// CTA's start but never depend on this grid, so the barrier always completes; the wait is bounded anyway.
+template <typename Kernel>
+int bn_grid(Kernel kernel, int64_t n, int cv, size_t smem) {
   const int rows_pass = kThreads / cv;
   int64_t g = mm3d_cdiv(n, (int64_t)rows_pass * 4);  // >= 4 rows per thread when there is enough work
   if (g < 1) g = 1;
-  // Single-launch kernels wait on each other, so every CTA must be resident at once -- also next to a weight-
-  // gradient CTA of the side stream (352 threads x 64 registers): two 256-thread CTAs x 64 registers per SM fit.
-  const int64_t cap = (int64_t)MM3D_NUM_SMS * 2;
+  // the query is cached per device and kernel instantiation for the 16 KB upper bound of these kernels' dynamic
+  // shared memory (2 * rows_pass * c floats <= 8 KB for every supported c); larger requests are queried directly
+  constexpr size_t kSmemBound = 16 * 1024;
+  static int cached[64] = {0};
+  int& slot = cached[mm3d_device_slot()];
+  int per_sm = smem <= kSmemBound ? slot : 0;
+  if (per_sm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem <= kSmemBound ? kSmemBound : smem) != cudaSuccess || per_sm < 1) {
+      (void)cudaGetLastError();
+      per_sm = 1;
+    }
+    if (per_sm > 2) per_sm = 2;
+    if (smem <= kSmemBound) slot = per_sm;
+  }
+  const int64_t cap = (int64_t)mm3d_sm_count() * per_sm;
   return (int)(g < cap ? g : cap);
 }
 
@@ -381,13 +406,16 @@ extern "C" size_t mm3d_bnrelu_workspace_bytes(int c) { return mm3d_align(sizeof(
 
 #define BN_DISPATCH(KERNEL, ...)                                                        \
   do {                                                                                  \
+    const int grid = mm3d_grid(n, kThreads / cv);                                       \
     if (vec4) KERNEL<4><<<grid, kThreads, smem, stream>>>(__VA_ARGS__);                 \
     else      KERNEL<1><<<grid, kThreads, smem, stream>>>(__VA_ARGS__);                 \
   } while (0)
 #define BN_DISPATCH_PDL(KERNEL, ...)                                                                        \
   do {                                                                                                      \
-    if (vec4) MM3D_CUDA(mm3d_launch_pdl(KERNEL<4>, dim3(grid), dim3(kThreads), smem, stream, __VA_ARGS__)); \
-    else      MM3D_CUDA(mm3d_launch_pdl(KERNEL<1>, dim3(grid), dim3(kThreads), smem, stream, __VA_ARGS__)); \
+    if (vec4) { const int grid = bn_grid(KERNEL<4>, n, cv, smem);                                           \
+                MM3D_CUDA(mm3d_launch_pdl(KERNEL<4>, dim3(grid), dim3(kThreads), smem, stream, __VA_ARGS__)); } \
+    else      { const int grid = bn_grid(KERNEL<1>, n, cv, smem);                                           \
+                MM3D_CUDA(mm3d_launch_pdl(KERNEL<1>, dim3(grid), dim3(kThreads), smem, stream, __VA_ARGS__)); } \
   } while (0)
 
 // ws_clean: the workspace is known to be all zero (the kernels leave it that way), skip the memset
@@ -395,7 +423,7 @@ int mm3d_bnrelu_fwd_impl(const float* x, const float* x_hi, int c_lo, float* y, 
                          const float* beta,
                          float* running_mean, float* running_var, float* save_mean, float* save_invstd,
                          float eps, float momentum, float leakiness, int training,
-                         void* ws, size_t ws_bytes, bool ws_clean, cudaStream_t stream) {
+                         void* ws, size_t ws_bytes, bool ws_clean, int round_tf32, cudaStream_t stream) {
   MM3D_REQUIRE(c > 0 && n >= 0, MM3D_ERR_INVALID, "bad sizes");
   const bool vec4 = (c % 4 == 0) && (c_lo % 4 == 0) && ((((uintptr_t)x | (uintptr_t)x_hi | (uintptr_t)y) & 15) == 0);
   const int cv = vec4 ? c / 4 : c;
@@ -405,17 +433,16 @@ int mm3d_bnrelu_fwd_impl(const float* x, const float* x_hi, int c_lo, float* y, 
   if (n == 0) return MM3D_OK;
   double* sums = (double*)ws;
   unsigned int* sync = (unsigned int*)(sums + 2 * c);
-  const int grid = bn_grid(n, cv);
   const size_t smem = sizeof(double) * 2 * c > sizeof(float) * 2 * (kThreads / cv) * (size_t)c
                           ? sizeof(double) * 2 * c : sizeof(float) * 2 * (kThreads / cv) * (size_t)c;
   if (training) {
     MM3D_REQUIRE(save_mean && save_invstd && running_mean && running_var, MM3D_ERR_INVALID, "training needs stat buffers");
     if (!ws_clean) MM3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c + 16, stream));
     BN_DISPATCH_PDL(k_bn_fwd_fused, x, x_hi, c_lo, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, sums, sync,
-                eps, momentum, leakiness, mm3d_device_err_flag());
+                eps, momentum, leakiness, round_tf32, mm3d_device_err_flag());
   } else {
     BN_DISPATCH(k_bn_apply, x, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, sums, eps,
-                momentum, leakiness, training);
+                momentum, leakiness, training, round_tf32);
   }
   mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_bnrelu_fwd");
@@ -425,7 +452,7 @@ int mm3d_bnrelu_fwd_impl(const float* x, const float* x_hi, int c_lo, float* y, 
 int mm3d_bnrelu_bwd_impl(const float* x, const float* x_hi, int c_lo, const float* dy, float* dx, float* dx_hi,
                          int64_t n, int c, const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
                          float* d_gamma, float* d_beta, float leakiness, int training,
-                         void* ws, size_t ws_bytes, bool ws_clean, cudaStream_t stream) {
+                         void* ws, size_t ws_bytes, bool ws_clean, int round_flags, cudaStream_t stream) {
   MM3D_REQUIRE(c > 0 && n >= 0, MM3D_ERR_INVALID, "bad sizes");
   const bool vec4 = (c % 4 == 0) && (c_lo % 4 == 0) &&
                     ((((uintptr_t)x | (uintptr_t)x_hi | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dx_hi) & 15) == 0);
@@ -435,16 +462,15 @@ int mm3d_bnrelu_bwd_impl(const float* x, const float* x_hi, int c_lo, const floa
   double* sums = (double*)ws;
   unsigned int* sync = (unsigned int*)(sums + 2 * c);
   if (n == 0) {
-    MM3D_CUDA(cudaMemsetAsync(d_gamma, 0, sizeof(float) * c, stream));
-    MM3D_CUDA(cudaMemsetAsync(d_beta, 0, sizeof(float) * c, stream));
+    if (d_gamma) MM3D_CUDA(cudaMemsetAsync(d_gamma, 0, sizeof(float) * c, stream));
+    if (d_beta) MM3D_CUDA(cudaMemsetAsync(d_beta, 0, sizeof(float) * c, stream));
     return MM3D_OK;
   }
   if (!ws_clean) MM3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c + 16, stream));
-  const int grid = bn_grid(n, cv);
   const size_t smem = sizeof(double) * 2 * c > sizeof(float) * 2 * (kThreads / cv) * (size_t)c
                           ? sizeof(double) * 2 * c : sizeof(float) * 2 * (kThreads / cv) * (size_t)c;
   BN_DISPATCH_PDL(k_bn_bwd_fused, x, x_hi, c_lo, dy, dx, dx_hi, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums, sync, d_gamma,
-              d_beta, training, mm3d_device_err_flag());
+              d_beta, training, round_flags, mm3d_device_err_flag());
   mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_bnrelu_bwd");
   return MM3D_OK;
@@ -455,7 +481,7 @@ extern "C" int mm3d_bnrelu_fwd(const float* x, float* y, int64_t n, int c, const
                                float eps, float momentum, float leakiness, int training,
                                void* ws, size_t ws_bytes, mm3d_stream_t stream) {
   return mm3d_bnrelu_fwd_impl(x, nullptr, 0, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, eps, momentum,
-                              leakiness, training, ws, ws_bytes, false, (cudaStream_t)stream);
+                              leakiness, training, ws, ws_bytes, false, 0, (cudaStream_t)stream);
 }
 
 extern "C" int mm3d_bnrelu_bwd(const float* x, const float* dy, float* dx, int64_t n, int c, const float* gamma,
@@ -463,5 +489,5 @@ extern "C" int mm3d_bnrelu_bwd(const float* x, const float* dy, float* dx, int64
                                float* d_gamma, float* d_beta, float leakiness, int training,
                                void* ws, size_t ws_bytes, mm3d_stream_t stream) {
   return mm3d_bnrelu_bwd_impl(x, nullptr, 0, dy, dx, nullptr, n, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, leakiness, training,
-                              ws, ws_bytes, false, (cudaStream_t)stream);
+                              ws, ws_bytes, false, 0, (cudaStream_t)stream);
 }

@@ -9,6 +9,10 @@
 
 #define MM3D_NUM_SMS 148  // B200: 2 dies x 74 SMs; persistent / grid-stride kernels size to this
 
+// SM count of the current device (cached per device); kernels that wait on each other size their grids from this
+// and from the occupancy API, not from the constant above
+int mm3d_sm_count();
+
 void mm3d_set_error(const char* fmt, ...);
 void mm3d_count_launches(int n);  // bookkeeping for mm3d_kernel_launches()
 
@@ -62,6 +66,22 @@ static inline int mm3d_grid(int64_t n, int block, int ctas_per_sm = 8) {
 // has completed and its writes are visible.  Kernels call mm3d_griddep_launch() early so that their own
 // successor can be scheduled as soon as SM resources free up.  MM3D_NO_PDL=1 launches plainly.
 #ifdef __CUDACC__
+// Sticky device-error words live in mapped pinned host memory (mm3d_device_err_flag): word 0 = a bounded wait of a
+// kernel pipeline / grid barrier timed out, word 1 = a lift index outside the image.  A plain store + system fence
+// is enough (the words only ever go 0 -> 1) and the host can poll them without any CUDA call.
+__device__ __forceinline__ void mm3d_raise(int* err, int word = 0) {
+  if (err) {
+    *reinterpret_cast<volatile int*>(err + word) = 1;
+    __threadfence_system();
+  }
+}
+// round-to-nearest (ties away) to TF32: what a producer stores when its consumer is a kind::tf32 tcgen05.mma, which
+// would otherwise TRUNCATE the low 13 mantissa bits of a raw FP32 operand
+__device__ __forceinline__ float mm3d_rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void mm3d_griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void mm3d_griddep_launch() {
 #ifdef MM3D_PDL_EARLY_TRIGGER

@@ -305,7 +305,7 @@ done:
   asm volatile("cp.async.wait_all;" ::: "memory");
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0 && *abort_flag && p.err) atomicExch(p.err, 1);
+  if (threadIdx.x == 0 && *abort_flag) mm3d_raise(p.err);
   if (warp == S + 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -341,27 +341,46 @@ size_t mm3d_conv_tc_workspace_bytes(int c_in, int c_out, int K) {
   return mm3d_align((size_t)K * nb * n_pad * 128);  // weight image
 }
 
-// Sticky per-device error flag set by a kernel whose mbarrier pipeline timed out (never in a
-// correct build; it turns a would-be GPU hang into a reportable error).
-static int* g_err_flag[64] = {nullptr};
+// Sticky per-device error words (mm3d_raise, common.cuh) in MAPPED PINNED host memory: a kernel whose bounded wait
+// timed out (never in a correct build; it turns a would-be GPU hang into a reportable error) or that met an
+// out-of-image lift index stores 1 there, and the host reads the words without any CUDA call or synchronisation --
+// the executor polls them at every forward / backward call.
+static int* g_err_host[64] = {nullptr};
+static int* g_err_dev[64] = {nullptr};
 int* mm3d_device_err_flag() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  if (!g_err_flag[dev]) {
-    int* p = nullptr;
-    if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) return nullptr;
-    cudaMemset(p, 0, sizeof(int));
-    g_err_flag[dev] = p;
+  if (!g_err_dev[dev]) {
+    int* h = nullptr;
+    if (cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    for (int i = 0; i < 16; ++i) h[i] = 0;
+    int* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { (void)cudaGetLastError(); cudaFreeHost(h); return nullptr; }
+    g_err_host[dev] = h;
+    g_err_dev[dev] = d;
   }
-  return g_err_flag[dev];
+  return g_err_dev[dev];
 }
 
+static int g_sm_count[64] = {0};
+int mm3d_sm_count() {
+  const int dev = mm3d_device_slot();
+  if (!g_sm_count[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = MM3D_NUM_SMS; }
+    g_sm_count[dev] = n;
+  }
+  return g_sm_count[dev];
+}
+
+// Bits: 1 = a kernel pipeline / grid barrier timed out, 2 = a lift index outside the image.  Reads and clears the
+// current device's words; no synchronisation (callers that want everything enqueued so far synchronise first).
 extern "C" int mm3d_take_device_error(void) {
-  int* p = mm3d_device_err_flag();
-  if (!p) return -1;
+  if (!mm3d_device_err_flag()) return -1;
+  volatile int* h = g_err_host[mm3d_device_slot()];
   int v = 0;
-  if (cudaMemcpy(&v, p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  if (v) cudaMemset(p, 0, sizeof(int));
+  if (h[0]) { v |= 1; h[0] = 0; }
+  if (h[1]) { v |= 2; h[1] = 0; }
   return v;
 }
 

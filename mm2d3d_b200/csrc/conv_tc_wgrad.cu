@@ -363,7 +363,7 @@ done:
   asm volatile("cp.async.wait_all;" ::: "memory");
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0 && *abort_flag && p.err) atomicExch(p.err, 1);
+  if (threadIdx.x == 0 && *abort_flag) mm3d_raise(p.err);
   if (warp == S + 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);

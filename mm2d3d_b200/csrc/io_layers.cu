@@ -10,6 +10,8 @@
 
 #include "common.cuh"
 
+int* mm3d_device_err_flag();  // conv_tc.cu
+
 namespace {
 
 // ------------------------------------------------------------------ InputLayer
@@ -91,7 +93,7 @@ __device__ __forceinline__ int find_sample(const int64_t* __restrict__ offs, int
 template <class T>
 __global__ void k_lift_fwd(const T* __restrict__ fmap, int B, int C, int H, int W,
                            const int64_t* __restrict__ idx, const int64_t* __restrict__ offs, int64_t n,
-                           T* __restrict__ out) {
+                           T* __restrict__ out, int* err) {
   const int64_t total = n * C;
   const int64_t hw = (int64_t)H * W;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -101,6 +103,12 @@ __global__ void k_lift_fwd(const T* __restrict__ fmap, int B, int C, int H, int 
     int64_t r = __ldg(idx + 2 * p), col = __ldg(idx + 2 * p + 1);
     if (r < 0) r += H;      // torch advanced indexing wraps negative indices
     if (col < 0) col += W;
+    if ((uint64_t)r >= (uint64_t)H || (uint64_t)col >= (uint64_t)W) {
+      // torch raises IndexError here (2d_net/model.py:131-137); a kernel cannot: zero row + sticky error word 1
+      out[i] = T(0.f);
+      if (ch == 0) mm3d_raise(err, 1);
+      continue;
+    }
     out[i] = fmap[((int64_t)b * C + ch) * hw + r * W + col];
   }
 }
@@ -113,7 +121,7 @@ __device__ __forceinline__ void lift_atomic_add(__nv_bfloat16* p, __nv_bfloat16 
 template <class T>
 __global__ void k_lift_bwd(const T* __restrict__ d_out, int B, int C, int H, int W,
                            const int64_t* __restrict__ idx, const int64_t* __restrict__ offs, int64_t n,
-                           T* __restrict__ d_fmap) {
+                           T* __restrict__ d_fmap, int* err) {
   const int64_t total = n * C;
   const int64_t hw = (int64_t)H * W;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -123,6 +131,10 @@ __global__ void k_lift_bwd(const T* __restrict__ d_out, int B, int C, int H, int
     int64_t r = __ldg(idx + 2 * p), col = __ldg(idx + 2 * p + 1);
     if (r < 0) r += H;
     if (col < 0) col += W;
+    if ((uint64_t)r >= (uint64_t)H || (uint64_t)col >= (uint64_t)W) {  // skipped + sticky error word 1
+      if (ch == 0) mm3d_raise(err, 1);
+      continue;
+    }
     lift_atomic_add(d_fmap + ((int64_t)b * C + ch) * hw + r * W + col, d_out[i]);
   }
 }
@@ -184,11 +196,12 @@ extern "C" int mm3d_lift2d_fwd(const void* fmap, int dtype, int B, int C, int H,
   cudaStream_t stream = (cudaStream_t)stream_;
   MM3D_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && n >= 0, MM3D_ERR_INVALID, "bad lift sizes");
   if (n == 0) return MM3D_OK;
+  int* err = mm3d_device_err_flag();
   const int grid = mm3d_grid(n * C, 256);
   switch (dtype) {
-    case 0: k_lift_fwd<float><<<grid, 256, 0, stream>>>((const float*)fmap, B, C, H, W, idx, sample_offsets, n, (float*)out); break;
-    case 1: k_lift_fwd<__half><<<grid, 256, 0, stream>>>((const __half*)fmap, B, C, H, W, idx, sample_offsets, n, (__half*)out); break;
-    case 2: k_lift_fwd<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)fmap, B, C, H, W, idx, sample_offsets, n, (__nv_bfloat16*)out); break;
+    case 0: k_lift_fwd<float><<<grid, 256, 0, stream>>>((const float*)fmap, B, C, H, W, idx, sample_offsets, n, (float*)out, err); break;
+    case 1: k_lift_fwd<__half><<<grid, 256, 0, stream>>>((const __half*)fmap, B, C, H, W, idx, sample_offsets, n, (__half*)out, err); break;
+    case 2: k_lift_fwd<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)fmap, B, C, H, W, idx, sample_offsets, n, (__nv_bfloat16*)out, err); break;
     default: MM3D_REQUIRE(false, MM3D_ERR_UNSUPPORTED, "lift dtype %d (0=f32,1=f16,2=bf16)", dtype);
   }
   mm3d_count_launches(1);
@@ -201,11 +214,12 @@ extern "C" int mm3d_lift2d_bwd(const void* d_out, int dtype, int B, int C, int H
   cudaStream_t stream = (cudaStream_t)stream_;
   MM3D_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && n >= 0, MM3D_ERR_INVALID, "bad lift sizes");
   if (n == 0) return MM3D_OK;
+  int* err = mm3d_device_err_flag();
   const int grid = mm3d_grid(n * C, 256);
   switch (dtype) {
-    case 0: k_lift_bwd<float><<<grid, 256, 0, stream>>>((const float*)d_out, B, C, H, W, idx, sample_offsets, n, (float*)d_fmap); break;
-    case 1: k_lift_bwd<__half><<<grid, 256, 0, stream>>>((const __half*)d_out, B, C, H, W, idx, sample_offsets, n, (__half*)d_fmap); break;
-    case 2: k_lift_bwd<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)d_out, B, C, H, W, idx, sample_offsets, n, (__nv_bfloat16*)d_fmap); break;
+    case 0: k_lift_bwd<float><<<grid, 256, 0, stream>>>((const float*)d_out, B, C, H, W, idx, sample_offsets, n, (float*)d_fmap, err); break;
+    case 1: k_lift_bwd<__half><<<grid, 256, 0, stream>>>((const __half*)d_out, B, C, H, W, idx, sample_offsets, n, (__half*)d_fmap, err); break;
+    case 2: k_lift_bwd<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)d_out, B, C, H, W, idx, sample_offsets, n, (__nv_bfloat16*)d_fmap, err); break;
     default: MM3D_REQUIRE(false, MM3D_ERR_UNSUPPORTED, "lift dtype %d (0=f32,1=f16,2=bf16)", dtype);
   }
   mm3d_count_launches(1);

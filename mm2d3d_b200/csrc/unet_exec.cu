@@ -27,11 +27,11 @@
 int mm3d_bnrelu_fwd_impl(const float* x, const float* x_hi, int c_lo, float* y, int64_t n, int c, const float* gamma,
                          const float* beta, float* running_mean, float* running_var, float* save_mean,
                          float* save_invstd, float eps, float momentum, float leakiness, int training, void* ws,
-                         size_t ws_bytes, bool ws_clean, cudaStream_t stream);
+                         size_t ws_bytes, bool ws_clean, int round_tf32, cudaStream_t stream);
 int mm3d_bnrelu_bwd_impl(const float* x, const float* x_hi, int c_lo, const float* dy, float* dx, float* dx_hi,
                          int64_t n, int c, const float* gamma, const float* beta, const float* save_mean,
                          const float* save_invstd, float* d_gamma, float* d_beta, float leakiness, int training,
-                         void* ws, size_t ws_bytes, bool ws_clean, cudaStream_t stream);
+                         void* ws, size_t ws_bytes, bool ws_clean, int round_flags, cudaStream_t stream);
 
 // conv_tc.cu
 size_t mm3d_conv_tc_workspace_bytes(int c_in, int c_out, int K);
@@ -153,20 +153,38 @@ __global__ void k_concat2(const float* __restrict__ a, const float* __restrict__
   }
 }
 
-__global__ void k_pad_cols(const float* __restrict__ src, int64_t n, int c_src, float* __restrict__ dst, int c_dst) {
+__global__ void k_pad_cols(const float* __restrict__ src, int64_t n, int c_src, float* __restrict__ dst, int c_dst,
+                           int round_tf32) {
   mm3d_griddep_launch();
   mm3d_griddep_wait();
-  // dst[r, j] = j < c_src ? src[r, j] : 0   (c_dst >= c_src: pad;  c_dst < c_src: slice)
+  // dst[r, j] = j < c_src ? src[r, j] : 0   (c_dst >= c_src: pad;  c_dst < c_src: slice); optionally RNA-rounded to
+  // TF32 (the padded stem input is the A operand of a kind::tf32 MMA)
   const int64_t total = n * c_dst;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / c_dst;
     const int j = (int)(i - r * c_dst);
-    dst[i] = j < c_src ? __ldg(src + r * c_src + j) : 0.f;
+    float v = j < c_src ? __ldg(src + r * c_src + j) : 0.f;
+    if (round_tf32) v = mm3d_rna_tf32(v);
+    dst[i] = v;
   }
 }
 
+// out = RNA-rounded-to-TF32(in), whole float4s + tail (module-by-module path: operands of a TF32 convolution that
+// were not produced by one of this library's rounding producers)
+__global__ void k_round_tf32(const float* __restrict__ in, float* __restrict__ out, int64_t n) {
+  mm3d_griddep_launch();
+  mm3d_griddep_wait();
+  const int64_t nv = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    v.x = mm3d_rna_tf32(v.x); v.y = mm3d_rna_tf32(v.y); v.z = mm3d_rna_tf32(v.z); v.w = mm3d_rna_tf32(v.w);
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[(nv << 2) + threadIdx.x] = mm3d_rna_tf32(__ldg(in + (nv << 2) + threadIdx.x));
+}
+
 __global__ void k_split_add(const float* __restrict__ dj, int ldj, const float* __restrict__ add, int64_t n, int p,
-                            float* __restrict__ dy, float* __restrict__ df) {
+                            float* __restrict__ dy, float* __restrict__ df, int round_tf32) {
   mm3d_griddep_launch();
   mm3d_griddep_wait();
   // dy = dj[:, :p] + add ; df = dj[:, p:]   (dj rows are ldj floats apart; df only with ldj == 2p)
@@ -178,7 +196,9 @@ __global__ void k_split_add(const float* __restrict__ dj, int ldj, const float* 
       const int j = (int)(i - r * pv) << 2;
       const float4 a = __ldg(reinterpret_cast<const float4*>(dj + r * ldj + j));
       const float4 b = __ldg(reinterpret_cast<const float4*>(add + r * p + j));
-      *reinterpret_cast<float4*>(dy + r * p + j) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      float4 o = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      if (round_tf32) { o.x = mm3d_rna_tf32(o.x); o.y = mm3d_rna_tf32(o.y); o.z = mm3d_rna_tf32(o.z); o.w = mm3d_rna_tf32(o.w); }
+      *reinterpret_cast<float4*>(dy + r * p + j) = o;
       if (df) *reinterpret_cast<float4*>(df + r * p + j) = __ldg(reinterpret_cast<const float4*>(dj + r * ldj + p + j));
     }
     return;
@@ -187,7 +207,8 @@ __global__ void k_split_add(const float* __restrict__ dj, int ldj, const float* 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / p;
     const int j = (int)(i - r * p);
-    dy[i] = __ldg(dj + r * ldj + j) + __ldg(add + i);
+    const float o = __ldg(dj + r * ldj + j) + __ldg(add + i);
+    dy[i] = round_tf32 ? mm3d_rna_tf32(o) : o;
     if (df) df[i] = __ldg(dj + r * ldj + p + j);
   }
 }
@@ -250,12 +271,17 @@ cudaStream_t wgrad_stream(Ctx& c) {
   return c.side->stream;
 }
 
-// Timing experiments only (results are garbage, never set in tests or by the bench): MM3D_ABL_SKIP lists kernel
-// families the executor does not launch -- any of "bn", "wgrad", "conv" (forward + dgrad).
+// Timing experiments only: a library built with -DMM3D_ABLATION reads MM3D_ABL_SKIP, a list of kernel families the
+// executor then does not launch (any of "bn", "wgrad", "conv" = forward + dgrad); results are garbage.  The
+// product build has no such switch.
+#ifdef MM3D_ABLATION
 bool abl_skip(const char* what) {
   static const char* e = getenv("MM3D_ABL_SKIP");
   return e && strstr(e, what) != nullptr;
 }
+#else
+constexpr bool abl_skip(const char*) { return false; }
+#endif
 
 #define EX(call)                   \
   do {                             \
@@ -267,17 +293,24 @@ float* Gp(Ctx& c, int i) { return (float*)c.grads[i]; }
 
 // x_hi != NULL: the input is the column blocks [x | x_hi] ([n, c_lo] and [n, ch - c_lo]) -- JoinTable without
 // materialising the concatenation (training mode only)
+// Tensor-core modes: every tensor that a kind::tf32 MMA reads as its gathered operand (activations in forward and
+// wgrad, d_out in dgrad and wgrad) is stored RNA-rounded to TF32 by the kernel that PRODUCES it, so that the
+// tensor core's truncation of the low mantissa bits is exact.  `to_conv`: the output feeds a convolution.
+bool tc_mode(const Ctx& c) { return c.net->mode != MM3D_MODE_FP32; }
+
 void bn_fwd(Ctx& c, int pidx, const float* x, float* y, int64_t n, int ch, float* save, const float* x_hi = nullptr,
-            int c_lo = 0) {
+            int c_lo = 0, bool to_conv = true) {
   if (abl_skip("bn")) return;
   EX(mm3d_bnrelu_fwd_impl(x, x_hi, c_lo, y, n, ch, P(c, pidx), P(c, pidx + 1), (float*)c.params[pidx + 2], (float*)c.params[pidx + 3],
-                          save, save + ch, c.eps, c.momentum, 0.f, c.training, c.bn_ws, c.bn_ws_bytes, true, c.stream));
+                          save, save + ch, c.eps, c.momentum, 0.f, c.training, c.bn_ws, c.bn_ws_bytes, true,
+                          tc_mode(c) && to_conv ? 1 : 0, c.stream));
 }
+// round: bit 0 = dx (its low column block when split) feeds a convolution as d_out, bit 1 = dx_hi does
 void bn_bwd(Ctx& c, int pidx, const float* x, const float* dy, float* dx, int64_t n, int ch, const float* save,
-            const float* x_hi = nullptr, int c_lo = 0, float* dx_hi = nullptr) {
+            int round, const float* x_hi = nullptr, int c_lo = 0, float* dx_hi = nullptr) {
   if (abl_skip("bn")) return;
   EX(mm3d_bnrelu_bwd_impl(x, x_hi, c_lo, dy, dx, dx_hi, n, ch, P(c, pidx), P(c, pidx + 1), save, save + ch, Gp(c, pidx), Gp(c, pidx + 1), 0.f,
-                          c.training, c.bn_ws, c.bn_ws_bytes, true, c.stream));
+                          c.training, c.bn_ws, c.bn_ws_bytes, true, tc_mode(c) ? round : 0, c.stream));
 }
 enum Kind { SMC, DOWN, UP };
 
@@ -317,7 +350,7 @@ void conv_bwd(Ctx& c, Kind kind, int l, const float* in, int c_in, const float* 
   const float* im = find_img(c, w);   // prebuilt dgrad image (tensor-core modes)
   // parameter gradients inside the caller's (pre-zeroed) flat buffer accumulate; temporaries are overwritten
   const int acc = c.wgrad_acc && c.grad_lo <= (const char*)d_w && (const char*)d_w < c.grad_hi;
-  const bool do_wg = !abl_skip("wgrad"), do_dg = !abl_skip("conv");
+  const bool do_wg = !abl_skip("wgrad") && d_w != nullptr, do_dg = !abl_skip("conv");  // (frozen weight: no d_w)
   if (kind == SMC) {
     if (do_wg)
       EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, f.n, c_out, d_w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap, acc,
@@ -361,9 +394,9 @@ void launch_copy_cols(Ctx& c, const float* src, int64_t n, int c_src, float* dst
   if (mm3d_launch_pdl(k_copy_cols, dim3(mm3d_grid(n * ncols / 4 + 1, 256)), dim3(256), 0, c.stream, src, n, c_src, dst, c_dst, col0, ncols, 0) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
   mm3d_count_launches(1);
 }
-void launch_pad_cols(Ctx& c, const float* src, int64_t n, int c_src, float* dst, int c_dst) {
+void launch_pad_cols(Ctx& c, const float* src, int64_t n, int c_src, float* dst, int c_dst, bool round_tf32 = false) {
   if (n == 0 || c.rc) return;
-  if (mm3d_launch_pdl(k_pad_cols, dim3(mm3d_grid(n * c_dst, 256)), dim3(256), 0, c.stream, src, n, c_src, dst, c_dst) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
+  if (mm3d_launch_pdl(k_pad_cols, dim3(mm3d_grid(n * c_dst, 256)), dim3(256), 0, c.stream, src, n, c_src, dst, c_dst, round_tf32 ? 1 : 0) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
   mm3d_count_launches(1);
 }
 
@@ -485,9 +518,9 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
     float* d_F = g.f(n, p);
     float* d_Yskip = g.f(n, p);
     if (split) {
-      bn_bwd(c, post, B.Y, d_G, d_J, n, 2 * p, B.s_post, B.F, p, d_F);
+      bn_bwd(c, post, B.Y, d_G, d_J, n, 2 * p, B.s_post, 2, B.F, p, d_F);  // d_F is the deconvolution's d_out
     } else {
-      bn_bwd(c, post, B.J, d_G, d_J, n, 2 * p, B.s_post);
+      bn_bwd(c, post, B.J, d_G, d_J, n, 2 * p, B.s_post, 0);  // (eval-mode backward: d_F stays unrounded)
       // d_F = d_J[:, p:]; the skip half is combined with the branch gradient further down
       if (n && !c.rc) {
         if (mm3d_launch_pdl(k_copy_cols, dim3(mm3d_grid(n * p / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)d_J, n, 2 * p, d_F, p, 0, p, p) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
@@ -497,23 +530,23 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
     float* d_E = g.f(nc, q);
     conv_bwd(c, UP, l, B.E, q, d_F, p, P(c, up + 4), d_E, Gp(c, up + 4));
     float* d_Rn = g.f(nc, q);
-    bn_bwd(c, up, net.b[l + 1].R, d_E, d_Rn, nc, q, B.s_up);
+    bn_bwd(c, up, net.b[l + 1].R, d_E, d_Rn, nc, q, B.s_up, 1);
     float* d_Xn = g.f(nc, q);
     level_bwd(c, g, l + 1, deeper, d_Rn, d_Xn);
     float* d_B = g.f(n, p);
     conv_bwd(c, DOWN, l, B.B, p, d_Xn, q, P(c, dn + 4), d_B, Gp(c, dn + 4));
     float* d_Ybr = g.f(n, p);
-    bn_bwd(c, dn, B.Y, d_B, d_Ybr, n, p, B.s_dn);
+    bn_bwd(c, dn, B.Y, d_B, d_Ybr, n, p, B.s_dn, 0);  // summed with the skip gradient below, rounded there
     // d_Y = d_J[:, :p] + d_Ybr
     if (n && !c.rc) {
-      if (mm3d_launch_pdl(k_split_add, dim3(mm3d_grid(n * p / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)d_J, split ? p : 2 * p, (const float*)d_Ybr, n, p, d_Yskip, (float*)nullptr) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
+      if (mm3d_launch_pdl(k_split_add, dim3(mm3d_grid(n * p / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)d_J, split ? p : 2 * p, (const float*)d_Ybr, n, p, d_Yskip, (float*)nullptr, tc_mode(c) ? 1 : 0) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
       mm3d_count_launches(1);
     }
     d_Y = d_Yskip;
   }
   float* d_A = g.f(n, p);
   conv_bwd(c, SMC, l, B.A, p, d_Y, p, P(c, pbase + 4), d_A, Gp(c, pbase + 4));
-  bn_bwd(c, pbase, B.X, d_A, d_X, n, p, B.s_pre);
+  bn_bwd(c, pbase, B.X, d_A, d_X, n, p, B.s_pre, 1);
   if (!c.side) g.off = mark;  // temporaries of this level are dead once d_X is written -- unless the side stream
                               // may still be reading a d_out (the workspace bound assumes no reuse anyway)
 }
@@ -629,16 +662,20 @@ MM3D_API int mm3d_unet_forward(int in_channels, int m, int num_planes, int mode,
   const float* w_stem = P(c, 0);
   if (net.cin_k != net.cin) {
     // tensor-core modes gather whole 16-byte pieces: pad features and stem weight with zero channels
-    launch_pad_cols(c, net.V, n0, net.cin, net.Vp, net.cin_k);
+    launch_pad_cols(c, net.V, n0, net.cin, net.Vp, net.cin_k, /*round_tf32=*/true);
     float* wp = wp_buf;
     launch_pad_cols(c, w_stem, 27, net.cin * m, wp, net.cin_k * m);
     w_stem = wp;
+  } else if (tc_mode(c) && n0 > 0 && !c.rc) {
+    // (stem input already a whole number of 64-byte pieces: round the InputLayer output in place)
+    if (mm3d_launch_pdl(k_round_tf32, dim3(mm3d_grid(n0 * net.cin / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)net.V, net.V, n0 * (int64_t)net.cin) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
+    mm3d_count_launches(1);
   }
   EX(build_images(c, false, w_stem));
   conv_fwd(c, SMC, 0, net.Vp, net.cin_k, net.b[0].X, m, w_stem);
   level_fwd(c, 0, 1);
   const int head = 1 + level_slots(0, net.L);
-  bn_fwd(c, head, net.b[0].R, net.Z, n0, m, net.s_head);
+  bn_fwd(c, head, net.b[0].R, net.Z, n0, m, net.s_head, nullptr, 0, /*to_conv=*/false);
   EX(mm3d_output_fwd(net.Z, p2v, n_points, m, out, c.stream));
   return c.rc;
 }
@@ -703,7 +740,7 @@ MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode
   float* d_Z = g.f(n0, m);
   EX(mm3d_output_bwd(d_out, p2v, n_points, n0, m, d_Z, c.stream));
   float* d_R0 = g.f(n0, m);
-  bn_bwd(c, head, net.b[0].R, d_Z, d_R0, n0, m, net.s_head);
+  bn_bwd(c, head, net.b[0].R, d_Z, d_R0, n0, m, net.s_head, 1);
   float* d_X0 = g.f(n0, m);
   level_bwd(c, g, 0, 1, d_R0, d_X0);
   // stem
@@ -712,10 +749,10 @@ MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode
   float* d_Vp = d_feats ? g.f(n0, net.cin_k) : nullptr;
   if (net.cin_k != net.cin) {
     float* wp = wp_buf;  // padded at the start of this call
-    float* d_wp = g.f(27, (int64_t)net.cin_k * m);
+    float* d_wp = d_w ? g.f(27, (int64_t)net.cin_k * m) : nullptr;  // (frozen stem weight: no gradient)
     conv_bwd(c, SMC, 0, net.Vp, net.cin_k, d_X0, m, wp, d_Vp, d_wp);
     join_side(c);  // d_wp comes from the side stream
-    launch_pad_cols(c, d_wp, 27, net.cin_k * m, d_w, net.cin * m);  // slice the real channels back out
+    if (d_w) launch_pad_cols(c, d_wp, 27, net.cin_k * m, d_w, net.cin * m);  // slice the real channels back out
     if (d_feats) {
       float* d_V = g.f(n0, net.cin);
       launch_pad_cols(c, d_Vp, n0, net.cin_k, d_V, net.cin);
@@ -728,6 +765,18 @@ MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode
   join_side(c);  // everything after this call on `stream` sees the weight gradients
   MM3D_REQUIRE(g.ok, MM3D_ERR_WORKSPACE, "backward workspace overflow");
   return c.rc;
+}
+
+// out[i] = in[i] rounded to TF32 (round-to-nearest, ties away); in == out allowed.  The module-by-module path uses
+// it on the operands of a TF32 convolution; the executor's producers round in place of it.
+MM3D_API int mm3d_round_tf32(const float* in, float* out, int64_t n, mm3d_stream_t stream_) {
+  MM3D_REQUIRE(n >= 0 && (n == 0 || (in && out)), MM3D_ERR_INVALID, "round_tf32: bad arguments");
+  MM3D_REQUIRE((((uintptr_t)in | (uintptr_t)out) & 15) == 0, MM3D_ERR_INVALID, "round_tf32: pointers must be 16-byte aligned");
+  if (n == 0) return MM3D_OK;
+  MM3D_CUDA(mm3d_launch_pdl(k_round_tf32, dim3(mm3d_grid(n / 4 + 1, 256)), dim3(256), 0, (cudaStream_t)stream_, in, out, n));
+  mm3d_count_launches(1);
+  MM3D_CHECK_LAUNCH("mm3d_round_tf32");
+  return MM3D_OK;
 }
 
 }  // extern "C"

@@ -86,6 +86,9 @@ class FlatGradAllReduce:
                 p.grad = view
                 off += p.numel()
             flat = self.flat
+        if flat.is_cuda and dist.get_backend(self.group) == "nccl":
+            # NCCL averages inside the collective: no separate scaling kernel
+            return dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
         flat.div_(world)
         return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
 

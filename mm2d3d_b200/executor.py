@@ -109,6 +109,9 @@ class UNetSCNFn(torch.autograd.Function):
         n_points = meta.n_points
         desc = _level_desc(meta, L, spatial0, plans=mode != _lib.MODE_FP32)
         with torch.cuda.device(dev):
+            # sticky device-error words (mapped host memory): whatever a kernel of an earlier call raised surfaces
+            # here -- no synchronisation, a few nanoseconds
+            _lib.raise_device_errors("UNetSCN.forward")
             act_bytes = lib.mm3d_unet_act_bytes(in_ch, m, L, mode, desc, n_points)
             act = torch.empty(act_bytes, dtype=torch.uint8, device=dev)
             scr = F.scratch(lib.mm3d_unet_scratch_bytes(in_ch, m, L, mode), dev)
@@ -130,6 +133,7 @@ class UNetSCNFn(torch.autograd.Function):
         n_points = meta.n_points
         need_feats = ctx.needs_input_grad[0]
         with torch.cuda.device(dev):
+            _lib.raise_device_errors("UNetSCN.backward")
             # one flat buffer for every parameter gradient; the returned grads are views into it
             numels = [t.numel() if t.requires_grad else 0 for t in slots]
             flat = torch.empty(sum(numels), dtype=torch.float32, device=dev)

@@ -134,6 +134,16 @@ def conv_tables(meta, kind: str, spatial_in: int, plans: bool = False):
     return (child, onehot, _lib.CONV_TRANSPOSE_W) if kind == "down" else (onehot, child, _lib.CONV_TRANSPOSE_W)
 
 
+def _tf32(t: torch.Tensor, inplace: bool = False) -> torch.Tensor:
+    """RNA-round a contiguous float32 tensor to TF32 (operands of the tensor-core convolutions: the MMA itself would
+    truncate).  The whole-network executor's producers store rounded values themselves; this is the module path."""
+    out = t if inplace else torch.empty_like(t)
+    if t.numel():
+        with torch.cuda.device(t.device):
+            check(lib.mm3d_round_tf32(ptr(t), ptr(out), t.numel(), _lib.stream_ptr()), "mm3d_round_tf32")
+    return out
+
+
 class TableConvFn(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
@@ -156,6 +166,8 @@ class TableConvFn(torch.autograd.Function):
             w = torch.nn.functional.pad(w, (0, 0, 0, pad))
             c_in += pad
         ctx.pad = pad
+        if m != _lib.MODE_FP32:
+            x = _tf32(x, inplace=bool(pad))  # (the saved x is the rounded one: wgrad reads the same operand)
         out = torch.empty(fwd_t.n_out, c_out, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             wsb = lib.mm3d_conv_workspace_bytes(fwd_t.n_in, fwd_t.n_out, c_in, c_out, K, m)
@@ -175,6 +187,8 @@ class TableConvFn(torch.autograd.Function):
         d_out = _f32c(d_out)
         K, c_in, c_out = w.shape[0], w.shape[-2], w.shape[-1]
         m = ctx.mode
+        if m != _lib.MODE_FP32:
+            d_out = _tf32(d_out)
         d_x = d_w = None
         with torch.cuda.device(x.device):
             stream = _lib.stream_ptr()

@@ -33,6 +33,10 @@ class LiftIndices:
         else:
             cat = np.zeros((0, 2), dtype=np.int64)
         self.counts = counts
+        # host-side bounds of the indices, so that lift2d can refuse an out-of-image index synchronously like the
+        # reference's advanced indexing does (IndexError), without reading anything back from the device
+        self.lo = (int(cat[:, 0].min()), int(cat[:, 1].min())) if len(cat) else (0, 0)
+        self.hi = (int(cat[:, 0].max()), int(cat[:, 1].max())) if len(cat) else (-1, -1)
         self.idx = torch.from_numpy(np.ascontiguousarray(cat)).to(device, non_blocking=True)
         self.offsets = torch.from_numpy(offs).to(device, non_blocking=True)
 
@@ -47,6 +51,10 @@ def lift2d(fmap: torch.Tensor, img_indices) -> torch.Tensor:
         img_indices = LiftIndices(img_indices, fmap.device)
     if len(img_indices.counts) != fmap.shape[0]:
         raise ValueError("lift2d: one index array per sample expected")
+    H, W = int(fmap.shape[2]), int(fmap.shape[3])
+    if img_indices.lo[0] < -H or img_indices.hi[0] >= H or img_indices.lo[1] < -W or img_indices.hi[1] >= W:
+        raise IndexError(f"lift2d: pixel index out of range for a {H}x{W} map "
+                         f"(rows {img_indices.lo[0]}..{img_indices.hi[0]}, columns {img_indices.lo[1]}..{img_indices.hi[1]})")
     return Lift2DFn.apply(fmap, img_indices.idx, img_indices.offsets)
 
 

@@ -417,12 +417,10 @@ def test_unetscn_full_config_one_scan():
 
 
 def _emulate_tf32_convs():
-    """Context manager: the CPU oracle's convolutions with TF32 operand rounding in forward and
-    dgrad (FP32 accumulate, FP32 wgrad) -- the arithmetic of the tcgen05 TF32 mode."""
+    """Context manager: the CPU oracle's convolutions with both operands of forward, dgrad AND wgrad rounded
+    to TF32 (round-to-nearest, ties away), FP32 accumulate -- the arithmetic of the tcgen05 TF32 mode (activations
+    and gradients are rounded where they are produced, weights inside the kernels)."""
     import contextlib
-
-    def trunc(t):
-        return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
 
     def rna(t):
         return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
@@ -433,16 +431,16 @@ def _emulate_tf32_convs():
             ctx.fn = fn
             ctx.save_for_backward(x, w)
             with torch.no_grad():
-                return fn(trunc(x), rna(w))
+                return fn(rna(x), rna(w))
 
         @staticmethod
         def backward(ctx, g):
             x, w = ctx.saved_tensors
             with torch.enable_grad():
                 xx = x.detach().requires_grad_(True)
-                (gx,) = torch.autograd.grad(ctx.fn(xx, rna(w.detach())), xx, trunc(g))
+                (gx,) = torch.autograd.grad(ctx.fn(xx, rna(w.detach())), xx, rna(g))
                 ww = w.detach().requires_grad_(True)
-                (gw,) = torch.autograd.grad(ctx.fn(x.detach(), ww), ww, g)
+                (gw,) = torch.autograd.grad(ctx.fn(rna(x.detach()), ww), ww, rna(g))
             return gx, gw, None
 
     @contextlib.contextmanager
@@ -465,11 +463,13 @@ def _emulate_tf32_convs():
 
 def test_unetscn_full_config_tf32():
     """Same network in the tcgen05 TF32 mode.  Forward: 1e-2 (north_star) against the FP64 oracle.
-    Whole-network GRADIENTS in TF32 are dominated by the arithmetic itself: the CPU oracle with its
-    convolution operands rounded to TF32 is ~1e-1 (relative L2) away from FP64 on this random-
-    initialised 60-layer BN/ReLU network (ReLU-mask flips), so the bar for the kernels is: no worse
-    than 1.5x the error of that TF32-emulating oracle, per tensor, and gradient direction preserved
-    (cosine > 0.97).  The per-op TF32 tests hold the strict 1e-2 per-op bar."""
+    Whole-network GRADIENTS of the FREE-RUNNING network (ReLU gates and batch statistics recomputed from
+    the perturbed activations) are dominated by gate flips: the CPU oracle with its convolution operands
+    rounded to TF32 is itself several 1e-2 (relative L2) away from FP64 on this randomly initialised
+    60-layer BN/ReLU network, so here the kernels are held to: no worse than 1.5x the error of that
+    TF32-emulating oracle, per tensor, and gradient direction preserved (cosine > 0.97).  north_star's
+    1e-2 on gradients is held directly, per tensor, by test_unetscn_gradients_with_frozen_gates (gates and
+    statistics pinned to the FP64 oracle's) and per op by test_conv_fwd_bwd / test_tf32_edge_sizes."""
     import copy
 
     import mm2d3d_b200.scn as scn
@@ -510,9 +510,10 @@ def test_unetscn_full_config_tf32():
         a64, b64 = a.detach().double().cpu().flatten(), g64[name].flatten()
         cos = float(torch.dot(a64, b64) / (a64.norm() * b64.norm()).clamp_min(1e-300))
         worst = max(worst, e_gpu)
+        print(f"[tf32 free-running] d {name:44s} rel-L2 {e_gpu:.2e} (TF32-emulating CPU oracle {e_emu:.2e})  cosine {cos:.5f}")
         assert e_gpu <= max(TOL["tf32"], 1.5 * e_emu), (name, e_gpu, e_emu)
         assert cos > 0.97, (name, cos)
-    print("worst whole-network gradient rel-L2 error in TF32 mode", worst)
+    print("worst whole-network gradient rel-L2 error in TF32 mode (free-running gates and statistics)", worst)
 
 
 def test_module_surface_matches_reference_usage():
@@ -845,3 +846,247 @@ def test_heads_reference_fixture():
     y2 = rgb_mask(x2, w.detach(), b.detach())
     ref = x2 * torch.sigmoid(x2 @ w.detach().t() + b.detach())
     assert float((y2 - ref).abs().max()) < 1e-6
+
+
+# ------------------------------------------------------------------------------ whole network, frozen gates
+def _bn_modules(net):
+    return [m for m in net.modules() if type(m).__name__ in ("BatchNormLeakyReLU", "BatchNormReLU")]
+
+
+def _freeze_gates(net, records, device, dtype, tensor_cls):
+    """Replace every BatchNorm+ReLU of `net` by the FROZEN map  y = gate * ((x - mean) * invstd * weight + bias)
+    with (mean, invstd, gate) taken from `records` (one per BN module, module order) as constants.  The network
+    becomes piecewise linear with fixed pieces: no ReLU-gate flips, no gradient through the batch statistics."""
+    import types
+    for m, (mean, invstd, gate) in zip(_bn_modules(net), records):
+        mean_d, invstd_d, gate_d = mean.to(device, dtype), invstd.to(device, dtype), gate.to(device, dtype)
+
+        def fwd(self, x, mean_d=mean_d, invstd_d=invstd_d, gate_d=gate_d):
+            y = ((x.features - mean_d) * (invstd_d * self.weight) + self.bias) * gate_d
+            return tensor_cls(y, x.metadata, x.spatial_size)
+        m.forward = types.MethodType(fwd, m)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_unetscn_gradients_with_frozen_gates(mode):
+    """north_star's tolerance on whole-network GRADIENTS, stated per tensor and held directly: 1e-4 (FP32 mode) /
+    1e-2 (TF32 mode), relative L2 AND max-abs-relative, against the FP64 oracle.
+
+    The free-running network cannot show this: one ReLU gate that flips under a 1e-3 perturbation changes its
+    gradient entry by O(1), and with batch statistics in the loop the FP32 CPU oracle itself is ~3e-3 away from
+    its FP64 run (test_unetscn_full_config_*).  Here the ReLU gates and the BatchNorm statistics of all 26
+    BatchNorm layers are taken from the FP64 oracle's forward and frozen in BOTH networks, so what is compared is
+    the chain of 27 sparse convolutions (forward, dgrad, wgrad), InputLayer and OutputLayer -- every kernel the
+    arithmetic mode touches -- over the whole depth of the network with its error accumulation, module by module
+    through the C ABI.  (The BatchNorm kernels are held to 1e-4 per op in test_bnrelu; the executor is tied to
+    this module path in test_fused_executor_matches_module_path.)"""
+    import copy
+
+    import mm2d3d_b200.scn as scn
+    from mm2d3d_b200.unet import UNetSCN
+    torch.manual_seed(8)
+    locs, feats = synth.make_batch("nuscenes", batch=1, seed0=6)
+    coords, feats = torch.from_numpy(locs), torch.from_numpy(feats)
+    net_ref = UNetSCN(in_channels=3, backend=scn_cpu)
+    with torch.no_grad():  # non-trivial affine parameters
+        for m in _bn_modules(net_ref):
+            m.weight.add_(0.2 * torch.randn_like(m.weight))
+            m.bias.add_(0.1 * torch.randn_like(m.bias))
+    net = UNetSCN(in_channels=3).to(DEV)
+    net.load_state_dict(net_ref.state_dict())
+    net.fused = False
+    net64 = copy.deepcopy(net_ref).double()
+
+    # 1) true FP64 forward: record statistics and gates of every BatchNorm layer
+    records, hooks = [], []
+
+    def hook(mod, inp, out):
+        x = inp[0].features.detach()
+        mean, var = x.mean(0), x.var(0, unbiased=False)
+        records.append((mean, 1.0 / torch.sqrt(var + mod.eps), (out.features.detach() > 0).to(x.dtype)))
+    for m in _bn_modules(net64):
+        hooks.append(m.register_forward_hook(hook))
+    with torch.no_grad():
+        out_true = net64([coords, feats.double()])
+    for h in hooks:
+        h.remove()
+    assert len(records) == 26
+
+    # 2) the frozen function in FP64 on the oracle (reference) and on the GPU in `mode`
+    _freeze_gates(net64, records, "cpu", torch.float64, scn_cpu.SparseConvNetTensor)
+    _freeze_gates(net, records, DEV, torch.float32, scn.SparseConvNetTensor)
+    x64 = feats.double().requires_grad_(True)
+    out64 = net64([coords, x64])
+    assert rel_err(out64, out_true) < 1e-12  # same statistics and gates: the frozen forward IS the true forward
+    g = torch.randn_like(out64)
+    p64 = dict(net64.named_parameters())
+    names = ["feats"] + list(p64)
+    g64 = dict(zip(names, torch.autograd.grad(out64, [x64] + list(p64.values()), g)))
+    scn.set_conv_mode(mode)
+    try:
+        x = feats.clone().to(DEV).requires_grad_(True)
+        out = net([coords.to(DEV), x])
+        p = dict(net.named_parameters())
+        gg = torch.autograd.grad(out, [x] + [p[k] for k in names[1:]], g.float().to(DEV))
+    finally:
+        scn.set_conv_mode("fp32")
+    _no_device_error()
+    tol = TOL[mode]
+    e_out = rel_err(out, out64)
+    assert e_out < tol, ("forward", e_out)
+    rows, worst = [], (0.0, 0.0, "")
+    for name, a in zip(names, gg):
+        e2, em = rel_l2(a, g64[name]), rel_err(a, g64[name])
+        rows.append((name, e2, em))
+        worst = max(worst, (max(e2, em), e2, name))
+    print(f"\n[{mode}] frozen-gate whole-network parity vs FP64 oracle: forward max-abs-rel {e_out:.2e}")
+    for name, e2, em in rows:
+        print(f"[{mode}]   d {name:44s} rel-L2 {e2:.2e}  max-abs-rel {em:.2e}")
+    for name, e2, em in rows:
+        assert e2 <= tol and em <= tol, (mode, name, e2, em)
+
+
+def test_frozen_parameters_backward():
+    """Gradient w.r.t. the features through a network whose parameters (all, or only BatchNorm / only the
+    convolutions) are frozen: the executor receives NULL gradient pointers for those slots."""
+    from mm2d3d_b200 import scn as scn_mod
+    from mm2d3d_b200.unet import UNetSCN
+    torch.manual_seed(4)
+    net = UNetSCN(in_channels=3, m=16, num_planes=4, full_scale=256).to(DEV)
+    locs, feats = synth.make_batch("nuscenes", batch=2, seed0=8)
+    locs[:, :3] //= 16
+    coords, feats = torch.from_numpy(locs).to(DEV), torch.from_numpy(feats).to(DEV)
+    g = torch.randn(locs.shape[0], 16, device=DEV)
+    for mode in ("fp32", "tf32"):
+        scn_mod.set_conv_mode(mode)
+        try:
+            net.requires_grad_(True)
+            x = feats.clone().requires_grad_(True)
+            full = torch.autograd.grad(net([coords, x]), [x] + list(net.parameters()), g)
+            named = list(dict(net.named_parameters()))
+            for frozen in ("all", "bn", "conv"):
+                for k, p_ in net.named_parameters():
+                    is_bn = p_.dim() == 1
+                    p_.requires_grad_(not (frozen == "all" or (frozen == "bn") == is_bn))
+                live = [p_ for p_ in net.parameters() if p_.requires_grad]
+                x2 = feats.clone().requires_grad_(True)
+                got = torch.autograd.grad(net([coords, x2]), [x2] + live, g)
+                torch.cuda.synchronize()
+                # same kernels as the all-trainable run: only the atomic accumulation order differs, amplified by the
+                # free-running BatchNorm/ReLU stack
+                bar = 5e-3 if mode == "fp32" else 2e-2
+                assert rel_l2(got[0], full[0]) < bar, (mode, frozen, rel_l2(got[0], full[0]))
+                want = {k: full[1 + i] for i, k in enumerate(named)}
+                name_of = {id(v): k for k, v in net.named_parameters()}
+                for p_, a in zip(live, got[1:]):
+                    assert rel_l2(a, want[name_of[id(p_)]]) < 2e-2, (mode, frozen, name_of[id(p_)])
+        finally:
+            scn_mod.set_conv_mode("fp32")
+            net.requires_grad_(True)
+    _no_device_error()
+
+
+class _ForeignUNet(torch.nn.Module):
+    """A host network assembled from the raw ``scn.*`` surface the way the reference's 3d_net/scn_unet.py:90-126 does
+    (five members layer1..layer5 called in sequence, InputLayer with its default prebuild of ONE level) -- i.e. NOT
+    mm2d3d_b200.unet.UNetSCN, so neither the whole-network executor nor the pre-built pyramid is involved and every
+    coarser level is built lazily by the first layer that needs it.  The reference file itself cannot run on the GPU
+    box (/root/reference does not travel, and it may not be copied); tests/test_oracle.py and tests/test_cabi.py load
+    the real file in the build container and pin that its module tree equals the one built here."""
+
+    def __init__(self, scn, in_channels, m, num_planes, full_scale):
+        super().__init__()
+        from mm2d3d_b200.unet import build_unet
+        self.layer1 = scn.InputLayer(3, full_scale, mode=4)
+        self.layer2 = scn.SubmanifoldConvolution(3, in_channels, m, 3, False)
+        self.layer3 = build_unet(scn, 1, [(i + 1) * m for i in range(num_planes)], False)
+        self.layer4 = scn.BatchNormReLU(m)
+        self.layer5 = scn.OutputLayer(3)
+
+    def forward(self, x):
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4, self.layer5):
+            x = layer(x)
+        return x
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_raw_scn_surface_forward_backward(mode):
+    """INTEGRATION.md option A on the GPU: forward AND backward of a network built from the raw scn.* modules
+    (reference call pattern, lazily built levels, coordinates left on the CPU) against the oracle."""
+    import mm2d3d_b200.scn as scn
+    torch.manual_seed(12)
+    kw = dict(in_channels=3, m=16, num_planes=5, full_scale=4096)
+    ref = _ForeignUNet(scn_cpu, **kw)
+    net = _ForeignUNet(scn, **kw).to(DEV)
+    net.load_state_dict(ref.state_dict())
+    locs, feats = synth.make_batch("nuscenes", batch=2, seed0=9)
+    keep = np.random.default_rng(1).random(locs.shape[0]) < 0.3
+    coords, feats = torch.from_numpy(locs[keep]), torch.from_numpy(feats[keep])
+    ref64 = __import__("copy").deepcopy(ref).double()
+    x64 = feats.double().requires_grad_(True)
+    out64 = ref64([coords, x64])
+    g = torch.randn_like(out64)
+    p64 = dict(ref64.named_parameters())
+    g64 = torch.autograd.grad(out64, [x64] + list(p64.values()), g)
+    scn.set_conv_mode(mode)
+    try:
+        x = feats.clone().to(DEV).requires_grad_(True)
+        out = net([coords, x])  # coords stay on the CPU as in scn_unet.py:131-137
+        gg = torch.autograd.grad(out, [x] + list(net.parameters()), g.float().to(DEV))
+    finally:
+        scn.set_conv_mode("fp32")
+    _no_device_error()
+    assert rel_err(out, out64) < TOL[mode]
+    # free-running BatchNorm/ReLU: gradients are compared by direction and size (see the frozen-gate test for the bar)
+    for (name, _), a, b in zip([("feats", None)] + list(p64.items()), gg, g64):
+        assert rel_l2(a, b) < (2e-2 if mode == "fp32" else 0.3), (name, rel_l2(a, b))
+    for (k, a), (_, b) in zip(net.named_buffers(), ref64.named_buffers()):
+        assert rel_err(a, b) < max(TOL[mode], 1e-4), k
+
+
+def test_unetscn_semantickitti_shaped_scan():
+    """BASELINE configs[3] shape: one SemanticKITTI-shaped scan (~120 k points) through the whole network, FP32
+    mode against the oracle (forward 1e-4; gradients relative to the FP32 CPU oracle's own error, as for nuScenes),
+    then the TF32 executor against the FP32 one on the same scan (forward 1e-2)."""
+    import mm2d3d_b200.scn as scn
+    from mm2d3d_b200.unet import UNetSCN
+    torch.manual_seed(15)
+    locs, feats = synth.make_batch("semantickitti", batch=1, seed0=2)
+    assert locs.shape[0] > 90_000
+    net_ref = UNetSCN(in_channels=3, backend=scn_cpu)
+    net = UNetSCN(in_channels=3).to(DEV)
+    net.load_state_dict(net_ref.state_dict())
+    worst = _run_pair(net_ref, net, torch.from_numpy(locs), torch.from_numpy(feats), TOL["fp32"])
+    print("SemanticKITTI-shaped scan: worst gradient error relative to the FP32 CPU oracle's own error", worst)
+    c, f = torch.from_numpy(locs).to(DEV), torch.from_numpy(feats).to(DEV)
+    with torch.no_grad():
+        net.eval()
+        a = net([c, f])
+        scn.set_conv_mode("tf32")
+        try:
+            b = net([c, f])
+        finally:
+            scn.set_conv_mode("fp32")
+    _no_device_error()
+    assert rel_err(b, a) < TOL["tf32"]
+
+
+def test_lift2d_out_of_image_index_raises():
+    from mm2d3d_b200 import _lib
+    from mm2d3d_b200.functional import Lift2DFn
+    from mm2d3d_b200.lift import LiftIndices, lift2d
+    fmap = torch.randn(2, 4, 10, 12, device=DEV)
+    good = [np.array([[0, 0], [9, 11], [-1, -12]]), np.array([[3, 4]])]
+    assert lift2d(fmap, good).shape == (4, 4)
+    for bad in ([np.array([[10, 0]]), np.array([[0, 0]])], [np.array([[0, 0]]), np.array([[0, 12]])],
+                [np.array([[-11, 0]]), np.array([[0, 0]])]):
+        with pytest.raises(IndexError):  # synchronous, like the reference's advanced indexing (2d_net/model.py:131-137)
+            lift2d(fmap, bad)
+    # the kernels bound-check too (a caller of the C ABI gets a zero row and the sticky error bit, no wild access)
+    li = LiftIndices([np.array([[0, 0], [10, 3]]), np.array([[2, 2]])], DEV)
+    torch.cuda.synchronize()
+    _lib.lib.mm3d_take_device_error()
+    out = Lift2DFn.apply(fmap, li.idx, li.offsets)
+    torch.cuda.synchronize()
+    assert _lib.lib.mm3d_take_device_error() & 2
+    assert float(out[1].abs().max()) == 0.0 and torch.equal(out[0], fmap[0, :, 0, 0])
