@@ -2,21 +2,24 @@
 //
 //   dW[k][ci][co] = sum_j in[tbl(j,k)][ci] * dout[j][co]
 //
-// Per tile of 128 output rows (plan order) and NON-EMPTY offset k this is
-//   dW[k]^T [co x ci] += G_tile^T [co x 128] . A_{tile,k} [128 x ci]
-// G_tile = the tile's 128 dout rows, A = the gathered, zero-filled input rows -- the same stage the
-// forward kernel builds, here with the 32-byte-granule swizzle that MN-major tf32 operands require
-// (SWIZZLE_128B_BASE32B).  Both operands are MN-major: the MMA's K dimension is the tile's rows
-// (16 tcgen05.mma of K=8 per stage), M = C_out (64 or 128 accumulator rows, taken from the dout
-// tile in 32-wide blocks), N = the stage's 32 (or 16) input channels.  Every (offset, channel block)
-// owns TMEM columns for the whole kernel; a CTA covers a group of offsets whose accumulators fit the
-// 512 columns and a slice of the tiles, skips tiles without any of its offsets, and adds its
-// accumulators to dW once at the end (atomics).  Offsets are dealt to groups by class (centre, faces,
-// edges, corners); how many CTAs a group gets is decided in the kernel from the plan's per-offset tile
-// counts, so the CTAs carry equal work whatever the geometry of the scans.
+// Per tile of 128 output rows (plan order) and NON-EMPTY offset k this is one small GEMM whose reduction
+// runs over the tile's rows:
+//   dW[k] [ci x co] += A_{tile,k}^T [ci x 128] . G_tile [128 x co]
+// A = the gathered, zero-filled input rows (the stage the forward kernel builds, here with the
+// 32-byte-granule swizzle that MN-major tf32 operands require, SWIZZLE_128B_BASE32B), G = the tile's 128
+// dout rows.  Both operands are MN-major; the MMA's K dimension is the tile's rows (16 tcgen05.mma of K = 8
+// per item), M = the gathered input channels (64 or 128 accumulator lanes; c_in > 128 is cut into two
+// M-blocks), N = c_out.  An accumulator therefore costs c_out TMEM columns per offset (not c_in, as with the
+// roles the other way round): the decoder layers (c_in = 2 c_out) keep twice as many offsets resident.  A CTA
+// covers a GROUP of offsets whose accumulators fit the 512 columns -- all 27 for the 16-channel layers -- and
+// the dout tile is loaded once per (tile, group).  ONE pipeline item = (tile, offset, M-block) with all its
+// channel blocks: 16 MMAs of M x c_out x 8 per hand-shake.  Accumulators stay in TMEM for the whole kernel
+// and are added to dW once at the end, each lane (= input channel) flushing its contiguous c_out floats with
+// red.global.add.v4.f32.  Offsets are dealt to groups by class (centre, faces, edges, corners); how many
+// CTAs a group gets is decided in the kernel from the plan's per-offset tile counts.
 //
-// Warp roles (S+7 warps): 0..S-1 gather producers (warp w owns ring stage w), S..S+3 epilogue
-// (TMEM -> atomics), S+4 MMA issuer + TMEM allocator, S+5 / S+6 dout-tile loaders (64 rows each).
+// Warp roles (13 warps): 0..7 producers (each owns 16 rows of every stage: gathers A, and the dout tile when
+// a new tile starts), 8..11 epilogue (TMEM -> red.add), 12 MMA issuer + TMEM allocator.
 #include <cstdlib>
 #include "plan.cuh"
 #include "tc_common.cuh"
@@ -26,11 +29,12 @@ namespace {
 using namespace tc;
 
 constexpr int kTileM = 128;
-constexpr int kStageBytes = kTileM * 128;
-constexpr int kEntBytes = kTileM * 4;
+constexpr int kBlockBytes = kTileM * 128;  // one 32-channel block of 128 rows
 constexpr int kMaxStages = 6;
 constexpr int kMaxGBufs = 4;
-constexpr int kMaxThreads = (kMaxStages + 7) * 32;
+constexpr int kProducers = 8;              // producer warps; each owns 128 / 8 = 16 rows of every item
+constexpr int kRowsPerWarp = kTileM / kProducers;
+constexpr int kThreads = (kProducers + 5) * 32;
 
 struct WgParams {
   const float* in;
@@ -43,8 +47,13 @@ struct WgParams {
   const int32_t* tbl;
   int64_t tstride;
   int c_in, c_out, K;
-  int nb, last_w;   // channel blocks per offset, 16-byte chunks of the last one (8 or 4)
-  int mw;           // UMMA M: 64 (c_out <= 64) or 128
+  int nmb;          // M-blocks per offset: 1, or 2 when c_in > 128
+  int cm;           // input channels per M-block = c_in / nmb
+  int nbi;          // 32-channel shared-memory blocks of one item = ceil(cm / 32)
+  int last_w;       // 16-byte chunks of an item's last block (8, or 4 when cm % 32 == 16)
+  int mm;           // UMMA M: 64 (cm <= 64) or 128
+  int gblocks;      // 32-channel blocks of the dout tile = ceil(c_out / 32)
+  int g_last_w;     // 16-byte chunks of its last block
   int S, gbufs;
   int num_tiles, tmem_cols;
   int n_local;      // tiles per CTA (upper bound: every group gets at least ceil(num_tiles / n_local) CTAs)
@@ -66,7 +75,7 @@ struct TileWalk {
     }
     m = 0;
   }
-  __device__ __forceinline__ void init(const WgParams& p, const uint32_t* local_masks, int n_loc) {
+  __device__ __forceinline__ void init(const uint32_t* local_masks, int n_loc) {
     lmask = local_masks; n_local = n_loc; lt = 0; tile = 0;
     seek();
   }
@@ -74,35 +83,63 @@ struct TileWalk {
   __device__ __forceinline__ void next_tile() { ++lt; seek(); }
 };
 
-// items = (tile, offset, channel block) over TileWalk
+// items = (tile, offset, M-block) over TileWalk
 struct ItemWalk {
   TileWalk t;
-  int nb, k, j;
+  int nmb, k, h;
   uint32_t rem;
+  bool first;  // first item of its tile (the dout tile is loaded with it)
   __device__ __forceinline__ void init(const WgParams& p, const uint32_t* local_masks, int n_loc) {
-    t.init(p, local_masks, n_loc); nb = p.nb; j = 0; rem = t.m; k = rem ? __ffs(rem) - 1 : 0;
+    t.init(local_masks, n_loc); nmb = p.nmb; h = 0; rem = t.m; k = rem ? __ffs(rem) - 1 : 0; first = true;
   }
   __device__ __forceinline__ bool valid() const { return t.valid(); }
   __device__ __forceinline__ void next() {
-    if (++j < nb) return;
-    j = 0;
+    first = false;
+    if (++h < nmb) return;
+    h = 0;
     rem &= rem - 1;
-    if (!rem) { t.next_tile(); rem = t.m; }
+    if (!rem) { t.next_tile(); rem = t.m; first = true; }
     k = rem ? __ffs(rem) - 1 : 0;
   }
 };
 
-__global__ void __launch_bounds__(kMaxThreads, 1)
+// 16 rows x (one 32-channel block) of a stage: row r of the block receives chunks [0, W) of the source row
+// `rowv` of lane (r - row0) (or zeros when negative).  W = 8: 8 lanes per row, 4 rows per pass, 4 passes;
+// W = 4: 4 lanes per row, 8 rows per pass, 2 passes.
+template <int W>
+__device__ __forceinline__ void gather16(uint32_t block_base, int row0, int rowv, const float* __restrict__ base,
+                                         const float* __restrict__ src0, uint32_t row_floats, int lane) {
+  constexpr int kRowsPerPass = 32 / W, kPasses = kRowsPerWarp / kRowsPerPass;
+  const int c = lane & (W - 1), rsub = lane / W;
+#pragma unroll
+  for (int u = 0; u < kPasses; ++u) {
+    const int rl = u * kRowsPerPass + rsub;
+    const int row = __shfl_sync(0xffffffffu, rowv, rl);
+    const int r = row0 + rl;
+    const bool ok = row >= 0;
+    cp_async16(block_base + (uint32_t)r * 128u + swz_base32(c, r), ok ? src0 + (size_t)(uint32_t)row * row_floats + c * 4 : base,
+               ok ? 16u : 0u);
+  }
+}
+
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
 k_wgrad_tc(const WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int S = p.S;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_bytes = (uint32_t)p.nbi * kBlockBytes;      // one stage: the item's channel blocks, LBO apart
+  const uint32_t g_bytes = (uint32_t)p.gblocks * kBlockBytes;  // dout tile: blocks of [128 rows][32 channels]
   const uint32_t a_base = smem_base;
-  const uint32_t g_bytes = (uint32_t)(p.mw / 32) * kStageBytes;  // dout tile: mw/32 blocks of [128 rows][32 channels]
-  const uint32_t g_base = a_base + (uint32_t)S * kStageBytes;
-  const uint32_t e_base = g_base + (uint32_t)p.gbufs * g_bytes;
-  const uint32_t m_base = e_base + (uint32_t)(S + 1) * kEntBytes;  // (mask & group) and index of this CTA's tiles
+  // (an M = 64 operand reads 2 blocks even when the item has one: the block past the stage is the next stage or the
+  // first dout buffer, and only feeds accumulator lanes >= cm, which nobody reads; M = 128 items have 3 or 4 blocks
+  // and the same holds for the 4th)
+  const uint32_t g_base = a_base + (uint32_t)S * a_bytes;
+  const uint32_t m_base = g_base + (uint32_t)p.gbufs * g_bytes;  // (mask & group) and index of this CTA's tiles
   const uint32_t bar_base = m_base + (((uint32_t)p.n_local * 8u + 15u) & ~15u);
   uint32_t* lmask = reinterpret_cast<uint32_t*>(smem + (m_base - smem_base));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar_base - smem_base));
@@ -119,8 +156,8 @@ k_wgrad_tc(const WgParams p) {
   mm3d_griddep_launch();
   mm3d_griddep_wait();  // (everything below reads the plan; the wgrad stream's kernels follow each other closely)
   // ---- CTAs -> offset groups in proportion to the groups' work, from the plan's per-offset tile counts
-  // (every CTA computes the same table; lane g of warp 0 owns group g): cost = 2 nb * sum_k tiles(k) for the
-  // gathers and MMAs + 3 * max_k tiles(k) for the dout tiles.
+  // (every CTA computes the same table; lane g of warp 0 owns group g): cost = nbi nmb * sum_k tiles(k) for the
+  // gathers and MMAs + gblocks * max_k tiles(k) for the dout tiles.
   __shared__ int s_cta0[33];
   if (warp == 0) {
     const int nctas = (int)gridDim.x;
@@ -132,7 +169,7 @@ k_wgrad_tc(const WgParams p) {
         sum += c;
         mx = max(mx, c);
       }
-      cost = (float)(2u * (uint32_t)p.nb * sum + 3u * mx) + 1.f;
+      cost = (float)((uint32_t)(p.nbi * p.nmb) * sum + (uint32_t)p.gblocks * mx) + 1.f;
     }
     float total = cost;
 #pragma unroll
@@ -174,7 +211,6 @@ k_wgrad_tc(const WgParams p) {
   while (grp + 1 < p.groups && (int)blockIdx.x >= s_cta0[grp + 1]) ++grp;
   const uint32_t gmask = p.gmask[grp];
   const int split = (int)blockIdx.x - s_cta0[grp], splits = s_cta0[grp + 1] - s_cta0[grp];
-  const int kn = __popc(gmask);
   if (split >= splits) return;  // (only if the shares could not be made to add up: more CTAs than tiles)
 
   int n_local = p.n_local;
@@ -186,53 +222,76 @@ k_wgrad_tc(const WgParams p) {
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(a_full(s), 32);
+      mbar_init(a_full(s), kProducers * 32);
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < kMaxGBufs; ++s) {
-      mbar_init(g_full(s), 64);  // two loader warps
+      mbar_init(g_full(s), kProducers * 32);
       mbar_init(g_empty(s), 1);
     }
     mbar_init(acc_full, 1);
     *abort_flag = 0;
     fence_barrier_init();
   }
-  if (warp == S + 4) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
+  if (warp == kProducers + 4) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < S) {
-    // =================================================================== gather producer: owns stage `warp`
-    const uint32_t stage = a_base + (uint32_t)warp * kStageBytes;
-    const uint32_t ent = e_base + (uint32_t)warp * kEntBytes;
+  if (warp < kProducers) {
+    // =================================================================== producers: warp w owns rows 16 w .. 16 w + 15
+    const int row0 = warp * kRowsPerWarp;
     ItemWalk it;
     it.init(p, lmask, n_local);
-    for (int i = 0; i < warp && it.valid(); ++i) it.next();
-    uint32_t round = 0;
-    int4 e = make_int4(-1, -1, -1, -1);
-    if (it.valid()) e = __ldg(reinterpret_cast<const int4*>(p.tbl + (int64_t)it.k * p.tstride + (int64_t)it.t.tile * kTileM) + lane);
-    while (it.valid()) {
-      const int j = it.j;
-      for (int i = 0; i < S && it.valid(); ++i) it.next();
-      int4 en = make_int4(-1, -1, -1, -1);
-      if (it.valid()) en = __ldg(reinterpret_cast<const int4*>(p.tbl + (int64_t)it.k * p.tstride + (int64_t)it.t.tile * kTileM) + lane);
-      if (!mbar_wait(a_empty(warp), (round & 1u) ^ 1u, abort_flag)) goto done;
-      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ent + (uint32_t)lane * 16u), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w) : "memory");
-      __syncwarp();
-      const float* src0 = p.in + j * 32;
-      const bool half = (j == p.nb - 1) && p.last_w == 4;
-      if (!half) gather_block<8, true>(stage, ent, p.in, src0, (uint32_t)p.c_in, lane);
-      else       gather_block<4, true>(stage, ent, p.in, src0, (uint32_t)p.c_in, lane);
-      cp_async_arrive(a_full(warp));
-      __syncwarp();
-      e = en;
-      ++round;
+    uint32_t n_item = 0, gi = 0;
+    // lanes 0..15: this warp's 16 table entries of the current item / its 16 dout rows of the current tile
+    int e = -1, pr = -1;
+    if (it.valid() && lane < kRowsPerWarp) {
+      e = __ldg(p.tbl + (int64_t)it.k * p.tstride + (int64_t)it.t.tile * kTileM + row0 + lane);
+      pr = __ldg(p.perm + (int64_t)it.t.tile * kTileM + row0 + lane);
     }
-  } else if (warp < S + 4) {
+    while (it.valid()) {
+      const int h = it.h;
+      const bool first = it.first;
+      it.next();
+      // the next item's entries (and, at a tile change, its dout rows) are in flight while this one is copied
+      int en = -1, prn = pr;
+      if (it.valid() && lane < kRowsPerWarp) {
+        en = it.h ? e : __ldg(p.tbl + (int64_t)it.k * p.tstride + (int64_t)it.t.tile * kTileM + row0 + lane);
+        if (it.first) prn = __ldg(p.perm + (int64_t)it.t.tile * kTileM + row0 + lane);
+      }
+      if (first) {  // the tile's dout rows, shared by all offsets of the group
+        const int buf = (int)(gi % (uint32_t)p.gbufs);
+        if (!mbar_wait(g_empty(buf), ((gi / (uint32_t)p.gbufs) & 1u) ^ 1u, abort_flag)) goto done;
+        const uint32_t gb = g_base + (uint32_t)buf * g_bytes;
+#pragma unroll 1
+        for (int jb = 0; jb < p.gblocks; ++jb) {
+          const bool half = (jb == p.gblocks - 1) && p.g_last_w == 4;
+          if (!half) gather16<8>(gb + (uint32_t)jb * kBlockBytes, row0, pr, p.dout, p.dout + jb * 32, (uint32_t)p.c_out, lane);
+          else       gather16<4>(gb + (uint32_t)jb * kBlockBytes, row0, pr, p.dout, p.dout + jb * 32, (uint32_t)p.c_out, lane);
+        }
+        cp_async_arrive(g_full(buf));
+        ++gi;
+      }
+      const int s = (int)(n_item % (uint32_t)S);
+      if (!mbar_wait(a_empty(s), ((n_item / (uint32_t)S) & 1u) ^ 1u, abort_flag)) goto done;
+      const uint32_t stage = a_base + (uint32_t)s * a_bytes;
+      const float* src0 = p.in + h * p.cm;
+#pragma unroll 1
+      for (int j = 0; j < p.nbi; ++j) {
+        const bool half = (j == p.nbi - 1) && p.last_w == 4;
+        if (!half) gather16<8>(stage + (uint32_t)j * kBlockBytes, row0, e, p.in, src0 + j * 32, (uint32_t)p.c_in, lane);
+        else       gather16<4>(stage + (uint32_t)j * kBlockBytes, row0, e, p.in, src0 + j * 32, (uint32_t)p.c_in, lane);
+      }
+      cp_async_arrive(a_full(s));
+      e = en;
+      pr = prn;
+      ++n_item;
+    }
+  } else if (warp < kProducers + 4) {
     // =================================================================== epilogue: TMEM -> dW (+=)
-    const int ew = warp & 3;
+    const int ew = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
     // offsets this CTA touched = OR of its tiles' masks (the MMA issuer derives the same set)
     uint32_t seen = 0;
     for (int i = lane; i < n_local; i += 32) seen |= lmask[i];
@@ -241,130 +300,82 @@ k_wgrad_tc(const WgParams p) {
     if (seen == 0) goto done;
     if (!mbar_wait_sleep(acc_full, 0u, abort_flag, 1000)) goto done;
     tc_fence_after();
-    // accumulator row (= output channel) of this thread: M=128 -> lane i holds row i; M=64 -> row m sits in
-    // lane 32*(m/16) + m%16 (16 lanes per sub-partition)
-    const int co = p.mw == 128 ? ew * 32 + lane : ew * 16 + lane;
-    const bool lane_ok = (p.mw == 128 || lane < 16) && co < p.c_out;
+    // accumulator row (= input channel of the M-block) of this thread: M=128 -> lane i holds row i; M=64 -> row m
+    // sits in lane 32*(m/16) + m%16 (16 lanes per sub-partition)
+    const int ci = p.mm == 128 ? ew * 32 + lane : ew * 16 + lane;
+    const bool lane_ok = (p.mm == 128 || lane < 16) && ci < p.cm;
     // every CTA of a group flushes the same addresses: start each at a different offset so that the L2
     // atomic units do not serialise on one line at a time
     const int rot = (int)((unsigned)split * 5u % 32u);
     const uint32_t hi = seen & ~((1u << rot) - 1u), lo = seen & ((1u << rot) - 1u);
-    (void)kn;
     for (int part = 0; part < 2; ++part)
     for (uint32_t rem = part ? lo : hi; rem; rem &= rem - 1) {
       const int k = __ffs(rem) - 1;
-      for (int j = 0; j < p.nb; ++j) {
-        const int wj = (j == p.nb - 1 && p.last_w == 4) ? 16 : 32;
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) +
-                               (uint32_t)(__popc(gmask & ((1u << k) - 1u)) * p.c_in + j * 32);
-        for (int c0 = 0; c0 < wj; c0 += 16) {
+      const int kidx = __popc(gmask & ((1u << k) - 1u));
+      for (int h = 0; h < p.nmb; ++h) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((kidx * p.nmb + h) * p.c_out);
+        float* dst = p.dw + ((int64_t)k * p.c_in + h * p.cm + ci) * p.c_out;
+        for (int c0 = 0; c0 < p.c_out; c0 += 16) {
           float acc[16];
           tmem_ld16(taddr + (uint32_t)c0, acc);
           if (lane_ok) {
-            float* dst = p.dw + ((int64_t)k * p.c_in + j * 32 + c0) * p.c_out + co;
 #pragma unroll
-            for (int q = 0; q < 16; ++q)
-              if (acc[q] != 0.f) atomicAdd(dst + (int64_t)q * p.c_out, acc[q]);
+            for (int q = 0; q < 16; q += 4)
+              if (acc[q] != 0.f || acc[q + 1] != 0.f || acc[q + 2] != 0.f || acc[q + 3] != 0.f)
+                red_add_v4(dst + c0 + q, acc[q], acc[q + 1], acc[q + 2], acc[q + 3]);
           }
         }
       }
     }
     tc_fence_before();
-  } else if (warp == S + 4) {
+  } else {
     // =================================================================== MMA issuer: the whole warp walks the
     // items (warp-uniform control flow), one elected lane issues
-    {
-      const uint32_t idesc32 = make_idesc_tf32(p.mw, 32, 1, 1), idesc16 = make_idesc_tf32(p.mw, 16, 1, 1);
-      const uint64_t desc0 = make_desc_sw128_base32(0, kStageBytes, 512);
-      TileWalk tw;
-      tw.init(p, lmask, n_local);
-      uint32_t gi = 0, seen = 0, ph = 0;
-      int s = 0;
-      bool ok = true, any = false;
-      while (tw.valid() && ok) {
-        const int buf = (int)(gi % (uint32_t)p.gbufs);
+    const uint32_t idesc = make_idesc_tf32(p.mm, p.c_out, 1, 1);
+    const uint64_t desc0 = make_desc_sw128_base32(0, kBlockBytes, 512);
+    ItemWalk it;
+    it.init(p, lmask, n_local);
+    uint32_t gi = 0, seen = 0, n_item = 0;
+    bool ok = true, any = false;
+    int buf = 0;
+    while (it.valid()) {
+      if (it.first) {
+        buf = (int)(gi % (uint32_t)p.gbufs);
         if (!mbar_wait(g_full(buf), (gi / (uint32_t)p.gbufs) & 1u, abort_flag)) { ok = false; break; }
+      }
+      const int s = (int)(n_item % (uint32_t)S);
+      if (!mbar_wait(a_full(s), (n_item / (uint32_t)S) & 1u, abort_flag)) { ok = false; break; }
+      tc_fence_after();
+      const int k = it.k, h = it.h;
+      it.next();
+      const bool tile_done = !it.valid() || it.first;
+      if (elect_one()) {
+        const uint64_t a_desc = desc0 + desc_addr(a_base + (uint32_t)s * a_bytes);
         const uint64_t g_desc = desc0 + desc_addr(g_base + (uint32_t)buf * g_bytes);
-        for (uint32_t rem = tw.m; rem && ok; rem &= rem - 1) {
-          const int k = __ffs(rem) - 1;
-          const uint32_t acc0 = (seen >> k) & 1u;
-          for (int j = 0; j < p.nb; ++j) {
-            if (!mbar_wait(a_full(s), ph, abort_flag)) { ok = false; break; }
-            tc_fence_after();
-            if (elect_one()) {
-              const bool half = (j == p.nb - 1) && p.last_w == 4;
-              const uint64_t a_desc = desc0 + desc_addr(a_base + (uint32_t)s * kStageBytes);
-              const uint32_t d_tmem = tmem_base + (uint32_t)(__popc(gmask & ((1u << k) - 1u)) * p.c_in + j * 32);
-              const uint32_t idesc = half ? idesc16 : idesc32;
-              // per K-step of 8 rows: two 4-row swizzle atoms (SBO = 512 B, 1024 B per step); the dout tile's
-              // 32-wide M blocks are LBO apart
-              umma_tf32(d_tmem, g_desc, a_desc, idesc, acc0);
+        const uint32_t d_tmem = tmem_base + (uint32_t)((__popc(gmask & ((1u << k) - 1u)) * p.nmb + h) * p.c_out);
+        // per K-step of 8 rows: two 4-row swizzle atoms (SBO = 512 B, 1024 B per step); 32-wide M / N blocks are
+        // LBO = 16 KB apart
+        umma_tf32(d_tmem, a_desc, g_desc, idesc, (seen >> k) & 1u);
 #pragma unroll
-              for (int r8 = 1; r8 < 16; ++r8) umma_tf32(d_tmem, g_desc + r8 * 64, a_desc + r8 * 64, idesc, 1u);
-              umma_commit(a_empty(s));
-            }
-            __syncwarp();
-            if (++s == S) { s = 0; ph ^= 1u; }
-          }
-          seen |= 1u << k;
-        }
-        if (!ok) break;
-        if (elect_one()) umma_commit(g_empty(buf));
-        __syncwarp();
-        any = true;
-        ++gi;
-        tw.next_tile();
+        for (int r8 = 1; r8 < 16; ++r8) umma_tf32(d_tmem, a_desc + r8 * 64, g_desc + r8 * 64, idesc, 1u);
+        umma_commit(a_empty(s));
+        if (tile_done) umma_commit(g_empty(buf));
       }
-      if (ok && any && elect_one()) umma_commit(acc_full);
       __syncwarp();
+      if (h == p.nmb - 1) seen |= 1u << k;
+      if (tile_done) ++gi;
+      any = true;
+      ++n_item;
     }
-  } else {
-    // =================================================================== dout-tile loaders: 64 rows each
-    const int half = warp - (S + 5);  // rows 64*half .. 64*half + 63
-    const int nch = p.c_out >> 2;
-    const uint32_t ent = e_base + (uint32_t)S * kEntBytes + (uint32_t)half * 256u;
-    TileWalk tw;
-    tw.init(p, lmask, n_local);
-    uint32_t gi = 0;
-    int2 pr = make_int2(-1, -1);  // rows 2*lane, 2*lane+1 of this half of the tile
-    if (tw.valid()) pr = __ldg(reinterpret_cast<const int2*>(p.perm + (int64_t)tw.tile * kTileM + half * 64) + lane);
-    while (tw.valid()) {
-      tw.next_tile();
-      int2 prn = make_int2(-1, -1);
-      if (tw.valid()) prn = __ldg(reinterpret_cast<const int2*>(p.perm + (int64_t)tw.tile * kTileM + half * 64) + lane);
-      const int buf = (int)(gi % (uint32_t)p.gbufs);
-      if (!mbar_wait(g_empty(buf), ((gi / (uint32_t)p.gbufs) & 1u) ^ 1u, abort_flag)) goto done;
-      const uint32_t gb = g_base + (uint32_t)buf * g_bytes;
-      asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ent + (uint32_t)lane * 8u), "r"(pr.x), "r"(pr.y) : "memory");
-      __syncwarp();
-#pragma unroll 1
-      for (int r0 = 0; r0 < 64; r0 += 32) {
-        int rows[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rows[u]) : "r"(ent + (uint32_t)(r0 + u * 4 + (lane >> 3)) * 4u) : "memory");
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int r = half * 64 + r0 + u * 4 + (lane >> 3);
-          const bool ok = rows[u] >= 0;
-          const float* src = p.dout + (int64_t)(ok ? rows[u] : 0) * p.c_out;
-          for (int ch = lane & 7; ch < nch; ch += 8)
-            cp_async16(gb + (uint32_t)(ch >> 3) * kStageBytes + (uint32_t)r * 128u + swz_base32(ch & 7, r), src + ch * 4,
-                       ok ? 16u : 0u);
-        }
-      }
-      cp_async_arrive(g_full(buf));
-      __syncwarp();
-      pr = prn;
-      ++gi;
-    }
+    if (ok && any && elect_one()) umma_commit(acc_full);
+    __syncwarp();
   }
 done:
   asm volatile("cp.async.wait_all;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0 && *abort_flag) mm3d_raise(p.err);
-  if (warp == S + 4) {
+  if (warp == kProducers + 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -375,7 +386,10 @@ done:
 int* mm3d_device_err_flag();  // conv_tc.cu
 
 int mm3d_conv_wgrad_tc_supported(int c_in, int c_out, int K) {
-  return (c_in % 16) == 0 && c_in <= 512 && (c_out % 4) == 0 && c_out >= 4 && c_out <= 128 && K <= 32;
+  if ((c_in % 16) != 0 || c_in < 16 || c_in > 256 || (c_out % 16) != 0 || c_out < 16 || c_out > 256 || K > 32) return 0;
+  const int nmb = c_in > 128 ? 2 : 1;
+  if (nmb == 2 && (c_in % 32) != 0) return 0;  // halves must stay whole 64-byte pieces
+  return nmb * c_out <= 512;
 }
 
 int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_out, int64_t n_out, int c_out,
@@ -383,8 +397,8 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
                        cudaStream_t stream) {
   MM3D_REQUIRE(mm3d_conv_wgrad_tc_supported(c_in, c_out, K), MM3D_ERR_UNSUPPORTED,
                "tcgen05 wgrad: unsupported shape c_in %d c_out %d K %d", c_in, c_out, K);
-  MM3D_REQUIRE(n_out < (1ll << 31) && n_in * (int64_t)c_in < (1ll << 32), MM3D_ERR_UNSUPPORTED,
-               "tcgen05 wgrad: tensor too large for 32-bit element offsets");
+  MM3D_REQUIRE(n_out < (1ll << 31) && n_in * (int64_t)c_in < (1ll << 32) && n_out * (int64_t)c_out < (1ll << 32),
+               MM3D_ERR_UNSUPPORTED, "tcgen05 wgrad: tensor too large for 32-bit element offsets");
   MM3D_REQUIRE(plan && plan_cap >= n_out, MM3D_ERR_INVALID, "tcgen05 wgrad: needs a row plan covering n_out rows");
   MM3D_REQUIRE((((uintptr_t)in | (uintptr_t)d_out | (uintptr_t)d_weight) & 15) == 0, MM3D_ERR_INVALID,
                "tcgen05 wgrad: pointers must be 16-byte aligned");
@@ -396,19 +410,34 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
   p.perm = pv.perm; p.tile_mask = pv.tile_mask; p.order = pv.order; p.off_tiles = pv.off_tiles; p.tbl = pv.tbl;
   p.tstride = pv.stride;
   p.c_in = c_in; p.c_out = c_out; p.K = K;
-  p.nb = (c_in + 31) / 32;
-  p.last_w = (c_in % 32) == 16 ? 4 : 8;
-  p.mw = c_out <= 64 ? 64 : 128;
+  p.nmb = c_in > 128 ? 2 : 1;
+  p.cm = c_in / p.nmb;
+  p.nbi = (p.cm + 31) / 32;
+  p.last_w = (p.cm % 32) == 16 ? 4 : 8;
+  p.mm = p.cm <= 64 ? 64 : 128;
+  p.gblocks = (c_out + 31) / 32;
+  p.g_last_w = (c_out % 32) == 16 ? 4 : 8;
   p.num_tiles = (int)mm3d_cdiv(n_out, kTileM);
-  int gk = 512 / c_in;  // TMEM: c_in accumulator columns per offset
+  int gk = 512 / (c_out * p.nmb);  // TMEM: c_out accumulator columns per (offset, M-block)
   if (gk > K) gk = K;
   const int groups = (K + gk - 1) / gk;
   int cols = 32;
-  while (cols < gk * c_in) cols <<= 1;
+  while (cols < gk * p.nmb * c_out) cols <<= 1;
   p.tmem_cols = cols;
-  // one CTA per SM: 4 ring stages + as many dout-tile buffers as fit
-  p.S = 4;
-  p.gbufs = p.mw == 128 ? 2 : kMaxGBufs;
+  // one CTA per SM: ring stages and dout-tile buffers from what fits into shared memory
+  const size_t a_bytes = (size_t)p.nbi * kBlockBytes, g_bytes = (size_t)p.gblocks * kBlockBytes;
+  const size_t fixed = 1024 + 8 * (2 * kMaxStages + 2 * kMaxGBufs + 1) + 64;
+  const size_t budget = 218 * 1024 - fixed;  // (the rest, >= 8 KB, holds the CTA's tile list)
+  p.gbufs = 2;
+  p.S = budget > 2 * g_bytes ? (int)((budget - 2 * g_bytes) / a_bytes) : 0;
+  if (p.S < 2) {
+    p.gbufs = 1;
+    p.S = budget > g_bytes ? (int)((budget - g_bytes) / a_bytes) : 0;
+  }
+  MM3D_REQUIRE(p.S >= 1, MM3D_ERR_UNSUPPORTED, "tcgen05 wgrad: shared memory budget exceeded");
+  if (p.S > kMaxStages) p.S = kMaxStages;
+  while (p.gbufs < kMaxGBufs && (size_t)p.S * a_bytes + (size_t)(p.gbufs + 1) * g_bytes <= budget) ++p.gbufs;
+  const size_t smem_fixed = fixed + (size_t)p.S * a_bytes + (size_t)p.gbufs * g_bytes;
   p.err = mm3d_device_err_flag();
   // Offsets -> groups and CTAs -> groups by expected work.  How often an offset occurs is data dependent; as a
   // prior, the centre of a 3^3 table is present for every row, faces often, edges sometimes, corners rarely.
@@ -443,12 +472,10 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
   }
   // CTA shares of the groups are computed in the kernel from measured offset frequencies; here only the bound
   // on tiles per CTA (size of the shared-memory tile list): every group gets >= ceil(num_tiles / n_local) CTAs
-  int total_ctas = MM3D_NUM_SMS;
+  int total_ctas = mm3d_sm_count();
   if (total_ctas < groups) total_ctas = groups;
   int per_group_min = total_ctas / groups / 3;
   if (per_group_min < 1) per_group_min = 1;
-  const size_t smem_fixed = 1024 + (size_t)p.S * kStageBytes + (size_t)(p.S + 1) * kEntBytes +
-                            (size_t)p.gbufs * (p.mw / 32) * kStageBytes + 8 * (2 * kMaxStages + 2 * kMaxGBufs + 1) + 64;
   MM3D_REQUIRE(smem_fixed + 1024 <= 226 * 1024, MM3D_ERR_UNSUPPORTED, "tcgen05 wgrad: shared memory budget exceeded");
   static bool once_dev[64] = {false};
   bool& once = once_dev[mm3d_device_slot()];
@@ -473,7 +500,7 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
     p.num_tiles = cnt;
     p.n_local = (cnt + per_group_min - 1) / per_group_min;
     const size_t smem = smem_fixed + ((size_t)p.n_local * 8 + 15) / 16 * 16;
-    MM3D_CUDA(mm3d_launch_pdl(k_wgrad_tc, dim3((unsigned)total_ctas), dim3((p.S + 7) * 32), smem, stream, p));
+    MM3D_CUDA(mm3d_launch_pdl(k_wgrad_tc, dim3((unsigned)total_ctas), dim3(kThreads), smem, stream, p));
     mm3d_count_launches(1);
   }
   MM3D_CHECK_LAUNCH("mm3d_conv_wgrad_tc");

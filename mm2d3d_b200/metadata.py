@@ -215,7 +215,9 @@ class Metadata:
             if len(self._order) >= self.MAX_LEVELS:
                 raise ValueError("too many levels")
             with torch.cuda.device(self.device):
-                cap = fine.n
+                # capacity of the fine level, not its row count: mm3d_coarsen sizes the coarse hash for n_fine_cap rows
+                # (the pre-built pyramid does the same: every level has the capacity of the point count)
+                cap = fine.cap
                 per_level, lay = self._level_layout(cap)
                 buf = torch.empty(per_level, dtype=torch.uint8, device=self.device)
                 coarse = self._make_level(s // 2, cap, buf, 0, lay, count_slot=len(self._order))

@@ -955,7 +955,10 @@ def test_frozen_parameters_backward():
     net = UNetSCN(in_channels=3, m=16, num_planes=4, full_scale=256).to(DEV)
     locs, feats = synth.make_batch("nuscenes", batch=2, seed0=8)
     locs[:, :3] //= 16
-    coords, feats = torch.from_numpy(locs).to(DEV), torch.from_numpy(feats).to(DEV)
+    # one point per voxel: no float atomics in the I/O layers, so the TF32 data path is bit-reproducible and the
+    # comparison below is not blurred by run-to-run noise amplified through the ReLU gates
+    locs, first = np.unique(locs, axis=0, return_index=True)
+    coords, feats = torch.from_numpy(locs).to(DEV), torch.from_numpy(feats[first]).to(DEV)
     g = torch.randn(locs.shape[0], 16, device=DEV)
     for mode in ("fp32", "tf32"):
         scn_mod.set_conv_mode(mode)
@@ -972,14 +975,18 @@ def test_frozen_parameters_backward():
                 x2 = feats.clone().requires_grad_(True)
                 got = torch.autograd.grad(net([coords, x2]), [x2] + live, g)
                 torch.cuda.synchronize()
-                # same kernels as the all-trainable run: only the atomic accumulation order differs, amplified by the
-                # free-running BatchNorm/ReLU stack
-                bar = 5e-3 if mode == "fp32" else 2e-2
-                assert rel_l2(got[0], full[0]) < bar, (mode, frozen, rel_l2(got[0], full[0]))
+                # same kernels as the all-trainable run.  TF32 mode: forward and dgrad have no atomics -> identical
+                # d_feats; FP32 mode: the SIMT kernels accumulate with atomics (order-dependent rounding, amplified by
+                # the free-running BatchNorm/ReLU stack)
+                if mode == "tf32":
+                    assert torch.equal(got[0], full[0]), (mode, frozen, rel_l2(got[0], full[0]))
+                else:
+                    assert rel_l2(got[0], full[0]) < 5e-3, (mode, frozen, rel_l2(got[0], full[0]))
                 want = {k: full[1 + i] for i, k in enumerate(named)}
                 name_of = {id(v): k for k, v in net.named_parameters()}
                 for p_, a in zip(live, got[1:]):
-                    assert rel_l2(a, want[name_of[id(p_)]]) < 2e-2, (mode, frozen, name_of[id(p_)])
+                    bar = 1e-4 if mode == "tf32" else 5e-3
+                    assert rel_l2(a, want[name_of[id(p_)]]) < bar, (mode, frozen, name_of[id(p_)])
         finally:
             scn_mod.set_conv_mode("fp32")
             net.requires_grad_(True)
