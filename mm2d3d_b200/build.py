@@ -43,6 +43,8 @@ def _stale(target, deps):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
+    # development builds only (e.g. MM3D_EXTRA_NVCC_FLAGS="-DMM3D_TRACE"): such a library is not the product
+    extra = os.environ.get("MM3D_EXTRA_NVCC_FLAGS", "").split()
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     headers = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(INCLUDE, "*.h")))
     nvcc = _nvcc()
@@ -52,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + headers):
-            jobs.append([nvcc, *NVCC_FLAGS, "-c", src, "-o", obj])
+            jobs.append([nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

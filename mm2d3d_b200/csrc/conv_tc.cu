@@ -20,7 +20,9 @@
 //                                      / a_empty[S] (tcgen05.commit)
 //                             accum    acc_full[2] (tcgen05.commit)       / acc_empty[2] (128 arrivals)
 // The accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the MMAs of i+1.
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "plan.cuh"
 #include "tc_common.cuh"
@@ -35,9 +37,11 @@ constexpr int kStageBytes = kTileM * 128;   // one A stage = one K-block of 128 
 constexpr int kEntBytes = kTileM * 4;       // the K-block's 128 table entries
 constexpr int kEpilogue = 128;
 constexpr int kMaxStages = 8;
-constexpr int kMaxThreads = (kMaxStages + 5) * 32;
 
 struct TcParams {
+  CUtensorMap tmap;   // `in` as a [n_in, c_in] float32 tensor, box {32 channels, 1 row}, SWIZZLE_128B (TMA gather path)
+  int use_tma;        // 1: producers gather rows with cp.async.bulk.tensor tile::gather4, 0: 16-byte cp.async
+  int oob_row;        // a row index outside the tensor (= n_in): TMA zero-fills it
   const float* in;
   float* out;
   const float* wimg;  // [K][nb][n_pad][32] tf32, rows 128-byte swizzled
@@ -52,8 +56,22 @@ struct TcParams {
   int S;        // ring stages = producer warps
   int n_pad, num_tiles, tmem_cols;
   int n_local;  // tiles per CTA (upper bound) = ceil(num_tiles / grid)
+  int split;      // MMA issuer warps with their own accumulators (2, or 1 when 4 accumulators do not fit TMEM)
+  int max_items;  // capacity of the shared-memory item list = n_local * K * nb
   int* err;
+#ifdef MM3D_TRACE
+  long long* trace;  // development builds: clock64 stamps of CTA 0's roles, [role][64 records][4]
+#endif
 };
+
+#ifdef MM3D_TRACE
+#define TRACE(role, rec, slot)                                                                                   \
+  do {                                                                                                           \
+    if (p.trace && blockIdx.x == 0 && lane == 0 && (rec) < 64) p.trace[(((role) * 64) + (rec)) * 4 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define TRACE(role, rec, slot) do {} while (0)
+#endif
 
 // Weight image: one [n_pad][32] block per (offset, channel block); element (n, e) of block (k, j) is
 // Wsel(k)[32 j + e][n] (0 beyond c_in / c_out), tf32-rounded, the 16-byte chunks of every 128-byte
@@ -114,47 +132,48 @@ __global__ void k_weight_images(const __grid_constant__ WImgBatch b) {
   }
 }
 
-// Walks the CTA's items in order: its tiles (dealt from the plan's cost-ordered list, kept in shared
-// memory with their masks); per tile the set bits of its mask (ascending offset); per offset the nb
-// channel blocks.  Every role runs its own copy.
-struct ItemWalk {
-  const uint32_t* lmask;  // shared memory: [n_local] masks, then [n_local] tile indices
-  int n_local, nb;
-  int lt, tile, k, j;
-  uint32_t rem;
-  __device__ __forceinline__ void init(const TcParams& p, const uint32_t* local_masks, int n_loc) {
-    lmask = local_masks; n_local = n_loc; nb = p.nb;
-    lt = 0; tile = 0; j = 0; rem = 0; k = 0;
-    if (lt < n_local) { rem = lmask[0]; tile = (int)lmask[n_local]; k = __ffs(rem) - 1; }
-  }
-  __device__ __forceinline__ bool valid() const { return lt < n_local; }
-  __device__ __forceinline__ void next() {
-    if (++j < nb) return;
-    j = 0;
-    rem &= rem - 1;
-    if (rem) { k = __ffs(rem) - 1; return; }
-    ++lt;
-    if (lt < n_local) { rem = lmask[lt]; tile = (int)lmask[n_local + lt]; k = __ffs(rem) - 1; }
-  }
-  // true when the current item is the last of its tile
-  __device__ __forceinline__ bool last_of_tile() const { return j == nb - 1 && (rem & (rem - 1)) == 0; }
-};
+// ---- the kernel --------------------------------------------------------------------------------
+// Every CTA first writes the list of its ITEMS into shared memory: its tiles (dealt from the plan's cost-ordered
+// list) x the set bits of each tile's mask (ascending offset) x the nb channel blocks of an offset, 16 bits per
+// item (local tile << 8 | offset << 3 | channel block).  The roles then index that list instead of each walking
+// the masks again: measured with clock64 stamps, the per-item walk cost every producer ~1000 cycles and the MMA
+// warp ~170 of its ~600 cycles per item, and that single MMA warp was what bounded every layer.
+//
+// Warp roles (14 warps):   warps 0..7     gather producers: warp w < S owns ring stage w and fills items w, w + S, ...
+//                                         (item i lives in stage i % S): the K-block's 128 gathered rows -- TMA tile::gather4 (one
+//                                         instruction per lane = 4 rows) for whole 32-channel blocks, 16-byte
+//                                         cp.async for 16-channel tails -- plus the bulk copy of its weight block
+//                          warps 8..11    epilogue (TMEM lanes -> registers -> out[perm[row]])
+//                          warps 12, 13   MMA issuers: warp m issues the items with i % 2 == m into ITS OWN
+//                                         accumulator (split K inside the CTA; S is even, so ring stage s is only
+//                                         ever consumed by warp s % 2, in order); the epilogue adds the two
+// Pipelines (mbarriers):   ring     a_full[S] (33 arrivals + expect_tx bytes)  / a_empty[S] (tcgen05.commit)
+//                          accum    acc_full[2] (one tcgen05.commit per issuer) / acc_empty[2] (128 arrivals)
+// The accumulator pair is double buffered in TMEM, so the epilogue of tile i overlaps the MMAs of i+1.
+constexpr int kProducers = 8;
+constexpr int kThreads = (kProducers + 6) * 32;
 
-__global__ void __launch_bounds__(kMaxThreads, 1)
-k_conv_tc(const TcParams p) {
+__device__ __forceinline__ int item_tile(uint32_t it) { return (int)(it >> 8); }
+__device__ __forceinline__ int item_k(uint32_t it) { return (int)((it >> 3) & 31u); }
+__device__ __forceinline__ int item_j(uint32_t it) { return (int)(it & 7u); }
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_conv_tc(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int S = p.S;
-  // carve: [A stages][B stages][entry rows][barriers][tmem ptr][abort]
+  // carve: [A stages][B stages][entry rows (one per producer warp)][tile masks | tile indices | item0][items][barriers]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t b_bytes = (uint32_t)p.n_pad * 128u;
   const uint32_t b_stride = (b_bytes + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + (uint32_t)S * kStageBytes;
-  const uint32_t e_base = b_base + (uint32_t)S * b_stride;  // one weight block and one entry row per A stage
-  const uint32_t m_base = e_base + (uint32_t)S * kEntBytes;  // masks of this CTA's tiles
-  const uint32_t bar_base = m_base + (((uint32_t)p.n_local * 8u + 15u) & ~15u);
-  uint32_t* lmask = reinterpret_cast<uint32_t*>(smem + (m_base - smem_base));
+  const uint32_t e_base = b_base + (uint32_t)S * b_stride;
+  const uint32_t m_base = e_base + (uint32_t)kProducers * kEntBytes;
+  const uint32_t i_base = m_base + (((uint32_t)(3 * p.n_local + 1) * 4u + 15u) & ~15u);
+  const uint32_t bar_base = i_base + (((uint32_t)p.max_items * 2u + 15u) & ~15u);
+  uint32_t* lmask = reinterpret_cast<uint32_t*>(smem + (m_base - smem_base));  // [n_local] masks, [n_local] tiles, [n_local + 1] item0
+  uint16_t* items = reinterpret_cast<uint16_t*>(smem + (i_base - smem_base));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar_base - smem_base));
   auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(kMaxStages + s); };
@@ -165,81 +184,145 @@ k_conv_tc(const TcParams p) {
   volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + kNumBars + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = p.split;  // 2: two issuers with their own accumulators; 1: warp 12 alone
 
   // ---- one-time setup.  Nothing before mm3d_griddep_wait() touches global memory (the previous kernel of the
   // stream may still be running: programmatic dependent launch).
   mm3d_griddep_launch();
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(a_full(s), 33);  // 32 cp.async arrivals (gathered rows) + 1 expect_tx arrival (weight block)
+      mbar_init(a_full(s), 33);  // 32 lane arrivals (cp.async completion or plain) + 1 expect_tx arrival
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(acc_full(s), 1);
+      mbar_init(acc_full(s), (uint32_t)split);
       mbar_init(acc_empty(s), kEpilogue);
     }
     *abort_flag = 0;
     fence_barrier_init();
   }
-  if (warp == S + 4) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
+  if (warp == kProducers + 4) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
   mm3d_griddep_wait();
-  // this CTA's tiles (mm3d_plan_local_tile) and their masks live in shared memory: [masks][tile indices]
+  // this CTA's tiles (mm3d_plan_local_tile), their masks and the item list
   int n_local = p.n_local;
   if (mm3d_plan_local_tile(p.order, p.num_tiles, (int)gridDim.x, (int)blockIdx.x, n_local - 1) < 0) --n_local;
+  uint32_t* ltile = lmask + p.n_local;
+  uint32_t* item0 = lmask + 2 * p.n_local;
   for (int i = threadIdx.x; i < n_local; i += blockDim.x) {
     const int t = mm3d_plan_local_tile(p.order, p.num_tiles, (int)gridDim.x, (int)blockIdx.x, i);
     lmask[i] = __ldg(p.tile_mask + t);
-    lmask[n_local + i] = (uint32_t)t;
+    ltile[i] = (uint32_t)t;
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of the tiles' item counts
+    uint32_t run = 0;
+    for (int b0 = 0; b0 < n_local; b0 += 32) {
+      const int i = b0 + lane;
+      const uint32_t c = i < n_local ? (uint32_t)(__popc(lmask[i]) * p.nb) : 0u;
+      uint32_t inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += x;
+      }
+      if (i < n_local) item0[i] = run + inc - c;
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) item0[n_local] = run;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_local; i += blockDim.x) {
+    uint32_t at = item0[i];
+    for (uint32_t rem = lmask[i]; rem; rem &= rem - 1) {
+      const uint32_t k = (uint32_t)(__ffs(rem) - 1);
+      for (int j = 0; j < p.nb; ++j) items[at++] = (uint16_t)(((uint32_t)i << 8) | (k << 3) | (uint32_t)j);
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int n_items = (int)item0[n_local];
 
-  if (warp < S) {
-    // =================================================================== gather producer: owns stage `warp`
-    const uint32_t stage = a_base + (uint32_t)warp * kStageBytes;
+  if (warp < kProducers) {
+    // =================================================================== gather producers
+    // Warp w < S OWNS ring stage w and fills items w, w + S, w + 2 S, ... (warps >= S idle): consecutive waits of a
+    // warp on its stage's barriers are then consecutive phases, which is what a parity wait can tell apart.
+    if (warp >= S) goto done;
     const uint32_t ent = e_base + (uint32_t)warp * kEntBytes;
-    ItemWalk it;
-    it.init(p, lmask, n_local);
-    for (int i = 0; i < warp && it.valid(); ++i) it.next();  // this warp takes every S-th item
-    uint32_t round = 0;
+    int i = warp;
     int4 e = make_int4(-1, -1, -1, -1);  // entries of rows 4*lane .. 4*lane+3 of the current item
-    if (it.valid()) e = __ldg(reinterpret_cast<const int4*>(p.tbl + (int64_t)it.k * p.tstride + (int64_t)it.tile * kTileM) + lane);
-    while (it.valid()) {
-      const int k = it.k, j = it.j;
-      for (int i = 0; i < S && it.valid(); ++i) it.next();
-      int4 en = make_int4(-1, -1, -1, -1);  // the next item's entries are in flight while this one is copied
-      if (it.valid()) en = __ldg(reinterpret_cast<const int4*>(p.tbl + (int64_t)it.k * p.tstride + (int64_t)it.tile * kTileM) + lane);
-      if (!mbar_wait(a_empty(warp), (round & 1u) ^ 1u, abort_flag)) goto done;
-      if (lane == 0) {  // this K-block's weight block rides on the same barrier as the gathered rows
-        mbar_arrive_expect_tx(a_full(warp), b_bytes);
-        bulk_g2s(b_base + (uint32_t)warp * b_stride, p.wimg + ((size_t)k * p.nb + j) * p.n_pad * kKBlock, b_bytes, a_full(warp));
-      }
-      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ent + (uint32_t)lane * 16u), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w) : "memory");
-      __syncwarp();
-      const float* src0 = p.in + j * kKBlock;
-      const bool half = (j == p.nb - 1) && p.last_w == 4;
-      if (!half) gather_block<8, false>(stage, ent, p.in, src0, (uint32_t)p.c_in, lane);
-      else       gather_block<4, false>(stage, ent, p.in, src0, (uint32_t)p.c_in, lane);
-      cp_async_arrive(a_full(warp));
-      __syncwarp();  // the entry row is rewritten by the next item
-      e = en;
-      ++round;
+    uint32_t cur = 0;
+    if (i < n_items) {
+      cur = items[i];
+      e = __ldg(reinterpret_cast<const int4*>(p.tbl + (int64_t)item_k(cur) * p.tstride + (int64_t)ltile[item_tile(cur)] * kTileM) + lane);
     }
-  } else if (warp < S + 4) {
+    while (i < n_items) {
+      const int k = item_k(cur), j = item_j(cur);
+      const int inext = i + S;
+      int4 en = make_int4(-1, -1, -1, -1);  // the next item's entries are in flight while this one is copied
+      uint32_t nxt = 0;
+      if (inext < n_items) {
+        nxt = items[inext];
+        en = __ldg(reinterpret_cast<const int4*>(p.tbl + (int64_t)item_k(nxt) * p.tstride + (int64_t)ltile[item_tile(nxt)] * kTileM) + lane);
+      }
+      const int s = warp;
+      const uint32_t stage = a_base + (uint32_t)s * kStageBytes;
+      TRACE(warp, i / S, 0);
+      if (!mbar_wait(a_empty(s), (((uint32_t)i / (uint32_t)S) & 1u) ^ 1u, abort_flag)) goto done;
+      TRACE(warp, i / S, 1);
+      const bool half = (j == p.nb - 1) && p.last_w == 4;
+      const bool tma = p.use_tma && !half;
+      if (lane == 0) {  // this K-block's weight block rides on the same barrier as the gathered rows
+        mbar_arrive_expect_tx(a_full(s), b_bytes + (tma ? (uint32_t)kStageBytes : 0u));
+        bulk_g2s(b_base + (uint32_t)s * b_stride, p.wimg + ((size_t)k * p.nb + j) * p.n_pad * kKBlock, b_bytes, a_full(s));
+      }
+      if (tma) {
+        // One tile::gather4 per lane: rows 4 lane .. 4 lane + 3 of the K-block (128 bytes each, swizzled by the TMA
+        // unit, zeros for absent rows = an out-of-bounds row coordinate) -- the whole 16 KB stage is ONE warp
+        // instruction, no per-row address arithmetic in the SM.
+        tma_gather4(stage + (uint32_t)lane * 512u, &p.tmap, j * kKBlock, e.x < 0 ? p.oob_row : e.x, e.y < 0 ? p.oob_row : e.y,
+                    e.z < 0 ? p.oob_row : e.z, e.w < 0 ? p.oob_row : e.w, a_full(s));
+        mbar_arrive(a_full(s));
+      } else {
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ent + (uint32_t)lane * 16u), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w) : "memory");
+        __syncwarp();
+        const float* src0 = p.in + j * kKBlock;
+        if (!half) gather_block<8, false>(stage, ent, p.in, src0, (uint32_t)p.c_in, lane);
+        else       gather_block<4, false>(stage, ent, p.in, src0, (uint32_t)p.c_in, lane);
+        cp_async_arrive(a_full(s));
+        __syncwarp();  // the entry row is rewritten by the next item
+      }
+      TRACE(warp, i / S, 2);
+      e = en;
+      cur = nxt;
+      i = inext;
+    }
+  } else if (warp < kProducers + 4) {
     // =================================================================== epilogue
     const int ew = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
     for (uint32_t tile_iter = 0; tile_iter < (uint32_t)n_local; ++tile_iter) {
       const int ab = (int)(tile_iter & 1u);
-      const int tile = (int)lmask[n_local + tile_iter];
+      const int tile = (int)ltile[tile_iter];
       const int row = __ldg(p.perm + (int64_t)tile * kTileM + ew * 32 + lane);
+      // which issuers had items of this tile (an accumulator nobody wrote holds the previous tile's values)
+      const uint32_t i0 = item0[tile_iter], i1 = item0[tile_iter + 1];
+      const bool two = split == 2 && i1 - i0 >= 2;
+      const int only = (int)(i0 & 1u) & (split - 1);  // the issuer of a one-item tile
+      if (ew == 0) TRACE(kProducers + 1, tile_iter, 0);
       if (!mbar_wait_sleep(acc_full(ab), (tile_iter >> 1) & 1u, abort_flag, 100)) goto done;
+      if (ew == 0) TRACE(kProducers + 1, tile_iter, 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * p.n_pad);
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * split * p.n_pad);
       for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
         float acc[16];
-        tmem_ld16(taddr + (uint32_t)c0, acc);
+        tmem_ld16(taddr + (uint32_t)((two ? 0 : only) * p.n_pad + c0), acc);
+        if (two) {
+          float acc1[16];
+          tmem_ld16(taddr + (uint32_t)(p.n_pad + c0), acc1);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) acc[q] += acc1[q];
+        }
         if (row >= 0) {
           float* dst = p.out + (int64_t)row * p.c_out + c0;
           if ((p.c_out & 3) == 0) {
@@ -255,49 +338,52 @@ k_conv_tc(const TcParams p) {
       }
       tc_fence_before();
       mbar_arrive(acc_empty(ab));
+      if (ew == 0) TRACE(kProducers + 1, tile_iter, 2);
     }
-  } else if (warp == S + 4) {
-    // =================================================================== MMA issuer: the whole warp walks the
-    // items (warp-uniform control flow), one elected lane issues
-    {
+  } else {
+    // =================================================================== MMA issuers: the whole warp runs the loop
+    // (warp-uniform control flow), one elected lane issues.  Issuer m takes the items with i % split == m.
+    const int m = warp - (kProducers + 4);
+    if (m < split) {
       const uint32_t idesc = make_idesc_tf32(kTileM, p.n_pad);
       const uint64_t desc0 = make_desc_sw128(0);
-      ItemWalk it;
-      it.init(p, lmask, n_local);
-      uint32_t tile_iter = 0;
-      int s = 0;
-      uint32_t ph = 0;
-      while (it.valid()) {
+      uint32_t n_mine = 0;
+      (void)n_mine;
+      for (uint32_t tile_iter = 0; tile_iter < (uint32_t)n_local; ++tile_iter) {
         const int ab = (int)(tile_iter & 1u);
-        if (!mbar_wait(acc_empty(ab), ((tile_iter >> 1) & 1u) ^ 1u, abort_flag)) break;
+        const int i0 = (int)item0[tile_iter], i1 = (int)item0[tile_iter + 1];
+        TRACE(kProducers + 2 + m, n_mine, 3);
+        if (!mbar_wait(acc_empty(ab), ((tile_iter >> 1) & 1u) ^ 1u, abort_flag)) goto done;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.n_pad);
-        bool first = true, ok = true;
-        while (true) {
-          const bool last = it.last_of_tile();
-          const int ksteps = (it.j == p.nb - 1 ? p.last_w : 8) >> 1;
-          if (!mbar_wait(a_full(s), ph, abort_flag)) { ok = false; break; }
+        const uint32_t d_tmem = tmem_base + (uint32_t)((ab * split + m) * p.n_pad);
+        uint32_t acc = 0u;
+        int i = i0 + (((i0 & (split - 1)) == m) ? 0 : 1);
+        if (split == 1) i = i0;
+        for (; i < i1; i += split) {
+          const int s = i % S;
+          const int ksteps = (item_j(items[i]) == p.nb - 1 ? p.last_w : 8) >> 1;
+          TRACE(kProducers + 2 + m, n_mine, 0);
+          if (!mbar_wait(a_full(s), ((uint32_t)i / (uint32_t)S) & 1u, abort_flag)) goto done;
+          TRACE(kProducers + 2 + m, n_mine, 1);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t a_desc = desc0 + desc_addr(a_base + (uint32_t)s * kStageBytes);
             const uint64_t b_desc = desc0 + desc_addr(b_base + (uint32_t)s * b_stride);
-            umma_tf32(d_tmem, a_desc, b_desc, idesc, first ? 0u : 1u);
+            umma_tf32(d_tmem, a_desc, b_desc, idesc, acc);
             umma_tf32(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);  // +32 bytes per K-step of 8
             if (ksteps == 4) {
               umma_tf32(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
               umma_tf32(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
             }
             umma_commit(a_empty(s));  // frees the stage and its weight block
-            if (last) umma_commit(acc_full(ab));
           }
           __syncwarp();
-          first = false;
-          if (++s == S) { s = 0; ph ^= 1u; }
-          it.next();
-          if (last) break;
+          TRACE(kProducers + 2 + m, n_mine, 2);
+          ++n_mine;
+          acc = 1u;
         }
-        if (!ok) break;
-        ++tile_iter;
+        if (elect_one()) umma_commit(acc_full(ab));  // (arrives at once when this issuer had no item of the tile)
+        __syncwarp();
       }
     }
   }
@@ -306,7 +392,7 @@ done:
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0 && *abort_flag) mm3d_raise(p.err);
-  if (warp == S + 4) {
+  if (warp == kProducers + 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -321,12 +407,45 @@ int pow2_cols(int n) {
 }  // namespace
 
 // ---- host entry points used by capi.cu -------------------------------------------------------
+#ifdef MM3D_TRACE
+static long long* g_trace = nullptr;
+extern "C" __attribute__((visibility("default"))) void mm3d_debug_set_trace(long long* p) { g_trace = p; }
+#endif
+
+// Tensor map of a row-major [rows, c] float32 feature tensor for row gathers: box = {32 channels, 1 row} (a
+// tile::gather4 moves 4 such rows), 128-byte swizzle -- plain for K-major MMA operands, 32-byte-atom for the MN-major
+// ones of the weight-gradient kernel.  Columns past c and rows past `rows` read as zeros.  false = TMA not available
+// (the kernels then gather with cp.async).
+bool mm3d_encode_rows_tmap(CUtensorMap* tm, const float* base, int64_t rows, int c, bool atom32) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeFn)f;
+    else
+      (void)cudaGetLastError();
+  }
+  if (!fn || (((uintptr_t)base) & 15) != 0 || (c % 4) != 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)c, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)c * 4};
+  const cuuint32_t box[2] = {32, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 static int tc_geometry(int c_in, int c_out, int K, int* nb, int* n_pad) {
   *nb = (c_in + 31) / 32;
   *n_pad = (c_out + 15) / 16 * 16;
   // input rows are cut into 128-byte blocks with an optional 64-byte tail
-  return (*n_pad <= 256 && (c_in % 16) == 0 && K <= 32) ? 0 : 1;
+  return (*n_pad <= 256 && (c_in % 16) == 0 && c_in <= 256 && K <= 32) ? 0 : 1;
 }
 
 // 1 when the tcgen05 kernel handles this shape
@@ -452,43 +571,69 @@ int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, in
   p.last_w = (c_in % 32) == 16 ? 4 : 8;
   p.n_pad = n_pad;
   p.num_tiles = (int)mm3d_cdiv(n_out, kTileM);
-  p.tmem_cols = pow2_cols(2 * n_pad);
   p.err = mm3d_device_err_flag();
+#ifdef MM3D_TRACE
+  p.trace = g_trace;
+#endif
+  p.use_tma = 0;
+  p.oob_row = (int)n_in;
+  // Row gathers: 16-byte cp.async by default.  MM3D_TC_GATHER=tma selects TMA tile::gather4 for whole 32-channel
+  // blocks instead (one instruction per 4 rows, no address arithmetic in the SM): measured on B200 it is on par
+  // for 64+ input channels and slower for 32 (the TMA unit takes ~4 cycles per 128-byte row and is shared by the SM's
+  // CTAs), 1 % slower over the whole step -- kept selectable for that comparison.
+  static const bool want_tma = [] { const char* e = getenv("MM3D_TC_GATHER"); return e && strcmp(e, "tma") == 0; }();
+  if (want_tma && n_in > 0 && n_in < (1ll << 31) - 1) {
+    p.use_tma = mm3d_encode_rows_tmap(&p.tmap, in, n_in, c_in, /*atom32=*/false) ? 1 : 0;
+  }
   const uint32_t b_stride = ((uint32_t)n_pad * 128u + 1023u) & ~1023u;
-  const size_t per_stage = (size_t)kStageBytes + b_stride + kEntBytes;
-  // as many stages as give two CTAs per SM; one CTA per SM (deeper ring) when the weight blocks are
-  // large or there are no more tiles than SMs anyway
-  const int two = (int)((112 * 1024) / per_stage), one = (int)((222 * 1024) / per_stage);
-  int S = (p.num_tiles > MM3D_NUM_SMS && two >= 3) ? two : one;
-  if (S > kMaxStages) S = kMaxStages;
-  p.S = S;
-  size_t smem = 1024 + (size_t)S * per_stage + 8 * (2 * kMaxStages + 4) + 64;
-  static int regs_dev[64] = {0};
-  int& regs = regs_dev[mm3d_device_slot()];
-  if (!regs) {
+  const size_t per_stage = (size_t)kStageBytes + b_stride;
+  static bool once_dev[64] = {false};
+  bool& once = once_dev[mm3d_device_slot()];
+  if (!once) {
     MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     MM3D_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    cudaFuncAttributes fa;
-    MM3D_CUDA(cudaFuncGetAttributes(&fa, k_conv_tc));
-    regs = fa.numRegs > 0 ? fa.numRegs : 64;
+    once = true;
   }
-  // persistent CTAs: as many as fit (registers, shared memory, threads, TMEM columns); tiles round-robin
-  const int threads = (S + 5) * 32;
-  const int regs_alloc = (regs + 7) / 8 * 8;
-  int per_sm = 65536 / (regs_alloc * threads);
-  const int by_smem = (int)((227 * 1024) / (smem + 1024));
-  const int by_tmem = 512 / p.tmem_cols;
-  if (per_sm > by_smem) per_sm = by_smem;
-  if (per_sm > 2048 / threads) per_sm = 2048 / threads;
-  if (per_sm > by_tmem) per_sm = by_tmem;
-  if (per_sm < 1) per_sm = 1;
-  int grid = MM3D_NUM_SMS * per_sm;
-  if (grid > p.num_tiles) grid = p.num_tiles;
-  p.n_local = (p.num_tiles + grid - 1) / grid;
-  smem += ((size_t)p.n_local * 8 + 15) / 16 * 16;
-  MM3D_REQUIRE(smem <= 226 * 1024, MM3D_ERR_UNSUPPORTED, "tcgen05 conv: too many rows per CTA for the tile-mask cache");
-  MM3D_CUDA(mm3d_launch_pdl(k_conv_tc, dim3(grid), dim3(threads), smem, stream, p));
-  mm3d_count_launches(1);
+  // Two issuer warps with their own accumulators (double buffered: 4 x n_pad TMEM columns) whenever they fit.
+  // Two CTAs per SM when the layer has more tiles than SMs, each CTA's accumulators fit half the TMEM and half the
+  // shared memory still holds a ring of >= 4 stages; one CTA per SM with a deeper ring otherwise.  S is even (ring
+  // stage s is consumed by issuer s % 2).
+  const int sms = mm3d_sm_count();
+  p.split = 4 * n_pad <= 512 ? 2 : 1;
+  p.tmem_cols = pow2_cols(2 * p.split * n_pad);
+  const size_t fixed = 1024 + (size_t)kProducers * kEntBytes + 8 * (2 * kMaxStages + 4) + 64 + 64;
+  const int two = (int)((108 * 1024 - fixed) / per_stage), one = (int)((218 * 1024 - fixed) / per_stage);
+  // (measured: two CTAs per SM win for one-block layers (c_in <= 32), one CTA with the deeper ring from 64 channels on)
+  const int per_sm = (p.num_tiles > sms && nb == 1 && two >= 4 && 2 * p.tmem_cols <= 512) ? 2 : 1;
+  int S = per_sm == 2 ? two : one;
+  if (S > kMaxStages) S = kMaxStages;
+  S &= ~1;
+  MM3D_REQUIRE(S >= 2, MM3D_ERR_UNSUPPORTED, "tcgen05 conv: a K-block of %d output channels does not fit the ring", n_pad);
+  p.S = S;
+  const size_t smem_fixed = fixed + (size_t)S * per_stage;
+  // Per-CTA lists (tile masks / indices / first items: 12 bytes per tile; items: 2 bytes each) live in shared memory
+  // next to the ring.  Row counts whose lists do not fit are processed in several launches over consecutive pieces of
+  // the plan's tile order (tiles are independent).
+  const size_t list_budget = (per_sm == 2 ? 110 * 1024 : 224 * 1024) - smem_fixed;
+  const size_t per_tile = 12 + 2 * (size_t)K * nb;
+  int64_t max_local = (int64_t)((list_budget - 64) / per_tile);
+  if (max_local > 255) max_local = 255;  // (8 bits of local tile index per item)
+  MM3D_REQUIRE(max_local >= 1, MM3D_ERR_UNSUPPORTED, "tcgen05 conv: no shared memory left for the item list");
+  const int all_tiles = p.num_tiles;
+  const int64_t max_tiles = max_local * sms * per_sm;
+  for (int64_t start = 0; start < all_tiles; start += max_tiles) {
+    const int cnt = (int)(all_tiles - start < max_tiles ? all_tiles - start : max_tiles);
+    p.order = pv.order + start;
+    p.num_tiles = cnt;
+    int grid = sms * per_sm;
+    if (grid > cnt) grid = cnt;
+    p.n_local = (cnt + grid - 1) / grid;
+    p.max_items = p.n_local * K * nb;
+    const size_t smem = smem_fixed + (((size_t)(3 * p.n_local + 1) * 4 + 15) & ~(size_t)15) + (((size_t)p.max_items * 2 + 15) & ~(size_t)15);
+    MM3D_REQUIRE(smem <= 226 * 1024, MM3D_ERR_UNSUPPORTED, "tcgen05 conv: shared memory budget exceeded");
+    MM3D_CUDA(mm3d_launch_pdl(k_conv_tc, dim3(grid), dim3(kThreads), smem, stream, p));
+    mm3d_count_launches(1);
+  }
   MM3D_CHECK_LAUNCH("mm3d_conv_fwd_tc");
   return MM3D_OK;
 }

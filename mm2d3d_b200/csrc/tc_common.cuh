@@ -91,6 +91,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// TMA row gather: 4 rows (row0..row3, any order) x the tensor map's box width starting at column `col` land as 4
+// consecutive 128-byte rows at dst (swizzled as the tensor map says); out-of-bounds rows / columns arrive as zeros;
+// the mbarrier receives complete_tx for the full 4 x box bytes.
+__device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const void* tmap, int col, int row0, int row1, int row2, int row3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+          dst_smem),
+      "l"(tmap), "r"(col), "r"(row0), "r"(row1), "r"(row2), "r"(row3), "r"(bar)
+      : "memory");
+}
 // 16-byte asynchronous copy global -> shared; src_bytes < 16 zero-fills the rest (0 = pure zero fill)
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");

@@ -1063,8 +1063,24 @@ def test_unetscn_semantickitti_shaped_scan():
     net_ref = UNetSCN(in_channels=3, backend=scn_cpu)
     net = UNetSCN(in_channels=3).to(DEV)
     net.load_state_dict(net_ref.state_dict())
-    worst = _run_pair(net_ref, net, torch.from_numpy(locs), torch.from_numpy(feats), TOL["fp32"])
-    print("SemanticKITTI-shaped scan: worst gradient error relative to the FP32 CPU oracle's own error", worst)
+    import copy
+    coords, fe = torch.from_numpy(locs), torch.from_numpy(feats)
+    net64 = copy.deepcopy(net_ref).double()
+    x64 = fe.double().requires_grad_(True)
+    out64 = net64([coords, x64])
+    g = torch.randn_like(out64)
+    p64 = dict(net64.named_parameters())
+    g64 = torch.autograd.grad(out64, [x64] + list(p64.values()), g)
+    x = fe.clone().to(DEV).requires_grad_(True)
+    out = net([coords.to(DEV), x])
+    gg = torch.autograd.grad(out, [x] + list(net.parameters()), g.float().to(DEV))
+    assert rel_err(out, out64) < TOL["fp32"], rel_err(out, out64)
+    # free-running ReLU gates and batch statistics: the FP32 SIMT kernels accumulate with atomics, and a gate that
+    # flips on that noise changes its gradient entry by O(1) -- gradients are held to 5e-3 relative L2 here, the strict
+    # 1e-4 is held with frozen gates (test_unetscn_gradients_with_frozen_gates) and per op
+    worst = max((rel_l2(a, b), n) for a, b, n in zip(gg, g64, ["feats"] + list(p64)))
+    print("SemanticKITTI-shaped scan, FP32 mode: forward", rel_err(out, out64), "worst gradient rel-L2", worst)
+    assert worst[0] < 5e-3, worst
     c, f = torch.from_numpy(locs).to(DEV), torch.from_numpy(feats).to(DEV)
     with torch.no_grad():
         net.eval()
