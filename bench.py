@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--no-pipeline", dest="pipeline", action="store_false",
                     help="build each step's sparse structure inline on the compute stream instead of one step ahead")
     ap.add_argument("--no-kernel-pass", action="store_true")
+    ap.add_argument("--full-step", action="store_true",
+                    help="BASELINE configs[2]: whole MM2D3D training step (2D ResNet34-UNet stand-in on stock cuDNN + lift + "
+                         "UNetSCN + heads + losses + optimiser), source and target batch, single GPU")
     return ap.parse_args()
 
 
@@ -462,25 +465,33 @@ def run_ours(args):
     # end to end: pinned host inputs -> device -> fwd+bwd (-> all-reduce) -> scalar back to the host
     # untimed lead-in: every distinct batch once (+2), so that the copy stream's allocator pool has seen all sizes and
     # no cudaMalloc (a device-wide synchronisation, slower still with N processes) falls into the timed region
-    n_pre = max(min(args.warmup, 3), args.rotate + 2)
-    for i in range(n_pre):
-        step_e2e(i)
-    barrier()
-    t0 = time.perf_counter()
-    prev, acc = None, 0.0
-    for i in range(n_pre, n_pre + args.steps):
-        cur = step_e2e(i)
-        if prev is not None:
-            prev[1].synchronize()
-            acc += float(prev[0])
-        prev = cur
-    prev[1].synchronize()
-    acc += float(prev[0])
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    pending.clear()
-    if acc != acc:
-        raise SystemExit("bench.py: the end-to-end loop produced NaN")
+    e2e_counter = [0]
+
+    def time_e2e(steps):
+        n_pre = max(min(args.warmup, 3), args.rotate + 2)
+        base = e2e_counter[0]
+        for i in range(base, base + n_pre):
+            step_e2e(i)
+        barrier()
+        t0 = time.perf_counter()
+        prev, acc = None, 0.0
+        for i in range(base + n_pre, base + n_pre + steps):
+            cur = step_e2e(i)
+            if prev is not None:
+                prev[1].synchronize()
+                acc += float(prev[0])
+            prev = cur
+        prev[1].synchronize()
+        acc += float(prev[0])
+        barrier()
+        dt = (time.perf_counter() - t0) * 1e3
+        e2e_counter[0] = base + n_pre + steps
+        pending.clear()
+        if acc != acc:
+            raise SystemExit("bench.py: the end-to-end loop produced NaN")
+        return dt
+
+    e2e_ms = time_e2e(args.steps)
 
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
@@ -504,32 +515,43 @@ def run_ours(args):
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         fp32_side = None
         if world == 1 and args.mode != "fp32" and not args.no_fp32_side:
+            # the precision-matched mode (the reference's 3D branch is FP32) as a full measurement: same
+            # workload, same loops -- device-timed value and end-to-end value
             scn_mod.set_conv_mode("fp32")
             prepared.clear()  # built for the tensor-core mode (row plans)
             try:
+                n_f = 20
                 for i in range(3):
                     step(i)
                 barrier()
                 f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 f0.record()
-                for i in range(8):
+                for i in range(n_f):
                     step(i)
                 f1.record()
                 barrier()
-                fms = f0.elapsed_time(f1) / 8
-                fp32_side = {"value": args.batch / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms, "steps": 8, "dtype": "f32",
-                             "note": "same workload in the FP32 SIMT parity mode (activations/gradients within 1e-4)"}
+                fms = f0.elapsed_time(f1) / n_f
+                prepared.clear()
+                fe2e = time_e2e(n_f) / n_f
+                fp32_side = {"value": args.batch / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms, "steps": n_f, "warmup": 3,
+                             "dtype": "f32", "e2e": {"value": args.batch / (fe2e * 1e-3), "unit": UNIT, "ms_per_step": fe2e},
+                             "note": "same workload and loops in the FP32 SIMT parity mode (activations / gradients within "
+                                     "1e-4): the figure to set against the reference's FP32 3D branch"}
             finally:
                 scn_mod.set_conv_mode(args.mode)
                 prepared.clear()
         if roofline is not None:
-            # DRAM traffic of the dominant kernel comes from a separate `ncu --set full` capture (profiles/)
+            # DRAM traffic of the dominant kernel: from an `ncu --set full` capture (profiles/ncu_traffic.json) of the SAME
+            # kernel source -- the entry records the SHA-1 of the kernel's .cu file at capture time; any other build
+            # prints null rather than a stale number
             try:
+                import hashlib
                 tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
                 key = roofline["kernel"].split(" @ ")[0] + f" rows {roofline['kernel'].split('(')[1].split(' rows')[0]} {args.mode}"
-                if key in tr:
-                    roofline["traffic"] = tr[key]["dram_bytes"]
-                    roofline["traffic_source"] = tr[key]["source"]
+                ent = tr.get(key)
+                if ent and hashlib.sha1(open(os.path.join(ROOT, ent["src_file"]), "rb").read()).hexdigest() == ent["src_sha1"]:
+                    roofline["traffic"] = ent["dram_bytes"]
+                    roofline["traffic_source"] = ent["source"]
             except Exception:
                 pass
         scans = world * args.batch * args.steps
@@ -569,6 +591,146 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------ full step (configs[2])
+def run_full_step(args):
+    """One optimisation step of the reference's trainer (train.py:186-292): source AND target batch through the 2D and
+    the 3D network (4 forwards), cross-entropy on the source, cross-modal KL on both, one backward, one optimiser step.
+    The 2D network is a stock-cuDNN stand-in of the reference's Net2DSeg (tools/net2d_standin.py; channels-last, BF16
+    autocast like the reference's AMP); lift, RGB mask, UNetSCN and the KL terms are this package's kernels."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from net2d_standin import RGBDUNet2D
+
+    from mm2d3d_b200 import _lib, synth
+    from mm2d3d_b200 import scn as scn_mod
+    from mm2d3d_b200.heads import cross_modal_kl, rgb_mask
+    from mm2d3d_b200.lift import LiftIndices
+    from mm2d3d_b200.unet import UNetSCN
+
+    if args.gpus != 1:
+        raise SystemExit("bench.py --full-step: single GPU only")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    scn_mod.set_conv_mode(args.mode)
+    torch.manual_seed(0)
+    C, H, W = 6, 225, 400  # nuScenes-lidarseg merged classes (config.yaml), resize [400, 225]
+    net2d = RGBDUNet2D(C).to(dev).to(memory_format=torch.channels_last)
+    net3d = UNetSCN(**NET_KW).to(dev)
+    mask = torch.nn.Linear(3, 1).to(dev)
+    head, head_aux = torch.nn.Linear(16, C).to(dev), torch.nn.Linear(16, C).to(dev)
+    params = [*net2d.parameters(), *net3d.parameters(), *mask.parameters(), *head.parameters(), *head_aux.parameters()]
+    opt = torch.optim.Adam(params, lr=1e-4, fused=True)
+
+    data = {"src": [], "trg": []}
+    for d, dom in enumerate(("src", "trg")):
+        for r in range(args.rotate):
+            seed0 = (d * args.rotate + r) * args.batch
+            locs, feats = synth.make_batch(args.shape, batch=args.batch, seed0=seed0)
+            counts = np.bincount(locs[:, 3], minlength=args.batch).tolist()
+            idx = synth.make_img_indices(counts, H, W, seed=seed0)
+            rng = np.random.default_rng(seed0)
+            data[dom].append(dict(
+                locs=torch.from_numpy(locs).to(dev), feats=torch.from_numpy(feats).to(dev),
+                img=torch.from_numpy(rng.random((args.batch, 3, H, W), dtype=np.float32)).to(dev).contiguous(memory_format=torch.channels_last),
+                depth=torch.from_numpy((rng.random((args.batch, 1, H, W), dtype=np.float32) < 0.04).astype(np.float32) * 30).to(dev),
+                li=LiftIndices(idx, dev), labels=torch.from_numpy(rng.integers(0, C, locs.shape[0])).to(dev)))
+    n_points = float(np.mean([b["locs"].shape[0] for dom in data for b in data[dom]]))
+    ev3d = []
+
+    def step(i, time3d=False):
+        loss = 0.0
+        for dom in ("src", "trg"):
+            b = data[dom][i % args.rotate]
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                l2d, a2d, _ = net2d(b["img"], b["depth"], b["li"])
+            if time3d:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            x = rgb_mask(b["feats"], mask.weight, mask.bias)
+            out3d = net3d([b["locs"], x])
+            if time3d:
+                e1.record()
+                ev3d.append((e0, e1))
+            l3d, a3d = head(out3d), head_aux(out3d)
+            if dom == "src":
+                loss = loss + F.cross_entropy(l2d, b["labels"]) + F.cross_entropy(l3d, b["labels"])
+            loss = loss + 0.1 * (cross_modal_kl(a3d, l2d) + cross_modal_kl(a2d, l3d))
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    sampler.mark()
+    launches0 = _lib.lib.mm3d_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        last = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = _lib.lib.mm3d_kernel_launches() - launches0
+    if not bool(torch.isfinite(last)):
+        raise SystemExit("bench.py --full-step: non-finite loss")
+    for i in range(max(0, int(400.0 / ms) - args.steps)):
+        step(i)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    # the 3D branch alone, same batches: mask + UNetSCN forward (events inside the step), and forward+backward
+    for i in range(4):
+        step(i, time3d=True)
+    torch.cuda.synchronize()
+    fwd3d = sum(a.elapsed_time(b) for a, b in ev3d) / 4
+
+    def only3d(i):
+        for dom in ("src", "trg"):
+            b = data[dom][i % args.rotate]
+            x = b["feats"].detach().requires_grad_(True)
+            out = net3d([b["locs"], x])
+            out.backward(torch.ones_like(out))
+        for p_ in net3d.parameters():
+            p_.grad = None
+    for i in range(3):
+        only3d(i)
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(10):
+        only3d(i)
+    f1.record()
+    torch.cuda.synchronize()
+    ms3d = f0.elapsed_time(f1) / 10
+    scans = 2 * args.batch
+    line = {
+        "impl": "ours", "metric": "full MM2D3D training step scans/sec (source + target)", "value": scans / (ms * 1e-3), "unit": UNIT,
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32"}[args.mode] + " (3D) / bf16 autocast (2D)", "data": "synthetic",
+        "config": {
+            "workload": f"BASELINE configs[2]: full MM2D3D step -- ResNet34-UNet stand-in on {H}x{W} RGB-D (46.2 M parameters, "
+                        f"stock cuDNN, channels-last, BF16 autocast) + 2D->3D lift + RGB mask + UNetSCN(m=16, 7 planes) + 2+2 heads "
+                        f"+ CE / cross-modal KL + fused Adam; batch {args.batch} source + {args.batch} target {args.shape}-shaped scans",
+            "points_per_batch": n_points, "conv_mode": args.mode,
+            "structure": "built inline by each 3D forward", "l2": f"{args.rotate} rotating resident batches per domain",
+        },
+        "clocks": clocks, "gpu_launches": int(launches),
+        "branch_3d": {"forward_ms_inside_step": fwd3d, "fwd_bwd_ms_alone": ms3d, "share_of_step": ms3d / ms,
+                      "note": "UNetSCN (+ mask) on the step's two batches; forward timed with events inside the full step, "
+                              "forward+backward timed alone on the same batches"},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
     if os.environ.get("MM3D_ABL_SKIP"):
@@ -576,6 +738,8 @@ def main():
         raise SystemExit("bench.py: MM3D_ABL_SKIP is set -- refusing to print a benchmark line for an ablated run")
     if args.impl == "reference":
         run_reference(args)
+    elif args.full_step:
+        run_full_step(args)
     else:
         run_ours(args)
 

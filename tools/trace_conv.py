@@ -51,8 +51,8 @@ def main():
     tr = trace.view(16, 64, 4).cpu().numpy()
     t0 = tr[tr > 0].min()
     rel = lambda v: "      -" if v == 0 else f"{(v - t0):7d}"
-    print("columns: producers (roles 0..S-1): wait_start got_stage filled -- MMA (role S): wait_start got_item issued acc_wait_start -- "
-          "epilogue (role S+1): wait_start got_tile done")
+    print("columns: producers (roles 0..7): wait_start got_stage filled -- epilogue (role 9): wait_start got_tile done -- "
+          "MMA issuers (roles 10, 11): wait_start got_item issued acc_wait_start")
     for role in range(16):
         if not (tr[role] > 0).any():
             continue
