@@ -402,11 +402,20 @@ def run_ours(args):
 
     res_ring = [torch.empty((), dtype=torch.float32, pin_memory=True) for _ in range(4)]
 
+    host_prof = {} if os.environ.get("MM3D_BENCH_HOST_PROFILE") else None
+
+    def _tick(name, t0):
+        if host_prof is not None:
+            host_prof.setdefault(name, []).append(time.perf_counter() - t0)
+        return time.perf_counter()
+
     def step_e2e(i):
+        t = time.perf_counter()
         if i not in pending:
             upload(i)
         locs_d, feats_d, ev, prep = pending.pop(i)
         upload(i + 1)
+        t = _tick("upload+prepare(i+1)", t)
         torch.cuda.current_stream().wait_event(ev)
         locs_d.record_stream(torch.cuda.current_stream())
         feats_d.record_stream(torch.cuda.current_stream())
@@ -414,13 +423,17 @@ def run_ours(args):
         flat.zero_()
         x = feats_d.requires_grad_(True)
         out = net([prep if args.pipeline else locs_d, x])
+        t = _tick("forward", t)
         out.backward(gout)
+        t = _tick("backward", t)
         flat.all_reduce_mean()
+        t = _tick("all_reduce", t)
         res = (out.detach() * gout).sum()  # the step's scalar result ...
         host_res = res_ring[i % len(res_ring)]  # pinned once: page-locking per step serialises in the driver at N > 1
         host_res.copy_(res, non_blocking=True)  # ... goes back to the host; it is waited for (and used) one step later,
         done = torch.cuda.Event()               # after the next step has been enqueued (lazy loss logging)
         done.record()
+        _tick("result", t)
         return host_res, done
 
     def barrier():
@@ -478,13 +491,19 @@ def run_ours(args):
         for i in range(base + n_pre, base + n_pre + steps):
             cur = step_e2e(i)
             if prev is not None:
+                tw = time.perf_counter()
                 prev[1].synchronize()
                 acc += float(prev[0])
+                _tick("wait(previous step)", tw)
             prev = cur
         prev[1].synchronize()
         acc += float(prev[0])
         barrier()
         dt = (time.perf_counter() - t0) * 1e3
+        if host_prof:
+            print(f"[rank {rank}] e2e host phases, median ms over {steps} steps: " +
+                  ", ".join(f"{k} {1e3 * sorted(v)[len(v) // 2]:.3f}" for k, v in host_prof.items()), file=sys.stderr, flush=True)
+            host_prof.clear()
         e2e_counter[0] = base + n_pre + steps
         pending.clear()
         if acc != acc:

@@ -35,7 +35,12 @@ def collect_slots(net):
             out += bn(mods[3][0]) + [mods[3][1].weight]
         return out
 
-    return [net.layer2.weight] + level(net.layer3) + bn(net.layer4)
+    cached = getattr(net, "_exec_slots", None)
+    if cached is not None and cached[0] is net.layer2.weight and cached[-1] is net.layer4.running_var:
+        return cached  # (the module walk costs ~0.1 ms per call; parameters are updated in place by optimisers / .to())
+    slots = [net.layer2.weight] + level(net.layer3) + bn(net.layer4)
+    net._exec_slots = slots
+    return slots
 
 
 def fusable(net) -> bool:
@@ -135,15 +140,16 @@ class UNetSCNFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.raise_device_errors("UNetSCN.backward")
             # one flat buffer for every parameter gradient; the returned grads are views into it
-            numels = [t.numel() if t.requires_grad else 0 for t in slots]
-            flat = torch.empty(sum(numels), dtype=torch.float32, device=dev)
-            base = flat.data_ptr()
-            gptrs, grads, off = [], [], 0
-            for t, k in zip(slots, numels):
-                if k:
-                    gptrs.append(base + 4 * off)
-                    grads.append(flat[off:off + k].view_as(t))
-                    off += k
+            live = [t for t in slots if t.requires_grad]
+            flat = torch.empty(sum(t.numel() for t in live), dtype=torch.float32, device=dev)
+            # all views in one native call (what DDP's buckets use) instead of ~130 slice + view calls
+            views = iter(torch._utils._unflatten_dense_tensors(flat, live)) if live else iter(())
+            gptrs, grads = [], []
+            for t in slots:
+                if t.requires_grad:
+                    g = next(views)
+                    gptrs.append(g.data_ptr())
+                    grads.append(g)
                 else:
                     gptrs.append(None)
                     grads.append(None)
