@@ -203,14 +203,16 @@ MM3D_API int mm3d_bnrelu_bwd(const float* x, const float* dy, float* dx, int64_t
 
 /* ------------------------------------------------------------------------------------------
  * 2D->3D lift (replaces the per-sample advanced indexing of 2d_net/model.py:131-137):
- * out[n,:] = fmap[b(n), :, idx[n,0], idx[n,1]], fmap NCHW; sample_offsets int64 [B+1] gives the
+ * out[n,:] = fmap[b(n), :, idx[n,0], idx[n,1]]; the [B, C, H, W] map is addressed through its element strides
+ * (sb, sc, sh, sw), so a channels-last map -- what cuDNN produces for the 2D network, and the layout in which a
+ * pixel's C values are one contiguous piece -- is read in place; sample_offsets int64 [B+1] gives the
  * row range of each sample in the concatenated idx; dtype 0=f32 1=f16 2=bf16 (map and out).
  * Backward scatter-adds into d_fmap (caller zero-fills), duplicates accumulate.
  * ---------------------------------------------------------------------------------------- */
-MM3D_API int mm3d_lift2d_fwd(const void* fmap, int dtype, int B, int C, int H, int W, const int64_t* idx,
-                    const int64_t* sample_offsets, int64_t n, void* out, mm3d_stream_t stream);
-MM3D_API int mm3d_lift2d_bwd(const void* d_out, int dtype, int B, int C, int H, int W, const int64_t* idx,
-                    const int64_t* sample_offsets, int64_t n, void* d_fmap, mm3d_stream_t stream);
+MM3D_API int mm3d_lift2d_fwd(const void* fmap, int dtype, int B, int C, int H, int W, int64_t sb, int64_t sc, int64_t sh,
+                    int64_t sw, const int64_t* idx, const int64_t* sample_offsets, int64_t n, void* out, mm3d_stream_t stream);
+MM3D_API int mm3d_lift2d_bwd(const void* d_out, int dtype, int B, int C, int H, int W, int64_t sb, int64_t sc, int64_t sh,
+                    int64_t sw, const int64_t* idx, const int64_t* sample_offsets, int64_t n, void* d_fmap, mm3d_stream_t stream);
 
 /* Point values -> image (the loaders' sparse depth and 2D label maps, lib/dataset/nuscenes_dataloader.py:275-278):
  * out[b, idx[i,0], idx[i,1]] = vals[i] over a map pre-filled with `fill`; where several points share a pixel the

@@ -15,66 +15,118 @@ int* mm3d_device_err_flag();  // conv_tc.cu
 namespace {
 
 // ------------------------------------------------------------------ InputLayer
-__global__ void k_input_fwd(const float* __restrict__ feats, const int32_t* __restrict__ p2v,
-                            const int32_t* __restrict__ npts, int64_t n_points, int c, int mode,
-                            float* __restrict__ out) {
+// One thread per point, 4 points per thread in flight: the point's C features are read as one contiguous piece and
+// written to its voxel's row -- a plain store when the point is alone in its voxel (88 % of the points), atomics
+// otherwise (the row was zeroed by the launch's memset).  No per-element index division.
+template <int C>
+__global__ void __launch_bounds__(256)
+k_input_fwd(const float* __restrict__ feats, const int32_t* __restrict__ p2v, const int32_t* __restrict__ npts,
+            int64_t n_points, int c_rt, int mode, float* __restrict__ out) {
   mm3d_griddep_wait();
-  const int64_t total = n_points * c;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = i / c;
-    const int ch = (int)(i - p * c);
+  const int c = C > 0 ? C : c_rt;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_points; p += stride) {
     const int32_t v = __ldg(p2v + p);
     const int32_t cnt = __ldg(npts + v);
-    const float f = __ldg(feats + i);
-    if (cnt == 1) {
-      out[(int64_t)v * c + ch] = f;  // sole contributor: plain store, no RMW
+    const float* src = feats + p * c;
+    float* dst = out + (int64_t)v * c;
+    if (C > 0) {
+      float f[C > 0 ? C : 1];
+#pragma unroll
+      for (int j = 0; j < C; ++j) f[j] = __ldg(src + j);
+      if (cnt == 1) {
+#pragma unroll
+        for (int j = 0; j < C; ++j) dst[j] = f[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < C; ++j) atomicAdd(dst + j, mode == 4 ? f[j] / (float)cnt : f[j]);
+      }
     } else {
-      atomicAdd(out + (int64_t)v * c + ch, mode == 4 ? f / (float)cnt : f);
+      for (int j = 0; j < c; ++j) {
+        const float f = __ldg(src + j);
+        if (cnt == 1) dst[j] = f;
+        else atomicAdd(dst + j, mode == 4 ? f / (float)cnt : f);
+      }
     }
   }
 }
 
-__global__ void k_input_bwd(const float* __restrict__ d_vox, const int32_t* __restrict__ p2v,
-                            const int32_t* __restrict__ npts, int64_t n_points, int c, int mode,
-                            float* __restrict__ d_feats) {
+template <int C>
+__global__ void __launch_bounds__(256)
+k_input_bwd(const float* __restrict__ d_vox, const int32_t* __restrict__ p2v, const int32_t* __restrict__ npts,
+            int64_t n_points, int c_rt, int mode, float* __restrict__ d_feats) {
   mm3d_griddep_wait();
-  const int64_t total = n_points * c;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = i / c;
-    const int ch = (int)(i - p * c);
+  const int c = C > 0 ? C : c_rt;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_points; p += stride) {
     const int32_t v = __ldg(p2v + p);
-    float g = __ldg(d_vox + (int64_t)v * c + ch);
-    if (mode == 4) g /= (float)__ldg(npts + v);
-    d_feats[i] = g;
+    const float* src = d_vox + (int64_t)v * c;
+    float* dst = d_feats + p * c;
+    const int32_t cnt = mode == 4 ? __ldg(npts + v) : 1;
+    if (C > 0) {
+#pragma unroll
+      for (int j = 0; j < C; ++j) dst[j] = cnt > 1 ? __ldg(src + j) / (float)cnt : __ldg(src + j);
+    } else {
+      for (int j = 0; j < c; ++j) dst[j] = cnt > 1 ? __ldg(src + j) / (float)cnt : __ldg(src + j);
+    }
   }
 }
 
 // ------------------------------------------------------------------ OutputLayer
+// cv float4 per row (cv a power of two <= 32 in the vector path): cv consecutive lanes copy one point's row, a warp
+// moves 32 / cv points per pass and every thread keeps 4 passes in flight.  32-bit index arithmetic.
 template <int VEC>
-__global__ void k_output_fwd(const float* __restrict__ vox, const int32_t* __restrict__ p2v,
-                             int64_t n_points, int cv, float* __restrict__ out) {
+__global__ void __launch_bounds__(256)
+k_output_fwd(const float* __restrict__ vox, const int32_t* __restrict__ p2v, int64_t n_points, int cv, int cv_shift,
+             float* __restrict__ out) {
   mm3d_griddep_wait();
   const int64_t total = n_points * cv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = i / cv;
-    const int ch = (int)(i - p * cv);
-    const int32_t v = __ldg(p2v + p);
-    if (VEC == 4) {
-      reinterpret_cast<float4*>(out)[i] = __ldg(reinterpret_cast<const float4*>(vox) + (int64_t)v * cv + ch);
-    } else {
-      out[i] = __ldg(vox + (int64_t)v * cv + ch);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (VEC == 4) {
+    const int ch = (int)(i & (cv - 1));  // stride is a multiple of cv: the lane keeps its channel vector
+    for (; i + 3 * stride < total; i += 4 * stride) {
+      int32_t v[4];
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(p2v + ((i + u * stride) >> cv_shift));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = __ldg(reinterpret_cast<const float4*>(vox) + ((int64_t)v[u] << cv_shift) + ch);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) reinterpret_cast<float4*>(out)[i + u * stride] = t[u];
+    }
+    for (; i < total; i += stride)
+      reinterpret_cast<float4*>(out)[i] = __ldg(reinterpret_cast<const float4*>(vox) + ((int64_t)__ldg(p2v + (i >> cv_shift)) << cv_shift) + ch);
+  } else {
+    for (; i < total; i += stride) {
+      const int64_t p = i / cv;
+      out[i] = __ldg(vox + (int64_t)__ldg(p2v + p) * cv + (int)(i - p * cv));
     }
   }
 }
 
-__global__ void k_output_bwd(const float* __restrict__ d_out, const int32_t* __restrict__ p2v,
-                             int64_t n_points, int c, float* __restrict__ d_vox) {
+// backward: voxel gradient = sum over its points.  Vector path: one red.global.add.v4.f32 per float4 (a quarter of
+// the atomics of the scalar form); d_vox was zeroed by the launch's memset.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_output_bwd(const float* __restrict__ d_out, const int32_t* __restrict__ p2v, int64_t n_points, int cv, int cv_shift,
+             float* __restrict__ d_vox) {
   mm3d_griddep_wait();
-  const int64_t total = n_points * c;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = i / c;
-    const int ch = (int)(i - p * c);
-    atomicAdd(d_vox + (int64_t)__ldg(p2v + p) * c + ch, __ldg(d_out + i));
+  const int64_t total = n_points * cv;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (VEC == 4) {
+    const int ch = (int)(i & (cv - 1));
+    for (; i < total; i += stride) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(d_out) + i);
+      float* dst = d_vox + ((((int64_t)__ldg(p2v + (i >> cv_shift)) << cv_shift) + ch) << 2);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w) : "memory");
+    }
+  } else {
+    for (; i < total; i += stride) {
+      const int64_t p = i / cv;
+      atomicAdd(d_vox + (int64_t)__ldg(p2v + p) * cv + (int)(i - p * cv), __ldg(d_out + i));
+    }
   }
 }
 
@@ -88,28 +140,38 @@ __device__ __forceinline__ int find_sample(const int64_t* __restrict__ offs, int
   return lo;
 }
 
-// one thread per (point, channel), channel fastest: the [N, C] side is coalesced; the map side
-// reads C planes at one pixel (stride H*W) -- inherent to gathering from NCHW.
-template <class T>
-__global__ void k_lift_fwd(const T* __restrict__ fmap, int B, int C, int H, int W,
-                           const int64_t* __restrict__ idx, const int64_t* __restrict__ offs, int64_t n,
-                           T* __restrict__ out, int* err) {
-  const int64_t total = n * C;
-  const int64_t hw = (int64_t)H * W;
+// One thread per (point, group of G channels), group fastest: the point's pixel index (one 16-byte load) and its
+// sample (binary search over the B + 1 offsets) are resolved once per G values, and the [N, C] side is coalesced.  The
+// map is addressed through its element strides (sb, sc, sh, sw): for a channels-last map (sc == 1, what cuDNN produces
+// for the 2D network) the C values of a pixel are one contiguous piece and a point costs one or two sectors; for a
+// channel-major map (NCHW) every value sits in its own plane -- 32 bytes moved per 4 used, inherent to that layout.
+template <class T, int G>
+__global__ void __launch_bounds__(256)
+k_lift_fwd(const T* __restrict__ fmap, int B, int C, int H, int W, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+           const int64_t* __restrict__ idx, const int64_t* __restrict__ offs, int64_t n, T* __restrict__ out, int* err) {
+  const int groups = C / G;
+  const int64_t total = n * groups;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = i / C;
-    const int ch = (int)(i - p * C);
-    const int b = find_sample(offs, B, p);
-    int64_t r = __ldg(idx + 2 * p), col = __ldg(idx + 2 * p + 1);
+    const int64_t p = total < (1ll << 31) ? (int64_t)((uint32_t)i / (uint32_t)groups) : i / groups;
+    const int ch0 = (int)(i - p * groups) * G;
+    const longlong2 rc = __ldg(reinterpret_cast<const longlong2*>(idx) + p);
+    int64_t r = rc.x, col = rc.y;
     if (r < 0) r += H;      // torch advanced indexing wraps negative indices
     if (col < 0) col += W;
+    T* dst = out + p * C + ch0;
     if ((uint64_t)r >= (uint64_t)H || (uint64_t)col >= (uint64_t)W) {
       // torch raises IndexError here (2d_net/model.py:131-137); a kernel cannot: zero row + sticky error word 1
-      out[i] = T(0.f);
-      if (ch == 0) mm3d_raise(err, 1);
+#pragma unroll
+      for (int j = 0; j < G; ++j) dst[j] = T(0.f);
+      if (ch0 == 0) mm3d_raise(err, 1);
       continue;
     }
-    out[i] = fmap[((int64_t)b * C + ch) * hw + r * W + col];
+    const T* src = fmap + find_sample(offs, B, p) * sb + ch0 * sc + r * sh + col * sw;
+    T v[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) v[j] = src[j * sc];
+#pragma unroll
+    for (int j = 0; j < G; ++j) dst[j] = v[j];
   }
 }
 
@@ -118,28 +180,49 @@ __device__ __forceinline__ void lift_atomic_add(__half* p, __half v) { atomicAdd
 __device__ __forceinline__ void lift_atomic_add(__nv_bfloat16* p, __nv_bfloat16 v) { atomicAdd(p, v); }
 
 // backward: scatter-add into the (zero-filled) map gradient; several points may share a pixel
-template <class T>
-__global__ void k_lift_bwd(const T* __restrict__ d_out, int B, int C, int H, int W,
-                           const int64_t* __restrict__ idx, const int64_t* __restrict__ offs, int64_t n,
-                           T* __restrict__ d_fmap, int* err) {
-  const int64_t total = n * C;
-  const int64_t hw = (int64_t)H * W;
+template <class T, int G>
+__global__ void __launch_bounds__(256)
+k_lift_bwd(const T* __restrict__ d_out, int B, int C, int H, int W, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+           const int64_t* __restrict__ idx, const int64_t* __restrict__ offs, int64_t n, T* __restrict__ d_fmap, int* err) {
+  const int groups = C / G;
+  const int64_t total = n * groups;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = i / C;
-    const int ch = (int)(i - p * C);
-    const int b = find_sample(offs, B, p);
-    int64_t r = __ldg(idx + 2 * p), col = __ldg(idx + 2 * p + 1);
+    const int64_t p = total < (1ll << 31) ? (int64_t)((uint32_t)i / (uint32_t)groups) : i / groups;
+    const int ch0 = (int)(i - p * groups) * G;
+    const longlong2 rc = __ldg(reinterpret_cast<const longlong2*>(idx) + p);
+    int64_t r = rc.x, col = rc.y;
     if (r < 0) r += H;
     if (col < 0) col += W;
     if ((uint64_t)r >= (uint64_t)H || (uint64_t)col >= (uint64_t)W) {  // skipped + sticky error word 1
-      if (ch == 0) mm3d_raise(err, 1);
+      if (ch0 == 0) mm3d_raise(err, 1);
       continue;
     }
-    lift_atomic_add(d_fmap + ((int64_t)b * C + ch) * hw + r * W + col, d_out[i]);
+    const T* src = d_out + p * C + ch0;
+    T* dst = d_fmap + find_sample(offs, B, p) * sb + ch0 * sc + r * sh + col * sw;
+    T v[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) v[j] = src[j];
+#pragma unroll
+    for (int j = 0; j < G; ++j) lift_atomic_add(dst + j * sc, v[j]);
   }
 }
 
+// channels per thread: contiguous channels (sc == 1, channels-last) in groups of 4 or 2; one per thread for a
+// channel-major map, where neighbouring threads should walk neighbouring planes of one pixel
+#define LIFT_DISPATCH(KERNEL, T, ...)                                                                               \
+  do {                                                                                                              \
+    if (sc == 1 && C % 4 == 0) KERNEL<T, 4><<<mm3d_grid(n * (C / 4), 256, 16), 256, 0, stream>>>(__VA_ARGS__);      \
+    else if (sc == 1 && C % 2 == 0) KERNEL<T, 2><<<mm3d_grid(n * (C / 2), 256, 16), 256, 0, stream>>>(__VA_ARGS__); \
+    else KERNEL<T, 1><<<mm3d_grid(n * C, 256, 16), 256, 0, stream>>>(__VA_ARGS__);                                  \
+  } while (0)
+
 }  // namespace
+
+static int pow2_shift(int v) {  // log2 of a power of two <= 32, else -1
+  for (int sft = 0; sft <= 5; ++sft)
+    if ((1 << sft) == v) return sft;
+  return -1;
+}
 
 extern "C" int mm3d_input_fwd(const float* feats, const int32_t* p2v, const int32_t* npts, int64_t n_points,
                               int64_t n_vox, int c, int mode, float* out_vox, mm3d_stream_t stream_) {
@@ -147,8 +230,12 @@ extern "C" int mm3d_input_fwd(const float* feats, const int32_t* p2v, const int3
   MM3D_REQUIRE(mode == 3 || mode == 4, MM3D_ERR_UNSUPPORTED, "InputLayer mode %d not implemented (3=sum, 4=mean)", mode);
   MM3D_REQUIRE(c > 0 && n_points >= 0 && n_vox >= 0, MM3D_ERR_INVALID, "bad sizes");
   if (n_vox > 0) MM3D_CUDA(cudaMemsetAsync(out_vox, 0, sizeof(float) * (size_t)n_vox * c, stream));
-  if (n_points > 0)
-    MM3D_CUDA(mm3d_launch_pdl(k_input_fwd, dim3(mm3d_grid(n_points * c, 256)), dim3(256), 0, stream, feats, p2v, npts, n_points, c, mode, out_vox));
+  if (n_points > 0) {
+    const dim3 grid(mm3d_grid(n_points, 256, 16)), block(256);
+    if (c == 3) MM3D_CUDA(mm3d_launch_pdl(k_input_fwd<3>, grid, block, 0, stream, feats, p2v, npts, n_points, c, mode, out_vox));
+    else if (c == 1) MM3D_CUDA(mm3d_launch_pdl(k_input_fwd<1>, grid, block, 0, stream, feats, p2v, npts, n_points, c, mode, out_vox));
+    else MM3D_CUDA(mm3d_launch_pdl(k_input_fwd<0>, grid, block, 0, stream, feats, p2v, npts, n_points, c, mode, out_vox));
+  }
   mm3d_count_launches(n_points > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_input_fwd");
   return MM3D_OK;
@@ -158,8 +245,12 @@ extern "C" int mm3d_input_bwd(const float* d_vox, const int32_t* p2v, const int3
                               int c, int mode, float* d_feats, mm3d_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MM3D_REQUIRE(mode == 3 || mode == 4, MM3D_ERR_UNSUPPORTED, "InputLayer mode %d not implemented", mode);
-  if (n_points > 0)
-    MM3D_CUDA(mm3d_launch_pdl(k_input_bwd, dim3(mm3d_grid(n_points * c, 256)), dim3(256), 0, stream, d_vox, p2v, npts, n_points, c, mode, d_feats));
+  if (n_points > 0) {
+    const dim3 grid(mm3d_grid(n_points, 256, 16)), block(256);
+    if (c == 3) MM3D_CUDA(mm3d_launch_pdl(k_input_bwd<3>, grid, block, 0, stream, d_vox, p2v, npts, n_points, c, mode, d_feats));
+    else if (c == 1) MM3D_CUDA(mm3d_launch_pdl(k_input_bwd<1>, grid, block, 0, stream, d_vox, p2v, npts, n_points, c, mode, d_feats));
+    else MM3D_CUDA(mm3d_launch_pdl(k_input_bwd<0>, grid, block, 0, stream, d_vox, p2v, npts, n_points, c, mode, d_feats));
+  }
   mm3d_count_launches(n_points > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_input_bwd");
   return MM3D_OK;
@@ -169,11 +260,13 @@ extern "C" int mm3d_output_fwd(const float* vox, const int32_t* p2v, int64_t n_p
                                mm3d_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_points > 0) {
-    const bool vec = (c % 4 == 0) && (((uintptr_t)vox | (uintptr_t)out) & 15) == 0;
-    if (vec)
-      MM3D_CUDA(mm3d_launch_pdl(k_output_fwd<4>, dim3(mm3d_grid(n_points * (c / 4), 256)), dim3(256), 0, stream, vox, p2v, n_points, c / 4, out));
+    const int sft = (c % 4 == 0) ? pow2_shift(c / 4) : -1;
+    const bool vec = sft >= 0 && (((uintptr_t)vox | (uintptr_t)out) & 15) == 0;
+    if (vec)  // a quarter of the threads of one-float4-per-thread: every thread keeps 4 float4 in flight
+      MM3D_CUDA(mm3d_launch_pdl(k_output_fwd<4>, dim3(mm3d_grid(n_points * (c / 4) / 4 + 1, 256, 16)), dim3(256), 0, stream, vox, p2v,
+                                n_points, c / 4, sft, out));
     else
-      MM3D_CUDA(mm3d_launch_pdl(k_output_fwd<1>, dim3(mm3d_grid(n_points * c, 256)), dim3(256), 0, stream, vox, p2v, n_points, c, out));
+      MM3D_CUDA(mm3d_launch_pdl(k_output_fwd<1>, dim3(mm3d_grid(n_points * c, 256)), dim3(256), 0, stream, vox, p2v, n_points, c, 0, out));
   }
   mm3d_count_launches(n_points > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_output_fwd");
@@ -184,24 +277,34 @@ extern "C" int mm3d_output_bwd(const float* d_out, const int32_t* p2v, int64_t n
                                float* d_vox, mm3d_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_vox > 0) MM3D_CUDA(cudaMemsetAsync(d_vox, 0, sizeof(float) * (size_t)n_vox * c, stream));
-  if (n_points > 0)
-    MM3D_CUDA(mm3d_launch_pdl(k_output_bwd, dim3(mm3d_grid(n_points * c, 256)), dim3(256), 0, stream, d_out, p2v, n_points, c, d_vox));
+  if (n_points > 0) {
+    const int sft = (c % 4 == 0) ? pow2_shift(c / 4) : -1;
+    const bool vec = sft >= 0 && (((uintptr_t)d_vox | (uintptr_t)d_out) & 15) == 0;
+    if (vec)
+      MM3D_CUDA(mm3d_launch_pdl(k_output_bwd<4>, dim3(mm3d_grid(n_points * (c / 4), 256, 16)), dim3(256), 0, stream, d_out, p2v, n_points,
+                                c / 4, sft, d_vox));
+    else
+      MM3D_CUDA(mm3d_launch_pdl(k_output_bwd<1>, dim3(mm3d_grid(n_points * c, 256)), dim3(256), 0, stream, d_out, p2v, n_points, c, 0, d_vox));
+  }
   mm3d_count_launches(n_points > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_output_bwd");
   return MM3D_OK;
 }
 
-extern "C" int mm3d_lift2d_fwd(const void* fmap, int dtype, int B, int C, int H, int W, const int64_t* idx,
-                               const int64_t* sample_offsets, int64_t n, void* out, mm3d_stream_t stream_) {
+// strides in ELEMENTS of the [B, C, H, W] map (a contiguous NCHW map: C*H*W, H*W, W, 1; channels-last: H*W*C, 1, W*C, C)
+extern "C" int mm3d_lift2d_fwd(const void* fmap, int dtype, int B, int C, int H, int W, int64_t sb, int64_t sc, int64_t sh,
+                               int64_t sw, const int64_t* idx, const int64_t* sample_offsets, int64_t n, void* out,
+                               mm3d_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MM3D_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && n >= 0, MM3D_ERR_INVALID, "bad lift sizes");
+  MM3D_REQUIRE(sb > 0 && sc > 0 && sh > 0 && sw > 0, MM3D_ERR_INVALID, "bad lift strides");
   if (n == 0) return MM3D_OK;
   int* err = mm3d_device_err_flag();
-  const int grid = mm3d_grid(n * C, 256);
+  MM3D_REQUIRE((((uintptr_t)idx) & 15) == 0, MM3D_ERR_INVALID, "lift: the index array must be 16-byte aligned");
   switch (dtype) {
-    case 0: k_lift_fwd<float><<<grid, 256, 0, stream>>>((const float*)fmap, B, C, H, W, idx, sample_offsets, n, (float*)out, err); break;
-    case 1: k_lift_fwd<__half><<<grid, 256, 0, stream>>>((const __half*)fmap, B, C, H, W, idx, sample_offsets, n, (__half*)out, err); break;
-    case 2: k_lift_fwd<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)fmap, B, C, H, W, idx, sample_offsets, n, (__nv_bfloat16*)out, err); break;
+    case 0: LIFT_DISPATCH(k_lift_fwd, float, (const float*)fmap, B, C, H, W, sb, sc, sh, sw, idx, sample_offsets, n, (float*)out, err); break;
+    case 1: LIFT_DISPATCH(k_lift_fwd, __half, (const __half*)fmap, B, C, H, W, sb, sc, sh, sw, idx, sample_offsets, n, (__half*)out, err); break;
+    case 2: LIFT_DISPATCH(k_lift_fwd, __nv_bfloat16, (const __nv_bfloat16*)fmap, B, C, H, W, sb, sc, sh, sw, idx, sample_offsets, n, (__nv_bfloat16*)out, err); break;
     default: MM3D_REQUIRE(false, MM3D_ERR_UNSUPPORTED, "lift dtype %d (0=f32,1=f16,2=bf16)", dtype);
   }
   mm3d_count_launches(1);
@@ -209,17 +312,19 @@ extern "C" int mm3d_lift2d_fwd(const void* fmap, int dtype, int B, int C, int H,
   return MM3D_OK;
 }
 
-extern "C" int mm3d_lift2d_bwd(const void* d_out, int dtype, int B, int C, int H, int W, const int64_t* idx,
-                               const int64_t* sample_offsets, int64_t n, void* d_fmap, mm3d_stream_t stream_) {
+extern "C" int mm3d_lift2d_bwd(const void* d_out, int dtype, int B, int C, int H, int W, int64_t sb, int64_t sc, int64_t sh,
+                               int64_t sw, const int64_t* idx, const int64_t* sample_offsets, int64_t n, void* d_fmap,
+                               mm3d_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   MM3D_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && n >= 0, MM3D_ERR_INVALID, "bad lift sizes");
+  MM3D_REQUIRE(sb > 0 && sc > 0 && sh > 0 && sw > 0, MM3D_ERR_INVALID, "bad lift strides");
   if (n == 0) return MM3D_OK;
   int* err = mm3d_device_err_flag();
-  const int grid = mm3d_grid(n * C, 256);
+  MM3D_REQUIRE((((uintptr_t)idx) & 15) == 0, MM3D_ERR_INVALID, "lift: the index array must be 16-byte aligned");
   switch (dtype) {
-    case 0: k_lift_bwd<float><<<grid, 256, 0, stream>>>((const float*)d_out, B, C, H, W, idx, sample_offsets, n, (float*)d_fmap, err); break;
-    case 1: k_lift_bwd<__half><<<grid, 256, 0, stream>>>((const __half*)d_out, B, C, H, W, idx, sample_offsets, n, (__half*)d_fmap, err); break;
-    case 2: k_lift_bwd<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)d_out, B, C, H, W, idx, sample_offsets, n, (__nv_bfloat16*)d_fmap, err); break;
+    case 0: LIFT_DISPATCH(k_lift_bwd, float, (const float*)d_out, B, C, H, W, sb, sc, sh, sw, idx, sample_offsets, n, (float*)d_fmap, err); break;
+    case 1: LIFT_DISPATCH(k_lift_bwd, __half, (const __half*)d_out, B, C, H, W, sb, sc, sh, sw, idx, sample_offsets, n, (__half*)d_fmap, err); break;
+    case 2: LIFT_DISPATCH(k_lift_bwd, __nv_bfloat16, (const __nv_bfloat16*)d_out, B, C, H, W, sb, sc, sh, sw, idx, sample_offsets, n, (__nv_bfloat16*)d_fmap, err); break;
     default: MM3D_REQUIRE(false, MM3D_ERR_UNSUPPORTED, "lift dtype %d (0=f32,1=f16,2=bf16)", dtype);
   }
   mm3d_count_launches(1);

@@ -251,21 +251,29 @@ class BatchNormReLUFn(torch.autograd.Function):
 _LIFT_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 
 
+def _dense_map(t):
+    """The map as it is when its memory is dense in NCHW or channels-last (NHWC) order, else a contiguous copy."""
+    if t.is_contiguous() or t.is_contiguous(memory_format=torch.channels_last):
+        return t
+    return t.contiguous()
+
+
 class Lift2DFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, fmap, idx, offsets):
         _require_cuda(fmap, "lift2d")
         if fmap.dtype not in _LIFT_DTYPES:
             raise TypeError(f"lift2d: unsupported dtype {fmap.dtype}")
-        fmap = fmap.contiguous()
+        fmap = _dense_map(fmap)  # channels-last maps (cuDNN's layout for the 2D network) are gathered in place
         B, C, H, W = fmap.shape
         n = idx.shape[0]
         out = torch.empty(n, C, dtype=fmap.dtype, device=fmap.device)
         with torch.cuda.device(fmap.device):
-            check(lib.mm3d_lift2d_fwd(ptr(fmap), _LIFT_DTYPES[fmap.dtype], B, C, H, W, ptr(idx), ptr(offsets), n,
+            check(lib.mm3d_lift2d_fwd(ptr(fmap), _LIFT_DTYPES[fmap.dtype], B, C, H, W, *fmap.stride(), ptr(idx), ptr(offsets), n,
                                       ptr(out), _lib.stream_ptr()), "mm3d_lift2d_fwd")
         ctx.save_for_backward(idx, offsets)
         ctx.shape = (B, C, H, W)
+        ctx.channels_last = not fmap.is_contiguous()
         return out
 
     @staticmethod
@@ -273,8 +281,10 @@ class Lift2DFn(torch.autograd.Function):
         idx, offsets = ctx.saved_tensors
         B, C, H, W = ctx.shape
         d_out = d_out.contiguous()
-        d_fmap = torch.zeros(B, C, H, W, dtype=d_out.dtype, device=d_out.device)
+        # the gradient has the map's memory format: the scatter-add then touches one contiguous piece per point
+        d_fmap = torch.empty(B, C, H, W, dtype=d_out.dtype, device=d_out.device,
+                             memory_format=torch.channels_last if ctx.channels_last else torch.contiguous_format).zero_()
         with torch.cuda.device(d_out.device):
-            check(lib.mm3d_lift2d_bwd(ptr(d_out), _LIFT_DTYPES[d_out.dtype], B, C, H, W, ptr(idx), ptr(offsets),
+            check(lib.mm3d_lift2d_bwd(ptr(d_out), _LIFT_DTYPES[d_out.dtype], B, C, H, W, *d_fmap.stride(), ptr(idx), ptr(offsets),
                                       idx.shape[0], ptr(d_fmap), _lib.stream_ptr()), "mm3d_lift2d_bwd")
         return d_fmap, None, None

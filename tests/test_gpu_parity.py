@@ -326,6 +326,26 @@ def test_lift2d_reference_fixture(dtype):
     assert torch.equal(lift2d(fmap, li), out)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_lift2d_channels_last_map(dtype):
+    """A channels-last map (what cuDNN produces for the 2D network) is gathered in place through its strides; results
+    and gradients equal those of the contiguous map, and the gradient comes back in the map's memory format."""
+    from mm2d3d_b200.lift import lift2d
+    torch.manual_seed(4)
+    fmap = torch.randn(3, 6, 45, 80, device=DEV).to(dtype)
+    idx = synth.make_img_indices([700, 0, 300], 45, 80, seed=3)
+    a = fmap.clone().requires_grad_(True)
+    b = fmap.clone().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    ra, rb = lift2d(a, idx), lift2d(b, idx)
+    assert torch.equal(ra, rb)
+    assert torch.equal(ra.detach().cpu(), lift_oracle.lift2d(fmap.cpu(), idx))
+    g = torch.randn_like(ra)
+    (ga,) = torch.autograd.grad(ra, a, g)
+    (gb,) = torch.autograd.grad(rb, b, g)
+    assert gb.is_contiguous(memory_format=torch.channels_last)
+    assert rel_err(gb, ga) < (1e-6 if dtype == torch.float32 else 2e-2)
+
+
 def test_lift2d_benchmark_shape():
     from mm2d3d_b200.lift import lift2d
     torch.manual_seed(3)

@@ -76,6 +76,23 @@ def main():
     timed("OutputLayer bwd, C=16", 64 * n0 + 64 * n + 4 * n,
           lambda: _lib.check(lib.mm3d_output_bwd(ptr(dO), meta.p2v_ptr, n, n0, 16, ptr(dZ), sp)))
 
+    # the same kernels on 8x the points (2.2 M points): at the bench's size (8 - 34 MB) these launches are bounded by
+    # launch latency (~4 us at 6.5 TB/s would already be 100 %), the large size shows what the kernels themselves reach
+    rep = 8
+    p2v_big = torch.cat([meta.p2v().int() + r * n0 for r in range(rep)]).contiguous()
+    npts_big = meta.npts().int().repeat(rep).contiguous()
+    nb_, n0b = n * rep, n0 * rep
+    feats_b, Vb = feats_d.repeat(rep, 1).contiguous(), torch.empty(n0 * rep, 3, device=DEV)
+    timed(f"InputLayer fwd, C=3, {nb_} points", nb_ * (4 + 12) + 4 * n0b + 12 * n0b,
+          lambda: _lib.check(lib.mm3d_input_fwd(ptr(feats_b), ptr(p2v_big), ptr(npts_big), nb_, n0b, 3, 4, ptr(Vb), sp)))
+    Zb, Ob = torch.randn(n0b, 16, device=DEV), torch.empty(nb_, 16, device=DEV)
+    timed(f"OutputLayer fwd, C=16, {nb_} points", 64 * n0b + 64 * nb_ + 4 * nb_,
+          lambda: _lib.check(lib.mm3d_output_fwd(ptr(Zb), ptr(p2v_big), nb_, 16, ptr(Ob), sp)))
+    dOb, dZb = torch.randn(nb_, 16, device=DEV), torch.empty(n0b, 16, device=DEV)
+    timed(f"OutputLayer bwd, C=16, {nb_} points", 64 * n0b + 64 * nb_ + 4 * nb_,
+          lambda: _lib.check(lib.mm3d_output_bwd(ptr(dOb), ptr(p2v_big), nb_, n0b, 16, ptr(dZb), sp)))
+    del feats_b, Vb, Zb, Ob, dOb, dZb
+
     # ---- BatchNorm + ReLU, training, at the sizes of levels 0, 2 and 5
     for lvl, c in ((0, 16), (0, 32), (2, 48), (2, 96), (5, 96)):
         rows_l = counts[lvl]
@@ -99,17 +116,20 @@ def main():
     per = [int((locs[:, 3] == b).sum()) for b in range(8)]
     li = LiftIndices(synth.make_img_indices(per, 225, 400, seed=0), DEV)
     for C_, dt, name in ((6, torch.float32, "f32"), (6, torch.float16, "f16"), (64, torch.float32, "f32")):
-        fmap = torch.randn(8, C_, 225, 400, device=DEV).to(dt)
-        out = torch.empty(li.n, C_, dtype=dt, device=DEV)
-        es = fmap.element_size()
-        code = {torch.float32: 0, torch.float16: 1}[dt]
-        timed(f"lift2d fwd [8,{C_},225,400] {name}, {li.n} points", li.n * (16 + 2 * es * C_),
-              lambda: _lib.check(lib.mm3d_lift2d_fwd(ptr(fmap), code, 8, C_, 225, 400, ptr(li.idx), ptr(li.offsets), li.n, ptr(out), sp)),
-              note="gather of single elements from a channel-major map: sector-bound (32 B moved per 4 B used)")
-        dmap = torch.zeros_like(fmap)
-        timed(f"lift2d bwd [8,{C_},225,400] {name}", li.n * (16 + 3 * es * C_),
-              lambda: _lib.check(lib.mm3d_lift2d_bwd(ptr(out), code, 8, C_, 225, 400, ptr(li.idx), ptr(li.offsets), li.n, ptr(dmap), sp)),
-              note="atomics")
+        for fmt, fname in ((torch.contiguous_format, "NCHW"), (torch.channels_last, "channels-last")):
+            fmap = torch.randn(8, C_, 225, 400, device=DEV).to(dt).contiguous(memory_format=fmt)
+            out = torch.empty(li.n, C_, dtype=dt, device=DEV)
+            es = fmap.element_size()
+            code = {torch.float32: 0, torch.float16: 1}[dt]
+            note = ("single elements from a channel-major map: sector-bound (32 B moved per 4 B used)" if fname == "NCHW"
+                    else "a pixel's channels are one contiguous piece")
+            timed(f"lift2d fwd [8,{C_},225,400] {name} {fname}", li.n * (16 + 2 * es * C_),
+                  lambda: _lib.check(lib.mm3d_lift2d_fwd(ptr(fmap), code, 8, C_, 225, 400, *fmap.stride(), ptr(li.idx), ptr(li.offsets),
+                                                         li.n, ptr(out), sp)), note=note)
+            dmap = torch.zeros_like(fmap)
+            timed(f"lift2d bwd [8,{C_},225,400] {name} {fname}", li.n * (16 + 3 * es * C_),
+                  lambda: _lib.check(lib.mm3d_lift2d_bwd(ptr(out), code, 8, C_, 225, 400, *dmap.stride(), ptr(li.idx), ptr(li.offsets),
+                                                         li.n, ptr(dmap), sp)), note="atomics")
     vals = torch.rand(li.n, device=DEV)
     timed("rasterize_points [8,225,400]", li.n * (16 + 4) + 2 * 4 * 8 * 225 * 400, lambda: rasterize_points(li, vals, 225, 400, 0.0),
           note="3 launches + allocation")
