@@ -410,6 +410,7 @@ int pow2_cols(int n) {
 #ifdef MM3D_TRACE
 static long long* g_trace = nullptr;
 extern "C" __attribute__((visibility("default"))) void mm3d_debug_set_trace(long long* p) { g_trace = p; }
+long long* mm3d_debug_trace_ptr() { return g_trace; }
 #endif
 
 // Tensor map of a row-major [rows, c] float32 feature tensor for row gathers: box = {32 channels, 1 row} (a

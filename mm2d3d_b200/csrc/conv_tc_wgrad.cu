@@ -60,7 +60,19 @@ struct WgParams {
   int groups;       // offset groups; group g owns the offsets of gmask[g]; its CTAs are decided in the kernel
   uint32_t gmask[32];
   int* err;
+#ifdef MM3D_TRACE
+  long long* trace;  // development builds: clock64 stamps of CTA 0's roles, [role][64 records][4]
+#endif
 };
+
+#ifdef MM3D_TRACE
+#define TRACE(role, rec, slot)                                                                                   \
+  do {                                                                                                           \
+    if (p.trace && blockIdx.x == 0 && lane == 0 && (rec) < 64) p.trace[(((role) * 64) + (rec)) * 4 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define TRACE(role, rec, slot) do {} while (0)
+#endif
 
 // tiles of this CTA that contain at least one offset of its group, in order
 struct TileWalk {
@@ -103,22 +115,47 @@ struct ItemWalk {
   }
 };
 
-// 16 rows x (one 32-channel block) of a stage: row r of the block receives chunks [0, W) of the source row
-// `rowv` of lane (r - row0) (or zeros when negative).  W = 8: 8 lanes per row, 4 rows per pass, 4 passes;
-// W = 4: 4 lanes per row, 8 rows per pass, 2 passes.
-template <int W>
-__device__ __forceinline__ void gather16(uint32_t block_base, int row0, int rowv, const float* __restrict__ base,
-                                         const float* __restrict__ src0, uint32_t row_floats, int lane) {
-  constexpr int kRowsPerPass = 32 / W, kPasses = kRowsPerWarp / kRowsPerPass;
-  const int c = lane & (W - 1), rsub = lane / W;
+// This warp's 16 rows of one operand tile (gathered input rows or dout rows): `nblk` 32-channel blocks, kBlockBytes
+// apart, the last one 16 channels wide when `last_half`.  Lanes 0..15 hold the 16 source rows in `rowv` (negative =
+// absent: zeros).  Row indices and source pointers are resolved ONCE per pass (4 shuffles + 4 address computations for
+// the full-width blocks) and every block then costs one cp.async per pass: the copies go out back to back instead of
+// each behind its own shuffle -> compare -> multiply chain (measured: the producers, not the MMA issuer, bound the
+// kernel, at ~100 cycles per copy).  Full blocks: 8 lanes per row, 4 rows per pass; the 16-channel tail: 4 lanes per
+// row, 8 rows per pass, a quarter-warp holding rows x and x + 2 (their 32-byte granules do not share banks).
+__device__ __forceinline__ void gather_rows16(uint32_t tile_base, int row0, int rowv, const float* __restrict__ src0,
+                                              uint32_t row_floats, int nblk, bool last_half, int lane) {
+  const int nfull = last_half ? nblk - 1 : nblk;
+  {
+    const int c = lane & 7, rsub = lane >> 3;
+    const float* ptr[4];
+    uint32_t dst[4];
+    bool absent[4];
 #pragma unroll
-  for (int u = 0; u < kPasses; ++u) {
-    const int rl = u * kRowsPerPass + rsub;
-    const int row = __shfl_sync(0xffffffffu, rowv, rl);
-    const int r = row0 + rl;
-    const bool ok = row >= 0;
-    cp_async16(block_base + (uint32_t)r * 128u + swz_base32(c, r), ok ? src0 + (size_t)(uint32_t)row * row_floats + c * 4 : base,
-               ok ? 16u : 0u);
+    for (int u = 0; u < 4; ++u) {
+      const int rl = u * 4 + rsub;
+      const int row = __shfl_sync(0xffffffffu, rowv, rl);
+      const int r = row0 + rl;
+      absent[u] = row < 0;
+      ptr[u] = src0 + (size_t)(uint32_t)max(row, 0) * row_floats + c * 4;
+      dst[u] = tile_base + (uint32_t)r * 128u + swz_base32(c, r);
+    }
+#pragma unroll 1
+    for (int j = 0; j < nfull; ++j) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cp_async16_zfill(dst[u] + (uint32_t)j * kBlockBytes, ptr[u] + j * 32, absent[u]);
+    }
+  }
+  if (last_half) {
+    const int c = lane & 3, q = lane >> 2;
+    const int rsub = (q & 4) | ((q & 1) << 1) | ((q >> 1) & 1);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int rl = u * 8 + rsub;
+      const int row = __shfl_sync(0xffffffffu, rowv, rl);
+      const int r = row0 + rl;
+      cp_async16_zfill(tile_base + (uint32_t)nfull * kBlockBytes + (uint32_t)r * 128u + swz_base32(c, r),
+                       src0 + (size_t)(uint32_t)max(row, 0) * row_floats + nfull * 32 + c * 4, row < 0);
+    }
   }
 }
 
@@ -261,30 +298,23 @@ k_wgrad_tc(const WgParams p) {
         en = it.h ? e : __ldg(p.tbl + (int64_t)it.k * p.tstride + (int64_t)it.t.tile * kTileM + row0 + lane);
         if (it.first) prn = __ldg(p.perm + (int64_t)it.t.tile * kTileM + row0 + lane);
       }
+      TRACE(warp, n_item, 0);
       if (first) {  // the tile's dout rows, shared by all offsets of the group
         const int buf = (int)(gi % (uint32_t)p.gbufs);
         if (!mbar_wait(g_empty(buf), ((gi / (uint32_t)p.gbufs) & 1u) ^ 1u, abort_flag)) goto done;
         const uint32_t gb = g_base + (uint32_t)buf * g_bytes;
-#pragma unroll 1
-        for (int jb = 0; jb < p.gblocks; ++jb) {
-          const bool half = (jb == p.gblocks - 1) && p.g_last_w == 4;
-          if (!half) gather16<8>(gb + (uint32_t)jb * kBlockBytes, row0, pr, p.dout, p.dout + jb * 32, (uint32_t)p.c_out, lane);
-          else       gather16<4>(gb + (uint32_t)jb * kBlockBytes, row0, pr, p.dout, p.dout + jb * 32, (uint32_t)p.c_out, lane);
-        }
+        gather_rows16(gb, row0, pr, p.dout, (uint32_t)p.c_out, p.gblocks, p.g_last_w == 4, lane);
         cp_async_arrive(g_full(buf));
         ++gi;
       }
       const int s = (int)(n_item % (uint32_t)S);
+      TRACE(warp, n_item, 1);
       if (!mbar_wait(a_empty(s), ((n_item / (uint32_t)S) & 1u) ^ 1u, abort_flag)) goto done;
+      TRACE(warp, n_item, 2);
       const uint32_t stage = a_base + (uint32_t)s * a_bytes;
-      const float* src0 = p.in + h * p.cm;
-#pragma unroll 1
-      for (int j = 0; j < p.nbi; ++j) {
-        const bool half = (j == p.nbi - 1) && p.last_w == 4;
-        if (!half) gather16<8>(stage + (uint32_t)j * kBlockBytes, row0, e, p.in, src0 + j * 32, (uint32_t)p.c_in, lane);
-        else       gather16<4>(stage + (uint32_t)j * kBlockBytes, row0, e, p.in, src0 + j * 32, (uint32_t)p.c_in, lane);
-      }
+      gather_rows16(stage, row0, e, p.in + h * p.cm, (uint32_t)p.c_in, p.nbi, p.last_w == 4, lane);
       cp_async_arrive(a_full(s));
+      TRACE(warp, n_item, 3);
       e = en;
       pr = prn;
       ++n_item;
@@ -299,6 +329,7 @@ k_wgrad_tc(const WgParams p) {
     for (int o = 16; o > 0; o >>= 1) seen |= __shfl_xor_sync(0xffffffffu, seen, o);
     if (seen == 0) goto done;
     if (!mbar_wait_sleep(acc_full, 0u, abort_flag, 1000)) goto done;
+    if (ew == 0) TRACE(kProducers + 2, 0, 0);
     tc_fence_after();
     // accumulator row (= input channel of the M-block) of this thread: M=128 -> lane i holds row i; M=64 -> row m
     // sits in lane 32*(m/16) + m%16 (16 lanes per sub-partition)
@@ -327,6 +358,7 @@ k_wgrad_tc(const WgParams p) {
         }
       }
     }
+    if (ew == 0) TRACE(kProducers + 2, 0, 1);
     tc_fence_before();
   } else {
     // =================================================================== MMA issuer: the whole warp walks the
@@ -344,7 +376,9 @@ k_wgrad_tc(const WgParams p) {
         if (!mbar_wait(g_full(buf), (gi / (uint32_t)p.gbufs) & 1u, abort_flag)) { ok = false; break; }
       }
       const int s = (int)(n_item % (uint32_t)S);
+      TRACE(kProducers + 1, n_item, 0);
       if (!mbar_wait(a_full(s), (n_item / (uint32_t)S) & 1u, abort_flag)) { ok = false; break; }
+      TRACE(kProducers + 1, n_item, 1);
       tc_fence_after();
       const int k = it.k, h = it.h;
       it.next();
@@ -362,6 +396,7 @@ k_wgrad_tc(const WgParams p) {
         if (tile_done) umma_commit(g_empty(buf));
       }
       __syncwarp();
+      TRACE(kProducers + 1, n_item, 2);
       if (h == p.nmb - 1) seen |= 1u << k;
       if (tile_done) ++gi;
       any = true;
@@ -384,6 +419,9 @@ done:
 }  // namespace
 
 int* mm3d_device_err_flag();  // conv_tc.cu
+#ifdef MM3D_TRACE
+long long* mm3d_debug_trace_ptr();  // conv_tc.cu
+#endif
 
 int mm3d_conv_wgrad_tc_supported(int c_in, int c_out, int K) {
   if ((c_in % 16) != 0 || c_in < 16 || c_in > 256 || (c_out % 16) != 0 || c_out < 16 || c_out > 256 || K > 32) return 0;
@@ -439,6 +477,9 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
   while (p.gbufs < kMaxGBufs && (size_t)p.S * a_bytes + (size_t)(p.gbufs + 1) * g_bytes <= budget) ++p.gbufs;
   const size_t smem_fixed = fixed + (size_t)p.S * a_bytes + (size_t)p.gbufs * g_bytes;
   p.err = mm3d_device_err_flag();
+#ifdef MM3D_TRACE
+  p.trace = mm3d_debug_trace_ptr();
+#endif
   // Offsets -> groups and CTAs -> groups by expected work.  How often an offset occurs is data dependent; as a
   // prior, the centre of a 3^3 table is present for every row, faces often, edges sometimes, corners rarely.
   // Heaviest offsets are dealt first, each to the lightest group with a free accumulator slot; then every group

@@ -106,6 +106,16 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const void* tmap,
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
+// Same with the copy's `ignore-src` predicate: `ignore` writes 16 zero bytes and reads nothing (src must still be a valid
+// address).  ptxas turns the variable src-size form above into ~6 extra instructions per copy (pointer / size
+// arithmetic for the partial-copy case); the predicate form is one ISETP.
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, bool ignore) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t"
+      "cp.async.ca.shared.global [%0], [%1], 16, p;\n\t}" ::"r"(dst_smem),
+      "l"(src), "r"((uint32_t)ignore)
+      : "memory");
+}
 // the mbarrier receives one arrival when all cp.async issued so far by this thread have landed
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -131,8 +141,8 @@ __device__ __forceinline__ void gather_block(uint32_t stage, uint32_t ent, const
     for (int u = 0; u < kBatch; ++u) {
       const int r = r0 + u * kRowsPerPass + rsub;
       const uint32_t off = BASE32 ? (uint32_t)((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4)) : (uint32_t)((c ^ (r & 7)) << 4);
-      const bool ok = rows[u] >= 0;
-      cp_async16(stage + (uint32_t)r * 128u + off, ok ? srcc + (size_t)(uint32_t)rows[u] * row_floats : base, ok ? 16u : 0u);
+      // (absent rows read nothing: the address of row 0 only has to be valid)
+      cp_async16_zfill(stage + (uint32_t)r * 128u + off, srcc + (size_t)(uint32_t)max(rows[u], 0) * row_floats, rows[u] < 0);
     }
   }
 }

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--cin", type=int, default=16)
     ap.add_argument("--cout", type=int, default=16)
     ap.add_argument("--warm", action="store_true")
+    ap.add_argument("--dir", default="fwd", choices=["fwd", "wgrad"])
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     locs, _ = synth.make_batch("nuscenes", batch=8)
@@ -36,7 +37,14 @@ def main():
     trace = torch.zeros(16 * 64 * 4, dtype=torch.int64, device=dev)
     flush = torch.empty(384 << 20, dtype=torch.uint8, device=dev)
 
+    dout = torch.randn(t.n_out, a.cout, device=dev)
+    dw = torch.empty_like(w)
+
     def run():
+        if a.dir == "wgrad":
+            _lib.check(lib.mm3d_conv_wgrad(x.data_ptr(), t.n_in, a.cin, dout.data_ptr(), t.n_out, a.cout, dw.data_ptr(), t.K, t.tbl,
+                                           t.stride, t.onehot, t.plan, t.plan_cap, 0, m, ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+            return
         _lib.check(lib.mm3d_conv_fwd(x.data_ptr(), t.n_in, a.cin, out.data_ptr(), t.n_out, a.cout, w.data_ptr(), t.K, t.tbl, t.stride,
                                      t.onehot, t.plan, t.plan_cap, 0, m, ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
     run()
@@ -52,7 +60,9 @@ def main():
     t0 = tr[tr > 0].min()
     rel = lambda v: "      -" if v == 0 else f"{(v - t0):7d}"
     print("columns: producers (roles 0..7): wait_start got_stage filled -- epilogue (role 9): wait_start got_tile done -- "
-          "MMA issuers (roles 10, 11): wait_start got_item issued acc_wait_start")
+          "MMA issuers (roles 10, 11): wait_start got_item issued acc_wait_start\n"
+          "wgrad: producers (0..7): item_start a_wait_start got_stage filled -- MMA issuer (role 9): wait_start got_item issued -- "
+          "epilogue (role 10): flush_start flush_end")
     for role in range(16):
         if not (tr[role] > 0).any():
             continue
