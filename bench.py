@@ -568,7 +568,8 @@ def run_ours(args):
                 tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
                 key = roofline["kernel"].split(" @ ")[0] + f" rows {roofline['kernel'].split('(')[1].split(' rows')[0]} {args.mode}"
                 ent = tr.get(key)
-                if ent and hashlib.sha1(open(os.path.join(ROOT, ent["src_file"]), "rb").read()).hexdigest() == ent["src_sha1"]:
+                srcs = (ent["src_file"], "mm2d3d_b200/csrc/tc_common.cuh", "mm2d3d_b200/csrc/plan.cuh") if ent else ()
+                if ent and hashlib.sha1(b"".join(open(os.path.join(ROOT, f), "rb").read() for f in srcs)).hexdigest() == ent["src_sha1"]:
                     roofline["traffic"] = ent["dram_bytes"]
                     roofline["traffic_source"] = ent["source"]
             except Exception:
