@@ -36,7 +36,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     # BASELINE.json configs[1] names both arithmetic modes; the tensor-core one (tcgen05 kind::tf32, FP32
     # accumulate, parity bar 1e-2) is the headline, the FP32 SIMT parity mode (1e-4) is timed beside it
-    ap.add_argument("--mode", default=os.environ.get("MM3D_BENCH_MODE", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--mode", default=os.environ.get("MM3D_BENCH_MODE", "tf32"), choices=["fp32", "tf32", "tf32x3"])
     ap.add_argument("--no-fp32-side", action="store_true", help="skip the short FP32-mode measurement")
     ap.add_argument("--shape", default="nuscenes", choices=["nuscenes", "semantickitti"])
     ap.add_argument("--batch", type=int, default=8, help="scans per GPU per step")
@@ -231,6 +231,8 @@ def kernel_pass(net, locs_d, feats_d, mode, pk):
         fwd_t, bwd_t, bwd_flags = F.conv_tables(meta, mod.kind, spatial, plans=mode != "fp32")
         out = torch.empty(fwd_t.n_out, c_out, device=dev)
         dout = torch.randn(fwd_t.n_out, c_out, device=dev)
+        if mode == "tf32x3":  # the gathered operands carry a hi and a lo plane in this mode
+            x, dout = F._planes(x), F._planes(dout)
         dx = torch.empty(bwd_t.n_out, c_in, device=dev)
         dw = torch.empty_like(w)
         ws = F.scratch(max(lib.mm3d_conv_workspace_bytes(fwd_t.n_in, fwd_t.n_out, c_in, c_out, K, m),
@@ -532,33 +534,38 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_reference_scans_per_s(5, 1, args.shape)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        fp32_side = None
-        if world == 1 and args.mode != "fp32" and not args.no_fp32_side:
-            # the precision-matched mode (the reference's 3D branch is FP32) as a full measurement: same
-            # workload, same loops -- device-timed value and end-to-end value
-            scn_mod.set_conv_mode("fp32")
-            prepared.clear()  # built for the tensor-core mode (row plans)
-            try:
-                n_f = 20
-                for i in range(3):
-                    step(i)
-                barrier()
-                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                f0.record()
-                for i in range(n_f):
-                    step(i)
-                f1.record()
-                barrier()
-                fms = f0.elapsed_time(f1) / n_f
-                prepared.clear()
-                fe2e = time_e2e(n_f) / n_f
-                fp32_side = {"value": args.batch / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms, "steps": n_f, "warmup": 3,
-                             "dtype": "f32", "e2e": {"value": args.batch / (fe2e * 1e-3), "unit": UNIT, "ms_per_step": fe2e},
-                             "note": "same workload and loops in the FP32 SIMT parity mode (activations / gradients within "
-                                     "1e-4): the figure to set against the reference's FP32 3D branch"}
-            finally:
-                scn_mod.set_conv_mode(args.mode)
-                prepared.clear()
+        # the precision-matched modes (the reference's 3D branch is FP32) as full measurements: same workload,
+        # same loops -- device-timed value and end-to-end value.  "fp32" = SIMT FMA kernels, "tf32x3" = tensor cores with
+        # three error-compensated TF32 products (both hold the 1e-4 bars)
+        side = {}
+        if world == 1 and args.mode == "tf32" and not args.no_fp32_side:
+            notes = {"fp32": "same workload and loops in the FP32 SIMT parity mode (activations / gradients within 1e-4): the "
+                             "figure to set against the reference's FP32 3D branch",
+                     "tf32x3": "same workload and loops with FP32-grade arithmetic on the tensor cores: every convolution as three "
+                               "error-compensated TF32 products (hi.hi + lo.hi + hi.lo), activations / gradients within 1e-4"}
+            for smode in ("fp32", "tf32x3"):
+                scn_mod.set_conv_mode(smode)
+                prepared.clear()  # (row plans are built per mode)
+                try:
+                    n_f = 20
+                    for i in range(3):
+                        step(i)
+                    barrier()
+                    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    f0.record()
+                    for i in range(n_f):
+                        step(i)
+                    f1.record()
+                    barrier()
+                    fms = f0.elapsed_time(f1) / n_f
+                    prepared.clear()
+                    fe2e = time_e2e(n_f) / n_f
+                    side[smode] = {"value": args.batch / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms, "steps": n_f, "warmup": 3,
+                                   "dtype": "f32" if smode == "fp32" else "tf32x3 (f32-grade)",
+                                   "e2e": {"value": args.batch / (fe2e * 1e-3), "unit": UNIT, "ms_per_step": fe2e}, "note": notes[smode]}
+                finally:
+                    scn_mod.set_conv_mode(args.mode)
+                    prepared.clear()
         if roofline is not None:
             # DRAM traffic of the dominant kernel: from an `ncu --set full` capture (profiles/ncu_traffic.json) of the SAME
             # kernel source -- the entry records the SHA-1 of the kernel's .cu file at capture time; any other build
@@ -580,7 +587,7 @@ def run_ours(args):
             "impl": "ours", "metric": METRIC, "value": scans / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.mode], "data": "synthetic",
+            "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16", "tf32x3": "tf32x3 (f32-grade)"}[args.mode], "data": "synthetic",
             "config": {
                 "workload": f"UNetSCN(m=16, 7 planes, full_scale=4096) fwd+bwd, batch {args.batch} "
                             f"{args.shape}-shaped scans per GPU (BASELINE configs[1])",
@@ -601,8 +608,8 @@ def run_ours(args):
         }
         if roofline is not None:
             line["roofline"] = roofline
-        if fp32_side is not None:
-            line["fp32_mode"] = fp32_side
+        for smode, rec in side.items():
+            line[smode + "_mode"] = rec
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -735,7 +742,7 @@ def run_full_step(args):
     line = {
         "impl": "ours", "metric": "full MM2D3D training step scans/sec (source + target)", "value": scans / (ms * 1e-3), "unit": UNIT,
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32"}[args.mode] + " (3D) / bf16 autocast (2D)", "data": "synthetic",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3"}[args.mode] + " (3D) / bf16 autocast (2D)", "data": "synthetic",
         "config": {
             "workload": f"BASELINE configs[2]: full MM2D3D step -- ResNet34-UNet stand-in on {H}x{W} RGB-D (46.2 M parameters, "
                         f"stock cuDNN, channels-last, BF16 autocast) + 2D->3D lift + RGB mask + UNetSCN(m=16, 7 planes) + 2+2 heads "

@@ -14,8 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libmm3d.so")
 ABI_VERSION = 3
 LEVEL_DESC_WORDS = 10
 
-MODE_FP32, MODE_TF32, MODE_BF16 = 0, 1, 2
-MODES = {"fp32": MODE_FP32, "tf32": MODE_TF32, "bf16": MODE_BF16}
+MODE_FP32, MODE_TF32, MODE_BF16, MODE_TF32X3 = 0, 1, 2, 3
+MODES = {"fp32": MODE_FP32, "tf32": MODE_TF32, "bf16": MODE_BF16, "tf32x3": MODE_TF32X3}
 CONV_TRANSPOSE_W, CONV_MIRROR_K = 1, 2
 STATUS_BAD_COORD = 1
 
@@ -53,6 +53,7 @@ SIGNATURES = {
     "mm3d_build_plans": (_i, [_p, _i, _p]),
     "mm3d_conv_fwd": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i, _p, _i64, _p, _p, _i64, _i, _i, _p, _sz, _p]),
     "mm3d_round_tf32": (_i, [_p, _p, _i64, _p]),
+    "mm3d_split_tf32": (_i, [_p, _p, _i64, _p]),
     "mm3d_conv_wgrad": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i, _p, _i64, _p, _p, _i64, _i, _i, _p, _sz, _p]),
     "mm3d_bnrelu_workspace_bytes": (_sz, [_i]),
     "mm3d_bnrelu_fwd": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i, _p, _sz, _p]),

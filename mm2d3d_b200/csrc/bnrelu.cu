@@ -36,6 +36,22 @@ template <> __device__ __forceinline__ void vstore<4>(float* p, const float (&v)
 }
 template <> __device__ __forceinline__ void vstore<1>(float* p, const float (&v)[1]) { *p = v[0]; }
 
+// Store for a tensor that a tensor-core convolution gathers: mode 0 = as is, 1 = rounded to TF32 (nearest), 2 = two
+// planes `plane` floats apart: hi = tf32(v), lo = tf32(v - hi) (the error-compensated TF32x3 mode)
+template <int VEC>
+__device__ __forceinline__ void store_planes(float* p, float (&v)[VEC], int mode, int64_t plane) {
+  if (mode == 0) { vstore<VEC>(p, v); return; }
+  float lo[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const float hi = mm3d_rna_tf32(v[j]);
+    lo[j] = mm3d_rna_tf32(v[j] - hi);
+    v[j] = hi;
+  }
+  vstore<VEC>(p, v);
+  if (mode == 2) vstore<VEC>(p + plane, lo);
+}
+
 // dynamic shared: 2*C doubles (accumulators) -- also reused as 2*C floats of scale/shift
 extern __shared__ double s_acc[];
 
@@ -113,9 +129,8 @@ k_bn_apply(const float* __restrict__ x, float* __restrict__ y, int64_t n, int c,
     for (int j = 0; j < VEC; ++j) {
       const float o = fmaf(t[j] - mean[j], scale[j], bet[j]);
       t[j] = o > 0.f ? o : o * leak;
-      if (round_tf32) t[j] = mm3d_rna_tf32(t[j]);
     }
-    vstore<VEC>(y + row * c + v * VEC, t);
+    store_planes<VEC>(y + row * c + v * VEC, t, round_tf32, n * c);
   }
 }
 
@@ -243,9 +258,8 @@ k_bn_fwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
       for (int j = 0; j < VEC; ++j) {
         const float o = fmaf(t[u][j] - mean[j], scale[j], bet[j]);
         t[u][j] = o > 0.f ? o : o * leak;
-        if (round_tf32) t[u][j] = mm3d_rna_tf32(t[u][j]);
       }
-      vstore<VEC>(y + (row + u * stride) * c + v * VEC, t[u]);
+      store_planes<VEC>(y + (row + u * stride) * c + v * VEC, t[u], round_tf32, n * c);
     }
   }
   for (; row < n; row += stride) {
@@ -255,9 +269,8 @@ k_bn_fwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
     for (int j = 0; j < VEC; ++j) {
       const float o = fmaf(t[j] - mean[j], scale[j], bet[j]);
       t[j] = o > 0.f ? o : o * leak;
-      if (round_tf32) t[j] = mm3d_rna_tf32(t[j]);
     }
-    vstore<VEC>(y + row * c + v * VEC, t);
+    store_planes<VEC>(y + row * c + v * VEC, t, round_tf32, n * c);
   }
 }
 
@@ -286,7 +299,9 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
   const int64_t dxld = dx_hi ? (hi ? c - c_lo : c_lo) : c;
   // round_flags bit 0: dx (or its low column block) feeds a TF32 convolution as d_out -> store RNA-rounded values;
   // bit 1: same for the high column block dx_hi
-  const bool rnd = (round_flags & ((dx_hi && hi) ? 2 : 1)) != 0;
+  // bit 2: those outputs carry a hi and a lo plane (TF32x3 mode), the lo plane n * (row length) floats behind
+  const int rnd = (round_flags & ((dx_hi && hi) ? 2 : 1)) ? ((round_flags & 4) ? 2 : 1) : 0;
+  const int64_t dplane = n * dxld;
   float mean[VEC], invstd[VEC], scale[VEC], bet[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) mean[j] = invstd[j] = scale[j] = bet[j] = 0.f;
@@ -369,9 +384,8 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
         const float o = fmaf(xc, scale[j], bet[j]);
         const float d = o > 0.f ? g[u][j] : g[u][j] * leak;
         g[u][j] = scale[j] * (d - md[j] - xc * invstd[j] * mdx[j]);
-        if (rnd) g[u][j] = mm3d_rna_tf32(g[u][j]);
       }
-      vstore<VEC>(dxb + (row + u * stride) * dxld, g[u]);
+      store_planes<VEC>(dxb + (row + u * stride) * dxld, g[u], rnd, dplane);
     }
   }
   for (; row < n; row += stride) {
@@ -384,9 +398,8 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
       const float o = fmaf(xc, scale[j], bet[j]);
       const float d = o > 0.f ? g[j] : g[j] * leak;
       g[j] = scale[j] * (d - md[j] - xc * invstd[j] * mdx[j]);
-      if (rnd) g[j] = mm3d_rna_tf32(g[j]);
     }
-    vstore<VEC>(dxb + row * dxld, g);
+    store_planes<VEC>(dxb + row * dxld, g, rnd, dplane);
   }
 }
 

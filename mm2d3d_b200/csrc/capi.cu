@@ -56,13 +56,13 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
                      size_t ws_bytes, cudaStream_t stream);
 
 extern "C" size_t mm3d_conv_workspace_bytes(int64_t n_in, int64_t n_out, int c_in, int c_out, int K, int mode) {
-  (void)n_in; (void)n_out; (void)mode;
+  (void)n_in; (void)n_out;
   // one size for every use of a layer's scratch (forward, dgrad with c_in/c_out swapped, wgrad)
   size_t a = mm3d_conv_simt_workspace_bytes(c_in, c_out, K);
   size_t b = mm3d_conv_tc_workspace_bytes(c_in, c_out, K), c = mm3d_conv_tc_workspace_bytes(c_out, c_in, K);
   if (b > a) a = b;
   if (c > a) a = c;
-  return a;
+  return mode == MM3D_MODE_TF32X3 ? 2 * a : a;  // two weight images
 }
 
 static int check_conv_args(const void* in, const void* out, const void* w, const int32_t* tbl, int64_t n_in,
@@ -92,6 +92,12 @@ extern "C" int mm3d_conv_fwd(const float* in, int64_t n_in, int c_in, float* out
       MM3D_REQUIRE(plan, MM3D_ERR_INVALID, "mm3d_conv_fwd: tf32 mode needs the table's row plan (mm3d_build_plan)");
       return mm3d_conv_fwd_tc(in, n_in, c_in, out, n_out, c_out, weight, K, plan, plan_cap, flags, ws, ws_bytes,
                               (cudaStream_t)stream);
+    case MM3D_MODE_TF32X3:
+      MM3D_REQUIRE(mm3d_conv_tc_supported(c_in, c_out, K), MM3D_ERR_UNSUPPORTED,
+                   "tf32x3 conv: c_in %d must be a multiple of 16 (pad the channels)", c_in);
+      MM3D_REQUIRE(plan, MM3D_ERR_INVALID, "mm3d_conv_fwd: tf32x3 mode needs the table's row plan (mm3d_build_plan)");
+      return mm3d_conv_fwd_tc(in, n_in, c_in, out, n_out, c_out, weight, K, plan, plan_cap, flags | MM3D_CONV_X3, ws, ws_bytes,
+                              (cudaStream_t)stream);
     default:
       MM3D_REQUIRE(false, MM3D_ERR_UNSUPPORTED, "conv mode %d not implemented in this build", mode);
   }
@@ -105,6 +111,19 @@ extern "C" int mm3d_conv_wgrad(const float* in, int64_t n_in, int c_in, const fl
   int rc = check_conv_args(in, d_out, d_weight, tbl, n_in, n_out, c_in, c_out, K, tbl_stride, onehot_off);
   if (rc) return rc;
   switch (mode) {
+    case MM3D_MODE_TF32X3: {
+      // d_weight = in_hi^T d_out_hi + in_lo^T d_out_hi + in_hi^T d_out_lo: three launches of the TF32 kernel that
+      // accumulate into d_weight (both operands carry a hi and a lo plane)
+      MM3D_REQUIRE(mm3d_conv_wgrad_tc_supported(c_in, c_out, K), MM3D_ERR_UNSUPPORTED,
+                   "tf32x3 wgrad: unsupported shape c_in %d c_out %d K %d", c_in, c_out, K);
+      MM3D_REQUIRE(plan, MM3D_ERR_INVALID, "mm3d_conv_wgrad: tf32x3 mode needs the table's row plan (mm3d_build_plan)");
+      const float* in_lo = in + n_in * (int64_t)c_in;
+      const float* dout_lo = d_out + n_out * (int64_t)c_out;
+      rc = mm3d_conv_wgrad_tc(in, n_in, c_in, d_out, n_out, c_out, d_weight, K, plan, plan_cap, accumulate, (cudaStream_t)stream);
+      if (!rc) rc = mm3d_conv_wgrad_tc(in_lo, n_in, c_in, d_out, n_out, c_out, d_weight, K, plan, plan_cap, 1, (cudaStream_t)stream);
+      if (!rc) rc = mm3d_conv_wgrad_tc(in, n_in, c_in, dout_lo, n_out, c_out, d_weight, K, plan, plan_cap, 1, (cudaStream_t)stream);
+      return rc;
+    }
     case MM3D_MODE_TF32:
       if (mm3d_conv_wgrad_tc_supported(c_in, c_out, K)) {
         MM3D_REQUIRE(plan, MM3D_ERR_INVALID, "mm3d_conv_wgrad: tf32 mode needs the table's row plan (mm3d_build_plan)");

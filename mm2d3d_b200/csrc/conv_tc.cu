@@ -56,6 +56,7 @@ struct TcParams {
   int S;        // ring stages = producer warps
   int n_pad, num_tiles, tmem_cols;
   int n_local;  // tiles per CTA (upper bound) = ceil(num_tiles / grid)
+  int accumulate; // epilogue adds to `out` instead of overwriting it (second / third product of the TF32x3 mode)
   int split;      // MMA issuer warps with their own accumulators (2, or 1 when 4 accumulators do not fit TMEM)
   int max_items;  // capacity of the shared-memory item list = n_local * K * nb
   int* err;
@@ -77,8 +78,14 @@ struct TcParams {
 // Wsel(k)[32 j + e][n] (0 beyond c_in / c_out), tf32-rounded, the 16-byte chunks of every 128-byte
 // row XOR-swizzled with (n & 7): exactly the bytes a SWIZZLE_128B K-major B tile has in shared
 // memory, so the kernel bulk-copies it verbatim.
+// lo != 0: the image of the weights' TF32 remainder, tf32(w - tf32(w)) (second term of the error-compensated mode)
+__device__ __forceinline__ float wimg_value(float v, int lo) {
+  const float hi = to_tf32(v);
+  return lo ? to_tf32(v - hi) : hi;
+}
+
 __global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ img, int K, int c_in, int c_out, int nb,
-                               int n_pad, int transposed, int mirror) {
+                               int n_pad, int transposed, int mirror, int lo) {
   const int64_t total = (int64_t)K * nb * n_pad * kKBlock;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int e_sw = (int)(i % kKBlock);
@@ -93,7 +100,7 @@ __global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ 
       v = transposed ? __ldg(w + ((int64_t)ks * c_out + n) * c_in + ci)   // forward weight is [K][c_out][c_in]
                      : __ldg(w + ((int64_t)ks * c_in + ci) * c_out + n);  // [K][c_in][c_out]
     }
-    img[i] = to_tf32(v);
+    img[i] = wimg_value(v, lo);
   }
 }
 
@@ -101,7 +108,7 @@ __global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ 
 struct WImgItem {
   const float* w;
   float* img;
-  int K, c_in, c_out, nb, n_pad, transposed, mirror, block0;
+  int K, c_in, c_out, nb, n_pad, transposed, mirror, lo, block0;
 };
 constexpr int kMaxImgBatch = 32;
 struct WImgBatch {
@@ -128,7 +135,7 @@ __global__ void k_weight_images(const __grid_constant__ WImgBatch b) {
       v = it.transposed ? __ldg(it.w + ((int64_t)ks * it.c_out + n) * it.c_in + ci)
                         : __ldg(it.w + ((int64_t)ks * it.c_in + ci) * it.c_out + n);
     }
-    it.img[e] = to_tf32(v);
+    it.img[e] = wimg_value(v, it.lo);
   }
 }
 
@@ -328,11 +335,18 @@ k_conv_tc(const __grid_constant__ TcParams p) {
           if ((p.c_out & 3) == 0) {
 #pragma unroll
             for (int jj = 0; jj < 16; jj += 4)
-              if (c0 + jj < p.c_out) *reinterpret_cast<float4*>(dst + jj) = make_float4(acc[jj], acc[jj + 1], acc[jj + 2], acc[jj + 3]);
+              if (c0 + jj < p.c_out) {
+                float4 o = make_float4(acc[jj], acc[jj + 1], acc[jj + 2], acc[jj + 3]);
+                if (p.accumulate) {  // (each row is owned by one thread: a plain read-modify-write)
+                  const float4 t = *reinterpret_cast<const float4*>(dst + jj);
+                  o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+                }
+                *reinterpret_cast<float4*>(dst + jj) = o;
+              }
           } else {
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj)
-              if (c0 + jj < p.c_out) dst[jj] = acc[jj];
+              if (c0 + jj < p.c_out) dst[jj] = p.accumulate ? dst[jj] + acc[jj] : acc[jj];
           }
         }
       }
@@ -519,6 +533,7 @@ int mm3d_conv_tc_build_images(const float* const* weights, float* const* images,
       it.w = weights[i]; it.img = images[i]; it.K = K[i]; it.c_in = c_in[i]; it.c_out = c_out[i];
       it.transposed = (flags[i] & MM3D_CONV_TRANSPOSE_W) ? 1 : 0;
       it.mirror = (flags[i] & MM3D_CONV_MIRROR_K) ? 1 : 0;
+      it.lo = (flags[i] & MM3D_CONV_WEIGHT_LO) ? 1 : 0;
       it.block0 = blocks;
       int nb_blocks = (int)mm3d_cdiv((int64_t)it.K * it.nb * it.n_pad * kKBlock, 256 * 8);
       blocks += nb_blocks < 1 ? 1 : nb_blocks;
@@ -532,7 +547,7 @@ int mm3d_conv_tc_build_images(const float* const* weights, float* const* images,
 }
 
 int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
-                         const float* wimg, int K, const void* plan, int64_t plan_cap, cudaStream_t stream);
+                         const float* wimg, int K, const void* plan, int64_t plan_cap, int accumulate, cudaStream_t stream);
 
 int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
                      const float* weight, int K, const void* plan, int64_t plan_cap, int flags, void* ws,
@@ -540,21 +555,33 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
   int nb, n_pad;
   MM3D_REQUIRE(tc_geometry(c_in, c_out, K, &nb, &n_pad) == 0, MM3D_ERR_UNSUPPORTED,
                "tcgen05 conv: unsupported shape c_in %d c_out %d K %d", c_in, c_out, K);
-  MM3D_REQUIRE(ws && ws_bytes >= mm3d_conv_tc_workspace_bytes(c_in, c_out, K), MM3D_ERR_WORKSPACE,
+  MM3D_REQUIRE(ws && ws_bytes >= mm3d_conv_tc_workspace_bytes(c_in, c_out, K) * ((flags & MM3D_CONV_X3) ? 2 : 1), MM3D_ERR_WORKSPACE,
                "tcgen05 conv: workspace too small");
   const bool tr = (flags & MM3D_CONV_TRANSPOSE_W) != 0, mir = (flags & MM3D_CONV_MIRROR_K) != 0;
   MM3D_REQUIRE(tr || !mir, MM3D_ERR_UNSUPPORTED, "MIRROR_K without TRANSPOSE_W not implemented");
   if (n_out == 0) return MM3D_OK;
   float* wimg = (float*)ws;
   k_weight_image<<<mm3d_grid((int64_t)K * nb * n_pad * kKBlock, 256), 256, 0, stream>>>(weight, wimg, K, c_in, c_out, nb,
-                                                                                    n_pad, tr ? 1 : 0, mir ? 1 : 0);
+                                                                                    n_pad, tr ? 1 : 0, mir ? 1 : 0, 0);
   mm3d_count_launches(1);
-  return mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, wimg, K, plan, plan_cap, stream);
+  if (!(flags & MM3D_CONV_X3)) return mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, wimg, K, plan, plan_cap, 0, stream);
+  // Error-compensated mode: `in` holds two planes, hi = tf32(x) and lo = tf32(x - hi) ([n_in, c_in] each), the
+  // workspace two weight images; out = hi.Whi + lo.Whi + hi.Wlo, accumulated in FP32 (the dropped lo.Wlo term and the
+  // roundings of the lo parts are ~2^-22 relative)
+  float* wimg_lo = wimg + mm3d_conv_tc_workspace_bytes(c_in, c_out, K) / sizeof(float);
+  k_weight_image<<<mm3d_grid((int64_t)K * nb * n_pad * kKBlock, 256), 256, 0, stream>>>(weight, wimg_lo, K, c_in, c_out, nb,
+                                                                                    n_pad, tr ? 1 : 0, mir ? 1 : 0, 1);
+  mm3d_count_launches(1);
+  const float* in_lo = in + n_in * (int64_t)c_in;
+  int rc = mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, wimg, K, plan, plan_cap, 0, stream);
+  if (!rc) rc = mm3d_conv_fwd_tc_img(in_lo, n_in, c_in, out, n_out, c_out, wimg, K, plan, plan_cap, 1, stream);
+  if (!rc) rc = mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, wimg_lo, K, plan, plan_cap, 1, stream);
+  return rc;
 }
 
 // the convolution proper, from a prebuilt weight image
 int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
-                         const float* wimg, int K, const void* plan, int64_t plan_cap, cudaStream_t stream) {
+                         const float* wimg, int K, const void* plan, int64_t plan_cap, int accumulate, cudaStream_t stream) {
   int nb, n_pad;
   MM3D_REQUIRE(tc_geometry(c_in, c_out, K, &nb, &n_pad) == 0, MM3D_ERR_UNSUPPORTED,
                "tcgen05 conv: unsupported shape c_in %d c_out %d K %d", c_in, c_out, K);
@@ -573,6 +600,7 @@ int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, in
   p.n_pad = n_pad;
   p.num_tiles = (int)mm3d_cdiv(n_out, kTileM);
   p.err = mm3d_device_err_flag();
+  p.accumulate = accumulate;
 #ifdef MM3D_TRACE
   p.trace = g_trace;
 #endif

@@ -39,7 +39,7 @@ int mm3d_conv_tc_supported(int c_in, int c_out, int K);
 int mm3d_conv_tc_build_images(const float* const* weights, float* const* images, const int* K, const int* c_in,
                               const int* c_out, const int* flags, int n, cudaStream_t stream);
 int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
-                         const float* wimg, int K, const void* plan, int64_t plan_cap, cudaStream_t stream);
+                         const float* wimg, int K, const void* plan, int64_t plan_cap, int accumulate, cudaStream_t stream);
 
 namespace {
 
@@ -80,31 +80,34 @@ struct Net {
   float *V, *Vp, *Z, *s_head;
   int64_t n_points;
   int planes(int l) const { return m * (l + 1); }
+  // TF32x3 mode: every tensor a convolution gathers carries a hi and a lo plane ([rows, c] floats each)
+  int pl() const { return mode == MM3D_MODE_TF32X3 ? 2 : 1; }
 };
 
 // the same carving in forward, backward and the size query
 void carve(Net& net, Bump& bp) {
   const int64_t n0 = net.lv[0].n;
   net.V = bp.f(n0, net.cin);
-  net.Vp = net.cin_k != net.cin ? bp.f(n0, net.cin_k) : net.V;
+  const int pl = net.pl();
+  net.Vp = (net.cin_k != net.cin || pl == 2) ? bp.f(n0, (int64_t)net.cin_k * pl) : net.V;
   net.b.assign(net.L, LevelBufs());
   for (int l = 0; l < net.L; ++l) {
     const int64_t n = net.lv[l].n;
     const int p = net.planes(l);
     LevelBufs& B = net.b[l];
     B.X = bp.f(n, p);
-    B.A = bp.f(n, p);
+    B.A = bp.f(n, (int64_t)p * pl);
     B.Y = bp.f(n, p);
     B.s_pre = bp.f(2, p);
     if (l + 1 < net.L) {
       const int q = net.planes(l + 1);
-      B.B = bp.f(n, p);
+      B.B = bp.f(n, (int64_t)p * pl);
       B.s_dn = bp.f(2, p);
-      B.E = bp.f(net.lv[l + 1].n, q);
+      B.E = bp.f(net.lv[l + 1].n, (int64_t)q * pl);
       B.s_up = bp.f(2, q);
       B.F = bp.f(n, p);
       B.J = bp.f(n, 2 * p);
-      B.G = bp.f(n, 2 * p);
+      B.G = bp.f(n, (int64_t)2 * p * pl);
       B.s_post = bp.f(2, 2 * p);
       B.R = bp.f(n, p);
     } else {
@@ -164,7 +167,11 @@ __global__ void k_pad_cols(const float* __restrict__ src, int64_t n, int c_src, 
     const int64_t r = i / c_dst;
     const int j = (int)(i - r * c_dst);
     float v = j < c_src ? __ldg(src + r * c_src + j) : 0.f;
-    if (round_tf32) v = mm3d_rna_tf32(v);
+    if (round_tf32) {
+      const float hi = mm3d_rna_tf32(v);
+      if (round_tf32 == 2) dst[total + i] = mm3d_rna_tf32(v - hi);  // lo plane (TF32x3 mode)
+      v = hi;
+    }
     dst[i] = v;
   }
 }
@@ -197,7 +204,13 @@ __global__ void k_split_add(const float* __restrict__ dj, int ldj, const float* 
       const float4 a = __ldg(reinterpret_cast<const float4*>(dj + r * ldj + j));
       const float4 b = __ldg(reinterpret_cast<const float4*>(add + r * p + j));
       float4 o = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-      if (round_tf32) { o.x = mm3d_rna_tf32(o.x); o.y = mm3d_rna_tf32(o.y); o.z = mm3d_rna_tf32(o.z); o.w = mm3d_rna_tf32(o.w); }
+      if (round_tf32) {
+        const float4 h = make_float4(mm3d_rna_tf32(o.x), mm3d_rna_tf32(o.y), mm3d_rna_tf32(o.z), mm3d_rna_tf32(o.w));
+        if (round_tf32 == 2)  // lo plane (TF32x3 mode)
+          *reinterpret_cast<float4*>(dy + n * p + r * p + j) =
+              make_float4(mm3d_rna_tf32(o.x - h.x), mm3d_rna_tf32(o.y - h.y), mm3d_rna_tf32(o.z - h.z), mm3d_rna_tf32(o.w - h.w));
+        o = h;
+      }
       *reinterpret_cast<float4*>(dy + r * p + j) = o;
       if (df) *reinterpret_cast<float4*>(df + r * p + j) = __ldg(reinterpret_cast<const float4*>(dj + r * ldj + p + j));
     }
@@ -208,7 +221,9 @@ __global__ void k_split_add(const float* __restrict__ dj, int ldj, const float* 
     const int64_t r = i / p;
     const int j = (int)(i - r * p);
     const float o = __ldg(dj + r * ldj + j) + __ldg(add + i);
-    dy[i] = round_tf32 ? mm3d_rna_tf32(o) : o;
+    const float h = round_tf32 ? mm3d_rna_tf32(o) : o;
+    if (round_tf32 == 2) dy[n * p + i] = mm3d_rna_tf32(o - h);
+    dy[i] = h;
     if (df) df[i] = __ldg(dj + r * ldj + p + j);
   }
 }
@@ -256,6 +271,7 @@ struct Ctx {
   int wgrad_acc = 0;  // 1: the weight-gradient buffers were zeroed by one memset up front, wgrad kernels accumulate
   std::vector<const float*> img_key;  // weight pointer ...
   std::vector<const float*> img_val;  // ... -> its image
+  std::vector<const float*> img_lo;   // ... -> the image of its TF32 remainder (TF32x3 mode)
 };
 
 // stream for a layer's weight gradient: the side stream once everything enqueued on the main stream so far
@@ -321,14 +337,14 @@ void bn_fwd(Ctx& c, int pidx, const float* x, float* y, int64_t n, int ch, float
   if (abl_skip("bn")) return;
   EX(mm3d_bnrelu_fwd_impl(x, x_hi, c_lo, y, n, ch, P(c, pidx), P(c, pidx + 1), (float*)c.params[pidx + 2], (float*)c.params[pidx + 3],
                           save, save + ch, c.eps, c.momentum, 0.f, c.training, c.bn_ws, c.bn_ws_bytes, true,
-                          tc_mode(c) && to_conv ? 1 : 0, c.stream));
+                          tc_mode(c) && to_conv ? c.net->pl() : 0, c.stream));
 }
 // round: bit 0 = dx (its low column block when split) feeds a convolution as d_out, bit 1 = dx_hi does
 void bn_bwd(Ctx& c, int pidx, const float* x, const float* dy, float* dx, int64_t n, int ch, const float* save,
             int round, const float* x_hi = nullptr, int c_lo = 0, float* dx_hi = nullptr) {
   if (abl_skip("bn")) return;
   EX(mm3d_bnrelu_bwd_impl(x, x_hi, c_lo, dy, dx, dx_hi, n, ch, P(c, pidx), P(c, pidx + 1), save, save + ch, Gp(c, pidx), Gp(c, pidx + 1), 0.f,
-                          c.training, c.bn_ws, c.bn_ws_bytes, true, tc_mode(c) ? round : 0, c.stream));
+                          c.training, c.bn_ws, c.bn_ws_bytes, true, tc_mode(c) ? (round | (c.net->pl() == 2 ? 4 : 0)) : 0, c.stream));
 }
 enum Kind { SMC, DOWN, UP };
 
@@ -337,15 +353,32 @@ const float* find_img(const Ctx& c, const float* w) {
     if (c.img_key[i] == w) return c.img_val[i];
   return nullptr;
 }
+const float* find_img_lo(const Ctx& c, const float* w) {
+  for (size_t i = 0; i < c.img_key.size() && i < c.img_lo.size(); ++i)
+    if (c.img_key[i] == w) return c.img_lo[i];
+  return nullptr;
+}
+// One rule-table convolution from prebuilt weight images.  TF32x3 mode: hi.Whi + lo.Whi + hi.Wlo, three launches of the
+// same kernel, the second and third adding to `out` (`in` carries the lo plane n_in * c_in floats behind the hi one).
+int conv_img(const Ctx& c, const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out, const float* im,
+             const float* im_lo, int K, const void* plan, int64_t plan_cap) {
+  int rc = mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, im, K, plan, plan_cap, 0, c.stream);
+  if (c.net->pl() == 1 || rc) return rc;
+  if (!im_lo) { mm3d_set_error("tf32x3: missing lo weight image"); return MM3D_ERR_INVALID; }
+  rc = mm3d_conv_fwd_tc_img(in + n_in * (int64_t)c_in, n_in, c_in, out, n_out, c_out, im, K, plan, plan_cap, 1, c.stream);
+  if (!rc) rc = mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, im_lo, K, plan, plan_cap, 1, c.stream);
+  return rc;
+}
 // forward of layer type `kind` whose FINE level is l
 void conv_fwd(Ctx& c, Kind kind, int l, const float* in, int c_in, float* out, int c_out, const float* w) {
   if (abl_skip("conv")) return;
   const LevelMeta& f = c.net->lv[l];
   if (const float* im = find_img(c, w)) {  // prebuilt weight image: the tcgen05 kernel directly
     const int64_t nc = l + 1 < c.net->L ? c.net->lv[l + 1].n : 0;
-    if (kind == SMC) EX(mm3d_conv_fwd_tc_img(in, f.n, c_in, out, f.n, c_out, im, 27, f.plan_smc, f.plan_cap, c.stream));
-    else if (kind == DOWN) EX(mm3d_conv_fwd_tc_img(in, f.n, c_in, out, nc, c_out, im, 8, f.plan_down, f.plan_cap, c.stream));
-    else EX(mm3d_conv_fwd_tc_img(in, nc, c_in, out, f.n, c_out, im, 8, f.plan_up, f.plan_cap, c.stream));
+    const float* il = find_img_lo(c, w);
+    if (kind == SMC) EX(conv_img(c, in, f.n, c_in, out, f.n, c_out, im, il, 27, f.plan_smc, f.plan_cap));
+    else if (kind == DOWN) EX(conv_img(c, in, f.n, c_in, out, nc, c_out, im, il, 8, f.plan_down, f.plan_cap));
+    else EX(conv_img(c, in, nc, c_in, out, f.n, c_out, im, il, 8, f.plan_up, f.plan_cap));
     return;
   }
   if (kind == SMC)
@@ -366,6 +399,7 @@ void conv_bwd(Ctx& c, Kind kind, int l, const float* in, int c_in, const float* 
   const int md = c.net->mode;
   cudaStream_t ws = wgrad_stream(c);  // d_out is complete on the main stream at this point
   const float* im = find_img(c, w);   // prebuilt dgrad image (tensor-core modes)
+  const float* il = find_img_lo(c, w);
   // parameter gradients inside the caller's (pre-zeroed) flat buffer accumulate; temporaries are overwritten
   const int acc = c.wgrad_acc && c.grad_lo <= (const char*)d_w && (const char*)d_w < c.grad_hi;
   const bool do_wg = !abl_skip("wgrad") && d_w != nullptr, do_dg = !abl_skip("conv");  // (frozen weight: no d_w)
@@ -377,7 +411,7 @@ void conv_bwd(Ctx& c, Kind kind, int l, const float* in, int c_in, const float* 
       EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, f.n, c_out, d_w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap, acc,
                          md, nullptr, 0, ws));
     if (d_in && im && do_dg)
-      EX(mm3d_conv_fwd_tc_img(d_out, f.n, c_out, d_in, f.n, c_in, im, 27, f.plan_smc, f.plan_cap, c.stream));
+      EX(conv_img(c, d_out, f.n, c_out, d_in, f.n, c_in, im, il, 27, f.plan_smc, f.plan_cap));
     else if (d_in && do_dg)
       EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, f.n, c_in, w, 27, f.nbr, f.tstride, nullptr, f.plan_smc, f.plan_cap,
                        MM3D_CONV_TRANSPOSE_W | MM3D_CONV_MIRROR_K, md, c.scratch, c.scratch_bytes, c.stream));
@@ -385,7 +419,7 @@ void conv_bwd(Ctx& c, Kind kind, int l, const float* in, int c_in, const float* 
     if (do_wg)
       EX(mm3d_conv_wgrad(in, f.n, c_in, d_out, nc, c_out, d_w, 8, f.child, f.tstride, nullptr, f.plan_down, f.plan_cap, acc,
                          md, nullptr, 0, ws));
-    if (im && do_dg) EX(mm3d_conv_fwd_tc_img(d_out, nc, c_out, d_in, f.n, c_in, im, 8, f.plan_up, f.plan_cap, c.stream));
+    if (im && do_dg) EX(conv_img(c, d_out, nc, c_out, d_in, f.n, c_in, im, il, 8, f.plan_up, f.plan_cap));
     else if (do_dg)
       EX(mm3d_conv_fwd(d_out, nc, c_out, d_in, f.n, c_in, w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap,
                        MM3D_CONV_TRANSPOSE_W, md, c.scratch, c.scratch_bytes, c.stream));
@@ -393,7 +427,7 @@ void conv_bwd(Ctx& c, Kind kind, int l, const float* in, int c_in, const float* 
     if (do_wg)
       EX(mm3d_conv_wgrad(in, nc, c_in, d_out, f.n, c_out, d_w, 8, f.parent, 0, f.off, f.plan_up, f.plan_cap, acc, md,
                          nullptr, 0, ws));
-    if (im && do_dg) EX(mm3d_conv_fwd_tc_img(d_out, f.n, c_out, d_in, nc, c_in, im, 8, f.plan_down, f.plan_cap, c.stream));
+    if (im && do_dg) EX(conv_img(c, d_out, f.n, c_out, d_in, nc, c_in, im, il, 8, f.plan_down, f.plan_cap));
     else if (do_dg)
       EX(mm3d_conv_fwd(d_out, f.n, c_out, d_in, nc, c_in, w, 8, f.child, f.tstride, nullptr, f.plan_down, f.plan_cap,
                        MM3D_CONV_TRANSPOSE_W, md, c.scratch, c.scratch_bytes, c.stream));
@@ -415,9 +449,9 @@ void launch_copy_cols(Ctx& c, const float* src, int64_t n, int c_src, float* dst
   if (mm3d_launch_pdl(k_copy_cols, dim3(mm3d_grid(n * ncols / 4 + 1, 256)), dim3(256), 0, c.stream, src, n, c_src, dst, c_dst, col0, ncols, 0) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
   mm3d_count_launches(1);
 }
-void launch_pad_cols(Ctx& c, const float* src, int64_t n, int c_src, float* dst, int c_dst, bool round_tf32 = false) {
+void launch_pad_cols(Ctx& c, const float* src, int64_t n, int c_src, float* dst, int c_dst, int round_tf32 = 0) {
   if (n == 0 || c.rc) return;
-  if (mm3d_launch_pdl(k_pad_cols, dim3(mm3d_grid(n * c_dst, 256)), dim3(256), 0, c.stream, src, n, c_src, dst, c_dst, round_tf32 ? 1 : 0) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
+  if (mm3d_launch_pdl(k_pad_cols, dim3(mm3d_grid(n * c_dst, 256)), dim3(256), 0, c.stream, src, n, c_src, dst, c_dst, round_tf32) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
   mm3d_count_launches(1);
 }
 
@@ -451,7 +485,7 @@ size_t img_region_bytes(const Net& net) {
     fwd += mm3d_align(mm3d_conv_tc_workspace_bytes(ci.c_in, ci.c_out, ci.K));
     bwd += mm3d_align(mm3d_conv_tc_workspace_bytes(ci.c_out, ci.c_in, ci.K));
   }
-  return (fwd > bwd ? fwd : bwd) + 256;
+  return (fwd > bwd ? fwd : bwd) * (size_t)net.pl() + 256;
 }
 
 // One launch builds the weight images of every layer for this direction (dgrad: W^T, mirrored for 3^3 layers).
@@ -480,6 +514,20 @@ int build_images(Ctx& c, bool backward, const float* w_stem) {
   if (rc) return rc;
   c.img_key.assign(w.begin(), w.end());
   c.img_val.assign(img.begin(), img.end());
+  c.img_lo.clear();
+  if (net.pl() == 2) {  // the images of the weights' TF32 remainders, behind the hi images
+    std::vector<float*> lo;
+    for (size_t i = 0; i < w.size(); ++i) {
+      const size_t bytes = mm3d_align(mm3d_conv_tc_workspace_bytes(ci[i], co[i], K[i]));
+      MM3D_REQUIRE((size_t)(at - (char*)c.img_ws) + bytes <= c.img_ws_bytes, MM3D_ERR_WORKSPACE, "weight image region too small");
+      lo.push_back((float*)at);
+      at += bytes;
+      fl[i] |= MM3D_CONV_WEIGHT_LO;
+    }
+    rc = mm3d_conv_tc_build_images(w.data(), lo.data(), K.data(), ci.data(), co.data(), fl.data(), (int)w.size(), c.stream);
+    if (rc) return rc;
+    c.img_lo.assign(lo.begin(), lo.end());
+  }
   return MM3D_OK;
 }
 
@@ -545,8 +593,9 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
     MARK("smc_dgrad post", l);
     const bool split = (p & 3) == 0 && c.training;  // as in the forward: [Y | F] was never concatenated
     float* d_J = g.f(n, split ? p : 2 * p);         // split: only the skip half d_J[:, :p]
-    float* d_F = g.f(n, p);
-    float* d_Yskip = g.f(n, p);
+    const int pl = net.pl();  // conv d_out tensors carry a lo plane in TF32x3 mode
+    float* d_F = g.f(n, (int64_t)p * pl);
+    float* d_Yskip = g.f(n, (int64_t)p * pl);
     if (split) {
       bn_bwd(c, post, B.Y, d_G, d_J, n, 2 * p, B.s_post, 2, B.F, p, d_F);  // d_F is the deconvolution's d_out
       MARK("bn_bwd post", l);
@@ -556,15 +605,16 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
       if (n && !c.rc) {
         if (mm3d_launch_pdl(k_copy_cols, dim3(mm3d_grid(n * p / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)d_J, n, 2 * p, d_F, p, 0, p, p) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
         mm3d_count_launches(1);
+        if (tc_mode(c)) launch_pad_cols(c, d_F, n, p, d_F, p, pl);  // round in place (+ lo plane): d_F is the deconvolution's d_out
       }
     }
     float* d_E = g.f(nc, q);
     conv_bwd(c, UP, l, B.E, q, d_F, p, P(c, up + 4), d_E, Gp(c, up + 4));
     MARK("up_dgrad", l);
-    float* d_Rn = g.f(nc, q);
+    float* d_Rn = g.f(nc, (int64_t)q * pl);
     bn_bwd(c, up, net.b[l + 1].R, d_E, d_Rn, nc, q, B.s_up, 1);
     MARK("bn_bwd up", l);
-    float* d_Xn = g.f(nc, q);
+    float* d_Xn = g.f(nc, (int64_t)q * pl);
     level_bwd(c, g, l + 1, deeper, d_Rn, d_Xn);
     float* d_B = g.f(n, p);
     conv_bwd(c, DOWN, l, B.B, p, d_Xn, q, P(c, dn + 4), d_B, Gp(c, dn + 4));
@@ -574,7 +624,7 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
     MARK("bn_bwd dn", l);
     // d_Y = d_J[:, :p] + d_Ybr
     if (n && !c.rc) {
-      if (mm3d_launch_pdl(k_split_add, dim3(mm3d_grid(n * p / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)d_J, split ? p : 2 * p, (const float*)d_Ybr, n, p, d_Yskip, (float*)nullptr, tc_mode(c) ? 1 : 0) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
+      if (mm3d_launch_pdl(k_split_add, dim3(mm3d_grid(n * p / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)d_J, split ? p : 2 * p, (const float*)d_Ybr, n, p, d_Yskip, (float*)nullptr, tc_mode(c) ? pl : 0) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
       mm3d_count_launches(1);
     }
     d_Y = d_Yskip;
@@ -591,7 +641,8 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
 
 int fill_net(Net& net, int in_channels, int m, int num_planes, int mode, const int64_t* level_desc, int64_t n_points) {
   MM3D_REQUIRE(num_planes >= 1 && num_planes <= 16 && m > 0 && in_channels > 0, MM3D_ERR_INVALID, "bad network shape");
-  MM3D_REQUIRE(mode == MM3D_MODE_FP32 || mode == MM3D_MODE_TF32, MM3D_ERR_UNSUPPORTED, "conv mode %d not implemented in this build", mode);
+  MM3D_REQUIRE(mode == MM3D_MODE_FP32 || mode == MM3D_MODE_TF32 || mode == MM3D_MODE_TF32X3, MM3D_ERR_UNSUPPORTED,
+               "conv mode %d not implemented in this build", mode);
   net.L = num_planes; net.m = m; net.cin = in_channels; net.mode = mode; net.n_points = n_points;
   // tensor-core kernels gather rows in 64-byte pieces: pad the stem input to a multiple of 16 channels
   net.cin_k = in_channels;
@@ -621,7 +672,7 @@ size_t bwd_temp_bytes(const Net& net) {
   const size_t n0 = (size_t)net.lv[0].n;
   total += mm3d_align(4 * n0 * (size_t)net.m) * 3 + mm3d_align(4 * n0 * (size_t)(net.cin + net.cin_k)) * 2 + 8 * 256;
   total += mm3d_align(4 * (size_t)27 * net.cin_k * net.m) * 2;
-  return total;
+  return total * (size_t)net.pl();
 }
 
 }  // namespace
@@ -700,16 +751,17 @@ MM3D_API int mm3d_unet_forward(int in_channels, int m, int num_planes, int mode,
   EX(mm3d_input_fwd(feats, p2v, npts, n_points, n0, in_channels, 4, net.V, c.stream));
   MARK("input_fwd", -1);
   const float* w_stem = P(c, 0);
-  if (net.cin_k != net.cin) {
-    // tensor-core modes gather whole 16-byte pieces: pad features and stem weight with zero channels
-    launch_pad_cols(c, net.V, n0, net.cin, net.Vp, net.cin_k, /*round_tf32=*/true);
-    float* wp = wp_buf;
-    launch_pad_cols(c, w_stem, 27, net.cin * m, wp, net.cin_k * m);
-    w_stem = wp;
-  } else if (tc_mode(c) && n0 > 0 && !c.rc) {
+  if (net.Vp != net.V)  // pad the stem input to whole 64-byte pieces; rounded to TF32 (+ lo plane in TF32x3 mode)
+    launch_pad_cols(c, net.V, n0, net.cin, net.Vp, net.cin_k, net.pl());
+  else if (tc_mode(c) && n0 > 0 && !c.rc) {
     // (stem input already a whole number of 64-byte pieces: round the InputLayer output in place)
     if (mm3d_launch_pdl(k_round_tf32, dim3(mm3d_grid(n0 * net.cin / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)net.V, net.V, n0 * (int64_t)net.cin) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
     mm3d_count_launches(1);
+  }
+  if (net.cin_k != net.cin) {  // zero input channels for the stem weight too
+    float* wp = wp_buf;
+    launch_pad_cols(c, w_stem, 27, net.cin * m, wp, net.cin_k * m);
+    w_stem = wp;
   }
   EX(build_images(c, false, w_stem));
   MARK("pad + weight images", -1);
@@ -785,10 +837,10 @@ MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode
   float* d_Z = g.f(n0, m);
   EX(mm3d_output_bwd(d_out, p2v, n_points, n0, m, d_Z, c.stream));
   MARK("output_bwd", -1);
-  float* d_R0 = g.f(n0, m);
+  float* d_R0 = g.f(n0, (int64_t)m * net.pl());
   bn_bwd(c, head, net.b[0].R, d_Z, d_R0, n0, m, net.s_head, 1);
   MARK("bn_bwd head", -1);
-  float* d_X0 = g.f(n0, m);
+  float* d_X0 = g.f(n0, (int64_t)m * net.pl());
   level_bwd(c, g, 0, 1, d_R0, d_X0);
   // stem
   const float* w_stem = P(c, 0);
@@ -806,7 +858,7 @@ MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode
       EX(mm3d_input_bwd(d_V, p2v, npts, n_points, net.cin, 4, d_feats, c.stream));
     }
   } else {
-    conv_bwd(c, SMC, 0, net.V, net.cin, d_X0, m, w_stem, d_Vp, d_w);
+    conv_bwd(c, SMC, 0, net.Vp, net.cin, d_X0, m, w_stem, d_Vp, d_w);
     if (d_feats) EX(mm3d_input_bwd(d_Vp, p2v, npts, n_points, net.cin, 4, d_feats, c.stream));
   }
   MARK("stem bwd + input_bwd", -1);
@@ -845,5 +897,16 @@ MM3D_API void mm3d_debug_dump_marks(void) {
   }
 }
 #endif
+
+// out[0..n) = tf32(in), out[n..2n) = tf32(in - tf32(in)): the operand planes of MM3D_MODE_TF32X3
+MM3D_API int mm3d_split_tf32(const float* in, float* out, int64_t n, mm3d_stream_t stream_) {
+  MM3D_REQUIRE(n >= 0 && (n == 0 || (in && out)), MM3D_ERR_INVALID, "split_tf32: bad arguments");
+  if (n == 0) return MM3D_OK;
+  // (k_pad_cols with equal widths: a copy that writes the rounded value and the lo plane `n` floats behind it)
+  MM3D_CUDA(mm3d_launch_pdl(k_pad_cols, dim3(mm3d_grid(n, 256)), dim3(256), 0, (cudaStream_t)stream_, in, n, 1, out, 1, 2));
+  mm3d_count_launches(1);
+  MM3D_CHECK_LAUNCH("mm3d_split_tf32");
+  return MM3D_OK;
+}
 
 }  // extern "C"

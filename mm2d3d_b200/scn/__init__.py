@@ -27,12 +27,13 @@ __all__ = [
 
 
 def set_conv_mode(mode: str) -> None:
-    """Arithmetic of the sparse convolutions: "fp32" (SIMT, parity) or "tf32" (tcgen05); "bf16" is reserved."""
+    """Arithmetic of the sparse convolutions: "fp32" (SIMT FMA, the parity mode), "tf32" (tcgen05, 1e-2) or "tf32x3"
+    (tcgen05 with three error-compensated TF32 products: FP32-grade results, 1e-4); "bf16" is reserved."""
     if mode not in _lib.MODES:
         raise ValueError(f"unknown mode {mode!r}; expected one of {sorted(_lib.MODES)}")
     if mode == "bf16":
         # the ABI reserves the mode; the kernels of this build take FP32 (SIMT) or TF32 (tcgen05) operands only
-        raise NotImplementedError("conv mode 'bf16' is not implemented in this build; use 'tf32' or 'fp32'")
+        raise NotImplementedError("conv mode 'bf16' is not implemented in this build; use 'tf32', 'tf32x3' or 'fp32'")
     F.DEFAULT_MODE = mode
 
 
