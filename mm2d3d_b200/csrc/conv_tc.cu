@@ -56,7 +56,11 @@ struct TcParams {
   int S;        // ring stages = producer warps
   int n_pad, num_tiles, tmem_cols;
   int n_local;  // tiles per CTA (upper bound) = ceil(num_tiles / grid)
-  int accumulate; // epilogue adds to `out` instead of overwriting it (second / third product of the TF32x3 mode)
+  int accumulate; // epilogue adds to `out` instead of overwriting it
+  int x3;         // TF32x3 mode: every stage also holds the lo planes of the gathered rows and of the weight block, and
+                  // an item is three products into the same accumulator: hi.Whi + lo.Whi + hi.Wlo
+  const float* in_lo;
+  const float* wimg_lo;
   int split;      // MMA issuer warps with their own accumulators (2, or 1 when 4 accumulators do not fit TMEM)
   int max_items;  // capacity of the shared-memory item list = n_local * K * nb
   int* err;
@@ -174,8 +178,9 @@ k_conv_tc(const __grid_constant__ TcParams p) {
   const uint32_t b_bytes = (uint32_t)p.n_pad * 128u;
   const uint32_t b_stride = (b_bytes + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = a_base + (uint32_t)S * kStageBytes;
-  const uint32_t e_base = b_base + (uint32_t)S * b_stride;
+  const uint32_t a_stage = (uint32_t)(1 + p.x3) * kStageBytes, b_stage = (uint32_t)(1 + p.x3) * b_stride;  // [hi | lo]
+  const uint32_t b_base = a_base + (uint32_t)S * a_stage;
+  const uint32_t e_base = b_base + (uint32_t)S * b_stage;
   const uint32_t m_base = e_base + (uint32_t)kProducers * kEntBytes;
   const uint32_t i_base = m_base + (((uint32_t)(3 * p.n_local + 1) * 4u + 15u) & ~15u);
   const uint32_t bar_base = i_base + (((uint32_t)p.max_items * 2u + 15u) & ~15u);
@@ -274,15 +279,17 @@ k_conv_tc(const __grid_constant__ TcParams p) {
         en = __ldg(reinterpret_cast<const int4*>(p.tbl + (int64_t)item_k(nxt) * p.tstride + (int64_t)ltile[item_tile(nxt)] * kTileM) + lane);
       }
       const int s = warp;
-      const uint32_t stage = a_base + (uint32_t)s * kStageBytes;
+      const uint32_t stage = a_base + (uint32_t)s * a_stage;
       TRACE(warp, i / S, 0);
       if (!mbar_wait(a_empty(s), (((uint32_t)i / (uint32_t)S) & 1u) ^ 1u, abort_flag)) goto done;
       TRACE(warp, i / S, 1);
       const bool half = (j == p.nb - 1) && p.last_w == 4;
       const bool tma = p.use_tma && !half;
       if (lane == 0) {  // this K-block's weight block rides on the same barrier as the gathered rows
-        mbar_arrive_expect_tx(a_full(s), b_bytes + (tma ? (uint32_t)kStageBytes : 0u));
-        bulk_g2s(b_base + (uint32_t)s * b_stride, p.wimg + ((size_t)k * p.nb + j) * p.n_pad * kKBlock, b_bytes, a_full(s));
+        mbar_arrive_expect_tx(a_full(s), (uint32_t)(1 + p.x3) * b_bytes + (tma ? (uint32_t)kStageBytes : 0u));
+        bulk_g2s(b_base + (uint32_t)s * b_stage, p.wimg + ((size_t)k * p.nb + j) * p.n_pad * kKBlock, b_bytes, a_full(s));
+        if (p.x3)
+          bulk_g2s(b_base + (uint32_t)s * b_stage + b_stride, p.wimg_lo + ((size_t)k * p.nb + j) * p.n_pad * kKBlock, b_bytes, a_full(s));
       }
       if (tma) {
         // One tile::gather4 per lane: rows 4 lane .. 4 lane + 3 of the K-block (128 bytes each, swizzled by the TMA
@@ -297,6 +304,11 @@ k_conv_tc(const __grid_constant__ TcParams p) {
         const float* src0 = p.in + j * kKBlock;
         if (!half) gather_block<8, false>(stage, ent, p.in, src0, (uint32_t)p.c_in, lane);
         else       gather_block<4, false>(stage, ent, p.in, src0, (uint32_t)p.c_in, lane);
+        if (p.x3) {  // the same rows of the lo plane, behind the hi block
+          const float* src1 = p.in_lo + j * kKBlock;
+          if (!half) gather_block<8, false>(stage + kStageBytes, ent, p.in_lo, src1, (uint32_t)p.c_in, lane);
+          else       gather_block<4, false>(stage + kStageBytes, ent, p.in_lo, src1, (uint32_t)p.c_in, lane);
+        }
         cp_async_arrive(a_full(s));
         __syncwarp();  // the entry row is rewritten by the next item
       }
@@ -381,13 +393,23 @@ k_conv_tc(const __grid_constant__ TcParams p) {
           TRACE(kProducers + 2 + m, n_mine, 1);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t a_desc = desc0 + desc_addr(a_base + (uint32_t)s * kStageBytes);
-            const uint64_t b_desc = desc0 + desc_addr(b_base + (uint32_t)s * b_stride);
+            const uint64_t a_desc = desc0 + desc_addr(a_base + (uint32_t)s * a_stage);
+            const uint64_t b_desc = desc0 + desc_addr(b_base + (uint32_t)s * b_stage);
             umma_tf32(d_tmem, a_desc, b_desc, idesc, acc);
             umma_tf32(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);  // +32 bytes per K-step of 8
             if (ksteps == 4) {
               umma_tf32(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
               umma_tf32(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+            }
+            if (p.x3) {  // + lo.Whi + hi.Wlo (the lo blocks sit one block behind the hi ones)
+              const uint64_t a_lo = a_desc + (kStageBytes >> 4), b_lo = b_desc + (b_stride >> 4);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (q < ksteps) {
+                  umma_tf32(d_tmem, a_lo + 2 * q, b_desc + 2 * q, idesc, 1u);
+                  umma_tf32(d_tmem, a_desc + 2 * q, b_lo + 2 * q, idesc, 1u);
+                }
+              }
             }
             umma_commit(a_empty(s));  // frees the stage and its weight block
           }
@@ -547,7 +569,8 @@ int mm3d_conv_tc_build_images(const float* const* weights, float* const* images,
 }
 
 int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
-                         const float* wimg, int K, const void* plan, int64_t plan_cap, int accumulate, cudaStream_t stream);
+                         const float* wimg, int K, const void* plan, int64_t plan_cap, int accumulate, cudaStream_t stream,
+                         const float* wimg_lo = nullptr);
 
 int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
                      const float* weight, int K, const void* plan, int64_t plan_cap, int flags, void* ws,
@@ -572,16 +595,15 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
   k_weight_image<<<mm3d_grid((int64_t)K * nb * n_pad * kKBlock, 256), 256, 0, stream>>>(weight, wimg_lo, K, c_in, c_out, nb,
                                                                                     n_pad, tr ? 1 : 0, mir ? 1 : 0, 1);
   mm3d_count_launches(1);
-  const float* in_lo = in + n_in * (int64_t)c_in;
-  int rc = mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, wimg, K, plan, plan_cap, 0, stream);
-  if (!rc) rc = mm3d_conv_fwd_tc_img(in_lo, n_in, c_in, out, n_out, c_out, wimg, K, plan, plan_cap, 1, stream);
-  if (!rc) rc = mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, wimg_lo, K, plan, plan_cap, 1, stream);
-  return rc;
+  return mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, wimg, K, plan, plan_cap, 0, stream, wimg_lo);
 }
 
 // the convolution proper, from a prebuilt weight image
+// wimg_lo != NULL: the TF32x3 form -- `in` carries a lo plane n_in * c_in floats behind the hi one, wimg_lo is the image of
+// the weights' TF32 remainder, and every item is three products (one launch, one gather of both planes)
 int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
-                         const float* wimg, int K, const void* plan, int64_t plan_cap, int accumulate, cudaStream_t stream) {
+                         const float* wimg, int K, const void* plan, int64_t plan_cap, int accumulate, cudaStream_t stream,
+                         const float* wimg_lo) {
   int nb, n_pad;
   MM3D_REQUIRE(tc_geometry(c_in, c_out, K, &nb, &n_pad) == 0, MM3D_ERR_UNSUPPORTED,
                "tcgen05 conv: unsupported shape c_in %d c_out %d K %d", c_in, c_out, K);
@@ -601,6 +623,9 @@ int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, in
   p.num_tiles = (int)mm3d_cdiv(n_out, kTileM);
   p.err = mm3d_device_err_flag();
   p.accumulate = accumulate;
+  p.x3 = wimg_lo ? 1 : 0;
+  p.in_lo = in + n_in * (int64_t)c_in;
+  p.wimg_lo = wimg_lo;
 #ifdef MM3D_TRACE
   p.trace = g_trace;
 #endif
@@ -611,11 +636,11 @@ int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, in
   // for 64+ input channels and slower for 32 (the TMA unit takes ~4 cycles per 128-byte row and is shared by the SM's
   // CTAs), 1 % slower over the whole step -- kept selectable for that comparison.
   static const bool want_tma = [] { const char* e = getenv("MM3D_TC_GATHER"); return e && strcmp(e, "tma") == 0; }();
-  if (want_tma && n_in > 0 && n_in < (1ll << 31) - 1) {
+  if (want_tma && !wimg_lo && n_in > 0 && n_in < (1ll << 31) - 1) {
     p.use_tma = mm3d_encode_rows_tmap(&p.tmap, in, n_in, c_in, /*atom32=*/false) ? 1 : 0;
   }
   const uint32_t b_stride = ((uint32_t)n_pad * 128u + 1023u) & ~1023u;
-  const size_t per_stage = (size_t)kStageBytes + b_stride;
+  const size_t per_stage = ((size_t)kStageBytes + b_stride) * (wimg_lo ? 2 : 1);
   static bool once_dev[64] = {false};
   bool& once = once_dev[mm3d_device_slot()];
   if (!once) {

@@ -39,7 +39,8 @@ int mm3d_conv_tc_supported(int c_in, int c_out, int K);
 int mm3d_conv_tc_build_images(const float* const* weights, float* const* images, const int* K, const int* c_in,
                               const int* c_out, const int* flags, int n, cudaStream_t stream);
 int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
-                         const float* wimg, int K, const void* plan, int64_t plan_cap, int accumulate, cudaStream_t stream);
+                         const float* wimg, int K, const void* plan, int64_t plan_cap, int accumulate, cudaStream_t stream,
+                         const float* wimg_lo = nullptr);
 
 namespace {
 
@@ -358,16 +359,12 @@ const float* find_img_lo(const Ctx& c, const float* w) {
     if (c.img_key[i] == w) return c.img_lo[i];
   return nullptr;
 }
-// One rule-table convolution from prebuilt weight images.  TF32x3 mode: hi.Whi + lo.Whi + hi.Wlo, three launches of the
-// same kernel, the second and third adding to `out` (`in` carries the lo plane n_in * c_in floats behind the hi one).
+// One rule-table convolution from prebuilt weight images.  TF32x3 mode: hi.Whi + lo.Whi + hi.Wlo inside one launch (`in`
+// carries the lo plane n_in * c_in floats behind the hi one, both planes are gathered into every ring stage).
 int conv_img(const Ctx& c, const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out, const float* im,
              const float* im_lo, int K, const void* plan, int64_t plan_cap) {
-  int rc = mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, im, K, plan, plan_cap, 0, c.stream);
-  if (c.net->pl() == 1 || rc) return rc;
-  if (!im_lo) { mm3d_set_error("tf32x3: missing lo weight image"); return MM3D_ERR_INVALID; }
-  rc = mm3d_conv_fwd_tc_img(in + n_in * (int64_t)c_in, n_in, c_in, out, n_out, c_out, im, K, plan, plan_cap, 1, c.stream);
-  if (!rc) rc = mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, im_lo, K, plan, plan_cap, 1, c.stream);
-  return rc;
+  if (c.net->pl() == 2 && !im_lo) { mm3d_set_error("tf32x3: missing lo weight image"); return MM3D_ERR_INVALID; }
+  return mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, im, K, plan, plan_cap, 0, c.stream, c.net->pl() == 2 ? im_lo : nullptr);
 }
 // forward of layer type `kind` whose FINE level is l
 void conv_fwd(Ctx& c, Kind kind, int l, const float* in, int c_in, float* out, int c_out, const float* w) {
