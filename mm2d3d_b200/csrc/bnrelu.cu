@@ -282,7 +282,7 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
                const float* __restrict__ gamma, const float* __restrict__ beta,
                const float* __restrict__ save_mean, const float* __restrict__ save_invstd, float leak,
                double* sums, unsigned int* sync, double* other, int other_words, float* d_gamma, float* d_beta, int training,
-               int round_flags, int* err) {
+               int round_flags, const float* __restrict__ add, int64_t add_ld, int* err) {
   mm3d_griddep_launch();
   mm3d_griddep_wait();
   zero_other(other, other_words);
@@ -385,6 +385,12 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
         const float d = o > 0.f ? g[u][j] : g[u][j] * leak;
         g[u][j] = scale[j] * (d - md[j] - xc * invstd[j] * mdx[j]);
       }
+      if (add) {  // dx += another gradient of the same tensor (the U-Net's skip connection), before any rounding
+        float a_[VEC];
+        vload<VEC>(add + (row + u * stride) * add_ld + v * VEC, a_);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) g[u][j] += a_[j];
+      }
       store_planes<VEC>(dxb + (row + u * stride) * dxld, g[u], rnd, dplane);
     }
   }
@@ -398,6 +404,12 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
       const float o = fmaf(xc, scale[j], bet[j]);
       const float d = o > 0.f ? g[j] : g[j] * leak;
       g[j] = scale[j] * (d - md[j] - xc * invstd[j] * mdx[j]);
+    }
+    if (add) {
+      float a_[VEC];
+      vload<VEC>(add + row * add_ld + v * VEC, a_);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) g[j] += a_[j];
     }
     store_planes<VEC>(dxb + row * dxld, g, rnd, dplane);
   }
@@ -494,10 +506,12 @@ int mm3d_bnrelu_fwd_impl(const float* x, const float* x_hi, int c_lo, float* y, 
 int mm3d_bnrelu_bwd_impl(const float* x, const float* x_hi, int c_lo, const float* dy, float* dx, float* dx_hi,
                          int64_t n, int c, const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
                          float* d_gamma, float* d_beta, float leakiness, int training,
-                         void* ws, size_t ws_bytes, bool ws_clean, int round_flags, cudaStream_t stream) {
+                         void* ws, size_t ws_bytes, bool ws_clean, int round_flags, const float* add, int64_t add_ld,
+                         cudaStream_t stream) {
   MM3D_REQUIRE(c > 0 && n >= 0, MM3D_ERR_INVALID, "bad sizes");
-  const bool vec4 = (c % 4 == 0) && (c_lo % 4 == 0) &&
-                    ((((uintptr_t)x | (uintptr_t)x_hi | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dx_hi) & 15) == 0);
+  MM3D_REQUIRE(!add || !dx_hi, MM3D_ERR_INVALID, "bnrelu_bwd: an addend is only supported for a single output block");
+  const bool vec4 = (c % 4 == 0) && (c_lo % 4 == 0) && (!add || add_ld % 4 == 0) &&
+                    ((((uintptr_t)x | (uintptr_t)x_hi | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)dx_hi | (uintptr_t)add) & 15) == 0);
   const int cv = vec4 ? c / 4 : c;
   MM3D_REQUIRE(cv <= kThreads, MM3D_ERR_UNSUPPORTED, "BatchNorm with %d channels not supported", c);
   MM3D_REQUIRE(ws_bytes >= mm3d_bnrelu_workspace_bytes(c) && ws, MM3D_ERR_WORKSPACE, "bnrelu workspace too small");
@@ -516,7 +530,7 @@ int mm3d_bnrelu_bwd_impl(const float* x, const float* x_hi, int c_lo, const floa
   const size_t smem = sizeof(double) * 2 * c > sizeof(float) * 2 * (kThreads / cv) * (size_t)c
                           ? sizeof(double) * 2 * c : sizeof(float) * 2 * (kThreads / cv) * (size_t)c;
   BN_DISPATCH_PDL(k_bn_bwd_fused, x, x_hi, c_lo, dy, dx, dx_hi, n, c, gamma, beta, save_mean, save_invstd, leakiness, sums, sync, other, other_words, d_gamma,
-              d_beta, training, round_flags, mm3d_device_err_flag());
+              d_beta, training, round_flags, add, add_ld, mm3d_device_err_flag());
   mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_bnrelu_bwd");
   return MM3D_OK;
@@ -535,5 +549,5 @@ extern "C" int mm3d_bnrelu_bwd(const float* x, const float* dy, float* dx, int64
                                float* d_gamma, float* d_beta, float leakiness, int training,
                                void* ws, size_t ws_bytes, mm3d_stream_t stream) {
   return mm3d_bnrelu_bwd_impl(x, nullptr, 0, dy, dx, nullptr, n, c, gamma, beta, save_mean, save_invstd, d_gamma, d_beta, leakiness, training,
-                              ws, ws_bytes, false, 0, (cudaStream_t)stream);
+                              ws, ws_bytes, false, 0, nullptr, 0, (cudaStream_t)stream);
 }

@@ -31,7 +31,8 @@ int mm3d_bnrelu_fwd_impl(const float* x, const float* x_hi, int c_lo, float* y, 
 int mm3d_bnrelu_bwd_impl(const float* x, const float* x_hi, int c_lo, const float* dy, float* dx, float* dx_hi,
                          int64_t n, int c, const float* gamma, const float* beta, const float* save_mean,
                          const float* save_invstd, float* d_gamma, float* d_beta, float leakiness, int training,
-                         void* ws, size_t ws_bytes, bool ws_clean, int round_flags, cudaStream_t stream);
+                         void* ws, size_t ws_bytes, bool ws_clean, int round_flags, const float* add, int64_t add_ld,
+                         cudaStream_t stream);
 
 // conv_tc.cu
 size_t mm3d_conv_tc_workspace_bytes(int c_in, int c_out, int K);
@@ -191,44 +192,6 @@ __global__ void k_round_tf32(const float* __restrict__ in, float* __restrict__ o
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[(nv << 2) + threadIdx.x] = mm3d_rna_tf32(__ldg(in + (nv << 2) + threadIdx.x));
 }
 
-__global__ void k_split_add(const float* __restrict__ dj, int ldj, const float* __restrict__ add, int64_t n, int p,
-                            float* __restrict__ dy, float* __restrict__ df, int round_tf32) {
-  mm3d_griddep_launch();
-  mm3d_griddep_wait();
-  // dy = dj[:, :p] + add ; df = dj[:, p:]   (dj rows are ldj floats apart; df only with ldj == 2p)
-  if ((p & 3) == 0) {
-    const int pv = p >> 2;
-    const int64_t total = n * pv;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-      const int64_t r = i / pv;
-      const int j = (int)(i - r * pv) << 2;
-      const float4 a = __ldg(reinterpret_cast<const float4*>(dj + r * ldj + j));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(add + r * p + j));
-      float4 o = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-      if (round_tf32) {
-        const float4 h = make_float4(mm3d_rna_tf32(o.x), mm3d_rna_tf32(o.y), mm3d_rna_tf32(o.z), mm3d_rna_tf32(o.w));
-        if (round_tf32 == 2)  // lo plane (TF32x3 mode)
-          *reinterpret_cast<float4*>(dy + n * p + r * p + j) =
-              make_float4(mm3d_rna_tf32(o.x - h.x), mm3d_rna_tf32(o.y - h.y), mm3d_rna_tf32(o.z - h.z), mm3d_rna_tf32(o.w - h.w));
-        o = h;
-      }
-      *reinterpret_cast<float4*>(dy + r * p + j) = o;
-      if (df) *reinterpret_cast<float4*>(df + r * p + j) = __ldg(reinterpret_cast<const float4*>(dj + r * ldj + p + j));
-    }
-    return;
-  }
-  const int64_t total = n * p;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / p;
-    const int j = (int)(i - r * p);
-    const float o = __ldg(dj + r * ldj + j) + __ldg(add + i);
-    const float h = round_tf32 ? mm3d_rna_tf32(o) : o;
-    if (round_tf32 == 2) dy[n * p + i] = mm3d_rna_tf32(o - h);
-    dy[i] = h;
-    if (df) df[i] = __ldg(dj + r * ldj + p + j);
-  }
-}
-
 // Backward runs the weight gradients on a second stream: a layer's wgrad only feeds the optimiser, while its
 // dgrad is on the critical chain, and neither kernel fills the GPU alone at the deeper levels.
 struct SideStream {
@@ -341,11 +304,14 @@ void bn_fwd(Ctx& c, int pidx, const float* x, float* y, int64_t n, int ch, float
                           tc_mode(c) && to_conv ? c.net->pl() : 0, c.stream));
 }
 // round: bit 0 = dx (its low column block when split) feeds a convolution as d_out, bit 1 = dx_hi does
+// add (rows add_ld floats apart): another gradient of the same tensor, summed into dx before it is stored
 void bn_bwd(Ctx& c, int pidx, const float* x, const float* dy, float* dx, int64_t n, int ch, const float* save,
-            int round, const float* x_hi = nullptr, int c_lo = 0, float* dx_hi = nullptr) {
+            int round, const float* x_hi = nullptr, int c_lo = 0, float* dx_hi = nullptr, const float* add = nullptr,
+            int64_t add_ld = 0) {
   if (abl_skip("bn")) return;
   EX(mm3d_bnrelu_bwd_impl(x, x_hi, c_lo, dy, dx, dx_hi, n, ch, P(c, pidx), P(c, pidx + 1), save, save + ch, Gp(c, pidx), Gp(c, pidx + 1), 0.f,
-                          c.training, c.bn_ws, c.bn_ws_bytes, true, tc_mode(c) ? (round | (c.net->pl() == 2 ? 4 : 0)) : 0, c.stream));
+                          c.training, c.bn_ws, c.bn_ws_bytes, true, tc_mode(c) ? (round | (c.net->pl() == 2 ? 4 : 0)) : 0, add, add_ld,
+                          c.stream));
 }
 enum Kind { SMC, DOWN, UP };
 
@@ -616,16 +582,11 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
     float* d_B = g.f(n, p);
     conv_bwd(c, DOWN, l, B.B, p, d_Xn, q, P(c, dn + 4), d_B, Gp(c, dn + 4));
     MARK("down_dgrad", l);
-    float* d_Ybr = g.f(n, p);
-    bn_bwd(c, dn, B.Y, d_B, d_Ybr, n, p, B.s_dn, 0);  // summed with the skip gradient below, rounded there
+    // d_Y = d_J[:, :p] (the skip half of the join's gradient) + the branch gradient: summed inside the BatchNorm
+    // backward of the down-branch, stored rounded (it is the pre-block convolution's d_out)
+    bn_bwd(c, dn, B.Y, d_B, d_Yskip, n, p, B.s_dn, 1, nullptr, 0, nullptr, d_J, split ? p : 2 * p);
     MARK("bn_bwd dn", l);
-    // d_Y = d_J[:, :p] + d_Ybr
-    if (n && !c.rc) {
-      if (mm3d_launch_pdl(k_split_add, dim3(mm3d_grid(n * p / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)d_J, split ? p : 2 * p, (const float*)d_Ybr, n, p, d_Yskip, (float*)nullptr, tc_mode(c) ? pl : 0) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
-      mm3d_count_launches(1);
-    }
     d_Y = d_Yskip;
-    MARK("split_add", l);
   }
   float* d_A = g.f(n, p);
   conv_bwd(c, SMC, l, B.A, p, d_Y, p, P(c, pbase + 4), d_A, Gp(c, pbase + 4));
