@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--no-pipeline", dest="pipeline", action="store_false",
                     help="build each step's sparse structure inline on the compute stream instead of one step ahead")
     ap.add_argument("--no-kernel-pass", action="store_true")
+    ap.add_argument("--ab", default="", help="development: NAME=VALUE, time alternating blocks of steps with that variable set / unset")
     ap.add_argument("--full-step", action="store_true",
                     help="BASELINE configs[2]: whole MM2D3D training step (2D ResNet34-UNet stand-in on stock cuDNN + lift + "
                          "UNetSCN + heads + losses + optimiser), source and target batch, single GPU")
@@ -476,6 +477,33 @@ def run_ours(args):
             torch.cuda.synchronize()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+
+    if args.ab and world == 1:
+        # development aid: alternate blocks of steps with an environment switch of the library set / unset (switches
+        # that the library reads at every call), in ONE process on ONE box -- box-to-box variation is larger than most
+        # kernel changes.  Printed on stderr; not part of the JSON line.
+        name, _, val = args.ab.partition("=")
+        rows = {"set": [], "unset": []}
+        for rnd in range(6):
+            for which in ("set", "unset"):
+                if which == "set":
+                    os.environ[name] = val
+                else:
+                    os.environ.pop(name, None)
+                for i in range(3):
+                    step(i)
+                barrier()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for i in range(20):
+                    step(i)
+                a1.record()
+                barrier()
+                rows[which].append(a0.elapsed_time(a1) / 20)
+        os.environ.pop(name, None)
+        for which in rows:
+            v = sorted(rows[which])
+            print(f"[ab] {name}={val} {which:5s}: median {v[len(v) // 2]:.3f} ms  all {' '.join(f'{x:.3f}' for x in rows[which])}", file=sys.stderr)
 
     # end to end: pinned host inputs -> device -> fwd+bwd (-> all-reduce) -> scalar back to the host
     # untimed lead-in: every distinct batch once (+2), so that the copy stream's allocator pool has seen all sizes and

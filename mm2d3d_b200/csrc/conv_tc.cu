@@ -65,14 +65,16 @@ struct TcParams {
   int max_items;  // capacity of the shared-memory item list = n_local * K * nb
   int* err;
 #ifdef MM3D_TRACE
-  long long* trace;  // development builds: clock64 stamps of CTA 0's roles, [role][64 records][4]
+  long long* trace;  // development builds: clock64 stamps of one CTA's roles, [role][64 records][4], then
+                     // [4096 + 2 cta]: globaltimer at every CTA's start (after the dependency wait) and end
+  int trace_cta;     // ... which CTA's roles (MM3D_TC_TRACE_CTA)
 #endif
 };
 
 #ifdef MM3D_TRACE
 #define TRACE(role, rec, slot)                                                                                   \
   do {                                                                                                           \
-    if (p.trace && blockIdx.x == 0 && lane == 0 && (rec) < 64) p.trace[(((role) * 64) + (rec)) * 4 + (slot)] = clock64(); \
+    if (p.trace && (int)blockIdx.x == p.trace_cta && lane == 0 && (rec) < 64) p.trace[(((role) * 64) + (rec)) * 4 + (slot)] = clock64(); \
   } while (0)
 #else
 #define TRACE(role, rec, slot) do {} while (0)
@@ -215,6 +217,13 @@ k_conv_tc(const __grid_constant__ TcParams p) {
   }
   if (warp == kProducers + 4) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
   mm3d_griddep_wait();
+#ifdef MM3D_TRACE
+  if (p.trace && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[4096 + 2 * blockIdx.x] = (long long)gt;
+  }
+#endif
   // this CTA's tiles (mm3d_plan_local_tile), their masks and the item list
   int n_local = p.n_local;
   if (mm3d_plan_local_tile(p.order, p.num_tiles, (int)gridDim.x, (int)blockIdx.x, n_local - 1) < 0) --n_local;
@@ -428,6 +437,13 @@ done:
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0 && *abort_flag) mm3d_raise(p.err);
+#ifdef MM3D_TRACE
+  if (p.trace && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[4096 + 2 * blockIdx.x + 1] = (long long)gt;
+  }
+#endif
   if (warp == kProducers + 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -628,6 +644,7 @@ int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, in
   p.wimg_lo = wimg_lo;
 #ifdef MM3D_TRACE
   p.trace = g_trace;
+  p.trace_cta = getenv("MM3D_TC_TRACE_CTA") ? atoi(getenv("MM3D_TC_TRACE_CTA")) : 0;
 #endif
   p.use_tma = 0;
   p.oob_row = (int)n_in;

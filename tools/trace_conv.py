@@ -34,7 +34,7 @@ def main():
     w = torch.randn(t.K, 1, a.cin, a.cout, device=dev) / (a.cin * t.K) ** 0.5
     out = torch.empty(t.n_out, a.cout, device=dev)
     ws = F.scratch(max(lib.mm3d_conv_workspace_bytes(t.n_in, t.n_out, a.cin, a.cout, t.K, m), 1 << 22), dev)
-    trace = torch.zeros(16 * 64 * 4, dtype=torch.int64, device=dev)
+    trace = torch.zeros(16 * 64 * 4 + 1024, dtype=torch.int64, device=dev)
     flush = torch.empty(384 << 20, dtype=torch.uint8, device=dev)
 
     dout = torch.randn(t.n_out, a.cout, device=dev)
@@ -56,7 +56,14 @@ def main():
     run()
     torch.cuda.synchronize()
     lib.mm3d_debug_set_trace(None)
-    tr = trace.view(16, 64, 4).cpu().numpy()
+    ctas = trace[4096:].view(-1, 2).cpu().numpy()
+    tr = trace[:4096].view(16, 64, 4).cpu().numpy()
+    if (ctas > 0).any():  # forward kernel: globaltimer at each CTA's start (after the dependency wait) and end, ns
+        live = ctas[ctas[:, 0] > 0]
+        g0 = live[:, 0].min()
+        print("CTA start/end (ns after the first start):")
+        for c, (b, e) in enumerate(live):
+            print(f"   cta {c:3d} {b - g0:7d} {e - g0:7d}")
     t0 = tr[tr > 0].min()
     rel = lambda v: "      -" if v == 0 else f"{(v - t0):7d}"
     print("columns: producers (roles 0..7): wait_start got_stage filled -- epilogue (role 9): wait_start got_tile done -- "
