@@ -48,6 +48,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     headers = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(INCLUDE, "*.h")))
     nvcc = _nvcc()
+    # objects compiled with other flags (a development build before or after a product build) are stale too
+    stamp = os.path.join(OBJ, "flags.txt")
+    flags_now = " ".join([*NVCC_FLAGS, *extra])
+    if not os.path.exists(stamp) or open(stamp).read() != flags_now:
+        force = True
     jobs = []
     objs = []
     for src in sources:
@@ -68,6 +73,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             list(ex.map(run, jobs))
     if jobs or force or _stale(LIB, objs):
         run([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    with open(stamp, "w") as f:
+        f.write(flags_now)
     return LIB
 
 
