@@ -36,7 +36,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     # BASELINE.json configs[1] names both arithmetic modes; the tensor-core one (tcgen05 kind::tf32, FP32
     # accumulate, parity bar 1e-2) is the headline, the FP32 SIMT parity mode (1e-4) is timed beside it
-    ap.add_argument("--mode", default=os.environ.get("MM3D_BENCH_MODE", "tf32"), choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--mode", default=os.environ.get("MM3D_BENCH_MODE", "tf32"), choices=["fp32", "tf32", "tf32x3", "bf16"])
     ap.add_argument("--no-fp32-side", action="store_true", help="skip the short FP32-mode measurement")
     ap.add_argument("--shape", default="nuscenes", choices=["nuscenes", "semantickitti"])
     ap.add_argument("--batch", type=int, default=8, help="scans per GPU per step")
@@ -232,8 +232,8 @@ def kernel_pass(net, locs_d, feats_d, mode, pk):
         fwd_t, bwd_t, bwd_flags = F.conv_tables(meta, mod.kind, spatial, plans=mode != "fp32")
         out = torch.empty(fwd_t.n_out, c_out, device=dev)
         dout = torch.randn(fwd_t.n_out, c_out, device=dev)
-        if mode == "tf32x3":  # the gathered operands carry a hi and a lo plane in this mode
-            x, dout = F._planes(x), F._planes(dout)
+        if mode in ("tf32x3", "bf16"):  # the gathered operands carry two planes in these modes
+            x, dout = F._planes(x, mode == "bf16"), F._planes(dout, mode == "bf16")
         dx = torch.empty(bwd_t.n_out, c_in, device=dev)
         dw = torch.empty_like(w)
         ws = F.scratch(max(lib.mm3d_conv_workspace_bytes(fwd_t.n_in, fwd_t.n_out, c_in, c_out, K, m),
@@ -570,8 +570,10 @@ def run_ours(args):
             notes = {"fp32": "same workload and loops in the FP32 SIMT parity mode (activations / gradients within 1e-4): the "
                              "figure to set against the reference's FP32 3D branch",
                      "tf32x3": "same workload and loops with FP32-grade arithmetic on the tensor cores: every convolution as three "
-                               "error-compensated TF32 products (hi.hi + lo.hi + hi.lo), activations / gradients within 1e-4"}
-            for smode in ("fp32", "tf32x3"):
+                               "error-compensated TF32 products (hi.hi + lo.hi + hi.lo), activations / gradients within 1e-4",
+                     "bf16": "same workload and loops with BF16 gathered operands and weights in forward and dgrad (kind::f16, FP32 "
+                             "accumulate, half the gathered bytes), TF32 weight gradients; 1e-2 per op"}
+            for smode in ("fp32", "tf32x3", "bf16"):
                 scn_mod.set_conv_mode(smode)
                 prepared.clear()  # (row plans are built per mode)
                 try:
@@ -589,7 +591,7 @@ def run_ours(args):
                     prepared.clear()
                     fe2e = time_e2e(n_f) / n_f
                     side[smode] = {"value": args.batch / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms, "steps": n_f, "warmup": 3,
-                                   "dtype": "f32" if smode == "fp32" else "tf32x3 (f32-grade)",
+                                   "dtype": {"fp32": "f32", "tf32x3": "tf32x3 (f32-grade)", "bf16": "bf16"}[smode],
                                    "e2e": {"value": args.batch / (fe2e * 1e-3), "unit": UNIT, "ms_per_step": fe2e}, "note": notes[smode]}
                 finally:
                     scn_mod.set_conv_mode(args.mode)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MM3D_ABI_VERSION 3
+#define MM3D_ABI_VERSION 4
 
 #define MM3D_OK 0
 #define MM3D_ERR_INVALID 1     /* bad argument */
@@ -39,7 +39,11 @@ extern "C" {
 /* arithmetic modes of the convolution kernels */
 #define MM3D_MODE_FP32 0 /* SIMT FP32 FMA -- the parity mode (1e-4) */
 #define MM3D_MODE_TF32 1 /* tcgen05 kind::tf32, FP32 accumulate in TMEM (1e-2) */
-#define MM3D_MODE_BF16 2 /* tcgen05 kind::f16 with BF16 operands, FP32 accumulate (1e-2) -- reserved, refused */
+#define MM3D_MODE_BF16 2 /* tcgen05 kind::f16 with BF16 gathered operands and weights, FP32 accumulate (1e-2 per
+                          * op): forward and dgrad gather half the bytes of the TF32 mode.  The gathered operand (`in` of
+                          * mm3d_conv_fwd) carries an FP32 plane of [rows, c] floats (TF32-rounded values) and, rows * c
+                          * floats behind it, a BF16 plane of [rows, c] bfloat16 (mm3d_split_bf16).  mm3d_conv_wgrad runs
+                          * the TF32 kernel on the FP32 planes of `in` and `d_out` */
 #define MM3D_MODE_TF32X3 3 /* tcgen05, three error-compensated TF32 products (hi.hi + lo.hi + hi.lo), FP32 accumulate:
                             * FP32-grade results (1e-4 bar) on the tensor cores.  The gathered operands (`in` of
                             * mm3d_conv_fwd; `in` and `d_out` of mm3d_conv_wgrad) carry TWO planes of [rows, c] floats,
@@ -187,6 +191,9 @@ MM3D_API int mm3d_conv_fwd(const float* in, int64_t n_in, int c_in, float* out, 
 MM3D_API int mm3d_round_tf32(const float* in, float* out, int64_t n, mm3d_stream_t stream);
 /* out[0..n) = tf32(in), out[n..2n) = tf32(in - tf32(in)): the two operand planes of MM3D_MODE_TF32X3 */
 MM3D_API int mm3d_split_tf32(const float* in, float* out, int64_t n, mm3d_stream_t stream);
+/* out[0..n) = tf32(in) (float32) and, starting at float index n, n bfloat16 values bf16(in) (round to nearest even):
+ * the two operand planes of MM3D_MODE_BF16; `out` holds 2 n floats, the BF16 plane fills the first half of the second n */
+MM3D_API int mm3d_split_bf16(const float* in, float* out, int64_t n, mm3d_stream_t stream);
 /* d_weight[k] (+)= sum_j in[tbl(j,k)]^T . d_out[j]   ([K, c_in, c_out]); accumulate=0 overwrites */
 MM3D_API int mm3d_conv_wgrad(const float* in, int64_t n_in, int c_in, const float* d_out, int64_t n_out,
                     int c_out, float* d_weight, int K, const int32_t* tbl, int64_t tbl_stride,

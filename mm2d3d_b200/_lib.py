@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmm3d.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 LEVEL_DESC_WORDS = 10
 
 MODE_FP32, MODE_TF32, MODE_BF16, MODE_TF32X3 = 0, 1, 2, 3
@@ -54,6 +54,7 @@ SIGNATURES = {
     "mm3d_conv_fwd": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i, _p, _i64, _p, _p, _i64, _i, _i, _p, _sz, _p]),
     "mm3d_round_tf32": (_i, [_p, _p, _i64, _p]),
     "mm3d_split_tf32": (_i, [_p, _p, _i64, _p]),
+    "mm3d_split_bf16": (_i, [_p, _p, _i64, _p]),
     "mm3d_conv_wgrad": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i, _p, _i64, _p, _p, _i64, _i, _i, _p, _sz, _p]),
     "mm3d_bnrelu_workspace_bytes": (_sz, [_i]),
     "mm3d_bnrelu_fwd": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _f, _f, _f, _i, _p, _sz, _p]),

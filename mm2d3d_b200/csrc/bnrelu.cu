@@ -8,6 +8,7 @@
 // warp reads consecutive float4s of consecutive rows (fully coalesced) and every thread keeps
 // one fixed channel vector; per-thread FP32 partials are combined in FP64 (shared, then global
 // atomics into 2*C doubles), which makes var = E[x^2] - mean^2 safe.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace {
@@ -37,10 +38,29 @@ template <> __device__ __forceinline__ void vstore<4>(float* p, const float (&v)
 template <> __device__ __forceinline__ void vstore<1>(float* p, const float (&v)[1]) { *p = v[0]; }
 
 // Store for a tensor that a tensor-core convolution gathers: mode 0 = as is, 1 = rounded to TF32 (nearest), 2 = two
-// planes `plane` floats apart: hi = tf32(v), lo = tf32(v - hi) (the error-compensated TF32x3 mode)
+// planes `plane` floats apart: hi = tf32(v), lo = tf32(v - hi) (the error-compensated TF32x3 mode), 3 = the
+// TF32-rounded FP32 plane (the weight-gradient operand) and, `plane` floats behind the tensor's base, a BF16 plane
+// (the gathered operand of the BF16 mode; element i of the tensor at BF16 index i)
 template <int VEC>
-__device__ __forceinline__ void store_planes(float* p, float (&v)[VEC], int mode, int64_t plane) {
+__device__ __forceinline__ void store_planes(float* base, float* p, float (&v)[VEC], int mode, int64_t plane) {
   if (mode == 0) { vstore<VEC>(p, v); return; }
+  if (mode == 3) {
+    __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(base + plane) + (p - base);
+    if (VEC == 4) {
+      const __nv_bfloat162 b01 = __floats2bfloat162_rn(v[0], v[1]), b23 = __floats2bfloat162_rn(v[2 % VEC], v[3 % VEC]);
+      uint2 u;
+      u.x = *reinterpret_cast<const unsigned int*>(&b01);
+      u.y = *reinterpret_cast<const unsigned int*>(&b23);
+      *reinterpret_cast<uint2*>(b) = u;
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) b[j] = __float2bfloat16_rn(v[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = mm3d_rna_tf32(v[j]);
+    vstore<VEC>(p, v);
+    return;
+  }
   float lo[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
@@ -130,7 +150,7 @@ k_bn_apply(const float* __restrict__ x, float* __restrict__ y, int64_t n, int c,
       const float o = fmaf(t[j] - mean[j], scale[j], bet[j]);
       t[j] = o > 0.f ? o : o * leak;
     }
-    store_planes<VEC>(y + row * c + v * VEC, t, round_tf32, n * c);
+    store_planes<VEC>(y, y + row * c + v * VEC, t, round_tf32, n * c);
   }
 }
 
@@ -259,7 +279,7 @@ k_bn_fwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
         const float o = fmaf(t[u][j] - mean[j], scale[j], bet[j]);
         t[u][j] = o > 0.f ? o : o * leak;
       }
-      store_planes<VEC>(y + (row + u * stride) * c + v * VEC, t[u], round_tf32, n * c);
+      store_planes<VEC>(y, y + (row + u * stride) * c + v * VEC, t[u], round_tf32, n * c);
     }
   }
   for (; row < n; row += stride) {
@@ -270,7 +290,7 @@ k_bn_fwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
       const float o = fmaf(t[j] - mean[j], scale[j], bet[j]);
       t[j] = o > 0.f ? o : o * leak;
     }
-    store_planes<VEC>(y + row * c + v * VEC, t, round_tf32, n * c);
+    store_planes<VEC>(y, y + row * c + v * VEC, t, round_tf32, n * c);
   }
 }
 
@@ -300,7 +320,9 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
   // round_flags bit 0: dx (or its low column block) feeds a TF32 convolution as d_out -> store RNA-rounded values;
   // bit 1: same for the high column block dx_hi
   // bit 2: those outputs carry a hi and a lo plane (TF32x3 mode), the lo plane n * (row length) floats behind
-  const int rnd = (round_flags & ((dx_hi && hi) ? 2 : 1)) ? ((round_flags & 4) ? 2 : 1) : 0;
+  // bit 3: ... a TF32-rounded FP32 plane and a BF16 plane behind it (BF16 mode)
+  const int rnd = (round_flags & ((dx_hi && hi) ? 2 : 1)) ? ((round_flags & 8) ? 3 : (round_flags & 4) ? 2 : 1) : 0;
+  float* dx0 = (dx_hi && hi) ? dx_hi : dx;  // base of the tensor this thread writes
   const int64_t dplane = n * dxld;
   float mean[VEC], invstd[VEC], scale[VEC], bet[VEC];
 #pragma unroll
@@ -391,7 +413,7 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
 #pragma unroll
         for (int j = 0; j < VEC; ++j) g[u][j] += a_[j];
       }
-      store_planes<VEC>(dxb + (row + u * stride) * dxld, g[u], rnd, dplane);
+      store_planes<VEC>(dx0, dxb + (row + u * stride) * dxld, g[u], rnd, dplane);
     }
   }
   for (; row < n; row += stride) {
@@ -411,7 +433,7 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
 #pragma unroll
       for (int j = 0; j < VEC; ++j) g[j] += a_[j];
     }
-    store_planes<VEC>(dxb + row * dxld, g, rnd, dplane);
+    store_planes<VEC>(dx0, dxb + row * dxld, g, rnd, dplane);
   }
 }
 

@@ -92,6 +92,13 @@ extern "C" int mm3d_conv_fwd(const float* in, int64_t n_in, int c_in, float* out
       MM3D_REQUIRE(plan, MM3D_ERR_INVALID, "mm3d_conv_fwd: tf32 mode needs the table's row plan (mm3d_build_plan)");
       return mm3d_conv_fwd_tc(in, n_in, c_in, out, n_out, c_out, weight, K, plan, plan_cap, flags, ws, ws_bytes,
                               (cudaStream_t)stream);
+    case MM3D_MODE_BF16:
+      // `in`: an FP32 plane and the BF16 plane behind it (mm3d_split_bf16); the BF16 plane is what is gathered
+      MM3D_REQUIRE(mm3d_conv_tc_supported(c_in, c_out, K), MM3D_ERR_UNSUPPORTED,
+                   "bf16 conv: c_in %d must be a multiple of 16 (pad the channels)", c_in);
+      MM3D_REQUIRE(plan, MM3D_ERR_INVALID, "mm3d_conv_fwd: bf16 mode needs the table's row plan (mm3d_build_plan)");
+      return mm3d_conv_fwd_tc(in, n_in, c_in, out, n_out, c_out, weight, K, plan, plan_cap, flags | MM3D_CONV_BF16, ws, ws_bytes,
+                              (cudaStream_t)stream);
     case MM3D_MODE_TF32X3:
       MM3D_REQUIRE(mm3d_conv_tc_supported(c_in, c_out, K), MM3D_ERR_UNSUPPORTED,
                    "tf32x3 conv: c_in %d must be a multiple of 16 (pad the channels)", c_in);
@@ -124,6 +131,7 @@ extern "C" int mm3d_conv_wgrad(const float* in, int64_t n_in, int c_in, const fl
       if (!rc) rc = mm3d_conv_wgrad_tc(in, n_in, c_in, dout_lo, n_out, c_out, d_weight, K, plan, plan_cap, 1, (cudaStream_t)stream);
       return rc;
     }
+    case MM3D_MODE_BF16:  // the weight gradient of the BF16 mode is the TF32 one, on the operands' FP32 planes
     case MM3D_MODE_TF32:
       if (mm3d_conv_wgrad_tc_supported(c_in, c_out, K)) {
         MM3D_REQUIRE(plan, MM3D_ERR_INVALID, "mm3d_conv_wgrad: tf32 mode needs the table's row plan (mm3d_build_plan)");

@@ -10,6 +10,7 @@
 // internal convolution flags (next to the public MM3D_CONV_TRANSPOSE_W / MM3D_CONV_MIRROR_K of mm3d.h)
 #define MM3D_CONV_WEIGHT_LO 4  // weight image of tf32(w - tf32(w)) instead of tf32(w)
 #define MM3D_CONV_X3 8         // error-compensated products: `in` carries hi and lo planes, two weight images
+#define MM3D_CONV_BF16 16      // BF16 operands: `in` carries an FP32 plane and, behind it, a BF16 plane (the one gathered)
 
 #define MM3D_NUM_SMS 148  // B200: 2 dies x 74 SMs; persistent / grid-stride kernels size to this
 

@@ -21,6 +21,7 @@
 //                             accum    acc_full[2] (tcgen05.commit)       / acc_empty[2] (128 arrivals)
 // The accumulator is double buffered in TMEM, so the epilogue of tile i overlaps the MMAs of i+1.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -59,8 +60,9 @@ struct TcParams {
   int accumulate; // epilogue adds to `out` instead of overwriting it
   int x3;         // TF32x3 mode: every stage also holds the lo planes of the gathered rows and of the weight block, and
                   // an item is three products into the same accumulator: hi.Whi + lo.Whi + hi.Wlo
-  const float* in_lo;
+ const float* in_lo;
   const float* wimg_lo;
+  int bf16;       // BF16 mode: `in` and the weight image hold BF16 elements (64 channels per 128-byte K-block), kind::f16
   int split;      // MMA issuer warps with their own accumulators (2, or 1 when 4 accumulators do not fit TMEM)
   int max_items;  // capacity of the shared-memory item list = n_local * K * nb
   int* err;
@@ -90,31 +92,38 @@ __device__ __forceinline__ float wimg_value(float v, int lo) {
   return lo ? to_tf32(v - hi) : hi;
 }
 
-__global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ img, int K, int c_in, int c_out, int nb,
-                               int n_pad, int transposed, int mirror, int lo) {
-  const int64_t total = (int64_t)K * nb * n_pad * kKBlock;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int e_sw = (int)(i % kKBlock);
-    const int n = (int)((i / kKBlock) % n_pad);
-    const int blk = (int)(i / ((int64_t)kKBlock * n_pad));
-    const int k = blk / nb, j = blk - k * nb;
-    const int chunk = (e_sw >> 2) ^ (n & 7);  // un-swizzle: which logical chunk lives here
-    const int ci = j * kKBlock + chunk * 4 + (e_sw & 3);
-    float v = 0.f;
-    if (ci < c_in && n < c_out) {
-      const int ks = mirror ? K - 1 - k : k;
-      v = transposed ? __ldg(w + ((int64_t)ks * c_out + n) * c_in + ci)   // forward weight is [K][c_out][c_in]
-                     : __ldg(w + ((int64_t)ks * c_in + ci) * c_out + n);  // [K][c_in][c_out]
-    }
-    img[i] = wimg_value(v, lo);
+// bf16 != 0: BF16 elements, 64 channels per 128-byte row (8 per 16-byte chunk), round to nearest even
+__device__ __forceinline__ void wimg_element(const float* __restrict__ w, float* __restrict__ img, int64_t i, int K, int c_in,
+                                             int c_out, int nb, int n_pad, int transposed, int mirror, int lo, int bf16) {
+  const int per_row = bf16 ? 2 * kKBlock : kKBlock, per_chunk = bf16 ? 8 : 4;
+  const int e_sw = (int)(i % per_row);
+  const int n = (int)((i / per_row) % n_pad);
+  const int blk = (int)(i / ((int64_t)per_row * n_pad));
+  const int k = blk / nb, j = blk - k * nb;
+  const int chunk = (e_sw / per_chunk) ^ (n & 7);  // un-swizzle: which logical chunk lives here
+  const int ci = j * per_row + chunk * per_chunk + (e_sw % per_chunk);
+  float v = 0.f;
+  if (ci < c_in && n < c_out) {
+    const int ks = mirror ? K - 1 - k : k;
+    v = transposed ? __ldg(w + ((int64_t)ks * c_out + n) * c_in + ci)   // forward weight is [K][c_out][c_in]
+                   : __ldg(w + ((int64_t)ks * c_in + ci) * c_out + n);  // [K][c_in][c_out]
   }
+  if (bf16) reinterpret_cast<__nv_bfloat16*>(img)[i] = __float2bfloat16_rn(v);
+  else img[i] = wimg_value(v, lo);
+}
+
+__global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ img, int K, int c_in, int c_out, int nb,
+                               int n_pad, int transposed, int mirror, int lo, int bf16) {
+  const int64_t total = (int64_t)K * nb * n_pad * (bf16 ? 2 * kKBlock : kKBlock);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    wimg_element(w, img, i, K, c_in, c_out, nb, n_pad, transposed, mirror, lo, bf16);
 }
 
 // Several weight images in one launch (the whole network's, built once per direction by the executor).
 struct WImgItem {
   const float* w;
   float* img;
-  int K, c_in, c_out, nb, n_pad, transposed, mirror, lo, block0;
+  int K, c_in, c_out, nb, n_pad, transposed, mirror, lo, bf16, block0;
 };
 constexpr int kMaxImgBatch = 32;
 struct WImgBatch {
@@ -126,23 +135,10 @@ __global__ void k_weight_images(const __grid_constant__ WImgBatch b) {
   int i = 0;
   while (i + 1 < b.n && (int)blockIdx.x >= b.item[i + 1].block0) ++i;
   const WImgItem& it = b.item[i];
-  const int64_t total = (int64_t)it.K * it.nb * it.n_pad * kKBlock;
+  const int64_t total = (int64_t)it.K * it.nb * it.n_pad * (it.bf16 ? 2 * kKBlock : kKBlock);
   const int nblk = (i + 1 < b.n ? b.item[i + 1].block0 : (int)gridDim.x) - it.block0;
-  for (int64_t e = (int64_t)((int)blockIdx.x - it.block0) * blockDim.x + threadIdx.x; e < total; e += (int64_t)nblk * blockDim.x) {
-    const int e_sw = (int)(e % kKBlock);
-    const int n = (int)((e / kKBlock) % it.n_pad);
-    const int blk = (int)(e / ((int64_t)kKBlock * it.n_pad));
-    const int k = blk / it.nb, j = blk - k * it.nb;
-    const int chunk = (e_sw >> 2) ^ (n & 7);
-    const int ci = j * kKBlock + chunk * 4 + (e_sw & 3);
-    float v = 0.f;
-    if (ci < it.c_in && n < it.c_out) {
-      const int ks = it.mirror ? it.K - 1 - k : k;
-      v = it.transposed ? __ldg(it.w + ((int64_t)ks * it.c_out + n) * it.c_in + ci)
-                        : __ldg(it.w + ((int64_t)ks * it.c_in + ci) * it.c_out + n);
-    }
-    it.img[e] = wimg_value(v, it.lo);
-  }
+  for (int64_t e = (int64_t)((int)blockIdx.x - it.block0) * blockDim.x + threadIdx.x; e < total; e += (int64_t)nblk * blockDim.x)
+    wimg_element(it.w, it.img, e, it.K, it.c_in, it.c_out, it.nb, it.n_pad, it.transposed, it.mirror, it.lo, it.bf16);
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
@@ -292,8 +288,8 @@ k_conv_tc(const __grid_constant__ TcParams p) {
       TRACE(warp, i / S, 0);
       if (!mbar_wait(a_empty(s), (((uint32_t)i / (uint32_t)S) & 1u) ^ 1u, abort_flag)) goto done;
       TRACE(warp, i / S, 1);
-      const bool half = (j == p.nb - 1) && p.last_w == 4;
-      const bool tma = p.use_tma && !half;
+      const int w = (j == p.nb - 1) ? p.last_w : 8;  // 16-byte chunks of this block's rows
+      const bool tma = p.use_tma && w == 8;
       if (lane == 0) {  // this K-block's weight block rides on the same barrier as the gathered rows
         mbar_arrive_expect_tx(a_full(s), (uint32_t)(1 + p.x3) * b_bytes + (tma ? (uint32_t)kStageBytes : 0u));
         bulk_g2s(b_base + (uint32_t)s * b_stage, p.wimg + ((size_t)k * p.nb + j) * p.n_pad * kKBlock, b_bytes, a_full(s));
@@ -310,13 +306,17 @@ k_conv_tc(const __grid_constant__ TcParams p) {
       } else {
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ent + (uint32_t)lane * 16u), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w) : "memory");
         __syncwarp();
+        // (addresses in 4-byte units: a K-block is 128 bytes of a row in both element types; BF16 rows are c_in / 2 units)
+        const uint32_t row_units = p.bf16 ? (uint32_t)p.c_in >> 1 : (uint32_t)p.c_in;
         const float* src0 = p.in + j * kKBlock;
-        if (!half) gather_block<8, false>(stage, ent, p.in, src0, (uint32_t)p.c_in, lane);
-        else       gather_block<4, false>(stage, ent, p.in, src0, (uint32_t)p.c_in, lane);
+        if (w == 8)      gather_block<8, false>(stage, ent, p.in, src0, row_units, lane);
+        else if (w == 4) gather_block<4, false>(stage, ent, p.in, src0, row_units, lane);
+        else if (w == 2) gather_block<2, false>(stage, ent, p.in, src0, row_units, lane);
+        else             gather_block<8, false>(stage, ent, p.in, src0, row_units, lane, w);  // (6: BF16 rows of 48 mod 64 channels)
         if (p.x3) {  // the same rows of the lo plane, behind the hi block
           const float* src1 = p.in_lo + j * kKBlock;
-          if (!half) gather_block<8, false>(stage + kStageBytes, ent, p.in_lo, src1, (uint32_t)p.c_in, lane);
-          else       gather_block<4, false>(stage + kStageBytes, ent, p.in_lo, src1, (uint32_t)p.c_in, lane);
+          if (w == 8) gather_block<8, false>(stage + kStageBytes, ent, p.in_lo, src1, row_units, lane);
+          else        gather_block<4, false>(stage + kStageBytes, ent, p.in_lo, src1, row_units, lane);
         }
         cp_async_arrive(a_full(s));
         __syncwarp();  // the entry row is rewritten by the next item
@@ -380,7 +380,7 @@ k_conv_tc(const __grid_constant__ TcParams p) {
     // (warp-uniform control flow), one elected lane issues.  Issuer m takes the items with i % split == m.
     const int m = warp - (kProducers + 4);
     if (m < split) {
-      const uint32_t idesc = make_idesc_tf32(kTileM, p.n_pad);
+      const uint32_t idesc = p.bf16 ? make_idesc_bf16(kTileM, p.n_pad) : make_idesc_tf32(kTileM, p.n_pad);
       const uint64_t desc0 = make_desc_sw128(0);
       uint32_t n_mine = 0;
       (void)n_mine;
@@ -404,11 +404,18 @@ k_conv_tc(const __grid_constant__ TcParams p) {
           if (elect_one()) {
             const uint64_t a_desc = desc0 + desc_addr(a_base + (uint32_t)s * a_stage);
             const uint64_t b_desc = desc0 + desc_addr(b_base + (uint32_t)s * b_stage);
-            umma_tf32(d_tmem, a_desc, b_desc, idesc, acc);
-            umma_tf32(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);  // +32 bytes per K-step of 8
-            if (ksteps == 4) {
-              umma_tf32(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
-              umma_tf32(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+            if (p.bf16) {  // K-steps of 16 BF16 elements = 32 bytes (1..4 per block)
+              umma_f16(d_tmem, a_desc, b_desc, idesc, acc);
+#pragma unroll
+              for (int q = 1; q < 4; ++q)
+                if (q < ksteps) umma_f16(d_tmem, a_desc + 2 * q, b_desc + 2 * q, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, a_desc, b_desc, idesc, acc);
+              umma_tf32(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);  // +32 bytes per K-step of 8
+              if (ksteps == 4) {
+                umma_tf32(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                umma_tf32(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+              }
             }
             if (p.x3) {  // + lo.Whi + hi.Wlo (the lo blocks sit one block behind the hi ones)
               const uint64_t a_lo = a_desc + (kStageBytes >> 4), b_lo = b_desc + (b_stride >> 4);
@@ -494,8 +501,8 @@ bool mm3d_encode_rows_tmap(CUtensorMap* tm, const float* base, int64_t rows, int
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int tc_geometry(int c_in, int c_out, int K, int* nb, int* n_pad) {
-  *nb = (c_in + 31) / 32;
+static int tc_geometry(int c_in, int c_out, int K, int* nb, int* n_pad, int bf16 = 0) {
+  *nb = bf16 ? (c_in + 63) / 64 : (c_in + 31) / 32;
   *n_pad = (c_out + 15) / 16 * 16;
   // input rows are cut into 128-byte blocks with an optional 64-byte tail
   return (*n_pad <= 256 && (c_in % 16) == 0 && c_in <= 256 && K <= 32) ? 0 : 1;
@@ -566,14 +573,15 @@ int mm3d_conv_tc_build_images(const float* const* weights, float* const* images,
     int blocks = 0;
     for (int i = first; i < n && i < first + kMaxImgBatch; ++i) {
       WImgItem& it = b.item[b.n++];
-      MM3D_REQUIRE(tc_geometry(c_in[i], c_out[i], K[i], &it.nb, &it.n_pad) == 0, MM3D_ERR_UNSUPPORTED,
+      it.bf16 = (flags[i] & MM3D_CONV_BF16) ? 1 : 0;
+      MM3D_REQUIRE(tc_geometry(c_in[i], c_out[i], K[i], &it.nb, &it.n_pad, it.bf16) == 0, MM3D_ERR_UNSUPPORTED,
                    "tcgen05 conv: unsupported shape c_in %d c_out %d K %d", c_in[i], c_out[i], K[i]);
       it.w = weights[i]; it.img = images[i]; it.K = K[i]; it.c_in = c_in[i]; it.c_out = c_out[i];
       it.transposed = (flags[i] & MM3D_CONV_TRANSPOSE_W) ? 1 : 0;
       it.mirror = (flags[i] & MM3D_CONV_MIRROR_K) ? 1 : 0;
       it.lo = (flags[i] & MM3D_CONV_WEIGHT_LO) ? 1 : 0;
       it.block0 = blocks;
-      int nb_blocks = (int)mm3d_cdiv((int64_t)it.K * it.nb * it.n_pad * kKBlock, 256 * 8);
+      int nb_blocks = (int)mm3d_cdiv((int64_t)it.K * it.nb * it.n_pad * (it.bf16 ? 2 * kKBlock : kKBlock), 256 * 8);
       blocks += nb_blocks < 1 ? 1 : nb_blocks;
     }
     if (blocks == 0) continue;
@@ -586,30 +594,34 @@ int mm3d_conv_tc_build_images(const float* const* weights, float* const* images,
 
 int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
                          const float* wimg, int K, const void* plan, int64_t plan_cap, int accumulate, cudaStream_t stream,
-                         const float* wimg_lo = nullptr);
+                         const float* wimg_lo = nullptr, int bf16 = 0);
 
 int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
                      const float* weight, int K, const void* plan, int64_t plan_cap, int flags, void* ws,
                      size_t ws_bytes, cudaStream_t stream) {
   int nb, n_pad;
-  MM3D_REQUIRE(tc_geometry(c_in, c_out, K, &nb, &n_pad) == 0, MM3D_ERR_UNSUPPORTED,
+  const int bf16 = (flags & MM3D_CONV_BF16) ? 1 : 0;
+  MM3D_REQUIRE(tc_geometry(c_in, c_out, K, &nb, &n_pad, bf16) == 0, MM3D_ERR_UNSUPPORTED,
                "tcgen05 conv: unsupported shape c_in %d c_out %d K %d", c_in, c_out, K);
+  MM3D_REQUIRE(!(bf16 && (flags & MM3D_CONV_X3)), MM3D_ERR_INVALID, "tcgen05 conv: BF16 and TF32x3 exclude each other");
   MM3D_REQUIRE(ws && ws_bytes >= mm3d_conv_tc_workspace_bytes(c_in, c_out, K) * ((flags & MM3D_CONV_X3) ? 2 : 1), MM3D_ERR_WORKSPACE,
                "tcgen05 conv: workspace too small");
   const bool tr = (flags & MM3D_CONV_TRANSPOSE_W) != 0, mir = (flags & MM3D_CONV_MIRROR_K) != 0;
   MM3D_REQUIRE(tr || !mir, MM3D_ERR_UNSUPPORTED, "MIRROR_K without TRANSPOSE_W not implemented");
   if (n_out == 0) return MM3D_OK;
   float* wimg = (float*)ws;
-  k_weight_image<<<mm3d_grid((int64_t)K * nb * n_pad * kKBlock, 256), 256, 0, stream>>>(weight, wimg, K, c_in, c_out, nb,
-                                                                                    n_pad, tr ? 1 : 0, mir ? 1 : 0, 0);
+  k_weight_image<<<mm3d_grid((int64_t)K * nb * n_pad * (bf16 ? 2 * kKBlock : kKBlock), 256), 256, 0, stream>>>(
+      weight, wimg, K, c_in, c_out, nb, n_pad, tr ? 1 : 0, mir ? 1 : 0, 0, bf16);
   mm3d_count_launches(1);
+  // BF16 mode: `in` holds an FP32 plane and, n_in * c_in floats behind it, the BF16 plane that is gathered
+  if (bf16) return mm3d_conv_fwd_tc_img(in + n_in * (int64_t)c_in, n_in, c_in, out, n_out, c_out, wimg, K, plan, plan_cap, 0, stream, nullptr, 1);
   if (!(flags & MM3D_CONV_X3)) return mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, wimg, K, plan, plan_cap, 0, stream);
   // Error-compensated mode: `in` holds two planes, hi = tf32(x) and lo = tf32(x - hi) ([n_in, c_in] each), the
   // workspace two weight images; out = hi.Whi + lo.Whi + hi.Wlo, accumulated in FP32 (the dropped lo.Wlo term and the
   // roundings of the lo parts are ~2^-22 relative)
   float* wimg_lo = wimg + mm3d_conv_tc_workspace_bytes(c_in, c_out, K) / sizeof(float);
   k_weight_image<<<mm3d_grid((int64_t)K * nb * n_pad * kKBlock, 256), 256, 0, stream>>>(weight, wimg_lo, K, c_in, c_out, nb,
-                                                                                    n_pad, tr ? 1 : 0, mir ? 1 : 0, 1);
+                                                                                    n_pad, tr ? 1 : 0, mir ? 1 : 0, 1, 0);
   mm3d_count_launches(1);
   return mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, wimg, K, plan, plan_cap, 0, stream, wimg_lo);
 }
@@ -619,9 +631,10 @@ int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_
 // the weights' TF32 remainder, and every item is three products (one launch, one gather of both planes)
 int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
                          const float* wimg, int K, const void* plan, int64_t plan_cap, int accumulate, cudaStream_t stream,
-                         const float* wimg_lo) {
+                         const float* wimg_lo, int bf16) {
   int nb, n_pad;
-  MM3D_REQUIRE(tc_geometry(c_in, c_out, K, &nb, &n_pad) == 0, MM3D_ERR_UNSUPPORTED,
+  MM3D_REQUIRE(!(bf16 && wimg_lo), MM3D_ERR_INVALID, "tcgen05 conv: BF16 and TF32x3 exclude each other");
+  MM3D_REQUIRE(tc_geometry(c_in, c_out, K, &nb, &n_pad, bf16) == 0, MM3D_ERR_UNSUPPORTED,
                "tcgen05 conv: unsupported shape c_in %d c_out %d K %d", c_in, c_out, K);
   MM3D_REQUIRE(n_out < (1ll << 31) && n_in * (int64_t)c_in < (1ll << 32), MM3D_ERR_UNSUPPORTED,
                "tcgen05 conv: tensor too large for 32-bit element offsets");
@@ -634,7 +647,9 @@ int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, in
   p.in = in; p.out = out; p.wimg = wimg;
   p.perm = pv.perm; p.tile_mask = pv.tile_mask; p.order = pv.order; p.tbl = pv.tbl; p.tstride = pv.stride;
   p.c_in = c_in; p.c_out = c_out; p.K = K; p.nb = nb;
-  p.last_w = (c_in % 32) == 16 ? 4 : 8;
+  // chunks of an offset's last block: TF32 rows are whole 64-byte pieces, BF16 rows whole 32-byte pieces
+  p.last_w = bf16 ? ((c_in % 64) ? (c_in % 64) / 8 : 8) : ((c_in % 32) == 16 ? 4 : 8);
+  p.bf16 = bf16;
   p.n_pad = n_pad;
   p.num_tiles = (int)mm3d_cdiv(n_out, kTileM);
   p.err = mm3d_device_err_flag();
@@ -653,7 +668,7 @@ int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, in
   // for 64+ input channels and slower for 32 (the TMA unit takes ~4 cycles per 128-byte row and is shared by the SM's
   // CTAs), 1 % slower over the whole step -- kept selectable for that comparison.
   static const bool want_tma = [] { const char* e = getenv("MM3D_TC_GATHER"); return e && strcmp(e, "tma") == 0; }();
-  if (want_tma && !wimg_lo && n_in > 0 && n_in < (1ll << 31) - 1) {
+  if (want_tma && !wimg_lo && !bf16 && n_in > 0 && n_in < (1ll << 31) - 1) {
     p.use_tma = mm3d_encode_rows_tmap(&p.tmap, in, n_in, c_in, /*atom32=*/false) ? 1 : 0;
   }
   const uint32_t b_stride = ((uint32_t)n_pad * 128u + 1023u) & ~1023u;

@@ -86,6 +86,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with BF16 operands (kind::f16, K = 16 elements = 32 bytes per instruction, FP32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src), "r"(bytes), "r"(bar)
@@ -125,9 +135,10 @@ __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
 // [0, W) of input row ent[r] starting at `src0` (or zeros when ent[r] < 0).  W = 8: 8 lanes per row, 4 rows per
 // pass; W = 4: 4 lanes per row, 8 rows per pass (chunks 4..7 of the stage are then never read).  Entries are
 // read eight passes at a time so that their shared-memory latency is paid once per batch, not once per row.
+// wvalid < W: only the first wvalid chunks of a row exist (the rest of the stage row is zero-filled).
 template <int W, bool BASE32>
 __device__ __forceinline__ void gather_block(uint32_t stage, uint32_t ent, const float* __restrict__ base,
-                                             const float* __restrict__ src0, uint32_t row_floats, int lane) {
+                                             const float* __restrict__ src0, uint32_t row_floats, int lane, int wvalid = W) {
   constexpr int kLanesPerRow = W, kRowsPerPass = 32 / W, kBatch = 8;
   const int c = lane & (kLanesPerRow - 1), rsub = lane / kLanesPerRow;
   const float* srcc = src0 + c * 4;
@@ -142,7 +153,7 @@ __device__ __forceinline__ void gather_block(uint32_t stage, uint32_t ent, const
       const int r = r0 + u * kRowsPerPass + rsub;
       const uint32_t off = BASE32 ? (uint32_t)((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4)) : (uint32_t)((c ^ (r & 7)) << 4);
       // (absent rows read nothing: the address of row 0 only has to be valid)
-      cp_async16_zfill(stage + (uint32_t)r * 128u + off, srcc + (size_t)(uint32_t)max(rows[u], 0) * row_floats, rows[u] < 0);
+      cp_async16_zfill(stage + (uint32_t)r * 128u + off, srcc + (size_t)(uint32_t)max(rows[u], 0) * row_floats, rows[u] < 0 || c >= wvalid);
     }
   }
 }
@@ -192,6 +203,12 @@ __device__ __forceinline__ uint32_t swz_base32(int c, int r) {
 // a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
 __device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n, int a_mn_major = 0, int b_mn_major = 0) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// A = B = BF16 (kind::f16 formats: 0 = F16, 1 = BF16), D = F32
+__device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n, int a_mn_major = 0, int b_mn_major = 0) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 

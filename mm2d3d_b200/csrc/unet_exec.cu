@@ -16,6 +16,7 @@
 // Parameter pointers come in the module tree's order (Appendix B of SURVEY.md):
 //   stem.w | per level: pre_bn{gamma,beta,rmean,rvar} pre.w [dn_bn{4} dn.w <deeper level> up_bn{4}
 //   up.w post_bn{4} post.w] | head_bn{4}
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include <cstring>
@@ -41,7 +42,7 @@ int mm3d_conv_tc_build_images(const float* const* weights, float* const* images,
                               const int* c_out, const int* flags, int n, cudaStream_t stream);
 int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
                          const float* wimg, int K, const void* plan, int64_t plan_cap, int accumulate, cudaStream_t stream,
-                         const float* wimg_lo = nullptr);
+                         const float* wimg_lo = nullptr, int bf16 = 0);
 
 namespace {
 
@@ -83,7 +84,13 @@ struct Net {
   int64_t n_points;
   int planes(int l) const { return m * (l + 1); }
   // TF32x3 mode: every tensor a convolution gathers carries a hi and a lo plane ([rows, c] floats each)
-  int pl() const { return mode == MM3D_MODE_TF32X3 ? 2 : 1; }
+  // BF16 mode: an FP32 plane (TF32-rounded: the weight-gradient operand) and a BF16 plane behind it (what forward and
+  // dgrad gather; it only fills the first half of its plane)
+  int pl() const { return (mode == MM3D_MODE_TF32X3 || mode == MM3D_MODE_BF16) ? 2 : 1; }
+  // how a producer stores a tensor that a convolution gathers (bnrelu.cu store_planes / k_pad_cols)
+  int rmode() const { return mode == MM3D_MODE_TF32X3 ? 2 : mode == MM3D_MODE_BF16 ? 3 : mode == MM3D_MODE_TF32 ? 1 : 0; }
+  bool x3() const { return mode == MM3D_MODE_TF32X3; }
+  bool bf16() const { return mode == MM3D_MODE_BF16; }
 };
 
 // the same carving in forward, backward and the size query
@@ -172,6 +179,7 @@ __global__ void k_pad_cols(const float* __restrict__ src, int64_t n, int c_src, 
     if (round_tf32) {
       const float hi = mm3d_rna_tf32(v);
       if (round_tf32 == 2) dst[total + i] = mm3d_rna_tf32(v - hi);  // lo plane (TF32x3 mode)
+      if (round_tf32 == 3) reinterpret_cast<__nv_bfloat16*>(dst + total)[i] = __float2bfloat16_rn(v);  // BF16 plane
       v = hi;
     }
     dst[i] = v;
@@ -301,7 +309,7 @@ void bn_fwd(Ctx& c, int pidx, const float* x, float* y, int64_t n, int ch, float
   if (abl_skip("bn")) return;
   EX(mm3d_bnrelu_fwd_impl(x, x_hi, c_lo, y, n, ch, P(c, pidx), P(c, pidx + 1), (float*)c.params[pidx + 2], (float*)c.params[pidx + 3],
                           save, save + ch, c.eps, c.momentum, 0.f, c.training, c.bn_ws, c.bn_ws_bytes, true,
-                          tc_mode(c) && to_conv ? c.net->pl() : 0, c.stream));
+                          tc_mode(c) && to_conv ? c.net->rmode() : 0, c.stream));
 }
 // round: bit 0 = dx (its low column block when split) feeds a convolution as d_out, bit 1 = dx_hi does
 // add (rows add_ld floats apart): another gradient of the same tensor, summed into dx before it is stored
@@ -310,7 +318,7 @@ void bn_bwd(Ctx& c, int pidx, const float* x, const float* dy, float* dx, int64_
             int64_t add_ld = 0) {
   if (abl_skip("bn")) return;
   EX(mm3d_bnrelu_bwd_impl(x, x_hi, c_lo, dy, dx, dx_hi, n, ch, P(c, pidx), P(c, pidx + 1), save, save + ch, Gp(c, pidx), Gp(c, pidx + 1), 0.f,
-                          c.training, c.bn_ws, c.bn_ws_bytes, true, tc_mode(c) ? (round | (c.net->pl() == 2 ? 4 : 0)) : 0, add, add_ld,
+                          c.training, c.bn_ws, c.bn_ws_bytes, true, tc_mode(c) ? (round | (c.net->x3() ? 4 : c.net->bf16() ? 8 : 0)) : 0, add, add_ld,
                           c.stream));
 }
 enum Kind { SMC, DOWN, UP };
@@ -329,8 +337,10 @@ const float* find_img_lo(const Ctx& c, const float* w) {
 // carries the lo plane n_in * c_in floats behind the hi one, both planes are gathered into every ring stage).
 int conv_img(const Ctx& c, const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out, const float* im,
              const float* im_lo, int K, const void* plan, int64_t plan_cap) {
-  if (c.net->pl() == 2 && !im_lo) { mm3d_set_error("tf32x3: missing lo weight image"); return MM3D_ERR_INVALID; }
-  return mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, im, K, plan, plan_cap, 0, c.stream, c.net->pl() == 2 ? im_lo : nullptr);
+  if (c.net->x3() && !im_lo) { mm3d_set_error("tf32x3: missing lo weight image"); return MM3D_ERR_INVALID; }
+  if (c.net->bf16())  // the BF16 plane sits n_in * c_in floats behind the FP32 one
+    return mm3d_conv_fwd_tc_img(in + n_in * (int64_t)c_in, n_in, c_in, out, n_out, c_out, im, K, plan, plan_cap, 0, c.stream, nullptr, 1);
+  return mm3d_conv_fwd_tc_img(in, n_in, c_in, out, n_out, c_out, im, K, plan, plan_cap, 0, c.stream, c.net->x3() ? im_lo : nullptr);
 }
 // forward of layer type `kind` whose FINE level is l
 void conv_fwd(Ctx& c, Kind kind, int l, const float* in, int c_in, float* out, int c_out, const float* w) {
@@ -470,7 +480,7 @@ int build_images(Ctx& c, bool backward, const float* w_stem) {
     w.push_back(x.pidx == 0 ? w_stem : (const float*)c.params[x.pidx]);
     img.push_back((float*)at);
     K.push_back(x.K); ci.push_back(a); co.push_back(b);
-    fl.push_back(backward ? (MM3D_CONV_TRANSPOSE_W | (x.smc ? MM3D_CONV_MIRROR_K : 0)) : 0);
+    fl.push_back((backward ? (MM3D_CONV_TRANSPOSE_W | (x.smc ? MM3D_CONV_MIRROR_K : 0)) : 0) | (net.bf16() ? MM3D_CONV_BF16 : 0));
     at += bytes;
   }
   int rc = mm3d_conv_tc_build_images(w.data(), img.data(), K.data(), ci.data(), co.data(), fl.data(), (int)w.size(), c.stream);
@@ -478,7 +488,7 @@ int build_images(Ctx& c, bool backward, const float* w_stem) {
   c.img_key.assign(w.begin(), w.end());
   c.img_val.assign(img.begin(), img.end());
   c.img_lo.clear();
-  if (net.pl() == 2) {  // the images of the weights' TF32 remainders, behind the hi images
+  if (net.x3()) {  // the images of the weights' TF32 remainders, behind the hi images
     std::vector<float*> lo;
     for (size_t i = 0; i < w.size(); ++i) {
       const size_t bytes = mm3d_align(mm3d_conv_tc_workspace_bytes(ci[i], co[i], K[i]));
@@ -556,7 +566,7 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
     MARK("smc_dgrad post", l);
     const bool split = (p & 3) == 0 && c.training;  // as in the forward: [Y | F] was never concatenated
     float* d_J = g.f(n, split ? p : 2 * p);         // split: only the skip half d_J[:, :p]
-    const int pl = net.pl();  // conv d_out tensors carry a lo plane in TF32x3 mode
+    const int pl = net.pl();  // conv d_out tensors carry a second plane in the TF32x3 and BF16 modes
     float* d_F = g.f(n, (int64_t)p * pl);
     float* d_Yskip = g.f(n, (int64_t)p * pl);
     if (split) {
@@ -568,7 +578,7 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
       if (n && !c.rc) {
         if (mm3d_launch_pdl(k_copy_cols, dim3(mm3d_grid(n * p / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)d_J, n, 2 * p, d_F, p, 0, p, p) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
         mm3d_count_launches(1);
-        if (tc_mode(c)) launch_pad_cols(c, d_F, n, p, d_F, p, pl);  // round in place (+ lo plane): d_F is the deconvolution's d_out
+        if (tc_mode(c)) launch_pad_cols(c, d_F, n, p, d_F, p, net.rmode());  // round in place (+ second plane): d_F is the deconvolution's d_out
       }
     }
     float* d_E = g.f(nc, q);
@@ -599,7 +609,7 @@ void level_bwd(Ctx& c, Bump& g, int l, int pbase, const float* d_R, float* d_X) 
 
 int fill_net(Net& net, int in_channels, int m, int num_planes, int mode, const int64_t* level_desc, int64_t n_points) {
   MM3D_REQUIRE(num_planes >= 1 && num_planes <= 16 && m > 0 && in_channels > 0, MM3D_ERR_INVALID, "bad network shape");
-  MM3D_REQUIRE(mode == MM3D_MODE_FP32 || mode == MM3D_MODE_TF32 || mode == MM3D_MODE_TF32X3, MM3D_ERR_UNSUPPORTED,
+  MM3D_REQUIRE(mode == MM3D_MODE_FP32 || mode == MM3D_MODE_TF32 || mode == MM3D_MODE_TF32X3 || mode == MM3D_MODE_BF16, MM3D_ERR_UNSUPPORTED,
                "conv mode %d not implemented in this build", mode);
   net.L = num_planes; net.m = m; net.cin = in_channels; net.mode = mode; net.n_points = n_points;
   // tensor-core kernels gather rows in 64-byte pieces: pad the stem input to a multiple of 16 channels
@@ -710,7 +720,7 @@ MM3D_API int mm3d_unet_forward(int in_channels, int m, int num_planes, int mode,
   MARK("input_fwd", -1);
   const float* w_stem = P(c, 0);
   if (net.Vp != net.V)  // pad the stem input to whole 64-byte pieces; rounded to TF32 (+ lo plane in TF32x3 mode)
-    launch_pad_cols(c, net.V, n0, net.cin, net.Vp, net.cin_k, net.pl());
+    launch_pad_cols(c, net.V, n0, net.cin, net.Vp, net.cin_k, net.rmode());
   else if (tc_mode(c) && n0 > 0 && !c.rc) {
     // (stem input already a whole number of 64-byte pieces: round the InputLayer output in place)
     if (mm3d_launch_pdl(k_round_tf32, dim3(mm3d_grid(n0 * net.cin / 4 + 1, 256)), dim3(256), 0, c.stream, (const float*)net.V, net.V, n0 * (int64_t)net.cin) != cudaSuccess) c.rc = MM3D_ERR_CUDA;
@@ -855,6 +865,17 @@ MM3D_API void mm3d_debug_dump_marks(void) {
   }
 }
 #endif
+
+// out[0..n) = tf32(in) as float32; behind it, at float index n, bf16(in) as n BF16 elements: the operand planes of
+// MM3D_MODE_BF16 (`out` holds 2 n floats like the TF32x3 planes; the BF16 plane fills the first half of the second one)
+MM3D_API int mm3d_split_bf16(const float* in, float* out, int64_t n, mm3d_stream_t stream_) {
+  MM3D_REQUIRE(n >= 0 && (n == 0 || (in && out)), MM3D_ERR_INVALID, "split_bf16: bad arguments");
+  if (n == 0) return MM3D_OK;
+  MM3D_CUDA(mm3d_launch_pdl(k_pad_cols, dim3(mm3d_grid(n, 256)), dim3(256), 0, (cudaStream_t)stream_, in, n, 1, out, 1, 3));
+  mm3d_count_launches(1);
+  MM3D_CHECK_LAUNCH("mm3d_split_bf16");
+  return MM3D_OK;
+}
 
 // out[0..n) = tf32(in), out[n..2n) = tf32(in - tf32(in)): the operand planes of MM3D_MODE_TF32X3
 MM3D_API int mm3d_split_tf32(const float* in, float* out, int64_t n, mm3d_stream_t stream_) {

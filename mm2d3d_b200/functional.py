@@ -144,13 +144,18 @@ def _tf32(t: torch.Tensor, inplace: bool = False) -> torch.Tensor:
     return out
 
 
-def _planes(t: torch.Tensor) -> torch.Tensor:
-    """[2, n, c]: hi = tf32(t) and lo = tf32(t - hi), the operand planes of the error-compensated "tf32x3" mode."""
+def _planes(t: torch.Tensor, bf16: bool = False) -> torch.Tensor:
+    """[2, n, c]: hi = tf32(t) and lo = tf32(t - hi), the operand planes of the error-compensated "tf32x3" mode.
+    ``bf16``: the planes of the "bf16" mode instead -- tf32(t) as float32, then bf16(t) (n * c bfloat16 values at the
+    start of the second plane)."""
     t = t.contiguous()
     out = torch.empty((2,) + tuple(t.shape), dtype=torch.float32, device=t.device)
     if t.numel():
         with torch.cuda.device(t.device):
-            check(lib.mm3d_split_tf32(ptr(t), ptr(out), t.numel(), _lib.stream_ptr()), "mm3d_split_tf32")
+            if bf16:
+                check(lib.mm3d_split_bf16(ptr(t), ptr(out), t.numel(), _lib.stream_ptr()), "mm3d_split_bf16")
+            else:
+                check(lib.mm3d_split_tf32(ptr(t), ptr(out), t.numel(), _lib.stream_ptr()), "mm3d_split_tf32")
     return out
 
 
@@ -162,7 +167,7 @@ class TableConvFn(torch.autograd.Function):
         x, w = _f32c(x), _f32c(weight)
         K, c_in, c_out = w.shape[0], w.shape[-2], w.shape[-1]
         m = MODES[mode]
-        if m == _lib.MODE_TF32X3 and c_out % 16:
+        if m in (_lib.MODE_TF32X3, _lib.MODE_BF16) and c_out % 16:
             m = _lib.MODE_FP32  # (dgrad / wgrad of such a layer have no tensor-core path; no layer of the network is one)
         fwd_t, bwd_t, bwd_flags = conv_tables(meta, kind, spatial_in, plans=m != _lib.MODE_FP32)
         if x.shape[0] != fwd_t.n_in or x.shape[1] != c_in or K != fwd_t.K:
@@ -178,8 +183,8 @@ class TableConvFn(torch.autograd.Function):
             w = torch.nn.functional.pad(w, (0, 0, 0, pad))
             c_in += pad
         ctx.pad = pad
-        if m == _lib.MODE_TF32X3:
-            x = _planes(x)  # hi and lo planes (saved: wgrad reads the same operand)
+        if m in (_lib.MODE_TF32X3, _lib.MODE_BF16):
+            x = _planes(x, m == _lib.MODE_BF16)  # two planes (saved: wgrad reads the same operand)
         elif m != _lib.MODE_FP32:
             x = _tf32(x, inplace=bool(pad))  # (the saved x is the rounded one: wgrad reads the same operand)
         out = torch.empty(fwd_t.n_out, c_out, dtype=torch.float32, device=x.device)
@@ -201,8 +206,8 @@ class TableConvFn(torch.autograd.Function):
         d_out = _f32c(d_out)
         K, c_in, c_out = w.shape[0], w.shape[-2], w.shape[-1]
         m = ctx.mode
-        if m == _lib.MODE_TF32X3:
-            d_out = _planes(d_out)
+        if m in (_lib.MODE_TF32X3, _lib.MODE_BF16):
+            d_out = _planes(d_out, m == _lib.MODE_BF16)
         elif m != _lib.MODE_FP32:
             d_out = _tf32(d_out)
         d_x = d_w = None

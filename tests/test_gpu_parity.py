@@ -243,7 +243,7 @@ def _no_device_error():
     assert _lib.lib.mm3d_take_device_error() == 0, "a kernel reported a pipeline time-out"
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32", "tf32x3"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "tf32x3", "bf16"])
 @pytest.mark.parametrize("kind", ["smc", "down", "up"])
 def test_conv_fwd_bwd(kind, mode):
     from mm2d3d_b200 import functional as F
@@ -640,7 +640,7 @@ def test_tf32_matches_fp32_kernels_at_bench_size(kind, c_in, c_out):
     _no_device_error()
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32", "tf32x3"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "tf32x3", "bf16"])
 def test_fused_executor_matches_module_path(mode):
     """UNetSCN.forward defaults to the native whole-network executor (csrc/unet_exec.cu); it issues
     the same kernels as the module-by-module path, so outputs, every gradient and the BN running
@@ -667,7 +667,8 @@ def test_fused_executor_matches_module_path(mode):
     finally:
         scn.set_conv_mode("fp32")
     _no_device_error()
-    tol = 1e-3 if mode == "tf32" else 1e-5
+    # (a last-bit difference of an FP32 value can move its TF32 / BF16 rounding by a whole unit of that format)
+    tol = {"tf32": 1e-3, "bf16": 1e-2}.get(mode, 1e-5)
     assert rel_err(res[0][0], res[1][0]) < tol
     for a, b in zip(res[0][1], res[1][1]):
         assert rel_l2(a, b) < 2e-2  # same kernels; atomic reduction order noise, amplified by the deep BN/ReLU net
@@ -887,7 +888,7 @@ def _freeze_gates(net, records, device, dtype, tensor_cls):
         m.forward = types.MethodType(fwd, m)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32", "tf32x3"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "tf32x3", "bf16"])
 def test_unetscn_gradients_with_frozen_gates(mode):
     """north_star's tolerance on whole-network GRADIENTS, stated per tensor and held directly: 1e-4 (FP32 mode) /
     1e-2 (TF32 mode), relative L2 AND max-abs-relative, against the FP64 oracle.
@@ -951,7 +952,10 @@ def test_unetscn_gradients_with_frozen_gates(mode):
     finally:
         scn.set_conv_mode("fp32")
     _no_device_error()
-    tol = TOL[mode]
+    # BF16 operands carry 8 mantissa bits (unit round-off 2^-9, four times TF32's 2^-11): the per-op bar of 1e-2 holds
+    # (test_conv_fwd_bwd); over the 27-convolution chain the achieved whole-network figures are printed (B200, this
+    # input: forward 1.0e-2, gradients rel-L2 <= 2.4e-2, max-abs-rel <= 3.2e-2) and held to 5e-2
+    tol = 5e-2 if mode == "bf16" else TOL[mode]
     e_out = rel_err(out, out64)
     assert e_out < tol, ("forward", e_out)
     rows, worst = [], (0.0, 0.0, "")
