@@ -57,6 +57,7 @@ struct WgParams {
   int S, gbufs;
   int num_tiles, tmem_cols;
   int n_local;      // tiles per CTA (upper bound: every group gets at least ceil(num_tiles / n_local) CTAs)
+  int max_items;    // two-ring variant: capacity of one ring's item list
   int groups;       // offset groups; group g owns the offsets of gmask[g]; its CTAs are decided in the kernel
   uint32_t gmask[32];
   int* err;
@@ -416,6 +417,378 @@ done:
   }
 }
 
+
+// ---- narrow layers: two rings -----------------------------------------------------------------------------------
+// For items of one 32-channel block (c_in <= 32) the kernel above is bound by per-item latencies, not by data: its
+// single issuer needs ~650 cycles for the 16 small MMAs of an item and its 8 cooperating producer warps ~1100 cycles
+// per item (exposed table-entry latency, a 256-arrival barrier) -- measured with clock64 stamps.  This variant runs
+// TWO independent rings inside the CTA, each with its own MMA issuer warp: the offsets of the CTA's group are dealt to
+// the rings by their tile counts (so every accumulator keeps a single writer), ring m owns the stages s with
+// s % 2 == m, and every producer warp OWNS one stage and fills whole items alone (32 arrivals, the next item's
+// entries in flight while the current one is copied).  One more warp loads the dout tiles, which both rings share.
+//
+// Warp roles (14 warps): 0..5 item producers (warp w = stage w, ring w & 1), 6 dout-tile loader, 7 idle,
+// 8..11 epilogue (TMEM -> red.add at the end), 12 / 13 MMA issuers of ring 0 / 1 (12 also allocates TMEM).
+constexpr int kRingStages = 6;
+constexpr int kRingThreads = 14 * 32;
+constexpr int kRingEntBytes = kTileM * 4;
+
+__global__ void __launch_bounds__(kRingThreads, 1)
+k_wgrad_tc_rings(const WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int S = p.S, R = p.S / 2;  // 6 stages (4 when an item has two channel blocks)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t a_bytes = (uint32_t)p.nbi * kBlockBytes;
+  const uint32_t g_bytes = (uint32_t)p.gblocks * kBlockBytes;
+  const uint32_t a_base = smem_base;
+  const uint32_t g_base = a_base + (uint32_t)S * a_bytes;  // (the block past the last stage is the first dout buffer: see above)
+  const uint32_t e_base = g_base + (uint32_t)p.gbufs * g_bytes;       // entry rows of warps 0..6
+  const uint32_t m_base = e_base + 7u * kRingEntBytes;                 // [n_local] masks, [n_local] tiles
+  const uint32_t f_base = m_base + (uint32_t)p.n_local * 8u;           // [2][n_local + 1] first item of a tile, per ring
+  const uint32_t i_base = f_base + (uint32_t)(p.n_local + 1) * 8u;     // [2][max_items] items (tile << 5 | offset), 16 bits
+  const uint32_t bar_base = (i_base + (uint32_t)p.max_items * 4u + 15u) & ~15u;
+  uint32_t* cmask = reinterpret_cast<uint32_t*>(smem + (m_base - smem_base));
+  uint32_t* ctile = cmask + p.n_local;
+  uint32_t* first = reinterpret_cast<uint32_t*>(smem + (f_base - smem_base));
+  uint16_t* items = reinterpret_cast<uint16_t*>(smem + (i_base - smem_base));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (bar_base - smem_base));
+  auto a_full = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (uint32_t)(kMaxStages + s); };
+  auto g_full = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + s); };
+  auto g_empty = [&](int s) { return bar_base + 8u * (uint32_t)(2 * kMaxStages + kMaxGBufs + s); };
+  const uint32_t acc_full = bar_base + 8u * (uint32_t)(2 * kMaxStages + 2 * kMaxGBufs);
+  constexpr int kNumBars = 2 * kMaxStages + 2 * kMaxGBufs + 1;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bars + kNumBars);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + kNumBars + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  mm3d_griddep_launch();
+  mm3d_griddep_wait();
+#ifdef MM3D_TRACE
+  if (p.trace && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[4096 + 2 * blockIdx.x] = (long long)gt;
+  }
+#endif
+  // ---- CTAs -> offset groups (as in k_wgrad_tc) and the group's offsets -> rings, both from the plan's per-offset
+  // tile counts; every CTA computes the same tables
+  __shared__ int s_cta0[33];
+  __shared__ uint32_t s_ring1[32];  // per group: the offsets of ring 1
+  __shared__ int s_byrank[32];
+  __shared__ uint32_t s_cnt[32];
+  __shared__ int s_ne;
+  if (warp == 0) {
+    const int nctas = (int)gridDim.x;
+    // lane k: tile count of offset k (one load), and its rank by descending count (ties: lower offset first)
+    const uint32_t cnt = lane < p.K ? __ldg(p.off_tiles + lane) : 0u;
+    int rank = 0;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+      const uint32_t oc = __shfl_sync(0xffffffffu, cnt, o);
+      if (o < p.K && (oc > cnt || (oc == cnt && o < lane))) ++rank;
+    }
+    if (lane < p.K) {
+      s_byrank[rank] = lane;
+      s_cnt[lane] = cnt;
+    }
+    __syncwarp();
+    float cost = 0.f;
+    if (lane < p.groups) {
+      // this group's offsets by descending tile count, each to the lighter ring
+      uint32_t sum = 0, mx = 0, r1 = 0, w0 = 0, w1 = 0;
+      const uint32_t gm = p.gmask[lane];
+      for (int r = 0; r < p.K; ++r) {
+        const int k = s_byrank[r];
+        if (!((gm >> k) & 1u)) continue;
+        const uint32_t c = s_cnt[k];
+        sum += c;
+        mx = max(mx, c);
+        if (w1 <= w0) { r1 |= 1u << k; w1 += c + 1; } else w0 += c + 1;
+      }
+      cost = (float)((uint32_t)p.nbi * sum + (uint32_t)p.gblocks * mx) + 1.f;
+      s_ring1[lane] = r1;
+    }
+    float total = cost;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    const int min_ct = (p.num_tiles + p.n_local - 1) / p.n_local;
+    int ct = 0;
+    if (lane < p.groups) ct = max(min_ct, min(p.num_tiles, (int)((float)nctas * cost / total)));
+    int used = ct;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) used += __shfl_xor_sync(0xffffffffu, used, o);
+    for (int guard = 0; used != nctas && guard < 4 * 148; ++guard) {
+      const bool add = used < nctas;
+      float load = -1.f;
+      if (lane < p.groups && (add ? ct < p.num_tiles : ct > min_ct)) load = add ? cost / (float)ct : (float)ct / cost;
+      float best = load;
+      int who = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+        if (ob > best || (ob == best && ow < who)) { best = ob; who = ow; }
+      }
+      if (best < 0.f) break;
+      if (lane == who) ct += add ? 1 : -1;
+      used += add ? 1 : -1;
+    }
+    int incl = ct;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int x = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += x;
+    }
+    s_cta0[lane + 1] = incl;
+    if (lane == 0) s_cta0[0] = 0;
+  }
+  __syncthreads();
+  int grp = 0;
+  while (grp + 1 < p.groups && (int)blockIdx.x >= s_cta0[grp + 1]) ++grp;
+  const uint32_t gmask = p.gmask[grp], ring1 = s_ring1[grp];
+  const int split = (int)blockIdx.x - s_cta0[grp], splits = s_cta0[grp + 1] - s_cta0[grp];
+  if (split >= splits) return;
+
+  int n_local = p.n_local;
+  while (n_local > 0 && mm3d_plan_local_tile(p.order, p.num_tiles, splits, split, n_local - 1) < 0) --n_local;
+  for (int i = threadIdx.x; i < n_local; i += blockDim.x) {
+    const int t = mm3d_plan_local_tile(p.order, p.num_tiles, splits, split, i);
+    cmask[i] = __ldg(p.tile_mask + t) & gmask;
+    ctile[i] = (uint32_t)t;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(a_full(s), 32);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < kMaxGBufs; ++s) {
+      mbar_init(g_full(s), 32);
+      mbar_init(g_empty(s), 2);  // both issuers are done with the tile
+    }
+    mbar_init(acc_full, 2);
+    *abort_flag = 0;
+    fence_barrier_init();
+  }
+  if (warp == 12) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
+  __syncthreads();
+  if (warp == 0) {
+    // tiles without an offset of this group drop out (in place: a chunk is read before anything of it is rewritten) ...
+    int base = 0;
+    for (int b0 = 0; b0 < n_local; b0 += 32) {
+      const int i = b0 + lane;
+      const uint32_t m = i < n_local ? cmask[i] : 0u, t = i < n_local ? ctile[i] : 0u;
+      const uint32_t bal = __ballot_sync(0xffffffffu, m != 0u);
+      __syncwarp();
+      if (m) {
+        const int pos = base + __popc(bal & ((1u << lane) - 1u));
+        cmask[pos] = m;
+        ctile[pos] = t;
+      }
+      base += __popc(bal);
+      __syncwarp();
+    }
+    const int ne = base;
+    if (lane == 0) s_ne = ne;
+    // ... and each ring's first item of every remaining tile (exclusive scans of the per-tile item counts)
+    uint32_t run0 = 0, run1 = 0;
+    for (int b0 = 0; b0 < ne; b0 += 32) {
+      const int i = b0 + lane;
+      const uint32_t m = i < ne ? cmask[i] : 0u;
+      const uint32_t c0 = (uint32_t)__popc(m & ~ring1), c1 = (uint32_t)__popc(m & ring1);
+      uint32_t i0 = c0, i1 = c1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x0 = __shfl_up_sync(0xffffffffu, i0, o), x1 = __shfl_up_sync(0xffffffffu, i1, o);
+        if (lane >= o) { i0 += x0; i1 += x1; }
+      }
+      if (i < ne) {
+        first[i] = run0 + i0 - c0;
+        first[p.n_local + 1 + i] = run1 + i1 - c1;
+      }
+      run0 += __shfl_sync(0xffffffffu, i0, 31);
+      run1 += __shfl_sync(0xffffffffu, i1, 31);
+    }
+    if (lane == 0) {
+      first[ne] = run0;
+      first[p.n_local + 1 + ne] = run1;
+    }
+  }
+  __syncthreads();
+  const int ne = s_ne;
+  for (int t = threadIdx.x; t < ne; t += blockDim.x) {
+    const uint32_t m = cmask[t];
+    uint32_t at0 = first[t], at1 = (uint32_t)p.max_items + first[p.n_local + 1 + t];
+    for (uint32_t rem = m & ~ring1; rem; rem &= rem - 1) items[at0++] = (uint16_t)(((uint32_t)t << 5) | (uint32_t)(__ffs(rem) - 1));
+    for (uint32_t rem = m & ring1; rem; rem &= rem - 1) items[at1++] = (uint16_t)(((uint32_t)t << 5) | (uint32_t)(__ffs(rem) - 1));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < S) {
+    // =================================================================== item producers: warp w owns stage w
+    const int m = warp & 1, q = warp >> 1;
+    const uint16_t* list = items + (size_t)m * p.max_items;
+    const int n_items = (int)first[m * (p.n_local + 1) + ne];
+    const uint32_t ent = e_base + (uint32_t)warp * kRingEntBytes;
+    const uint32_t stage = a_base + (uint32_t)warp * a_bytes;
+    int e[4] = {-1, -1, -1, -1};  // table entries of rows lane, 32 + lane, 64 + lane, 96 + lane of the current item
+    int i = q;
+    if (i < n_items) {
+      const uint32_t it = list[i];
+      const int32_t* src = p.tbl + (int64_t)(it & 31u) * p.tstride + (int64_t)ctile[it >> 5] * kTileM + lane;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) e[r] = __ldg(src + 32 * r);
+    }
+    for (uint32_t use = 0; i < n_items; i += R, ++use) {
+      int en[4] = {-1, -1, -1, -1};  // the next item's entries are in flight while this one is copied
+      if (i + R < n_items) {
+        const uint32_t it = list[i + R];
+        const int32_t* src = p.tbl + (int64_t)(it & 31u) * p.tstride + (int64_t)ctile[it >> 5] * kTileM + lane;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) en[r] = __ldg(src + 32 * r);
+      }
+      TRACE(warp, use, 0);
+      if (!mbar_wait(a_empty(warp), (use & 1u) ^ 1u, abort_flag)) goto done;
+      TRACE(warp, use, 1);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ent + (uint32_t)(32 * r + lane) * 4u), "r"(e[r]) : "memory");
+      __syncwarp();
+      for (int jb = 0; jb < p.nbi; ++jb) {
+        if (jb == p.nbi - 1 && p.last_w == 4) gather_block<4, true>(stage + (uint32_t)jb * kBlockBytes, ent, p.in, p.in + jb * 32, (uint32_t)p.c_in, lane);
+        else gather_block<8, true>(stage + (uint32_t)jb * kBlockBytes, ent, p.in, p.in + jb * 32, (uint32_t)p.c_in, lane);
+      }
+      cp_async_arrive(a_full(warp));
+      __syncwarp();  // the entry row is rewritten by the next item
+      TRACE(warp, use, 2);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) e[r] = en[r];
+    }
+  } else if (warp == 6) {
+    // =================================================================== dout tiles, shared by both rings
+    const uint32_t ent = e_base + 6u * kRingEntBytes;
+    int e[4] = {-1, -1, -1, -1};
+    if (ne > 0) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) e[r] = __ldg(p.perm + (int64_t)ctile[0] * kTileM + 32 * r + lane);
+    }
+    for (int t = 0; t < ne; ++t) {
+      int en[4] = {-1, -1, -1, -1};
+      if (t + 1 < ne) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) en[r] = __ldg(p.perm + (int64_t)ctile[t + 1] * kTileM + 32 * r + lane);
+      }
+      const int buf = t % p.gbufs;
+      if (!mbar_wait(g_empty(buf), (((uint32_t)t / (uint32_t)p.gbufs) & 1u) ^ 1u, abort_flag)) goto done;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ent + (uint32_t)(32 * r + lane) * 4u), "r"(e[r]) : "memory");
+      __syncwarp();
+      const uint32_t gb = g_base + (uint32_t)buf * g_bytes;
+      for (int jb = 0; jb < p.gblocks; ++jb) {
+        if (jb == p.gblocks - 1 && p.g_last_w == 4) gather_block<4, true>(gb + (uint32_t)jb * kBlockBytes, ent, p.dout, p.dout + jb * 32, (uint32_t)p.c_out, lane);
+        else gather_block<8, true>(gb + (uint32_t)jb * kBlockBytes, ent, p.dout, p.dout + jb * 32, (uint32_t)p.c_out, lane);
+      }
+      cp_async_arrive(g_full(buf));
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 4; ++r) e[r] = en[r];
+    }
+  } else if (warp >= 8 && warp < 12) {
+    // =================================================================== epilogue: TMEM -> dW (+=)
+    const int ew = warp & 3;
+    uint32_t seen = 0;
+    for (int i = lane; i < ne; i += 32) seen |= cmask[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) seen |= __shfl_xor_sync(0xffffffffu, seen, o);
+    if (seen == 0) goto done;
+    if (!mbar_wait_sleep(acc_full, 0u, abort_flag, 1000)) goto done;
+    if (ew == 0) TRACE(kProducers + 2, 0, 0);
+    tc_fence_after();
+    const int ci = p.mm == 128 ? ew * 32 + lane : ew * 16 + lane;
+    const bool lane_ok = (p.mm == 128 || lane < 16) && ci < p.cm;
+    const int rot = (int)((unsigned)split * 5u % 32u);
+    const uint32_t hi = seen & ~((1u << rot) - 1u), lo = seen & ((1u << rot) - 1u);
+    for (int part = 0; part < 2; ++part)
+    for (uint32_t rem = part ? lo : hi; rem; rem &= rem - 1) {
+      const int k = __ffs(rem) - 1;
+      const int kidx = __popc(gmask & ((1u << k) - 1u));
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(kidx * p.c_out);
+      float* dst = p.dw + ((int64_t)k * p.c_in + ci) * p.c_out;
+      for (int c0 = 0; c0 < p.c_out; c0 += 16) {
+        float acc[16];
+        tmem_ld16(taddr + (uint32_t)c0, acc);
+        if (lane_ok) {
+#pragma unroll
+          for (int qq = 0; qq < 16; qq += 4)
+            if (acc[qq] != 0.f || acc[qq + 1] != 0.f || acc[qq + 2] != 0.f || acc[qq + 3] != 0.f)
+              red_add_v4(dst + c0 + qq, acc[qq], acc[qq + 1], acc[qq + 2], acc[qq + 3]);
+        }
+      }
+    }
+    if (ew == 0) TRACE(kProducers + 2, 0, 1);
+    tc_fence_before();
+  } else if (warp >= 12) {
+    // =================================================================== MMA issuers: ring m = warp - 12
+    const int m = warp - 12;
+    const uint16_t* list = items + (size_t)m * p.max_items;
+    const uint32_t* fst = first + m * (p.n_local + 1);
+    const uint32_t idesc = make_idesc_tf32(p.mm, p.c_out, 1, 1);
+    const uint64_t desc0 = make_desc_sw128_base32(0, kBlockBytes, 512);
+    uint32_t seen = 0;
+    bool ok = true;
+    for (int t = 0; t < ne && ok; ++t) {
+      const int buf = t % p.gbufs;
+      if (!mbar_wait(g_full(buf), ((uint32_t)t / (uint32_t)p.gbufs) & 1u, abort_flag)) { ok = false; break; }
+      const uint64_t g_desc = desc0 + desc_addr(g_base + (uint32_t)buf * g_bytes);
+      for (uint32_t i = fst[t]; i < fst[t + 1]; ++i) {
+        const int s = 2 * (int)(i % (uint32_t)R) + m;
+        TRACE(kProducers + 3 + m, i, 0);
+        if (!mbar_wait(a_full(s), (i / (uint32_t)R) & 1u, abort_flag)) { ok = false; break; }
+        TRACE(kProducers + 3 + m, i, 1);
+        tc_fence_after();
+        const int k = (int)(list[i] & 31u);
+        if (elect_one()) {
+          const uint64_t a_desc = desc0 + desc_addr(a_base + (uint32_t)s * a_bytes);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(__popc(gmask & ((1u << k) - 1u)) * p.c_out);
+          umma_tf32(d_tmem, a_desc, g_desc, idesc, (seen >> k) & 1u);
+#pragma unroll
+          for (int r8 = 1; r8 < 16; ++r8) umma_tf32(d_tmem, a_desc + r8 * 64, g_desc + r8 * 64, idesc, 1u);
+          umma_commit(a_empty(s));
+        }
+        __syncwarp();
+        TRACE(kProducers + 3 + m, i, 2);
+        seen |= 1u << k;
+      }
+      if (!ok) break;
+      if (elect_one()) umma_commit(g_empty(buf));  // (arrives at once when this ring had no item of the tile)
+      __syncwarp();
+    }
+    if (ok && elect_one()) umma_commit(acc_full);
+    __syncwarp();
+  }
+done:
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0 && *abort_flag) mm3d_raise(p.err);
+#ifdef MM3D_TRACE
+  if (p.trace && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[4096 + 2 * blockIdx.x + 1] = (long long)gt;
+  }
+#endif
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
 }  // namespace
 
 int* mm3d_device_err_flag();  // conv_tc.cu
@@ -467,6 +840,7 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
   const size_t fixed = 1024 + 8 * (2 * kMaxStages + 2 * kMaxGBufs + 1) + 64;
   const size_t budget = 218 * 1024 - fixed;  // (the rest, >= 8 KB, holds the CTA's tile list)
   p.gbufs = 2;
+  p.max_items = 0;
   p.S = budget > 2 * g_bytes ? (int)((budget - 2 * g_bytes) / a_bytes) : 0;
   if (p.S < 2) {
     p.gbufs = 1;
@@ -525,6 +899,50 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
     MM3D_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     once = true;
   }
+  // Narrow layers (one 32-channel block per item): the two-ring kernel.  MM3D_WGRAD_RINGS_NBI overrides the widest
+  // item it takes (in 32-channel blocks; 0 = never), for A/B measurements.
+  int ring_nbi = 1;
+  if (const char* e = getenv("MM3D_WGRAD_RINGS_NBI")) ring_nbi = atoi(e);
+  const int all_tiles = p.num_tiles;
+  if (p.nmb == 1 && p.nbi <= ring_nbi) {
+    static bool once_r[64] = {false};
+    bool& once2 = once_r[mm3d_device_slot()];
+    if (!once2) {
+      MM3D_CUDA(cudaFuncSetAttribute(k_wgrad_tc_rings, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      MM3D_CUDA(cudaFuncSetAttribute(k_wgrad_tc_rings, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      once2 = true;
+    }
+    int gbufs = 4;
+    const int ring_s = p.nbi == 1 ? kRingStages : 4;
+    const size_t ring_fixed = 1024 + (size_t)ring_s * a_bytes + 7 * kRingEntBytes + 8 * (2 * kMaxStages + 2 * kMaxGBufs + 1) + 64 + 64;
+    while (gbufs > 1 && ring_fixed + (size_t)gbufs * g_bytes + 16 * 1024 > 226 * 1024) --gbufs;
+    if (ring_fixed + (size_t)gbufs * g_bytes + 16 * 1024 <= 226 * 1024) {
+      p.gbufs = gbufs;
+      p.S = ring_s;
+      const size_t fixed_r = ring_fixed + (size_t)gbufs * g_bytes;
+      const size_t per_tile = 8 + 8 + 4 * (size_t)gk;  // mask + index, two first-item entries, two lists of 16-bit items
+      int64_t max_local_r = (int64_t)((226 * 1024 - fixed_r - 64) / per_tile);
+      if (max_local_r > 2047) max_local_r = 2047;  // (11 bits of local tile index per item)
+      if (const char* e = getenv("MM3D_WGRAD_MAX_LOCAL")) {
+        const int64_t v = atoll(e);
+        if (v >= 2 && v < max_local_r) max_local_r = v;
+      }
+      const int64_t max_tiles_r = max_local_r * per_group_min;
+      for (int64_t start = 0; start < all_tiles; start += max_tiles_r) {
+        const int cnt = (int)(all_tiles - start < max_tiles_r ? all_tiles - start : max_tiles_r);
+        p.order = pv.order + start;
+        p.num_tiles = cnt;
+        p.n_local = (cnt + per_group_min - 1) / per_group_min;
+        p.max_items = p.n_local * gk;
+        const size_t smem = fixed_r + (size_t)p.n_local * 8 + (size_t)(p.n_local + 1) * 8 + (size_t)p.max_items * 4 + 32;
+        MM3D_REQUIRE(smem <= 226 * 1024, MM3D_ERR_UNSUPPORTED, "tcgen05 wgrad: shared memory budget exceeded");
+        MM3D_CUDA(mm3d_launch_pdl(k_wgrad_tc_rings, dim3((unsigned)total_ctas), dim3(kRingThreads), smem, stream, p));
+        mm3d_count_launches(1);
+      }
+      MM3D_CHECK_LAUNCH("mm3d_conv_wgrad_tc");
+      return MM3D_OK;
+    }
+  }
   // The kernel keeps the list of a CTA's tiles (index + mask, 8 bytes each) in shared memory.  Row counts whose list
   // does not fit next to the stages are processed in several launches over consecutive pieces of the plan's tile
   // order (the kernel only ever adds into d_weight, so the pieces simply accumulate).
@@ -534,7 +952,6 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
     if (v >= 2 && v < max_local) max_local = v & ~(int64_t)1;
   }
   const int64_t max_tiles = max_local * per_group_min;
-  const int all_tiles = p.num_tiles;
   for (int64_t start = 0; start < all_tiles; start += max_tiles) {
     const int cnt = (int)(all_tiles - start < max_tiles ? all_tiles - start : max_tiles);
     p.order = pv.order + start;
