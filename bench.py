@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--no-pipeline", dest="pipeline", action="store_false",
                     help="build each step's sparse structure inline on the compute stream instead of one step ahead")
     ap.add_argument("--no-kernel-pass", action="store_true")
+    ap.add_argument("--graph-2d", action="store_true",
+                    help="--full-step: replay the dense 2D network (forward and backward, source and target pass) from CUDA graphs")
     ap.add_argument("--ab", default="", help="development: NAME=VALUE, time alternating blocks of steps with that variable set / unset")
     ap.add_argument("--full-step", action="store_true",
                     help="BASELINE configs[2]: whole MM2D3D training step (2D ResNet34-UNet stand-in on stock cuDNN + lift + "
@@ -659,7 +661,7 @@ def run_full_step(args):
     import torch.nn.functional as F
 
     sys.path.insert(0, os.path.join(ROOT, "tools"))
-    from net2d_standin import RGBDUNet2D
+    from net2d_standin import Dense2D, RGBDUNet2D
 
     from mm2d3d_b200 import _lib, synth
     from mm2d3d_b200 import scn as scn_mod
@@ -696,13 +698,28 @@ def run_full_step(args):
                 li=LiftIndices(idx, dev), labels=torch.from_numpy(rng.integers(0, C, locs.shape[0])).to(dev)))
     n_points = float(np.mean([b["locs"].shape[0] for dom in data for b in data[dom]]))
     ev3d = []
+    # the dense 2D network (static shapes) replayed from CUDA graphs -- one graph pair (forward, backward)
+    # per pass of the step, because the source and the target pass are both alive when backward starts; the lifts (a
+    # different number of points every batch) stay outside
+    graphed = None
+    if args.graph_2d:
+        b0 = data["src"][0]
+        with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
+            graphed = dict(zip(("src", "trg"), torch.cuda.make_graphed_callables(
+                (Dense2D(net2d), Dense2D(net2d)), ((b0["img"], b0["depth"]), (b0["img"], b0["depth"])))))
+    from mm2d3d_b200.lift import lift2d
 
     def step(i, time3d=False):
         loss = 0.0
         for dom in ("src", "trg"):
             b = data[dom][i % args.rotate]
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                l2d, a2d, _ = net2d(b["img"], b["depth"], b["li"])
+            if graphed is not None:
+                with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
+                    m2d, ma2d = graphed[dom](b["img"], b["depth"])
+                l2d, a2d = lift2d(m2d.float(), b["li"]), lift2d(ma2d.float(), b["li"])
+            else:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    l2d, a2d, _ = net2d(b["img"], b["depth"], b["li"])
             if time3d:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -772,10 +789,10 @@ def run_full_step(args):
     line = {
         "impl": "ours", "metric": "full MM2D3D training step scans/sec (source + target)", "value": scans / (ms * 1e-3), "unit": UNIT,
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3"}[args.mode] + " (3D) / bf16 autocast (2D)", "data": "synthetic",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "tf32x3": "tf32x3", "bf16": "bf16"}[args.mode] + " (3D) / bf16 autocast (2D)", "data": "synthetic",
         "config": {
             "workload": f"BASELINE configs[2]: full MM2D3D step -- ResNet34-UNet stand-in on {H}x{W} RGB-D (46.2 M parameters, "
-                        f"stock cuDNN, channels-last, BF16 autocast) + 2D->3D lift + RGB mask + UNetSCN(m=16, 7 planes) + 2+2 heads "
+                        f"stock cuDNN, channels-last, BF16 autocast{', dense part replayed from CUDA graphs' if args.graph_2d else ''}) + 2D->3D lift + RGB mask + UNetSCN(m=16, 7 planes) + 2+2 heads "
                         f"+ CE / cross-modal KL + fused Adam; batch {args.batch} source + {args.batch} target {args.shape}-shaped scans",
             "points_per_batch": n_points, "conv_mode": args.mode,
             "structure": "built inline by each 3D forward", "l2": f"{args.rotate} rotating resident batches per domain",

@@ -57,7 +57,8 @@ class RGBDUNet2D(nn.Module):
         self.pool = nn.AvgPool2d(5, 1, 2)
         self.cls, self.cls_aux = nn.Conv2d(64, num_classes, 1), nn.Conv2d(64, num_classes, 1)
 
-    def forward(self, img, depth, lift_indices):
+    def dense(self, img, depth):
+        """The dense part (static shapes: what a CUDA graph can hold): logits of both heads and the feature map."""
         h, w = img.shape[-2:]
         ph, pw = (-h) % 16, (-w) % 16
         if ph or pw:
@@ -69,6 +70,21 @@ class RGBDUNet2D(nn.Module):
             x = fuse(torch.cat([b[s], up(x), a[s]], 1))
         fmap = x[:, :, :h, :w]
         pooled = self.pool(fmap)
-        logit_2d, logit_aux_2d = self.cls(pooled), self.cls_aux(pooled)
+        return self.cls(pooled), self.cls_aux(pooled), fmap
+
+    def forward(self, img, depth, lift_indices):
+        logit_2d, logit_aux_2d, fmap = self.dense(img, depth)
         # the lift: one gather kernel over all samples instead of the reference's per-sample indexing loop
         return lift2d(logit_2d.float(), lift_indices), lift2d(logit_aux_2d.float(), lift_indices), fmap
+
+
+class Dense2D(nn.Module):
+    """``RGBDUNet2D.dense`` as a module of its own (for ``torch.cuda.make_graphed_callables``)."""
+
+    def __init__(self, net):
+        super().__init__()
+        self.net = net
+
+    def forward(self, img, depth):
+        a, b, _ = self.net.dense(img, depth)
+        return a, b
