@@ -14,6 +14,7 @@
 //   off_tiles uint32[32]         number of tiles that contain offset k (the weight-gradient kernel shares its CTAs
 //                                among offset groups in proportion)
 //   tbl       int32 [K][T*128]   tbl[k][128 t + r] = input row of perm[128 t + r] at offset k, or -1
+//   (3^3 tables: builder scratch behind it, mm3d_plan_off_scratch)
 //
 // with T = ceil(n_cap / 128).  Features stay in SparseConvNet row order everywhere; only the order
 // in which rows are computed changes, and results do not depend on it (an all-zero K-block adds 0).
@@ -42,8 +43,15 @@ __host__ __device__ inline size_t mm3d_plan_off_cnt(int64_t n_cap) {
   return mm3d_plan_off_order(n_cap) + ((size_t)mm3d_plan_tiles(n_cap) * 4 + 255) / 256 * 256;
 }
 __host__ __device__ inline size_t mm3d_plan_off_tbl(int64_t n_cap) { return mm3d_plan_off_cnt(n_cap) + 256; }
-__host__ __device__ inline size_t mm3d_plan_size(int64_t n_cap, int K) {
+// behind the permuted table: scratch of the builder for 3^3 tables (the global pre-ordering of plan.cu): pre int32[T*128],
+// keys uint32[T*128], per-chunk digit counters uint32[ceil(n_cap / 8192)][1024]
+__host__ __device__ inline size_t mm3d_plan_off_scratch(int64_t n_cap, int K) {
   return mm3d_plan_off_tbl(n_cap) + ((size_t)K * mm3d_plan_tiles(n_cap) * 128 * 4 + 255) / 256 * 256;
+}
+__host__ __device__ inline size_t mm3d_plan_size(int64_t n_cap, int K) {
+  size_t s = mm3d_plan_off_scratch(n_cap, K);
+  if (K == 27) s += 2 * (((size_t)mm3d_plan_tiles(n_cap) * 128 * 4 + 255) / 256 * 256) + (size_t)((n_cap + 8191) / 8192) * 1024 * 4 + 256;
+  return s;
 }
 
 inline Mm3dPlanView mm3d_plan_view(const void* plan, int64_t n_cap) {

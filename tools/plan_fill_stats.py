@@ -60,6 +60,35 @@ def main():
         # what-if: one pass, rows sorted globally by the full mask (the plan sorts within chunks of 8192 rows by a class-ordered key)
         u = tiles_union(torch.sort(rowmask).values)
         line += f" | global sort: items {int(popc(u).sum())}"
+        # the plan's 19-bit key (bit 18 = any corner, 17..6 edges, 5..0 faces), sorted globally / two-level (a stable global
+        # sort by the key's top bits, then a stable sort by the full key inside chunks of 8192 rows)
+        key = torch.zeros(n, dtype=torch.int64, device=dev)
+        edge, face = 17, 5
+        for k in range(27):
+            c = int(cls[k])
+            if c == 0:
+                continue
+            if c == 3:
+                pos = 18
+            elif c == 2:
+                pos = edge
+                edge -= 1
+            else:
+                pos = face
+                face -= 1
+            key |= ((rowmask >> k) & 1) << pos
+        def items_of(order):
+            return int(popc(tiles_union(rowmask[order])).sum())
+        line += f" | global by key: {items_of(torch.sort(key, stable=True).indices)}"
+        for top in (4, 7, 10, 13):
+            coarse = key >> (19 - top)
+            o1 = torch.sort(coarse, stable=True).indices
+            k1 = key[o1]
+            chunks = []
+            for c0 in range(0, n, 8192):
+                kk = k1[c0:c0 + 8192]
+                chunks.append(o1[c0:c0 + 8192][torch.sort(kk, stable=True).indices])
+            line += f" | top{top}+chunks: {items_of(torch.cat(chunks))}"
         print(line)
         s //= 2
 
