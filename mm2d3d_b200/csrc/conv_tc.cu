@@ -690,7 +690,11 @@ int mm3d_conv_fwd_tc_img(const float* in, int64_t n_in, int c_in, float* out, in
   const size_t fixed = 1024 + (size_t)kProducers * kEntBytes + 8 * (2 * kMaxStages + 4) + 64 + 64;
   const int two = (int)((108 * 1024 - fixed) / per_stage), one = (int)((218 * 1024 - fixed) / per_stage);
   // (measured: two CTAs per SM win for one-block layers (c_in <= 32), one CTA with the deeper ring from 64 channels on)
-  const int per_sm = (p.num_tiles > sms && nb == 1 && two >= 4 && 2 * p.tmem_cols <= 512) ? 2 : 1;
+  int per_sm = (p.num_tiles > sms && nb == 1 && two >= 4 && 2 * p.tmem_cols <= 512) ? 2 : 1;
+  if (const char* e = getenv("MM3D_TC_PER_SM")) {  // A/B measurements: 2 = two CTAs per SM wherever they fit
+    if (atoi(e) == 2 && p.num_tiles > sms && two >= 2 && 2 * p.tmem_cols <= 512) per_sm = 2;
+    if (atoi(e) == 1) per_sm = 1;
+  }
   int S = per_sm == 2 ? two : one;
   if (S > kMaxStages) S = kMaxStages;
   S &= ~1;
