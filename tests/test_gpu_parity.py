@@ -213,6 +213,40 @@ def test_row_plan(kind, shape, batch):
     assert np.array_equal(perm2[:T * 128], p) and np.array_equal(mask2[:T], mask[:T])
 
 
+def test_row_plan_global_preorder(monkeypatch):
+    """3^3 tables with more than one chunk of 8192 rows are pre-ordered globally before the chunk sort (plan.cu):
+    fewer non-empty (tile, offset) blocks than the chunk-only order, the same plan on every build, and convolution
+    results that do not depend on the order (up to the FP32 summation order inside a row)."""
+    from mm2d3d_b200 import functional as F
+    coords = synth.make_batch("nuscenes", batch=2)[0]
+
+    def build():
+        meta = _meta(coords, 4096, 2)
+        perm, mask, tbl, order = (t.cpu().numpy() for t in meta.plan_tensors("smc", 4096))
+        return meta, perm, mask
+
+    def blocks(mask, n):
+        m = mask[:(n + 127) // 128].astype(np.int64) & 0xFFFFFFFF
+        return int(sum(((m >> k) & 1).sum() for k in range(27)))
+
+    meta_a, perm_a, mask_a = build()
+    n = meta_a.nbr_table(4096).shape[0]
+    assert n > 3 * 8192
+    meta_a2, perm_a2, mask_a2 = build()
+    assert np.array_equal(perm_a, perm_a2) and np.array_equal(mask_a, mask_a2)  # deterministic
+    monkeypatch.setenv("MM3D_PLAN_NO_PREORDER", "1")
+    meta_b, perm_b, mask_b = build()
+    monkeypatch.delenv("MM3D_PLAN_NO_PREORDER")
+    assert blocks(mask_a, n) < 0.9 * blocks(mask_b, n), (blocks(mask_a, n), blocks(mask_b, n))
+    torch.manual_seed(3)
+    x = torch.randn(n, 32, device=DEV)
+    w = torch.randn(27, 1, 32, 48, device=DEV) / 32 ** 0.5
+    ya = F.TableConvFn.apply(x, w, meta_a, "smc", 4096, "tf32")
+    yb = F.TableConvFn.apply(x, w, meta_b, "smc", 4096, "tf32")
+    assert rel_err(ya, yb) < 1e-5
+    _no_device_error()
+
+
 # ------------------------------------------------------------------------------ single ops
 def test_io_layers():
     from mm2d3d_b200 import functional as F
@@ -810,7 +844,8 @@ def test_prepared_structure_on_side_stream_matches_inline():
             scn_mod.set_conv_mode("fp32")
 
 
-def test_tf32_wgrad_in_several_launches(monkeypatch):
+@pytest.mark.parametrize("ci", [32, 64])  # 32: the two-ring kernel of the narrow layers, 64: the general one
+def test_tf32_wgrad_in_several_launches(monkeypatch, ci):
     """Row counts whose per-CTA tile list does not fit in shared memory are processed in several launches over
     pieces of the plan's tile order (happens from ~300 k rows at 192 channels); forced here at 20 k rows."""
     from mm2d3d_b200 import _lib
@@ -819,7 +854,7 @@ def test_tf32_wgrad_in_several_launches(monkeypatch):
     locs, _ = synth.make_batch("nuscenes", batch=1, seed0=3)
     meta = Metadata(torch.from_numpy(locs).to(DEV), 4096, 1, plans=True)
     t, _, _ = F.conv_tables(meta, "smc", 4096, plans=True)
-    n, ci, co = t.n_out, 32, 48
+    n, co = t.n_out, 48
     torch.manual_seed(1)
     x, dout = torch.randn(n, ci, device=DEV), torch.randn(n, co, device=DEV)
     lib, sp = _lib.lib, _lib.stream_ptr()
