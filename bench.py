@@ -665,7 +665,7 @@ def run_full_step(args):
 
     from mm2d3d_b200 import _lib, synth
     from mm2d3d_b200 import scn as scn_mod
-    from mm2d3d_b200.heads import cross_modal_kl, rgb_mask
+    from mm2d3d_b200.heads import cross_modal_kl, heads3d, rgb_mask
     from mm2d3d_b200.lift import LiftIndices
     from mm2d3d_b200.unet import UNetSCN
 
@@ -728,10 +728,11 @@ def run_full_step(args):
             if time3d:
                 e1.record()
                 ev3d.append((e0, e1))
-            l3d, a3d = head(out3d), head_aux(out3d)
+            # both 3D heads and the 3D side of the cross-modal loss in one pass over the [N, 16] features
+            l3d, _, xm3d = heads3d(out3d, head.weight, head.bias, head_aux.weight, head_aux.bias, l2d)
             if dom == "src":
                 loss = loss + F.cross_entropy(l2d, b["labels"]) + F.cross_entropy(l3d, b["labels"])
-            loss = loss + 0.1 * (cross_modal_kl(a3d, l2d) + cross_modal_kl(a2d, l3d))
+            loss = loss + 0.1 * (xm3d + cross_modal_kl(a2d, l3d))
         loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MM3D_ABI_VERSION 4
+#define MM3D_ABI_VERSION 5
 
 #define MM3D_OK 0
 #define MM3D_ERR_INVALID 1     /* bad argument */
@@ -250,6 +250,19 @@ MM3D_API int mm3d_kl_logits_fwd(const float* pred, const float* target, int64_t 
                        mm3d_stream_t stream);
 MM3D_API int mm3d_kl_logits_bwd(const float* pred, const float* target, int64_t n, int C, const float* dloss, float* dpred,
                        mm3d_stream_t stream);
+/* The two point-wise heads of the 3D branch and the 3D side of the cross-modal loss in ONE pass over the features
+ * (3d_net/model.py:38,49 `linear`; :73,85 `L2G_classifier_3D.linear_point`; train.py:157-184 `loss_3d`):
+ *   logit1 = feat w1^T + b1,   logit2 = feat w2^T + b2,   loss[0] = mean_n KL(softmax(target_n) || softmax(logit2_n))
+ * feat float32 [n, f] (f a multiple of 4, <= 32, 16-byte aligned), w1 / w2 [C, f] and b1 / b2 [C] as nn.Linear stores
+ * them (C <= 20), target [n, C] logits (detached).  logit2 and loss may be NULL (then target may be NULL); ws: 1 double.
+ * Backward: d_logit1 / d_logit2 [n, C] upstream gradients (either may be NULL), d_loss [1] (NULL = loss unused);
+ * d_feat [n, f] (may be NULL), d_w1 / d_w2 [C, f], d_b1 / d_b2 [C] overwritten; ws: (2 C f + 2 C) doubles. */
+MM3D_API int mm3d_heads3d_fwd(const float* feat, int64_t n, int f, int C, const float* w1, const float* b1, const float* w2,
+                     const float* b2, const float* target, float* logit1, float* logit2, float* loss, void* ws,
+                     size_t ws_bytes, mm3d_stream_t stream);
+MM3D_API int mm3d_heads3d_bwd(const float* feat, int64_t n, int f, int C, const float* w1, const float* w2, const float* b2,
+                     const float* target, const float* d_logit1, const float* d_logit2, const float* d_loss, float* d_feat,
+                     float* d_w1, float* d_b1, float* d_w2, float* d_b2, void* ws, size_t ws_bytes, mm3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Whole-network executor: UNetSCN (3d_net/scn_unet.py:90-126, VGG blocks, block_reps == 1) forward and

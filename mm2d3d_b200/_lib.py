@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmm3d.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 LEVEL_DESC_WORDS = 10
 
 MODE_FP32, MODE_TF32, MODE_BF16, MODE_TF32X3 = 0, 1, 2, 3
@@ -67,6 +67,8 @@ SIGNATURES = {
     "mm3d_rgb_mask_bwd": (_i, [_p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "mm3d_kl_logits_fwd": (_i, [_p, _p, _i64, _i, _p, _p, _sz, _p]),
     "mm3d_kl_logits_bwd": (_i, [_p, _p, _i64, _i, _p, _p, _p]),
+    "mm3d_heads3d_fwd": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mm3d_heads3d_bwd": (_i, [_p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mm3d_unet_num_params": (_i64, [_i]),
     "mm3d_unet_act_bytes": (_sz, [_i, _i, _i, _i, _p, _i64]),
     "mm3d_unet_bwd_bytes": (_sz, [_i, _i, _i, _i, _p, _i64]),

@@ -11,6 +11,8 @@ the lift fixture):  ``python tests/golden/make_golden.py``.
 * ``structure_small.npz`` -- oracle voxel ids / level coords / rule tables for a seeded cloud.
 * ``augment_ref.npz`` -- produced by the REFERENCE ITSELF: ``augment_and_scale_3d``
   (``lib/utils/augmentation_3d.py``) + the loader's integer cast and range filter.
+* ``heads3d_ref.npz`` -- the two 3D heads by the REFERENCE's ``Net3DSeg.forward`` with its real heads (backbone replaced by a
+  16-channel pass-through), 3D cross-modal term by the torch lines of ``train.py:174-182``.
 * ``heads_ref.npz`` -- RGB mask by the REFERENCE's ``Net3DSeg.forward`` (``3d_net/model.py:44-58``, backbone replaced by
   a pass-through), cross-modal KL term by the torch lines of ``train.py:157-184``.
 """
@@ -215,6 +217,47 @@ def heads_from_reference():
                         dpred=pred.grad.numpy())
 
 
+def heads3d_from_reference():
+    """``heads3d_ref.npz``: ``seg_logit`` and ``seg_logit_point`` computed by the reference's own ``Net3DSeg.forward``
+    (``3d_net/model.py:44-58``, real ``linear`` and ``L2G_classifier_3D`` heads; its sparse backbone replaced by a
+    pass-through that hands on a recorded 16-channel feature tensor), the 3D term of the cross-modal loss by the torch
+    lines of ``train.py:174-182``, and the autograd gradients of  sum(seg_logit * g1) + sum(seg_logit_point * g2) +
+    lam * loss_3d  with respect to the features and the four head parameters."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    src = open(os.path.join(REF_3D_DIR, "model.py")).read().replace("from .scn_unet import UNetSCN", "UNetSCN = None")
+    mod = type(sys)("ref_3d_model_heads")
+    exec(compile(src, os.path.join(REF_3D_DIR, "model.py"), "exec"), mod.__dict__)
+    rng = np.random.default_rng(23)
+    n, classes = 1777, 6
+    feat = torch.from_numpy(rng.standard_normal((n, 16)).astype(np.float32)).requires_grad_(True)
+
+    class PassThrough(nn.Module):  # stands in for UNetSCN: hands on the recorded backbone output
+        out_channels = 16
+
+        def forward(self, x):
+            return feat
+
+    mod.UNetSCN = lambda **kw: PassThrough()
+    torch.manual_seed(23)
+    net = mod.Net3DSeg(num_classes=classes, dual_head=True, backbone_3d_kwargs={})
+    preds, out_feat, out_aux = net({"x": [torch.zeros(n, 4, dtype=torch.int64), torch.rand(n, 3)]})   # model.py:44-58
+    l1, l2 = preds["seg_logit"], out_aux["seg_logit_point"]
+    target = torch.from_numpy((2 * rng.standard_normal((n, classes))).astype(np.float32))           # 2D logits
+    loss = F.kl_div(F.log_softmax(l2, dim=1), F.softmax(target.detach(), dim=1), reduction="none").sum(1).mean()
+    g1 = torch.from_numpy(rng.standard_normal((n, classes)).astype(np.float32))
+    g2 = torch.from_numpy(rng.standard_normal((n, classes)).astype(np.float32))
+    lam = 0.7
+    ((l1 * g1).sum() + (l2 * g2).sum() + lam * loss).backward()
+    np.savez_compressed(
+        os.path.join(HERE, "heads3d_ref.npz"), feat=feat.detach().numpy(), target=target.numpy(), g1=g1.numpy(), g2=g2.numpy(),
+        lam=np.float32(lam), w1=net.linear.weight.detach().numpy(), b1=net.linear.bias.detach().numpy(),
+        w2=net.aux.linear_point.weight.detach().numpy(), b2=net.aux.linear_point.bias.detach().numpy(),
+        logit1=l1.detach().numpy(), logit2=l2.detach().numpy(), loss=loss.detach().numpy(), d_feat=feat.grad.numpy(),
+        d_w1=net.linear.weight.grad.numpy(), d_b1=net.linear.bias.grad.numpy(),
+        d_w2=net.aux.linear_point.weight.grad.numpy(), d_b2=net.aux.linear_point.bias.grad.numpy())
+
+
 if __name__ == "__main__":
     only = sys.argv[1] if len(sys.argv) > 1 else None  # e.g. `make_golden.py augment` regenerates one fixture
     if only in (None, "lift"):
@@ -227,6 +270,8 @@ if __name__ == "__main__":
         augment_from_reference()
     if only in (None, "heads"):
         heads_from_reference()
+    if only in (None, "heads3d"):
+        heads3d_from_reference()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -100,3 +100,20 @@ def test_heads_oracle_matches_reference_fixture():
     assert float(loss.detach()) == float(z["loss"])
     loss.backward()
     assert np.array_equal(pred.grad.numpy(), z["dpred"])
+
+
+def test_heads3d_oracle_matches_reference_fixture():
+    """The two 3D heads vs what the reference's own Net3DSeg.forward produced (real `linear` / `linear_point`), the 3D
+    cross-modal term and the autograd gradients of the fixture's combined scalar."""
+    import torch
+    from oracle import heads_oracle
+    z = np.load(os.path.join(G, "heads3d_ref.npz"))
+    t = lambda k: torch.from_numpy(z[k])
+    feat = t("feat").requires_grad_(True)
+    w1, b1, w2, b2 = (t(k).requires_grad_(True) for k in ("w1", "b1", "w2", "b2"))
+    l1, l2, loss = heads_oracle.heads3d(feat, w1, b1, w2, b2, t("target"))
+    assert np.array_equal(l1.detach().numpy(), z["logit1"]) and np.array_equal(l2.detach().numpy(), z["logit2"])
+    assert float(loss.detach()) == float(z["loss"])
+    ((l1 * t("g1")).sum() + (l2 * t("g2")).sum() + float(z["lam"]) * loss).backward()
+    for got, key in ((feat.grad, "d_feat"), (w1.grad, "d_w1"), (b1.grad, "d_b1"), (w2.grad, "d_w2"), (b2.grad, "d_b2")):
+        assert np.allclose(got.numpy(), z[key], rtol=1e-6, atol=1e-7), key

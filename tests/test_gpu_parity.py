@@ -906,6 +906,42 @@ def test_heads_reference_fixture():
     assert float((y2 - ref).abs().max()) < 1e-6
 
 
+def test_heads3d_reference_fixture():
+    """The fused 3D heads (two Linear(16 -> classes) + the 3D cross-modal term in one pass) against
+    tests/golden/heads3d_ref.npz, whose logits the reference's own Net3DSeg.forward produced: forward 1e-6, gradients
+    1e-5 relative to the tensor scale; also without a target, without a feature gradient and on a large odd batch."""
+    from mm2d3d_b200.heads import heads3d
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "heads3d_ref.npz"))
+    dev = lambda k: torch.from_numpy(z[k]).to(DEV)
+    feat = dev("feat").requires_grad_(True)
+    w1, b1, w2, b2 = (dev(k).requires_grad_(True) for k in ("w1", "b1", "w2", "b2"))
+    l1, l2, loss = heads3d(feat, w1, b1, w2, b2, dev("target"))
+    assert float((l1.detach().cpu() - torch.from_numpy(z["logit1"])).abs().max()) < 1e-5
+    assert float((l2.detach().cpu() - torch.from_numpy(z["logit2"])).abs().max()) < 1e-5
+    assert abs(float(loss.detach()) - float(z["loss"])) <= 1e-6 * abs(float(z["loss"]))
+    ((l1 * dev("g1")).sum() + (l2 * dev("g2")).sum() + float(z["lam"]) * loss).backward()
+    for got, key in ((feat.grad, "d_feat"), (w1.grad, "d_w1"), (b1.grad, "d_b1"), (w2.grad, "d_w2"), (b2.grad, "d_b2")):
+        want = torch.from_numpy(z[key])
+        assert got.shape == want.shape, key
+        assert float((got.cpu() - want).abs().max()) <= 1e-5 * max(float(want.abs().max()), 1.0), key
+    # no target (inference), features that are data, a large odd row count and 10 classes vs plain torch
+    torch.manual_seed(5)
+    n, f, C = 100003, 16, 10
+    x = torch.randn(n, f, device=DEV)
+    lin1, lin2 = torch.nn.Linear(f, C).to(DEV), torch.nn.Linear(f, C).to(DEV)
+    a1, a2, zero = heads3d(x, lin1.weight, lin1.bias, lin2.weight, lin2.bias)
+    assert float((a1 - lin1(x)).detach().abs().max()) < 1e-5 and float((a2 - lin2(x)).detach().abs().max()) < 1e-5 and float(zero) == 0.0
+    tgt = torch.randn(n, C, device=DEV)
+    a1, a2, kl = heads3d(x, lin1.weight, lin1.bias, lin2.weight, lin2.bias, tgt)
+    want_kl = torch.nn.functional.kl_div(torch.log_softmax(lin2(x), 1), torch.softmax(tgt, 1), reduction="none").sum(1).mean()
+    assert abs(float(kl.detach()) - float(want_kl.detach())) < 1e-5 * abs(float(want_kl.detach()))
+    g = torch.randn(n, C, device=DEV)
+    got = torch.autograd.grad((a1 * g).sum() + kl, [lin1.weight, lin1.bias, lin2.weight, lin2.bias])
+    want = torch.autograd.grad((lin1(x) * g).sum() + want_kl, [lin1.weight, lin1.bias, lin2.weight, lin2.bias])
+    for a, b in zip(got, want):
+        assert float((a - b).abs().max()) <= 2e-5 * max(float(b.abs().max()), 1.0)
+
+
 # ------------------------------------------------------------------------------ whole network, frozen gates
 def _bn_modules(net):
     return [m for m in net.modules() if type(m).__name__ in ("BatchNormLeakyReLU", "BatchNormReLU")]
