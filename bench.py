@@ -665,7 +665,7 @@ def run_full_step(args):
 
     from mm2d3d_b200 import _lib, synth
     from mm2d3d_b200 import scn as scn_mod
-    from mm2d3d_b200.heads import cross_modal_kl, heads3d, rgb_mask
+    from mm2d3d_b200.heads import cross_modal_kl, heads3d
     from mm2d3d_b200.lift import LiftIndices
     from mm2d3d_b200.unet import UNetSCN
 
@@ -723,8 +723,7 @@ def run_full_step(args):
             if time3d:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            x = rgb_mask(b["feats"], mask.weight, mask.bias)
-            out3d = net3d([b["locs"], x])
+            out3d = net3d([b["locs"], b["feats"]], rgb_mask=mask)  # the RGB-mask prologue rides in the InputLayer scatter
             if time3d:
                 e1.record()
                 ev3d.append((e0, e1))

@@ -163,6 +163,16 @@ MM3D_API int mm3d_input_fwd(const float* feats, const int32_t* p2v, const int32_
                    int64_t n_vox, int c, int mode, float* out_vox, mm3d_stream_t stream);
 MM3D_API int mm3d_input_bwd(const float* d_vox, const int32_t* p2v, const int32_t* npts, int64_t n_points,
                    int c, int mode, float* d_feats, mm3d_stream_t stream);
+/* InputLayer with the RGB-mask prologue of Net3DSeg.forward (3d_net/model.py:46-48) folded in: the voxel rows of
+ * feats * sigmoid(feats . w + b) without the masked [N, c] tensor; c == 3; wb = [w_0, w_1, w_2, b] (device);
+ * s_out [n_points] keeps the gates.  Backward: d_feats may be NULL; d_wb [c + 1] = (d_w, d_b), overwritten; feats are the
+ * UNMASKED features; ws: (c + 1) doubles. */
+MM3D_API int mm3d_input_masked_fwd(const float* feats, const int32_t* p2v, const int32_t* npts, int64_t n_points,
+                          int64_t n_vox, int c, int mode, const float* wb, float* out_vox, float* s_out,
+                          mm3d_stream_t stream);
+MM3D_API int mm3d_input_masked_bwd(const float* d_vox, const float* feats, const float* s, const int32_t* p2v,
+                          const int32_t* npts, int64_t n_points, int c, int mode, const float* wb, float* d_feats,
+                          float* d_wb, void* ws, size_t ws_bytes, mm3d_stream_t stream);
 MM3D_API int mm3d_output_fwd(const float* vox, const int32_t* p2v, int64_t n_points, int c, float* out,
                     mm3d_stream_t stream);
 MM3D_API int mm3d_output_bwd(const float* d_out, const int32_t* p2v, int64_t n_points, int64_t n_vox, int c,
@@ -281,15 +291,26 @@ MM3D_API size_t mm3d_unet_act_bytes(int in_channels, int m, int num_planes, int 
 MM3D_API size_t mm3d_unet_bwd_bytes(int in_channels, int m, int num_planes, int mode, const int64_t* level_desc,
                            int64_t n_points);
 MM3D_API size_t mm3d_unet_scratch_bytes(int in_channels, int m, int num_planes, int mode);
+/* Optional RGB-mask prologue (3d_net/model.py:46-48, feats *= sigmoid(linear_rgb_mask(feats))) folded into the
+ * network's InputLayer (mm3d_input_masked_fwd / _bwd); NULL = the features are used as they are.  Forward reads wb and
+ * writes s; backward reads wb, s, feats (the UNMASKED features of the forward) and writes d_wb, using ws. */
+typedef struct {
+  const float* wb;    /* [in_channels + 1] device: the Linear(in_channels, 1) weight, then its bias */
+  float* s;           /* [n_points] gates */
+  const float* feats; /* backward only */
+  float* d_wb;        /* backward only: [in_channels + 1] gradient of wb, overwritten */
+  void* ws;           /* backward only: (in_channels + 1) doubles */
+  size_t ws_bytes;
+} mm3d_unet_mask;
 MM3D_API int mm3d_unet_forward(int in_channels, int m, int num_planes, int mode, int training, float eps, float momentum,
                       const int64_t* level_desc, int64_t n_points, const int32_t* p2v, const int32_t* npts,
                       const float* feats, float* out, void* const* params, void* act, size_t act_bytes,
-                      void* scratch, size_t scratch_bytes, mm3d_stream_t stream);
+                      void* scratch, size_t scratch_bytes, const mm3d_unet_mask* mask, mm3d_stream_t stream);
 MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode, int training,
                        const int64_t* level_desc, int64_t n_points, const int32_t* p2v, const int32_t* npts,
                        const float* d_out, float* d_feats, void* const* params, void* const* grads,
                        void* act, size_t act_bytes, void* tmp, size_t tmp_bytes, void* scratch,
-                       size_t scratch_bytes, mm3d_stream_t stream);
+                       size_t scratch_bytes, const mm3d_unet_mask* mask, mm3d_stream_t stream);
 
 #ifdef __cplusplus
 }

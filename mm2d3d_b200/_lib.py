@@ -12,6 +12,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmm3d.so")
 
 ABI_VERSION = 5
+
+
+class UnetMask(C.Structure):
+    """``mm3d_unet_mask`` of ``include/mm3d.h``."""
+    _fields_ = [("wb", C.c_void_p), ("s", C.c_void_p), ("feats", C.c_void_p), ("d_wb", C.c_void_p),
+                ("ws", C.c_void_p), ("ws_bytes", C.c_size_t)]
+
 LEVEL_DESC_WORDS = 10
 
 MODE_FP32, MODE_TF32, MODE_BF16, MODE_TF32X3 = 0, 1, 2, 3
@@ -73,8 +80,10 @@ SIGNATURES = {
     "mm3d_unet_act_bytes": (_sz, [_i, _i, _i, _i, _p, _i64]),
     "mm3d_unet_bwd_bytes": (_sz, [_i, _i, _i, _i, _p, _i64]),
     "mm3d_unet_scratch_bytes": (_sz, [_i, _i, _i, _i]),
-    "mm3d_unet_forward": (_i, [_i, _i, _i, _i, _i, _f, _f, _p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p, _sz, _p]),
-    "mm3d_unet_backward": (_i, [_i, _i, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _sz, _p, _sz, _p]),
+    "mm3d_unet_forward": (_i, [_i, _i, _i, _i, _i, _f, _f, _p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p, _sz, _p, _p]),
+    "mm3d_unet_backward": (_i, [_i, _i, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _sz, _p, _sz, _p, _p]),
+    "mm3d_input_masked_fwd": (_i, [_p, _p, _p, _i64, _i64, _i, _i, _p, _p, _p, _p]),
+    "mm3d_input_masked_bwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _sz, _p]),
 }
 
 class PlanDesc(C.Structure):

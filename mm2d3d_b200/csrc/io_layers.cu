@@ -72,6 +72,93 @@ k_input_bwd(const float* __restrict__ d_vox, const int32_t* __restrict__ p2v, co
   }
 }
 
+
+// InputLayer with the RGB-mask prologue of Net3DSeg.forward (3d_net/model.py:46-48) folded in: the point's features
+// are scaled by s = sigmoid(x . w + b) on their way into the voxel row -- the masked [N, C] tensor of the reference
+// (and its three element-wise kernels) never exists.  wb = [w_0 .. w_{C-1}, b]; s_out keeps the gate for the backward.
+template <int C>
+__global__ void __launch_bounds__(256)
+k_input_masked_fwd(const float* __restrict__ feats, const int32_t* __restrict__ p2v, const int32_t* __restrict__ npts,
+                   int64_t n_points, int mode, const float* __restrict__ wb, float* __restrict__ out, float* __restrict__ s_out) {
+  mm3d_griddep_wait();
+  float w[C + 1];
+#pragma unroll
+  for (int j = 0; j <= C; ++j) w[j] = __ldg(wb + j);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_points; p += stride) {
+    const int32_t v = __ldg(p2v + p);
+    const int32_t cnt = __ldg(npts + v);
+    float f[C], acc = w[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      f[j] = __ldg(feats + p * C + j);
+      acc = fmaf(f[j], w[j], acc);
+    }
+    const float sg = 1.f / (1.f + expf(-acc));
+    s_out[p] = sg;
+    float* dst = out + (int64_t)v * C;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const float y = f[j] * sg;
+      if (cnt == 1) dst[j] = y;
+      else atomicAdd(dst + j, mode == 4 ? y / (float)cnt : y);
+    }
+  }
+}
+
+// backward of the above: g = d_vox[voxel] (/ count); t = (g . x) s (1 - s); d_feats = g s + t w; d_w += t x; d_b += t
+// (FP64 totals, one atomic per CTA and value, as in heads.cu)
+template <int C>
+__global__ void __launch_bounds__(256)
+k_input_masked_bwd(const float* __restrict__ d_vox, const float* __restrict__ feats, const float* __restrict__ s_in,
+                   const int32_t* __restrict__ p2v, const int32_t* __restrict__ npts, int64_t n_points, int mode,
+                   const float* __restrict__ wb, float* __restrict__ d_feats, double* __restrict__ dwb) {
+  mm3d_griddep_wait();
+  __shared__ double red[C + 1];
+  if (threadIdx.x <= C) red[threadIdx.x] = 0.0;
+  __syncthreads();
+  float w[C];
+#pragma unroll
+  for (int j = 0; j < C; ++j) w[j] = __ldg(wb + j);
+  double loc[C + 1];
+#pragma unroll
+  for (int j = 0; j <= C; ++j) loc[j] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_points; p += stride) {
+    const int32_t v = __ldg(p2v + p);
+    const int32_t cnt = mode == 4 ? __ldg(npts + v) : 1;
+    const float sg = __ldg(s_in + p);
+    float g[C], x[C], dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      g[j] = __ldg(d_vox + (int64_t)v * C + j);
+      if (cnt > 1) g[j] /= (float)cnt;
+      x[j] = __ldg(feats + p * C + j);
+      dot = fmaf(g[j], x[j], dot);
+    }
+    const float t = dot * sg * (1.f - sg);
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      if (d_feats) d_feats[p * C + j] = fmaf(t, w[j], g[j] * sg);
+      loc[j] += (double)(t * x[j]);
+    }
+    loc[C] += (double)t;
+  }
+#pragma unroll
+  for (int j = 0; j <= C; ++j) {
+    double vv = loc[j];
+    for (int o = 16; o; o >>= 1) vv += __shfl_xor_sync(0xffffffffu, vv, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[j], vv);
+  }
+  __syncthreads();
+  if (threadIdx.x <= C) atomicAdd(dwb + threadIdx.x, red[threadIdx.x]);
+}
+
+__global__ void k_f64_to_f32_io(const double* __restrict__ src, float* __restrict__ dst, int n) {
+  mm3d_griddep_wait();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (float)src[i];
+}
+
 // ------------------------------------------------------------------ OutputLayer
 // cv float4 per row (cv a power of two <= 32 in the vector path): cv consecutive lanes copy one point's row, a warp
 // moves 32 / cv points per pass and every thread keeps 4 passes in flight.  32-bit index arithmetic.
@@ -253,6 +340,47 @@ extern "C" int mm3d_input_bwd(const float* d_vox, const int32_t* p2v, const int3
   }
   mm3d_count_launches(n_points > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_input_bwd");
+  return MM3D_OK;
+}
+
+// InputLayer forward with the RGB mask folded in (3 feature channels: the reference's rgb features): out_vox as
+// mm3d_input_fwd of feats * sigmoid(feats . w + b); wb = [w_0, w_1, w_2, b] on the device, s_out [n_points] = the gates.
+extern "C" int mm3d_input_masked_fwd(const float* feats, const int32_t* p2v, const int32_t* npts, int64_t n_points,
+                                     int64_t n_vox, int c, int mode, const float* wb, float* out_vox, float* s_out,
+                                     mm3d_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MM3D_REQUIRE(mode == 3 || mode == 4, MM3D_ERR_UNSUPPORTED, "InputLayer mode %d not implemented (3=sum, 4=mean)", mode);
+  MM3D_REQUIRE(c == 3, MM3D_ERR_UNSUPPORTED, "masked InputLayer: 3 feature channels supported, got %d", c);
+  MM3D_REQUIRE(n_points >= 0 && n_vox >= 0 && wb && (n_points == 0 || (feats && s_out)), MM3D_ERR_INVALID, "masked InputLayer: bad arguments");
+  if (n_vox > 0) MM3D_CUDA(cudaMemsetAsync(out_vox, 0, sizeof(float) * (size_t)n_vox * c, stream));
+  if (n_points > 0) {
+    MM3D_CUDA(mm3d_launch_pdl(k_input_masked_fwd<3>, dim3(mm3d_grid(n_points, 256, 16)), dim3(256), 0, stream, feats, p2v, npts, n_points,
+                              mode, wb, out_vox, s_out));
+    mm3d_count_launches(1);
+  }
+  MM3D_CHECK_LAUNCH("mm3d_input_masked_fwd");
+  return MM3D_OK;
+}
+
+// ... and its backward: d_feats [n_points, c] (may be NULL: the features are data), d_wb [c + 1] = d_w, d_b
+// (overwritten); feats = the UNMASKED features, s = the gates of the forward; ws: (c + 1) doubles
+extern "C" int mm3d_input_masked_bwd(const float* d_vox, const float* feats, const float* s, const int32_t* p2v,
+                                     const int32_t* npts, int64_t n_points, int c, int mode, const float* wb, float* d_feats,
+                                     float* d_wb, void* ws, size_t ws_bytes, mm3d_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MM3D_REQUIRE(mode == 3 || mode == 4, MM3D_ERR_UNSUPPORTED, "InputLayer mode %d not implemented", mode);
+  MM3D_REQUIRE(c == 3, MM3D_ERR_UNSUPPORTED, "masked InputLayer: 3 feature channels supported, got %d", c);
+  MM3D_REQUIRE(d_wb && wb && ws && ws_bytes >= sizeof(double) * (size_t)(c + 1), MM3D_ERR_WORKSPACE, "masked InputLayer: workspace too small");
+  MM3D_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (size_t)(c + 1), stream));
+  if (n_points > 0) {
+    MM3D_REQUIRE(d_vox && feats && s, MM3D_ERR_INVALID, "masked InputLayer: null pointer");
+    MM3D_CUDA(mm3d_launch_pdl(k_input_masked_bwd<3>, dim3(mm3d_grid(n_points, 256, 8)), dim3(256), 0, stream, d_vox, feats, s, p2v, npts,
+                              n_points, mode, wb, d_feats, (double*)ws));
+    mm3d_count_launches(1);
+  }
+  MM3D_CUDA(mm3d_launch_pdl(k_f64_to_f32_io, dim3(1), dim3(32), 0, stream, (const double*)ws, d_wb, c + 1));
+  mm3d_count_launches(1);
+  MM3D_CHECK_LAUNCH("mm3d_input_masked_bwd");
   return MM3D_OK;
 }
 

@@ -703,7 +703,7 @@ int carve_tail(Ctx& c, const Net& net) {
 MM3D_API int mm3d_unet_forward(int in_channels, int m, int num_planes, int mode, int training, float eps, float momentum,
                                const int64_t* level_desc, int64_t n_points, const int32_t* p2v, const int32_t* npts,
                                const float* feats, float* out, void* const* params, void* act, size_t act_bytes,
-                               void* scratch, size_t scratch_bytes, mm3d_stream_t stream_) {
+                               void* scratch, size_t scratch_bytes, const mm3d_unet_mask* mask, mm3d_stream_t stream_) {
   Net net;
   int rc = fill_net(net, in_channels, m, num_planes, mode, level_desc, n_points);
   if (rc) return rc;
@@ -716,7 +716,12 @@ MM3D_API int mm3d_unet_forward(int in_channels, int m, int num_planes, int mode,
   if (rc) return rc;
   const int64_t n0 = net.lv[0].n;
   MARK("fwd start", -1);
-  EX(mm3d_input_fwd(feats, p2v, npts, n_points, n0, in_channels, 4, net.V, c.stream));
+  if (mask) {  // the RGB-mask prologue of Net3DSeg.forward folded into the point -> voxel scatter
+    MM3D_REQUIRE(mask->wb && (n_points == 0 || mask->s), MM3D_ERR_INVALID, "unet forward: incomplete mask descriptor");
+    EX(mm3d_input_masked_fwd(feats, p2v, npts, n_points, n0, in_channels, 4, mask->wb, net.V, mask->s, c.stream));
+  } else {
+    EX(mm3d_input_fwd(feats, p2v, npts, n_points, n0, in_channels, 4, net.V, c.stream));
+  }
   MARK("input_fwd", -1);
   const float* w_stem = P(c, 0);
   if (net.Vp != net.V)  // pad the stem input to whole 64-byte pieces; rounded to TF32 (+ lo plane in TF32x3 mode)
@@ -749,7 +754,7 @@ MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode
                                 const int64_t* level_desc, int64_t n_points, const int32_t* p2v, const int32_t* npts,
                                 const float* d_out, float* d_feats, void* const* params, void* const* grads,
                                 void* act, size_t act_bytes, void* tmp, size_t tmp_bytes, void* scratch,
-                                size_t scratch_bytes, mm3d_stream_t stream_) {
+                                size_t scratch_bytes, const mm3d_unet_mask* mask, mm3d_stream_t stream_) {
   Net net;
   int rc = fill_net(net, in_channels, m, num_planes, mode, level_desc, n_points);
   if (rc) return rc;
@@ -813,21 +818,32 @@ MM3D_API int mm3d_unet_backward(int in_channels, int m, int num_planes, int mode
   // stem
   const float* w_stem = P(c, 0);
   float* d_w = Gp(c, 0);
-  float* d_Vp = d_feats ? g.f(n0, net.cin_k) : nullptr;
+  if (mask)
+    MM3D_REQUIRE(mask->wb && mask->d_wb && mask->ws && (n_points == 0 || (mask->s && mask->feats)), MM3D_ERR_INVALID,
+                 "unet backward: incomplete mask descriptor");
+  const bool need_dv = d_feats || mask;  // (the mask parameters get their gradient through the InputLayer)
+  float* d_Vp = need_dv ? g.f(n0, net.cin_k) : nullptr;
+  auto input_bwd = [&](const float* d_v) {
+    if (mask)
+      EX(mm3d_input_masked_bwd(d_v, mask->feats, mask->s, p2v, npts, n_points, net.cin, 4, mask->wb, d_feats, mask->d_wb,
+                               mask->ws, mask->ws_bytes, c.stream));
+    else
+      EX(mm3d_input_bwd(d_v, p2v, npts, n_points, net.cin, 4, d_feats, c.stream));
+  };
   if (net.cin_k != net.cin) {
     float* wp = wp_buf;  // padded at the start of this call
     float* d_wp = d_w ? g.f(27, (int64_t)net.cin_k * m) : nullptr;  // (frozen stem weight: no gradient)
     conv_bwd(c, SMC, 0, net.Vp, net.cin_k, d_X0, m, wp, d_Vp, d_wp);
     join_side(c);  // d_wp comes from the side stream
     if (d_w) launch_pad_cols(c, d_wp, 27, net.cin_k * m, d_w, net.cin * m);  // slice the real channels back out
-    if (d_feats) {
+    if (need_dv) {
       float* d_V = g.f(n0, net.cin);
       launch_pad_cols(c, d_Vp, n0, net.cin_k, d_V, net.cin);
-      EX(mm3d_input_bwd(d_V, p2v, npts, n_points, net.cin, 4, d_feats, c.stream));
+      input_bwd(d_V);
     }
   } else {
     conv_bwd(c, SMC, 0, net.Vp, net.cin, d_X0, m, w_stem, d_Vp, d_w);
-    if (d_feats) EX(mm3d_input_bwd(d_Vp, p2v, npts, n_points, net.cin, 4, d_feats, c.stream));
+    if (need_dv) input_bwd(d_Vp);
   }
   MARK("stem bwd + input_bwd", -1);
   join_side(c);  // everything after this call on `stream` sees the weight gradients

@@ -107,10 +107,14 @@ def _level_desc(meta: Metadata, num_planes: int, spatial0: int, plans: bool):
 
 class UNetSCNFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feats, meta, cfg, *slots):
+    def forward(ctx, feats, meta, cfg, mask_w, mask_b, *slots):
         in_ch, m, L, mode, training, eps, momentum, spatial0 = cfg
         feats = feats.float().contiguous()
         dev = feats.device
+        # optional RGB mask of Net3DSeg.forward (3d_net/model.py:46-48), folded into the InputLayer scatter
+        masked = mask_w is not None
+        if masked and (mask_w.numel() != in_ch or mask_b is None or mask_b.numel() != 1):
+            raise ValueError("UNetSCN: rgb_mask must be the weight [1, C] and bias [1] of an nn.Linear(C, 1)")
         n_points = meta.n_points
         desc = _level_desc(meta, L, spatial0, plans=mode != _lib.MODE_FP32)
         with torch.cuda.device(dev):
@@ -122,11 +126,17 @@ class UNetSCNFn(torch.autograd.Function):
             scr = F.scratch(lib.mm3d_unet_scratch_bytes(in_ch, m, L, mode), dev)
             out = torch.empty(n_points, m, dtype=torch.float32, device=dev)
             params = (C.c_void_p * len(slots))(*[t.data_ptr() for t in slots])
+            mask, wb, gate = None, None, None
+            if masked:
+                wb = torch.cat([mask_w.detach().reshape(-1), mask_b.detach().reshape(-1)]).float().contiguous()
+                gate = torch.empty(max(n_points, 1), dtype=torch.float32, device=dev)
+                mask = C.byref(_lib.UnetMask(wb.data_ptr(), gate.data_ptr(), None, None, None, 0))
             check(lib.mm3d_unet_forward(in_ch, m, L, mode, int(training), eps, momentum, desc, n_points, meta.p2v_ptr,
                                         meta.npts_ptr, feats.data_ptr(), out.data_ptr(), params, act.data_ptr(), act_bytes,
-                                        scr.data_ptr(), scr.numel(), _lib.stream_ptr()), "mm3d_unet_forward")
+                                        scr.data_ptr(), scr.numel(), mask, _lib.stream_ptr()), "mm3d_unet_forward")
         ctx.meta, ctx.cfg, ctx.desc, ctx.act, ctx.slots = meta, cfg, desc, act, slots
         ctx.feats_shape = feats.shape
+        ctx.mask = (feats, wb, gate, mask_w.shape, mask_b.shape) if masked else None
         return out
 
     @staticmethod
@@ -161,11 +171,19 @@ class UNetSCNFn(torch.autograd.Function):
             scr = F.scratch(lib.mm3d_unet_scratch_bytes(in_ch, m, L, mode), dev)
             params = (C.c_void_p * len(slots))(*[t.data_ptr() for t in slots])
             gp = (C.c_void_p * len(slots))(*gptrs)
+            mask, d_mw, d_mb = None, None, None
+            if ctx.mask is not None:
+                feats, wb, gate, w_shape, b_shape = ctx.mask
+                d_wb = torch.empty(in_ch + 1, dtype=torch.float32, device=dev)
+                mws = torch.empty(in_ch + 1, dtype=torch.float64, device=dev)
+                mask = C.byref(_lib.UnetMask(wb.data_ptr(), gate.data_ptr(), feats.data_ptr(), d_wb.data_ptr(), mws.data_ptr(),
+                                             mws.numel() * 8))
+                d_mw, d_mb = d_wb[:in_ch].reshape(w_shape), d_wb[in_ch:].reshape(b_shape)
             check(lib.mm3d_unet_backward(in_ch, m, L, mode, int(training), desc, n_points, meta.p2v_ptr, meta.npts_ptr,
                                          d_out.data_ptr(), d_feats.data_ptr() if need_feats else None, params, gp,
                                          act.data_ptr(), act.numel(), tmp.data_ptr(), tmp_bytes, scr.data_ptr(),
-                                         scr.numel(), _lib.stream_ptr()), "mm3d_unet_backward")
-        return (d_feats, None, None, *grads)
+                                         scr.numel(), mask, _lib.stream_ptr()), "mm3d_unet_backward")
+        return (d_feats, None, None, d_mw, d_mb, *grads)
 
 
 class PreparedScans:
@@ -200,7 +218,7 @@ def prepare(net, coords, wait=False):
         return PreparedScans(meta, F.DEFAULT_MODE, spatial0, L)
 
 
-def run(net, coords, feats):
+def run(net, coords, feats, rgb_mask=None):
     if not feats.is_cuda:
         raise RuntimeError("UNetSCN: features must be a CUDA tensor -- mm2d3d_b200 has no CPU path")
     spatial0 = int(net.layer1.spatial_size[0])
@@ -223,5 +241,6 @@ def run(net, coords, feats):
     bn0 = net.layer4
     cfg = (net.in_channels, net.out_channels, L, _lib.MODES[F.DEFAULT_MODE], bool(net.training), float(bn0.eps),
            float(bn0.momentum), spatial0)
+    mask_w, mask_b = rgb_mask if rgb_mask is not None else (None, None)
     with torch.autocast("cuda", enabled=False):
-        return UNetSCNFn.apply(feats, meta, cfg, *collect_slots(net))
+        return UNetSCNFn.apply(feats, meta, cfg, mask_w, mask_b, *collect_slots(net))

@@ -17,6 +17,7 @@ reference network, the default is the CUDA implementation in ``mm2d3d_b200.scn``
 """
 from __future__ import annotations
 
+import torch
 import torch.nn as nn
 
 DIMENSION = 3
@@ -104,12 +105,24 @@ class UNetSCN(nn.Module):
             raise RuntimeError("UNetSCN.prepare needs the fused executor (native backend, fused=True)")
         return executor.prepare(self, coords, wait)
 
-    def forward(self, x):
+    def forward(self, x, rgb_mask=None):
+        """``x = [coords, feats]`` as in the reference.  ``rgb_mask``: an ``nn.Linear(in_channels, 1)`` (or its
+        ``(weight, bias)``) -- the prologue of ``Net3DSeg.forward`` (``3d_net/model.py:46-48``,
+        ``feats *= sigmoid(linear_rgb_mask(feats))``): the executor folds it into the InputLayer scatter, so that
+        ``net_3d(data_batch["x"], rgb_mask=self.linear_rgb_mask)`` replaces the three lines and the call."""
+        if rgb_mask is not None and not isinstance(rgb_mask, (tuple, list)):
+            rgb_mask = (rgb_mask.weight, rgb_mask.bias)
         if self.fused and self._native:
             from . import executor
-            if executor.fusable(self):
+            if executor.fusable(self) and (rgb_mask is None or self.in_channels == 3):
                 # whole forward (and backward) as one native call each: csrc/unet_exec.cu
-                return executor.run(self, x[0], x[1])
+                return executor.run(self, x[0], x[1], rgb_mask)
+        if rgb_mask is not None:  # module-by-module path (or the oracle backend): the prologue as its own op
+            if self._native:
+                from .heads import rgb_mask as _mask
+                x = [x[0], _mask(x[1], rgb_mask[0], rgb_mask[1])]
+            else:
+                x = [x[0], x[1] * torch.sigmoid(torch.nn.functional.linear(x[1], rgb_mask[0], rgb_mask[1]))]
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4, self.layer5):
             x = layer(x)
         return x
