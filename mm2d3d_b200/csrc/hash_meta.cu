@@ -216,33 +216,30 @@ __global__ void k_ids_coarsen(const int32_t* __restrict__ item_slot, const int32
   }
 }
 
-// ---- 3^3 neighbour table, offset-major: one thread per (k, row), rows fastest => coalesced
+// ---- 3^3 neighbour table, offset-major: one thread per (k, row), rows fastest => coalesced.  The table is symmetric
+// (row j is the neighbour of row i at offset k exactly when i is the neighbour of j at offset 26 - k), so only the
+// offsets 0..12 are probed: a hit also writes the mirrored entry, and the mirrored half is pre-filled with -1 by the
+// launch's memset -- 13 hash probes per voxel instead of 26.  blockIdx.y = k: no 64-bit division per entry.
 __global__ void k_nbr27(const uint64_t* __restrict__ keys, const int32_t* __restrict__ n_dev, int spatial,
                         const uint64_t* __restrict__ hash_keys, const int32_t* __restrict__ hash_vals,
                         const int32_t* __restrict__ hash_mask_dev, int32_t* __restrict__ tbl, int64_t tbl_stride) {
   mm3d_griddep_wait();  // programmatic dependent launch: the previous kernel's writes are visible from here
   const int64_t n = *n_dev;
   const uint32_t mask = (uint32_t)*hash_mask_dev;
-  const int64_t total = 27 * n;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(idx / n);
-    const int64_t row = idx - (int64_t)k * n;
-    const uint64_t key = __ldg(keys + row);
-    int32_t r;
+  const int k = (int)blockIdx.y;  // 0..13
+  const int dx = k / 9 - 1, dy = (k / 3) % 3 - 1, dz = k % 3 - 1;
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
     if (k == 13) {
-      r = (int32_t)row;
-    } else {
-      const int x = mm3d_key_x(key) + k / 9 - 1;
-      const int y = mm3d_key_y(key) + (k / 3) % 3 - 1;
-      const int z = mm3d_key_z(key) + k % 3 - 1;
-      if ((unsigned)x >= (unsigned)spatial || (unsigned)y >= (unsigned)spatial || (unsigned)z >= (unsigned)spatial)
-        r = -1;
-      else
-        r = mm3d_hash_find(hash_keys, hash_vals, mask,
-                           mm3d_pack_key((uint64_t)x, (uint64_t)y, (uint64_t)z, mm3d_key_b(key)));
+      tbl[(int64_t)13 * tbl_stride + row] = (int32_t)row;
+      continue;
     }
+    const uint64_t key = __ldg(keys + row);
+    const int x = mm3d_key_x(key) + dx, y = mm3d_key_y(key) + dy, z = mm3d_key_z(key) + dz;
+    int32_t r = -1;
+    if ((unsigned)x < (unsigned)spatial && (unsigned)y < (unsigned)spatial && (unsigned)z < (unsigned)spatial)
+      r = mm3d_hash_find(hash_keys, hash_vals, mask, mm3d_pack_key((uint64_t)x, (uint64_t)y, (uint64_t)z, mm3d_key_b(key)));
     tbl[(int64_t)k * tbl_stride + row] = r;
+    if (r >= 0) tbl[(int64_t)(26 - k) * tbl_stride + r] = (int32_t)row;  // (r, 26 - k) is unique: no race
   }
 }
 
@@ -355,9 +352,12 @@ extern "C" int mm3d_build_nbr27(const uint64_t* keys, const int32_t* n_dev, int6
   cudaStream_t stream = (cudaStream_t)stream_;
   MM3D_REQUIRE(tbl_stride >= n_cap, MM3D_ERR_INVALID, "tbl_stride must be >= n_cap");
   MM3D_REQUIRE(spatial_size > 0 && spatial_size <= 65536, MM3D_ERR_INVALID, "spatial_size must be in (0, 65536]");
-  if (n_cap > 0)
-    MM3D_CUDA(mm3d_launch_pdl(k_nbr27, dim3(mm3d_grid(27 * n_cap, 256)), dim3(256), 0, stream, keys, n_dev, spatial_size, hash_keys, hash_vals,
-                                                           hash_vals + (hash_cap - 1), nbr_tbl, tbl_stride));
+  if (n_cap > 0) {
+    // the mirrored half (offsets 14..26) starts as "no neighbour"; hits of the probed half fill it in
+    MM3D_CUDA(cudaMemsetAsync(nbr_tbl + 14 * tbl_stride, 0xFF, sizeof(int32_t) * (size_t)13 * tbl_stride, stream));
+    MM3D_CUDA(mm3d_launch_pdl(k_nbr27, dim3(mm3d_grid(n_cap, 256, 8), 14), dim3(256), 0, stream, keys, n_dev, spatial_size, hash_keys,
+                              hash_vals, hash_vals + (hash_cap - 1), nbr_tbl, tbl_stride));
+  }
   mm3d_count_launches(n_cap > 0 ? 1 : 0);
   MM3D_CHECK_LAUNCH("mm3d_build_nbr27");
   return MM3D_OK;
