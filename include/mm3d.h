@@ -40,10 +40,11 @@ extern "C" {
 #define MM3D_MODE_FP32 0 /* SIMT FP32 FMA -- the parity mode (1e-4) */
 #define MM3D_MODE_TF32 1 /* tcgen05 kind::tf32, FP32 accumulate in TMEM (1e-2) */
 #define MM3D_MODE_BF16 2 /* tcgen05 kind::f16 with BF16 gathered operands and weights, FP32 accumulate (1e-2 per
-                          * op): forward and dgrad gather half the bytes of the TF32 mode.  The gathered operand (`in` of
-                          * mm3d_conv_fwd) carries an FP32 plane of [rows, c] floats (TF32-rounded values) and, rows * c
-                          * floats behind it, a BF16 plane of [rows, c] bfloat16 (mm3d_split_bf16).  mm3d_conv_wgrad runs
-                          * the TF32 kernel on the FP32 planes of `in` and `d_out` */
+                          * op): forward, dgrad and weight gradient move half the bytes of the TF32 mode.  The gathered
+                          * operands (`in` of mm3d_conv_fwd; `in` and `d_out` of mm3d_conv_wgrad) carry an FP32 plane of
+                          * [rows, c] floats (TF32-rounded values) and, rows * c floats behind it, a BF16 plane of
+                          * [rows, c] bfloat16 (mm3d_split_bf16).  mm3d_conv_wgrad reads the BF16 planes for c_in <= 128
+                          * and falls back to the TF32 kernel on the FP32 planes above that */
 #define MM3D_MODE_TF32X3 3 /* tcgen05, three error-compensated TF32 products (hi.hi + lo.hi + hi.lo), FP32 accumulate:
                             * FP32-grade results (1e-4 bar) on the tensor cores.  The gathered operands (`in` of
                             * mm3d_conv_fwd; `in` and `d_out` of mm3d_conv_wgrad) carry TWO planes of [rows, c] floats,

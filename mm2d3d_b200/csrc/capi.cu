@@ -50,7 +50,7 @@ int mm3d_conv_tc_supported(int c_in, int c_out, int K);
 int mm3d_conv_wgrad_tc_supported(int c_in, int c_out, int K);
 int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_out, int64_t n_out, int c_out,
                        float* d_weight, int K, const void* plan, int64_t plan_cap, int accumulate,
-                       cudaStream_t stream);
+                       cudaStream_t stream, int bf16 = 0);
 int mm3d_conv_fwd_tc(const float* in, int64_t n_in, int c_in, float* out, int64_t n_out, int c_out,
                      const float* weight, int K, const void* plan, int64_t plan_cap, int flags, void* ws,
                      size_t ws_bytes, cudaStream_t stream);
@@ -131,7 +131,15 @@ extern "C" int mm3d_conv_wgrad(const float* in, int64_t n_in, int c_in, const fl
       if (!rc) rc = mm3d_conv_wgrad_tc(in, n_in, c_in, dout_lo, n_out, c_out, d_weight, K, plan, plan_cap, 1, (cudaStream_t)stream);
       return rc;
     }
-    case MM3D_MODE_BF16:  // the weight gradient of the BF16 mode is the TF32 one, on the operands' FP32 planes
+    case MM3D_MODE_BF16:
+      // BF16 planes of both operands (behind the FP32 ones) where the two-ring kernel takes the shape (c_in <= 128);
+      // otherwise the TF32 kernel on the FP32 planes
+      if (plan && mm3d_conv_wgrad_tc_supported(c_in, c_out, K) && n_out > 0) {
+        rc = mm3d_conv_wgrad_tc(in + n_in * (int64_t)c_in, n_in, c_in, d_out + n_out * (int64_t)c_out, n_out, c_out, d_weight, K,
+                                plan, plan_cap, accumulate, (cudaStream_t)stream, 1);
+        if (rc != MM3D_ERR_UNSUPPORTED) return rc;
+      }
+      // fall through
     case MM3D_MODE_TF32:
       if (mm3d_conv_wgrad_tc_supported(c_in, c_out, K)) {
         MM3D_REQUIRE(plan, MM3D_ERR_INVALID, "mm3d_conv_wgrad: tf32 mode needs the table's row plan (mm3d_build_plan)");

@@ -58,6 +58,7 @@ struct WgParams {
   int num_tiles, tmem_cols;
   int n_local;      // tiles per CTA (upper bound: every group gets at least ceil(num_tiles / n_local) CTAs)
   int max_items;    // two-ring variant: capacity of one ring's item list
+  int bf16;         // two-ring variant: `in` / `dout` are BF16 planes (64 channels per 128-byte block), kind::f16 MMAs of K = 16 rows
   int groups;       // offset groups; group g owns the offsets of gmask[g]; its CTAs are decided in the kernel
   uint32_t gmask[32];
   int* err;
@@ -659,7 +660,9 @@ k_wgrad_tc_rings(const WgParams p) {
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(ent + (uint32_t)(32 * r + lane) * 4u), "r"(e[r]) : "memory");
       __syncwarp();
       for (int jb = 0; jb < p.nbi; ++jb) {
-        if (jb == p.nbi - 1 && p.last_w == 4) gather_block<4, true>(stage + (uint32_t)jb * kBlockBytes, ent, p.in, p.in + jb * 32, (uint32_t)p.c_in, lane);
+        // (BF16: plain 128-byte swizzle, rows of c_in / 2 four-byte units, the last block's missing chunks zero-filled)
+        if (p.bf16) gather_block<8, false>(stage + (uint32_t)jb * kBlockBytes, ent, p.in, p.in + jb * 32, (uint32_t)p.c_in >> 1, lane, jb == p.nbi - 1 ? p.last_w : 8);
+        else if (jb == p.nbi - 1 && p.last_w == 4) gather_block<4, true>(stage + (uint32_t)jb * kBlockBytes, ent, p.in, p.in + jb * 32, (uint32_t)p.c_in, lane);
         else gather_block<8, true>(stage + (uint32_t)jb * kBlockBytes, ent, p.in, p.in + jb * 32, (uint32_t)p.c_in, lane);
       }
       cp_async_arrive(a_full(warp));
@@ -690,7 +693,8 @@ k_wgrad_tc_rings(const WgParams p) {
       __syncwarp();
       const uint32_t gb = g_base + (uint32_t)buf * g_bytes;
       for (int jb = 0; jb < p.gblocks; ++jb) {
-        if (jb == p.gblocks - 1 && p.g_last_w == 4) gather_block<4, true>(gb + (uint32_t)jb * kBlockBytes, ent, p.dout, p.dout + jb * 32, (uint32_t)p.c_out, lane);
+        if (p.bf16) gather_block<8, false>(gb + (uint32_t)jb * kBlockBytes, ent, p.dout, p.dout + jb * 32, (uint32_t)p.c_out >> 1, lane, jb == p.gblocks - 1 ? p.g_last_w : 8);
+        else if (jb == p.gblocks - 1 && p.g_last_w == 4) gather_block<4, true>(gb + (uint32_t)jb * kBlockBytes, ent, p.dout, p.dout + jb * 32, (uint32_t)p.c_out, lane);
         else gather_block<8, true>(gb + (uint32_t)jb * kBlockBytes, ent, p.dout, p.dout + jb * 32, (uint32_t)p.c_out, lane);
       }
       cp_async_arrive(g_full(buf));
@@ -737,8 +741,10 @@ k_wgrad_tc_rings(const WgParams p) {
     const int m = warp - 12;
     const uint16_t* list = items + (size_t)m * p.max_items;
     const uint32_t* fst = first + m * (p.n_local + 1);
-    const uint32_t idesc = make_idesc_tf32(p.mm, p.c_out, 1, 1);
-    const uint64_t desc0 = make_desc_sw128_base32(0, kBlockBytes, 512);
+    // TF32: MN-major operands need the 32-byte-granule swizzle (4-row atoms, 8 rows = 1024 bytes per K-step);
+    // BF16: the plain 128-byte swizzle (8-row atoms, K = 16 rows = 2048 bytes per instruction)
+    const uint32_t idesc = p.bf16 ? make_idesc_bf16(p.mm, p.c_out, 1, 1) : make_idesc_tf32(p.mm, p.c_out, 1, 1);
+    const uint64_t desc0 = p.bf16 ? make_desc_sw128(0, kBlockBytes, 1024) : make_desc_sw128_base32(0, kBlockBytes, 512);
     uint32_t seen = 0;
     bool ok = true;
     for (int t = 0; t < ne && ok; ++t) {
@@ -755,9 +761,15 @@ k_wgrad_tc_rings(const WgParams p) {
         if (elect_one()) {
           const uint64_t a_desc = desc0 + desc_addr(a_base + (uint32_t)s * a_bytes);
           const uint32_t d_tmem = tmem_base + (uint32_t)(__popc(gmask & ((1u << k) - 1u)) * p.c_out);
-          umma_tf32(d_tmem, a_desc, g_desc, idesc, (seen >> k) & 1u);
+          if (p.bf16) {
+            umma_f16(d_tmem, a_desc, g_desc, idesc, (seen >> k) & 1u);
 #pragma unroll
-          for (int r8 = 1; r8 < 16; ++r8) umma_tf32(d_tmem, a_desc + r8 * 64, g_desc + r8 * 64, idesc, 1u);
+            for (int r16 = 1; r16 < 8; ++r16) umma_f16(d_tmem, a_desc + r16 * 128, g_desc + r16 * 128, idesc, 1u);
+          } else {
+            umma_tf32(d_tmem, a_desc, g_desc, idesc, (seen >> k) & 1u);
+#pragma unroll
+            for (int r8 = 1; r8 < 16; ++r8) umma_tf32(d_tmem, a_desc + r8 * 64, g_desc + r8 * 64, idesc, 1u);
+          }
           umma_commit(a_empty(s));
         }
         __syncwarp();
@@ -803,9 +815,11 @@ int mm3d_conv_wgrad_tc_supported(int c_in, int c_out, int K) {
   return nmb * c_out <= 512;
 }
 
+// bf16 != 0: `in` / `d_out` point at BF16 planes ([rows, c] bfloat16); only shapes the two-ring kernel takes
+// (c_in <= 128), MM3D_ERR_UNSUPPORTED otherwise (the caller then runs the TF32 kernel on the FP32 planes)
 int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_out, int64_t n_out, int c_out,
                        float* d_weight, int K, const void* plan, int64_t plan_cap, int accumulate,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int bf16) {
   MM3D_REQUIRE(mm3d_conv_wgrad_tc_supported(c_in, c_out, K), MM3D_ERR_UNSUPPORTED,
                "tcgen05 wgrad: unsupported shape c_in %d c_out %d K %d", c_in, c_out, K);
   MM3D_REQUIRE(n_out < (1ll << 31) && n_in * (int64_t)c_in < (1ll << 32) && n_out * (int64_t)c_out < (1ll << 32),
@@ -823,11 +837,20 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
   p.c_in = c_in; p.c_out = c_out; p.K = K;
   p.nmb = c_in > 128 ? 2 : 1;
   p.cm = c_in / p.nmb;
-  p.nbi = (p.cm + 31) / 32;
-  p.last_w = (p.cm % 32) == 16 ? 4 : 8;
+  p.bf16 = bf16;
+  if (bf16) {
+    if (p.nmb != 1 || getenv("MM3D_WGRAD_NO_BF16")) return MM3D_ERR_UNSUPPORTED;  // (quietly: the caller falls back)
+    p.nbi = (p.cm + 63) / 64;
+    p.last_w = (p.cm % 64) ? (p.cm % 64) / 8 : 8;
+    p.gblocks = (c_out + 63) / 64;
+    p.g_last_w = (c_out % 64) ? (c_out % 64) / 8 : 8;
+  } else {
+    p.nbi = (p.cm + 31) / 32;
+    p.last_w = (p.cm % 32) == 16 ? 4 : 8;
+    p.gblocks = (c_out + 31) / 32;
+    p.g_last_w = (c_out % 32) == 16 ? 4 : 8;
+  }
   p.mm = p.cm <= 64 ? 64 : 128;
-  p.gblocks = (c_out + 31) / 32;
-  p.g_last_w = (c_out % 32) == 16 ? 4 : 8;
   p.num_tiles = (int)mm3d_cdiv(n_out, kTileM);
   int gk = 512 / (c_out * p.nmb);  // TMEM: c_out accumulator columns per (offset, M-block)
   if (gk > K) gk = K;
@@ -904,6 +927,7 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
   int ring_nbi = 1;
   if (const char* e = getenv("MM3D_WGRAD_RINGS_NBI")) ring_nbi = atoi(e);
   const int all_tiles = p.num_tiles;
+  if (bf16) ring_nbi = 2;
   if (p.nmb == 1 && p.nbi <= ring_nbi) {
     static bool once_r[64] = {false};
     bool& once2 = once_r[mm3d_device_slot()];
@@ -943,6 +967,7 @@ int mm3d_conv_wgrad_tc(const float* in, int64_t n_in, int c_in, const float* d_o
       return MM3D_OK;
     }
   }
+  if (bf16) return MM3D_ERR_UNSUPPORTED;
   // The kernel keeps the list of a CTA's tiles (index + mask, 8 bytes each) in shared memory.  Row counts whose list
   // does not fit next to the stages are processed in several launches over consecutive pieces of the plan's tile
   // order (the kernel only ever adds into d_weight, so the pieces simply accumulate).

@@ -29,8 +29,8 @@ __all__ = [
 def set_conv_mode(mode: str) -> None:
     """Arithmetic of the sparse convolutions: "fp32" (SIMT FMA, the parity mode), "tf32" (tcgen05, 1e-2), "tf32x3"
     (tcgen05 with three error-compensated TF32 products: FP32-grade results, 1e-4) or "bf16" (tcgen05 kind::f16 on
-    BF16 copies of the gathered operands and weights in forward and dgrad, FP32 accumulate, TF32 weight gradients:
-    1e-2 per op)."""
+    BF16 copies of the gathered operands and weights in forward, dgrad and -- up to 128 input channels -- the weight
+    gradient, FP32 accumulate: 1e-2 per op)."""
     if mode not in _lib.MODES:
         raise ValueError(f"unknown mode {mode!r}; expected one of {sorted(_lib.MODES)}")
     F.DEFAULT_MODE = mode
