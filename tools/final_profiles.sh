@@ -17,6 +17,7 @@ cap() {  # name kernel-regex args...
     python tools/run_conv_layer.py "$@" --reps 4 > $O/$name.log 2>&1
 }
 cap r2f_wgrad_L2_96x48 k_wgrad_tc --kind smc --level 2 --cin 96 --cout 48 --dir wgrad
+cap r2f_wgrad_L1_64x32 k_wgrad_tc --kind smc --level 1 --cin 64 --cout 32 --dir wgrad
 cap r2f_wgrad_rings_L0_32x16 k_wgrad_tc_rings --kind smc --level 0 --cin 32 --cout 16 --dir wgrad
 cap r2f_conv_tc_L0_16x16 k_conv_tc --kind smc --level 0 --cin 16 --cout 16 --dir fwd
 cap r2f_conv_tc_L2_96x48 k_conv_tc --kind smc --level 2 --cin 96 --cout 48 --dir fwd
