@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MM3D_ABI_VERSION 5
+#define MM3D_ABI_VERSION 6
 
 #define MM3D_OK 0
 #define MM3D_ERR_INVALID 1     /* bad argument */
@@ -86,6 +86,7 @@ MM3D_API int mm3d_take_device_error(void);
  * are capacities (upper bounds).  status_dev is OR-ed with MM3D_STATUS_* bits.
  * ---------------------------------------------------------------------------------------- */
 #define MM3D_STATUS_BAD_COORD 1 /* a coordinate outside [0, spatial_size) or batch outside [0, 32768) */
+#define MM3D_STATUS_DROPPED 2   /* mm3d_voxelize_points: a point fell outside the receptive field (see there) */
 
 /* number of hash slots needed for up to n keys (power of two, load <= 0.5) */
 MM3D_API int64_t mm3d_hash_capacity(int64_t n);
@@ -155,6 +156,21 @@ MM3D_API size_t mm3d_scale_points_workspace_bytes(int B);
 MM3D_API int mm3d_scale_points(const float* points, const int64_t* sample_offsets, int B, int64_t n, const float* rot,
                       float scale, int full_scale, const double* transl_u, int64_t* coords, uint8_t* keep,
                       float* min_value, double* offset, void* ws, size_t ws_bytes, mm3d_stream_t stream);
+
+/* The two steps above in one: raw float points straight into the voxel hash -- the reference's
+ * augment_and_scale_3d + cast + filter (same files/lines as mm3d_scale_points, same device arithmetic) feeding
+ * scn.InputLayer(3, full_scale, mode) (3d_net/scn_unet.py:108), without the int64 [n,4] coordinate tensor in between.
+ * Arguments as in mm3d_scale_points (no coords output) followed by those of mm3d_voxelize (spatial size = full_scale).
+ * The reference drops points outside [0, full_scale)^3 BEFORE the collate; when any point of the batch is outside,
+ * MM3D_STATUS_DROPPED is OR-ed into *status_dev, keep[] marks the survivors and the structure built here must be
+ * discarded: rebuild with mm3d_scale_points + mm3d_voxelize on the kept points (mm2d3d_b200.augment does). */
+MM3D_API size_t mm3d_voxelize_points_workspace_bytes(int64_t n, int B);
+MM3D_API int mm3d_voxelize_points(const float* points, const int64_t* sample_offsets, int B, int64_t n_points,
+                         const float* rot, float scale, int full_scale, const double* transl_u,
+                         uint8_t* keep, float* min_value, double* offset,
+                         uint64_t* hash_keys, int32_t* hash_vals, int64_t hash_cap,
+                         int32_t* p2v, uint64_t* vox_keys, int32_t* npts, int32_t* n_vox_dev,
+                         int32_t* status_dev, void* ws, size_t ws_bytes, mm3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * I/O layers (replace SCN InputLayer_updateOutput/updateGradInput, OutputLayer_*).

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmm3d.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class UnetMask(C.Structure):
@@ -25,6 +25,7 @@ MODE_FP32, MODE_TF32, MODE_BF16, MODE_TF32X3 = 0, 1, 2, 3
 MODES = {"fp32": MODE_FP32, "tf32": MODE_TF32, "bf16": MODE_BF16, "tf32x3": MODE_TF32X3}
 CONV_TRANSPOSE_W, CONV_MIRROR_K = 1, 2
 STATUS_BAD_COORD = 1
+STATUS_DROPPED = 2
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -50,6 +51,8 @@ SIGNATURES = {
     "mm3d_build_nbr27": (_i, [_p, _p, _i64, _i, _p, _p, _i64, _p, _i64, _p]),
     "mm3d_scale_points_workspace_bytes": (_sz, [_i]),
     "mm3d_scale_points": (_i, [_p, _p, _i, _i64, _p, _f, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mm3d_voxelize_points_workspace_bytes": (_sz, [_i64, _i]),
+    "mm3d_voxelize_points": (_i, [_p, _p, _i, _i64, _p, _f, _i, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mm3d_input_fwd": (_i, [_p, _p, _p, _i64, _i64, _i, _i, _p, _p]),
     "mm3d_input_bwd": (_i, [_p, _p, _p, _i64, _i, _i, _p, _p]),
     "mm3d_output_fwd": (_i, [_p, _p, _i64, _i, _p, _p]),

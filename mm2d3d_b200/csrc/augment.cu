@@ -13,37 +13,9 @@
 // parts (min / max reductions, scaling, cast, filter) run here.  Arithmetic follows numpy's float32 / float64
 // promotion step by step; the only step whose rounding is not pinned by numpy is the dot product (BLAS): it is
 // evaluated as fma(p2, R2j, fma(p1, R1j, p0 * R0j)).  HBM-bound: 12 B read + 33 B written per point, two passes.
-#include "common.cuh"
+#include "augment.cuh"
 
 namespace {
-
-// order-preserving map float -> uint32 so that atomicMin / atomicMax work on floats
-__device__ __forceinline__ uint32_t f2o(float f) {
-  const uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float o2f(uint32_t o) {
-  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
-}
-
-__device__ __forceinline__ void rotate_scale(const float* __restrict__ p, const float* __restrict__ R, float scale,
-                                             float (&c)[3]) {
-  const float p0 = __ldg(p), p1 = __ldg(p + 1), p2 = __ldg(p + 2);
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const float r = __fmaf_rn(p2, R[6 + j], __fmaf_rn(p1, R[3 + j], __fmul_rn(p0, R[j])));
-    c[j] = __fmul_rn(r, scale);
-  }
-}
-
-__device__ __forceinline__ int sample_of(const int64_t* __restrict__ offs, int B, int64_t i) {
-  int lo = 0, hi = B - 1;  // last sample whose first point is <= i
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (__ldg(offs + mid) <= i) lo = mid; else hi = mid - 1;
-  }
-  return lo;
-}
 
 __global__ void k_init_minmax(uint32_t* __restrict__ mm, int B) {
   mm3d_griddep_wait();
@@ -55,17 +27,17 @@ __global__ void k_minmax(const float* __restrict__ pts, const int64_t* __restric
                          const float* __restrict__ rot, float scale, uint32_t* __restrict__ mm) {
   mm3d_griddep_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int b = sample_of(offs, B, i);
+    const int b = mm3d_sample_of(offs, B, i);
     float R[9], c[3];
 #pragma unroll
     for (int q = 0; q < 9; ++q) R[q] = __ldg(rot + 9 * b + q);
-    rotate_scale(pts + 3 * i, R, scale, c);
+    mm3d_rotate_scale(pts + 3 * i, R, scale, c);
     // one atomic per warp and component where the whole warp is in one sample (the common case)
     const int b0 = __shfl_sync(__activemask(), b, __ffs(__activemask()) - 1);
     const bool uniform = __all_sync(__activemask(), b == b0);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      uint32_t lo = f2o(c[j]), hi = lo;
+      uint32_t lo = mm3d_f2o(c[j]), hi = lo;
       if (uniform) {
         lo = __reduce_min_sync(__activemask(), lo);
         hi = __reduce_max_sync(__activemask(), hi);
@@ -87,42 +59,25 @@ __global__ void k_coords(const float* __restrict__ pts, const int64_t* __restric
                          float* __restrict__ min_value, double* __restrict__ offset) {
   mm3d_griddep_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int b = sample_of(offs, B, i);
-    float R[9], c[3];
-#pragma unroll
-    for (int q = 0; q < 9; ++q) R[q] = __ldg(rot + 9 * b + q);
-    rotate_scale(pts + 3 * i, R, scale, c);
-    long long out[4];
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const float mn = o2f(mm[6 * b + j]), mx = o2f(mm[6 * b + 3 + j]);
-      float v = __fsub_rn(c[j], mn);
-      double off = 0.0;
-      if (u) {
-        // numpy: full_scale - coords.max(0) - 0.001 stays float32 (python scalars are weak), the product with
-        // the float64 draws and the in-place += are float64, stored back as float32
-        float room = __fsub_rn(__fsub_rn((float)full_scale, __fsub_rn(mx, mn)), 0.001f);
-        room = room > 0.f ? room : 0.f;
-        off = (double)room * __ldg(u + 3 * b + j);
-        v = (float)((double)v + off);
-      }
-      if (i == __ldg(offs + b)) {  // the sample's first point records the sample's min / offset
-        min_value[3 * b + j] = mn;
-        offset[3 * b + j] = off;
-      }
-      const long long q = (long long)v;  // astype(int64): truncation
-      out[j] = q;
-      ok = ok && q >= 0 && q < full_scale;
-    }
-    out[3] = b;
-    reinterpret_cast<longlong2*>(coords)[2 * i] = make_longlong2(out[0], out[1]);
-    reinterpret_cast<longlong2*>(coords)[2 * i + 1] = make_longlong2(out[2], out[3]);
+    const int b = mm3d_sample_of(offs, B, i);
+    long long q[3];
+    const bool ok = mm3d_point_voxel(pts, offs, b, i, rot, scale, full_scale, u, mm, min_value, offset, q);
+    reinterpret_cast<longlong2*>(coords)[2 * i] = make_longlong2(q[0], q[1]);
+    reinterpret_cast<longlong2*>(coords)[2 * i + 1] = make_longlong2(q[2], (long long)b);
     keep[i] = ok ? 1 : 0;
   }
 }
 
 }  // namespace
+
+int mm3d_launch_minmax(const float* points, const int64_t* sample_offsets, int B, int64_t n, const float* rot, float scale,
+                       uint32_t* mm, cudaStream_t stream) {
+  MM3D_CUDA(mm3d_launch_pdl(k_init_minmax, dim3(1), dim3(256), 0, stream, mm, B));
+  MM3D_CUDA(mm3d_launch_pdl(k_minmax, dim3(mm3d_grid(n, 256)), dim3(256), 0, stream, points, sample_offsets, B, n, rot,
+                            scale, mm));
+  mm3d_count_launches(2);
+  return MM3D_OK;
+}
 
 extern "C" size_t mm3d_scale_points_workspace_bytes(int B) { return mm3d_align(sizeof(uint32_t) * 6 * (size_t)(B > 0 ? B : 1)); }
 
@@ -137,12 +92,11 @@ extern "C" int mm3d_scale_points(const float* points, const int64_t* sample_offs
   MM3D_REQUIRE(points && sample_offsets && rot && coords && keep && min_value && offset, MM3D_ERR_INVALID,
                "scale_points: null pointer");
   uint32_t* mm = (uint32_t*)ws;
-  MM3D_CUDA(mm3d_launch_pdl(k_init_minmax, dim3(1), dim3(256), 0, stream, mm, B));
-  MM3D_CUDA(mm3d_launch_pdl(k_minmax, dim3(mm3d_grid(n, 256)), dim3(256), 0, stream, points, sample_offsets, B, n, rot,
-                            scale, mm));
+  int rc = mm3d_launch_minmax(points, sample_offsets, B, n, rot, scale, mm, stream);
+  if (rc) return rc;
   MM3D_CUDA(mm3d_launch_pdl(k_coords, dim3(mm3d_grid(n, 256)), dim3(256), 0, stream, points, sample_offsets, B, n, rot,
                             scale, full_scale, transl_u, (const uint32_t*)mm, coords, keep, min_value, offset));
-  mm3d_count_launches(3);
+  mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_scale_points");
   return MM3D_OK;
 }

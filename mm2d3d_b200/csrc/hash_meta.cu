@@ -6,6 +6,7 @@
 // a prefix scan over the "I am the first occurrence" flags -- NOT atomic tickets -- so voxel
 // rows are bit-identical to SparseConvNet's `nActive++` order on every run.
 // Row counts stay on the device; the host only passes capacities.
+#include "augment.cuh"
 #include "common.cuh"
 
 namespace {
@@ -62,6 +63,38 @@ struct SrcCoords {
       xy.x &= 0xFFFF; xy.y &= 0xFFFF; zb.x &= 0xFFFF; zb.y &= 0x7FFF;
     }
     return mm3d_pack_key((uint64_t)xy.x, (uint64_t)xy.y, (uint64_t)zb.x, (uint64_t)zb.y);
+  }
+};
+
+// Raw float points (metres) as the item source: rotation, scaling, min-shift, random translation, cast and
+// receptive-field test of the reference's augment_and_scale_3d + loader filter (augment.cuh) are evaluated on the fly,
+// so the int64 [N, 4] coordinate tensor between the two never exists.  A point outside the receptive
+// field is what the reference drops before the collate: it raises MM3D_STATUS_DROPPED (the caller rebuilds from the
+// filtered points -- row numbering must not see it) and is held at a clamped coordinate so the build stays well formed.
+struct SrcPoints {
+  const float* pts;
+  const int64_t* offs;
+  int B;
+  const float* rot;
+  float scale;
+  int full_scale;
+  const double* u;
+  const uint32_t* mm;
+  uint8_t* keep;
+  float* min_value;
+  double* offset;
+  int32_t* status;
+  __device__ __forceinline__ uint64_t operator()(int64_t i) const {
+    const int b = mm3d_sample_of(offs, B, i);
+    long long q[3];
+    const bool ok = mm3d_point_voxel(pts, offs, b, i, rot, scale, full_scale, u, mm, min_value, offset, q);
+    keep[i] = ok ? 1 : 0;
+    if (!ok) {
+      atomicOr(status, MM3D_STATUS_DROPPED);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) q[j] = q[j] < 0 ? 0 : (q[j] >= full_scale ? full_scale - 1 : q[j]);
+    }
+    return mm3d_pack_key((uint64_t)q[0], (uint64_t)q[1], (uint64_t)q[2], (uint64_t)b);
   }
 };
 
@@ -312,6 +345,47 @@ extern "C" int mm3d_voxelize(const int64_t* coords, int64_t n_points, int spatia
   }
   mm3d_count_launches(n_points > 0 ? 7 : 2);
   MM3D_CHECK_LAUNCH("mm3d_voxelize");
+  return MM3D_OK;
+}
+
+extern "C" size_t mm3d_voxelize_points_workspace_bytes(int64_t n, int B) {
+  return unique_ws_bytes(n) + mm3d_align(sizeof(uint32_t) * 6 * (size_t)(B > 0 ? B : 1));
+}
+
+extern "C" int mm3d_voxelize_points(const float* points, const int64_t* sample_offsets, int B, int64_t n_points,
+                                    const float* rot, float scale, int full_scale, const double* transl_u,
+                                    uint8_t* keep, float* min_value, double* offset,
+                                    uint64_t* hash_keys, int32_t* hash_vals, int64_t hash_cap,
+                                    int32_t* p2v, uint64_t* vox_keys, int32_t* npts, int32_t* n_vox_dev,
+                                    int32_t* status_dev, void* ws, size_t ws_bytes, mm3d_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MM3D_REQUIRE(n_points >= 0 && n_points < (1ll << 30), MM3D_ERR_INVALID, "n_points out of range");
+  MM3D_REQUIRE(B > 0 && B <= 32768, MM3D_ERR_INVALID, "voxelize_points: B must be in (0, 32768]");
+  MM3D_REQUIRE(full_scale > 0 && full_scale <= 65536, MM3D_ERR_INVALID, "full_scale must be in (0, 65536]");
+  MM3D_REQUIRE(ws_bytes >= mm3d_voxelize_points_workspace_bytes(n_points, B), MM3D_ERR_WORKSPACE,
+               "voxelize_points: workspace too small");
+  MM3D_REQUIRE(n_points == 0 || (points && sample_offsets && rot && keep && min_value && offset), MM3D_ERR_INVALID,
+               "voxelize_points: null pointer");
+  UniqueWs w;
+  int rc = carve_ws(ws, ws_bytes, n_points, hash_cap, &w);
+  if (rc) return rc;
+  uint32_t* mm = (uint32_t*)((char*)ws + unique_ws_bytes(n_points));
+  int32_t* mask_dev = mask_slot(hash_vals, hash_cap);
+  MM3D_CUDA(mm3d_launch_pdl(k_setup, dim3(1), dim3(32), 0, stream, nullptr, n_points, hash_cap - 1, mask_dev, n_vox_dev, w.n_items));
+  MM3D_CUDA(mm3d_launch_pdl(k_clear, dim3(mm3d_grid(hash_cap, 256)), dim3(256), 0, stream, hash_keys, w.slot_min, mask_dev, w.n_items, npts, 1, 0, 0));
+  if (n_points > 0) {
+    rc = mm3d_launch_minmax(points, sample_offsets, B, n_points, rot, scale, mm, stream);
+    if (rc) return rc;
+    SrcPoints src{points, sample_offsets, B, rot, scale, full_scale, transl_u, mm, keep, min_value, offset, status_dev};
+    MM3D_CUDA(mm3d_launch_pdl(k_insert<SrcPoints>, dim3(mm3d_grid(n_points, 256)), dim3(256), 0, stream, src, w.n_items, hash_keys, w.slot_min, mask_dev, w.item_slot));
+    MM3D_CUDA(mm3d_launch_pdl(k_count, dim3(w.nblocks), dim3(kScanThreads), 0, stream, w.item_slot, w.slot_min, w.n_items, w.block_sums));
+    MM3D_CUDA(mm3d_launch_pdl(k_scan_blocks, dim3(1), dim3(kScanThreads), 0, stream, w.block_sums, w.nblocks, n_vox_dev));
+    MM3D_CUDA(mm3d_launch_pdl(k_assign, dim3(w.nblocks), dim3(kScanThreads), 0, stream, w.item_slot, w.slot_min, w.n_items, w.block_sums,
+                                                     hash_keys, hash_vals, vox_keys));
+    MM3D_CUDA(mm3d_launch_pdl(k_ids_level0, dim3(mm3d_grid(n_points, 256)), dim3(256), 0, stream, w.item_slot, hash_vals, w.n_items, p2v, npts));
+  }
+  mm3d_count_launches(n_points > 0 ? 7 : 2);
+  MM3D_CHECK_LAUNCH("mm3d_voxelize_points");
   return MM3D_OK;
 }
 

@@ -191,13 +191,36 @@ class PreparedScans:
     typically on a side stream while the previous step still computes, the way a prefetching data loader prepares
     the next batch.  Pass it to ``UNetSCN.forward`` in place of the coordinate tensor."""
 
-    __slots__ = ("meta", "event", "stream", "mode", "spatial0", "levels")
+    __slots__ = ("meta", "event", "stream", "mode", "spatial0", "levels", "points")
 
-    def __init__(self, meta, mode, spatial0, levels):
+    def __init__(self, meta, mode, spatial0, levels, points=None):
         self.meta, self.mode, self.spatial0, self.levels = meta, mode, spatial0, levels
+        self.points = points  # augment.PointStructure when the batch was prepared from raw float points
         self.stream = torch.cuda.current_stream(meta.device)
         self.event = torch.cuda.Event()
         self.event.record(self.stream)
+
+    def kept(self):
+        """Prepared from points (``UNetSCN.prepare_points``): ``None`` when every point lies inside the receptive
+        field, else the bool ``[N]`` mask of the points the reference's loader keeps -- features and labels passed
+        to the forward must be filtered with it.  Waits for the build's row counts (the build's one host sync)."""
+        if self.points is None:
+            return None
+        meta, keep = self.points.resolve()
+        if meta is not self.meta:  # rebuilt from the kept points, on the stream current at the time of this call
+            self.meta = meta
+            self.stream = torch.cuda.current_stream(meta.device)
+            self.event = torch.cuda.Event()
+            self.event.record(self.stream)
+        return keep
+
+    @property
+    def min_value(self):
+        return self.points.min_value
+
+    @property
+    def offset(self):
+        return self.points.offset
 
     @property
     def n_points(self):
@@ -218,6 +241,23 @@ def prepare(net, coords, wait=False):
         return PreparedScans(meta, F.DEFAULT_MODE, spatial0, L)
 
 
+def prepare_points(net, points, sample_offsets, rot, transl_u, scale, wait=False):
+    """:func:`prepare` from raw float points: the reference's ``augment_and_scale_3d`` + cast + filter fused into the
+    voxel-hash insert (``augment.voxelize_points``).  ``rot`` / ``transl_u`` are the host-side random draws
+    (``augment.draw_augmentation``).  The returned handle's :meth:`PreparedScans.kept` tells which points survive
+    (``None`` = all), ``.min_value`` / ``.offset`` are what ``augment_and_scale_3d`` returns beside the coordinates."""
+    from .augment import voxelize_points
+    spatial0 = int(net.layer1.spatial_size[0])
+    L = net._num_planes
+    ps = voxelize_points(points, sample_offsets, rot, transl_u, scale, spatial0, L, plans=F.DEFAULT_MODE != "fp32",
+                         defer_sync=not wait)
+    with torch.cuda.device(ps.meta.device):
+        prep = PreparedScans(ps.meta, F.DEFAULT_MODE, spatial0, L, points=ps)
+    if wait:
+        prep.kept()
+    return prep
+
+
 def run(net, coords, feats, rgb_mask=None):
     if not feats.is_cuda:
         raise RuntimeError("UNetSCN: features must be a CUDA tensor -- mm2d3d_b200 has no CPU path")
@@ -227,6 +267,7 @@ def run(net, coords, feats, rgb_mask=None):
         prep = coords
         if (prep.mode, prep.spatial0, prep.levels) != (F.DEFAULT_MODE, spatial0, L) or prep.meta.device != feats.device:
             raise ValueError("UNetSCN: the prepared structure was built for another network, device or convolution mode")
+        prep.kept()  # (prepared from points: settles which structure is used)
         meta = prep.meta.finish()
         cur = torch.cuda.current_stream(feats.device)
         if cur != prep.stream:

@@ -41,18 +41,32 @@ class Metadata:
     _side = {}  # per-device side stream for the neighbour tables
 
     def __init__(self, coords: torch.Tensor, spatial_size: int, prebuild_levels: int = 1, plans: bool = False,
-                 defer_sync: bool = False):
+                 defer_sync: bool = False, points=None):
         """``defer_sync``: enqueue the build and an asynchronous read-back of the row counts, but do not wait for
         them; :meth:`finish` (called by every accessor that needs a row count) does.  Lets a caller enqueue a build
-        on a side stream and keep launching other work."""
-        if coords.dim() != 2 or coords.shape[1] != 4:
-            raise ValueError("coords must be [N, 4] = (x, y, z, batch)")
-        if not coords.is_cuda:
-            coords = coords.cuda(non_blocking=True)
-        coords = coords.to(torch.int64).contiguous()
-        self.device = coords.device
+        on a side stream and keep launching other work.
+
+        ``points`` (with ``coords=None``): build level 0 from raw float points with ``mm3d_voxelize_points`` -- a
+        dict of device tensors ``points [N,3] f32, offsets [B+1] i64, rot [B,9] f32, u [B,3] f64 or None, keep [N] u8,
+        min_value [B,3] f32, offset [B,3] f64`` and the float ``scale`` (see ``augment.voxelize_points``).  If the
+        batch holds a point outside the receptive field :attr:`dropped` is set once the counts are known and the
+        structure must not be used."""
+        self.dropped = False
+        self._points = points  # (keeps the build's input tensors alive)
+        if points is not None:
+            if coords is not None:
+                raise ValueError("Metadata: pass coords or points, not both")
+            self.device = points["points"].device
+            self.n_points = int(points["points"].shape[0])
+        else:
+            if coords.dim() != 2 or coords.shape[1] != 4:
+                raise ValueError("coords must be [N, 4] = (x, y, z, batch)")
+            if not coords.is_cuda:
+                coords = coords.cuda(non_blocking=True)
+            coords = coords.to(torch.int64).contiguous()
+            self.device = coords.device
+            self.n_points = int(coords.shape[0])
         self._pending = None
-        self.n_points = int(coords.shape[0])
         self.spatial_size0 = int(spatial_size)
         self.levels: dict[int, Level] = {}
         self._order: list[Level] = []
@@ -67,7 +81,11 @@ class Metadata:
         with torch.cuda.device(self.device):
             stream = _lib.stream_ptr()
             self._counts = torch.zeros(self.MAX_LEVELS + 1, dtype=torch.int32, device=self.device)
-            ws_bytes = lib.mm3d_unique_workspace_bytes(n)
+            if points is not None:
+                B = int(points["offsets"].numel()) - 1
+                ws_bytes = lib.mm3d_voxelize_points_workspace_bytes(n, B)
+            else:
+                ws_bytes = lib.mm3d_unique_workspace_bytes(n)
             head = _al(4 * n) * 2 + _al(ws_bytes)
             per_level, lay = self._level_layout(n)
             self._buf = torch.empty(head + per_level * L, dtype=torch.uint8, device=self.device)
@@ -80,9 +98,19 @@ class Metadata:
                 self._order.append(lv)
             l0 = self._order[0]
             cp = self._counts.data_ptr()
-            check(lib.mm3d_voxelize(coords.data_ptr(), n, self.spatial_size0, l0.ptr(l0.o_hkeys), l0.ptr(l0.o_hvals),
-                                    l0.hcap, base + self._o_p2v, l0.ptr(l0.o_keys), base + self._o_npts,
-                                    cp, cp + 4 * self.MAX_LEVELS, self._ws[0], self._ws[1], stream), "mm3d_voxelize")
+            if points is not None:
+                q = points
+                check(lib.mm3d_voxelize_points(q["points"].data_ptr(), q["offsets"].data_ptr(), B, n, q["rot"].data_ptr(),
+                                               float(q["scale"]), self.spatial_size0,
+                                               None if q["u"] is None else q["u"].data_ptr(), q["keep"].data_ptr(),
+                                               q["min_value"].data_ptr(), q["offset"].data_ptr(), l0.ptr(l0.o_hkeys),
+                                               l0.ptr(l0.o_hvals), l0.hcap, base + self._o_p2v, l0.ptr(l0.o_keys),
+                                               base + self._o_npts, cp, cp + 4 * self.MAX_LEVELS, self._ws[0],
+                                               self._ws[1], stream), "mm3d_voxelize_points")
+            else:
+                check(lib.mm3d_voxelize(coords.data_ptr(), n, self.spatial_size0, l0.ptr(l0.o_hkeys), l0.ptr(l0.o_hvals),
+                                        l0.hcap, base + self._o_p2v, l0.ptr(l0.o_keys), base + self._o_npts,
+                                        cp, cp + 4 * self.MAX_LEVELS, self._ws[0], self._ws[1], stream), "mm3d_voxelize")
             # The level chain (coarsen l -> l+1) is a sequence of small latency-bound kernels; the 3^3 table of a
             # level only needs that level's hash, so it runs beside the chain on a second stream.
             main = torch.cuda.current_stream()
@@ -174,6 +202,8 @@ class Metadata:
             host = self._counts.cpu()  # the one host synchronisation of a build
         if int(host[self.MAX_LEVELS]) & _lib.STATUS_BAD_COORD:
             raise ValueError("InputLayer: coordinates must lie in [0, spatial_size) and batch index in [0, 32768)")
+        if int(host[self.MAX_LEVELS]) & _lib.STATUS_DROPPED:
+            self.dropped = True  # (a point outside the receptive field: the owner rebuilds from the kept points)
         for lv in self._order:
             if lv.n is None:
                 lv.n = int(host[lv.count_slot])

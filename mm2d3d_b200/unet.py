@@ -105,6 +105,16 @@ class UNetSCN(nn.Module):
             raise RuntimeError("UNetSCN.prepare needs the fused executor (native backend, fused=True)")
         return executor.prepare(self, coords, wait)
 
+    def prepare_points(self, points, sample_offsets, rot, transl_u, scale, wait=False):
+        """:meth:`prepare` from raw float points ``[N, 3]`` (metres, samples concatenated): the reference's
+        ``augment_and_scale_3d`` + integer cast + receptive-field filter (``lib/utils/augmentation_3d.py:83-158``,
+        ``nuscenes_dataloader.py:312-327``) evaluated inside the voxel-hash insert -- the int64 ``[N, 4]`` coordinate
+        tensor of the collate never exists.  See ``executor.prepare_points``."""
+        from . import executor
+        if not (self.fused and self._native and executor.fusable(self)):
+            raise RuntimeError("UNetSCN.prepare_points needs the fused executor (native backend, fused=True)")
+        return executor.prepare_points(self, points, sample_offsets, rot, transl_u, scale, wait)
+
     def forward(self, x, rgb_mask=None):
         """``x = [coords, feats]`` as in the reference.  ``rgb_mask``: an ``nn.Linear(in_channels, 1)`` (or its
         ``(weight, bias)``) -- the prologue of ``Net3DSeg.forward`` (``3d_net/model.py:46-48``,

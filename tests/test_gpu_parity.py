@@ -753,6 +753,118 @@ def test_scale_points_reference_fixture():
     assert np.array_equal(meta.p2v().cpu().numpy(), ref.p2v)
 
 
+def _same_structure(a, b, levels, spatial):
+    """Two Metadata objects hold bit-identical structures (point map, rows, tables of every level)."""
+    assert a.n_points == b.n_points and a.n_voxels == b.n_voxels
+    assert torch.equal(a.p2v(), b.p2v()) and torch.equal(a.npts(), b.npts())
+    s = spatial
+    for l in range(levels):
+        assert torch.equal(a.coords_at(s), b.coords_at(s))
+        assert torch.equal(a.nbr_table(s), b.nbr_table(s))
+        if l + 1 < levels:
+            for x, y in zip(a.down_tables(s), b.down_tables(s)):
+                assert torch.equal(x, y)
+        s //= 2
+
+
+def test_voxelize_points_matches_scale_then_voxelize():
+    """mm3d_voxelize_points (raw float points straight into the voxel hash) against the two-step path
+    it replaces, mm3d_scale_points -> coords[keep] -> mm3d_voxelize, itself pinned by the reference-produced fixture
+    above.  Integer work: every output is bit-exact -- point -> voxel map, voxel rows of all levels, 3^3 and 2^3
+    tables, min_value / offset by-products; and when points fall outside the receptive field (the small grid of the
+    fixture), the keep mask and the structure of the survivors."""
+    from mm2d3d_b200.augment import scale_points, voxelize_points
+    from mm2d3d_b200.metadata import Metadata
+    z = np.load(os.path.join(G, "augment_ref.npz"))
+    pts = torch.from_numpy(z["points"]).to(DEV)
+    offs = z["offsets"]
+    u = z["u"] * z["transl"][:, None]
+    for full_scale, transl_u, levels in ((int(z["full_scale"]), u, 4), (int(z["small_full_scale"]), None, 3)):
+        coords, keep, mn, off = scale_points(pts, offs, z["rot"], transl_u, float(z["scale"]), full_scale)
+        ref = Metadata(coords[keep], full_scale, levels)
+        ps = voxelize_points(pts, offs, z["rot"], transl_u, float(z["scale"]), full_scale, prebuild_levels=levels)
+        meta, kept = ps.resolve()
+        if bool(keep.all()):
+            assert kept is None and not meta.dropped
+        else:
+            assert kept is not None and torch.equal(kept, keep)
+        assert torch.equal(ps.min_value, mn) and torch.equal(ps.offset, off)
+        _same_structure(meta, ref, levels, full_scale)
+    assert not bool(keep.all()), "the fixture's small grid must drop points (exercises the rebuild)"
+    # full nuScenes-shaped batch, all 7 levels, deferred synchronisation, with and without augmentation
+    from mm2d3d_b200.augment import draw_augmentation
+    scans = [synth.raycast_points("nuscenes", seed) for seed in range(3)]
+    offs = np.concatenate([[0], np.cumsum([len(p) for p in scans])]).astype(np.int64)
+    pts = torch.from_numpy(np.concatenate(scans, 0)).to(DEV)
+    rng = np.random.RandomState(7)
+    draws = [draw_augmentation(noisy_rot=0.03, flip_y=0.5, rot_z=6.2831, transl=True, rng=rng) for _ in scans]
+    for rot, tu in ((np.stack([np.eye(3, dtype=np.float32)] * 3), None),
+                    (np.stack([d[0] for d in draws]), np.stack([d[1] for d in draws]))):
+        coords, keep, mn, off = scale_points(pts, offs, rot, tu, 20.0, 4096)
+        assert bool(keep.all())
+        ref = Metadata(coords, 4096, 7)
+        ps = voxelize_points(pts, offs, rot, tu, 20.0, 4096, prebuild_levels=7, plans=True, defer_sync=True)
+        meta, kept = ps.resolve()
+        assert kept is None
+        assert torch.equal(ps.min_value, mn) and torch.equal(ps.offset, off)
+        _same_structure(meta, ref, 7, 4096)
+        if tu is None:  # without augmentation: the synthetic generator's own (float64, numpy) transform
+            want = np.concatenate([np.concatenate([synth.scan_coords("nuscenes", s), np.full((len(scans[s]), 1), s)], 1)
+                                   for s in range(3)])
+            differ = (np.abs(coords.cpu().numpy() - want).max(1) > 0).mean()
+            assert differ < 5e-3, differ  # (float32 vs float64 arithmetic at integer boundaries)
+    _no_device_error()
+
+
+def test_unetscn_prepare_points_equals_coordinate_input():
+    """UNetSCN.prepare_points(raw points) -> forward([prepared, feats]) equals forward([coords, feats]) with the
+    coordinates of the two-step path: same structure bits, same kernels (FP32 mode: only the float atomics of the
+    InputLayer's duplicate points differ in order; TF32 mode: rounding amplifies that, bars as in
+    test_fused_executor_matches_module_path)."""
+    from mm2d3d_b200 import scn as scn_mod
+    from mm2d3d_b200.augment import scale_points
+    from mm2d3d_b200.unet import UNetSCN
+    torch.manual_seed(11)
+    net = UNetSCN(in_channels=3, m=16, num_planes=5, full_scale=4096).to(DEV)
+    scans = [synth.raycast_points("nuscenes", seed) for seed in (5, 6)]
+    offs = np.concatenate([[0], np.cumsum([len(p) for p in scans])]).astype(np.int64)
+    pts = torch.from_numpy(np.concatenate(scans, 0)).to(DEV)
+    rot = np.stack([np.eye(3, dtype=np.float32)] * 2)
+    feats = torch.rand(pts.shape[0], 3, device=DEV)
+    coords, keep, _, _ = scale_points(pts, offs, rot, None, 20.0, 4096)
+    assert bool(keep.all())
+    try:
+        for mode, tol_out, tol_grad in (("fp32", 1e-5, 1e-4), ("tf32", 1e-3, 2e-2)):
+            scn_mod.set_conv_mode(mode)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                prep = net.prepare_points(pts, offs, rot, None, 20.0)
+            assert prep.kept() is None
+            outs = []
+            for x0 in (prep, coords):
+                x = feats.clone().requires_grad_(True)
+                out = net([x0, x])
+                (g,) = torch.autograd.grad(out.square().sum(), x)
+                outs.append((out.detach(), g))
+            assert rel_err(outs[0][0], outs[1][0]) < tol_out, mode
+            assert rel_l2(outs[0][1], outs[1][1]) < tol_grad, mode
+        scn_mod.set_conv_mode("fp32")
+        # a receptive field the scans do not fit into: the handle reports the survivors and serves the rebuilt structure
+        small = UNetSCN(in_channels=3, m=16, num_planes=3, full_scale=1024).to(DEV)
+        prep = small.prepare_points(pts, offs, rot, None, 20.0)
+        k = prep.kept()
+        c2, keep2, _, _ = scale_points(pts, offs, rot, None, 20.0, 1024)
+        assert k is not None and torch.equal(k, keep2) and 0 < int(k.sum()) < len(k)
+        with torch.no_grad():
+            a = small([prep, feats[k]])
+            b = small([c2[keep2], feats[keep2]])
+        assert rel_err(a, b) < 1e-5
+    finally:
+        scn_mod.set_conv_mode("fp32")
+    _no_device_error()
+
+
 @pytest.mark.parametrize("sizes", [[4000, 3000], [0, 17], [1], [20000, 20000, 1, 0]])
 def test_rasterize_points_matches_numpy_assignment(sizes):
     """Sparse depth / 2D label maps (nuscenes_dataloader.py:274-278): bit-exact, including which of several points on one
