@@ -830,9 +830,11 @@ def test_unetscn_prepare_points_equals_coordinate_input():
     offs = np.concatenate([[0], np.cumsum([len(p) for p in scans])]).astype(np.int64)
     pts = torch.from_numpy(np.concatenate(scans, 0)).to(DEV)
     rot = np.stack([np.eye(3, dtype=np.float32)] * 2)
-    feats = torch.rand(pts.shape[0], 3, device=DEV)
     coords, keep, _, _ = scale_points(pts, offs, rot, None, 20.0, 4096)
     assert bool(keep.all())
+    # features are a function of the voxel: the InputLayer's float atomics then add equal values, whose sum does not
+    # depend on their order -- the data path is reproducible and the two runs can be held to tight bars
+    feats = ((coords[:, :3].double() * torch.tensor([0.37, 0.11, 0.73], dtype=torch.float64, device=DEV)) % 1.0).float()
     try:
         for mode, tol_out, tol_grad in (("fp32", 1e-5, 1e-4), ("tf32", 1e-3, 2e-2)):
             scn_mod.set_conv_mode(mode)
@@ -847,8 +849,9 @@ def test_unetscn_prepare_points_equals_coordinate_input():
                 out = net([x0, x])
                 (g,) = torch.autograd.grad(out.square().sum(), x)
                 outs.append((out.detach(), g))
-            assert rel_err(outs[0][0], outs[1][0]) < tol_out, mode
-            assert rel_l2(outs[0][1], outs[1][1]) < tol_grad, mode
+            e_out, e_grad = rel_err(outs[0][0], outs[1][0]), rel_l2(outs[0][1], outs[1][1])
+            print(f"\n[prepare_points vs coordinates, {mode}] forward max-abs-rel {e_out:.2e}, d_feats rel-L2 {e_grad:.2e}")
+            assert e_out < tol_out and e_grad < tol_grad, (mode, e_out, e_grad)
         scn_mod.set_conv_mode("fp32")
         # a receptive field the scans do not fit into: the handle reports the survivors and serves the rebuilt structure
         small = UNetSCN(in_channels=3, m=16, num_planes=3, full_scale=1024).to(DEV)
