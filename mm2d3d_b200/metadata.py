@@ -59,6 +59,8 @@ class Metadata:
             self.device = points["points"].device
             self.n_points = int(points["points"].shape[0])
         else:
+            if not isinstance(coords, torch.Tensor):
+                raise TypeError("Metadata: coords must be a tensor [N, 4] = (x, y, z, batch)")
             if coords.dim() != 2 or coords.shape[1] != 4:
                 raise ValueError("coords must be [N, 4] = (x, y, z, batch)")
             if not coords.is_cuda:

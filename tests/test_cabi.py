@@ -35,6 +35,8 @@ def test_python_binding_covers_header():
     assert _lib.lib.mm3d_hash_capacity(1000) >= 2000
     assert _lib.lib.mm3d_unique_workspace_bytes(1000) > 4000
     assert _lib.lib.mm3d_bnrelu_workspace_bytes(16) >= 256
+    # the fused points -> voxel-hash build needs the unique workspace plus the per-sample min / max words
+    assert _lib.lib.mm3d_voxelize_points_workspace_bytes(1000, 8) >= _lib.lib.mm3d_unique_workspace_bytes(1000) + 6 * 4 * 8
 
 
 def test_sm100a_code_is_embedded():
