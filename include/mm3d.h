@@ -253,6 +253,16 @@ MM3D_API int mm3d_lift2d_fwd(const void* fmap, int dtype, int B, int C, int H, i
                     int64_t sw, const int64_t* idx, const int64_t* sample_offsets, int64_t n, void* out, mm3d_stream_t stream);
 MM3D_API int mm3d_lift2d_bwd(const void* d_out, int dtype, int B, int C, int H, int W, int64_t sb, int64_t sc, int64_t sh,
                     int64_t sw, const int64_t* idx, const int64_t* sample_offsets, int64_t n, void* d_fmap, mm3d_stream_t stream);
+/* Bilinear variant -- an extension, the reference only gathers at integer pixels (2d_net/model.py:131-137): uv float32
+ * [n,2] = (row, col) in pixel units, pixel centres at the integers; out[n,:] = the blend of the four neighbouring pixels,
+ * a neighbour outside the map contributing zero (torch.nn.functional.grid_sample, mode "bilinear", padding_mode "zeros",
+ * align_corners=True, on the normalised coordinates).  Backward: gradient of the map only (the coordinates are data). */
+MM3D_API int mm3d_lift2d_bilinear_fwd(const void* fmap, int dtype, int B, int C, int H, int W, int64_t sb, int64_t sc,
+                             int64_t sh, int64_t sw, const float* uv, const int64_t* sample_offsets, int64_t n, void* out,
+                             mm3d_stream_t stream);
+MM3D_API int mm3d_lift2d_bilinear_bwd(const void* d_out, int dtype, int B, int C, int H, int W, int64_t sb, int64_t sc,
+                             int64_t sh, int64_t sw, const float* uv, const int64_t* sample_offsets, int64_t n, void* d_fmap,
+                             mm3d_stream_t stream);
 
 /* Point values -> image (the loaders' sparse depth and 2D label maps, lib/dataset/nuscenes_dataloader.py:275-278):
  * out[b, idx[i,0], idx[i,1]] = vals[i] over a map pre-filled with `fill`; where several points share a pixel the

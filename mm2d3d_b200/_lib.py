@@ -71,6 +71,8 @@ SIGNATURES = {
     "mm3d_bnrelu_bwd": (_i, [_p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _f, _i, _p, _sz, _p]),
     "mm3d_lift2d_fwd": (_i, [_p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _i64, _p, _p]),
     "mm3d_lift2d_bwd": (_i, [_p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _i64, _p, _p]),
+    "mm3d_lift2d_bilinear_fwd": (_i, [_p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _i64, _p, _p]),
+    "mm3d_lift2d_bilinear_bwd": (_i, [_p, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _i64, _p, _p]),
     "mm3d_raster2d_workspace_bytes": (_sz, [_i, _i, _i]),
     "mm3d_raster2d": (_i, [_p, _p, _i, _i, _i, _i64, _p, _f, _p, _p, _sz, _p]),
     "mm3d_rgb_mask_fwd": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p]),

@@ -294,6 +294,90 @@ k_lift_bwd(const T* __restrict__ d_out, int B, int C, int H, int W, int64_t sb, 
   }
 }
 
+// ---- bilinear variant (an extension: the reference only ever gathers at integer pixels).  uv = float32 (row, col) in
+// pixel units, pixel centres at the integers; the four neighbouring pixels are blended with the usual weights and a
+// neighbour outside the map contributes zero -- F.grid_sample(mode="bilinear", padding_mode="zeros",
+// align_corners=True) on the normalised coordinates.  Same thread layout as the integer gather; arithmetic in FP32.
+template <class T> __device__ __forceinline__ float lift_to_f32(T v) { return (float)v; }
+
+struct BilinearTaps {
+  int64_t off[4];  // element offset of the tap inside the sample's map (without the channel term)
+  float w[4];      // 0 for a tap outside the map
+};
+
+__device__ __forceinline__ BilinearTaps bilinear_taps(float r, float c, int H, int W, int64_t sh, int64_t sw) {
+  BilinearTaps t;
+  const float r0f = floorf(r), c0f = floorf(c);
+  const float fr = r - r0f, fc = c - c0f;
+  // (coordinates far outside the map: every tap is outside; clamp before the integer conversion)
+  const int r0 = (int)fminf(fmaxf(r0f, -2.f), (float)H), c0 = (int)fminf(fmaxf(c0f, -2.f), (float)W);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int rr = r0 + (q >> 1), cc = c0 + (q & 1);
+    const bool in = (unsigned)rr < (unsigned)H && (unsigned)cc < (unsigned)W;
+    const float w = ((q >> 1) ? fr : 1.f - fr) * ((q & 1) ? fc : 1.f - fc);
+    t.w[q] = in ? w : 0.f;
+    t.off[q] = in ? rr * sh + cc * sw : 0;
+  }
+  return t;
+}
+
+template <class T, int G>
+__global__ void __launch_bounds__(256)
+k_lift_bilinear_fwd(const T* __restrict__ fmap, int B, int C, int H, int W, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+                    const float* __restrict__ uv, const int64_t* __restrict__ offs, int64_t n, T* __restrict__ out, int* err) {
+  (void)err;
+  const int groups = C / G;
+  const int64_t total = n * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = total < (1ll << 31) ? (int64_t)((uint32_t)i / (uint32_t)groups) : i / groups;
+    const int ch0 = (int)(i - p * groups) * G;
+    const float2 rc = __ldg(reinterpret_cast<const float2*>(uv) + p);
+    const BilinearTaps t = bilinear_taps(rc.x, rc.y, H, W, sh, sw);
+    const T* base = fmap + find_sample(offs, B, p) * sb + ch0 * sc;
+    float acc[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (t.w[q] != 0.f) {
+#pragma unroll
+        for (int j = 0; j < G; ++j) acc[j] = fmaf(t.w[q], lift_to_f32(base[t.off[q] + j * sc]), acc[j]);
+      }
+    }
+    T* dst = out + p * C + ch0;
+#pragma unroll
+    for (int j = 0; j < G; ++j) dst[j] = T(acc[j]);
+  }
+}
+
+// backward with respect to the map (the projected coordinates are data: no gradient for uv)
+template <class T, int G>
+__global__ void __launch_bounds__(256)
+k_lift_bilinear_bwd(const T* __restrict__ d_out, int B, int C, int H, int W, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+                    const float* __restrict__ uv, const int64_t* __restrict__ offs, int64_t n, T* __restrict__ d_fmap, int* err) {
+  (void)err;
+  const int groups = C / G;
+  const int64_t total = n * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = total < (1ll << 31) ? (int64_t)((uint32_t)i / (uint32_t)groups) : i / groups;
+    const int ch0 = (int)(i - p * groups) * G;
+    const float2 rc = __ldg(reinterpret_cast<const float2*>(uv) + p);
+    const BilinearTaps t = bilinear_taps(rc.x, rc.y, H, W, sh, sw);
+    T* base = d_fmap + find_sample(offs, B, p) * sb + ch0 * sc;
+    float g[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) g[j] = lift_to_f32(d_out[p * C + ch0 + j]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (t.w[q] != 0.f) {
+#pragma unroll
+        for (int j = 0; j < G; ++j) lift_atomic_add(base + t.off[q] + j * sc, T(t.w[q] * g[j]));
+      }
+    }
+  }
+}
+
 // channels per thread: contiguous channels (sc == 1, channels-last) in groups of 4 or 2; one per thread for a
 // channel-major map, where neighbouring threads should walk neighbouring planes of one pixel
 #define LIFT_DISPATCH(KERNEL, T, ...)                                                                               \
@@ -457,6 +541,46 @@ extern "C" int mm3d_lift2d_bwd(const void* d_out, int dtype, int B, int C, int H
   }
   mm3d_count_launches(1);
   MM3D_CHECK_LAUNCH("mm3d_lift2d_bwd");
+  return MM3D_OK;
+}
+
+extern "C" int mm3d_lift2d_bilinear_fwd(const void* fmap, int dtype, int B, int C, int H, int W, int64_t sb, int64_t sc,
+                                        int64_t sh, int64_t sw, const float* uv, const int64_t* sample_offsets, int64_t n,
+                                        void* out, mm3d_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MM3D_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && n >= 0, MM3D_ERR_INVALID, "bad lift sizes");
+  MM3D_REQUIRE(sb > 0 && sc > 0 && sh > 0 && sw > 0, MM3D_ERR_INVALID, "bad lift strides");
+  if (n == 0) return MM3D_OK;
+  int* err = nullptr;
+  MM3D_REQUIRE(uv && (((uintptr_t)uv) & 7) == 0, MM3D_ERR_INVALID, "lift: the coordinate array must be 8-byte aligned");
+  switch (dtype) {
+    case 0: LIFT_DISPATCH(k_lift_bilinear_fwd, float, (const float*)fmap, B, C, H, W, sb, sc, sh, sw, uv, sample_offsets, n, (float*)out, err); break;
+    case 1: LIFT_DISPATCH(k_lift_bilinear_fwd, __half, (const __half*)fmap, B, C, H, W, sb, sc, sh, sw, uv, sample_offsets, n, (__half*)out, err); break;
+    case 2: LIFT_DISPATCH(k_lift_bilinear_fwd, __nv_bfloat16, (const __nv_bfloat16*)fmap, B, C, H, W, sb, sc, sh, sw, uv, sample_offsets, n, (__nv_bfloat16*)out, err); break;
+    default: MM3D_REQUIRE(false, MM3D_ERR_UNSUPPORTED, "lift dtype %d (0=f32,1=f16,2=bf16)", dtype);
+  }
+  mm3d_count_launches(1);
+  MM3D_CHECK_LAUNCH("mm3d_lift2d_bilinear_fwd");
+  return MM3D_OK;
+}
+
+extern "C" int mm3d_lift2d_bilinear_bwd(const void* d_out, int dtype, int B, int C, int H, int W, int64_t sb, int64_t sc,
+                                        int64_t sh, int64_t sw, const float* uv, const int64_t* sample_offsets, int64_t n,
+                                        void* d_fmap, mm3d_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MM3D_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && n >= 0, MM3D_ERR_INVALID, "bad lift sizes");
+  MM3D_REQUIRE(sb > 0 && sc > 0 && sh > 0 && sw > 0, MM3D_ERR_INVALID, "bad lift strides");
+  if (n == 0) return MM3D_OK;
+  int* err = nullptr;
+  MM3D_REQUIRE(uv && (((uintptr_t)uv) & 7) == 0, MM3D_ERR_INVALID, "lift: the coordinate array must be 8-byte aligned");
+  switch (dtype) {
+    case 0: LIFT_DISPATCH(k_lift_bilinear_bwd, float, (const float*)d_out, B, C, H, W, sb, sc, sh, sw, uv, sample_offsets, n, (float*)d_fmap, err); break;
+    case 1: LIFT_DISPATCH(k_lift_bilinear_bwd, __half, (const __half*)d_out, B, C, H, W, sb, sc, sh, sw, uv, sample_offsets, n, (__half*)d_fmap, err); break;
+    case 2: LIFT_DISPATCH(k_lift_bilinear_bwd, __nv_bfloat16, (const __nv_bfloat16*)d_out, B, C, H, W, sb, sc, sh, sw, uv, sample_offsets, n, (__nv_bfloat16*)d_fmap, err); break;
+    default: MM3D_REQUIRE(false, MM3D_ERR_UNSUPPORTED, "lift dtype %d (0=f32,1=f16,2=bf16)", dtype);
+  }
+  mm3d_count_launches(1);
+  MM3D_CHECK_LAUNCH("mm3d_lift2d_bilinear_bwd");
   return MM3D_OK;
 }
 

@@ -309,3 +309,37 @@ class Lift2DFn(torch.autograd.Function):
             check(lib.mm3d_lift2d_bwd(ptr(d_out), _LIFT_DTYPES[d_out.dtype], B, C, H, W, *d_fmap.stride(), ptr(idx), ptr(offsets),
                                       idx.shape[0], ptr(d_fmap), _lib.stream_ptr()), "mm3d_lift2d_bwd")
         return d_fmap, None, None
+
+
+class Lift2DBilinearFn(torch.autograd.Function):
+    """Bilinear lift (an extension of the reference's integer gather): ``uv`` float32 ``[N, 2]`` = (row, col)."""
+
+    @staticmethod
+    def forward(ctx, fmap, uv, offsets):
+        _require_cuda(fmap, "lift2d_bilinear")
+        if fmap.dtype not in _LIFT_DTYPES:
+            raise TypeError(f"lift2d_bilinear: unsupported dtype {fmap.dtype}")
+        fmap = _dense_map(fmap)
+        B, C, H, W = fmap.shape
+        n = uv.shape[0]
+        out = torch.empty(n, C, dtype=fmap.dtype, device=fmap.device)
+        with torch.cuda.device(fmap.device):
+            check(lib.mm3d_lift2d_bilinear_fwd(ptr(fmap), _LIFT_DTYPES[fmap.dtype], B, C, H, W, *fmap.stride(), ptr(uv),
+                                               ptr(offsets), n, ptr(out), _lib.stream_ptr()), "mm3d_lift2d_bilinear_fwd")
+        ctx.save_for_backward(uv, offsets)
+        ctx.shape = (B, C, H, W)
+        ctx.channels_last = not fmap.is_contiguous()
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        uv, offsets = ctx.saved_tensors
+        B, C, H, W = ctx.shape
+        d_out = d_out.contiguous()
+        d_fmap = torch.empty(B, C, H, W, dtype=d_out.dtype, device=d_out.device,
+                             memory_format=torch.channels_last if ctx.channels_last else torch.contiguous_format).zero_()
+        with torch.cuda.device(d_out.device):
+            check(lib.mm3d_lift2d_bilinear_bwd(ptr(d_out), _LIFT_DTYPES[d_out.dtype], B, C, H, W, *d_fmap.stride(), ptr(uv),
+                                               ptr(offsets), uv.shape[0], ptr(d_fmap), _lib.stream_ptr()),
+                  "mm3d_lift2d_bilinear_bwd")
+        return d_fmap, None, None

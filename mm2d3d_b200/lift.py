@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib  # noqa: F401  (raises when the library is missing)
-from .functional import Lift2DFn
+from .functional import Lift2DBilinearFn, Lift2DFn
 
 
 class LiftIndices:
@@ -56,6 +56,28 @@ def lift2d(fmap: torch.Tensor, img_indices) -> torch.Tensor:
         raise IndexError(f"lift2d: pixel index out of range for a {H}x{W} map "
                          f"(rows {img_indices.lo[0]}..{img_indices.hi[0]}, columns {img_indices.lo[1]}..{img_indices.hi[1]})")
     return Lift2DFn.apply(fmap, img_indices.idx, img_indices.offsets)
+
+
+def lift2d_bilinear(fmap: torch.Tensor, pixel_coords) -> torch.Tensor:
+    """Bilinear variant of :func:`lift2d` -- an extension: the reference only gathers at integer pixels.
+
+    ``pixel_coords``: one float array ``[N_i, 2]`` of (row, col) per sample, in pixel units with pixel centres at the
+    integers (the un-floored projection of the LiDAR points).  Returns ``[sum N_i, C]``: the blend of the four
+    neighbouring pixels, a neighbour outside the map contributing zero -- ``F.grid_sample(fmap[i:i+1], grid,
+    mode="bilinear", padding_mode="zeros", align_corners=True)`` on the normalised coordinates.  At integer coordinates
+    inside the map it equals :func:`lift2d`.  Differentiable with respect to the map."""
+    counts = [int(len(c)) for c in pixel_coords]
+    if len(counts) != fmap.shape[0]:
+        raise ValueError("lift2d_bilinear: one coordinate array per sample expected")
+    offs = np.zeros(len(counts) + 1, dtype=np.int64)
+    np.cumsum(counts, out=offs[1:])
+    if offs[-1] > 0:
+        cat = np.concatenate([np.asarray(c, dtype=np.float32).reshape(-1, 2) for c in pixel_coords], 0)
+    else:
+        cat = np.zeros((0, 2), dtype=np.float32)
+    uv = torch.from_numpy(np.ascontiguousarray(cat)).to(fmap.device, non_blocking=True)
+    offsets = torch.from_numpy(offs).to(fmap.device, non_blocking=True)
+    return Lift2DBilinearFn.apply(fmap, uv, offsets)
 
 
 def rasterize_points(img_indices, values, height: int, width: int, fill: float = 0.0) -> torch.Tensor:

@@ -18,3 +18,25 @@ def lift2d(fmap: torch.Tensor, img_indices) -> torch.Tensor:
         idx = torch.as_tensor(img_indices[i], dtype=torch.long)
         out.append(fmap.permute(0, 2, 3, 1)[i][idx[:, 0], idx[:, 1]])
     return torch.cat(out, 0)
+
+
+def lift2d_bilinear(fmap: torch.Tensor, pixel_coords) -> torch.Tensor:
+    """Bilinear variant -- NOT in the reference (which only gathers at integer pixels); the definition is torch's
+    ``F.grid_sample(mode="bilinear", padding_mode="zeros", align_corners=True)`` and ``tests/test_oracle.py`` pins this
+    explicit four-tap restatement to it.  ``pixel_coords[i]``: float ``[N_i, 2]`` (row, col), pixel centres at integers."""
+    B, C, H, W = fmap.shape
+    out = []
+    for i in range(B):
+        rc = torch.as_tensor(pixel_coords[i], dtype=torch.float32).reshape(-1, 2)
+        r0, c0 = torch.floor(rc[:, 0]), torch.floor(rc[:, 1])
+        fr, fc = rc[:, 0] - r0, rc[:, 1] - c0
+        acc = torch.zeros(rc.shape[0], C, dtype=torch.float32)
+        for dr in (0, 1):
+            for dc in (0, 1):
+                rr, cc = (r0 + dr).long(), (c0 + dc).long()
+                inside = (rr >= 0) & (rr < H) & (cc >= 0) & (cc < W)
+                w = (fr if dr else 1 - fr) * (fc if dc else 1 - fc) * inside
+                v = fmap[i].float()[:, rr.clamp(0, H - 1), cc.clamp(0, W - 1)].t()  # [N, C]
+                acc = acc + w[:, None] * v
+        out.append(acc.to(fmap.dtype))
+    return torch.cat(out, 0)

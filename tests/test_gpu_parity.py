@@ -400,6 +400,46 @@ def test_lift2d_benchmark_shape():
     assert rel_err(gb, ga) < 1e-6
 
 
+@pytest.mark.parametrize("dtype,channels_last", [(torch.float32, False), (torch.float32, True), (torch.bfloat16, True)])
+def test_lift2d_bilinear_matches_oracle_and_grid_sample(dtype, channels_last):
+    """Bilinear lift (an extension of the reference's integer gather; floating-point kernel, FP32 arithmetic): against
+    the four-tap oracle, which tests/test_oracle.py pins to F.grid_sample, and against torch's own CUDA grid_sample;
+    bar 1e-5 in FP32 (bf16: the output rounding, 1e-2).  Gradient of the map against autograd of the oracle."""
+    import torch.nn.functional as F
+    from mm2d3d_b200.lift import lift2d, lift2d_bilinear
+    torch.manual_seed(9)
+    B, C, H, W = 3, 8, 45, 80
+    fmap = torch.randn(B, C, H, W, device=DEV).to(dtype)
+    if channels_last:
+        fmap = fmap.contiguous(memory_format=torch.channels_last)
+    rng = np.random.default_rng(2)
+    coords = [np.stack([rng.uniform(-1.5, H + 0.5, n), rng.uniform(-1.5, W + 0.5, n)], 1).astype(np.float32) for n in (900, 0, 400)]
+    coords[0][:6] = [[0, 0], [H - 1, W - 1], [3, 4], [H - 1, 2.5], [-1, -1], [H, W]]
+    x = fmap.clone().requires_grad_(True)
+    out = lift2d_bilinear(x, coords)
+    xr = fmap.detach().cpu().float().contiguous().requires_grad_(True)
+    want = lift_oracle.lift2d_bilinear(xr, coords)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert out.dtype == dtype and rel_err(out, want) < tol
+    if dtype == torch.float32:
+        for i, rc in enumerate(coords):
+            if len(rc) == 0:
+                continue
+            rc = torch.from_numpy(rc).to(DEV)
+            grid = torch.stack([2 * rc[:, 1] / (W - 1) - 1, 2 * rc[:, 0] / (H - 1) - 1], 1)[None, :, None, :]
+            ref = F.grid_sample(fmap[i:i + 1], grid, mode="bilinear", padding_mode="zeros", align_corners=True)[0, :, :, 0].t()
+            lo = sum(len(c) for c in coords[:i])
+            assert rel_err(out[lo:lo + len(rc)], ref) < 1e-5
+    g = torch.randn(out.shape, device=DEV).to(dtype)
+    (gx,) = torch.autograd.grad(out, x, g)
+    (gr,) = torch.autograd.grad(want, xr, g.cpu().float())
+    assert gx.is_contiguous(memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    assert rel_err(gx, gr) < (1e-5 if dtype == torch.float32 else 3e-2)
+    # at integer pixels the blend degenerates to the reference's gather, bit for bit
+    ints = synth.make_img_indices([500, 0, 300], H, W, seed=5)
+    assert torch.equal(lift2d_bilinear(fmap, [a.astype(np.float32) for a in ints]), lift2d(fmap, ints))
+
+
 # ------------------------------------------------------------------------------ whole network
 def rel_l2(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()

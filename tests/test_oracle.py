@@ -227,3 +227,28 @@ def test_reference_scn_unet_runs_on_oracle_and_matches_our_builder():
     r2 = ref.UNetSCN(in_channels=3, m=8, block_reps=2, residual_blocks=True, num_planes=3)
     o2 = UNetSCN(in_channels=3, m=8, block_reps=2, residual_blocks=True, num_planes=3, backend=scn_cpu)
     assert list(r2.state_dict().keys()) == list(o2.state_dict().keys())
+
+
+def test_bilinear_lift_oracle_is_grid_sample():
+    """The bilinear lift has no counterpart in the reference; its oracle (explicit four taps, zero outside the map) is
+    pinned to torch's grid_sample (bilinear, zeros padding, align_corners=True) on CPU, including points on the border,
+    outside the map and at integer pixels (where it equals the reference's integer gather)."""
+    import torch.nn.functional as F
+    from oracle import lift_oracle
+    torch.manual_seed(0)
+    B, C, H, W = 3, 5, 9, 14
+    fmap = torch.randn(B, C, H, W)
+    rng = np.random.default_rng(0)
+    coords = [np.stack([rng.uniform(-1.5, H + 0.5, n), rng.uniform(-1.5, W + 0.5, n)], 1).astype(np.float32) for n in (40, 0, 25)]
+    coords[0][:6] = [[0, 0], [H - 1, W - 1], [3, 4], [H - 1, 2.5], [-1, -1], [H, W]]
+    got = lift_oracle.lift2d_bilinear(fmap, coords)
+    want = []
+    for i, rc in enumerate(coords):
+        rc = torch.from_numpy(rc)
+        grid = torch.stack([2 * rc[:, 1] / (W - 1) - 1, 2 * rc[:, 0] / (H - 1) - 1], 1)[None, :, None, :]  # (x, y)
+        want.append(F.grid_sample(fmap[i:i + 1], grid, mode="bilinear", padding_mode="zeros", align_corners=True)[0, :, :, 0].t())
+    want = torch.cat(want, 0)
+    assert got.shape == want.shape == (65, C)
+    assert (got - want).abs().max().item() < 1e-5
+    ints = [np.stack([rng.integers(0, H, 30), rng.integers(0, W, 30)], 1) for _ in range(B)]
+    assert torch.allclose(lift_oracle.lift2d_bilinear(fmap, [x.astype(np.float32) for x in ints]), lift_oracle.lift2d(fmap, ints))
