@@ -9,6 +9,7 @@
 // one fixed channel vector; per-thread FP32 partials are combined in FP64 (shared, then global
 // atomics into 2*C doubles), which makes var = E[x^2] - mean^2 safe.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -441,6 +442,13 @@ k_bn_bwd_fused(const float* __restrict__ x, const float* __restrict__ x_hi, int 
 // is capped at (CTAs per SM the occupancy API reports for this kernel and shared-memory size, at most 2) x (the
 // device's real SM count).  Kernels of other streams (the weight-gradient CTAs of the side stream) may delay a
 // CTA's start but never depend on this grid, so the barrier always completes; the wait is bounded anyway.
+// CTAs per SM the grid may count on.  MM3D_BN_PER_SM overrides it for A/B measurements (bench.py --ab).
+static int bn_per_sm_cap() {
+  const char* e = getenv("MM3D_BN_PER_SM");
+  const int v = e ? atoi(e) : 0;
+  return v >= 1 && v <= 8 ? v : 2;
+}
+
 template <typename Kernel>
 int bn_grid(Kernel kernel, int64_t n, int cv, size_t smem) {
   const int rows_pass = kThreads / cv;
@@ -457,9 +465,9 @@ int bn_grid(Kernel kernel, int64_t n, int cv, size_t smem) {
       (void)cudaGetLastError();
       per_sm = 1;
     }
-    if (per_sm > 2) per_sm = 2;
     if (smem <= kSmemBound) slot = per_sm;
   }
+  if (per_sm > bn_per_sm_cap()) per_sm = bn_per_sm_cap();
   const int64_t cap = (int64_t)mm3d_sm_count() * per_sm;
   return (int)(g < cap ? g : cap);
 }
